@@ -1,0 +1,217 @@
+"""CPU: the numpy oracle (oracle/laminr_oracle.py) against golden vectors produced by the unmodified reference
+(oracle/make_golden.py).  This is what pins the oracle; the GPU parity tests then compare CUDA against the oracle."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import laminr_oracle as O
+from tests._util import golden, net_params, relerr
+
+TOL = 2e-5  # float32 restatement vs float32 torch reference (different summation orders)
+
+
+@pytest.mark.parametrize("name,res", [("inr_12x10", (12, 10)), ("inr_9x16_c2", (9, 16))])
+def test_inr_forward_backward(name, res):
+    d = golden(name)
+    W, b = net_params(d)
+    # torch.linspace vectorises (base + step*lane), so the scalar restatement may differ by 1 ulp; coords are an INPUT
+    # of the kernels (the product builds the buffer with torch.linspace exactly like inr.py:194-198)
+    np.testing.assert_allclose(O.pixel_coords(res), d["coords"], rtol=0, atol=6e-8)
+    img, cache = O.inr_forward(W, b, d["B"], d["auxB"], d["grid"], d["coords"][None], res, keep=True)
+    assert relerr(img[0], d["out"]) < TOL
+    g = O.inr_backward(W, d["B"], cache, d["upstream"][None])
+    for l in range(5):
+        assert relerr(g["dW"][l], d[f"dW{l}"]) < 5e-5, l
+        assert relerr(g["db"][l], d[f"db{l}"]) < 5e-5, l
+    # float64 restatement agrees too (tighter): rules out a same-precision coincidence
+    W64, b64 = [w.astype(np.float64) for w in W], [x.astype(np.float64) for x in b]
+    img64 = O.inr_forward(W64, b64, d["B"].astype(np.float64), d["auxB"].astype(np.float64), d["grid"].astype(np.float64),
+                          d["coords"][None].astype(np.float64), res)
+    assert relerr(img64[0], d["out"]) < TOL
+
+
+def test_match_coords_and_affine_grads():
+    d = golden("match_inr_14x14")
+    W, b = net_params(d)
+    res = (14, 14)
+    shift_to, tc, shift_from = O.coords_shifts(d["template_xy"], d["target_xy"], res)
+    np.testing.assert_allclose(shift_to, d["shift_to"], atol=1e-6)
+    np.testing.assert_allclose(tc, d["tc"], atol=1e-6)
+    np.testing.assert_allclose(shift_from, d["shift_from"], atol=1e-6)
+    M, _ = O.affine_matrices(d["angles"], d["scalings"], d["shears"])
+    cdp = O.match_coords(d["coords"], M, d["translation"], tc, shift_to, shift_from)
+    np.testing.assert_allclose(cdp, d["coords_transformed"], atol=2e-6)
+    assert (np.abs(cdp) == 1).any(), "fixture should exercise the clamp"
+    img, cache = O.inr_forward(W, b, d["B"], d["auxB"], d["grid"], cdp, res, keep=True)
+    assert relerr(img, d["out"]) < TOL
+    G = O.inr_backward(W, d["B"], cache, d["upstream"], want_weights=False, want_coords=True)["dcoords"]
+    da, ds, dsh, dt = O.affine_backward(G, d["coords"], tc, d["angles"], d["scalings"], d["shears"])
+    for got, key in ((da, "d_angles"), (ds, "d_scalings"), (dsh, "d_shears"), (dt, "d_translation")):
+        assert relerr(got, d[key]) < 2e-4, key
+
+
+def test_constrain():
+    d = golden("constrain")
+    y, c = O.constrain_norm_fwd(d["norm_x"], 3.0, 0.25, -0.5, 1.0)
+    assert relerr(y, d["norm_y"]) < 1e-6
+    assert relerr(O.constrain_norm_bwd(d["norm_up"], c, 3.0, -0.5, 1.0), d["norm_gx"]) < TOL
+    y, c = O.constrain_std_fwd(d["std_x"], 0.4, 0.25, -0.5, 1.0)
+    assert relerr(y, d["std_y"]) < 1e-6
+    assert relerr(O.constrain_std_bwd(d["std_up"], c, 0.4, -0.5, 1.0), d["std_gx"]) < TOL
+
+
+def test_simresp_and_banks():
+    d = golden("simresp")
+    for res in (16, 24):
+        banks = O.demo1_banks([res, res])
+        for i in range(3):
+            np.testing.assert_array_equal(banks[i], d[f"bank{i}_{res}"])  # bit-identical float32 banks
+        x = d[f"x_{res}"]
+        assert relerr(O.multi_resp_fwd(x, banks), d[f"y_{res}"]) < 1e-6
+        gx = np.zeros_like(x)
+        for i in range(3):
+            _, c = O.simresp_fwd(x, banks[i])
+            gx += O.simresp_bwd(d[f"up_{res}"][:, i], c, x.shape, banks[i])
+        assert relerr(gx, d[f"gx_{res}"]) < 1e-5
+    banks = O.demo1_banks([16, 16])
+    assert relerr(O.multi_resp_fwd(d["x_c2"], banks), d["y_c2"]) < 1e-6
+    gx = sum(O.simresp_bwd(np.ones(3, np.float32), O.simresp_fwd(d["x_c2"], f)[1], d["x_c2"].shape, f) for f in banks)
+    assert relerr(gx, d["gx_c2"]) < 1e-5
+
+
+def test_banks_full_resolution_hashes():
+    d = golden("banks")
+    for res in (100, 200):
+        for i, f in enumerate(O.demo1_banks([res, res])):
+            assert tuple(d[f"shape_{res}_{i}"]) == f.shape
+            assert hashlib.sha256(f.tobytes()).digest() == d[f"sha_{res}_{i}"].tobytes(), (res, i)
+    # known-answer: unit-norm filters
+    for f in O.demo1_banks([100, 100]):
+        np.testing.assert_allclose(np.linalg.norm(f.reshape(len(f), -1).astype(np.float64), axis=1), 1.0, atol=1e-6)
+
+
+def test_simclr():
+    d = golden("simclr")
+    for tag, n, periodic, nb in (("p20", 20, True, 0.1), ("np7", 7, False, 0.3), ("p10", 10, True, 0.1)):
+        pos, neg = O.pos_neg_masks(n, nb, periodic)
+        np.testing.assert_array_equal(pos, d[f"{tag}_pos"])
+        np.testing.assert_array_equal(neg, d[f"{tag}_neg"])
+        pmin, pmax = map(float, d[f"{tag}_pm"])
+        x, mask = d[f"{tag}_x"], d[f"{tag}_mask"]
+        xm = O.apply_mask(x, mask, pmin, pmax)
+        reg, c = O.simclr_reg_fwd(xm, pos, neg, 0.3)
+        assert abs(reg - d[f"{tag}_reg"]) < 1e-6 * max(1, abs(d[f"{tag}_reg"]))
+        gx = O.simclr_reg_bwd(c, pos, neg, 0.3).reshape(x.shape) * mask
+        assert relerr(gx, d[f"{tag}_gx"]) < 5e-5, tag
+    pos, neg = O.pos_neg_masks(20, 0.1, True)  # known-answer: 4 positives / 15 negatives per row
+    assert (pos.sum(1) == 4).all() and (neg.sum(1) == 15).all()
+
+
+def test_training_utils():
+    d = golden("training_utils")
+    for n in (20, 7, 32):
+        np.testing.assert_allclose(O.latent_grid(n), d[f"grid_{n}"], rtol=0, atol=5e-7)  # 1 ulp: torch.linspace vectorisation
+    np.testing.assert_allclose(O.jittered_grids(O.latent_grid(20), d["jitter_u01"], 2 * np.pi / 20), d["jitter_batches"], atol=5e-7)
+    sch = O.ParamReduceOnPlateau(factor=0.8, patience=5, threshold=0.005, mode="max")
+    val, vals = 2.0, []
+    for s in d["plateau_seq"]:
+        val = sch.step(s, val)
+        vals.append(val)
+    np.testing.assert_array_equal(np.array(vals), d["plateau_vals"])
+    chk = O.ImprovementChecker(patience=4, ignore_diff_smaller_than=1e-3)
+    np.testing.assert_array_equal(np.array([chk.is_increasing(float(s)) for s in d["plateau_seq"]]), d["improve_flags"])
+    req = dict(avg=0.99, std=1.0, necessary_min=0.98)
+    np.testing.assert_array_equal(np.array([O.check_activity_requirements(a, req) for a in d["req_acts"]]), d["req_pass"])
+    assert d["req_pass"].any() and not d["req_pass"].all()
+
+
+def test_adam():
+    d = golden("adam")
+    p, m, v = d["p0"], np.zeros_like(d["p0"]), np.zeros_like(d["p0"])
+    for i, g in enumerate(d["grads"]):
+        p, m, v = O.adam_step(p, g, m, v, i + 1)
+        np.testing.assert_allclose(p, d["ps"][i], rtol=0, atol=2e-7)
+
+
+def test_mei_ascent():
+    d = golden("mei")
+    banks = O.demo1_banks([16, 16])
+    for tag, kw in (("norm", dict(norm=1.0)), ("std", dict(std=0.1))):
+        for idx in range(3):
+            x, fevals = O.mei_ascent(d[f"{tag}_x0_{idx}"], banks[idx], 10, 60, -1.0, 1.0, **kw)
+            assert len(fevals) == 61  # known-answer: num_iterations + 1 (featurevis/core.py:122-126)
+            np.testing.assert_allclose(fevals, d[f"{tag}_fevals_{idx}"], rtol=2e-5)
+            assert relerr(x, d[f"{tag}_x_{idx}"]) < 1e-4, (tag, idx)
+
+
+@pytest.mark.parametrize("res", [20, 100])
+def test_learn_step(res):
+    d = golden(f"learn_step_{res}")
+    W, b = net_params(d)
+    pos, neg = O.pos_neg_masks(20, 0.1, True)
+    banks = O.demo1_banks([res, res])
+    out = O.learn_step(W, b, d["B"], d["auxB"], d["grid"], d["coords"], (res, res), banks[0], d["mask"], float(d["mei_act"]),
+                       2.0, 1.0, -1.0, 1.0, pos, neg, 0.3)
+    assert abs(out["loss"] - d["loss"]) < 1e-3 * abs(d["loss"])  # north-star tolerance ...
+    assert abs(out["loss"] - d["loss"]) < 2e-5 * abs(d["loss"])  # ... and what fp32 actually achieves
+    assert abs(out["sim"] - d["sim"]) < 2e-5 * abs(d["sim"])
+    assert relerr(out["acts"], d["acts"]) < 1e-5
+    sub = slice(None) if res == 20 else slice(None, None, 37)
+    assert relerr(out["img_pre"].reshape(20, -1)[:, sub], d["img_pre"]) < TOL
+    assert relerr(out["img_post"].reshape(20, -1)[:, sub], d["img_post"]) < TOL
+    for l in range(5):
+        assert relerr(out["dW"][l], d[f"dW{l}"]) < 2e-3, l  # gradients are small residuals; fp32 summation-order noise
+        assert relerr(out["db"][l], d[f"db{l}"]) < 2e-3, l
+
+
+def test_learn_step_grads_fp64_close():
+    """fp64 oracle vs the fp32 reference gradients: the fp32 restatement error above is rounding, not maths."""
+    d = golden("learn_step_20")
+    f64 = lambda a: np.asarray(a, np.float64)
+    W, b = net_params(d)
+    pos, neg = O.pos_neg_masks(20, 0.1, True, np.float64)
+    bank = f64(O.demo1_banks([20, 20])[0])
+    out = O.learn_step([f64(w) for w in W], [f64(x) for x in b], f64(d["B"]), f64(d["auxB"]), f64(d["grid"]), f64(d["coords"]),
+                       (20, 20), bank, f64(d["mask"]), float(d["mei_act"]), 2.0, 1.0, -1.0, 1.0, pos, neg, 0.3)
+    for l in range(5):
+        assert relerr(out["dW"][l], d[f"dW{l}"]) < 2e-3, l
+
+
+def test_match_step():
+    d = golden("match_step_20")
+    W, b = net_params(d)
+    res = (20, 20)
+    banks = O.demo1_banks(list(res))
+    shifts = O.coords_shifts(d["template_xy"], d["target_xy"], res)
+    aff = dict(angles=d["angles"], scalings=d["scalings"], shears=d["shears"], translation=d["translation"])
+    out = O.match_step(W, b, d["B"], d["auxB"], d["grid"], d["coords"], res, [banks[k] for k in d["targets"]],
+                       d["mei_acts"].astype(np.float32), aff, shifts, 1.0, -1.0, 1.0)
+    assert abs(out["loss"] - d["loss"]) < 2e-5 * abs(d["loss"])
+    assert relerr(out["acts_dn"], d["acts_dn"]) < 1e-5
+    assert relerr(out["img_pre"], d["img_pre"]) < TOL
+    assert relerr(out["img_post"], d["img_post"]) < TOL
+    for k in ("d_angles", "d_scalings", "d_shears", "d_translation"):
+        assert relerr(out[k], d[k]) < 1e-3, k
+
+
+def test_learn_trajectory():
+    """30 Adam steps replayed with the oracle: per-step loss within 1e-3 rel (north-star), final params close."""
+    d = golden("learn_traj_20")
+    W = [d[f"init_W{l}"] for l in range(5)]
+    b = [d[f"init_b{l}"] for l in range(5)]
+    mW, vW = [np.zeros_like(w) for w in W], [np.zeros_like(w) for w in W]
+    mb, vb = [np.zeros_like(x) for x in b], [np.zeros_like(x) for x in b]
+    pos, neg = O.pos_neg_masks(20, 0.1, True)
+    bank = O.demo1_banks([20, 20])[0]
+    grids = O.jittered_grids(O.latent_grid(20), d["jitter_u01"], 2 * np.pi / 20)
+    np.testing.assert_allclose(grids, d["grids"], atol=5e-7)
+    for i in range(30):
+        out = O.learn_step(W, b, d["init_B"], d["init_auxB"], d["grids"][i], d["init_coords"], (20, 20), bank, d["mask"],
+                           1.0000009536743164, 2.0, 1.0, -1.0, 1.0, pos, neg, 0.3)
+        assert abs(out["loss"] - d["losses"][i]) < 1e-3 * abs(d["losses"][i]), i
+        for l in range(5):
+            W[l], mW[l], vW[l] = O.adam_step(W[l], out["dW"][l], mW[l], vW[l], i + 1)
+            b[l], mb[l], vb[l] = O.adam_step(b[l], out["db"][l], mb[l], vb[l], i + 1)
+    for l in range(5):
+        assert relerr(W[l], d[f"final_W{l}"]) < 1e-2, l
