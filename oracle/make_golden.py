@@ -208,7 +208,7 @@ def case_training_utils(laminr):
     d["plateau_seq"], d["plateau_vals"] = seq, np.array(vals)
     chk = ImprovementChecker(patience=4, ignore_diff_smaller_than=1e-3)
     d["improve_flags"] = np.array([chk.is_increasing(float(s)) for s in seq])
-    acts = torch.tensor(rng.rand(8, 20).astype(np.float32) * np.linspace(0.005, 0.03, 8, dtype=np.float32)[:, None] + 0.979)
+    acts = torch.tensor(rng.rand(8, 20).astype(np.float32) * np.linspace(0.005, 0.03, 8, dtype=np.float32)[:, None] + np.linspace(0.979, 0.9895, 8, dtype=np.float32)[:, None])
     d["req_acts"] = npy(acts)
     d["req_pass"] = np.array([check_activity_requirements(a, dict(avg=0.99, std=1.0, necessary_min=0.98)) for a in acts])
     np.savez_compressed(os.path.join(OUT, "training_utils.npz"), **d)
