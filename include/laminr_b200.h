@@ -1,0 +1,174 @@
+/*
+ * laminr_b200 -- C ABI of the B200-native (sm_100a) LAMINR hot path.
+ *
+ * Drop-in boundary for the invariance-manifold optimisation loop of sinzlab/laminr v0.0.7.  The reference has no
+ * FFI of its own (it is pure PyTorch); each entry point below replaces the PyTorch op sequence of one reference
+ * callable, cited as `file:line` relative to the reference's `src/`.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous row-major float32 (or int32) unless marked "host";
+ *   - the caller (PyTorch's allocator) owns every buffer including workspaces (`*_workspace_bytes` queries);
+ *   - no allocation, no host synchronisation, no RNG inside: calls are stream-ordered and CUDA-graph capturable;
+ *   - return 0 on success, a negative lmr_status otherwise; `lmr_last_error()` gives a thread-local message;
+ *   - `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef LAMINR_B200_H
+#define LAMINR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LMR_ABI_VERSION 1
+
+typedef enum {
+    LMR_OK = 0,
+    LMR_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+    LMR_ERR_WORKSPACE = -2,   /* workspace too small */
+    LMR_ERR_CUDA = -3,        /* CUDA runtime error (message in lmr_last_error) */
+    LMR_ERR_NO_DEVICE = -4    /* not an sm_100 device */
+} lmr_status;
+
+/* arithmetic mode of the INR MLP hidden layers */
+typedef enum {
+    LMR_PREC_FP32 = 0,        /* CUDA-core fp32 FMA, tanhf: the bit-tight parity path */
+    LMR_PREC_TF32 = 1,        /* tcgen05 kind::tf32, fp32 accumulate in TMEM; layer 0 / output layer stay fp32 */
+    LMR_PREC_BF16X3 = 2       /* tcgen05 kind::f16 error-compensated split-bf16 (hi*hi + lo*hi + hi*lo) */
+} lmr_precision;
+
+typedef enum { LMR_CONSTRAIN_NORM = 0, LMR_CONSTRAIN_STD = 1 } lmr_constrain_mode;
+
+int lmr_abi_version(void);
+const char* lmr_last_error(void);
+/* 0 if the current device is sm_100 (B200); LMR_ERR_NO_DEVICE otherwise. */
+int lmr_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * INR generator  -- replaces INRTemplates.forward (laminr/inr.py:53-100) incl. transform_auxiliary_input
+ * (:371-386), apply_positional_encoding (:388-413), apply_coordinate_transform (:317-369) with
+ * CoordinateTransform(only_affine=True) / AffineTransform (laminr/coordinate_transforms.py:226-309,351-354),
+ * combine_multiple_tensors (:436-452, never materialised) and `func` (:156-174).
+ *
+ * Network: n_hidden layers Linear(+bias)+tanh of width `hidden`, then Linear(hidden, channels)+tanh.
+ * `params` is the concatenation of func.parameters() in module order, torch Linear layout [out,in]:
+ *     W0[hidden, 1+2*aux_pe+2*pe] b0[hidden]  W1[hidden,hidden] b1 ... W_L[channels,hidden] b_L[channels]
+ * Input column order of W0: [template(1) | sin,cos(aux.auxB) (2*aux_pe) | sin,cos(coords.B) (2*pe)].
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int hidden;      /* width of every hidden layer (supported: 50) */
+    int n_hidden;    /* number of hidden layers (2..8) */
+    int pe_dim;      /* positional_encoding_dim: B is [2, pe_dim] */
+    int aux_pe_dim;  /* aux_positional_encoding_dim: auxB is [2, aux_pe_dim] (periodic latent: [sin g, cos g]) */
+    int channels;    /* out_channels, 1..4 */
+} lmr_inr_desc;
+
+/* Per-target affine coordinate transform (match stage).  All NULL => learn stage (identity; D must be 1).
+ * M_d = R(angle_d) diag(scal_d) [[1,sh_d0],[sh_d1,1]];  c = clamp(M_d(c_p - tc) + t_d + tc + [M_d(shift_from_d + shift_to) + t_d])
+ * with a straight-through clamp and the bracket constant in the backward pass (inr.py:345-369).  */
+typedef struct {
+    const float* angles;       /* [D] */
+    const float* scalings;     /* [D, scal_cols] */
+    int scal_cols;             /* 2, or 1 for uniform_scale */
+    const float* shears;       /* [D,2] */
+    const float* translation;  /* [D,2] (the reference's [D,1,2]) */
+    const float* tc;           /* [2] template_center_in_coords_space (y,x); NULL => 0 */
+    const float* shift_to;     /* [2] coords_shift_to_center; NULL => 0 */
+    const float* shift_from;   /* [D,2] coords_shift_from_center; NULL => 0 */
+    int clamp;                 /* coordinate_transform_clamp_boundaries */
+} lmr_affine;
+
+size_t lmr_inr_params_count(const lmr_inr_desc* desc);
+size_t lmr_inr_forward_workspace_bytes(const lmr_inr_desc* desc, int N, int P, int D);
+size_t lmr_inr_backward_workspace_bytes(const lmr_inr_desc* desc, int N, int P, int D);
+
+/* img[D,N,C,P] = INR(grid[N] latents, coords[P,2] (y,x) pixel coordinates).
+ * coord_shift: optional [2] added to coords (centralize_template, inr.py:329-335), learn stage only. */
+int lmr_inr_forward(const lmr_inr_desc* desc, const float* params, const float* B, const float* auxB,
+                    const float* grid, int N, const float* coords, int P, const float* coord_shift,
+                    const lmr_affine* affine, int D, float* img, void* workspace, size_t workspace_bytes,
+                    int precision, void* stream);
+
+/* Backward of lmr_inr_forward given g_img[D,N,C,P] (recomputes the forward per tile; stores no activations).
+ * g_params (nullable): gradient wrt `params`, same layout, overwritten.          [learn: Adam over template.func]
+ * g_angles[D], g_scalings[D,scal_cols], g_shears[D,2], g_translation[D,2] (nullable as a group), overwritten.
+ *                                                                       [match: Adam over coordinate_transform] */
+int lmr_inr_backward(const lmr_inr_desc* desc, const float* params, const float* B, const float* auxB,
+                     const float* grid, int N, const float* coords, int P, const float* coord_shift,
+                     const lmr_affine* affine, int D, const float* g_img, float* g_params, float* g_angles,
+                     float* g_scalings, float* g_shears, float* g_translation, void* workspace,
+                     size_t workspace_bytes, int precision, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Image-constraint projection -- replaces FixEnergyNormClip / StandardizeClip (laminr/utils/img_transforms.py:5-65)
+ * and, with eps = 1e-9, the non-differentiable ChangeNorm/ChangeStats + ClipRange (featurevis/ops.py:294-307,441-481).
+ *   NORM: y = (x-mean)/(||x-mean||+eps)*target + mean          STD: y = target*(x-mu)/(std_unbiased(x)+eps) + mean
+ *   z = clamp(y, pmin, pmax) (each bound optional)
+ * x,z: [B, n]; stats: [B,2] = (||x-mean|| or std, mu), consumed by the backward.
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t lmr_constrain_workspace_bytes(int B, int n);
+int lmr_constrain_fwd(int mode, const float* x, int B, int n, float target, float mean, int has_min, float pmin,
+                      int has_max, float pmax, float eps, float* z, float* stats, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int lmr_constrain_bwd(int mode, const float* x, const float* g_z, const float* stats, int B, int n, float target,
+                      float mean, int has_min, float pmin, int has_max, float pmax, float eps, float* g_x,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Simulated response model -- replaces ArbitraryNeuronModel / ArbitraryMultiNeuronModel.forward
+ * (laminr/neuron_models/utils/simulated_model.py:8-29) and SingleNeuronModel (laminr/utils/general.py:5-12).
+ *   r_f = sum_{c,p} img[c,p] w_f[p];  m = max_f r_f (first maximum);  act = (elu(m)+1)/2 + eps
+ * Work is organised in G groups: group g evaluates neuron `neuron_of_group[g]` on NB images starting at
+ * img + g*img_group_stride (stride 0: every group sees the same NB images = "all neurons on all images").
+ * filters: [n_neurons, Fmax, HW] (ragged banks padded by repeating a filter), nfilt[n_neurons] valid counts.
+ * Outputs act, rmax: [G,NB]; argmax: [G,NB] (int32).
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t lmr_simresp_workspace_bytes(int G, int NB, int Fmax, int HW);
+int lmr_simresp_fwd(const float* img, long long img_group_stride, int NB, int G, int C, int HW,
+                    const float* filters, int Fmax, const int* nfilt, const int* neuron_of_group, float eps,
+                    float* act, float* rmax, int* argmax, void* workspace, size_t workspace_bytes, void* stream);
+/* g_img (+)= sum over groups g_act[g,b] * 1/2 * elu'(rmax) * w_{argmax}; `accumulate` adds into g_img. */
+int lmr_simresp_bwd(const float* g_act, const float* rmax, const int* argmax, long long img_group_stride, int NB,
+                    int G, int C, int HW, const float* filters, int Fmax, const int* neuron_of_group, float* g_img,
+                    int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Masked contrastive objective -- replaces apply_mask (laminr/utils/mask.py:7-22) + SimCLROnGrid.reg_term
+ * (laminr/contrastive_loss.py:139-154) + cosine_similarity (laminr/utils/img_similarity_metrics.py:4-10).
+ * img: [N, C, HW]; mask: [HW] (broadcast over channels); pos/neg: [N,N] 0/1 neighbour masks.
+ * reg: [1];  K: [N,N] coefficients such that d reg/d img_i = mask * sum_j K_ij xm_j (consumed by the backward).
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t lmr_simclr_workspace_bytes(int N, int C, int HW);
+int lmr_simclr_fwd(const float* img, const float* mask, int N, int C, int HW, float pmin, float pmax,
+                   const float* pos, const float* neg, float temperature, float eps, float* reg, float* K,
+                   void* workspace, size_t workspace_bytes, void* stream);
+/* g_img (+)= g_reg[0] * scale * d reg/d img.  g_reg is a device scalar (the autograd upstream). */
+int lmr_simclr_bwd(const float* img, const float* mask, const float* K, const float* g_reg, float scale, int N,
+                   int C, int HW, float pmin, float pmax, float* g_img, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Adam -- torch.optim.Adam(lr, betas, eps) single-tensor update (used on template.func / coordinate_transform
+ * parameters, inv_temp_learn_match.py:162,335).  `step` is a device int32 holding the number of steps already
+ * taken; it is incremented by the call (graph-capturable).  One flat tensor per call.
+ * ---------------------------------------------------------------------------------------------------------- */
+int lmr_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int n, float lr, float beta1,
+                  float beta2, float eps, int* step, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * MEI gradient ascent -- replaces featurevis.gradient_ascent with SGD (featurevis/core.py:54-136) driven as in
+ * generate_mei (laminr/utils/mei.py:33-59), batched over G neurons (the reference loops neurons sequentially,
+ * mei.py:98-119):   x <- post(x + step_size * d act/dx),  post = ChangeNorm|ChangeStats -> ClipRange (eps 1e-9).
+ * x: [G,C,HW] in/out.  If apply_post_first, post() is applied once before the first evaluation (mei.py:42).
+ * fevals: [G, iters+1]: f before every step and once after the last (core.py:81-82,122-126).
+ * ---------------------------------------------------------------------------------------------------------- */
+int lmr_mei_ascent(float* x, int G, int C, int HW, const float* filters, int Fmax, const int* nfilt,
+                   const int* neuron_of_group, float step_size, int iters, int mode, float target, float mean,
+                   float pmin, float pmax, float act_eps, int apply_post_first, float* fevals, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAMINR_B200_H */

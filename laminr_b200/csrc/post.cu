@@ -1,0 +1,666 @@
+// Bandwidth-bound stages of the LAMINR hot path: image-constraint projection, simulated response model,
+// masked contrastive objective, Adam, batched MEI ascent.  All fp32, coalesced / vectorised, warp-shuffle
+// reductions, deterministic two-stage reductions (no float atomics).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace lmr {
+namespace post {
+
+// ===============================================================================================================
+// Image-constraint projection (reference laminr/utils/img_transforms.py:19-65; featurevis/ops.py:441-481)
+// ===============================================================================================================
+constexpr int CCH = 2048;  // elements per CTA chunk (256 threads x 8)
+
+// partial layout per (image b, chunk s): 4 floats
+//   fwd NORM: [sum (x-mean)^2]                 fwd STD: [count, chunk mean, chunk M2]
+//   bwd NORM: [sum gy*u]                       bwd STD: [sum gy, sum gy*(x-mu)]
+__global__ void __launch_bounds__(256) constrain_stats_kernel(int mode, const float* __restrict__ x, int n, float mean, float* __restrict__ part) {
+    __shared__ float scratch[40];
+    const int b = blockIdx.y, s = blockIdx.x, S = gridDim.x;
+    const float* xb = x + (size_t)b * n;
+    const int i0 = s * CCH, i1 = min(n, i0 + CCH);
+    float v[CCH / 256];
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < CCH / 256; ++q) {
+        const int i = i0 + q * 256 + threadIdx.x;
+        v[q] = i < i1 ? xb[i] : 0.f;
+        cnt += i < i1;
+    }
+    float* dst = part + ((size_t)b * S + s) * 4;
+    if (mode == LMR_CONSTRAIN_NORM) {
+        float acc = 0.f;
+#pragma unroll
+        for (int q = 0; q < CCH / 256; ++q) {
+            const int i = i0 + q * 256 + threadIdx.x;
+            const float u = v[q] - mean;
+            acc += i < i1 ? u * u : 0.f;
+        }
+        acc = block_sum(acc, scratch);
+        if (threadIdx.x == 0) dst[0] = acc;
+    } else {
+        float sum = 0.f;
+#pragma unroll
+        for (int q = 0; q < CCH / 256; ++q) sum += v[q];
+        sum = block_sum(sum, scratch);
+        const float m = sum / (float)(i1 - i0);
+        float m2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < CCH / 256; ++q) {
+            const int i = i0 + q * 256 + threadIdx.x;
+            const float u = v[q] - m;
+            m2 += i < i1 ? u * u : 0.f;
+        }
+        m2 = block_sum(m2, scratch);
+        if (threadIdx.x == 0) dst[0] = (float)(i1 - i0), dst[1] = m, dst[2] = m2;
+    }
+    (void)cnt;
+}
+
+// combine the S chunk partials of image b -> (s or std, mu).  Chan et al. pairwise update for the variance.
+__device__ inline void combine_stats(int mode, const float* part, int S, int n, float* out_s, float* out_mu) {
+    if (mode == LMR_CONSTRAIN_NORM) {
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += part[s * 4];
+        *out_s = sqrtf(acc);
+        *out_mu = 0.f;
+    } else {
+        float cnt = 0.f, m = 0.f, m2 = 0.f;
+        for (int s = 0; s < S; ++s) {
+            const float cb = part[s * 4], mb = part[s * 4 + 1], m2b = part[s * 4 + 2];
+            const float tot = cnt + cb, delta = mb - m;
+            m2 += m2b + delta * delta * cnt * cb / tot;
+            m += delta * cb / tot;
+            cnt = tot;
+        }
+        *out_s = sqrtf(m2 / (float)(n - 1));  // unbiased (Tensor.std default)
+        *out_mu = m;
+    }
+}
+
+__global__ void __launch_bounds__(256) constrain_apply_kernel(int mode, const float* __restrict__ x, int n, float target, float mean, int has_min,
+                                                              float pmin, int has_max, float pmax, float eps, const float* __restrict__ part,
+                                                              float* __restrict__ z, float* __restrict__ stats) {
+    __shared__ float sh[2];
+    const int b = blockIdx.y, s = blockIdx.x, S = gridDim.x;
+    if (threadIdx.x == 0) {
+        combine_stats(mode, part + (size_t)b * S * 4, S, n, &sh[0], &sh[1]);
+        if (s == 0) stats[2 * b] = sh[0], stats[2 * b + 1] = sh[1];
+    }
+    __syncthreads();
+    const float sd = sh[0], mu = sh[1];
+    const float* xb = x + (size_t)b * n;
+    float* zb = z + (size_t)b * n;
+    const int i0 = s * CCH, i1 = min(n, i0 + CCH);
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+        float y;
+        if (mode == LMR_CONSTRAIN_NORM) y = (xb[i] - mean) / (sd + eps) * target + mean;
+        else y = target * (xb[i] - mu) / (sd + eps) + mean;
+        if (has_min) y = fmaxf(y, pmin);
+        if (has_max) y = fminf(y, pmax);
+        zb[i] = y;
+    }
+}
+
+__device__ __forceinline__ float clamp_pass(float y, int has_min, float pmin, int has_max, float pmax) {
+    // torch.clamp backward passes the gradient where pmin <= y <= pmax (inclusive)
+    return ((!has_min || y >= pmin) && (!has_max || y <= pmax)) ? 1.f : 0.f;
+}
+
+__global__ void __launch_bounds__(256) constrain_bwd_stats_kernel(int mode, const float* __restrict__ x, const float* __restrict__ gz,
+                                                                  const float* __restrict__ stats, int n, float target, float mean, int has_min,
+                                                                  float pmin, int has_max, float pmax, float eps, float* __restrict__ part) {
+    __shared__ float scratch[40];
+    const int b = blockIdx.y, s = blockIdx.x, S = gridDim.x;
+    const float sd = stats[2 * b], mu = stats[2 * b + 1];
+    const float* xb = x + (size_t)b * n;
+    const float* gb = gz + (size_t)b * n;
+    const int i0 = s * CCH, i1 = min(n, i0 + CCH);
+    float a0 = 0.f, a1 = 0.f;
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+        float u, y;
+        if (mode == LMR_CONSTRAIN_NORM) u = xb[i] - mean, y = u / (sd + eps) * target + mean;
+        else u = xb[i] - mu, y = target * u / (sd + eps) + mean;
+        const float gy = gb[i] * clamp_pass(y, has_min, pmin, has_max, pmax);
+        a0 += gy;
+        a1 = fmaf(gy, u, a1);
+    }
+    a0 = block_sum(a0, scratch);
+    a1 = block_sum(a1, scratch);
+    if (threadIdx.x == 0) part[((size_t)b * S + s) * 4] = a0, part[((size_t)b * S + s) * 4 + 1] = a1;
+}
+
+__global__ void __launch_bounds__(256) constrain_bwd_apply_kernel(int mode, const float* __restrict__ x, const float* __restrict__ gz,
+                                                                  const float* __restrict__ stats, int n, float target, float mean, int has_min,
+                                                                  float pmin, int has_max, float pmax, float eps, const float* __restrict__ part,
+                                                                  float* __restrict__ gx) {
+    __shared__ float sh[2];
+    const int b = blockIdx.y, s = blockIdx.x, S = gridDim.x;
+    if (threadIdx.x == 0) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int q = 0; q < S; ++q) a0 += part[((size_t)b * S + q) * 4], a1 += part[((size_t)b * S + q) * 4 + 1];
+        sh[0] = a0, sh[1] = a1;
+    }
+    __syncthreads();
+    const float sd = stats[2 * b], mu = stats[2 * b + 1];
+    const float sum_gy = sh[0], dot = sh[1];
+    const float k = target / (sd + eps);
+    // NORM: gx = k gy - target dot / ((s+eps)^2 s) u ;  STD: gx = k (gy - mean(gy)) - target dot / ((sd+eps)^2 (n-1) sd) (x-mu)
+    const float denom = (sd + eps) * (sd + eps) * sd * (mode == LMR_CONSTRAIN_NORM ? 1.f : (float)(n - 1));
+    const float c2 = target * dot / denom;
+    const float gmean = mode == LMR_CONSTRAIN_NORM ? 0.f : sum_gy / (float)n;
+    const float* xb = x + (size_t)b * n;
+    const float* gb = gz + (size_t)b * n;
+    float* ob = gx + (size_t)b * n;
+    const int i0 = s * CCH, i1 = min(n, i0 + CCH);
+    for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+        float u, y;
+        if (mode == LMR_CONSTRAIN_NORM) u = xb[i] - mean, y = u / (sd + eps) * target + mean;
+        else u = xb[i] - mu, y = target * u / (sd + eps) + mean;
+        const float gy = gb[i] * clamp_pass(y, has_min, pmin, has_max, pmax);
+        ob[i] = k * (gy - gmean) - c2 * u;
+    }
+}
+
+// ===============================================================================================================
+// Simulated response model (reference laminr/neuron_models/utils/simulated_model.py:8-29)
+// ===============================================================================================================
+constexpr int RCH = 512;  // pixels per CTA chunk
+constexpr int RIB = 8;    // images per register block
+
+// Rpart[g][s][b][f] = sum_{p in chunk s} (sum_c img[g,b,c,p]) * w[f][p]
+__global__ void __launch_bounds__(256) simresp_partial_kernel(const float* __restrict__ img, long long gstride, int NB, int C, int HW,
+                                                              const float* __restrict__ filters, int Fmax, const int* __restrict__ nfilt,
+                                                              const int* __restrict__ neuron_of_group, float* __restrict__ Rpart) {
+    __shared__ float xs[RIB][RCH];
+    const int s = blockIdx.x, S = gridDim.x, g = blockIdx.y;
+    const int neuron = neuron_of_group[g];
+    const int F = nfilt[neuron];
+    const float* bank = filters + (size_t)neuron * Fmax * HW;
+    const float* gimg = img + (size_t)g * gstride;
+    const int p0 = s * RCH, np = min(RCH, HW - p0);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* out = Rpart + ((size_t)g * S + s) * NB * Fmax;
+    for (int b0 = 0; b0 < NB; b0 += RIB) {
+        const int nb = min(RIB, NB - b0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < RIB * RCH; i += 256) {
+            const int bb = i / RCH, p = i % RCH;
+            float v = 0.f;
+            if (bb < nb && p < np) {
+                const float* src = gimg + ((size_t)(b0 + bb) * C) * HW + p0 + p;
+                for (int c = 0; c < C; ++c) v += src[(size_t)c * HW];
+            }
+            xs[bb][p] = v;
+        }
+        __syncthreads();
+        for (int f = warp; f < F; f += 8) {
+            const float* w = bank + (size_t)f * HW + p0;
+            float acc[RIB];
+#pragma unroll
+            for (int bb = 0; bb < RIB; ++bb) acc[bb] = 0.f;
+            for (int p = lane; p < np; p += 32) {
+                const float wv = __ldg(w + p);
+#pragma unroll
+                for (int bb = 0; bb < RIB; ++bb) acc[bb] = fmaf(xs[bb][p], wv, acc[bb]);
+            }
+#pragma unroll
+            for (int bb = 0; bb < RIB; ++bb) acc[bb] = warp_sum(acc[bb]);
+            if (lane == 0)
+                for (int bb = 0; bb < nb; ++bb) out[(size_t)(b0 + bb) * Fmax + f] = acc[bb];
+        }
+    }
+}
+
+__global__ void simresp_finalize_kernel(const float* __restrict__ Rpart, int S, int NB, int G, int Fmax, const int* __restrict__ nfilt,
+                                        const int* __restrict__ neuron_of_group, float eps, float* __restrict__ act, float* __restrict__ rmax,
+                                        int* __restrict__ argmax) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= G * NB) return;
+    const int g = i / NB, b = i % NB;
+    const int F = nfilt[neuron_of_group[g]];
+    float best = -INFINITY;
+    int bi = 0;
+    for (int f = 0; f < F; ++f) {
+        float r = 0.f;
+        for (int s = 0; s < S; ++s) r += Rpart[(((size_t)g * S + s) * NB + b) * Fmax + f];
+        if (r > best) best = r, bi = f;  // strict: first maximum wins (torch.max)
+    }
+    rmax[i] = best;
+    argmax[i] = bi;
+    const float e = best > 0.f ? best : expm1f(best);
+    act[i] = (e + 1.f) / 2.f + eps;
+}
+
+// g_img[g,b,c,p] (+)= g_act * 1/2 * elu'(m) * w_{f*}[p]
+__global__ void __launch_bounds__(256) simresp_bwd_kernel(const float* __restrict__ g_act, const float* __restrict__ rmax, const int* __restrict__ argmax,
+                                                          long long gstride, int NB, int G, int C, int HW, const float* __restrict__ filters, int Fmax,
+                                                          const int* __restrict__ neuron_of_group, float* __restrict__ g_img, int accumulate) {
+    const int b = blockIdx.y;
+    const int gout = blockIdx.z;  // == group when images are per-group; single slice when shared
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    float v = 0.f;
+    const int g_lo = gstride ? gout : 0, g_hi = gstride ? gout + 1 : G;
+    for (int g = g_lo; g < g_hi; ++g) {
+        const int i = g * NB + b;
+        const float m = rmax[i];
+        const float coef = g_act[i] * 0.5f * (m > 0.f ? 1.f : expf(m));
+        v = fmaf(coef, __ldg(filters + ((size_t)neuron_of_group[g] * Fmax + argmax[i]) * HW + p), v);
+    }
+    float* dst = g_img + (size_t)gout * gstride + ((size_t)b * C) * HW + p;
+    for (int c = 0; c < C; ++c) {
+        if (accumulate) dst[(size_t)c * HW] += v;
+        else dst[(size_t)c * HW] = v;
+    }
+}
+
+// ===============================================================================================================
+// Masked contrastive objective (reference laminr/utils/mask.py:7-22, laminr/contrastive_loss.py:139-154)
+// ===============================================================================================================
+constexpr int GCH = 256;   // elements per CTA chunk
+constexpr int GMAXN = 64;  // max grid points
+
+__device__ __forceinline__ float masked_value(float x, float m, float c0, float g1, float g2) {
+    // rescale(x, pmin, pmax, -1, 1) * mask, then rescale back (same op order as mask.py:7-22)
+    const float r = (x - c0) * g1 + 0.f;
+    return (r * m - 0.f) * g2 + c0;
+}
+
+// Gpart[s][i][j] = sum_{e in chunk s} xm_i[e] xm_j[e]
+__global__ void __launch_bounds__(256) simclr_gram_kernel(const float* __restrict__ img, const float* __restrict__ mask, int N, int C, int HW,
+                                                          float c0, float g1, float g2, float* __restrict__ Gpart) {
+    extern __shared__ float xm[];  // [N][GCH+1]
+    const int n = C * HW;
+    const int e0 = blockIdx.x * GCH, ne = min(GCH, n - e0);
+    for (int i = threadIdx.x; i < N * GCH; i += 256) {
+        const int r = i / GCH, e = i % GCH;
+        float v = 0.f;
+        if (e < ne) v = masked_value(img[(size_t)r * n + e0 + e], mask[(e0 + e) % HW], c0, g1, g2);
+        xm[r * (GCH + 1) + e] = v;
+    }
+    __syncthreads();
+    float* out = Gpart + (size_t)blockIdx.x * N * N;
+    for (int pr = threadIdx.x; pr < N * N; pr += 256) {
+        const int i = pr / N, j = pr % N;
+        if (j < i) continue;
+        const float* a = xm + i * (GCH + 1);
+        const float* b = xm + j * (GCH + 1);
+        float acc = 0.f;
+        for (int e = 0; e < GCH; ++e) acc = fmaf(a[e], b[e], acc);
+        out[i * N + j] = acc;
+        out[j * N + i] = acc;
+    }
+}
+
+// one CTA: reduce the gram, evaluate reg and the backward coefficient matrix K
+__global__ void __launch_bounds__(256) simclr_finalize_kernel(const float* __restrict__ Gpart, int S, int N, const float* __restrict__ pos,
+                                                              const float* __restrict__ neg, float T, float eps, float* __restrict__ reg,
+                                                              float* __restrict__ K) {
+    extern __shared__ float sm[];
+    float* cosm = sm;             // [N][N] cos, later Lambda
+    float* Sm = cosm + N * N;     // [N][N] exp(cos/T), later Gamma
+    float* rho = Sm + N * N;      // [N]
+    float* rowc = rho + N;        // [N][4]: a_pos, a_neg (row coefficients), log term, kappa
+    __shared__ float scratch[40];
+    for (int pr = threadIdx.x; pr < N * N; pr += 256) {
+        float acc = 0.f;
+        for (int s = 0; s < S; ++s) acc += Gpart[(size_t)s * N * N + pr];
+        cosm[pr] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += 256) rho[i] = sqrtf(cosm[i * N + i]);
+    __syncthreads();
+    for (int pr = threadIdx.x; pr < N * N; pr += 256) {
+        const int i = pr / N, j = pr % N;
+        const float c = cosm[pr] / (rho[i] * rho[j]);
+        cosm[pr] = c;
+        Sm[pr] = expf(c / T);
+    }
+    __syncthreads();
+    float logsum = 0.f;
+    for (int i = threadIdx.x; i < N; i += 256) {
+        float ps = 0.f, np_ = 0.f, ns = 0.f, nn = 0.f;
+        for (int j = 0; j < N; ++j) {
+            ps = fmaf(Sm[i * N + j], pos[i * N + j], ps), np_ += pos[i * N + j];
+            ns = fmaf(Sm[i * N + j], neg[i * N + j], ns), nn += neg[i * N + j];
+        }
+        const float num = (ps == 0.f ? 0.f : ps / np_) + eps;
+        const float den = (ns == 0.f ? 0.f : ns / nn) + eps;
+        logsum += logf(num / den);
+        rowc[i * 4 + 0] = ps == 0.f ? 0.f : (T / (2.f * N)) / (np_ * num);
+        rowc[i * 4 + 1] = ns == 0.f ? 0.f : (T / (2.f * N)) / (nn * den);
+    }
+    logsum = block_sum(logsum, scratch);
+    if (threadIdx.x == 0) reg[0] = logsum / (float)N * T / 2.f;
+    __syncthreads();
+    // Gamma_ij = A_ij S_ij / T
+    for (int pr = threadIdx.x; pr < N * N; pr += 256) {
+        const int i = pr / N;
+        Sm[pr] = (pos[pr] * rowc[i * 4] - neg[pr] * rowc[i * 4 + 1]) * Sm[pr] / T;
+    }
+    __syncthreads();
+    // kappa_i = sum_j Lambda_ij cos_ij, Lambda = Gamma + Gamma^T
+    for (int i = threadIdx.x; i < N; i += 256) {
+        float kap = 0.f;
+        for (int j = 0; j < N; ++j) kap = fmaf(Sm[i * N + j] + Sm[j * N + i], cosm[i * N + j], kap);
+        rowc[i * 4 + 3] = kap;
+    }
+    __syncthreads();
+    for (int pr = threadIdx.x; pr < N * N; pr += 256) {
+        const int i = pr / N, j = pr % N;
+        float k = (Sm[i * N + j] + Sm[j * N + i]) / (rho[i] * rho[j]);
+        if (i == j) k -= rowc[i * 4 + 3] / (rho[i] * rho[i]);
+        K[pr] = k;
+    }
+}
+
+// g_img[i][e] (+)= g_reg * scale * (g1 * mask * g2) * sum_j K_ij xm_j[e]
+__global__ void __launch_bounds__(128) simclr_bwd_kernel(const float* __restrict__ img, const float* __restrict__ mask, const float* __restrict__ K,
+                                                         const float* __restrict__ g_reg, float scale, int N, int C, int HW, float c0, float g1,
+                                                         float g2, float* __restrict__ g_img, int accumulate) {
+    extern __shared__ float Ks[];  // [N][N]
+    for (int i = threadIdx.x; i < N * N; i += blockDim.x) Ks[i] = K[i];
+    __syncthreads();
+    const int n = C * HW;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const float m = mask[e % HW];
+    float xm[GMAXN];
+    for (int j = 0; j < N; ++j) xm[j] = masked_value(img[(size_t)j * n + e], m, c0, g1, g2);
+    const float up = g_reg[0] * scale * (g1 * m * g2);
+    for (int i = 0; i < N; ++i) {
+        float acc = 0.f;
+        for (int j = 0; j < N; ++j) acc = fmaf(Ks[i * N + j], xm[j], acc);
+        const float v = up * acc;
+        if (accumulate) g_img[(size_t)i * n + e] += v;
+        else g_img[(size_t)i * n + e] = v;
+    }
+}
+
+// ===============================================================================================================
+// Adam (torch.optim.Adam single-tensor update order; reference inv_temp_learn_match.py:162,335)
+// ===============================================================================================================
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int n, float lr,
+                            float b1, float b2, float eps, const int* __restrict__ step) {
+    const int t = step[0] + 1;
+    const float bc1 = 1.f - powf(b1, (float)t);
+    const float bc2 = 1.f - powf(b2, (float)t);
+    const float step_size = lr / bc1;
+    const float bc2_sqrt = sqrtf(bc2);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = m[i] + (gi - m[i]) * (1.f - b1);  // lerp_
+        const float vi = v[i] * b2 + (1.f - b2) * gi * gi;  // mul_ + addcmul_
+        m[i] = mi, v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - step_size * (mi / denom);  // addcdiv_
+    }
+}
+__global__ void counter_inc_kernel(int* c) { c[0] += 1; }
+
+// ===============================================================================================================
+// Batched MEI gradient ascent (reference featurevis/core.py:54-136 with SGD, laminr/utils/mei.py:33-59)
+// One CTA per neuron; the image lives in shared memory for all iterations; filters stream from L2/HBM.
+// ===============================================================================================================
+constexpr int MEI_THREADS = 512;
+
+__device__ inline void mei_post(float* xs, int n, int mode, float target, float mean, float pmin, float pmax, float* scratch) {
+    // ChangeNorm / ChangeStats (eps 1e-9) then ClipRange
+    if (mode == LMR_CONSTRAIN_NORM) {
+        float acc = 0.f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float u = xs[i] - mean;
+            acc = fmaf(u, u, acc);
+        }
+        acc = block_sum(acc, scratch);
+        const float denom = sqrtf(acc) + 1e-9f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float y = (xs[i] - mean) / denom * target + mean;  // same op order as ops.py:479
+            xs[i] = fminf(fmaxf(y, pmin), pmax);
+        }
+    } else {
+        float sum = 0.f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sum += xs[i];
+        sum = block_sum(sum, scratch);
+        const float mu = sum / (float)n;
+        float m2 = 0.f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float u = xs[i] - mu;
+            m2 = fmaf(u, u, m2);
+        }
+        m2 = block_sum(m2, scratch);
+        const float sd = sqrtf(m2 / (float)(n - 1));
+        const float k = target / (sd + 1e-9f);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float y = (xs[i] - mu) * k + mean;
+            xs[i] = fminf(fmaxf(y, pmin), pmax);
+        }
+    }
+    __syncthreads();
+}
+
+// r[f] = sum_p (sum_c x[c][p]) w_f[p]; returns via rs[] (smem), one warp per filter
+__device__ inline void mei_dots(const float* xs, int C, int HW, const float* __restrict__ bank, int F, float* rs) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const bool vec = (HW % 4) == 0;
+    for (int f = warp; f < F; f += nw) {
+        const float* w = bank + (size_t)f * HW;
+        float acc = 0.f;
+        if (vec) {
+            const float4* w4 = reinterpret_cast<const float4*>(w);
+            for (int q = lane; q < HW / 4; q += 32) {
+                const float4 ww = __ldg(w4 + q);
+                float4 xv = reinterpret_cast<const float4*>(xs)[q];
+                for (int c = 1; c < C; ++c) {
+                    const float4 t = reinterpret_cast<const float4*>(xs + (size_t)c * HW)[q];
+                    xv.x += t.x, xv.y += t.y, xv.z += t.z, xv.w += t.w;
+                }
+                acc = fmaf(xv.x, ww.x, acc), acc = fmaf(xv.y, ww.y, acc), acc = fmaf(xv.z, ww.z, acc), acc = fmaf(xv.w, ww.w, acc);
+            }
+        } else {
+            for (int p = lane; p < HW; p += 32) {
+                float xv = xs[p];
+                for (int c = 1; c < C; ++c) xv += xs[(size_t)c * HW + p];
+                acc = fmaf(xv, __ldg(w + p), acc);
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) rs[f] = acc;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(MEI_THREADS) mei_kernel(float* __restrict__ x, int C, int HW, const float* __restrict__ filters, int Fmax,
+                                                          const int* __restrict__ nfilt, const int* __restrict__ neuron_of_group, float step_size,
+                                                          int iters, int mode, float target, float mean, float pmin, float pmax, float act_eps,
+                                                          int apply_post_first, float* __restrict__ fevals) {
+    extern __shared__ __align__(16) float xs[];  // [C*HW] + r[Fmax]
+    __shared__ float scratch[40];
+    __shared__ float sel[2];
+    const int g = blockIdx.x, n = C * HW;
+    const int neuron = neuron_of_group[g];
+    const int F = nfilt[neuron];
+    const float* bank = filters + (size_t)neuron * Fmax * HW;
+    float* rs = xs + ((n + 3) / 4 * 4);
+    float* xg = x + (size_t)g * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = xg[i];
+    __syncthreads();
+    if (apply_post_first) mei_post(xs, n, mode, target, mean, pmin, pmax, scratch);
+    for (int it = 0; it <= iters; ++it) {
+        mei_dots(xs, C, HW, bank, F, rs);
+        if (threadIdx.x == 0) {
+            float best = -INFINITY;
+            int bi = 0;
+            for (int f = 0; f < F; ++f)
+                if (rs[f] > best) best = rs[f], bi = f;
+            const float e = best > 0.f ? best : expm1f(best);
+            fevals[(size_t)g * (iters + 1) + it] = (e + 1.f) / 2.f + act_eps;
+            sel[0] = 0.5f * (best > 0.f ? 1.f : expf(best));
+            sel[1] = __int_as_float(bi);
+        }
+        __syncthreads();
+        if (it == iters) break;
+        const float coef = sel[0];
+        const float* w = bank + (size_t)__float_as_int(sel[1]) * HW;
+        // SGD on -f: x <- x - lr * (-(coef * w)) for every channel
+        for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = xs[i] + step_size * (coef * __ldg(w + i % HW));
+        __syncthreads();
+        mei_post(xs, n, mode, target, mean, pmin, pmax, scratch);
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) xg[i] = xs[i];
+}
+
+}  // namespace post
+}  // namespace lmr
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+using namespace lmr;
+using namespace lmr::post;
+
+extern "C" size_t lmr_constrain_workspace_bytes(int B, int n) {
+    const int S = (n + CCH - 1) / CCH;
+    return (size_t)B * S * 4 * sizeof(float);
+}
+
+extern "C" int lmr_constrain_fwd(int mode, const float* x, int B, int n, float target, float mean, int has_min, float pmin, int has_max,
+                                 float pmax, float eps, float* z, float* stats, void* ws, size_t ws_bytes, void* stream) {
+    LMR_CHECK_ARG(mode == LMR_CONSTRAIN_NORM || mode == LMR_CONSTRAIN_STD, "constrain: bad mode %d", mode);
+    LMR_CHECK_ARG(B >= 1 && n >= 2, "constrain: bad sizes B=%d n=%d", B, n);
+    if (ws_bytes < lmr_constrain_workspace_bytes(B, n)) {
+        set_error("constrain_fwd: workspace too small");
+        return LMR_ERR_WORKSPACE;
+    }
+    const int S = (n + CCH - 1) / CCH;
+    LMR_CHECK_ARG(B <= 65535, "constrain: B=%d > 65535", B);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid(S, B);
+    constrain_stats_kernel<<<grid, 256, 0, st>>>(mode, x, n, mean, static_cast<float*>(ws));
+    LMR_LAUNCH_OK();
+    constrain_apply_kernel<<<grid, 256, 0, st>>>(mode, x, n, target, mean, has_min, pmin, has_max, pmax, eps, static_cast<const float*>(ws), z, stats);
+    LMR_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int lmr_constrain_bwd(int mode, const float* x, const float* g_z, const float* stats, int B, int n, float target, float mean,
+                                 int has_min, float pmin, int has_max, float pmax, float eps, float* g_x, void* ws, size_t ws_bytes,
+                                 void* stream) {
+    LMR_CHECK_ARG(mode == LMR_CONSTRAIN_NORM || mode == LMR_CONSTRAIN_STD, "constrain: bad mode %d", mode);
+    LMR_CHECK_ARG(B >= 1 && n >= 2 && B <= 65535, "constrain: bad sizes B=%d n=%d", B, n);
+    if (ws_bytes < lmr_constrain_workspace_bytes(B, n)) {
+        set_error("constrain_bwd: workspace too small");
+        return LMR_ERR_WORKSPACE;
+    }
+    const int S = (n + CCH - 1) / CCH;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid(S, B);
+    constrain_bwd_stats_kernel<<<grid, 256, 0, st>>>(mode, x, g_z, stats, n, target, mean, has_min, pmin, has_max, pmax, eps, static_cast<float*>(ws));
+    LMR_LAUNCH_OK();
+    constrain_bwd_apply_kernel<<<grid, 256, 0, st>>>(mode, x, g_z, stats, n, target, mean, has_min, pmin, has_max, pmax, eps,
+                                                     static_cast<const float*>(ws), g_x);
+    LMR_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" size_t lmr_simresp_workspace_bytes(int G, int NB, int Fmax, int HW) {
+    const int S = (HW + RCH - 1) / RCH;
+    return (size_t)G * S * NB * Fmax * sizeof(float);
+}
+
+extern "C" int lmr_simresp_fwd(const float* img, long long gstride, int NB, int G, int C, int HW, const float* filters, int Fmax, const int* nfilt,
+                               const int* neuron_of_group, float eps, float* act, float* rmax, int* argmax, void* ws, size_t ws_bytes,
+                               void* stream) {
+    LMR_CHECK_ARG(NB >= 1 && G >= 1 && C >= 1 && HW >= 1 && Fmax >= 1, "simresp: bad sizes");
+    LMR_CHECK_ARG(G <= 65535, "simresp: G=%d > 65535 groups per call", G);
+    if (ws_bytes < lmr_simresp_workspace_bytes(G, NB, Fmax, HW)) {
+        set_error("simresp_fwd: workspace too small");
+        return LMR_ERR_WORKSPACE;
+    }
+    const int S = (HW + RCH - 1) / RCH;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    simresp_partial_kernel<<<dim3(S, G), 256, 0, st>>>(img, gstride, NB, C, HW, filters, Fmax, nfilt, neuron_of_group, static_cast<float*>(ws));
+    LMR_LAUNCH_OK();
+    simresp_finalize_kernel<<<(G * NB + 127) / 128, 128, 0, st>>>(static_cast<const float*>(ws), S, NB, G, Fmax, nfilt, neuron_of_group, eps, act, rmax,
+                                                                   argmax);
+    LMR_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int lmr_simresp_bwd(const float* g_act, const float* rmax, const int* argmax, long long gstride, int NB, int G, int C, int HW,
+                               const float* filters, int Fmax, const int* neuron_of_group, float* g_img, int accumulate, void* stream) {
+    LMR_CHECK_ARG(NB >= 1 && G >= 1 && C >= 1 && HW >= 1, "simresp_bwd: bad sizes");
+    LMR_CHECK_ARG(NB <= 65535 && G <= 65535, "simresp_bwd: NB/G too large for one call");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid((HW + 255) / 256, NB, gstride ? G : 1);
+    simresp_bwd_kernel<<<grid, 256, 0, st>>>(g_act, rmax, argmax, gstride, NB, G, C, HW, filters, Fmax, neuron_of_group, g_img, accumulate);
+    LMR_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" size_t lmr_simclr_workspace_bytes(int N, int C, int HW) {
+    const int S = (C * HW + GCH - 1) / GCH;
+    return (size_t)S * N * N * sizeof(float);
+}
+
+extern "C" int lmr_simclr_fwd(const float* img, const float* mask, int N, int C, int HW, float pmin, float pmax, const float* pos,
+                              const float* neg, float T, float eps, float* reg, float* K, void* ws, size_t ws_bytes, void* stream) {
+    LMR_CHECK_ARG(N >= 2 && N <= GMAXN, "simclr: N=%d out of range [2,%d]", N, GMAXN);
+    LMR_CHECK_ARG(pmax > pmin, "simclr: pixel bounds required (pmin < pmax)");
+    if (ws_bytes < lmr_simclr_workspace_bytes(N, C, HW)) {
+        set_error("simclr_fwd: workspace too small");
+        return LMR_ERR_WORKSPACE;
+    }
+    const int S = (C * HW + GCH - 1) / GCH;
+    const float c0 = (pmin + pmax) / 2, g1 = 2.f / (pmax - pmin), g2 = (pmax - pmin) / 2.f;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t smem1 = (size_t)N * (GCH + 1) * sizeof(float);
+    LMR_CUDA_OK(cudaFuncSetAttribute(simclr_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    simclr_gram_kernel<<<S, 256, smem1, st>>>(img, mask, N, C, HW, c0, g1, g2, static_cast<float*>(ws));
+    LMR_LAUNCH_OK();
+    const size_t smem2 = ((size_t)2 * N * N + 5 * N) * sizeof(float);
+    simclr_finalize_kernel<<<1, 256, smem2, st>>>(static_cast<const float*>(ws), S, N, pos, neg, T, eps, reg, K);
+    LMR_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int lmr_simclr_bwd(const float* img, const float* mask, const float* K, const float* g_reg, float scale, int N, int C, int HW,
+                              float pmin, float pmax, float* g_img, int accumulate, void* stream) {
+    LMR_CHECK_ARG(N >= 2 && N <= GMAXN, "simclr: N=%d out of range [2,%d]", N, GMAXN);
+    const float c0 = (pmin + pmax) / 2, g1 = 2.f / (pmax - pmin), g2 = (pmax - pmin) / 2.f;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int n = C * HW;
+    simclr_bwd_kernel<<<(n + 127) / 128, 128, (size_t)N * N * sizeof(float), st>>>(img, mask, K, g_reg, scale, N, C, HW, c0, g1, g2, g_img, accumulate);
+    LMR_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int lmr_adam_step(float* p, const float* g, float* m, float* v, int n, float lr, float b1, float b2, float eps, int* step,
+                             void* stream) {
+    LMR_CHECK_ARG(n >= 1 && step != nullptr, "adam: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = n < 256 * 1024 ? (n + 255) / 256 : 1024;
+    adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, step);
+    LMR_LAUNCH_OK();
+    counter_inc_kernel<<<1, 1, 0, st>>>(step);
+    LMR_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int lmr_mei_ascent(float* x, int G, int C, int HW, const float* filters, int Fmax, const int* nfilt, const int* neuron_of_group,
+                              float step_size, int iters, int mode, float target, float mean, float pmin, float pmax, float act_eps,
+                              int apply_post_first, float* fevals, void* stream) {
+    LMR_CHECK_ARG(G >= 1 && C >= 1 && HW >= 2 && iters >= 0, "mei: bad sizes");
+    LMR_CHECK_ARG(mode == LMR_CONSTRAIN_NORM || mode == LMR_CONSTRAIN_STD, "mei: bad mode %d", mode);
+    const size_t smem = ((size_t)(C * HW + 3) / 4 * 4 + Fmax) * sizeof(float);
+    LMR_CHECK_ARG(smem <= 200 * 1024, "mei: image of %d floats does not fit the shared-memory resident kernel", C * HW);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LMR_CUDA_OK(cudaFuncSetAttribute(mei_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mei_kernel<<<G, MEI_THREADS, smem, st>>>(x, C, HW, filters, Fmax, nfilt, neuron_of_group, step_size, iters, mode, target, mean, pmin, pmax, act_eps,
+                                            apply_post_first, fevals);
+    LMR_LAUNCH_OK();
+    return 0;
+}

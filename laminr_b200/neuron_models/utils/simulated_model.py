@@ -1,0 +1,93 @@
+"""Simulated Gabor-bank response models.
+
+Mirror of the reference interface laminr/neuron_models/utils/simulated_model.py:8-29,71-115,171-204:
+`ArbitraryNeuronModel(filters)`, `ArbitraryMultiNeuronModel(list)`, `generate_gabor_filter`,
+`random_transformation_matrices`.  Filter *construction* is a one-off NumPy float64 computation on the host in the
+same operation order as the reference (bit-identical float32 banks are a precondition for parity and are tested
+against the reference's sha256).  The *response* (filter-bank dot products, max, elu) runs in the fused kernels
+lmr_simresp_fwd/bwd on a packed `[n, Fmax, H*W]` bank.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from ... import ops
+
+
+def _transform_pattern(xx, yy, mat, centre):
+    px, py = centre
+    shifted = np.stack((xx - px, yy - py)).reshape(2, -1)
+    xr, yr = (mat @ shifted).reshape(2, *xx.shape)
+    return xr + px, yr + py
+
+
+def generate_gabor_filter(theta, width_x, width_y, frequency, phase, center, grid_size, transformation_matrix=None):
+    """Gaussian envelope x cosine carrier on a [-1,1]^2 grid ('xy' meshgrid: filter[i, j] has x = column j, y = row i)."""
+    xx, yy = np.meshgrid(np.linspace(-1, 1, grid_size[0]), np.linspace(-1, 1, grid_size[1]))
+    dx, dy = center
+    xx, yy = xx - dx, yy - dy  # translate
+    rot = np.array([[np.cos(theta), np.sin(theta)], [-np.sin(theta), np.cos(theta)]])
+    xx, yy = _transform_pattern(xx, yy, rot, (center[0] - dx, center[1] - dy))  # local rotation about the (moved) centre
+    if transformation_matrix is not None:  # global transform about the image centre
+        xx, yy = _transform_pattern(xx, yy, transformation_matrix, rot @ (0 - dx, 0 - dy))
+    envelope = np.exp(-0.5 * (xx**2 / width_x**2 + yy**2 / width_y**2))
+    return envelope * np.cos(2 * np.pi * frequency * xx + phase)
+
+
+def random_transformation_matrices(n):
+    """rotation . scaling . shearing with the reference's draw order from the NumPy global RNG (simulated_model.py:188-204)."""
+    out = []
+    for _ in range(n):
+        theta = np.random.uniform(0, 2 * np.pi)
+        s_x = np.random.uniform(0.5, 1.3)
+        s_y = s_x + np.random.uniform(-0.3, 0.3)
+        s_h = np.random.uniform(-0.15, 0.15)
+        s_v = np.random.uniform(-0.15, 0.15)
+        rot = np.array([[np.cos(theta), -np.sin(theta)], [np.sin(theta), np.cos(theta)]])
+        out.append(np.dot(rot, np.dot(np.array([[s_x, 0], [0, s_y]]), np.array([[1, s_h], [s_v, 1]]))))
+    return out
+
+
+class ArbitraryNeuronModel(nn.Module):
+    """act = (elu(max_f <x, w_f>) + 1)/2 + eps for one neuron (simulated_model.py:8-17)."""
+
+    def __init__(self, filters, eps=1e-6):
+        super().__init__()
+        self.register_buffer("filters", torch.from_numpy(np.ascontiguousarray(filters.astype(np.float32))))
+        self.eps = eps
+        self._nf = None
+
+    def forward(self, x):
+        F, H, W = self.filters.shape
+        if self._nf is None or self._nf.device != x.device:
+            self._nf = (torch.tensor([F], dtype=torch.int32, device=x.device), torch.zeros(1, dtype=torch.int32, device=x.device))
+        return ops.simresp(x, self.filters.reshape(1, F, H * W), self._nf[0], self._nf[1], self.eps)[0]
+
+
+class ArbitraryMultiNeuronModel(nn.Module):
+    """Population of simulated neurons -> [B, n] (simulated_model.py:20-29).  The per-neuron banks are packed into one
+    `[n, Fmax, H*W]` buffer (ragged banks padded by repeating their first filter: the max is unaffected)."""
+
+    def __init__(self, neuron_models_list):
+        super().__init__()
+        self.neuron_models_list = nn.ModuleList(neuron_models_list)
+        banks = [m.filters for m in neuron_models_list]
+        self.eps = neuron_models_list[0].eps
+        fmax = max(b.shape[0] for b in banks)
+        self.img_res = tuple(banks[0].shape[1:])
+        packed = torch.stack([torch.cat([b, b[:1].expand(fmax - b.shape[0], -1, -1)]) if b.shape[0] < fmax else b for b in banks])
+        self.register_buffer("packed_filters", packed.reshape(len(banks), fmax, -1).contiguous(), persistent=False)
+        self.register_buffer("nfilt", torch.tensor([b.shape[0] for b in banks], dtype=torch.int32), persistent=False)
+        self.register_buffer("all_neurons", torch.arange(len(banks), dtype=torch.int32), persistent=False)
+
+    @property
+    def n_neurons(self):
+        return self.packed_filters.shape[0]
+
+    def forward_neurons(self, x, neuron_idxs):
+        """Responses of the listed neurons only -> [B, len(neuron_idxs)]."""
+        idx = torch.as_tensor(list(neuron_idxs), dtype=torch.int32, device=x.device)
+        return ops.simresp(x, self.packed_filters, self.nfilt, idx, self.eps).t()
+
+    def forward(self, x):
+        return ops.simresp(x, self.packed_filters, self.nfilt, self.all_neurons, self.eps).t()

@@ -1,0 +1,355 @@
+"""PyTorch-facing operators over the C ABI (include/laminr_b200.h).
+
+Two levels:
+  * `raw_*` functions: thin stream-ordered wrappers (device pointers in, nothing allocated inside the library);
+    these are what the fused learn/match/MEI drivers call directly and what CUDA-graph capture records.
+  * `torch.autograd.Function`s (`inr_images`, `constrain`, `simresp`, `simclr_reg`): differentiable operators so
+    the drop-in modules compose with stock autograd (e.g. a user-supplied nn.Module response model).
+
+PyTorch is plumbing here (device memory, streams); every op fails loudly without a CUDA device / the library.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import Affine, InrDesc, check
+
+_DEFAULT_PRECISION = _lib.PREC_FP32
+_PREC_NAMES = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "bf16x3": _lib.PREC_BF16X3}
+
+
+def set_default_precision(name):
+    """'fp32' (CUDA cores, parity path) | 'tf32' | 'bf16x3' (tcgen05 paths) for the INR hidden layers."""
+    global _DEFAULT_PRECISION
+    _DEFAULT_PRECISION = _PREC_NAMES[name]
+
+
+def default_precision():
+    return _DEFAULT_PRECISION
+
+
+def precision_code(p):
+    if p is None:
+        return _DEFAULT_PRECISION
+    return _PREC_NAMES[p] if isinstance(p, str) else int(p)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "laminr_b200 operators run on CUDA (sm_100a) only; got a tensor on %s. There is no CPU fallback." % t.device
+            )
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise TypeError("laminr_b200 operators take float32 tensors")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _workspace(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# INR
+# ------------------------------------------------------------------------------------------------------------------
+class AffineArgs:
+    """Device tensors of the per-target affine transform (match stage); see lmr_affine in the header."""
+
+    def __init__(self, angles, scalings, shears, translation, tc=None, shift_to=None, shift_from=None, clamp=True):
+        self.angles, self.scalings, self.shears = _f32c(angles), _f32c(scalings), _f32c(shears)
+        self.translation = _f32c(translation).reshape(-1, 2)
+        self.tc = None if tc is None else _f32c(tc)
+        self.shift_to = None if shift_to is None else _f32c(shift_to)
+        self.shift_from = None if shift_from is None else _f32c(shift_from)
+        self.clamp = bool(clamp)
+        self.D = self.angles.numel()
+
+    def struct(self):
+        return Affine(
+            self.angles.data_ptr(), self.scalings.data_ptr(), int(self.scalings.shape[-1]) if self.scalings.dim() > 1 else 1,
+            self.shears.data_ptr(), self.translation.data_ptr(),
+            None if self.tc is None else self.tc.data_ptr(), None if self.shift_to is None else self.shift_to.data_ptr(),
+            None if self.shift_from is None else self.shift_from.data_ptr(), int(self.clamp),
+        )
+
+
+def make_desc(hidden, n_hidden, pe_dim, aux_pe_dim, channels):
+    return InrDesc(int(hidden), int(n_hidden), int(pe_dim), int(aux_pe_dim), int(channels))
+
+
+def raw_inr_forward(desc, params, B, auxB, grid, coords, coord_shift, affine, out=None, precision=None, workspace=None):
+    """-> img [D, N, C, P] (float32).  params: flat parameter vector (see header); grid [N]; coords [P,2]."""
+    lib = _lib.load()
+    _require_cuda(params, B, auxB, grid, coords)
+    N, P = grid.numel(), coords.shape[0]
+    D = 1 if affine is None else affine.D
+    if out is None:
+        out = torch.empty((D, N, desc.channels, P), dtype=torch.float32, device=params.device)
+    if workspace is None:
+        workspace = _workspace(lib.lmr_inr_forward_workspace_bytes(C.byref(desc), N, P, D), params.device)
+    aff = affine.struct() if affine is not None else None
+    check(lib.lmr_inr_forward(
+        C.byref(desc), _ptr(params), _ptr(B), _ptr(auxB), _ptr(grid), N, _ptr(coords), P, _ptr(coord_shift),
+        C.byref(aff) if aff is not None else None, D, _ptr(out), _ptr(workspace), workspace.numel(), precision_code(precision), _stream(),
+    ))
+    return out
+
+
+def raw_inr_backward(desc, params, B, auxB, grid, coords, coord_shift, affine, g_img, want_params=True, want_affine=False,
+                     precision=None, workspace=None, g_params=None, g_affine=None):
+    """-> (g_params flat | None, (g_angles, g_scalings, g_shears, g_translation) | None)."""
+    lib = _lib.load()
+    _require_cuda(params, g_img)
+    N, P = grid.numel(), coords.shape[0]
+    D = 1 if affine is None else affine.D
+    dev = params.device
+    if want_params and g_params is None:
+        g_params = torch.empty_like(params)
+    if want_affine and g_affine is None:
+        g_affine = (torch.empty_like(affine.angles), torch.empty_like(affine.scalings), torch.empty_like(affine.shears),
+                    torch.empty_like(affine.translation))
+    if workspace is None:
+        workspace = _workspace(lib.lmr_inr_backward_workspace_bytes(C.byref(desc), N, P, D), dev)
+    aff = affine.struct() if affine is not None else None
+    ga = g_affine if want_affine else (None, None, None, None)
+    check(lib.lmr_inr_backward(
+        C.byref(desc), _ptr(params), _ptr(B), _ptr(auxB), _ptr(grid), N, _ptr(coords), P, _ptr(coord_shift),
+        C.byref(aff) if aff is not None else None, D, _ptr(_f32c(g_img)), _ptr(g_params if want_params else None),
+        _ptr(ga[0]), _ptr(ga[1]), _ptr(ga[2]), _ptr(ga[3]), _ptr(workspace), workspace.numel(), precision_code(precision), _stream(),
+    ))
+    return (g_params if want_params else None), (g_affine if want_affine else None)
+
+
+class _InrImages(torch.autograd.Function):
+    """img[D,N,C,P] = INR(...).  Differentiable wrt the MLP parameters (learn) and the affine scalars (match)."""
+
+    @staticmethod
+    def forward(ctx, meta, flat_params, B, auxB, grid, coords, coord_shift, angles, scalings, shears, translation, *param_views):
+        desc, aff_const, precision = meta["desc"], meta["affine_const"], meta["precision"]
+        affine = None
+        if angles is not None:
+            affine = AffineArgs(angles.detach(), scalings.detach(), shears.detach(), translation.detach(), **aff_const)
+        grid = _f32c(grid.detach().reshape(-1))
+        out = raw_inr_forward(desc, flat_params, B, auxB, grid, coords, coord_shift, affine, precision=precision)
+        ctx.meta, ctx.affine = meta, affine
+        ctx.save_for_backward(flat_params, B, auxB, grid, coords, coord_shift)
+        ctx.param_shapes = [p.shape for p in param_views]
+        ctx.translation_shape = None if translation is None else translation.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, g_img):
+        flat_params, B, auxB, grid, coords, coord_shift = ctx.saved_tensors
+        meta = ctx.meta
+        n_fixed = 11
+        want_params = any(ctx.needs_input_grad[n_fixed:])
+        want_affine = ctx.affine is not None and any(ctx.needs_input_grad[7:11])
+        grads = [None] * (n_fixed + len(ctx.param_shapes))
+        if not (want_params or want_affine):
+            return tuple(grads)
+        g_params, g_aff = raw_inr_backward(meta["desc"], flat_params, B, auxB, grid, coords, coord_shift, ctx.affine, g_img,
+                                           want_params=want_params, want_affine=want_affine, precision=meta["precision"])
+        if want_affine:
+            grads[7], grads[8], grads[9] = g_aff[0], g_aff[1], g_aff[2]
+            grads[10] = g_aff[3].reshape(ctx.translation_shape)
+        if want_params:
+            off = 0
+            for i, shp in enumerate(ctx.param_shapes):
+                n = int(torch.Size(shp).numel())
+                grads[n_fixed + i] = g_params[off:off + n].view(shp)
+                off += n
+        return tuple(grads)
+
+
+def inr_images(meta, flat_params, B, auxB, grid, coords, coord_shift, affine_params, param_views):
+    a = affine_params if affine_params is not None else (None, None, None, None)
+    return _InrImages.apply(meta, flat_params, B, auxB, grid, coords, coord_shift, a[0], a[1], a[2], a[3], *param_views)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# constraint projection
+# ------------------------------------------------------------------------------------------------------------------
+def raw_constrain_fwd(mode, x, target, mean, pmin, pmax, eps, out=None, stats=None, workspace=None):
+    lib = _lib.load()
+    _require_cuda(x)
+    Bn, n = x.shape[0], x[0].numel()
+    if out is None:
+        out = torch.empty_like(x)
+    if stats is None:
+        stats = torch.empty((Bn, 2), dtype=torch.float32, device=x.device)
+    if workspace is None:
+        workspace = _workspace(lib.lmr_constrain_workspace_bytes(Bn, n), x.device)
+    check(lib.lmr_constrain_fwd(mode, _ptr(x), Bn, n, float(target), float(mean), int(pmin is not None), float(pmin or 0.0),
+                                int(pmax is not None), float(pmax or 0.0), float(eps), _ptr(out), _ptr(stats), _ptr(workspace),
+                                workspace.numel(), _stream()))
+    return out, stats
+
+
+def raw_constrain_bwd(mode, x, g_z, stats, target, mean, pmin, pmax, eps, out=None, workspace=None):
+    lib = _lib.load()
+    Bn, n = x.shape[0], x[0].numel()
+    if out is None:
+        out = torch.empty_like(x)
+    if workspace is None:
+        workspace = _workspace(lib.lmr_constrain_workspace_bytes(Bn, n), x.device)
+    check(lib.lmr_constrain_bwd(mode, _ptr(x), _ptr(g_z), _ptr(stats), Bn, n, float(target), float(mean), int(pmin is not None),
+                                float(pmin or 0.0), int(pmax is not None), float(pmax or 0.0), float(eps), _ptr(out), _ptr(workspace),
+                                workspace.numel(), _stream()))
+    return out
+
+
+class _Constrain(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mode, target, mean, pmin, pmax, eps):
+        x = _f32c(x)
+        z, stats = raw_constrain_fwd(mode, x, target, mean, pmin, pmax, eps)
+        ctx.save_for_backward(x, stats)
+        ctx.cfg = (mode, target, mean, pmin, pmax, eps)
+        return z
+
+    @staticmethod
+    def backward(ctx, g_z):
+        x, stats = ctx.saved_tensors
+        mode, target, mean, pmin, pmax, eps = ctx.cfg
+        return raw_constrain_bwd(mode, x, _f32c(g_z), stats, target, mean, pmin, pmax, eps), None, None, None, None, None, None
+
+
+def constrain(x, mode, target, mean, pmin, pmax, eps=1e-12):
+    return _Constrain.apply(x, mode, target, mean, pmin, pmax, eps)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# simulated response
+# ------------------------------------------------------------------------------------------------------------------
+def raw_simresp_fwd(img, group_stride, NB, G, Cc, HW, filters, nfilt, neuron_of_group, eps, out=None, workspace=None):
+    """-> act, rmax, argmax, each [G, NB]."""
+    lib = _lib.load()
+    _require_cuda(img, filters)
+    Fmax = filters.shape[1]
+    dev = img.device
+    if out is None:
+        out = (torch.empty((G, NB), dtype=torch.float32, device=dev), torch.empty((G, NB), dtype=torch.float32, device=dev),
+               torch.empty((G, NB), dtype=torch.int32, device=dev))
+    if workspace is None:
+        workspace = _workspace(lib.lmr_simresp_workspace_bytes(G, NB, Fmax, HW), dev)
+    check(lib.lmr_simresp_fwd(_ptr(img), int(group_stride), NB, G, Cc, HW, _ptr(filters), Fmax, _ptr(nfilt), _ptr(neuron_of_group),
+                              float(eps), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(workspace), workspace.numel(), _stream()))
+    return out
+
+
+def raw_simresp_bwd(g_act, rmax, argmax, group_stride, NB, G, Cc, HW, filters, neuron_of_group, g_img, accumulate=False):
+    lib = _lib.load()
+    check(lib.lmr_simresp_bwd(_ptr(g_act), _ptr(rmax), _ptr(argmax), int(group_stride), NB, G, Cc, HW, _ptr(filters), filters.shape[1],
+                              _ptr(neuron_of_group), _ptr(g_img), int(accumulate), _stream()))
+    return g_img
+
+
+class _SimResp(torch.autograd.Function):
+    """x [B,C,H,W] -> act [G,B] for the neurons in `neuron_of_group` (every neuron sees every image)."""
+
+    @staticmethod
+    def forward(ctx, x, filters, nfilt, neuron_of_group, eps):
+        x = _f32c(x)
+        Bn, Cc = x.shape[0], x.shape[1]
+        HW = x.shape[2] * x.shape[3]
+        G = neuron_of_group.numel()
+        act, rmax, argmax = raw_simresp_fwd(x, 0, Bn, G, Cc, HW, filters, nfilt, neuron_of_group, eps)
+        ctx.save_for_backward(rmax, argmax, filters, neuron_of_group)
+        ctx.shape = x.shape
+        return act
+
+    @staticmethod
+    def backward(ctx, g_act):
+        rmax, argmax, filters, neuron_of_group = ctx.saved_tensors
+        Bn, Cc, H, W = ctx.shape
+        g_img = torch.empty(ctx.shape, dtype=torch.float32, device=g_act.device)
+        raw_simresp_bwd(_f32c(g_act), rmax, argmax, 0, Bn, neuron_of_group.numel(), Cc, H * W, filters, neuron_of_group, g_img)
+        return g_img, None, None, None, None
+
+
+def simresp(x, filters, nfilt, neuron_of_group, eps=1e-6):
+    return _SimResp.apply(x, filters, nfilt, neuron_of_group, eps)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# masked contrastive term
+# ------------------------------------------------------------------------------------------------------------------
+def raw_simclr_fwd(img, mask, N, Cc, HW, pmin, pmax, pos, neg, T, eps, reg=None, K=None, workspace=None):
+    lib = _lib.load()
+    _require_cuda(img, mask, pos, neg)
+    dev = img.device
+    if reg is None:
+        reg = torch.empty((1,), dtype=torch.float32, device=dev)
+    if K is None:
+        K = torch.empty((N, N), dtype=torch.float32, device=dev)
+    if workspace is None:
+        workspace = _workspace(lib.lmr_simclr_workspace_bytes(N, Cc, HW), dev)
+    check(lib.lmr_simclr_fwd(_ptr(img), _ptr(mask), N, Cc, HW, float(pmin), float(pmax), _ptr(pos), _ptr(neg), float(T), float(eps),
+                             _ptr(reg), _ptr(K), _ptr(workspace), workspace.numel(), _stream()))
+    return reg, K
+
+
+def raw_simclr_bwd(img, mask, K, g_reg, scale, N, Cc, HW, pmin, pmax, g_img, accumulate=False):
+    lib = _lib.load()
+    check(lib.lmr_simclr_bwd(_ptr(img), _ptr(mask), _ptr(K), _ptr(g_reg), float(scale), N, Cc, HW, float(pmin), float(pmax), _ptr(g_img),
+                             int(accumulate), _stream()))
+    return g_img
+
+
+class _SimclrReg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, mask, pmin, pmax, pos, neg, T, eps):
+        img = _f32c(img)
+        N, Cc = img.shape[0], img.shape[1]
+        HW = img[0, 0].numel()
+        reg, K = raw_simclr_fwd(img, mask, N, Cc, HW, pmin, pmax, pos, neg, T, eps)
+        ctx.save_for_backward(img, mask, K)
+        ctx.cfg = (N, Cc, HW, pmin, pmax)
+        return reg.reshape(())
+
+    @staticmethod
+    def backward(ctx, g_reg):
+        img, mask, K = ctx.saved_tensors
+        N, Cc, HW, pmin, pmax = ctx.cfg
+        g_img = torch.empty_like(img)
+        raw_simclr_bwd(img, mask, K, _f32c(g_reg.reshape(1)), 1.0, N, Cc, HW, pmin, pmax, g_img)
+        return g_img, None, None, None, None, None, None, None
+
+
+def simclr_reg(img, mask, pmin, pmax, pos, neg, T, eps=1e-6):
+    """apply_mask + SimCLROnGrid.reg_term fused.  img [N,C,H,W]; mask [H,W]."""
+    return _SimclrReg.apply(img, _f32c(mask), pmin, pmax, pos, neg, T, eps)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Adam / MEI
+# ------------------------------------------------------------------------------------------------------------------
+def raw_adam_step(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    lib = _lib.load()
+    _require_cuda(p, g, m, v, step)
+    check(lib.lmr_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(b1), float(b2), float(eps), _ptr(step), _stream()))
+
+
+def raw_mei_ascent(x, filters, nfilt, neuron_of_group, step_size, iters, mode, target, mean, pmin, pmax, act_eps=1e-6, apply_post_first=True):
+    """x [G,C,H,W] in/out -> fevals [G, iters+1]."""
+    lib = _lib.load()
+    _require_cuda(x, filters)
+    G, Cc = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel()
+    fevals = torch.empty((G, iters + 1), dtype=torch.float32, device=x.device)
+    check(lib.lmr_mei_ascent(_ptr(x), G, Cc, HW, _ptr(filters), filters.shape[1], _ptr(nfilt), _ptr(neuron_of_group), float(step_size), int(iters),
+                             int(mode), float(target), float(mean), float(pmin), float(pmax), float(act_eps), int(apply_post_first),
+                             _ptr(fevals), _stream()))
+    return fevals

@@ -1,0 +1,27 @@
+"""Boundary glue: mirror of laminr/utils/general.py:5-20."""
+import torch
+from torch import nn
+
+
+class SingleNeuronModel(nn.Module):
+    """model(x)[:, idx].squeeze().  For the packed simulated population only neuron `idx` is evaluated
+    (the reference evaluates every neuron and discards all but one, general.py:11-12)."""
+
+    def __init__(self, model, idx):
+        super().__init__()
+        self.model = model
+        self.idx = idx
+
+    def forward(self, x):
+        single = getattr(self.model, "forward_neurons", None)
+        if single is not None:
+            return single(x, [self.idx])[:, 0].squeeze()
+        return self.model(x)[:, self.idx].squeeze()
+
+
+def infer_device(module):
+    for param in module.parameters():
+        return param.device
+    for buffer in module.buffers():
+        return buffer.device
+    return torch.device("cpu")
