@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- INR opt steps/sec of `InvarianceManifold.learn` on demo1 @ 100x100 (BASELINE.json metric), B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--res 100] [--precision fp32|tf32|bf16x3]
+
+One "step" is one pass of the learn hot path (reference laminr/inv_temp_learn_match.py:186-208): INR forward over
+20 latents x HxW pixels, constraint projection, template-neuron response, masked contrastive term, backward, Adam.
+
+  value    : steps/s with inputs resident in HBM.  Each step is timed with its own CUDA-event pair on the launching
+             stream; L2 is flushed (256 MiB write) between timed steps, outside the event pairs.
+  e2e      : steps/s through the host-facing call: per step H2D of the jittered latent grid from pinned memory, the
+             step, D2H of the step's loss.
+  roofline : the INR backward launch group (dominant), algorithmic FLOPs / CUDA-event time vs measured bf16 peak.
+  cpu_baseline : the reference's CPU path (torch-CPU port of its op sequence, oracle/torch_port.py; or the reference
+             itself when /root/reference is mounted) on a bounded sample of the same workload.
+  match    : extra -- target-steps/s of the match hot step (:351-366), targets sharded over the N ranks.
+N > 1: learn does not shard (one template) -> N independent replicas ("replicas only"); value = N*K / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_LATENTS = 20
+
+
+def algorithmic_flops(res, N=N_LATENTS, h=50, pe=50, C=1):
+    """separable layer 0, recomputation not counted."""
+    P = res * res
+    R = N * P
+    fwd = 2 * P * 2 * pe + 2 * P * (2 * pe) * h + 2 * N * (2 * pe) * h + 3 * 2 * R * h * h + 2 * R * h * C
+    bwd = 3 * 4 * R * h * h + 2 * 2 * R * h * C + 2 * P * (2 * pe) * h + 2 * N * (2 * pe) * h
+    return fwd, bwd
+
+
+def synthetic_meis(res):
+    """Synthetic meis_dict: Gaussian-bump RF masks at the demo1 filter centres, MEI activation of a unit-norm optimum."""
+    yy, xx = np.meshgrid(np.arange(res) + 0.5, np.arange(res) + 0.5, indexing="ij")
+    out = {}
+    for i, (cx, cy) in enumerate([(0.6 * res, 0.6 * res), (0.4 * res, 0.4 * res), (0.4 * res, 0.6 * res)]):
+        mask = np.exp(-0.5 * (((xx - cx) / (0.16 * res)) ** 2 + ((yy - cy) / (0.16 * res)) ** 2)).astype(np.float32)
+        out[i] = dict(mei=np.zeros((1, res, res), np.float32), activation=1.0000009536743164, mask=mask, center_pos=dict(x=cx, y=cy))
+    return out
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], None, set()
+        for line in out.strip().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])), (smax := float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
+                if val == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_learn_steps(res, n_steps, warmup, threads):
+    """Times the reference's CPU learn step.  Uses the reference itself when it is mounted, else the torch-CPU port."""
+    import torch
+
+    torch.set_num_threads(threads)
+    from oracle import laminr_oracle as O
+
+    rng = np.random.RandomState(0)
+    grid0 = O.latent_grid(N_LATENTS)
+    sigma = 2 * np.pi / N_LATENTS
+    grids = [grid0 + np.float32(rng.rand() * sigma - 0.5 * sigma) for _ in range(n_steps + warmup)]
+    meis = synthetic_meis(res)
+    kind = "port"
+    step_fn = None
+    try:
+        from oracle.ref_harness import import_reference, reference_available
+        if reference_available():
+            laminr = import_reference()
+            from laminr.contrastive_loss import SimCLROnGrid
+            from laminr.utils.general import SingleNeuronModel
+            from laminr.utils.mask import apply_mask
+            torch.manual_seed(0)
+            model = laminr.neuron_models.simulated("demo1", img_res=[res, res])
+            im = laminr.InvarianceManifold(model, meis, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+            reg = SimCLROnGrid(1, N_LATENTS, 0.1, 0.3, True)
+            opt = torch.optim.Adam(im.template.func.parameters(), lr=1e-3)
+            snm = SingleNeuronModel(model, 0)
+            mask = torch.from_numpy(meis[0]["mask"])
+
+            def step_fn(g):  # inv_temp_learn_match.py:186-208 verbatim in behaviour (anomaly mode on, as shipped)
+                gt = torch.as_tensor(g, dtype=torch.float32).reshape(-1, 1)
+                _, img_post, _acts, _ = im.forward(gt, im.template, im.img_transforms, snm, return_template=True)
+                acts = _acts / meis[0]["activation"]
+                sim = reg.reg_term(apply_mask(img_post, mask, -1.0, 1.0))
+                loss = -acts.mean() - 2 * sim
+                opt.zero_grad()
+                torch.autograd.set_detect_anomaly(True)
+                loss.backward()
+                opt.step()
+
+            kind = "reference"
+    except Exception:  # noqa: BLE001 -- any import problem -> the port
+        step_fn = None
+    if step_fn is None:
+        from oracle.torch_port import LearnPort
+        torch.manual_seed(0)
+        h, pe, ape = 50, 50, 50
+        W = [np.random.RandomState(1).randn(h, 1 + 2 * ape + 2 * pe).astype(np.float32) * 0.1] + \
+            [np.random.RandomState(2 + l).randn(h, h).astype(np.float32) * 0.1 for l in range(3)] + \
+            [np.random.RandomState(9).randn(1, h).astype(np.float32) * 0.1]
+        b = [np.zeros(w.shape[0], np.float32) for w in W]
+        B = np.random.RandomState(10).randn(2, pe).astype(np.float32) * 10
+        auxB = np.random.RandomState(11).randn(2, ape).astype(np.float32) * 0.1
+        pos, neg = O.pos_neg_masks(N_LATENTS, 0.1, True)
+        port = LearnPort(W, b, B, auxB, O.pixel_coords((res, res)), O.demo1_banks([res, res])[0], meis[0]["mask"], meis[0]["activation"], pos, neg,
+                         res=(res, res), anomaly_mode=True)
+        step_fn = port.step
+    for g in grids[:warmup]:
+        step_fn(g)
+    t0 = time.perf_counter()
+    for g in grids[warmup:]:
+        step_fn(g)
+    dt = time.perf_counter() - t0
+    return n_steps / dt, dt, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(1, min(args.steps, 60 if args.res <= 100 else 15))  # bounded sample: a reference step is ~0.2 s (100^2) / ~0.9 s (200^2)
+    warm = max(1, min(args.warmup, 3))
+    sps, dt, kind = cpu_learn_steps(args.res, steps, warm, threads)
+    sample = f"{steps} learn steps of demo1 @{args.res}x{args.res} ({N_LATENTS} latents), {'unmodified reference' if kind == 'reference' else 'torch-CPU port of the reference op sequence'}, anomaly mode on as shipped"
+    line = {
+        "impl": "reference", "metric": "INR opt steps/sec (learn, 100x100)", "value": sps, "unit": "steps/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"demo1 learn step, {args.res}x{args.res}x1, {N_LATENTS} latents (CPU, {threads} threads)"},
+        "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the laminr_b200 path has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import laminr_b200 as L
+    from laminr_b200.contrastive_loss import SimCLROnGrid
+    from laminr_b200.fused import LearnStepper, MatchStepper
+    from laminr_b200.utils.training import JitteringGridDatamodule
+
+    res, K, Wm = args.res, args.steps, max(args.warmup, 3)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = L.neuron_models.simulated("demo1", img_res=[res, res]).to(dev)
+    meis = synthetic_meis(res)
+    im = L.InvarianceManifold(model, meis, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0, precision=args.precision)
+    reg = SimCLROnGrid(1, N_LATENTS, 0.1, 0.3, True).to(dev)
+    stepper = LearnStepper(im.template, im.img_transforms, model, 0, meis[0]["mask"], meis[0]["activation"], reg, -1.0, 1.0, N_LATENTS, lr=1e-3,
+                           reg_scale=2.0, precision=args.precision, use_graph=True)
+    dm = JitteringGridDatamodule(1, N_LATENTS, K + Wm)
+    grids_host = torch.stack(list(dm.train_dataloader())).reshape(K + Wm, N_LATENTS).pin_memory()
+    grids = grids_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs, per-step event pairs, L2 flushed between steps
+    for i in range(Wm):
+        stepper.step(grids[i])
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for i in range(K):
+        flush.fill_(float(i))
+        starts[i].record()
+        stepper.step(grids[Wm + i])
+        ends[i].record()
+    barrier()
+    step_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    # back-to-back (no flush): what the training loop actually sees
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        stepper.step(grids[Wm + i])
+    e1.record()
+    barrier()
+    b2b_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler is not None else None
+
+    # ---- e2e: host grid (pinned) -> H2D -> step -> D2H loss, every step
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    for i in range(3):
+        stepper.step(grids_host[i].to(dev, non_blocking=True))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        g = grids_host[Wm + i].to(dev, non_blocking=True)
+        stepper.step(g)
+        loss_host.copy_(stepper.loss().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    # ---- roofline of the dominant launch group (INR backward), timed alone with CUDA events
+    from laminr_b200 import ops
+    t = im.template
+    gx = stepper.g_x.view(1, N_LATENTS, 1, res * res)
+    def bwd_only():
+        ops.raw_inr_backward(t._desc, stepper.flat, t.B, t.auxB, stepper.grid, stepper.coords, None, None, gx, want_params=True,
+                             precision=args.precision, workspace=stepper.ws_bwd, g_params=stepper.g_flat)
+    def fwd_only():
+        ops.raw_inr_forward(t._desc, stepper.flat, t.B, t.auxB, stepper.grid, stepper.coords, None, None, out=stepper.img_pre.view(1, N_LATENTS, 1, res * res),
+                            precision=args.precision, workspace=stepper.ws_fwd)
+    def time_fn(fn, reps=30):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for r in range(reps):
+            flush.fill_(float(r))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            tot += a.elapsed_time(b)
+        return tot / reps
+    bwd_ms, fwd_ms = time_fn(bwd_only), time_fn(fwd_only)
+
+    # ---- match hot step (extra): targets sharded over ranks, weak scaling (fixed targets per GPU)
+    match = None
+    if args.match_targets > 0:
+        Dloc = args.match_targets
+        pop = L.neuron_models.simulated_population(Dloc + 1, img_res=[res, res], seed=1000 + rank).to(dev)
+        yy, xx = np.meshgrid(np.arange(res) + 0.5, np.arange(res) + 0.5, indexing="ij")
+        pmeis = {}
+        rs = np.random.RandomState(rank)
+        for i in range(Dloc + 1):
+            cx, cy = rs.uniform(0.3, 0.7, 2) * res
+            mask = np.exp(-0.5 * (((xx - cx) / (0.15 * res)) ** 2 + ((yy - cy) / (0.15 * res)) ** 2)).astype(np.float32)
+            pmeis[i] = dict(mei=np.zeros((1, res, res), np.float32), activation=1.0000009536743164, mask=mask, center_pos=dict(x=cx, y=cy))
+        im2 = L.InvarianceManifold(pop, pmeis, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0, precision=args.precision)
+        im2.template.load_state_dict(im.template.state_dict())
+        targets = list(range(1, Dloc + 1))
+        im2.template.initialize_coordinate_transform(Dloc, True, False, 0.1, True, True, False, True)
+        rfs = torch.tensor([[pmeis[i]["center_pos"]["x"], pmeis[i]["center_pos"]["y"]] for i in range(Dloc + 1)], dtype=torch.float32, device=dev)
+        im2.template.register_coords_shifts(rfs[0], rfs[1:])
+        aff = im2.template.coordinate_transform.transforms.Affine
+        with torch.no_grad():
+            aff.angles.copy_(torch.rand(Dloc, device=dev) * 2 * np.pi)
+        ms = MatchStepper(im2.template, im2.img_transforms, pop, targets, np.ones(Dloc, np.float32), N_LATENTS, total_targets=Dloc * world,
+                          precision=args.precision, use_graph=True)
+        mk = max(3, min(K, args.match_steps))
+        for i in range(3):
+            ms.step(grids[i])
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(mk):
+            ms.step(grids[Wm + (i % K)])
+        b.record()
+        barrier()
+        mt = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(mt, op=dist.ReduceOp.MAX)
+        match = {"metric": "match target-steps/sec (one Adam step of one target's affine transform)", "value": Dloc * world * mk / (mt.item() / 1e3),
+                 "unit": "target-steps/s", "targets_per_gpu": Dloc, "steps": mk, "ms_per_step": mt.item() / mk,
+                 "algorithmic_gflop_per_target_step": 2 * algorithmic_flops(res)[0] / 1e9}
+
+    # ---- reduce over ranks (max time), CPU baseline on rank 0 at N == 1
+    tt = torch.tensor([step_ms, b2b_ms, e2e_s * 1e3], device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    step_ms, b2b_ms, e2e_ms = tt.tolist()
+    if rank == 0:
+        fwd_f, bwd_f = algorithmic_flops(res)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak_tf = peaks.get("bf16_tflops", 1590.0)  # burst figure: the launch group is timed alone
+        achieved = bwd_f / (bwd_ms * 1e-3) / 1e12
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n_cpu = 40 if res <= 100 else 12
+            sps, dt, kind = cpu_learn_steps(res, n_cpu, 2, threads)
+            cpu = {"value": sps, "unit": "steps/s", "cores": threads, "kind": kind,
+                   "sample": f"{n_cpu} learn steps of demo1 @{res}x{res} ({dt:.1f} s), {'unmodified reference' if kind == 'reference' else 'torch-CPU port of the reference op sequence'}, anomaly mode on as shipped"}
+        line = {
+            "metric": "INR opt steps/sec (learn, 100x100)", "value": world * K / (step_ms / 1e3), "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision in (None, "fp32") else args.precision,
+            "data": "synthetic",
+            "config": {"workload": f"demo1 learn step, {res}x{res}x1, {N_LATENTS} latents, template neuron 0 (BASELINE configs[0] objects on B200)",
+                       "precision": args.precision or "fp32", "l2": "flushed (256 MiB write) between timed steps, outside the event pairs",
+                       "multi_gpu": "replicas only (learn has one template; match shards, see 'match')", "cuda_graph": True},
+            "back_to_back": {"value": world * K / (b2b_ms / 1e3), "unit": "steps/s", "ms_per_step": b2b_ms / K, "note": "K graph replays in one event pair, no L2 flush (the loop as it runs)"},
+            "e2e": {"value": world * K / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": 4 * N_LATENTS, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(stepper.kernels_per_step * K),
+            "roofline": {"bound": "tensor", "kernel": "lmr_inr_backward launch group (inr_bwd_kernel dominant)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved / peak_tf, "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback",
+                         "algorithmic_gflop": bwd_f / 1e9, "ms": bwd_ms, "forward": {"algorithmic_gflop": fwd_f / 1e9, "ms": fwd_ms, "achieved": fwd_f / (fwd_ms * 1e-3) / 1e12}},
+            "cpu_baseline": cpu, "clocks": clocks, "match": match,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--res", type=int, default=100)
+    ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32", "bf16x3"])
+    ap.add_argument("--match-targets", type=int, default=32, help="targets per GPU for the extra match measurement (0 = skip)")
+    ap.add_argument("--match-steps", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

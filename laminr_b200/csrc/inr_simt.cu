@@ -817,7 +817,11 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
     float* dummy = nullptr;
     Smem<50> s(dummy, nt, tl, false, false);
     const size_t smem = s.floats * sizeof(float) + 16;
-    LMR_CUDA_OK(cudaFuncSetAttribute(inr_fwd_kernel<50>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set_fwd = 0;  // per-process cache: avoid a driver call per launch (and inside graph capture)
+    if (smem > smem_set_fwd) {
+        LMR_CUDA_OK(cudaFuncSetAttribute(inr_fwd_kernel<50>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set_fwd = smem;
+    }
     const int grid_x = tl.numTiles < 4 * num_sms() ? tl.numTiles : 4 * num_sms();
     inr_fwd_kernel<50><<<grid_x, TR_MAX, smem, st>>>(a);
     LMR_LAUNCH_OK();
@@ -852,13 +856,21 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     Smem<50> s(dummy, nt, tl, true, a.want_weights != 0);
     const size_t smem = s.floats * sizeof(float) + 16;
     LMR_CHECK_ARG(smem <= 227 * 1024, "inr_backward: configuration needs %zu bytes of shared memory (> 227 KB)", smem);
-    LMR_CUDA_OK(cudaFuncSetAttribute(inr_bwd_kernel<50>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set_bwd = 0;
+    if (smem > smem_set_bwd) {
+        LMR_CUDA_OK(cudaFuncSetAttribute(inr_bwd_kernel<50>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set_bwd = smem;
+    }
     inr_bwd_kernel<50><<<wl.gridMain, TR_MAX, smem, st>>>(a);
     LMR_LAUNCH_OK();
     if (a.want_weights) {
         float* l0part = reinterpret_cast<float*>(static_cast<char*>(ws) + wl.l0part);
         const size_t smem0 = (size_t)L0_CHUNK * (Smem<50>::HP + 2 * nt.pe) * sizeof(float);
-        LMR_CUDA_OK(cudaFuncSetAttribute(l0_partial_kernel<50>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+        static size_t smem_set_l0 = 0;
+        if (smem0 > smem_set_l0) {
+            LMR_CUDA_OK(cudaFuncSetAttribute(l0_partial_kernel<50>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+            smem_set_l0 = smem0;
+        }
         l0_partial_kernel<50><<<wl.gridL0, 256, smem0, st>>>(a, l0part);
         LMR_LAUNCH_OK();
         const int blocks = (int)((nt.count() + 127) / 128);

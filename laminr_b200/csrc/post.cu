@@ -618,7 +618,11 @@ extern "C" int lmr_simclr_fwd(const float* img, const float* mask, int N, int C,
     const float c0 = (pmin + pmax) / 2, g1 = 2.f / (pmax - pmin), g2 = (pmax - pmin) / 2.f;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t smem1 = (size_t)N * (GCH + 1) * sizeof(float);
-    LMR_CUDA_OK(cudaFuncSetAttribute(simclr_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    static size_t smem_set = 0;
+    if (smem1 > smem_set) {
+        LMR_CUDA_OK(cudaFuncSetAttribute(simclr_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        smem_set = smem1;
+    }
     simclr_gram_kernel<<<S, 256, smem1, st>>>(img, mask, N, C, HW, c0, g1, g2, static_cast<float*>(ws));
     LMR_LAUNCH_OK();
     const size_t smem2 = ((size_t)2 * N * N + 5 * N) * sizeof(float);
@@ -658,7 +662,11 @@ extern "C" int lmr_mei_ascent(float* x, int G, int C, int HW, const float* filte
     const size_t smem = ((size_t)(C * HW + 3) / 4 * 4 + Fmax) * sizeof(float);
     LMR_CHECK_ARG(smem <= 200 * 1024, "mei: image of %d floats does not fit the shared-memory resident kernel", C * HW);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    LMR_CUDA_OK(cudaFuncSetAttribute(mei_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        LMR_CUDA_OK(cudaFuncSetAttribute(mei_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
     mei_kernel<<<G, MEI_THREADS, smem, st>>>(x, C, HW, filters, Fmax, nfilt, neuron_of_group, step_size, iters, mode, target, mean, pmin, pmax, act_eps,
                                             apply_post_first, fevals);
     LMR_LAUNCH_OK();

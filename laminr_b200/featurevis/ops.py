@@ -1,0 +1,55 @@
+"""Post-update operators of the MEI ascent (reference featurevis/ops.py:294-307,441-481): non-differentiable
+renormalisation (eps 1e-9) and range clipping, each one fused launch pair of lmr_constrain_fwd."""
+import torch
+
+from .. import _lib
+from .. import ops as _ops
+from .utils import varargin
+
+
+class ClipRange:
+    def __init__(self, x_min, x_max):
+        self.x_min, self.x_max = x_min, x_max
+
+    @varargin
+    def __call__(self, x):
+        return torch.clamp(x, self.x_min, self.x_max)
+
+
+class _Renorm:
+    mode = None
+
+    def _apply(self, x, target, mean, pmin=None, pmax=None):
+        with torch.no_grad():
+            z, _ = _ops.raw_constrain_fwd(self.mode, x.contiguous(), target, mean, pmin, pmax, 1e-9)
+        return z
+
+
+class ChangeNorm(_Renorm):
+    """x -> (x-mean)/(||x-mean|| + 1e-9) * norm + mean, per image."""
+    mode = _lib.MODE_NORM
+
+    def __init__(self, norm, mean=0):
+        self.norm, self.mean = norm, mean
+
+    @varargin
+    def __call__(self, x):
+        return self._apply(x, self.norm, self.mean)
+
+
+class ChangeStats(_Renorm):
+    """x -> (x-mu) * std/(std_unbiased(x) + 1e-9) + mean, per image."""
+    mode = _lib.MODE_STD
+
+    def __init__(self, std, mean):
+        self.std, self.mean = std, mean
+
+    @varargin
+    def __call__(self, x):
+        return self._apply(x, self.std, self.mean)
+
+
+class GaussianBlur:
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("laminr_b200: the GaussianBlur gradient preconditioner (gb= / gaussian_blur_sigma=) is a 'next' row "
+                                  "(SURVEY 8f-3); it is also broken in the reference on scipy >= 1.13")

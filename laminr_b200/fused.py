@@ -1,0 +1,217 @@
+"""Fused step drivers: the learn / match hot steps as a fixed sequence of C-ABI launches on static buffers.
+
+One `LearnStepper.step()` is the body of the reference's inner loop (laminr/inv_temp_learn_match.py:186-208: forward,
+objective, backward, Adam) without autograd, without per-step allocation or host synchronisation, optionally replayed
+from a CUDA graph.  `MatchStepper.step()` is the body of :351-366 for D targets, each neuron evaluated on its own
+images only (the reference evaluates all neurons on all D*N images and keeps the diagonal, :551,:361).
+"""
+import torch
+
+from . import _lib
+from . import ops
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+class _Constraint:
+    """(mode, target, mean, pmin, pmax, eps) of a FixEnergyNormClip / StandardizeClip module."""
+
+    def __init__(self, img_transf):
+        for k in ("mode", "target", "mean", "pixel_min", "pixel_max", "eps"):
+            if not hasattr(img_transf, k):
+                raise TypeError("fused path needs a laminr_b200 FixEnergyNormClip / StandardizeClip module")
+        self.mode, self.target, self.mean, self.eps = img_transf.mode, img_transf.target, img_transf.mean, img_transf.eps
+        self.pmin, self.pmax = img_transf.pixel_min, img_transf.pixel_max
+
+
+class LearnStepper:
+    def __init__(self, template, img_transf, model, neuron_idx, rf_mask, mei_act, grid_reg, pixel_min, pixel_max, n_grid, lr=1e-3,
+                 reg_scale=2.0, precision=None, use_graph=True):
+        lib = _lib.load()
+        import ctypes as C
+        self.t, self.model, self.reg_mod = template, model, grid_reg
+        self.con = _Constraint(img_transf)
+        dev = next(template.parameters()).device
+        self.dev, self.N, self.lr, self.precision = dev, int(n_grid), lr, precision
+        self.C, (H, W) = template.out_channels, template.img_res
+        self.P = H * W
+        N, Cc, P = self.N, self.C, self.P
+        self.pixel_min, self.pixel_max, self.mei_act = float(pixel_min), float(pixel_max), float(mei_act)
+        self.flat = template.flat_params()
+        self.coords = template.coords.reshape(-1, 2).contiguous()
+        self.mask = torch.as_tensor(rf_mask, dtype=torch.float32).to(dev).reshape(-1).contiguous()
+        self.nog = torch.tensor([int(neuron_idx)], dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.grid = torch.zeros(N, **f32)
+        self.img_pre = torch.empty((N, Cc, H, W), **f32)
+        self.z = torch.empty_like(self.img_pre)
+        self.g_z = torch.empty_like(self.img_pre)
+        self.g_x = torch.empty_like(self.img_pre)
+        self.stats = torch.empty((N, 2), **f32)
+        self.act, self.rmax = torch.empty((1, N), **f32), torch.empty((1, N), **f32)
+        self.argmax = torch.empty((1, N), dtype=torch.int32, device=dev)
+        self.reg, self.K = torch.empty(1, **f32), torch.empty((N, N), **f32)
+        self.g_act = torch.full((1, N), -1.0 / (N * self.mei_act), **f32)
+        self.g_reg = torch.full((1,), -float(reg_scale), **f32)  # d loss / d reg = -reg_scale (host float, changes between epochs)
+        self.g_flat = torch.zeros_like(self.flat)
+        self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        d = template._desc
+        self.ws_fwd = _ws(lib.lmr_inr_forward_workspace_bytes(C.byref(d), N, P, 1), dev)
+        self.ws_bwd = _ws(lib.lmr_inr_backward_workspace_bytes(C.byref(d), N, P, 1), dev)
+        self.ws_con = _ws(lib.lmr_constrain_workspace_bytes(N, Cc * P), dev)
+        self.ws_resp = _ws(lib.lmr_simresp_workspace_bytes(1, N, model.packed_filters.shape[1], P), dev)
+        self.ws_clr = _ws(lib.lmr_simclr_workspace_bytes(N, Cc, P), dev)
+        self.use_graph, self.graph, self.eval_graph = use_graph, None, None
+        self.kernels_per_step = 20
+
+    def set_reg_scale(self, reg_scale):
+        self.g_reg.fill_(-float(reg_scale))
+
+    # ---- launches -------------------------------------------------------------------------------------------------
+    def _forward(self):
+        t, c, N, Cc, P = self.t, self.con, self.N, self.C, self.P
+        ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, out=self.img_pre.view(1, N, Cc, P),
+                            precision=self.precision, workspace=self.ws_fwd)
+        ops.raw_constrain_fwd(c.mode, self.img_pre, c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.z, stats=self.stats, workspace=self.ws_con)
+        ops.raw_simresp_fwd(self.z, 0, N, 1, Cc, P, self.model.packed_filters, self.model.nfilt, self.nog, self.model.eps,
+                            out=(self.act, self.rmax, self.argmax), workspace=self.ws_resp)
+
+    def _train(self):
+        t, c, N, Cc, P = self.t, self.con, self.N, self.C, self.P
+        self._forward()
+        r = self.reg_mod
+        ops.raw_simclr_fwd(self.z, self.mask, N, Cc, P, self.pixel_min, self.pixel_max, r.flat_neighbor_mask_pos, r.flat_neighbor_mask_neg,
+                           r.temperature, r.eps, reg=self.reg, K=self.K, workspace=self.ws_clr)
+        ops.raw_simresp_bwd(self.g_act, self.rmax, self.argmax, 0, N, 1, Cc, P, self.model.packed_filters, self.nog, self.g_z, accumulate=False)
+        ops.raw_simclr_bwd(self.z, self.mask, self.K, self.g_reg, 1.0, N, Cc, P, self.pixel_min, self.pixel_max, self.g_z, accumulate=True)
+        ops.raw_constrain_bwd(c.mode, self.img_pre, self.g_z, self.stats, c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.g_x, workspace=self.ws_con)
+        ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, self.g_x.view(1, N, Cc, P), want_params=True,
+                             precision=self.precision, workspace=self.ws_bwd, g_params=self.g_flat)
+        ops.raw_adam_step(self.flat, self.g_flat, self.m, self.v, self.step_count, lr=self.lr)
+
+    def _capture(self, fn):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            fn()
+        return g
+
+    def step(self, grid_row):
+        """One optimisation step on the jittered latents `grid_row` ([N] device tensor)."""
+        self.grid.copy_(grid_row.reshape(-1), non_blocking=True)
+        if not self.use_graph:
+            self._train()
+        elif self.graph is None:
+            # the first step runs eagerly (it is also the warm-up that sets kernel attributes); capture afterwards
+            self._train()
+            self.graph = self._capture(self._train)  # stream capture records the launches without executing them
+        else:
+            self.graph.replay()
+
+    def evaluate(self, grid_row):
+        """No-grad forward: images and the template neuron's activations on `grid_row` (normalised by the MEI activation)."""
+        self.grid.copy_(grid_row.reshape(-1), non_blocking=True)
+        self._forward()
+        return self.act[0] / self.mei_act
+
+    def loss(self):
+        """loss of the last training step (device scalar): -mean(act/a*) - reg_scale * reg  (inv_temp_learn_match.py:204)."""
+        return -(self.act[0] / self.mei_act).mean() + self.g_reg[0] * self.reg[0]
+
+    def last_acts(self):
+        return self.act[0] / self.mei_act
+
+
+class MatchStepper:
+    def __init__(self, template, img_transf, model, target_idxs, mei_acts, n_grid, lr=1e-3, total_targets=None, precision=None, use_graph=True):
+        lib = _lib.load()
+        import ctypes as C
+        self.t, self.model = template, model
+        self.con = _Constraint(img_transf)
+        dev = next(template.parameters()).device
+        self.dev, self.N, self.lr, self.precision = dev, int(n_grid), lr, precision
+        self.C, (H, W) = template.out_channels, template.img_res
+        self.P, self.D = H * W, len(target_idxs)
+        N, D, Cc, P = self.N, self.D, self.C, self.P
+        self.Dtot = int(total_targets) if total_targets is not None else D  # loss = -sum_local / D_total (sharded match)
+        self.flat = template.flat_params()
+        self.coords = template.coords.reshape(-1, 2).contiguous()
+        self.nog = torch.as_tensor(list(target_idxs), dtype=torch.int32, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.mei_acts = torch.as_tensor(mei_acts, dtype=torch.float32).to(dev).reshape(D)
+        self.grid = torch.zeros(N, **f32)
+        self.img_pre = torch.empty((D, N, Cc, H, W), **f32)
+        self.z = torch.empty_like(self.img_pre)
+        self.g_z = torch.empty_like(self.img_pre)
+        self.g_x = torch.empty_like(self.img_pre)
+        self.stats = torch.empty((D * N, 2), **f32)
+        self.act, self.rmax = torch.empty((D, N), **f32), torch.empty((D, N), **f32)
+        self.argmax = torch.empty((D, N), dtype=torch.int32, device=dev)
+        self.g_act = (-1.0 / (N * self.Dtot * self.mei_acts))[:, None].expand(D, N).contiguous()
+        self.aff_mod = template.coordinate_transform.transforms.Affine
+        a = self.aff_mod
+        self.params = [p for p in (a.angles, a.scalings, a.shears, a.translation)]
+        self.trainable = [isinstance(p, torch.nn.Parameter) and p.requires_grad for p in self.params]
+        self.grads = [torch.zeros_like(p) for p in self.params]
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        self.steps = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in self.params]
+        d = template._desc
+        self.ws_fwd = _ws(lib.lmr_inr_forward_workspace_bytes(C.byref(d), N, P, D), dev)
+        self.ws_bwd = _ws(lib.lmr_inr_backward_workspace_bytes(C.byref(d), N, P, D), dev)
+        self.ws_con = _ws(lib.lmr_constrain_workspace_bytes(D * N, Cc * P), dev)
+        self.ws_resp = _ws(lib.lmr_simresp_workspace_bytes(D, N, model.packed_filters.shape[1], P), dev)
+        self.use_graph, self.graph = use_graph, None
+
+    def _affine(self):
+        return self.t.affine_args()
+
+    def _forward(self):
+        t, c, N, D, Cc, P = self.t, self.con, self.N, self.D, self.C, self.P
+        ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, self._affine(), out=self.img_pre.view(D, N, Cc, P),
+                            precision=self.precision, workspace=self.ws_fwd)
+        ops.raw_constrain_fwd(c.mode, self.img_pre.view(D * N, Cc, P), c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.z.view(D * N, Cc, P),
+                              stats=self.stats, workspace=self.ws_con)
+        ops.raw_simresp_fwd(self.z, N * Cc * P, N, D, Cc, P, self.model.packed_filters, self.model.nfilt, self.nog, self.model.eps,
+                            out=(self.act, self.rmax, self.argmax), workspace=self.ws_resp)
+
+    def _train(self):
+        t, c, N, D, Cc, P = self.t, self.con, self.N, self.D, self.C, self.P
+        self._forward()
+        ops.raw_simresp_bwd(self.g_act, self.rmax, self.argmax, N * Cc * P, N, D, Cc, P, self.model.packed_filters, self.nog, self.g_z, accumulate=False)
+        ops.raw_constrain_bwd(c.mode, self.img_pre.view(D * N, Cc, P), self.g_z.view(D * N, Cc, P), self.stats, c.target, c.mean, c.pmin, c.pmax, c.eps,
+                              out=self.g_x.view(D * N, Cc, P), workspace=self.ws_con)
+        ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, self._affine(), self.g_x.view(D, N, Cc, P),
+                             want_params=False, want_affine=True, precision=self.precision, workspace=self.ws_bwd,
+                             g_affine=(self.grads[0], self.grads[1], self.grads[2], self.grads[3].view(D, 2)))
+        for p, g, m, v, s, tr in zip(self.params, self.grads, self.m, self.v, self.steps, self.trainable):
+            if tr:
+                ops.raw_adam_step(p.data, g, m, v, s, lr=self.lr)
+
+    def step(self, grid_row):
+        self.grid.copy_(grid_row.reshape(-1), non_blocking=True)
+        if not self.use_graph:
+            self._train()
+        elif self.graph is None:
+            self._train()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):  # records the launches without executing them
+                self._train()
+        else:
+            self.graph.replay()
+
+    def evaluate(self, grid_row):
+        """No-grad forward on `grid_row`: act [D,N] of every target neuron on its own images."""
+        self.grid.copy_(grid_row.reshape(-1), non_blocking=True)
+        self._forward()
+        return self.act
+
+    def normalised_acts(self):
+        """acts_d = mean_n act[d,n] / a*_d of the last step (inv_temp_learn_match.py:362)."""
+        return self.act.mean(dim=1) / self.mei_acts

@@ -1,0 +1,1 @@
+from .mei import get_mei_dict  # noqa: F401

@@ -1,0 +1,213 @@
+"""GPU parity at the API level: the drop-in modules / fused steppers / public functions of laminr_b200 against the golden
+vectors of the unmodified reference and the numpy oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import laminr_oracle as O
+from tests._util import golden, relerr, flat_params, split_flat
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def L():
+    import laminr_b200
+    return laminr_b200
+
+
+def _meis(res, mask0=None, act=1.0000009536743164):
+    yy, xx = np.meshgrid(np.arange(res) + 0.5, np.arange(res) + 0.5, indexing="ij")
+    out = {}
+    for i, (cx, cy) in enumerate([(0.6 * res, 0.6 * res), (0.4 * res, 0.4 * res), (0.4 * res, 0.6 * res)]):
+        mask = np.exp(-0.5 * (((xx - cx) / (0.16 * res)) ** 2 + ((yy - cy) / (0.16 * res)) ** 2)).astype(np.float32)
+        out[i] = dict(mei=np.zeros((1, res, res), np.float32), activation=act, mask=mask, center_pos=dict(x=cx, y=cy))
+    if mask0 is not None:
+        out[0]["mask"] = mask0
+    return out
+
+
+def _manifold(L, res, d=None, prefix="", **kw):
+    model = L.neuron_models.simulated("demo1", img_res=[res, res]).cuda()
+    torch.manual_seed(0)
+    im = L.InvarianceManifold(model, _meis(res, None if d is None else d["mask"]), required_img_norm=1.0, pixel_value_lower_bound=-1.0,
+                              pixel_value_upper_bound=1.0, **kw)
+    if d is not None:
+        sd = {f"func.layer{l}.weight": torch.from_numpy(d[f"{prefix}W{l}"]) for l in range(5)}
+        sd.update({f"func.layer{l}.bias": torch.from_numpy(d[f"{prefix}b{l}"]) for l in range(5)})
+        sd.update(B=torch.from_numpy(d[f"{prefix}B"]), auxB=torch.from_numpy(d[f"{prefix}auxB"]))
+        im.template.load_state_dict(sd, strict=False)
+    return model, im
+
+
+def test_autograd_learn_step_matches_reference(L):
+    """The generic (autograd) composition of the drop-in modules reproduces the reference's loss and parameter gradients."""
+    from laminr_b200.contrastive_loss import SimCLROnGrid
+    from laminr_b200.utils.general import SingleNeuronModel
+    d = golden("learn_step_20")
+    model, im = _manifold(L, 20, d)
+    grid = torch.from_numpy(d["grid"]).reshape(-1, 1).cuda()
+    reg = SimCLROnGrid(1, 20, 0.1, 0.3, True).cuda()
+    img_pre, img_post, _acts, _ = im.forward(grid, im.template, im.img_transforms, SingleNeuronModel(model, 0), return_template=True)
+    assert img_pre.shape == (20, 1, 20, 20) and _acts.shape == (20, 1)
+    acts = _acts / float(d["mei_act"])
+    sim = reg.masked_reg_term(img_post, torch.from_numpy(d["mask"]).cuda(), -1.0, 1.0)
+    loss = -acts.mean() - 2 * sim
+    loss.backward()
+    assert abs(loss.item() - d["loss"]) < 3e-5 * abs(d["loss"])
+    assert relerr(img_post.detach().cpu().numpy().reshape(20, -1), d["img_post"]) < 3e-5
+    for l in range(5):
+        lay = getattr(im.template.func, f"layer{l}")
+        assert relerr(lay.weight.grad.cpu().numpy(), d[f"dW{l}"]) < 3e-3, l
+        assert relerr(lay.bias.grad.cpu().numpy(), d[f"db{l}"]) < 3e-3, l
+    # the all-neuron forward of the packed model agrees with per-neuron evaluation
+    full = model(img_post.detach())
+    assert full.shape == (20, 3)
+    assert torch.allclose(full[:, 0], _acts[:, 0].detach(), rtol=1e-6, atol=1e-7)
+    # reg_term on pre-masked images == masked_reg_term
+    from laminr_b200.utils.mask import apply_mask
+    sim2 = reg.reg_term(apply_mask(img_post.detach(), torch.from_numpy(d["mask"]).cuda(), -1.0, 1.0))
+    assert abs(sim2.item() - sim.item()) < 1e-6
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_fused_learn_trajectory_matches_reference(L, use_graph):
+    """30 Adam steps of the fused stepper from the reference's initial network and jitter stream: per-step loss within 1e-3
+    relative (north star), final parameters within 1e-2 relative."""
+    from laminr_b200.contrastive_loss import SimCLROnGrid
+    from laminr_b200.fused import LearnStepper
+    d = golden("learn_traj_20")
+    model, im = _manifold(L, 20, d, prefix="init_")
+    reg = SimCLROnGrid(1, 20, 0.1, 0.3, True).cuda()
+    st = LearnStepper(im.template, im.img_transforms, model, 0, d["mask"], 1.0000009536743164, reg, -1.0, 1.0, 20, lr=1e-3, reg_scale=2.0,
+                      use_graph=use_graph)
+    grids = torch.from_numpy(d["grids"]).cuda()
+    losses, means = [], []
+    for i in range(30):
+        st.step(grids[i])
+        losses.append(st.loss().item())
+        means.append(st.last_acts().mean().item())
+    np.testing.assert_allclose(losses, d["losses"], rtol=1e-3)
+    np.testing.assert_allclose(means, d["means"], rtol=1e-3)
+    assert max(abs(a - b) / abs(b) for a, b in zip(losses, d["losses"])) < 2e-4  # what fp32 achieves
+    assert st.step_count.item() == 30
+    dW, db = split_flat(st.flat.cpu().numpy(), d, prefix="final_")
+    for l in range(5):
+        assert relerr(dW[l], d[f"final_W{l}"]) < 1e-2, l
+        assert relerr(dW[l], d[f"final_W{l}"]) < 2e-3, l
+    # the nn.Parameters are views of the flat vector the kernels updated
+    assert torch.equal(im.template.func.layer1.weight.detach().reshape(-1), st.flat[50 * 201 + 50:50 * 201 + 50 + 2500])
+
+
+def test_learn_api_fused_equals_generic(L):
+    """InvarianceManifold.learn: the fused path and the generic autograd path (user-style nn.Module model) walk the same trajectory."""
+    class PlainModel(torch.nn.Module):  # a user-supplied response model: stock PyTorch ops, same maths as the simulated population
+        def __init__(self, banks):
+            super().__init__()
+            self.banks = torch.nn.ParameterList([torch.nn.Parameter(b, requires_grad=False) for b in banks])
+
+        def forward(self, x):
+            outs = []
+            for b in self.banks:
+                r = torch.einsum("bchw,fhw->bf", x, b).max(dim=1)[0]
+                outs.append((torch.nn.functional.elu(r) + 1) / 2 + 1e-6)
+            return torch.stack(outs, 1)
+
+    res = 16
+    results = []
+    for kind in ("fused", "generic"):
+        model = L.neuron_models.simulated("demo1", img_res=[res, res]).cuda()
+        if kind == "generic":
+            model = PlainModel([m.filters.clone() for m in model.neuron_models_list]).cuda()
+        torch.manual_seed(3)
+        im = L.InvarianceManifold(model, _meis(res), required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+        imgs, acts = im.learn(0, steps_per_epoch=4, num_max_epochs=3, min_epochs=0)
+        assert imgs.shape == (20, 1, res, res) and acts.shape == (20,)
+        assert im.learn_steps_taken == 12
+        results.append((imgs, acts, im.template.flat_params().cpu().numpy()))
+    assert relerr(results[0][2], results[1][2]) < 1e-4
+    assert relerr(results[0][0], results[1][0]) < 1e-3
+    assert relerr(results[0][1], results[1][1]) < 1e-4
+    # FixEnergyNorm known answer: ||img - mean|| == norm where nothing was clipped
+    n = np.linalg.norm(results[0][0].reshape(20, -1), axis=1)
+    assert np.all(n <= 1.0 + 1e-5)
+
+
+def test_match_api_fused_equals_generic_and_reference_step(L):
+    d = golden("match_step_20")
+    outs = []
+    for fused in (True, False):
+        model, im = _manifold(L, 20, d)
+        if not fused:
+            im._fused_ok = lambda gaussian_blur=None: False
+        im.template_neuron_idx = 0
+        torch.manual_seed(5)
+        imgs, acts = im.match([1, 2], num_epochs=6, patience=15)
+        assert imgs.shape == (2, 20, 1, 20, 20) and acts.shape == (2, 20)
+        aff = im.template.coordinate_transform.transforms.Affine
+        outs.append((imgs, acts, [p.detach().cpu().numpy().copy() for p in (aff.angles, aff.scalings, aff.shears, aff.translation)]))
+        assert im.match_steps_taken == 6
+    for a, b in zip(outs[0][2], outs[1][2]):
+        np.testing.assert_allclose(a, b, rtol=2e-4, atol=2e-6)
+    assert relerr(outs[0][0], outs[1][0]) < 2e-3
+    assert relerr(outs[0][1], outs[1][1]) < 1e-4
+    # scalings were initialised to 1 / (mask-size fraction) on both axes (inv_temp_learn_match.py:591,619)
+    m = _meis(20, d["mask"])
+    frac = np.array([m[k]["mask"].sum() / m[0]["mask"].sum() for k in (1, 2)])
+    assert np.allclose(outs[0][2][1], (1 / frac)[:, None], rtol=0.02)  # six Adam steps of 1e-3 later
+
+
+def test_get_mei_dict_known_answer(L):
+    """demo1 filters are unit-norm and images are constrained to norm 1, so the MEI activation is (elu(1)+1)/2 + 1e-6
+    (the reference measures 1.0000009536743164 for all three neurons)."""
+    model = L.neuron_models.simulated("demo1", img_res=[100, 100]).cuda()
+    torch.manual_seed(0)
+    np.random.seed(0)
+    meis = L.get_mei_dict(model, [1, 100, 100], -1.0, 1.0, required_img_norm=1.0)
+    assert sorted(meis) == [0, 1, 2]
+    for k, v in meis.items():
+        assert v["mei"].shape == (1, 100, 100) and v["mask"].shape == (100, 100)
+        assert abs(v["activation"] - 1.0000009536743164) < 2e-6, v["activation"]
+        assert abs(np.linalg.norm(v["mei"]) - 1.0) < 1e-5
+    # RF centres land on the filter centres of demo1: loc (0.2,0.2) -> pixel (60,60); (-0.2,-0.2) -> (40,40); (-0.2,0.2) -> x 40, y 60
+    for k, (x, y) in {0: (60, 60), 1: (40, 40), 2: (40, 60)}.items():
+        assert abs(meis[k]["center_pos"]["x"] - x) < 4 and abs(meis[k]["center_pos"]["y"] - y) < 4, (k, meis[k]["center_pos"])
+
+
+def test_generic_mei_path_matches_batched_kernel(L):
+    """featurevis.gradient_ascent (generic autograd path) == lmr_mei_ascent on the same start image."""
+    from laminr_b200 import featurevis
+    from laminr_b200.featurevis import ops as fops
+    from laminr_b200.utils.general import SingleNeuronModel
+    from laminr_b200.utils.mei import batched_simulated_meis
+    d = golden("mei")
+    model = L.neuron_models.simulated("demo1", img_res=[16, 16]).cuda()
+    x0 = torch.from_numpy(d["norm_x0_1"]).cuda()
+    post = featurevis.Compose([fops.ChangeNorm(norm=1.0, mean=0.0), fops.ClipRange(-1.0, 1.0)])
+    x, fevals, _ = featurevis.gradient_ascent(SingleNeuronModel(model, 1), post(x0), step_size=10, num_iterations=60, post_update=post, print_iters=1001)
+    assert len(fevals) == 61
+    np.testing.assert_allclose(fevals, d["norm_fevals_1"], rtol=5e-5)
+    xb, fb = batched_simulated_meis(model, [1], x0, -1.0, 1.0, norm=1.0, step_size=10, num_iterations=60)
+    np.testing.assert_allclose(fb[0].cpu().numpy(), fevals, rtol=2e-5)
+    assert relerr(xb.cpu().numpy(), x.cpu().numpy()) < 1e-4
+
+
+def test_state_dict_round_trip_and_getters(L):
+    model, im = _manifold(L, 16)
+    sd = {k: v.clone() for k, v in im.template.state_dict().items()}
+    imgs = im.get_images_from_learned_template(n_images=7)
+    assert imgs.shape == (7, 1, 16, 16)
+    model2, im2 = _manifold(L, 16)
+    with torch.no_grad():
+        for p in im2.template.parameters():
+            p.add_(1.0)
+    im2.template.load_state_dict(sd)
+    np.testing.assert_array_equal(im2.get_images_from_learned_template(n_images=7), imgs)
+    im.template_neuron_idx = 0
+    im.match([2], num_epochs=2)
+    out = im.get_images_from_matched_template(2, n_images=5)
+    assert out.shape == (5, 1, 16, 16)
+    with pytest.raises(ValueError):
+        im.get_images_from_matched_template(1)
+    with pytest.raises(ValueError):
+        im.get_images_from_matched_template("2")

@@ -1,0 +1,185 @@
+"""CPU: host-side logic of the product (no kernels are launched): library exports, RNG-parity of constructors and the
+jittered-grid stream, filter banks, control logic, error behaviour."""
+import ctypes
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests._util import golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from laminr_b200.csrc import build
+    build.build()
+    import laminr_b200
+    return laminr_b200
+
+
+def test_library_exports_every_header_symbol(L):
+    from laminr_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "laminr_b200.h")).read()
+    declared = set(re.findall(r"\b(lmr_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 19
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert set(_lib.SIGNATURES) == declared
+    assert lib.lmr_abi_version() == 1
+
+
+def test_no_cpu_fallback(L):
+    """ops refuse CPU tensors instead of silently computing something else."""
+    from laminr_b200 import ops
+    x = torch.zeros(2, 1, 4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.raw_constrain_fwd(0, x, 1.0, 0.0, -1.0, 1.0, 1e-12)
+    m = L.neuron_models.simulated("demo1", img_res=[8, 8])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 1, 8, 8))
+
+
+def test_demo1_banks_bit_identical_to_reference(L):
+    d = golden("banks")
+    for res in (100, 200):
+        m = L.neuron_models.simulated("demo1", img_res=[res, res])
+        for i, sub in enumerate(m.neuron_models_list):
+            f = sub.filters.numpy()
+            assert tuple(d[f"shape_{res}_{i}"]) == f.shape
+            assert hashlib.sha256(f.tobytes()).digest() == d[f"sha_{res}_{i}"].tobytes(), (res, i)
+    assert m.packed_filters.shape == (3, 60, 200 * 200) and m.nfilt.tolist() == [20, 20, 60]
+    # ragged banks are padded by repeating a filter
+    assert torch.equal(m.packed_filters[0, 20:], m.packed_filters[0, :1].expand(40, -1))
+    pop = L.neuron_models.simulated_population(4, img_res=[100, 100], seed=0)
+    got = np.stack([s.filters.numpy() for s in pop.neuron_models_list])
+    assert hashlib.sha256(got.tobytes()).digest() == d["pop4_sha"].tobytes()
+    with pytest.raises(ValueError):
+        L.neuron_models.simulated("nope")
+
+
+def _meis(res):
+    return {i: dict(mei=np.zeros((1, res, res), np.float32), activation=1.0, mask=np.ones((res, res), np.float32), center_pos=dict(x=res / 2, y=res / 2))
+            for i in range(3)}
+
+
+def test_constructor_consumes_rng_like_the_reference(L):
+    """torch.manual_seed(0); InvarianceManifold(...) must give the reference's initial network (inr.py:49-51 draw order)."""
+    d = golden("learn_traj_20")
+    m = L.neuron_models.simulated("demo1", img_res=[20, 20])
+    torch.manual_seed(0)
+    im = L.InvarianceManifold(m, _meis(20), device="cpu", required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+    sd = im.template.state_dict()
+    for l in range(5):
+        np.testing.assert_array_equal(sd[f"func.layer{l}.weight"].numpy(), d[f"init_W{l}"])
+        np.testing.assert_array_equal(sd[f"func.layer{l}.bias"].numpy(), d[f"init_b{l}"])
+    np.testing.assert_array_equal(sd["B"].numpy(), d["init_B"])
+    np.testing.assert_array_equal(sd["auxB"].numpy(), d["init_auxB"])
+    np.testing.assert_array_equal(sd["coords"].numpy().reshape(-1, 2), d["init_coords"])
+    assert sum(p.numel() for p in im.template.parameters()) == 17801 and im.template.in_dim == 201
+    # the parameters are views of one flat vector, in func.parameters() order
+    flat = im.template.flat_params()
+    assert flat.numel() == 17801
+    np.testing.assert_array_equal(flat[:50 * 201].numpy().reshape(50, 201), d["init_W0"])
+    flat[0] = 123.0
+    assert im.template.func.layer0.weight[0, 0].item() == 123.0
+    with pytest.raises(ValueError):
+        L.InvarianceManifold(m, _meis(20), device="cpu", pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+    with pytest.raises(ValueError):
+        L.InvarianceManifold(m, _meis(20), device="cpu", required_img_norm=1.0, required_img_std=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+
+
+def test_jittered_grid_stream_matches_reference(L):
+    from laminr_b200.utils.training import JitteringGridDatamodule
+    d = golden("training_utils")
+    for n in (20, 7, 32):
+        np.testing.assert_array_equal(JitteringGridDatamodule(1, n, 3).grid[:, 0].numpy(), d[f"grid_{n}"])
+    torch.manual_seed(4)
+    dm = JitteringGridDatamodule(1, 20, 5)
+    batches = torch.stack(list(dm.train_dataloader()))
+    np.testing.assert_array_equal(batches[:, :, 0].numpy(), d["jitter_batches"])
+    t = golden("learn_traj_20")
+    torch.manual_seed(123)
+    dm = JitteringGridDatamodule(1, 20, 30)
+    np.testing.assert_array_equal(torch.stack(list(dm.train_dataloader()))[:, :, 0].numpy(), t["grids"])
+
+
+def test_iterating_consumes_the_dataloader_seed_draw(L):
+    """DataLoader.__iter__ draws one int64 from the CPU generator; our iterable must leave the generator in the same state."""
+    from torch.utils.data import DataLoader
+    from laminr_b200.utils.training import JitteringGridDatamodule
+    torch.manual_seed(7)
+    dm = JitteringGridDatamodule(1, 20, 4)
+    for _ in dm.train_dataloader():
+        pass
+    ours = torch.rand(3)
+    torch.manual_seed(7)
+    jitter = torch.rand([4, 1]) * dm.sigma - 0.5 * dm.sigma
+    grids = dm.base_grid + jitter.repeat_interleave(20, dim=0)
+    for _ in DataLoader(grids, batch_size=20):
+        pass
+    assert torch.equal(ours, torch.rand(3))
+
+
+def test_control_logic_traces(L):
+    from laminr_b200.utils.training import ImprovementChecker, ParamReduceOnPlateau, check_activity_requirements
+    d = golden("training_utils")
+    sch = ParamReduceOnPlateau(factor=0.8, patience=5, threshold=0.005, mode="max")
+    val, vals = 2.0, []
+    for s in d["plateau_seq"]:
+        val = sch.step(torch.tensor(s), val)
+        vals.append(val)
+    np.testing.assert_array_equal(np.array(vals), d["plateau_vals"])
+    chk = ImprovementChecker(patience=4, ignore_diff_smaller_than=1e-3)
+    np.testing.assert_array_equal(np.array([chk.is_increasing(float(s)) for s in d["plateau_seq"]]), d["improve_flags"])
+    req = dict(avg=0.99, std=1.0, necessary_min=0.98)
+    np.testing.assert_array_equal(np.array([check_activity_requirements(torch.tensor(a), req) for a in d["req_acts"]]), d["req_pass"])
+
+
+def test_neighbour_masks(L):
+    from laminr_b200.contrastive_loss import SimCLROnGrid
+    d = golden("simclr")
+    for tag, n, periodic, nb in (("p20", 20, True, 0.1), ("np7", 7, False, 0.3), ("p10", 10, True, 0.1)):
+        reg = SimCLROnGrid(1, n, nb, 0.3, periodic)
+        np.testing.assert_array_equal(reg.flat_neighbor_mask_pos.numpy(), d[f"{tag}_pos"])
+        np.testing.assert_array_equal(reg.flat_neighbor_mask_neg.numpy(), d[f"{tag}_neg"])
+
+
+def test_affine_parameter_names_and_init(L):
+    from laminr_b200.inr import INRTemplates
+    from torch import nn
+    t = INRTemplates((8, 8), widths=[50] * 4, periodic_invariance=True, positional_encoding_dim=50, positional_encoding_projection_scale=10,
+                     aux_positional_encoding_dim=50, aux_positional_encoding_projection_scale=0.1, final_nonlinearity=nn.Tanh, bias=True, weights_scale=0.1)
+    t.initialize_coordinate_transform(3, True, False, 0.1, True, True, False, True)
+    keys = set(t.state_dict())
+    for k in ("angles", "scalings", "shears", "translation"):
+        assert f"coordinate_transform.transforms.Affine.{k}" in keys
+    aff = t.coordinate_transform.transforms.Affine
+    assert aff.translation.shape == (3, 1, 2) and torch.all(aff.scalings == 1) and torch.all(aff.angles == 0)
+    assert torch.allclose(aff.As, torch.eye(2).expand(3, 2, 2))
+    t.register_coords_shifts(torch.tensor([5.0, 3.0]), torch.tensor([[2.0, 6.0], [4.0, 4.0], [1.0, 1.0]]))
+    assert {"coords_shift_to_center", "template_center_in_coords_space", "coords_shift_from_center"} <= set(t.state_dict())
+    with pytest.raises(NotImplementedError):
+        t.initialize_coordinate_transform(3, False, False, 0.1, True, True, False, True)  # RealNVP warp: out of scope
+
+
+def test_mei_argument_errors(L):
+    m = L.neuron_models.simulated("demo1", img_res=[8, 8])
+    with pytest.raises(ValueError, match="Either std or norm"):
+        L.get_mei_dict(m, [1, 8, 8], -1.0, 1.0, neuron_idxs=[0])
+    with pytest.raises(ValueError, match="Only one"):
+        L.get_mei_dict(m, [1, 8, 8], -1.0, 1.0, neuron_idxs=[0], required_img_std=1.0, required_img_norm=1.0)
+
+
+def test_create_mask_centroid(L):
+    from laminr_b200.utils.mask import create_mask
+    yy, xx = np.meshgrid(np.arange(40), np.arange(40), indexing="ij")
+    mei = (np.exp(-0.5 * (((xx - 25) / 4.0) ** 2 + ((yy - 12) / 4.0) ** 2)) * np.cos(0.9 * (xx - 25))).astype(np.float32)  # Gabor-like, zero-mean
+    mask, c = create_mask(torch.from_numpy(mei), zscore_thresh=0.3, return_mask_centroid=True)
+    assert mask.shape == (40, 40) and abs(c["x"] - 25.5) < 1.0 and abs(c["y"] - 12.5) < 1.0
+    assert float(mask.max()) <= 1.0 + 1e-6 and float(mask[12, 25]) > 0.95 and float(mask[35, 3]) < 1e-3
