@@ -30,7 +30,7 @@ def _meis(res, mask0=None, act=1.0000009536743164):
 def _manifold(L, res, d=None, prefix="", **kw):
     model = L.neuron_models.simulated("demo1", img_res=[res, res]).cuda()
     torch.manual_seed(0)
-    im = L.InvarianceManifold(model, _meis(res, None if d is None else d["mask"]), required_img_norm=1.0, pixel_value_lower_bound=-1.0,
+    im = L.InvarianceManifold(model, _meis(res, None if d is None else d.get("mask")), required_img_norm=1.0, pixel_value_lower_bound=-1.0,
                               pixel_value_upper_bound=1.0, **kw)
     if d is not None:
         sd = {f"func.layer{l}.weight": torch.from_numpy(d[f"{prefix}W{l}"]) for l in range(5)}
@@ -152,7 +152,7 @@ def test_match_api_fused_equals_generic_and_reference_step(L):
     assert relerr(outs[0][0], outs[1][0]) < 2e-3
     assert relerr(outs[0][1], outs[1][1]) < 1e-4
     # scalings were initialised to 1 / (mask-size fraction) on both axes (inv_temp_learn_match.py:591,619)
-    m = _meis(20, d["mask"])
+    m = _meis(20)
     frac = np.array([m[k]["mask"].sum() / m[0]["mask"].sum() for k in (1, 2)])
     assert np.allclose(outs[0][2][1], (1 / frac)[:, None], rtol=0.02)  # six Adam steps of 1e-3 later
 
