@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- INR opt steps/sec of `InvarianceManifold.learn` on demo1 @ 100x100 (BASELINE.json metric), B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--res 100] [--precision fp32|tf32|bf16x3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--res 100] [--precision fp32|bf16x3|bf16x3_fast]
 
 One "step" is one pass of the learn hot path (reference laminr/inv_temp_learn_match.py:186-208): INR forward over
 20 latents x HxW pixels, constraint projection, template-neuron response, masked contrastive term, backward, Adam.
@@ -367,7 +367,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--res", type=int, default=100)
-    ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32", "bf16x3"])
+    ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16x3", "bf16x3_fast"])
     ap.add_argument("--match-targets", type=int, default=32, help="targets per GPU for the extra match measurement (0 = skip)")
     ap.add_argument("--match-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")

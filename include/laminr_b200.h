@@ -36,8 +36,9 @@ typedef enum {
 /* arithmetic mode of the INR MLP hidden layers */
 typedef enum {
     LMR_PREC_FP32 = 0,        /* CUDA-core fp32 FMA, tanhf: the bit-tight parity path */
-    LMR_PREC_TF32 = 1,        /* tcgen05 kind::tf32, fp32 accumulate in TMEM; layer 0 / output layer stay fp32 */
-    LMR_PREC_BF16X3 = 2       /* tcgen05 kind::f16 error-compensated split-bf16 (hi*hi + lo*hi + hi*lo) */
+    LMR_PREC_BF16X3_FAST = 1, /* as BF16X3 but tanh = MUFU tanh.approx.f32 (2^-11 relative error): the throughput mode */
+    LMR_PREC_BF16X3 = 2       /* tcgen05 kind::f16, error-compensated split-bf16 operands (hi*hi + lo*hi + hi*lo), fp32 accumulate in
+                                 TMEM, tanh from ex2/rcp (~1e-7): fp32-class results; layer 0 and the output layer stay on CUDA cores */
 } lmr_precision;
 
 typedef enum { LMR_CONSTRAIN_NORM = 0, LMR_CONSTRAIN_STD = 1 } lmr_constrain_mode;

@@ -5,7 +5,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblaminr_b200.so")
 
-PREC_FP32, PREC_TF32, PREC_BF16X3 = 0, 1, 2
+PREC_FP32, PREC_BF16X3_FAST, PREC_BF16X3 = 0, 1, 2
 MODE_NORM, MODE_STD = 0, 1
 
 

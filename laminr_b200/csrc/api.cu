@@ -79,7 +79,7 @@ extern "C" int lmr_inr_forward(const lmr_inr_desc* desc, const float* params, co
                                size_t ws_bytes, int precision, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (precision == LMR_PREC_FP32) return simt::forward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, img, ws, ws_bytes, st);
-    if (precision == LMR_PREC_TF32 || precision == LMR_PREC_BF16X3)
+    if (precision == LMR_PREC_BF16X3_FAST || precision == LMR_PREC_BF16X3)
         return tc::forward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, img, ws, ws_bytes, precision, st);
     set_error("inr_forward: unknown precision %d", precision);
     return LMR_ERR_INVALID;
@@ -93,7 +93,7 @@ extern "C" int lmr_inr_backward(const lmr_inr_desc* desc, const float* params, c
     if (precision == LMR_PREC_FP32)
         return simt::backward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, g_img, g_params, g_angles, g_scalings, g_shears,
                               g_translation, ws, ws_bytes, st);
-    if (precision == LMR_PREC_TF32 || precision == LMR_PREC_BF16X3)
+    if (precision == LMR_PREC_BF16X3_FAST || precision == LMR_PREC_BF16X3)
         return tc::backward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, g_img, g_params, g_angles, g_scalings, g_shears,
                             g_translation, ws, ws_bytes, precision, st);
     set_error("inr_backward: unknown precision %d", precision);

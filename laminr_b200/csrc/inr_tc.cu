@@ -1,20 +1,704 @@
-// INR generator, tcgen05 tensor-core path (LMR_PREC_TF32 / LMR_PREC_BF16X3).  Placeholder until the kernels land.
-#include "common.cuh"
+// INR generator, tcgen05 tensor-core path (LMR_PREC_BF16X3 / LMR_PREC_BF16X3_FAST): forward and recompute-backward.
+//
+// Same tiling and layer-0 separability as inr_simt.cu (a tile = TP pixels x N latents <= 128 rows of one target,
+// thread t <-> row t <-> TMEM lane t).  The 50x50 hidden layers run on the 5th-gen tensor cores:
+//   * operands are error-compensated split-bf16: x = hi + lo (bf16 each), products hi*hi + lo*hi + hi*lo (3 tcgen05.mma,
+//     kind::f16, fp32 accumulate in TMEM) -> ~2^-16 relative operand error, fp32-class results (precision probe);
+//   * activation tiles [128 rows x 64 features] live in shared memory in the canonical no-swizzle core-matrix layout
+//     (tc_common.cuh); feature 50 is the constant 1 so the bias is a column of the weight tile and the bias gradient a
+//     column of the weight-gradient accumulator;
+//   * forward      z_l   = h_l W_l^T        A = h tile (K-major),    B = W_l tile (K-major)           M=128 N=64 K=64
+//     data grad    dh_l  = dz_l W_l         A = dz tile (K-major),   B = W_l tile read MN-major       M=128 N=64 K=64
+//     weight grad  dW_l += dz_l^T h_l       A = dz tile read MN-major, B = h tile read MN-major       M=64  N=64 K=128
+//     -- the transposed products reuse the SAME bytes through MN-major descriptors (no transposed copies);
+//   * weight-gradient accumulators stay resident in TMEM across all tiles of the persistent CTA (3 x 64 columns + 16);
+//   * nothing is stored between forward and backward: the backward recomputes the forward per tile (5 tiles of smem).
+// The weight-gradient MMAs of a layer overlap with the epilogue that produces the next dz tile (rotating 5 tile buffers).
+#include <cuda_bf16.h>
+
+#include "inr_common.cuh"
+#include "tc_common.cuh"
 
 namespace lmr {
 namespace tc {
 
-int forward(const lmr_inr_desc*, const float*, const float*, const float*, const float*, int, const float*, int, const float*, const lmr_affine*, int,
-            float*, void*, size_t, int, cudaStream_t) {
-    set_error("inr_forward: tensor-core precision modes are not built yet");
-    return LMR_ERR_INVALID;
+using namespace lmr::inr;
+using namespace lmr::tcx;
+
+constexpr int HID = 50;               // hidden width served by this path
+constexpr int HPAD = 64;              // padded feature count of a tile (K and N of the MMAs)
+constexpr int ONE_COL = 50;           // feature slot holding the constant 1 (bias column)
+constexpr int TP_CAP_TC = 8;          // pixels per tile cap (bounds the per-tile scratch)
+constexpr int TILE_HALF = 128 * HPAD * 2;   // bytes of the hi (or lo) half of an activation tile
+constexpr int TILE_BYTES = 2 * TILE_HALF;   // 32 KB
+constexpr int WT_HALF = HPAD * HPAD * 2;    // 8 KB
+constexpr int WT_BYTES = 2 * WT_HALF;       // 16 KB
+constexpr int DY_HALF = 128 * 8 * 2;        // dy tile: 128 rows x 8 channels(padded), hi / lo
+constexpr int MAXL = 8;
+
+// TMEM columns
+constexpr uint32_t TM_ACC = 0;        // [128 lanes x 64]  forward / data-gradient accumulator
+constexpr uint32_t TM_DW = 64;        // (L-1) x [64 lanes(M=64 layout) x 64] weight-gradient accumulators
+constexpr uint32_t TM_COLS = 512;
+
+template <bool FAST>
+__device__ __forceinline__ float act_tanh(float x) {
+    return FAST ? tanh_mufu(x) : tanh_ex2(x);
 }
-int backward(const lmr_inr_desc*, const float*, const float*, const float*, const float*, int, const float*, int, const float*, const lmr_affine*, int,
-             const float*, float*, float*, float*, float*, float*, void*, size_t, int, cudaStream_t) {
-    set_error("inr_backward: tensor-core precision modes are not built yet");
-    return LMR_ERR_INVALID;
+
+// split 8 floats into bf16 hi / lo and store the two 16-byte chunks of row r, feature chunk c
+__device__ __forceinline__ void store_chunk(uint8_t* tile, int r, int c, const float* v) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+        const float2 hf = __bfloat1622float2(h2);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * q] - hf.x, v[2 * q + 1] - hf.y);
+        hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
+        lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    const uint32_t off = tile_off(r, c, 128);
+    *reinterpret_cast<uint4*>(tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(tile + TILE_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
-size_t workspace_bytes(const lmr_inr_desc*, int, int, int, bool) { return 0; }
+
+// read back 8 features (hi + lo) of row r, chunk c
+__device__ __forceinline__ void load_chunk(const uint8_t* tile, int r, int c, float* v) {
+    const uint32_t off = tile_off(r, c, 128);
+    const uint4 h = *reinterpret_cast<const uint4*>(tile + off);
+    const uint4 l = *reinterpret_cast<const uint4*>(tile + TILE_HALF + off);
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hh[q]));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ll[q]));
+        v[2 * q] = a.x + b.x, v[2 * q + 1] = a.y + b.y;
+    }
+}
+__device__ __forceinline__ float load_elem(const uint8_t* tile, int r, int f) {
+    const uint32_t off = tile_off(r, f >> 3, 128) + (f & 7) * 2;
+    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + off)) +
+           __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + TILE_HALF + off));
+}
+
+struct TcSmem {
+    uint8_t* tiles;   // ntiles x TILE_BYTES
+    uint8_t* wt;      // (L-1) x WT_BYTES
+    uint8_t* dy;      // 2 x DY_HALF
+    float *Cp, *beta, *Wout, *bout, *affc, *G0s;
+    uint64_t* bars;   // [0] accumulator ready, [1] all MMAs of the tile done
+    uint32_t* tmem;
+    size_t bytes;
+    __host__ __device__ TcSmem(uint8_t* base, const Net& nt, const Tiling& tl, int ntiles) {
+        uint8_t* p = base;
+        auto take = [&](size_t n) {
+            uint8_t* r = p;
+            p += (n + 127) / 128 * 128;
+            return r;
+        };
+        tiles = take((size_t)ntiles * TILE_BYTES);
+        wt = take((size_t)(nt.nl - 1) * WT_BYTES);
+        dy = take(2 * DY_HALF);
+        Cp = reinterpret_cast<float*>(take((size_t)tl.TP * SHP * 4));
+        beta = reinterpret_cast<float*>(take((size_t)tl.TP * 2 * nt.pe * 4));
+        Wout = reinterpret_cast<float*>(take((size_t)nt.C * HPAD * 4));
+        bout = reinterpret_cast<float*>(take(16));
+        affc = reinterpret_cast<float*>(take(48));
+        G0s = reinterpret_cast<float*>(take((size_t)tl.TP * SHP * 4));
+        bars = reinterpret_cast<uint64_t*>(take(16));
+        tmem = reinterpret_cast<uint32_t*>(take(16));
+        bytes = p - base;
+    }
+};
+
+// weights of hidden layers 1..L-1 as split-bf16 K-major tiles: W_l[o][k] for k < 50, column 50 = bias b_l[o], rest 0
+__device__ inline void load_weight_tiles(const Args& a, TcSmem& s) {
+    const Net& nt = a.net;
+    for (int l = 1; l < nt.nl; ++l) {
+        const float* W = a.params + nt.offW(l);
+        const float* b = a.params + nt.offb(l);
+        uint8_t* dst = s.wt + (size_t)(l - 1) * WT_BYTES;
+        for (int i = threadIdx.x; i < HPAD * HPAD; i += blockDim.x) {
+            const int o = i / HPAD, k = i % HPAD;
+            float v = 0.f;
+            if (o < HID) v = k < HID ? W[o * HID + k] : (k == ONE_COL ? b[o] : 0.f);
+            const __nv_bfloat16 hi = __float2bfloat16(v);
+            const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
+            const uint32_t off = tile_off(o, k >> 3, HPAD) + (k & 7) * 2;
+            *reinterpret_cast<__nv_bfloat16*>(dst + off) = hi;
+            *reinterpret_cast<__nv_bfloat16*>(dst + WT_HALF + off) = lo;
+        }
+    }
+    const float* Wo = a.params + nt.offWout();
+    for (int i = threadIdx.x; i < nt.C * HPAD; i += blockDim.x) {
+        const int c = i / HPAD, k = i % HPAD;
+        s.Wout[i] = k < HID ? Wo[c * HID + k] : 0.f;
+    }
+    if (threadIdx.x < 4) s.bout[threadIdx.x] = threadIdx.x < nt.C ? a.params[nt.offbout() + threadIdx.x] : 0.f;
+}
+
+// Phase 0 of a tile (CUDA cores): beta[j][2pe] = sin/cos(coords.B), Cp[j][o] = sum_k beta[j][k] W0c[o][k]
+__device__ inline void tile_prologue(const Args& a, TcSmem& s, const TileIdx& ti) {
+    const Net& nt = a.net;
+    const int pe = nt.pe;
+    if (a.has_aff && threadIdx.x == 0) affine_consts(a.aff, ti.d, s.affc);
+    __syncthreads();
+    for (int i = threadIdx.x; i < ti.np * pe; i += blockDim.x) {
+        const int j = i / pe, m = i % pe;
+        const float2 c = transformed_coord(a, s.affc, ti.p0 + j);
+        float sn, cs;
+        sincosf(c.x * a.B[m] + c.y * a.B[pe + m], &sn, &cs);
+        s.beta[j * 2 * pe + m] = sn;
+        s.beta[j * 2 * pe + pe + m] = cs;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ti.np * (SHP / 4); i += blockDim.x) {
+        const int j = i / (SHP / 4), o4 = i % (SHP / 4);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* bj = s.beta + j * 2 * pe;
+        const float4* w = reinterpret_cast<const float4*>(a.W0cT) + o4;
+        for (int k = 0; k < 2 * pe; ++k) {
+            const float bk = bj[k];
+            const float4 ww = __ldg(w + (size_t)k * (SHP / 4));
+            acc.x = fmaf(bk, ww.x, acc.x), acc.y = fmaf(bk, ww.y, acc.y), acc.z = fmaf(bk, ww.z, acc.z), acc.w = fmaf(bk, ww.w, acc.w);
+        }
+        reinterpret_cast<float4*>(s.Cp + j * SHP)[o4] = acc;
+    }
+    __syncthreads();
+}
+
+// h1 = tanh(A[n] + Cp[j]) -> tile (feature 50 := 1, 51.. := 0); inactive rows are all-zero
+template <bool FAST>
+__device__ __forceinline__ void layer0_to_tile(const Args& a, const TcSmem& s, uint8_t* tile, int t, bool active, int n, int j) {
+    const float* An = a.Avec + (size_t)n * SHP;
+    const float* Cj = s.Cp + j * SHP;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int o = c * 8 + q;
+            float x = 0.f;
+            if (active) {
+                if (o < HID) x = act_tanh<FAST>(__ldg(An + o) + Cj[o]);
+                else if (o == ONE_COL) x = 1.f;
+            }
+            v[q] = x;
+        }
+        store_chunk(tile, t, c, v);
+    }
+}
+
+// D(tmem_d)[128 x 64] (+)= A . B^T with split-bf16 operands: hi*hi + lo*hi + hi*lo.  A K-major [128 x 64]; B is a [64 x 64] weight tile,
+// K-major (b_transposed = 0: forward) or read MN-major (b_transposed = 1: data gradient).
+__device__ __forceinline__ void issue_rows_x_weights(uint32_t tmem_d, const uint8_t* a_tile, const uint8_t* w_tile, int b_transposed) {
+    const uint32_t idesc = instr_desc(FMT_BF16, 128, HPAD, 0, b_transposed);
+    const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(w_tile);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {  // K = 16 per MMA
+        const uint32_t ao = a0 + ks * 2 * (128 * 16);
+        const uint64_t ah = smem_desc(ao, 128 * 16, 128), al = smem_desc(ao + TILE_HALF, 128 * 16, 128);
+        uint64_t bh, bl;
+        if (b_transposed) {
+            bh = smem_desc(b0 + ks * 256, 128, HPAD * 16), bl = smem_desc(b0 + WT_HALF + ks * 256, 128, HPAD * 16);
+        } else {
+            bh = smem_desc(b0 + ks * 2 * (HPAD * 16), HPAD * 16, 128), bl = smem_desc(b0 + WT_HALF + ks * 2 * (HPAD * 16), HPAD * 16, 128);
+        }
+        mma_f16(tmem_d, ah, bh, idesc, ks > 0);
+        mma_f16(tmem_d, al, bh, idesc, 1);
+        mma_f16(tmem_d, ah, bl, idesc, 1);
+    }
+}
+
+// D(tmem_d)[64(M=64 layout) x N] += X^T . Y over the 128 rows: X [128 x 64] tile and Y ([128 x 64] tile or the [128 x 8] dy tile), both read MN-major
+__device__ __forceinline__ void issue_transposed_product(uint32_t tmem_d, const uint8_t* x_tile, const uint8_t* y_tile, int n_cols, uint32_t y_half,
+                                                         bool zero_first) {
+    const uint32_t idesc = instr_desc(FMT_BF16, 64, n_cols, 1, 1);
+    const uint32_t x0 = smem_u32(x_tile), y0 = smem_u32(y_tile);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {  // 16 rows per MMA
+        const uint64_t xh = smem_desc(x0 + ks * 256, 128, 128 * 16), xl = smem_desc(x0 + TILE_HALF + ks * 256, 128, 128 * 16);
+        const uint64_t yh = smem_desc(y0 + ks * 256, 128, 128 * 16), yl = smem_desc(y0 + y_half + ks * 256, 128, 128 * 16);
+        mma_f16(tmem_d, xh, yh, idesc, (ks > 0 || !zero_first) ? 1u : 0u);
+        mma_f16(tmem_d, xl, yh, idesc, 1);
+        mma_f16(tmem_d, xh, yl, idesc, 1);
+    }
+}
+
+__device__ __forceinline__ uint32_t lane_base(int warp) { return (uint32_t)((warp & 3) * 32) << 16; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------------
+template <bool FAST>
+__global__ void __launch_bounds__(128) inr_fwd_tc_kernel(Args a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    TcSmem s(smem_raw, a.net, a.tl, 1);
+    const Net& nt = a.net;
+    const Tiling& tl = a.tl;
+    const int t = threadIdx.x, warp = t >> 5;
+    const int L = nt.nl;
+    load_weight_tiles(a, s);
+    if (warp == 0) tmem_alloc(s.tmem, 64);
+    if (t == 0) {
+        mbar_init(&s.bars[0], 1);
+        mbar_fence_init();
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = *s.tmem;
+    uint32_t phase = 0;
+    uint8_t* T = s.tiles;
+    for (int tile = blockIdx.x; tile < tl.numTiles; tile += gridDim.x) {
+        const TileIdx ti = decode_tile(tl, tile);
+        tile_prologue(a, s, ti);
+        const int nl = t / tl.TP, j = t % tl.TP;
+        const bool active = nl < ti.nn && j < ti.np;
+        layer0_to_tile<FAST>(a, s, T, t, active, ti.n0 + nl, j);
+        float h[HID];
+        for (int l = 1; l < L; ++l) {
+            fence_proxy_async();
+            fence_before_sync();
+            __syncthreads();
+            if (t == 0) {
+                fence_after_sync();
+                issue_rows_x_weights(tm + TM_ACC, T, s.wt + (size_t)(l - 1) * WT_BYTES, 0);
+                mma_commit(&s.bars[0]);
+            }
+            mbar_wait(&s.bars[0], phase);
+            phase ^= 1;
+            fence_after_sync();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float v[16];
+                tmem_ld16(tm + TM_ACC + lane_base(warp) + g * 16, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int o = g * 16 + q;
+                    float x = 0.f;
+                    if (active) {
+                        if (o < HID) x = act_tanh<FAST>(v[q]);
+                        else if (o == ONE_COL) x = 1.f;
+                    }
+                    v[q] = x;
+                    if (o < HID) h[o] = x;
+                }
+                if (l < L - 1) {
+                    store_chunk(T, t, 2 * g, v);
+                    store_chunk(T, t, 2 * g + 1, v + 8);
+                }
+            }
+        }
+        if (active) {
+            const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + nl)) * nt.C) * tl.P + ti.p0 + j;
+            for (int c = 0; c < nt.C; ++c) {
+                float y = s.bout[c];
+#pragma unroll
+                for (int k = 0; k < HID; ++k) y = fmaf(h[k], s.Wout[c * HPAD + k], y);
+                a.img[base + (size_t)c * tl.P] = act_tanh<FAST>(y);
+            }
+        }
+        fence_before_sync();
+        __syncthreads();  // the tile buffer / Cp / beta are rewritten by the next tile
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, 64);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------------
+template <bool FAST>
+__global__ void __launch_bounds__(128) inr_bwd_tc_kernel(Args a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const Net& nt = a.net;
+    const Tiling& tl = a.tl;
+    const int L = nt.nl;          // hidden layers; activation tiles T[0..L-1] hold h_1..h_L, one extra rotating tile X
+    TcSmem s(smem_raw, nt, tl, L + 1);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const bool want_w = a.want_weights != 0;
+    load_weight_tiles(a, s);
+    if (warp == 0) tmem_alloc(s.tmem, TM_COLS);
+    if (t == 0) {
+        mbar_init(&s.bars[0], 1);
+        mbar_init(&s.bars[1], 1);
+        mbar_fence_init();
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = *s.tmem;
+    const uint32_t tm_dwout = TM_DW + (uint32_t)(L - 1) * 64;
+    uint32_t ph_acc = 0, ph_done = 0;
+    bool first = true;
+    auto Tile = [&](int i) { return s.tiles + (size_t)i * TILE_BYTES; };  // i in [0, L]: h_{i+1} for i < L, X for i == L
+    // dA[n][o] accumulators of this thread: entries e = t + 128*q  ->  (n = e / HID, o = e % HID)
+    constexpr int DA_PER_THREAD = 16;  // covers N*HID <= 2048 entries (N <= 40); larger N falls back to the fp32 path (host check)
+    float dA[DA_PER_THREAD];
+#pragma unroll
+    for (int q = 0; q < DA_PER_THREAD; ++q) dA[q] = 0.f;
+
+    for (int tile = blockIdx.x; tile < tl.numTiles; tile += gridDim.x) {
+        const TileIdx ti = decode_tile(tl, tile);
+        tile_prologue(a, s, ti);
+        const int nl = t / tl.TP, j = t % tl.TP;
+        const bool active = nl < ti.nn && j < ti.np;
+        if (!first) {  // every MMA of the previous tile (they read the tiles we are about to overwrite) has completed
+            mbar_wait(&s.bars[1], ph_done);
+            ph_done ^= 1;
+            fence_after_sync();
+        }
+        // ---- forward recompute: h_1 (CUDA cores), h_2..h_L (tensor cores), all kept as tiles
+        layer0_to_tile<FAST>(a, s, Tile(0), t, active, ti.n0 + nl, j);
+        float h[HID];  // h_L of this row (registers), for the output layer
+        for (int l = 1; l < L; ++l) {
+            fence_proxy_async();
+            fence_before_sync();
+            __syncthreads();
+            if (t == 0) {
+                fence_after_sync();
+                issue_rows_x_weights(tm + TM_ACC, Tile(l - 1), s.wt + (size_t)(l - 1) * WT_BYTES, 0);
+                mma_commit(&s.bars[0]);
+            }
+            mbar_wait(&s.bars[0], ph_acc);
+            ph_acc ^= 1;
+            fence_after_sync();
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float v[16];
+                tmem_ld16(tm + TM_ACC + lane_base(warp) + g * 16, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int o = g * 16 + q;
+                    float x = 0.f;
+                    if (active) {
+                        if (o < HID) x = act_tanh<FAST>(v[q]);
+                        else if (o == ONE_COL) x = 1.f;
+                    }
+                    v[q] = x;
+                    if (l == L - 1 && o < HID) h[o] = x;
+                }
+                store_chunk(Tile(l), t, 2 * g, v);
+                store_chunk(Tile(l), t, 2 * g + 1, v + 8);
+            }
+        }
+        // ---- output layer (CUDA cores): y, dy, dz_{L-1} = (Wout^T dy) * (1 - h_L^2)  ->  tile X; dy -> dy tile
+        {
+            float dy[4] = {0.f, 0.f, 0.f, 0.f};
+            if (active) {
+                const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + nl)) * nt.C) * tl.P + ti.p0 + j;
+                for (int c = 0; c < nt.C; ++c) {
+                    float y = s.bout[c];
+#pragma unroll
+                    for (int k = 0; k < HID; ++k) y = fmaf(h[k], s.Wout[c * HPAD + k], y);
+                    y = act_tanh<FAST>(y);
+                    dy[c] = a.g_img[base + (size_t)c * tl.P] * (1.f - y * y);
+                }
+            }
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int k = c8 * 8 + q;
+                    float dh = 0.f;
+                    if (k < HID) {
+                        for (int c = 0; c < nt.C; ++c) dh = fmaf(s.Wout[c * HPAD + k], dy[c], dh);
+                        dh *= (1.f - h[k] * h[k]);
+                    }
+                    v[q] = active ? dh : 0.f;
+                }
+                store_chunk(Tile(L), t, c8, v);
+            }
+            if (want_w) {  // dy as a [128 x 8] split-bf16 tile (one 16-byte chunk per row)
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(dy[2 * q], dy[2 * q + 1]);
+                    const float2 hf = __bfloat1622float2(h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(dy[2 * q] - hf.x, dy[2 * q + 1] - hf.y);
+                    hi[q] = *reinterpret_cast<const uint32_t*>(&h2), lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+                hi[2] = hi[3] = lo[2] = lo[3] = 0u;
+                *reinterpret_cast<uint4*>(s.dy + t * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(s.dy + DY_HALF + t * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        // ---- layers L-1 .. 1.  dz_l sits in `src`; h_l in Tile(l-1); dz_{l-1} goes to `dst` (a tile no pending MMA reads)
+        int src = L, dst = L - 1;
+        for (int l = L - 1; l >= 1; --l) {
+            fence_proxy_async();
+            fence_before_sync();
+            __syncthreads();
+            if (t == 0) {
+                fence_after_sync();
+                if (want_w && l == L - 1)  // output layer: dWout[c][i] (and dbout in column ONE_COL) = sum_r h_L[r][i] dy[r][c]
+                    issue_transposed_product(tm + tm_dwout, Tile(L - 1), s.dy, 8, DY_HALF, first);
+                issue_rows_x_weights(tm + TM_ACC, Tile(src), s.wt + (size_t)(l - 1) * WT_BYTES, 1);
+                mma_commit(&s.bars[0]);
+                if (want_w)  // dW_l[o][i] (bias gradient in column ONE_COL) += sum_r dz_l[r][o] h_l[r][i]; overlaps the epilogue below
+                    issue_transposed_product(tm + TM_DW + (uint32_t)(l - 1) * 64, Tile(src), Tile(l - 1), HPAD, TILE_HALF, first);
+                if (l == 1) mma_commit(&s.bars[1]);
+            }
+            mbar_wait(&s.bars[0], ph_acc);
+            ph_acc ^= 1;
+            fence_after_sync();
+            // dz_{l-1}[k] = dh_l[k] * (1 - h_l[k]^2)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float v[16], hv[16];
+                tmem_ld16(tm + TM_ACC + lane_base(warp) + g * 16, v);
+                load_chunk(Tile(l - 1), t, 2 * g, hv);
+                load_chunk(Tile(l - 1), t, 2 * g + 1, hv + 8);
+                tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int k = g * 16 + q;
+                    v[q] = (active && k < HID) ? v[q] * (1.f - hv[q] * hv[q]) : 0.f;
+                }
+                store_chunk(Tile(dst), t, 2 * g, v);
+                store_chunk(Tile(dst), t, 2 * g + 1, v + 8);
+            }
+            // rotate: the old src is free once the NEXT step's data-gradient MMAs (issued after this step's dW MMAs) have completed
+            src = dst;
+            dst = (src == L) ? L - 1 : L;  // the free tile alternates between T[L-1] and X
+        }
+        __syncthreads();  // dz_0 (tile `src`) complete
+        // ---- layer 0: G0[j][o] = sum_n dz0, dA[n][o] += sum_j dz0   (CUDA cores, from the split-bf16 tile)
+        const uint8_t* Z = Tile(src);
+        for (int i = t; i < ti.np * SHP; i += 128) {
+            const int jj = i / SHP, o = i % SHP;
+            float sum = 0.f;
+            if (o < HID)
+                for (int n = 0; n < ti.nn; ++n) sum += load_elem(Z, n * tl.TP + jj, o);
+            s.G0s[i] = sum;
+        }
+        if (want_w) {
+#pragma unroll
+            for (int q = 0; q < DA_PER_THREAD; ++q) {
+                const int e = t + 128 * q;
+                if (e < ti.nn * HID) {
+                    const int n = e / HID, o = e % HID;
+                    float sum = 0.f;
+                    for (int jj = 0; jj < ti.np; ++jj) sum += load_elem(Z, n * tl.TP + jj, o);
+                    dA[q] += sum;
+                }
+            }
+        }
+        __syncthreads();
+        if (want_w) {
+            float* gdst = a.G0 + ((size_t)ti.d * tl.P + ti.p0) * SHP;
+            for (int i = t; i < ti.np * SHP; i += 128) gdst[i] = s.G0s[i];
+        }
+        if (a.want_affine) {
+            const int pe = nt.pe;
+            for (int i = t; i < ti.np * pe; i += 128) {
+                const int jj = i / pe, m = i % pe;
+                const float4* ws_ = reinterpret_cast<const float4*>(a.W0cT + (size_t)m * SHP);
+                const float4* wc_ = reinterpret_cast<const float4*>(a.W0cT + (size_t)(pe + m) * SHP);
+                const float4* g4 = reinterpret_cast<const float4*>(s.G0s + jj * SHP);
+                float ds = 0.f, dc = 0.f;
+                for (int o4 = 0; o4 < SHP / 4; ++o4) {
+                    const float4 g = g4[o4], a4 = __ldg(ws_ + o4), b4 = __ldg(wc_ + o4);
+                    ds += g.x * a4.x + g.y * a4.y + g.z * a4.z + g.w * a4.w;
+                    dc += g.x * b4.x + g.y * b4.y + g.z * b4.z + g.w * b4.w;
+                }
+                const float sn = s.beta[jj * 2 * pe + m], cs = s.beta[jj * 2 * pe + pe + m];
+                s.beta[jj * 2 * pe + m] = ds * cs - dc * sn;  // d/dphi
+            }
+            __syncthreads();
+            float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (t < ti.np) {
+                float g0 = 0.f, g1 = 0.f;
+                for (int m = 0; m < pe; ++m) {
+                    const float dphi = s.beta[t * 2 * pe + m];
+                    g0 = fmaf(dphi, a.B[m], g0);
+                    g1 = fmaf(dphi, a.B[pe + m], g1);
+                }
+                const int p = ti.p0 + t;
+                const float r0 = a.coords[2 * p] - s.affc[6], r1 = a.coords[2 * p + 1] - s.affc[7];
+                v[0] = g0, v[1] = g1, v[2] = g0 * r0, v[3] = g0 * r1, v[4] = g1 * r0, v[5] = g1 * r1;
+            }
+            if (t < 32) {  // TP <= 8: the first warp holds every contribution
+#pragma unroll
+                for (int q = 0; q < 6; ++q) v[q] = warp_sum(v[q]);
+                if (t == 0) {
+                    float* pdst = a.affpart + ((size_t)ti.d * tl.tilesP + ti.p0 / tl.TP) * 6;
+                    for (int q = 0; q < 6; ++q) pdst[q] = v[q];
+                }
+            }
+        }
+        first = false;
+        __syncthreads();
+    }
+    // ---- drain: wait for the last tile's MMAs, then read the weight-gradient accumulators out of TMEM
+    if (!first) {
+        mbar_wait(&s.bars[1], ph_done);
+        fence_after_sync();
+    }
+    if (want_w) {
+        float* part = a.partials + (size_t)blockIdx.x * partial_size(nt, tl, SHP);
+        float* p_dW = part;
+        float* p_db = part + (size_t)(L - 1) * HID * HID;
+        float* p_dWout = p_db + (size_t)(L - 1) * SHP;
+        float* p_dA = p_dWout + (size_t)nt.C * SHP + 4;
+        const int o = 16 * warp + lane;  // M=64 accumulator layout: row o -> lane (o/16)*32 + o%16
+        for (int l = 1; l < L; ++l) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float v[16];
+                tmem_ld16(tm + TM_DW + (uint32_t)(l - 1) * 64 + lane_base(warp) + g * 16, v);
+                tmem_ld_wait();
+                if (lane < 16 && o < HID) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const int i = g * 16 + q;
+                        if (i < HID) p_dW[(size_t)(l - 1) * HID * HID + o * HID + i] = first ? 0.f : v[q];
+                        else if (i == ONE_COL) p_db[(l - 1) * SHP + o] = first ? 0.f : v[q];
+                    }
+                }
+            }
+        }
+        {
+            float v[16];
+            tmem_ld16(tm + tm_dwout + lane_base(warp), v);
+            tmem_ld_wait();
+            if (lane < 16) {  // row i = o of D[i][c]
+                for (int c = 0; c < nt.C; ++c) {
+                    if (o < HID) p_dWout[c * SHP + o] = first ? 0.f : v[c];
+                    else if (o == ONE_COL) p_dWout[nt.C * SHP + c] = first ? 0.f : v[c];
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < DA_PER_THREAD; ++q) {
+            const int e = t + 128 * q;
+            if (e < tl.NC * HID) p_dA[(e / HID) * SHP + e % HID] = dA[q];
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm, TM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static int check_tc(const Net& nt, int N) {
+    LMR_CHECK_ARG(nt.hid == HID, "tensor-core path: hidden width %d not supported (50)", nt.hid);
+    LMR_CHECK_ARG(nt.nl >= 2 && nt.nl <= 4, "tensor-core path: n_hidden %d out of range [2,4]", nt.nl);
+    LMR_CHECK_ARG(nt.pe <= 64, "tensor-core path: pe_dim %d > 64", nt.pe);
+    (void)N;
+    return 0;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes, size_t* cache) {
+    if (bytes > *cache) {
+        LMR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        *cache = bytes;
+    }
+    return 0;
+}
+
+int forward(const lmr_inr_desc* desc, const float* params, const float* B, const float* auxB, const float* grid, int N, const float* coords,
+            int P, const float* coord_shift, const lmr_affine* affine, int D, float* img, void* ws, size_t ws_bytes, int precision,
+            cudaStream_t st) {
+    Net nt;
+    if (int rc = make_net(desc, &nt)) return rc;
+    if (int rc = check_tc(nt, N)) return rc;
+    LMR_CHECK_ARG(N >= 1 && P >= 1 && D >= 1, "inr_forward: bad sizes N=%d P=%d D=%d", N, P, D);
+    const Tiling tl = make_tiling(N, P, D, TP_CAP_TC);
+    const WsLayout wl = ws_layout(nt, tl, false);
+    if (ws_bytes < wl.total) {
+        set_error("inr_forward: workspace %zu < %zu bytes", ws_bytes, wl.total);
+        return LMR_ERR_WORKSPACE;
+    }
+    Args a;
+    if (int rc = fill_args(a, nt, tl, params, B, auxB, grid, coords, coord_shift, affine, ws, wl)) return rc;
+    a.img = img;
+    if (int rc = launch_prep<50>(a, st)) return rc;
+    TcSmem s(nullptr, nt, tl, 1);
+    const size_t smem = s.bytes + 1024;
+    const int grid_x = tl.numTiles < 2 * num_sms() ? tl.numTiles : 2 * num_sms();
+    static size_t c0 = 0, c1 = 0;
+    if (precision == LMR_PREC_BF16X3_FAST) {
+        if (int rc = set_smem(inr_fwd_tc_kernel<true>, smem, &c0)) return rc;
+        inr_fwd_tc_kernel<true><<<grid_x, 128, smem, st>>>(a);
+    } else {
+        if (int rc = set_smem(inr_fwd_tc_kernel<false>, smem, &c1)) return rc;
+        inr_fwd_tc_kernel<false><<<grid_x, 128, smem, st>>>(a);
+    }
+    LMR_LAUNCH_OK();
+    return 0;
+}
+
+int backward(const lmr_inr_desc* desc, const float* params, const float* B, const float* auxB, const float* grid, int N, const float* coords,
+             int P, const float* coord_shift, const lmr_affine* affine, int D, const float* g_img, float* g_params, float* g_angles,
+             float* g_scalings, float* g_shears, float* g_translation, void* ws, size_t ws_bytes, int precision, cudaStream_t st) {
+    Net nt;
+    if (int rc = make_net(desc, &nt)) return rc;
+    if (int rc = check_tc(nt, N)) return rc;
+    LMR_CHECK_ARG(N >= 1 && P >= 1 && D >= 1, "inr_backward: bad sizes N=%d P=%d D=%d", N, P, D);
+    LMR_CHECK_ARG(N <= 40, "inr_backward (tensor-core path): N=%d latents per step not supported (max 40); use the fp32 path", N);
+    const bool want_aff = g_angles != nullptr;
+    LMR_CHECK_ARG(g_params != nullptr || want_aff, "inr_backward: nothing to compute");
+    if (want_aff) {
+        LMR_CHECK_ARG(g_scalings && g_shears && g_translation, "inr_backward: incomplete affine gradient outputs");
+        LMR_CHECK_ARG(affine && affine->angles, "inr_backward: affine gradients requested without an affine transform");
+    }
+    const Tiling tl = make_tiling(N, P, D, TP_CAP_TC);
+    const WsLayout wl = ws_layout(nt, tl, true);
+    if (ws_bytes < wl.total) {
+        set_error("inr_backward: workspace %zu < %zu bytes", ws_bytes, wl.total);
+        return LMR_ERR_WORKSPACE;
+    }
+    Args a;
+    if (int rc = fill_args(a, nt, tl, params, B, auxB, grid, coords, coord_shift, affine, ws, wl)) return rc;
+    a.g_img = g_img;
+    a.want_weights = g_params != nullptr, a.want_affine = want_aff;
+    if (int rc = launch_prep<50>(a, st)) return rc;
+    TcSmem s(nullptr, nt, tl, nt.nl + 1);
+    const size_t smem = s.bytes + 1024;
+    LMR_CHECK_ARG(smem <= 227 * 1024, "inr_backward (tensor-core path): needs %zu bytes of shared memory (> 227 KB)", smem);
+    static size_t c0 = 0, c1 = 0;
+    if (precision == LMR_PREC_BF16X3_FAST) {
+        if (int rc = set_smem(inr_bwd_tc_kernel<true>, smem, &c0)) return rc;
+        inr_bwd_tc_kernel<true><<<wl.gridMain, 128, smem, st>>>(a);
+    } else {
+        if (int rc = set_smem(inr_bwd_tc_kernel<false>, smem, &c1)) return rc;
+        inr_bwd_tc_kernel<false><<<wl.gridMain, 128, smem, st>>>(a);
+    }
+    LMR_LAUNCH_OK();
+    if (a.want_weights) {
+        float* l0part = reinterpret_cast<float*>(static_cast<char*>(ws) + wl.l0part);
+        const size_t smem0 = (size_t)L0_CHUNK * (SHP + 2 * nt.pe) * sizeof(float);
+        static size_t c2 = 0;
+        if (int rc = set_smem(l0_partial_kernel<50>, smem0, &c2)) return rc;
+        l0_partial_kernel<50><<<wl.gridL0, 256, smem0, st>>>(a, l0part);
+        LMR_LAUNCH_OK();
+        const int blocks = (int)((nt.count() + 127) / 128);
+        finish_weights_kernel<50><<<blocks, 128, 0, st>>>(a, l0part, wl.gridMain, wl.gridL0, g_params);
+        LMR_LAUNCH_OK();
+    }
+    if (want_aff) {
+        finish_affine_kernel<<<D, 128, 0, st>>>(a, g_angles, g_scalings, g_shears, g_translation);
+        LMR_LAUNCH_OK();
+    }
+    return 0;
+}
+
+size_t workspace_bytes(const lmr_inr_desc* desc, int N, int P, int D, bool bwd) {
+    Net nt;
+    if (make_net(desc, &nt)) return 0;
+    return ws_layout(nt, make_tiling(N, P, D, TP_CAP_TC), bwd).total;
+}
 
 }  // namespace tc
 }  // namespace lmr

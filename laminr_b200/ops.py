@@ -16,11 +16,11 @@ from . import _lib
 from ._lib import Affine, InrDesc, check
 
 _DEFAULT_PRECISION = _lib.PREC_FP32
-_PREC_NAMES = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "bf16x3": _lib.PREC_BF16X3}
+_PREC_NAMES = {"fp32": _lib.PREC_FP32, "bf16x3_fast": _lib.PREC_BF16X3_FAST, "bf16x3": _lib.PREC_BF16X3}
 
 
 def set_default_precision(name):
-    """'fp32' (CUDA cores, parity path) | 'tf32' | 'bf16x3' (tcgen05 paths) for the INR hidden layers."""
+    """'fp32' (CUDA cores, bit-tight parity path) | 'bf16x3' | 'bf16x3_fast' (tcgen05 split-bf16 paths) for the INR hidden layers."""
     global _DEFAULT_PRECISION
     _DEFAULT_PRECISION = _PREC_NAMES[name]
 

@@ -169,9 +169,13 @@ def test_get_mei_dict_known_answer(L):
         assert v["mei"].shape == (1, 100, 100) and v["mask"].shape == (100, 100)
         assert abs(v["activation"] - 1.0000009536743164) < 2e-6, v["activation"]
         assert abs(np.linalg.norm(v["mei"]) - 1.0) < 1e-5
-    # RF centres land on the filter centres of demo1: loc (0.2,0.2) -> pixel (60,60); (-0.2,-0.2) -> (40,40); (-0.2,0.2) -> x 40, y 60
-    for k, (x, y) in {0: (60, 60), 1: (40, 40), 2: (40, 60)}.items():
+    # RF centres land on the filter centres of demo1: loc (0.2,0.2) -> pixel (60,60); loc (-0.2,-0.2) under the global 45-degree
+    # transform sits at T^-1 loc = (-0.283, 0) -> pixel (35.9, 50); neuron 2's three Gabors are centred near loc (-0.2,0.2) -> (40,60)
+    for k, (x, y) in {0: (60, 60), 1: (35.9, 50), 2: (40, 60)}.items():
         assert abs(meis[k]["center_pos"]["x"] - x) < 4 and abs(meis[k]["center_pos"]["y"] - y) < 4, (k, meis[k]["center_pos"])
+    # RF mask sizes measured on the unmodified reference for the same seed: 1033 / 1035 / 1621 px
+    for k, want in {0: 1033, 1: 1035, 2: 1621}.items():
+        assert abs(meis[k]["mask"].sum() - want) < 0.03 * want, (k, meis[k]["mask"].sum())
 
 
 def test_generic_mei_path_matches_batched_kernel(L):
