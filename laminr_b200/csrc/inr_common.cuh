@@ -102,6 +102,8 @@ __global__ void prep_A_kernel(Args a) {
             const float* w = W0 + (size_t)o * nt.in_dim + 1;
             const float* al = a.alpha + (size_t)n * na;
             for (int k = 0; k < na; ++k) acc = fmaf(w[k], al[k], acc);
+        } else if (o == HID) {
+            acc = 20.f;  // tanh(20) == 1 in fp32: the tensor-core path keeps a constant-1 feature (bias column) in slot HID
         }
         a.Avec[i] = acc;
     }

@@ -1,19 +1,22 @@
 // INR generator, tcgen05 tensor-core path (LMR_PREC_BF16X3 / LMR_PREC_BF16X3_FAST): forward and recompute-backward.
 //
-// Same tiling and layer-0 separability as inr_simt.cu (a tile = TP pixels x N latents <= 128 rows of one target,
-// thread t <-> row t <-> TMEM lane t).  The 50x50 hidden layers run on the 5th-gen tensor cores:
+// Same tiling and layer-0 separability as inr_simt.cu (a tile = TP pixels x N latents <= 128 rows of one target; row r
+// <-> TMEM lane r).  The 50x50 hidden layers run on the 5th-gen tensor cores:
 //   * operands are error-compensated split-bf16: x = hi + lo (bf16 each), products hi*hi + lo*hi + hi*lo (3 tcgen05.mma,
 //     kind::f16, fp32 accumulate in TMEM) -> ~2^-16 relative operand error, fp32-class results (precision probe);
 //   * activation tiles [128 rows x 64 features] live in shared memory in the canonical no-swizzle core-matrix layout
-//     (tc_common.cuh); feature 50 is the constant 1 so the bias is a column of the weight tile and the bias gradient a
-//     column of the weight-gradient accumulator;
-//   * forward      z_l   = h_l W_l^T        A = h tile (K-major),    B = W_l tile (K-major)           M=128 N=64 K=64
-//     data grad    dh_l  = dz_l W_l         A = dz tile (K-major),   B = W_l tile read MN-major       M=128 N=64 K=64
+//     (tc_common.cuh).  Feature 50 is the constant 1: the bias is column 50 of the weight tile and the bias gradient
+//     column 50 of the weight-gradient accumulator.  The weight tile's entry [50][50] = 20 regenerates the constant through
+//     the activation (tanh(20) == 1 in fp32) and every other padding entry is 0 (tanh(0) == 0), so all epilogues are
+//     uniform over the 64 columns -- no per-column branches;
+//   * forward      z_l   = h_l W_l^T        A = h tile (K-major),      B = W_l tile (K-major)         M=128 N=64 K=64
+//     data grad    dh_l  = dz_l W_l         A = dz tile (K-major),     B = W_l tile read MN-major     M=128 N=64 K=64
 //     weight grad  dW_l += dz_l^T h_l       A = dz tile read MN-major, B = h tile read MN-major       M=64  N=64 K=128
 //     -- the transposed products reuse the SAME bytes through MN-major descriptors (no transposed copies);
-//   * weight-gradient accumulators stay resident in TMEM across all tiles of the persistent CTA (3 x 64 columns + 16);
-//   * nothing is stored between forward and backward: the backward recomputes the forward per tile (5 tiles of smem).
-// The weight-gradient MMAs of a layer overlap with the epilogue that produces the next dz tile (rotating 5 tile buffers).
+//   * weight-gradient accumulators stay resident in TMEM across all tiles of the persistent CTA;
+//   * nothing is stored between forward and backward: the backward recomputes the forward per tile (L+1 tiles of smem),
+//     and the weight-gradient MMAs of a layer overlap the epilogue that produces the next dz tile (rotating buffers).
+// 512 threads per CTA: thread = (row, column quarter); warp w reads TMEM lanes 32*(w%4).. and columns 16*(w/4)...
 #include <cuda_bf16.h>
 
 #include "inr_common.cuh"
@@ -28,22 +31,35 @@ using namespace lmr::tcx;
 constexpr int HID = 50;               // hidden width served by this path
 constexpr int HPAD = 64;              // padded feature count of a tile (K and N of the MMAs)
 constexpr int ONE_COL = 50;           // feature slot holding the constant 1 (bias column)
+constexpr float ONE_SEED = 20.f;      // tanh(20) == 1
 constexpr int TP_CAP_TC = 8;          // pixels per tile cap (bounds the per-tile scratch)
+constexpr int NT = 512;               // threads per CTA
 constexpr int TILE_HALF = 128 * HPAD * 2;   // bytes of the hi (or lo) half of an activation tile
 constexpr int TILE_BYTES = 2 * TILE_HALF;   // 32 KB
 constexpr int WT_HALF = HPAD * HPAD * 2;    // 8 KB
 constexpr int WT_BYTES = 2 * WT_HALF;       // 16 KB
-constexpr int DY_HALF = 128 * 8 * 2;        // dy tile: 128 rows x 8 channels(padded), hi / lo
-constexpr int MAXL = 8;
+constexpr int DY_HALF = 128 * 8 * 2;        // dy tile: 128 rows x 8 channels (padded), hi / lo
 
 // TMEM columns
 constexpr uint32_t TM_ACC = 0;        // [128 lanes x 64]  forward / data-gradient accumulator
-constexpr uint32_t TM_DW = 64;        // (L-1) x [64 lanes(M=64 layout) x 64] weight-gradient accumulators
+constexpr uint32_t TM_DW = 64;        // (L-1) x [64 rows (M=64 lane layout) x 64] weight-gradient accumulators, then 16 columns for dWout
 constexpr uint32_t TM_COLS = 512;
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 template <bool FAST>
 __device__ __forceinline__ float act_tanh(float x) {
-    return FAST ? tanh_mufu(x) : tanh_ex2(x);
+    if (FAST) return tanh_mufu(x);
+    // 1 - 2/(e^{2x} + 1): saturates cleanly (e -> inf gives 1, e -> 0 gives -1); ~1e-7 absolute error
+    return fmaf(-2.f, rcp_approx(ex2_approx(x * 2.885390081777927f) + 1.f), 1.f);
 }
 
 // split 8 floats into bf16 hi / lo and store the two 16-byte chunks of row r, feature chunk c
@@ -70,22 +86,22 @@ __device__ __forceinline__ void load_chunk(const uint8_t* tile, int r, int c, fl
     const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hh[q]));
-        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ll[q]));
-        v[2 * q] = a.x + b.x, v[2 * q + 1] = a.y + b.y;
+        // a bf16 is the upper half of an fp32
+        v[2 * q] = __uint_as_float(hh[q] << 16) + __uint_as_float(ll[q] << 16);
+        v[2 * q + 1] = __uint_as_float(hh[q] & 0xffff0000u) + __uint_as_float(ll[q] & 0xffff0000u);
     }
 }
 __device__ __forceinline__ float load_elem(const uint8_t* tile, int r, int f) {
     const uint32_t off = tile_off(r, f >> 3, 128) + (f & 7) * 2;
-    return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + off)) +
-           __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(tile + TILE_HALF + off));
+    return __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(tile + off)) << 16) +
+           __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(tile + TILE_HALF + off)) << 16);
 }
 
 struct TcSmem {
     uint8_t* tiles;   // ntiles x TILE_BYTES
     uint8_t* wt;      // (L-1) x WT_BYTES
     uint8_t* dy;      // 2 x DY_HALF
-    float *Cp, *beta, *Wout, *bout, *affc, *G0s;
+    float *Cp, *beta, *Wout, *bout, *affc, *scratch;  // scratch: output-layer partial sums [128][4][C], later G0s [TP][SHP]
     uint64_t* bars;   // [0] accumulator ready, [1] all MMAs of the tile done
     uint32_t* tmem;
     size_t bytes;
@@ -99,19 +115,21 @@ struct TcSmem {
         tiles = take((size_t)ntiles * TILE_BYTES);
         wt = take((size_t)(nt.nl - 1) * WT_BYTES);
         dy = take(2 * DY_HALF);
-        Cp = reinterpret_cast<float*>(take((size_t)tl.TP * SHP * 4));
+        Cp = reinterpret_cast<float*>(take((size_t)tl.TP * HPAD * 4));
         beta = reinterpret_cast<float*>(take((size_t)tl.TP * 2 * nt.pe * 4));
         Wout = reinterpret_cast<float*>(take((size_t)nt.C * HPAD * 4));
         bout = reinterpret_cast<float*>(take(16));
         affc = reinterpret_cast<float*>(take(48));
-        G0s = reinterpret_cast<float*>(take((size_t)tl.TP * SHP * 4));
+        const size_t sc1 = (size_t)128 * 4 * nt.C * 4, sc2 = (size_t)tl.TP * SHP * 4;
+        scratch = reinterpret_cast<float*>(take(sc1 > sc2 ? sc1 : sc2));
         bars = reinterpret_cast<uint64_t*>(take(16));
         tmem = reinterpret_cast<uint32_t*>(take(16));
         bytes = p - base;
     }
 };
 
-// weights of hidden layers 1..L-1 as split-bf16 K-major tiles: W_l[o][k] for k < 50, column 50 = bias b_l[o], rest 0
+// weights of hidden layers 1..L-1 as split-bf16 K-major tiles: W_l[o][k] for k < 50, column 50 = bias b_l[o],
+// entry [50][50] = ONE_SEED (regenerates the constant-1 feature), rest 0.  Also the fp32 output layer and zeroed Cp padding.
 __device__ inline void load_weight_tiles(const Args& a, TcSmem& s) {
     const Net& nt = a.net;
     for (int l = 1; l < nt.nl; ++l) {
@@ -122,6 +140,7 @@ __device__ inline void load_weight_tiles(const Args& a, TcSmem& s) {
             const int o = i / HPAD, k = i % HPAD;
             float v = 0.f;
             if (o < HID) v = k < HID ? W[o * HID + k] : (k == ONE_COL ? b[o] : 0.f);
+            else if (o == ONE_COL && k == ONE_COL) v = ONE_SEED;
             const __nv_bfloat16 hi = __float2bfloat16(v);
             const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
             const uint32_t off = tile_off(o, k >> 3, HPAD) + (k & 7) * 2;
@@ -135,6 +154,7 @@ __device__ inline void load_weight_tiles(const Args& a, TcSmem& s) {
         s.Wout[i] = k < HID ? Wo[c * HID + k] : 0.f;
     }
     if (threadIdx.x < 4) s.bout[threadIdx.x] = threadIdx.x < nt.C ? a.params[nt.offbout() + threadIdx.x] : 0.f;
+    for (int i = threadIdx.x; i < a.tl.TP * HPAD; i += blockDim.x) s.Cp[i] = 0.f;  // columns >= 52 stay 0 forever
 }
 
 // Phase 0 of a tile (CUDA cores): beta[j][2pe] = sin/cos(coords.B), Cp[j][o] = sum_k beta[j][k] W0c[o][k]
@@ -152,91 +172,94 @@ __device__ inline void tile_prologue(const Args& a, TcSmem& s, const TileIdx& ti
         s.beta[j * 2 * pe + pe + m] = cs;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < ti.np * (SHP / 4); i += blockDim.x) {
-        const int j = i / (SHP / 4), o4 = i % (SHP / 4);
+    // item = (pixel j, 4 output columns o4); the K = 2*pe sum is split over 4 adjacent lanes and combined by shuffles
+    const int items = ti.np * (SHP / 4);
+    const int kq = threadIdx.x & 3, kper = (2 * pe + 3) / 4;
+    for (int base = 0; base < items; base += blockDim.x / 4) {
+        const int it = base + (threadIdx.x >> 2);
+        const bool ok = it < items;
+        const int j = ok ? it / (SHP / 4) : 0, o4 = ok ? it % (SHP / 4) : 0;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         const float* bj = s.beta + j * 2 * pe;
         const float4* w = reinterpret_cast<const float4*>(a.W0cT) + o4;
-        for (int k = 0; k < 2 * pe; ++k) {
+        const int k1 = min(2 * pe, (kq + 1) * kper);
+#pragma unroll 5
+        for (int k = kq * kper; k < k1; ++k) {
             const float bk = bj[k];
             const float4 ww = __ldg(w + (size_t)k * (SHP / 4));
             acc.x = fmaf(bk, ww.x, acc.x), acc.y = fmaf(bk, ww.y, acc.y), acc.z = fmaf(bk, ww.z, acc.z), acc.w = fmaf(bk, ww.w, acc.w);
         }
-        reinterpret_cast<float4*>(s.Cp + j * SHP)[o4] = acc;
+#pragma unroll
+        for (int sh = 1; sh <= 2; sh <<= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sh), acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sh);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, sh), acc.w += __shfl_xor_sync(0xffffffffu, acc.w, sh);
+        }
+        if (ok && kq == 0) reinterpret_cast<float4*>(s.Cp + j * HPAD)[o4] = acc;
     }
     __syncthreads();
 }
 
-// h1 = tanh(A[n] + Cp[j]) -> tile (feature 50 := 1, 51.. := 0); inactive rows are all-zero
+// h1 = tanh(A[n] + Cp[j]) for this thread's 16 columns (A[n][50] = ONE_SEED from the prep kernel -> constant-1 feature)
 template <bool FAST>
-__device__ __forceinline__ void layer0_to_tile(const Args& a, const TcSmem& s, uint8_t* tile, int t, bool active, int n, int j) {
+__device__ __forceinline__ void layer0_to_tile(const Args& a, const TcSmem& s, uint8_t* tile, int row, int quarter, float actf, int n, int j) {
     const float* An = a.Avec + (size_t)n * SHP;
-    const float* Cj = s.Cp + j * SHP;
+    const float* Cj = s.Cp + j * HPAD;
+    float v[16];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int o = c * 8 + q;
-            float x = 0.f;
-            if (active) {
-                if (o < HID) x = act_tanh<FAST>(__ldg(An + o) + Cj[o]);
-                else if (o == ONE_COL) x = 1.f;
-            }
-            v[q] = x;
-        }
-        store_chunk(tile, t, c, v);
+    for (int q = 0; q < 16; ++q) {
+        const int o = quarter * 16 + q;
+        const float av = o < SHP ? __ldg(An + o) : 0.f;
+        v[q] = act_tanh<FAST>(av + Cj[o]) * actf;
     }
+    store_chunk(tile, row, 2 * quarter, v);
+    store_chunk(tile, row, 2 * quarter + 1, v + 8);
 }
 
-// D(tmem_d)[128 x 64] (+)= A . B^T with split-bf16 operands: hi*hi + lo*hi + hi*lo.  A K-major [128 x 64]; B is a [64 x 64] weight tile,
-// K-major (b_transposed = 0: forward) or read MN-major (b_transposed = 1: data gradient).
+// D(tmem_d)[128 x 64] = A . B^T with split-bf16 operands: hi*hi + lo*hi + hi*lo.  A K-major [128 x 64]; B is a [64 x 64] weight tile,
+// K-major (b_transposed = 0: forward) or read MN-major (b_transposed = 1: data gradient).  Issued by ONE thread.
 __device__ __forceinline__ void issue_rows_x_weights(uint32_t tmem_d, const uint8_t* a_tile, const uint8_t* w_tile, int b_transposed) {
     const uint32_t idesc = instr_desc(FMT_BF16, 128, HPAD, 0, b_transposed);
-    const uint32_t a0 = smem_u32(a_tile), b0 = smem_u32(w_tile);
-#pragma unroll
+    uint64_t ah = smem_desc(smem_u32(a_tile), 128 * 16, 128);
+    uint64_t bh = b_transposed ? smem_desc(smem_u32(w_tile), 128, HPAD * 16) : smem_desc(smem_u32(w_tile), HPAD * 16, 128);
+    const uint64_t a_step = (2 * 128 * 16) >> 4, b_step = (b_transposed ? 256 : 2 * HPAD * 16) >> 4;  // start-address field is in 16-byte units
+    const uint64_t a_lo = TILE_HALF >> 4, b_lo = WT_HALF >> 4;
+#pragma unroll 1
     for (int ks = 0; ks < 4; ++ks) {  // K = 16 per MMA
-        const uint32_t ao = a0 + ks * 2 * (128 * 16);
-        const uint64_t ah = smem_desc(ao, 128 * 16, 128), al = smem_desc(ao + TILE_HALF, 128 * 16, 128);
-        uint64_t bh, bl;
-        if (b_transposed) {
-            bh = smem_desc(b0 + ks * 256, 128, HPAD * 16), bl = smem_desc(b0 + WT_HALF + ks * 256, 128, HPAD * 16);
-        } else {
-            bh = smem_desc(b0 + ks * 2 * (HPAD * 16), HPAD * 16, 128), bl = smem_desc(b0 + WT_HALF + ks * 2 * (HPAD * 16), HPAD * 16, 128);
-        }
         mma_f16(tmem_d, ah, bh, idesc, ks > 0);
-        mma_f16(tmem_d, al, bh, idesc, 1);
-        mma_f16(tmem_d, ah, bl, idesc, 1);
+        mma_f16(tmem_d, ah + a_lo, bh, idesc, 1);
+        mma_f16(tmem_d, ah, bh + b_lo, idesc, 1);
+        ah += a_step, bh += b_step;
     }
 }
 
-// D(tmem_d)[64(M=64 layout) x N] += X^T . Y over the 128 rows: X [128 x 64] tile and Y ([128 x 64] tile or the [128 x 8] dy tile), both read MN-major
+// D(tmem_d)[64 (M=64 lane layout) x n_cols] (+)= X^T . Y over the 128 rows: X a [128 x 64] tile, Y a [128 x 64] tile or the [128 x 8] dy tile,
+// both read MN-major
 __device__ __forceinline__ void issue_transposed_product(uint32_t tmem_d, const uint8_t* x_tile, const uint8_t* y_tile, int n_cols, uint32_t y_half,
                                                          bool zero_first) {
     const uint32_t idesc = instr_desc(FMT_BF16, 64, n_cols, 1, 1);
-    const uint32_t x0 = smem_u32(x_tile), y0 = smem_u32(y_tile);
-#pragma unroll
+    uint64_t xh = smem_desc(smem_u32(x_tile), 128, 128 * 16), yh = smem_desc(smem_u32(y_tile), 128, 128 * 16);
+    const uint64_t x_lo = TILE_HALF >> 4, y_lo = y_half >> 4;
+#pragma unroll 1
     for (int ks = 0; ks < 8; ++ks) {  // 16 rows per MMA
-        const uint64_t xh = smem_desc(x0 + ks * 256, 128, 128 * 16), xl = smem_desc(x0 + TILE_HALF + ks * 256, 128, 128 * 16);
-        const uint64_t yh = smem_desc(y0 + ks * 256, 128, 128 * 16), yl = smem_desc(y0 + y_half + ks * 256, 128, 128 * 16);
         mma_f16(tmem_d, xh, yh, idesc, (ks > 0 || !zero_first) ? 1u : 0u);
-        mma_f16(tmem_d, xl, yh, idesc, 1);
-        mma_f16(tmem_d, xh, yl, idesc, 1);
+        mma_f16(tmem_d, xh + x_lo, yh, idesc, 1);
+        mma_f16(tmem_d, xh, yh + y_lo, idesc, 1);
+        xh += 256 >> 4, yh += 256 >> 4;
     }
 }
-
-__device__ __forceinline__ uint32_t lane_base(int warp) { return (uint32_t)((warp & 3) * 32) << 16; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------
 template <bool FAST>
-__global__ void __launch_bounds__(128) inr_fwd_tc_kernel(Args a) {
+__global__ void __launch_bounds__(NT, 2) inr_fwd_tc_kernel(Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     TcSmem s(smem_raw, a.net, a.tl, 1);
     const Net& nt = a.net;
     const Tiling& tl = a.tl;
     const int t = threadIdx.x, warp = t >> 5;
+    const int row = t & 127, quarter = warp >> 2;
+    const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(quarter * 16);
     const int L = nt.nl;
     load_weight_tiles(a, s);
     if (warp == 0) tmem_alloc(s.tmem, 64);
@@ -254,10 +277,11 @@ __global__ void __launch_bounds__(128) inr_fwd_tc_kernel(Args a) {
     for (int tile = blockIdx.x; tile < tl.numTiles; tile += gridDim.x) {
         const TileIdx ti = decode_tile(tl, tile);
         tile_prologue(a, s, ti);
-        const int nl = t / tl.TP, j = t % tl.TP;
+        const int nl = row / tl.TP, j = row % tl.TP;
         const bool active = nl < ti.nn && j < ti.np;
-        layer0_to_tile<FAST>(a, s, T, t, active, ti.n0 + nl, j);
-        float h[HID];
+        const float actf = active ? 1.f : 0.f;
+        layer0_to_tile<FAST>(a, s, T, row, quarter, actf, active ? ti.n0 + nl : 0, active ? j : 0);
+#pragma unroll 1
         for (int l = 1; l < L; ++l) {
             fence_proxy_async();
             fence_before_sync();
@@ -270,39 +294,34 @@ __global__ void __launch_bounds__(128) inr_fwd_tc_kernel(Args a) {
             mbar_wait(&s.bars[0], phase);
             phase ^= 1;
             fence_after_sync();
+            float v[16];
+            tmem_ld16(tm + TM_ACC + lane_addr, v);
+            tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                float v[16];
-                tmem_ld16(tm + TM_ACC + lane_base(warp) + g * 16, v);
-                tmem_ld_wait();
+            for (int q = 0; q < 16; ++q) v[q] = act_tanh<FAST>(v[q]) * actf;
+            if (l < L - 1) {
+                store_chunk(T, row, 2 * quarter, v);
+                store_chunk(T, row, 2 * quarter + 1, v + 8);
+            } else {  // output layer: partial dot products of this thread's 16 features
+                for (int c = 0; c < nt.C; ++c) {
+                    float y = 0.f;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int o = g * 16 + q;
-                    float x = 0.f;
-                    if (active) {
-                        if (o < HID) x = act_tanh<FAST>(v[q]);
-                        else if (o == ONE_COL) x = 1.f;
-                    }
-                    v[q] = x;
-                    if (o < HID) h[o] = x;
+                    for (int q = 0; q < 16; ++q) y = fmaf(v[q], s.Wout[c * HPAD + quarter * 16 + q], y);
+                    s.scratch[(row * 4 + quarter) * nt.C + c] = y;
                 }
-                if (l < L - 1) {
-                    store_chunk(T, t, 2 * g, v);
-                    store_chunk(T, t, 2 * g + 1, v + 8);
-                }
-            }
-        }
-        if (active) {
-            const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + nl)) * nt.C) * tl.P + ti.p0 + j;
-            for (int c = 0; c < nt.C; ++c) {
-                float y = s.bout[c];
-#pragma unroll
-                for (int k = 0; k < HID; ++k) y = fmaf(h[k], s.Wout[c * HPAD + k], y);
-                a.img[base + (size_t)c * tl.P] = act_tanh<FAST>(y);
             }
         }
         fence_before_sync();
-        __syncthreads();  // the tile buffer / Cp / beta are rewritten by the next tile
+        __syncthreads();
+        if (quarter == 0 && active) {
+            const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + nl)) * nt.C) * tl.P + ti.p0 + j;
+            for (int c = 0; c < nt.C; ++c) {
+                const float* yp = s.scratch + (row * 4) * nt.C + c;
+                const float y = s.bout[c] + ((yp[0] + yp[nt.C]) + (yp[2 * nt.C] + yp[3 * nt.C]));
+                a.img[base + (size_t)c * tl.P] = act_tanh<FAST>(y);
+            }
+        }
+        __syncthreads();  // scratch / Cp / beta / the tile buffer are rewritten by the next tile
     }
     fence_before_sync();
     __syncthreads();
@@ -313,13 +332,15 @@ __global__ void __launch_bounds__(128) inr_fwd_tc_kernel(Args a) {
 // backward
 // ---------------------------------------------------------------------------------------------------------------
 template <bool FAST>
-__global__ void __launch_bounds__(128) inr_bwd_tc_kernel(Args a) {
+__global__ void __launch_bounds__(NT, 1) inr_bwd_tc_kernel(Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const Net& nt = a.net;
     const Tiling& tl = a.tl;
-    const int L = nt.nl;          // hidden layers; activation tiles T[0..L-1] hold h_1..h_L, one extra rotating tile X
+    const int L = nt.nl;  // hidden layers; activation tiles T[0..L-1] hold h_1..h_L, one extra rotating tile X = T[L]
     TcSmem s(smem_raw, nt, tl, L + 1);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int row = t & 127, quarter = warp >> 2;
+    const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(quarter * 16);
     const bool want_w = a.want_weights != 0;
     load_weight_tiles(a, s);
     if (warp == 0) tmem_alloc(s.tmem, TM_COLS);
@@ -336,26 +357,25 @@ __global__ void __launch_bounds__(128) inr_bwd_tc_kernel(Args a) {
     const uint32_t tm_dwout = TM_DW + (uint32_t)(L - 1) * 64;
     uint32_t ph_acc = 0, ph_done = 0;
     bool first = true;
-    auto Tile = [&](int i) { return s.tiles + (size_t)i * TILE_BYTES; };  // i in [0, L]: h_{i+1} for i < L, X for i == L
-    // dA[n][o] accumulators of this thread: entries e = t + 128*q  ->  (n = e / HID, o = e % HID)
-    constexpr int DA_PER_THREAD = 16;  // covers N*HID <= 2048 entries (N <= 40); larger N falls back to the fp32 path (host check)
-    float dA[DA_PER_THREAD];
-#pragma unroll
-    for (int q = 0; q < DA_PER_THREAD; ++q) dA[q] = 0.f;
+    auto Tile = [&](int i) { return s.tiles + (size_t)i * TILE_BYTES; };
+    // dA[n][o] accumulators of this thread: entries e = t + NT*q  ->  (n = e / HID, o = e % HID); N <= 40 (host check)
+    constexpr int DA_PER_THREAD = 4;
+    float dA[DA_PER_THREAD] = {0.f, 0.f, 0.f, 0.f};
 
     for (int tile = blockIdx.x; tile < tl.numTiles; tile += gridDim.x) {
         const TileIdx ti = decode_tile(tl, tile);
         tile_prologue(a, s, ti);
-        const int nl = t / tl.TP, j = t % tl.TP;
+        const int nl = row / tl.TP, j = row % tl.TP;
         const bool active = nl < ti.nn && j < ti.np;
+        const float actf = active ? 1.f : 0.f;
         if (!first) {  // every MMA of the previous tile (they read the tiles we are about to overwrite) has completed
             mbar_wait(&s.bars[1], ph_done);
             ph_done ^= 1;
             fence_after_sync();
         }
         // ---- forward recompute: h_1 (CUDA cores), h_2..h_L (tensor cores), all kept as tiles
-        layer0_to_tile<FAST>(a, s, Tile(0), t, active, ti.n0 + nl, j);
-        float h[HID];  // h_L of this row (registers), for the output layer
+        layer0_to_tile<FAST>(a, s, Tile(0), row, quarter, actf, active ? ti.n0 + nl : 0, active ? j : 0);
+#pragma unroll 1
         for (int l = 1; l < L; ++l) {
             fence_proxy_async();
             fence_before_sync();
@@ -368,56 +388,46 @@ __global__ void __launch_bounds__(128) inr_bwd_tc_kernel(Args a) {
             mbar_wait(&s.bars[0], ph_acc);
             ph_acc ^= 1;
             fence_after_sync();
+            float v[16];
+            tmem_ld16(tm + TM_ACC + lane_addr, v);
+            tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                float v[16];
-                tmem_ld16(tm + TM_ACC + lane_base(warp) + g * 16, v);
-                tmem_ld_wait();
+            for (int q = 0; q < 16; ++q) v[q] = act_tanh<FAST>(v[q]) * actf;
+            store_chunk(Tile(l), row, 2 * quarter, v);
+            store_chunk(Tile(l), row, 2 * quarter + 1, v + 8);
+            if (l == L - 1) {  // output layer: partial dot products of this thread's 16 features of h_L
+                for (int c = 0; c < nt.C; ++c) {
+                    float y = 0.f;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int o = g * 16 + q;
-                    float x = 0.f;
-                    if (active) {
-                        if (o < HID) x = act_tanh<FAST>(v[q]);
-                        else if (o == ONE_COL) x = 1.f;
-                    }
-                    v[q] = x;
-                    if (l == L - 1 && o < HID) h[o] = x;
+                    for (int q = 0; q < 16; ++q) y = fmaf(v[q], s.Wout[c * HPAD + quarter * 16 + q], y);
+                    s.scratch[(row * 4 + quarter) * nt.C + c] = y;
                 }
-                store_chunk(Tile(l), t, 2 * g, v);
-                store_chunk(Tile(l), t, 2 * g + 1, v + 8);
             }
         }
-        // ---- output layer (CUDA cores): y, dy, dz_{L-1} = (Wout^T dy) * (1 - h_L^2)  ->  tile X; dy -> dy tile
+        __syncthreads();
+        // ---- output layer (CUDA cores): y, dy = g (1 - y^2), dz_{L-1} = (Wout^T dy) (1 - h_L^2) -> tile X; dy -> dy tile
         {
             float dy[4] = {0.f, 0.f, 0.f, 0.f};
-            if (active) {
-                const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + nl)) * nt.C) * tl.P + ti.p0 + j;
-                for (int c = 0; c < nt.C; ++c) {
-                    float y = s.bout[c];
-#pragma unroll
-                    for (int k = 0; k < HID; ++k) y = fmaf(h[k], s.Wout[c * HPAD + k], y);
-                    y = act_tanh<FAST>(y);
-                    dy[c] = a.g_img[base + (size_t)c * tl.P] * (1.f - y * y);
-                }
+            const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + (active ? nl : 0))) * nt.C) * tl.P + ti.p0 + (active ? j : 0);
+            for (int c = 0; c < nt.C; ++c) {
+                const float* yp = s.scratch + (row * 4) * nt.C + c;
+                const float y = act_tanh<FAST>(s.bout[c] + ((yp[0] + yp[nt.C]) + (yp[2 * nt.C] + yp[3 * nt.C])));
+                const float g = active ? a.g_img[base + (size_t)c * tl.P] : 0.f;
+                dy[c] = g * (1.f - y * y);
             }
+            float hv[16], v[16];
+            load_chunk(Tile(L - 1), row, 2 * quarter, hv);
+            load_chunk(Tile(L - 1), row, 2 * quarter + 1, hv + 8);
 #pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {
-                float v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int k = c8 * 8 + q;
-                    float dh = 0.f;
-                    if (k < HID) {
-                        for (int c = 0; c < nt.C; ++c) dh = fmaf(s.Wout[c * HPAD + k], dy[c], dh);
-                        dh *= (1.f - h[k] * h[k]);
-                    }
-                    v[q] = active ? dh : 0.f;
-                }
-                store_chunk(Tile(L), t, c8, v);
+            for (int q = 0; q < 16; ++q) {
+                float dh = 0.f;
+                for (int c = 0; c < nt.C; ++c) dh = fmaf(s.Wout[c * HPAD + quarter * 16 + q], dy[c], dh);
+                v[q] = dh * (1.f - hv[q] * hv[q]);  // padding columns: Wout == 0; constant-1 column: 1 - 1 == 0
             }
-            if (want_w) {  // dy as a [128 x 8] split-bf16 tile (one 16-byte chunk per row)
-                uint32_t hi[4], lo[4];
+            store_chunk(Tile(L), row, 2 * quarter, v);
+            store_chunk(Tile(L), row, 2 * quarter + 1, v + 8);
+            if (want_w && quarter == 0) {  // dy as a [128 x 8] split-bf16 tile (one 16-byte chunk per row)
+                uint32_t hi[2], lo[2];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const __nv_bfloat162 h2 = __floats2bfloat162_rn(dy[2 * q], dy[2 * q + 1]);
@@ -425,20 +435,20 @@ __global__ void __launch_bounds__(128) inr_bwd_tc_kernel(Args a) {
                     const __nv_bfloat162 l2 = __floats2bfloat162_rn(dy[2 * q] - hf.x, dy[2 * q + 1] - hf.y);
                     hi[q] = *reinterpret_cast<const uint32_t*>(&h2), lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
-                hi[2] = hi[3] = lo[2] = lo[3] = 0u;
-                *reinterpret_cast<uint4*>(s.dy + t * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(s.dy + DY_HALF + t * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4*>(s.dy + row * 16) = make_uint4(hi[0], hi[1], 0u, 0u);
+                *reinterpret_cast<uint4*>(s.dy + DY_HALF + row * 16) = make_uint4(lo[0], lo[1], 0u, 0u);
             }
         }
-        // ---- layers L-1 .. 1.  dz_l sits in `src`; h_l in Tile(l-1); dz_{l-1} goes to `dst` (a tile no pending MMA reads)
+        // ---- layers L-1 .. 1.  dz_l sits in tile `src`; h_l in Tile(l-1); dz_{l-1} goes to `dst` (a tile no pending MMA reads)
         int src = L, dst = L - 1;
+#pragma unroll 1
         for (int l = L - 1; l >= 1; --l) {
             fence_proxy_async();
             fence_before_sync();
             __syncthreads();
             if (t == 0) {
                 fence_after_sync();
-                if (want_w && l == L - 1)  // output layer: dWout[c][i] (and dbout in column ONE_COL) = sum_r h_L[r][i] dy[r][c]
+                if (want_w && l == L - 1)  // output layer: dWout[c][i] (dbout in column ONE_COL) = sum_r h_L[r][i] dy[r][c]
                     issue_transposed_product(tm + tm_dwout, Tile(L - 1), s.dy, 8, DY_HALF, first);
                 issue_rows_x_weights(tm + TM_ACC, Tile(src), s.wt + (size_t)(l - 1) * WT_BYTES, 1);
                 mma_commit(&s.bars[0]);
@@ -449,40 +459,35 @@ __global__ void __launch_bounds__(128) inr_bwd_tc_kernel(Args a) {
             mbar_wait(&s.bars[0], ph_acc);
             ph_acc ^= 1;
             fence_after_sync();
-            // dz_{l-1}[k] = dh_l[k] * (1 - h_l[k]^2)
+            // dz_{l-1}[k] = dh_l[k] (1 - h_l[k]^2)   (h_l[50] == 1 zeroes the bias column; padding columns of W are 0)
+            float v[16], hv[16];
+            tmem_ld16(tm + TM_ACC + lane_addr, v);
+            load_chunk(Tile(l - 1), row, 2 * quarter, hv);
+            load_chunk(Tile(l - 1), row, 2 * quarter + 1, hv + 8);
+            tmem_ld_wait();
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                float v[16], hv[16];
-                tmem_ld16(tm + TM_ACC + lane_base(warp) + g * 16, v);
-                load_chunk(Tile(l - 1), t, 2 * g, hv);
-                load_chunk(Tile(l - 1), t, 2 * g + 1, hv + 8);
-                tmem_ld_wait();
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int k = g * 16 + q;
-                    v[q] = (active && k < HID) ? v[q] * (1.f - hv[q] * hv[q]) : 0.f;
-                }
-                store_chunk(Tile(dst), t, 2 * g, v);
-                store_chunk(Tile(dst), t, 2 * g + 1, v + 8);
-            }
+            for (int q = 0; q < 16; ++q) v[q] = v[q] * (1.f - hv[q] * hv[q]);
+            store_chunk(Tile(dst), row, 2 * quarter, v);
+            store_chunk(Tile(dst), row, 2 * quarter + 1, v + 8);
             // rotate: the old src is free once the NEXT step's data-gradient MMAs (issued after this step's dW MMAs) have completed
             src = dst;
-            dst = (src == L) ? L - 1 : L;  // the free tile alternates between T[L-1] and X
+            dst = (src == L) ? L - 1 : L;
         }
         __syncthreads();  // dz_0 (tile `src`) complete
         // ---- layer 0: G0[j][o] = sum_n dz0, dA[n][o] += sum_j dz0   (CUDA cores, from the split-bf16 tile)
         const uint8_t* Z = Tile(src);
-        for (int i = t; i < ti.np * SHP; i += 128) {
+        float* G0s = s.scratch;
+        for (int i = t; i < ti.np * SHP; i += NT) {
             const int jj = i / SHP, o = i % SHP;
             float sum = 0.f;
             if (o < HID)
                 for (int n = 0; n < ti.nn; ++n) sum += load_elem(Z, n * tl.TP + jj, o);
-            s.G0s[i] = sum;
+            G0s[i] = sum;
         }
         if (want_w) {
 #pragma unroll
             for (int q = 0; q < DA_PER_THREAD; ++q) {
-                const int e = t + 128 * q;
+                const int e = t + NT * q;
                 if (e < ti.nn * HID) {
                     const int n = e / HID, o = e % HID;
                     float sum = 0.f;
@@ -494,15 +499,15 @@ __global__ void __launch_bounds__(128) inr_bwd_tc_kernel(Args a) {
         __syncthreads();
         if (want_w) {
             float* gdst = a.G0 + ((size_t)ti.d * tl.P + ti.p0) * SHP;
-            for (int i = t; i < ti.np * SHP; i += 128) gdst[i] = s.G0s[i];
+            for (int i = t; i < ti.np * SHP; i += NT) gdst[i] = G0s[i];
         }
         if (a.want_affine) {
             const int pe = nt.pe;
-            for (int i = t; i < ti.np * pe; i += 128) {
+            for (int i = t; i < ti.np * pe; i += NT) {
                 const int jj = i / pe, m = i % pe;
                 const float4* ws_ = reinterpret_cast<const float4*>(a.W0cT + (size_t)m * SHP);
                 const float4* wc_ = reinterpret_cast<const float4*>(a.W0cT + (size_t)(pe + m) * SHP);
-                const float4* g4 = reinterpret_cast<const float4*>(s.G0s + jj * SHP);
+                const float4* g4 = reinterpret_cast<const float4*>(G0s + jj * SHP);
                 float ds = 0.f, dc = 0.f;
                 for (int o4 = 0; o4 < SHP / 4; ++o4) {
                     const float4 g = g4[o4], a4 = __ldg(ws_ + o4), b4 = __ldg(wc_ + o4);
@@ -548,37 +553,39 @@ __global__ void __launch_bounds__(128) inr_bwd_tc_kernel(Args a) {
         float* p_db = part + (size_t)(L - 1) * HID * HID;
         float* p_dWout = p_db + (size_t)(L - 1) * SHP;
         float* p_dA = p_dWout + (size_t)nt.C * SHP + 4;
-        const int o = 16 * warp + lane;  // M=64 accumulator layout: row o -> lane (o/16)*32 + o%16
-        for (int l = 1; l < L; ++l) {
+        if (warp < 4) {  // M=64 accumulator layout: row o -> lane (o/16)*32 + o%16
+            const int o = 16 * warp + lane;
+            const uint32_t lb = (uint32_t)(warp * 32) << 16;
+#pragma unroll 1
+            for (int l = 1; l < L; ++l) {
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) {
+                    float v[16];
+                    tmem_ld16(tm + TM_DW + (uint32_t)(l - 1) * 64 + lb + g * 16, v);
+                    tmem_ld_wait();
+                    if (lane < 16 && o < HID) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                float v[16];
-                tmem_ld16(tm + TM_DW + (uint32_t)(l - 1) * 64 + lane_base(warp) + g * 16, v);
-                tmem_ld_wait();
-                if (lane < 16 && o < HID) {
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const int i = g * 16 + q;
-                        if (i < HID) p_dW[(size_t)(l - 1) * HID * HID + o * HID + i] = first ? 0.f : v[q];
-                        else if (i == ONE_COL) p_db[(l - 1) * SHP + o] = first ? 0.f : v[q];
+                        for (int q = 0; q < 16; ++q) {
+                            const int i = g * 16 + q;
+                            if (i < HID) p_dW[(size_t)(l - 1) * HID * HID + o * HID + i] = v[q];
+                            else if (i == ONE_COL) p_db[(l - 1) * SHP + o] = v[q];
+                        }
                     }
                 }
             }
-        }
-        {
             float v[16];
-            tmem_ld16(tm + tm_dwout + lane_base(warp), v);
+            tmem_ld16(tm + tm_dwout + lb, v);
             tmem_ld_wait();
             if (lane < 16) {  // row i = o of D[i][c]
                 for (int c = 0; c < nt.C; ++c) {
-                    if (o < HID) p_dWout[c * SHP + o] = first ? 0.f : v[c];
-                    else if (o == ONE_COL) p_dWout[nt.C * SHP + c] = first ? 0.f : v[c];
+                    if (o < HID) p_dWout[c * SHP + o] = v[c];
+                    else if (o == ONE_COL) p_dWout[nt.C * SHP + c] = v[c];
                 }
             }
         }
 #pragma unroll
         for (int q = 0; q < DA_PER_THREAD; ++q) {
-            const int e = t + 128 * q;
+            const int e = t + NT * q;
             if (e < tl.NC * HID) p_dA[(e / HID) * SHP + e % HID] = dA[q];
         }
     }
@@ -590,11 +597,10 @@ __global__ void __launch_bounds__(128) inr_bwd_tc_kernel(Args a) {
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static int check_tc(const Net& nt, int N) {
+static int check_tc(const Net& nt) {
     LMR_CHECK_ARG(nt.hid == HID, "tensor-core path: hidden width %d not supported (50)", nt.hid);
     LMR_CHECK_ARG(nt.nl >= 2 && nt.nl <= 4, "tensor-core path: n_hidden %d out of range [2,4]", nt.nl);
     LMR_CHECK_ARG(nt.pe <= 64, "tensor-core path: pe_dim %d > 64", nt.pe);
-    (void)N;
     return 0;
 }
 
@@ -612,7 +618,7 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
             cudaStream_t st) {
     Net nt;
     if (int rc = make_net(desc, &nt)) return rc;
-    if (int rc = check_tc(nt, N)) return rc;
+    if (int rc = check_tc(nt)) return rc;
     LMR_CHECK_ARG(N >= 1 && P >= 1 && D >= 1, "inr_forward: bad sizes N=%d P=%d D=%d", N, P, D);
     const Tiling tl = make_tiling(N, P, D, TP_CAP_TC);
     const WsLayout wl = ws_layout(nt, tl, false);
@@ -630,10 +636,10 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
     static size_t c0 = 0, c1 = 0;
     if (precision == LMR_PREC_BF16X3_FAST) {
         if (int rc = set_smem(inr_fwd_tc_kernel<true>, smem, &c0)) return rc;
-        inr_fwd_tc_kernel<true><<<grid_x, 128, smem, st>>>(a);
+        inr_fwd_tc_kernel<true><<<grid_x, NT, smem, st>>>(a);
     } else {
         if (int rc = set_smem(inr_fwd_tc_kernel<false>, smem, &c1)) return rc;
-        inr_fwd_tc_kernel<false><<<grid_x, 128, smem, st>>>(a);
+        inr_fwd_tc_kernel<false><<<grid_x, NT, smem, st>>>(a);
     }
     LMR_LAUNCH_OK();
     return 0;
@@ -644,7 +650,7 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
              float* g_scalings, float* g_shears, float* g_translation, void* ws, size_t ws_bytes, int precision, cudaStream_t st) {
     Net nt;
     if (int rc = make_net(desc, &nt)) return rc;
-    if (int rc = check_tc(nt, N)) return rc;
+    if (int rc = check_tc(nt)) return rc;
     LMR_CHECK_ARG(N >= 1 && P >= 1 && D >= 1, "inr_backward: bad sizes N=%d P=%d D=%d", N, P, D);
     LMR_CHECK_ARG(N <= 40, "inr_backward (tensor-core path): N=%d latents per step not supported (max 40); use the fp32 path", N);
     const bool want_aff = g_angles != nullptr;
@@ -670,10 +676,10 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     static size_t c0 = 0, c1 = 0;
     if (precision == LMR_PREC_BF16X3_FAST) {
         if (int rc = set_smem(inr_bwd_tc_kernel<true>, smem, &c0)) return rc;
-        inr_bwd_tc_kernel<true><<<wl.gridMain, 128, smem, st>>>(a);
+        inr_bwd_tc_kernel<true><<<wl.gridMain, NT, smem, st>>>(a);
     } else {
         if (int rc = set_smem(inr_bwd_tc_kernel<false>, smem, &c1)) return rc;
-        inr_bwd_tc_kernel<false><<<wl.gridMain, 128, smem, st>>>(a);
+        inr_bwd_tc_kernel<false><<<wl.gridMain, NT, smem, st>>>(a);
     }
     LMR_LAUNCH_OK();
     if (a.want_weights) {
