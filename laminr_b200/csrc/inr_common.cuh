@@ -55,6 +55,8 @@ struct Args {
     float* alpha;  // [N, 2*ape]
     float* Avec;   // [N, HP]
     float* W0cT;   // [2*pe, HP]
+    float* Cpg;    // [D*P, HP]  layer-0 coordinate part Cp[d,p][o] = sum_k beta[d,p][k] W0c[o][k]   (tensor-core path)
+    int want_cp;
     // forward
     float* img;  // [D,N,C,P]
     // backward
@@ -62,53 +64,13 @@ struct Args {
     float* G0;        // [D*P, HP]   (learn: sum_n delta0)
     float* partials;  // [grid, partial_size]
     float* affpart;   // [D, tilesP, 6]  (match)
+    float* dAred;     // [N, HP]  sum over CTAs of the dA partials
     int want_weights, want_affine;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
 // prep: latent encoding (inr.py:371-386,401-409), A[n] = b0 + W0[:,1:1+2a] alpha_n, packed transpose of W0's coord block
 // ---------------------------------------------------------------------------------------------------------------
-template <int HID>
-__global__ void prep_kernel(Args a) {
-    constexpr int HP = (HID + 3) / 4 * 4;
-    const Net& nt = a.net;
-    const int N = a.tl.N, na = 2 * nt.ape, nb = 2 * nt.pe;
-    const float* W0 = a.params;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * nt.ape; i += gridDim.x * blockDim.x) {
-        const int n = i / nt.ape, m = i % nt.ape;
-        const float g = a.grid[n];
-        const float phi = sinf(g) * a.auxB[m] + cosf(g) * a.auxB[nt.ape + m];
-        a.alpha[n * na + m] = sinf(phi);
-        a.alpha[n * na + nt.ape + m] = cosf(phi);
-    }
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb * HP; i += gridDim.x * blockDim.x) {
-        const int k = i / HP, o = i % HP;
-        a.W0cT[i] = o < HID ? W0[(size_t)o * nt.in_dim + 1 + na + k] : 0.f;
-    }
-}
-
-template <int HID>
-__global__ void prep_A_kernel(Args a) {
-    constexpr int HP = (HID + 3) / 4 * 4;
-    const Net& nt = a.net;
-    const int N = a.tl.N, na = 2 * nt.ape;
-    const float* W0 = a.params;
-    const float* b0 = a.params + nt.offb(0);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N * HP; i += gridDim.x * blockDim.x) {
-        const int n = i / HP, o = i % HP;
-        float acc = 0.f;
-        if (o < HID) {
-            acc = b0[o];
-            const float* w = W0 + (size_t)o * nt.in_dim + 1;
-            const float* al = a.alpha + (size_t)n * na;
-            for (int k = 0; k < na; ++k) acc = fmaf(w[k], al[k], acc);
-        } else if (o == HID) {
-            acc = 20.f;  // tanh(20) == 1 in fp32: the tensor-core path keeps a constant-1 feature (bias column) in slot HID
-        }
-        a.Avec[i] = acc;
-    }
-}
-
 __host__ __device__ inline size_t partial_size(const Net& nt, const Tiling& tl, int HP) {
     return (size_t)(nt.nl - 1) * nt.hid * nt.hid + (size_t)(nt.nl - 1) * HP + (size_t)nt.C * HP + 4 + (size_t)tl.NC * HP;
 }
@@ -143,6 +105,89 @@ __device__ inline float2 transformed_coord(const Args& a, const float* affc, int
     o0 += affc[8], o1 += affc[9];
     if (a.aff.clamp) o0 = fminf(fmaxf(o0, -1.f), 1.f), o1 = fminf(fmaxf(o1, -1.f), 1.f);
     return make_float2(o0, o1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prep (ONE launch, heterogeneous blocks):
+//   blocks [0, N)      latent n: alpha_n = sin/cos(a_n.auxB) (inr.py:371-386,401-409), A[n] = b0 + W0[:,1:1+2a] alpha_n, A[n][HID] = 20
+//   block  N           packed transpose W0cT[k][o] of W0's coordinate block
+//   blocks (N, ...)    (want_cp) 64 pixels each: beta = sin/cos(coords.B) (inr.py:390-397), Cp[d,p][o] = sum_k beta[k] W0c[o][k]
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PREP_PIX = 64;
+
+template <int HID>
+__global__ void __launch_bounds__(256) prep_all_kernel(Args a) {
+    constexpr int HP = (HID + 3) / 4 * 4;
+    extern __shared__ __align__(16) float psm[];
+    const Net& nt = a.net;
+    const int N = a.tl.N, na = 2 * nt.ape, nb = 2 * nt.pe, pe = nt.pe;
+    const float* W0 = a.params;
+    const int bid = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (bid < N) {
+        float* als = psm;  // [na]
+        const float g = a.grid[bid];
+        float sg, cg;
+        sincosf(g, &sg, &cg);
+        for (int m = t; m < nt.ape; m += blockDim.x) {
+            float sn, cs;
+            sincosf(sg * a.auxB[m] + cg * a.auxB[nt.ape + m], &sn, &cs);
+            als[m] = sn, als[nt.ape + m] = cs;
+            a.alpha[(size_t)bid * na + m] = sn, a.alpha[(size_t)bid * na + nt.ape + m] = cs;
+        }
+        __syncthreads();
+        const float* b0 = a.params + nt.offb(0);
+        for (int o = warp; o < HP; o += blockDim.x / 32) {  // one warp per output: coalesced reads of W0's row
+            float acc = 0.f;
+            if (o < HID) {
+                const float* w = W0 + (size_t)o * nt.in_dim + 1;
+                for (int k = lane; k < na; k += 32) acc = fmaf(w[k], als[k], acc);
+                acc = warp_sum(acc) + b0[o];
+            } else if (o == HID) {
+                acc = 20.f;  // tanh(20) == 1 in fp32: the tensor-core path keeps a constant-1 feature (bias column) in slot HID
+            }
+            if (lane == 0) a.Avec[(size_t)bid * HP + o] = acc;
+        }
+    } else if (bid == N) {
+        for (int i = t; i < HID * nb; i += blockDim.x) {  // coalesced read over k
+            const int o = i / nb, k = i % nb;
+            a.W0cT[(size_t)k * HP + o] = W0[(size_t)o * nt.in_dim + 1 + na + k];
+        }
+        for (int i = t; i < nb * (HP - HID); i += blockDim.x) a.W0cT[(size_t)(i / (HP - HID)) * HP + HID + i % (HP - HID)] = 0.f;
+    } else {
+        float* Wc = psm;             // [nb][HP]
+        float* bet = Wc + nb * HP;   // [PREP_PIX][nb]
+        const int total = a.tl.D * a.tl.P;
+        const int q0 = (bid - N - 1) * PREP_PIX, nq = min(PREP_PIX, total - q0);
+        for (int i = t; i < HID * nb; i += blockDim.x) {
+            const int o = i / nb, k = i % nb;
+            Wc[k * HP + o] = W0[(size_t)o * nt.in_dim + 1 + na + k];
+        }
+        for (int i = t; i < nb * (HP - HID); i += blockDim.x) Wc[(i / (HP - HID)) * HP + HID + i % (HP - HID)] = 0.f;
+        for (int i = t; i < nq * pe; i += blockDim.x) {
+            const int jj = i / pe, m = i % pe;
+            const int q = q0 + jj;
+            float cst[10];
+            if (a.has_aff) affine_consts(a.aff, q / a.tl.P, cst);
+            const float2 c = transformed_coord(a, cst, q % a.tl.P);
+            float sn, cs;
+            sincosf(c.x * a.B[m] + c.y * a.B[pe + m], &sn, &cs);
+            bet[jj * nb + m] = sn, bet[jj * nb + pe + m] = cs;
+        }
+        __syncthreads();
+        for (int i = t; i < nq * (HP / 4); i += blockDim.x) {
+            const int jj = i / (HP / 4), o4 = i % (HP / 4);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* bj = bet + jj * nb;
+            const float4* w = reinterpret_cast<const float4*>(Wc) + o4;
+#pragma unroll 4
+            for (int k = 0; k < nb; ++k) {
+                const float bk = bj[k];
+                const float4 ww = w[k * (HP / 4)];
+                acc.x = fmaf(bk, ww.x, acc.x), acc.y = fmaf(bk, ww.y, acc.y), acc.z = fmaf(bk, ww.z, acc.z), acc.w = fmaf(bk, ww.w, acc.w);
+            }
+            reinterpret_cast<float4*>(a.Cpg + (size_t)(q0 + jj) * HP)[o4] = acc;
+        }
+    }
 }
 
 struct TileIdx {
@@ -233,57 +278,72 @@ __global__ void __launch_bounds__(256) l0_partial_kernel(Args a, float* l0part /
     }
 }
 
-// learn: deterministic reduction of every partial into g_params (torch layout)
+// learn: deterministic reductions of the per-CTA partials into g_params (torch layout).
+// (1) one thread per output element sums it over the partial blocks (coalesced across threads): hidden / output layers, the
+//     coordinate block of W0 (from l0part) and dAred[n][o]; (2) the latent block of W0 and b0 follow from dAred.
 template <int HID>
-__global__ void finish_weights_kernel(Args a, const float* l0part, int nPartMain, int nPartL0, float* g_params) {
+__global__ void __launch_bounds__(128) reduce_partials_kernel(Args a, const float* l0part, int nPartMain, int nPartL0, float* g_params) {
     constexpr int HP = (HID + 3) / 4 * 4;
     const Net& nt = a.net;
     const Tiling& tl = a.tl;
     const size_t psz = partial_size(nt, tl, HP);
     const int L = nt.nl, na = 2 * nt.ape, nb = 2 * nt.pe;
     const size_t total = nt.count();
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t offA = (size_t)(L - 1) * HID * HID + (size_t)(L - 1) * HP + (size_t)nt.C * HP + 4;
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= total + (size_t)tl.N * HP) return;
+    if (i >= total) {  // dAred
+        const size_t e = i - total;
+        float s0 = 0.f, s1 = 0.f;
+        int b = 0;
+        for (; b + 1 < nPartMain; b += 2) s0 += a.partials[b * psz + offA + e], s1 += a.partials[(b + 1) * psz + offA + e];
+        if (b < nPartMain) s0 += a.partials[b * psz + offA + e];
+        a.dAred[e] = s0 + s1;
+        return;
+    }
+    const float* src = a.partials;
+    size_t off = 0, stride = psz;
+    int nPart = nPartMain;
+    if (i < nt.size0()) {
+        if (i >= (size_t)nt.hid * nt.in_dim) return;  // b0: finish_w0a
+        const int o = i / nt.in_dim, col = i % nt.in_dim;
+        if (col < 1 + na) return;                      // template / latent columns: finish_w0a
+        src = l0part, off = (size_t)o * nb + (col - 1 - na), stride = (size_t)HID * nb, nPart = nPartL0;
+    } else if (i < nt.offWout()) {
+        const size_t r = i - nt.size0();
+        const int l = r / nt.sizeh();
+        const size_t w = r % nt.sizeh();
+        off = w < (size_t)HID * HID ? (size_t)l * HID * HID + w : (size_t)(L - 1) * HID * HID + (size_t)l * HP + (w - (size_t)HID * HID);
+    } else {
+        const size_t r = i - nt.offWout();
+        const size_t base = (size_t)(L - 1) * HID * HID + (size_t)(L - 1) * HP;
+        off = r < (size_t)nt.C * HID ? base + (r / HID) * HP + (r % HID) : base + (size_t)nt.C * HP + (r - (size_t)nt.C * HID);
+    }
+    float s0 = 0.f, s1 = 0.f;
+    int b = 0;
+    for (; b + 1 < nPart; b += 2) s0 += src[b * stride + off], s1 += src[(b + 1) * stride + off];
+    if (b < nPart) s0 += src[b * stride + off];
+    g_params[i] = s0 + s1;
+}
+
+template <int HID>
+__global__ void __launch_bounds__(128) finish_w0a_kernel(Args a, float* g_params) {
+    constexpr int HP = (HID + 3) / 4 * 4;
+    const Net& nt = a.net;
+    const int N = a.tl.N, na = 2 * nt.ape;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nW = HID * (1 + na);
+    if (i < nW) {
+        const int o = i / (1 + na), col = i % (1 + na);
+        float sum = 0.f;  // col 0: the template input is the constant 0 (inr.py:200-205)
+        if (col > 0)
+            for (int n = 0; n < N; ++n) sum = fmaf(a.dAred[(size_t)n * HP + o], a.alpha[(size_t)n * na + col - 1], sum);
+        g_params[(size_t)o * nt.in_dim + col] = sum;
+    } else if (i < nW + HID) {
+        const int o = i - nW;
         float sum = 0.f;
-        if (i < nt.size0()) {
-            if (i < (size_t)nt.hid * nt.in_dim) {
-                const int o = i / nt.in_dim, col = i % nt.in_dim;
-                if (col == 0) {
-                    sum = 0.f;  // template input is the constant 0 (inr.py:200-205)
-                } else if (col < 1 + na) {
-                    const int k = col - 1;
-                    const size_t offA = (size_t)(L - 1) * HID * HID + (size_t)(L - 1) * HP + (size_t)nt.C * HP + 4;
-                    for (int n = 0; n < tl.N; ++n) {
-                        float dA = 0.f;
-                        for (int b = 0; b < nPartMain; ++b) dA += a.partials[b * psz + offA + (size_t)n * HP + o];
-                        sum = fmaf(dA, a.alpha[(size_t)n * na + k], sum);
-                    }
-                } else {
-                    const int k = col - 1 - na;
-                    for (int b = 0; b < nPartL0; ++b) sum += l0part[(size_t)b * HID * nb + o * nb + k];
-                }
-            } else {
-                const int o = i - (size_t)nt.hid * nt.in_dim;
-                const size_t offA = (size_t)(L - 1) * HID * HID + (size_t)(L - 1) * HP + (size_t)nt.C * HP + 4;
-                for (int n = 0; n < tl.N; ++n)
-                    for (int b = 0; b < nPartMain; ++b) sum += a.partials[b * psz + offA + (size_t)n * HP + o];
-            }
-        } else if (i < nt.offWout()) {
-            const size_t r = i - nt.size0();
-            const int l = r / nt.sizeh();  // hidden layer l+1
-            const size_t w = r % nt.sizeh();
-            size_t off;
-            if (w < (size_t)HID * HID) off = (size_t)l * HID * HID + w;
-            else off = (size_t)(L - 1) * HID * HID + (size_t)l * HP + (w - (size_t)HID * HID);
-            for (int b = 0; b < nPartMain; ++b) sum += a.partials[b * psz + off];
-        } else {
-            const size_t r = i - nt.offWout();
-            const size_t base = (size_t)(L - 1) * HID * HID + (size_t)(L - 1) * HP;
-            size_t off;
-            if (r < (size_t)nt.C * HID) off = base + (r / HID) * HP + (r % HID);
-            else off = base + (size_t)nt.C * HP + (r - (size_t)nt.C * HID);
-            for (int b = 0; b < nPartMain; ++b) sum += a.partials[b * psz + off];
-        }
-        g_params[i] = sum;
+        for (int n = 0; n < N; ++n) sum += a.dAred[(size_t)n * HP + o];
+        g_params[nt.offb(0) + o] = sum;
     }
 }
 
@@ -333,11 +393,11 @@ static __global__ void finish_affine_kernel(Args a, float* g_angles, float* g_sc
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 struct WsLayout {
-    size_t alpha, Avec, W0cT, G0, partials, l0part, affpart, total;
+    size_t alpha, Avec, W0cT, Cpg, G0, partials, l0part, affpart, dAred, total;
     int gridMain, gridL0;
 };
 
-static inline WsLayout ws_layout(const Net& nt, const Tiling& tl, bool bwd) {
+static inline WsLayout ws_layout(const Net& nt, const Tiling& tl, bool bwd, bool want_cp = false) {
     const int HP = (nt.hid + 3) / 4 * 4;
     WsLayout w;
     size_t off = 0;
@@ -349,16 +409,18 @@ static inline WsLayout ws_layout(const Net& nt, const Tiling& tl, bool bwd) {
     w.alpha = take((size_t)tl.N * 2 * nt.ape);
     w.Avec = take((size_t)tl.N * HP);
     w.W0cT = take((size_t)2 * nt.pe * HP);
+    w.Cpg = want_cp ? take((size_t)tl.D * tl.P * HP) : 0;
     w.gridMain = tl.numTiles < num_sms() ? tl.numTiles : num_sms();
     const int total = tl.D * tl.P;
     const int nchunks = (total + L0_CHUNK - 1) / L0_CHUNK;
     w.gridL0 = nchunks < num_sms() ? nchunks : num_sms();
-    w.G0 = w.partials = w.l0part = w.affpart = 0;
+    w.G0 = w.partials = w.l0part = w.affpart = w.dAred = 0;
     if (bwd) {
         w.G0 = take((size_t)tl.D * tl.P * HP);
         w.partials = take((size_t)w.gridMain * partial_size(nt, tl, HP));
         w.l0part = take((size_t)w.gridL0 * nt.hid * 2 * nt.pe);
         w.affpart = take((size_t)tl.D * tl.tilesP * 6);
+        w.dAred = take((size_t)tl.N * HP);
     }
     w.total = off;
     return w;
@@ -393,6 +455,9 @@ static inline int fill_args(Args& a, const Net& nt, const Tiling& tl, const floa
     a.alpha = reinterpret_cast<float*>(base + wl.alpha);
     a.Avec = reinterpret_cast<float*>(base + wl.Avec);
     a.W0cT = reinterpret_cast<float*>(base + wl.W0cT);
+    a.Cpg = reinterpret_cast<float*>(base + wl.Cpg);
+    a.want_cp = 0;
+    a.dAred = reinterpret_cast<float*>(base + wl.dAred);
     a.G0 = reinterpret_cast<float*>(base + wl.G0);
     a.partials = reinterpret_cast<float*>(base + wl.partials);
     a.affpart = reinterpret_cast<float*>(base + wl.affpart);
@@ -402,13 +467,33 @@ static inline int fill_args(Args& a, const Net& nt, const Tiling& tl, const floa
 
 template <int HID>
 static int launch_prep(const Args& a, cudaStream_t st) {
-    prep_kernel<HID><<<4, 256, 0, st>>>(a);
-    LMR_LAUNCH_OK();
-    prep_A_kernel<HID><<<(a.tl.N * ((HID + 3) / 4 * 4) + 255) / 256, 256, 0, st>>>(a);
+    constexpr int HP = (HID + 3) / 4 * 4;
+    const int nb = 2 * a.net.pe;
+    const int cp_blocks = a.want_cp ? (a.tl.D * a.tl.P + PREP_PIX - 1) / PREP_PIX : 0;
+    size_t smem = (size_t)2 * a.net.ape * sizeof(float);
+    if (a.want_cp) smem = ((size_t)nb * HP + (size_t)PREP_PIX * nb) * sizeof(float);
+    static size_t cache = 0;
+    if (smem > 48 * 1024 && smem > cache) {
+        LMR_CUDA_OK(cudaFuncSetAttribute(prep_all_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cache = smem;
+    }
+    prep_all_kernel<HID><<<a.tl.N + 1 + cp_blocks, 256, smem, st>>>(a);
     LMR_LAUNCH_OK();
     return 0;
 }
 
+// the two launches that turn the per-CTA partials into g_params
+template <int HID>
+static int launch_finish_weights(const Args& a, const float* l0part, int nPartMain, int nPartL0, float* g_params, cudaStream_t st) {
+    constexpr int HP = (HID + 3) / 4 * 4;
+    const size_t n1 = a.net.count() + (size_t)a.tl.N * HP;
+    reduce_partials_kernel<HID><<<(int)((n1 + 127) / 128), 128, 0, st>>>(a, l0part, nPartMain, nPartL0, g_params);
+    LMR_LAUNCH_OK();
+    const int n2 = HID * (1 + 2 * a.net.ape) + HID;
+    finish_w0a_kernel<HID><<<(n2 + 127) / 128, 128, 0, st>>>(a, g_params);
+    LMR_LAUNCH_OK();
+    return 0;
+}
 
 }  // namespace inr
 }  // namespace lmr

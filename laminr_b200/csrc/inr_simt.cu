@@ -480,9 +480,7 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
         }
         l0_partial_kernel<50><<<wl.gridL0, 256, smem0, st>>>(a, l0part);
         LMR_LAUNCH_OK();
-        const int blocks = (int)((nt.count() + 127) / 128);
-        finish_weights_kernel<50><<<blocks, 128, 0, st>>>(a, l0part, wl.gridMain, wl.gridL0, g_params);
-        LMR_LAUNCH_OK();
+        if (int rc = launch_finish_weights<50>(a, l0part, wl.gridMain, wl.gridL0, g_params, st)) return rc;
     }
     if (want_aff) {
         finish_affine_kernel<<<D, 128, 0, st>>>(a, g_angles, g_scalings, g_shears, g_translation);

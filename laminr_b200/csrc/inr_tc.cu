@@ -55,22 +55,48 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2 on sm_100): halves the issue slots of the epilogue maths
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
 template <bool FAST>
 __device__ __forceinline__ float act_tanh(float x) {
     if (FAST) return tanh_mufu(x);
     // 1 - 2/(e^{2x} + 1): saturates cleanly (e -> inf gives 1, e -> 0 gives -1); ~1e-7 absolute error
     return fmaf(-2.f, rcp_approx(ex2_approx(x * 2.885390081777927f) + 1.f), 1.f);
 }
+template <bool FAST>
+__device__ __forceinline__ float2 act_tanh2(float2 x) {
+    if (FAST) return make_float2(tanh_mufu(x.x), tanh_mufu(x.y));
+    const float2 t = mul2(x, make_float2(2.885390081777927f, 2.885390081777927f));
+    const float2 d = add2(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.f, 1.f));
+    return fma2(make_float2(-2.f, -2.f), make_float2(rcp_approx(d.x), rcp_approx(d.y)), make_float2(1.f, 1.f));
+}
 
-// split 8 floats into bf16 hi / lo and store the two 16-byte chunks of row r, feature chunk c
-__device__ __forceinline__ void store_chunk(uint8_t* tile, int r, int c, const float* v) {
+// split 8 floats (4 pairs) into bf16 hi / lo and store the two 16-byte chunks of row r, feature chunk c
+__device__ __forceinline__ void store_chunk2(uint8_t* tile, int r, int c, const float2* v) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-        const float2 hf = __bfloat1622float2(h2);
-        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * q] - hf.x, v[2 * q + 1] - hf.y);
-        hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[q].x, v[q].y);
+        const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h2);
+        const float2 hf = make_float2(__uint_as_float(hw << 16), __uint_as_float(hw & 0xffff0000u));  // a bf16 is the upper half of an fp32
+        const float2 d = fma2(hf, make_float2(-1.f, -1.f), v[q]);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(d.x, d.y);
+        hi[q] = hw;
         lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
     }
     const uint32_t off = tile_off(r, c, 128);
@@ -78,30 +104,23 @@ __device__ __forceinline__ void store_chunk(uint8_t* tile, int r, int c, const f
     *reinterpret_cast<uint4*>(tile + TILE_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// read back 8 features (hi + lo) of row r, chunk c
-__device__ __forceinline__ void load_chunk(const uint8_t* tile, int r, int c, float* v) {
+// read back 8 features (hi + lo) of row r, chunk c, as 4 pairs
+__device__ __forceinline__ void load_chunk2(const uint8_t* tile, int r, int c, float2* v) {
     const uint32_t off = tile_off(r, c, 128);
     const uint4 h = *reinterpret_cast<const uint4*>(tile + off);
     const uint4 l = *reinterpret_cast<const uint4*>(tile + TILE_HALF + off);
     const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        // a bf16 is the upper half of an fp32
-        v[2 * q] = __uint_as_float(hh[q] << 16) + __uint_as_float(ll[q] << 16);
-        v[2 * q + 1] = __uint_as_float(hh[q] & 0xffff0000u) + __uint_as_float(ll[q] & 0xffff0000u);
-    }
-}
-__device__ __forceinline__ float load_elem(const uint8_t* tile, int r, int f) {
-    const uint32_t off = tile_off(r, f >> 3, 128) + (f & 7) * 2;
-    return __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(tile + off)) << 16) +
-           __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(tile + TILE_HALF + off)) << 16);
+    for (int q = 0; q < 4; ++q)
+        v[q] = add2(make_float2(__uint_as_float(hh[q] << 16), __uint_as_float(hh[q] & 0xffff0000u)),
+                    make_float2(__uint_as_float(ll[q] << 16), __uint_as_float(ll[q] & 0xffff0000u)));
 }
 
 struct TcSmem {
     uint8_t* tiles;   // ntiles x TILE_BYTES
     uint8_t* wt;      // (L-1) x WT_BYTES
     uint8_t* dy;      // 2 x DY_HALF
-    float *Cp, *beta, *Wout, *bout, *affc, *scratch;  // scratch: output-layer partial sums [128][4][C], later G0s [TP][SHP]
+    float *Cp, *beta, *Wout, *bout, *affc, *scratch, *As;  // scratch: output-layer partial sums [128][4][C], later G0s [TP][SHP]
     uint64_t* bars;   // [0] accumulator ready, [1] all MMAs of the tile done
     uint32_t* tmem;
     size_t bytes;
@@ -124,6 +143,8 @@ struct TcSmem {
         scratch = reinterpret_cast<float*>(take(sc1 > sc2 ? sc1 : sc2));
         bars = reinterpret_cast<uint64_t*>(take(16));
         tmem = reinterpret_cast<uint32_t*>(take(16));
+        // A[n] rows staged in shared memory when they fit (L1 is almost entirely carved out for shared memory here)
+        As = tl.NC <= 24 ? reinterpret_cast<float*>(take((size_t)tl.NC * SHP * 4)) : nullptr;
         bytes = p - base;
     }
 };
@@ -157,62 +178,54 @@ __device__ inline void load_weight_tiles(const Args& a, TcSmem& s) {
     for (int i = threadIdx.x; i < a.tl.TP * HPAD; i += blockDim.x) s.Cp[i] = 0.f;  // columns >= 52 stay 0 forever
 }
 
-// Phase 0 of a tile (CUDA cores): beta[j][2pe] = sin/cos(coords.B), Cp[j][o] = sum_k beta[j][k] W0c[o][k]
-__device__ inline void tile_prologue(const Args& a, TcSmem& s, const TileIdx& ti) {
+// Phase 0 of a tile: fetch Cp[j][o] (precomputed for every pixel by the prep kernel) into shared memory; for the affine
+// gradient (match backward) also beta[j][2pe] = sin/cos(coords.B)
+__device__ inline void tile_prologue(const Args& a, TcSmem& s, const TileIdx& ti, bool need_beta) {
     const Net& nt = a.net;
     const int pe = nt.pe;
-    if (a.has_aff && threadIdx.x == 0) affine_consts(a.aff, ti.d, s.affc);
-    __syncthreads();
-    for (int i = threadIdx.x; i < ti.np * pe; i += blockDim.x) {
-        const int j = i / pe, m = i % pe;
-        const float2 c = transformed_coord(a, s.affc, ti.p0 + j);
-        float sn, cs;
-        sincosf(c.x * a.B[m] + c.y * a.B[pe + m], &sn, &cs);
-        s.beta[j * 2 * pe + m] = sn;
-        s.beta[j * 2 * pe + pe + m] = cs;
-    }
-    __syncthreads();
-    // item = (pixel j, 4 output columns o4); the K = 2*pe sum is split over 4 adjacent lanes and combined by shuffles
-    const int items = ti.np * (SHP / 4);
-    const int kq = threadIdx.x & 3, kper = (2 * pe + 3) / 4;
-    for (int base = 0; base < items; base += blockDim.x / 4) {
-        const int it = base + (threadIdx.x >> 2);
-        const bool ok = it < items;
-        const int j = ok ? it / (SHP / 4) : 0, o4 = ok ? it % (SHP / 4) : 0;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const float* bj = s.beta + j * 2 * pe;
-        const float4* w = reinterpret_cast<const float4*>(a.W0cT) + o4;
-        const int k1 = min(2 * pe, (kq + 1) * kper);
-#pragma unroll 5
-        for (int k = kq * kper; k < k1; ++k) {
-            const float bk = bj[k];
-            const float4 ww = __ldg(w + (size_t)k * (SHP / 4));
-            acc.x = fmaf(bk, ww.x, acc.x), acc.y = fmaf(bk, ww.y, acc.y), acc.z = fmaf(bk, ww.z, acc.z), acc.w = fmaf(bk, ww.w, acc.w);
+    if (need_beta) {
+        if (a.has_aff && threadIdx.x == 0) affine_consts(a.aff, ti.d, s.affc);
+        __syncthreads();
+        for (int i = threadIdx.x; i < ti.np * pe; i += blockDim.x) {
+            const int j = i / pe, m = i % pe;
+            const float2 c = transformed_coord(a, s.affc, ti.p0 + j);
+            float sn, cs;
+            sincosf(c.x * a.B[m] + c.y * a.B[pe + m], &sn, &cs);
+            s.beta[j * 2 * pe + m] = sn;
+            s.beta[j * 2 * pe + pe + m] = cs;
         }
-#pragma unroll
-        for (int sh = 1; sh <= 2; sh <<= 1) {
-            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, sh), acc.y += __shfl_xor_sync(0xffffffffu, acc.y, sh);
-            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, sh), acc.w += __shfl_xor_sync(0xffffffffu, acc.w, sh);
-        }
-        if (ok && kq == 0) reinterpret_cast<float4*>(s.Cp + j * HPAD)[o4] = acc;
     }
+    const float4* src = reinterpret_cast<const float4*>(a.Cpg + ((size_t)ti.d * a.tl.P + ti.p0) * SHP);
+    for (int i = threadIdx.x; i < ti.np * (SHP / 4); i += blockDim.x)
+        reinterpret_cast<float4*>(s.Cp + (i / (SHP / 4)) * HPAD)[i % (SHP / 4)] = __ldg(src + i);
     __syncthreads();
 }
 
 // h1 = tanh(A[n] + Cp[j]) for this thread's 16 columns (A[n][50] = ONE_SEED from the prep kernel -> constant-1 feature)
 template <bool FAST>
-__device__ __forceinline__ void layer0_to_tile(const Args& a, const TcSmem& s, uint8_t* tile, int row, int quarter, float actf, int n, int j) {
-    const float* An = a.Avec + (size_t)n * SHP;
-    const float* Cj = s.Cp + j * HPAD;
-    float v[16];
+__device__ __forceinline__ void layer0_to_tile(const Args& a, const TcSmem& s, uint8_t* tile, int row, int quarter, float actf, int n, int nl, int j) {
+    const float2* Cj = reinterpret_cast<const float2*>(s.Cp + j * HPAD + quarter * 16);
+    const float2 act2 = make_float2(actf, actf);
+    float2 v[8];
+    if (s.As != nullptr) {
+        const float* An = s.As + nl * SHP;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const int o = quarter * 16 + q;
-        const float av = o < SHP ? __ldg(An + o) : 0.f;
-        v[q] = act_tanh<FAST>(av + Cj[o]) * actf;
+        for (int q = 0; q < 8; ++q) {
+            const int o = quarter * 16 + 2 * q;  // SHP is even: a pair never straddles the end of the row
+            const float2 av = o < SHP ? *reinterpret_cast<const float2*>(An + o) : make_float2(0.f, 0.f);
+            v[q] = mul2(act_tanh2<FAST>(add2(av, Cj[q])), act2);
+        }
+    } else {
+        const float* An = a.Avec + (size_t)n * SHP;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int o = quarter * 16 + 2 * q;
+            const float2 av = o < SHP ? __ldg(reinterpret_cast<const float2*>(An + o)) : make_float2(0.f, 0.f);
+            v[q] = mul2(act_tanh2<FAST>(add2(av, Cj[q])), act2);
+        }
     }
-    store_chunk(tile, row, 2 * quarter, v);
-    store_chunk(tile, row, 2 * quarter + 1, v + 8);
+    store_chunk2(tile, row, 2 * quarter, v);
+    store_chunk2(tile, row, 2 * quarter + 1, v + 4);
 }
 
 // D(tmem_d)[128 x 64] = A . B^T with split-bf16 operands: hi*hi + lo*hi + hi*lo.  A K-major [128 x 64]; B is a [64 x 64] weight tile,
@@ -251,7 +264,7 @@ __device__ __forceinline__ void issue_transposed_product(uint32_t tmem_d, const 
 // ---------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------
-template <bool FAST>
+template <bool FAST, int C>
 __global__ void __launch_bounds__(NT, 2) inr_fwd_tc_kernel(Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     TcSmem s(smem_raw, a.net, a.tl, 1);
@@ -262,6 +275,8 @@ __global__ void __launch_bounds__(NT, 2) inr_fwd_tc_kernel(Args a) {
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(quarter * 16);
     const int L = nt.nl;
     load_weight_tiles(a, s);
+    if (s.As != nullptr && tl.nChunks == 1)
+        for (int i = t; i < tl.NC * SHP; i += NT) s.As[i] = a.Avec[i];
     if (warp == 0) tmem_alloc(s.tmem, 64);
     if (t == 0) {
         mbar_init(&s.bars[0], 1);
@@ -276,11 +291,13 @@ __global__ void __launch_bounds__(NT, 2) inr_fwd_tc_kernel(Args a) {
     uint8_t* T = s.tiles;
     for (int tile = blockIdx.x; tile < tl.numTiles; tile += gridDim.x) {
         const TileIdx ti = decode_tile(tl, tile);
-        tile_prologue(a, s, ti);
+        if (s.As != nullptr && tl.nChunks > 1)
+            for (int i = t; i < ti.nn * SHP; i += NT) s.As[i] = a.Avec[(size_t)ti.n0 * SHP + i];
+        tile_prologue(a, s, ti, false);
         const int nl = row / tl.TP, j = row % tl.TP;
         const bool active = nl < ti.nn && j < ti.np;
         const float actf = active ? 1.f : 0.f;
-        layer0_to_tile<FAST>(a, s, T, row, quarter, actf, active ? ti.n0 + nl : 0, active ? j : 0);
+        layer0_to_tile<FAST>(a, s, T, row, quarter, actf, active ? ti.n0 + nl : 0, active ? nl : 0, active ? j : 0);
 #pragma unroll 1
         for (int l = 1; l < L; ++l) {
             fence_proxy_async();
@@ -294,34 +311,37 @@ __global__ void __launch_bounds__(NT, 2) inr_fwd_tc_kernel(Args a) {
             mbar_wait(&s.bars[0], phase);
             phase ^= 1;
             fence_after_sync();
-            float v[16];
-            tmem_ld16(tm + TM_ACC + lane_addr, v);
+            float2 v[8];
+            tmem_ld16(tm + TM_ACC + lane_addr, reinterpret_cast<float*>(v));
             tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = act_tanh<FAST>(v[q]) * actf;
+            for (int q = 0; q < 8; ++q) v[q] = act_tanh2<FAST>(v[q]);  // inactive rows: h_1 == 0 (bias feature too) => z == 0 => tanh == 0
             if (l < L - 1) {
-                store_chunk(T, row, 2 * quarter, v);
-                store_chunk(T, row, 2 * quarter + 1, v + 8);
+                store_chunk2(T, row, 2 * quarter, v);
+                store_chunk2(T, row, 2 * quarter + 1, v + 4);
             } else {  // output layer: partial dot products of this thread's 16 features
-                for (int c = 0; c < nt.C; ++c) {
-                    float y = 0.f;
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) y = fmaf(v[q], s.Wout[c * HPAD + quarter * 16 + q], y);
-                    s.scratch[(row * 4 + quarter) * nt.C + c] = y;
+                for (int c = 0; c < C; ++c) {
+                    const float2* w = reinterpret_cast<const float2*>(s.Wout + c * HPAD + quarter * 16);
+                    float2 y = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) y = fma2(v[q], w[q], y);
+                    s.scratch[(row * 4 + quarter) * C + c] = y.x + y.y;
                 }
             }
         }
         fence_before_sync();
         __syncthreads();
         if (quarter == 0 && active) {
-            const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + nl)) * nt.C) * tl.P + ti.p0 + j;
-            for (int c = 0; c < nt.C; ++c) {
-                const float* yp = s.scratch + (row * 4) * nt.C + c;
-                const float y = s.bout[c] + ((yp[0] + yp[nt.C]) + (yp[2 * nt.C] + yp[3 * nt.C]));
+            const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + nl)) * C) * tl.P + ti.p0 + j;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float* yp = s.scratch + (row * 4) * C + c;
+                const float y = s.bout[c] + ((yp[0] + yp[C]) + (yp[2 * C] + yp[3 * C]));
                 a.img[base + (size_t)c * tl.P] = act_tanh<FAST>(y);
             }
         }
-        __syncthreads();  // scratch / Cp / beta / the tile buffer are rewritten by the next tile
+        __syncthreads();  // scratch / Cp / the tile buffer are rewritten by the next tile
     }
     fence_before_sync();
     __syncthreads();
@@ -331,7 +351,9 @@ __global__ void __launch_bounds__(NT, 2) inr_fwd_tc_kernel(Args a) {
 // ---------------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------------
-template <bool FAST>
+constexpr int STG = 132;  // row stride (floats) of the fp32 staging panel stage[o][row] for dz_0
+
+template <bool FAST, int C>
 __global__ void __launch_bounds__(NT, 1) inr_bwd_tc_kernel(Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const Net& nt = a.net;
@@ -343,6 +365,8 @@ __global__ void __launch_bounds__(NT, 1) inr_bwd_tc_kernel(Args a) {
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(quarter * 16);
     const bool want_w = a.want_weights != 0;
     load_weight_tiles(a, s);
+    if (s.As != nullptr)
+        for (int i = t; i < tl.NC * SHP; i += NT) s.As[i] = a.Avec[i];
     if (warp == 0) tmem_alloc(s.tmem, TM_COLS);
     if (t == 0) {
         mbar_init(&s.bars[0], 1);
@@ -358,13 +382,16 @@ __global__ void __launch_bounds__(NT, 1) inr_bwd_tc_kernel(Args a) {
     uint32_t ph_acc = 0, ph_done = 0;
     bool first = true;
     auto Tile = [&](int i) { return s.tiles + (size_t)i * TILE_BYTES; };
+    // dz_0 is staged in fp32 ([o][row], conflict-free) in the tile that held h_2: it is not an MMA operand.  L == 2 has no free
+    // tile before the last data-gradient epilogue, so the staging panel then lives in X's successor: host guarantees L >= 3 here.
+    float* stage = reinterpret_cast<float*>(Tile(1));
     // dA[n][o] accumulators of this thread: entries e = t + NT*q  ->  (n = e / HID, o = e % HID); N <= 40 (host check)
     constexpr int DA_PER_THREAD = 4;
     float dA[DA_PER_THREAD] = {0.f, 0.f, 0.f, 0.f};
 
     for (int tile = blockIdx.x; tile < tl.numTiles; tile += gridDim.x) {
         const TileIdx ti = decode_tile(tl, tile);
-        tile_prologue(a, s, ti);
+        tile_prologue(a, s, ti, a.want_affine != 0);
         const int nl = row / tl.TP, j = row % tl.TP;
         const bool active = nl < ti.nn && j < ti.np;
         const float actf = active ? 1.f : 0.f;
@@ -374,7 +401,7 @@ __global__ void __launch_bounds__(NT, 1) inr_bwd_tc_kernel(Args a) {
             fence_after_sync();
         }
         // ---- forward recompute: h_1 (CUDA cores), h_2..h_L (tensor cores), all kept as tiles
-        layer0_to_tile<FAST>(a, s, Tile(0), row, quarter, actf, active ? ti.n0 + nl : 0, active ? j : 0);
+        layer0_to_tile<FAST>(a, s, Tile(0), row, quarter, actf, active ? ti.n0 + nl : 0, active ? nl : 0, active ? j : 0);
 #pragma unroll 1
         for (int l = 1; l < L; ++l) {
             fence_proxy_async();
@@ -388,19 +415,21 @@ __global__ void __launch_bounds__(NT, 1) inr_bwd_tc_kernel(Args a) {
             mbar_wait(&s.bars[0], ph_acc);
             ph_acc ^= 1;
             fence_after_sync();
-            float v[16];
-            tmem_ld16(tm + TM_ACC + lane_addr, v);
+            float2 v[8];
+            tmem_ld16(tm + TM_ACC + lane_addr, reinterpret_cast<float*>(v));
             tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = act_tanh<FAST>(v[q]) * actf;
-            store_chunk(Tile(l), row, 2 * quarter, v);
-            store_chunk(Tile(l), row, 2 * quarter + 1, v + 8);
+            for (int q = 0; q < 8; ++q) v[q] = act_tanh2<FAST>(v[q]);  // inactive rows: h_1 == 0 (bias feature too) => z == 0 => tanh == 0
+            store_chunk2(Tile(l), row, 2 * quarter, v);
+            store_chunk2(Tile(l), row, 2 * quarter + 1, v + 4);
             if (l == L - 1) {  // output layer: partial dot products of this thread's 16 features of h_L
-                for (int c = 0; c < nt.C; ++c) {
-                    float y = 0.f;
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) y = fmaf(v[q], s.Wout[c * HPAD + quarter * 16 + q], y);
-                    s.scratch[(row * 4 + quarter) * nt.C + c] = y;
+                for (int c = 0; c < C; ++c) {
+                    const float2* w = reinterpret_cast<const float2*>(s.Wout + c * HPAD + quarter * 16);
+                    float2 y = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) y = fma2(v[q], w[q], y);
+                    s.scratch[(row * 4 + quarter) * C + c] = y.x + y.y;
                 }
             }
         }
@@ -408,24 +437,28 @@ __global__ void __launch_bounds__(NT, 1) inr_bwd_tc_kernel(Args a) {
         // ---- output layer (CUDA cores): y, dy = g (1 - y^2), dz_{L-1} = (Wout^T dy) (1 - h_L^2) -> tile X; dy -> dy tile
         {
             float dy[4] = {0.f, 0.f, 0.f, 0.f};
-            const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + (active ? nl : 0))) * nt.C) * tl.P + ti.p0 + (active ? j : 0);
-            for (int c = 0; c < nt.C; ++c) {
-                const float* yp = s.scratch + (row * 4) * nt.C + c;
-                const float y = act_tanh<FAST>(s.bout[c] + ((yp[0] + yp[nt.C]) + (yp[2 * nt.C] + yp[3 * nt.C])));
+            const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + (active ? nl : 0))) * C) * tl.P + ti.p0 + (active ? j : 0);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float* yp = s.scratch + (row * 4) * C + c;
+                const float y = act_tanh<FAST>(s.bout[c] + ((yp[0] + yp[C]) + (yp[2 * C] + yp[3 * C])));
                 const float g = active ? a.g_img[base + (size_t)c * tl.P] : 0.f;
                 dy[c] = g * (1.f - y * y);
             }
-            float hv[16], v[16];
-            load_chunk(Tile(L - 1), row, 2 * quarter, hv);
-            load_chunk(Tile(L - 1), row, 2 * quarter + 1, hv + 8);
+            float2 hv[8], v[8];
+            load_chunk2(Tile(L - 1), row, 2 * quarter, hv);
+            load_chunk2(Tile(L - 1), row, 2 * quarter + 1, hv + 4);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                float dh = 0.f;
-                for (int c = 0; c < nt.C; ++c) dh = fmaf(s.Wout[c * HPAD + quarter * 16 + q], dy[c], dh);
-                v[q] = dh * (1.f - hv[q] * hv[q]);  // padding columns: Wout == 0; constant-1 column: 1 - 1 == 0
+            for (int q = 0; q < 8; ++q) {
+                float2 dh = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    dh = fma2(reinterpret_cast<const float2*>(s.Wout + c * HPAD + quarter * 16)[q], make_float2(dy[c], dy[c]), dh);
+                // dh (1 - h^2); padding columns: Wout == 0; constant-1 column: 1 - 1 == 0
+                v[q] = fma2(mul2(dh, mul2(hv[q], hv[q])), make_float2(-1.f, -1.f), dh);
             }
-            store_chunk(Tile(L), row, 2 * quarter, v);
-            store_chunk(Tile(L), row, 2 * quarter + 1, v + 8);
+            store_chunk2(Tile(L), row, 2 * quarter, v);
+            store_chunk2(Tile(L), row, 2 * quarter + 1, v + 4);
             if (want_w && quarter == 0) {  // dy as a [128 x 8] split-bf16 tile (one 16-byte chunk per row)
                 uint32_t hi[2], lo[2];
 #pragma unroll
@@ -460,38 +493,48 @@ __global__ void __launch_bounds__(NT, 1) inr_bwd_tc_kernel(Args a) {
             ph_acc ^= 1;
             fence_after_sync();
             // dz_{l-1}[k] = dh_l[k] (1 - h_l[k]^2)   (h_l[50] == 1 zeroes the bias column; padding columns of W are 0)
-            float v[16], hv[16];
-            tmem_ld16(tm + TM_ACC + lane_addr, v);
-            load_chunk(Tile(l - 1), row, 2 * quarter, hv);
-            load_chunk(Tile(l - 1), row, 2 * quarter + 1, hv + 8);
+            float2 v[8], hv[8];
+            tmem_ld16(tm + TM_ACC + lane_addr, reinterpret_cast<float*>(v));
+            load_chunk2(Tile(l - 1), row, 2 * quarter, hv);
+            load_chunk2(Tile(l - 1), row, 2 * quarter + 1, hv + 4);
             tmem_ld_wait();
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = v[q] * (1.f - hv[q] * hv[q]);
-            store_chunk(Tile(dst), row, 2 * quarter, v);
-            store_chunk(Tile(dst), row, 2 * quarter + 1, v + 8);
+            for (int q = 0; q < 8; ++q) v[q] = fma2(mul2(v[q], mul2(hv[q], hv[q])), make_float2(-1.f, -1.f), v[q]);
+            if (l > 1) {
+                store_chunk2(Tile(dst), row, 2 * quarter, v);
+                store_chunk2(Tile(dst), row, 2 * quarter + 1, v + 4);
+            } else {  // dz_0 feeds only CUDA-core reductions: stage it in fp32 (the tile of h_2 is free: dW_2's MMAs completed before bar 0 fired)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    stage[(quarter * 16 + 2 * q) * STG + row] = v[q].x;
+                    stage[(quarter * 16 + 2 * q + 1) * STG + row] = v[q].y;
+                }
+            }
             // rotate: the old src is free once the NEXT step's data-gradient MMAs (issued after this step's dW MMAs) have completed
             src = dst;
             dst = (src == L) ? L - 1 : L;
         }
-        __syncthreads();  // dz_0 (tile `src`) complete
-        // ---- layer 0: G0[j][o] = sum_n dz0, dA[n][o] += sum_j dz0   (CUDA cores, from the split-bf16 tile)
-        const uint8_t* Z = Tile(src);
+        __syncthreads();  // dz_0 staged
+        // ---- layer 0: G0[j][o] = sum_n dz0, dA[n][o] += sum_j dz0   (CUDA cores, fp32 staging panel)
         float* G0s = s.scratch;
         for (int i = t; i < ti.np * SHP; i += NT) {
-            const int jj = i / SHP, o = i % SHP;
+            const int o = i / ti.np, jj = i % ti.np;  // consecutive lanes -> consecutive pixels of one feature row
             float sum = 0.f;
-            if (o < HID)
-                for (int n = 0; n < ti.nn; ++n) sum += load_elem(Z, n * tl.TP + jj, o);
-            G0s[i] = sum;
+            if (o < HID) {
+                const float* zr = stage + o * STG + jj;
+                for (int n = 0; n < ti.nn; ++n) sum += zr[n * tl.TP];
+            }
+            G0s[jj * SHP + o] = sum;
         }
         if (want_w) {
 #pragma unroll
             for (int q = 0; q < DA_PER_THREAD; ++q) {
                 const int e = t + NT * q;
                 if (e < ti.nn * HID) {
-                    const int n = e / HID, o = e % HID;
+                    const int o = e / ti.nn, n = e % ti.nn;  // NOTE: entry order (o-major) is this kernel's private convention, see the read-out
+                    const float* zr = stage + o * STG + n * tl.TP;
                     float sum = 0.f;
-                    for (int jj = 0; jj < ti.np; ++jj) sum += load_elem(Z, n * tl.TP + jj, o);
+                    for (int jj = 0; jj < ti.np; ++jj) sum += zr[jj];
                     dA[q] += sum;
                 }
             }
@@ -552,7 +595,7 @@ __global__ void __launch_bounds__(NT, 1) inr_bwd_tc_kernel(Args a) {
         float* p_dW = part;
         float* p_db = part + (size_t)(L - 1) * HID * HID;
         float* p_dWout = p_db + (size_t)(L - 1) * SHP;
-        float* p_dA = p_dWout + (size_t)nt.C * SHP + 4;
+        float* p_dA = p_dWout + (size_t)C * SHP + 4;
         if (warp < 4) {  // M=64 accumulator layout: row o -> lane (o/16)*32 + o%16
             const int o = 16 * warp + lane;
             const uint32_t lb = (uint32_t)(warp * 32) << 16;
@@ -577,16 +620,17 @@ __global__ void __launch_bounds__(NT, 1) inr_bwd_tc_kernel(Args a) {
             tmem_ld16(tm + tm_dwout + lb, v);
             tmem_ld_wait();
             if (lane < 16) {  // row i = o of D[i][c]
-                for (int c = 0; c < nt.C; ++c) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
                     if (o < HID) p_dWout[c * SHP + o] = v[c];
-                    else if (o == ONE_COL) p_dWout[nt.C * SHP + c] = v[c];
+                    else if (o == ONE_COL) p_dWout[C * SHP + c] = v[c];
                 }
             }
         }
 #pragma unroll
         for (int q = 0; q < DA_PER_THREAD; ++q) {
             const int e = t + NT * q;
-            if (e < tl.NC * HID) p_dA[(e / HID) * SHP + e % HID] = dA[q];
+            if (e < tl.NC * HID) p_dA[(e % tl.NC) * SHP + e / tl.NC] = dA[q];  // e = o * N + n (single latent chunk: nn == NC == N)
         }
     }
     fence_before_sync();
@@ -599,7 +643,7 @@ __global__ void __launch_bounds__(NT, 1) inr_bwd_tc_kernel(Args a) {
 // ---------------------------------------------------------------------------------------------------------------
 static int check_tc(const Net& nt) {
     LMR_CHECK_ARG(nt.hid == HID, "tensor-core path: hidden width %d not supported (50)", nt.hid);
-    LMR_CHECK_ARG(nt.nl >= 2 && nt.nl <= 4, "tensor-core path: n_hidden %d out of range [2,4]", nt.nl);
+    LMR_CHECK_ARG(nt.nl >= 3 && nt.nl <= 4, "tensor-core path: n_hidden %d out of range [3,4]", nt.nl);
     LMR_CHECK_ARG(nt.pe <= 64, "tensor-core path: pe_dim %d > 64", nt.pe);
     return 0;
 }
@@ -621,7 +665,7 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
     if (int rc = check_tc(nt)) return rc;
     LMR_CHECK_ARG(N >= 1 && P >= 1 && D >= 1, "inr_forward: bad sizes N=%d P=%d D=%d", N, P, D);
     const Tiling tl = make_tiling(N, P, D, TP_CAP_TC);
-    const WsLayout wl = ws_layout(nt, tl, false);
+    const WsLayout wl = ws_layout(nt, tl, false, true);
     if (ws_bytes < wl.total) {
         set_error("inr_forward: workspace %zu < %zu bytes", ws_bytes, wl.total);
         return LMR_ERR_WORKSPACE;
@@ -629,18 +673,21 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
     Args a;
     if (int rc = fill_args(a, nt, tl, params, B, auxB, grid, coords, coord_shift, affine, ws, wl)) return rc;
     a.img = img;
+    a.want_cp = 1;
     if (int rc = launch_prep<50>(a, st)) return rc;
     TcSmem s(nullptr, nt, tl, 1);
     const size_t smem = s.bytes + 1024;
     const int grid_x = tl.numTiles < 2 * num_sms() ? tl.numTiles : 2 * num_sms();
-    static size_t c0 = 0, c1 = 0;
-    if (precision == LMR_PREC_BF16X3_FAST) {
-        if (int rc = set_smem(inr_fwd_tc_kernel<true>, smem, &c0)) return rc;
-        inr_fwd_tc_kernel<true><<<grid_x, NT, smem, st>>>(a);
-    } else {
-        if (int rc = set_smem(inr_fwd_tc_kernel<false>, smem, &c1)) return rc;
-        inr_fwd_tc_kernel<false><<<grid_x, NT, smem, st>>>(a);
+    static size_t cache[2][5] = {};
+    const bool fast = precision == LMR_PREC_BF16X3_FAST;
+#define LMR_FWD_CASE(FASTV, CV)                                                                          \
+    if (fast == FASTV && nt.C == CV) {                                                                   \
+        if (int rc = set_smem(inr_fwd_tc_kernel<FASTV, CV>, smem, &cache[FASTV][CV])) return rc;        \
+        inr_fwd_tc_kernel<FASTV, CV><<<grid_x, NT, smem, st>>>(a);                                       \
     }
+    LMR_FWD_CASE(false, 1) LMR_FWD_CASE(false, 2) LMR_FWD_CASE(false, 3) LMR_FWD_CASE(false, 4)
+    LMR_FWD_CASE(true, 1) LMR_FWD_CASE(true, 2) LMR_FWD_CASE(true, 3) LMR_FWD_CASE(true, 4)
+#undef LMR_FWD_CASE
     LMR_LAUNCH_OK();
     return 0;
 }
@@ -660,7 +707,7 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
         LMR_CHECK_ARG(affine && affine->angles, "inr_backward: affine gradients requested without an affine transform");
     }
     const Tiling tl = make_tiling(N, P, D, TP_CAP_TC);
-    const WsLayout wl = ws_layout(nt, tl, true);
+    const WsLayout wl = ws_layout(nt, tl, true, true);
     if (ws_bytes < wl.total) {
         set_error("inr_backward: workspace %zu < %zu bytes", ws_bytes, wl.total);
         return LMR_ERR_WORKSPACE;
@@ -669,18 +716,21 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     if (int rc = fill_args(a, nt, tl, params, B, auxB, grid, coords, coord_shift, affine, ws, wl)) return rc;
     a.g_img = g_img;
     a.want_weights = g_params != nullptr, a.want_affine = want_aff;
+    a.want_cp = 1;
     if (int rc = launch_prep<50>(a, st)) return rc;
     TcSmem s(nullptr, nt, tl, nt.nl + 1);
     const size_t smem = s.bytes + 1024;
     LMR_CHECK_ARG(smem <= 227 * 1024, "inr_backward (tensor-core path): needs %zu bytes of shared memory (> 227 KB)", smem);
-    static size_t c0 = 0, c1 = 0;
-    if (precision == LMR_PREC_BF16X3_FAST) {
-        if (int rc = set_smem(inr_bwd_tc_kernel<true>, smem, &c0)) return rc;
-        inr_bwd_tc_kernel<true><<<wl.gridMain, NT, smem, st>>>(a);
-    } else {
-        if (int rc = set_smem(inr_bwd_tc_kernel<false>, smem, &c1)) return rc;
-        inr_bwd_tc_kernel<false><<<wl.gridMain, NT, smem, st>>>(a);
+    static size_t cache[2][5] = {};
+    const bool fast = precision == LMR_PREC_BF16X3_FAST;
+#define LMR_BWD_CASE(FASTV, CV)                                                                          \
+    if (fast == FASTV && nt.C == CV) {                                                                   \
+        if (int rc = set_smem(inr_bwd_tc_kernel<FASTV, CV>, smem, &cache[FASTV][CV])) return rc;        \
+        inr_bwd_tc_kernel<FASTV, CV><<<wl.gridMain, NT, smem, st>>>(a);                                  \
     }
+    LMR_BWD_CASE(false, 1) LMR_BWD_CASE(false, 2) LMR_BWD_CASE(false, 3) LMR_BWD_CASE(false, 4)
+    LMR_BWD_CASE(true, 1) LMR_BWD_CASE(true, 2) LMR_BWD_CASE(true, 3) LMR_BWD_CASE(true, 4)
+#undef LMR_BWD_CASE
     LMR_LAUNCH_OK();
     if (a.want_weights) {
         float* l0part = reinterpret_cast<float*>(static_cast<char*>(ws) + wl.l0part);
@@ -689,9 +739,7 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
         if (int rc = set_smem(l0_partial_kernel<50>, smem0, &c2)) return rc;
         l0_partial_kernel<50><<<wl.gridL0, 256, smem0, st>>>(a, l0part);
         LMR_LAUNCH_OK();
-        const int blocks = (int)((nt.count() + 127) / 128);
-        finish_weights_kernel<50><<<blocks, 128, 0, st>>>(a, l0part, wl.gridMain, wl.gridL0, g_params);
-        LMR_LAUNCH_OK();
+        if (int rc = launch_finish_weights<50>(a, l0part, wl.gridMain, wl.gridL0, g_params, st)) return rc;
     }
     if (want_aff) {
         finish_affine_kernel<<<D, 128, 0, st>>>(a, g_angles, g_scalings, g_shears, g_translation);
@@ -703,7 +751,7 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
 size_t workspace_bytes(const lmr_inr_desc* desc, int N, int P, int D, bool bwd) {
     Net nt;
     if (make_net(desc, &nt)) return 0;
-    return ws_layout(nt, make_tiling(N, P, D, TP_CAP_TC), bwd).total;
+    return ws_layout(nt, make_tiling(N, P, D, TP_CAP_TC), bwd, true).total;
 }
 
 }  // namespace tc
