@@ -66,6 +66,7 @@ struct Args {
     float* affpart;   // [D, tilesP, 6]  (match)
     float* dAred;     // [N, HP]  sum over CTAs of the dA partials
     int want_weights, want_affine;
+    long long* trace;  // debug: per-event clock64 stamps of CTA 0 (LMR_TC_TRACE=1), else null
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -462,6 +463,7 @@ static inline int fill_args(Args& a, const Net& nt, const Tiling& tl, const floa
     a.partials = reinterpret_cast<float*>(base + wl.partials);
     a.affpart = reinterpret_cast<float*>(base + wl.affpart);
     a.img = nullptr, a.g_img = nullptr, a.want_weights = 0, a.want_affine = 0;
+    a.trace = nullptr;
     return 0;
 }
 

@@ -1,23 +1,34 @@
 // INR generator, tcgen05 tensor-core path (LMR_PREC_BF16X3 / LMR_PREC_BF16X3_FAST): forward and recompute-backward.
 //
-// Same tiling and layer-0 separability as inr_simt.cu (a tile = TP pixels x N latents <= 128 rows of one target; row r
-// <-> TMEM lane r).  The 50x50 hidden layers run on the 5th-gen tensor cores:
+// Tiling and layer-0 separability as in inr_simt.cu: a tile = TP pixels x N latents <= 128 rows of one target; row r <-> TMEM
+// lane r.  The 50x50 hidden layers run on the 5th-gen tensor cores:
 //   * operands are error-compensated split-bf16: x = hi + lo (bf16 each), products hi*hi + lo*hi + hi*lo (3 tcgen05.mma,
 //     kind::f16, fp32 accumulate in TMEM) -> ~2^-16 relative operand error, fp32-class results (precision probe);
-//   * activation tiles [128 rows x 64 features] live in shared memory in the canonical no-swizzle core-matrix layout
-//     (tc_common.cuh).  Feature 50 is the constant 1: the bias is column 50 of the weight tile and the bias gradient
-//     column 50 of the weight-gradient accumulator.  The weight tile's entry [50][50] = 20 regenerates the constant through
-//     the activation (tanh(20) == 1 in fp32) and every other padding entry is 0 (tanh(0) == 0), so all epilogues are
-//     uniform over the 64 columns -- no per-column branches;
-//   * forward      z_l   = h_l W_l^T        A = h tile (K-major),      B = W_l tile (K-major)         M=128 N=64 K=64
-//     data grad    dh_l  = dz_l W_l         A = dz tile (K-major),     B = W_l tile read MN-major     M=128 N=64 K=64
-//     weight grad  dW_l += dz_l^T h_l       A = dz tile read MN-major, B = h tile read MN-major       M=64  N=64 K=128
-//     -- the transposed products reuse the SAME bytes through MN-major descriptors (no transposed copies);
-//   * weight-gradient accumulators stay resident in TMEM across all tiles of the persistent CTA;
-//   * nothing is stored between forward and backward: the backward recomputes the forward per tile (L+1 tiles of smem),
-//     and the weight-gradient MMAs of a layer overlap the epilogue that produces the next dz tile (rotating buffers).
-// 512 threads per CTA: thread = (row, column quarter); warp w reads TMEM lanes 32*(w%4).. and columns 16*(w/4)...
+//   * activation tiles [128 rows x 64 features] (hi half, lo half) live in shared memory in the canonical no-swizzle
+//     core-matrix layout (tc_common.cuh).  Feature 50 is the constant 1: the bias is column 50 of the weight tile and the bias
+//     gradient column 50 of the weight-gradient accumulator.  The weight tile's entry [50][50] = 20 regenerates the constant
+//     through the activation (tanh(20) == 1 in fp32); every other padding entry is 0 (tanh(0) == 0);
+//   * forward      z_l   = h_l W_l^T        A = h tile (K-major),      B = W_l tile (K-major)      M=128 N=64  K=16 x4 x3
+//     data grad    dh_l  = dz_l W_l         A = dz tile (K-major),     B = W_l tile read MN-major  M=128 N=64  K=16 x4 x3
+//     weight grad  dW_l += dz_l^T h_l       A = [dz_hi|dz_lo] tile read MN-major, B = [h_hi|h_lo] tile read MN-major
+//                                            M=128 N=128 K=16 x8: ONE MMA per 16 rows gives all four hi/lo products (the lo*lo
+//                                            quadrant is dropped at read-out) -- the transposed products reuse the SAME bytes
+//                                            through MN-major descriptors (no transposed copies);
+//   * weight-gradient accumulators (3 x 128 TMEM columns) stay resident in TMEM across all tiles of the persistent CTA;
+//   * nothing is stored between forward and backward: the backward recomputes the forward per tile.
+//
+// Warp-specialised pipeline (one CTA per SM in the backward, two in the forward):
+//   "epilogue" warps: thread = (row, column group g of NG): warps q, q+4, .. own TMEM lanes 32q..32q+31; group g owns the 8-feature
+//              chunks {g, g+NG, ..} of the row (NG = 2 / 8 warps in the forward, NG = 4 / 16 warps in the backward).  They turn an
+//              accumulator into the next operand tile (tanh, or dh (1 - h^2)) and signal each finished 16-feature k-chunk on an mbarrier;
+//   last warp  one elected thread issues the MMAs of the NEXT layer k-step by k-step as the chunks arrive (so the tensor pipe trails
+//              the epilogue by one chunk instead of waiting for the whole tile), into the other of two ping-pong accumulators, and
+//              commits; weight-gradient MMAs of a layer are issued right behind its data-gradient MMAs and overlap the epilogues.
+// Buffer hazards are covered by commit ordering: a tcgen05.commit tracks every MMA issued before it by the same thread.
 #include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include <type_traits>
 
 #include "inr_common.cuh"
 #include "tc_common.cuh"
@@ -32,18 +43,24 @@ constexpr int HID = 50;               // hidden width served by this path
 constexpr int HPAD = 64;              // padded feature count of a tile (K and N of the MMAs)
 constexpr int ONE_COL = 50;           // feature slot holding the constant 1 (bias column)
 constexpr float ONE_SEED = 20.f;      // tanh(20) == 1
+constexpr int LH = 4;                 // hidden layers served by this path (the pipeline default widths=[50]*4)
 constexpr int TP_CAP_TC = 8;          // pixels per tile cap (bounds the per-tile scratch)
-constexpr int NT = 512;               // threads per CTA
 constexpr int TILE_HALF = 128 * HPAD * 2;   // bytes of the hi (or lo) half of an activation tile
 constexpr int TILE_BYTES = 2 * TILE_HALF;   // 32 KB
 constexpr int WT_HALF = HPAD * HPAD * 2;    // 8 KB
 constexpr int WT_BYTES = 2 * WT_HALF;       // 16 KB
-constexpr int DY_HALF = 128 * 8 * 2;        // dy tile: 128 rows x 8 channels (padded), hi / lo
+constexpr int NBUF_BWD = LH + 1;            // h_1..h_3, two rotating gradient tiles
 
 // TMEM columns
-constexpr uint32_t TM_ACC = 0;        // [128 lanes x 64]  forward / data-gradient accumulator
-constexpr uint32_t TM_DW = 64;        // (L-1) x [64 rows (M=64 lane layout) x 64] weight-gradient accumulators, then 16 columns for dWout
-constexpr uint32_t TM_COLS = 512;
+constexpr uint32_t TM_ACC = 0;        // 2 x [128 lanes x 64]  ping-pong forward / data-gradient accumulators
+constexpr uint32_t TM_DW = 128;       // 3 x [128 x 128] weight-gradient accumulators ([dz_hi;dz_lo] x [h_hi|h_lo])
+constexpr uint32_t TM_COLS_BWD = 512, TM_COLS_FWD = 128;
+
+// mbarriers
+constexpr int BAR_K = 0;      // [0..3] k-chunk kc of the operand tile under construction is complete (epilogue warps -> MMA thread)
+constexpr int BAR_ACC = 4;    // [4..5] accumulator ready (tcgen05.commit -> epilogue threads)
+constexpr int BAR_DONE = 6;   // every MMA of the CTA has completed
+constexpr int NBARS = 8;
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -86,11 +103,12 @@ __device__ __forceinline__ float2 act_tanh2(float2 x) {
     return fma2(make_float2(-2.f, -2.f), make_float2(rcp_approx(d.x), rcp_approx(d.y)), make_float2(1.f, 1.f));
 }
 
-// split 8 floats (4 pairs) into bf16 hi / lo and store the two 16-byte chunks of row r, feature chunk c
+// split NP pairs (2*NP <= 8 features, the rest of the 16-byte chunk is zero) into bf16 hi / lo and store the two chunks of row r, chunk c
+template <int NP>
 __device__ __forceinline__ void store_chunk2(uint8_t* tile, int r, int c, const float2* v) {
-    uint32_t hi[4], lo[4];
+    uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < NP; ++q) {
         const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[q].x, v[q].y);
         const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h2);
         const float2 hf = make_float2(__uint_as_float(hw << 16), __uint_as_float(hw & 0xffff0000u));  // a bf16 is the upper half of an fp32
@@ -103,28 +121,39 @@ __device__ __forceinline__ void store_chunk2(uint8_t* tile, int r, int c, const 
     *reinterpret_cast<uint4*>(tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(tile + TILE_HALF + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
+__device__ __forceinline__ void store_chunk_zero(uint8_t* tile, int r, int c) {
+    const uint32_t off = tile_off(r, c, 128);
+    *reinterpret_cast<uint4*>(tile + off) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(tile + TILE_HALF + off) = make_uint4(0u, 0u, 0u, 0u);
+}
 
-// read back 8 features (hi + lo) of row r, chunk c, as 4 pairs
+// read back 2*NP features (hi + lo) of row r, chunk c
+template <int NP>
 __device__ __forceinline__ void load_chunk2(const uint8_t* tile, int r, int c, float2* v) {
     const uint32_t off = tile_off(r, c, 128);
     const uint4 h = *reinterpret_cast<const uint4*>(tile + off);
     const uint4 l = *reinterpret_cast<const uint4*>(tile + TILE_HALF + off);
     const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int q = 0; q < NP; ++q)
         v[q] = add2(make_float2(__uint_as_float(hh[q] << 16), __uint_as_float(hh[q] & 0xffff0000u)),
                     make_float2(__uint_as_float(ll[q] << 16), __uint_as_float(ll[q] & 0xffff0000u)));
 }
 
+// debug tracing (LMR_TC_TRACE=1): CTA 0 stamps clock64 at pipeline events; slot 0 = epilogue thread 0, slot 1 = MMA thread
+#define LMR_TRACE(slot, idx)                                                                   \
+    do {                                                                                       \
+        if (a.trace != nullptr && blockIdx.x == 0 && (idx) < 512) a.trace[(slot) * 512 + (idx)] = clock64(); \
+    } while (0)
+
 struct TcSmem {
     uint8_t* tiles;   // ntiles x TILE_BYTES
-    uint8_t* wt;      // (L-1) x WT_BYTES
-    uint8_t* dy;      // 2 x DY_HALF
-    float *Cp, *beta, *Wout, *bout, *affc, *scratch, *As;  // scratch: output-layer partial sums [128][4][C], later G0s [TP][SHP]
-    uint64_t* bars;   // [0] accumulator ready, [1] all MMAs of the tile done
+    uint8_t* wt;      // (LH-1) x WT_BYTES
+    float *Cps, *beta, *Wout, *bout, *scratch, *As;  // Cps: 2 x [TP][SHP] staged layer-0 coordinate parts; scratch: y partials [128][NG][C] / G0s [TP][SHP]
+    uint64_t* bars;
     uint32_t* tmem;
     size_t bytes;
-    __host__ __device__ TcSmem(uint8_t* base, const Net& nt, const Tiling& tl, int ntiles) {
+    __host__ __device__ TcSmem(uint8_t* base, const Net& nt, const Tiling& tl, int ntiles, bool want_beta, int ng) {
         uint8_t* p = base;
         auto take = [&](size_t n) {
             uint8_t* r = p;
@@ -132,16 +161,14 @@ struct TcSmem {
             return r;
         };
         tiles = take((size_t)ntiles * TILE_BYTES);
-        wt = take((size_t)(nt.nl - 1) * WT_BYTES);
-        dy = take(2 * DY_HALF);
-        Cp = reinterpret_cast<float*>(take((size_t)tl.TP * HPAD * 4));
-        beta = reinterpret_cast<float*>(take((size_t)tl.TP * 2 * nt.pe * 4));
+        wt = take((size_t)(LH - 1) * WT_BYTES);
+        Cps = reinterpret_cast<float*>(take((size_t)2 * tl.TP * SHP * 4));
+        beta = reinterpret_cast<float*>(take(want_beta ? (size_t)tl.TP * 2 * nt.pe * 4 : 0));
         Wout = reinterpret_cast<float*>(take((size_t)nt.C * HPAD * 4));
         bout = reinterpret_cast<float*>(take(16));
-        affc = reinterpret_cast<float*>(take(48));
-        const size_t sc1 = (size_t)128 * 4 * nt.C * 4, sc2 = (size_t)tl.TP * SHP * 4;
+        const size_t sc1 = (size_t)128 * ng * nt.C * 4, sc2 = (size_t)tl.TP * SHP * 4;
         scratch = reinterpret_cast<float*>(take(sc1 > sc2 ? sc1 : sc2));
-        bars = reinterpret_cast<uint64_t*>(take(16));
+        bars = reinterpret_cast<uint64_t*>(take(NBARS * 8));
         tmem = reinterpret_cast<uint32_t*>(take(16));
         // A[n] rows staged in shared memory when they fit (L1 is almost entirely carved out for shared memory here)
         As = tl.NC <= 24 ? reinterpret_cast<float*>(take((size_t)tl.NC * SHP * 4)) : nullptr;
@@ -149,11 +176,11 @@ struct TcSmem {
     }
 };
 
-// weights of hidden layers 1..L-1 as split-bf16 K-major tiles: W_l[o][k] for k < 50, column 50 = bias b_l[o],
-// entry [50][50] = ONE_SEED (regenerates the constant-1 feature), rest 0.  Also the fp32 output layer and zeroed Cp padding.
+// weights of hidden layers 1..LH-1 as split-bf16 K-major tiles: W_l[o][k] for k < 50, column 50 = bias b_l[o],
+// entry [50][50] = ONE_SEED (regenerates the constant-1 feature), rest 0.  Also the fp32 output layer.
 __device__ inline void load_weight_tiles(const Args& a, TcSmem& s) {
     const Net& nt = a.net;
-    for (int l = 1; l < nt.nl; ++l) {
+    for (int l = 1; l < LH; ++l) {
         const float* W = a.params + nt.offW(l);
         const float* b = a.params + nt.offb(l);
         uint8_t* dst = s.wt + (size_t)(l - 1) * WT_BYTES;
@@ -175,467 +202,678 @@ __device__ inline void load_weight_tiles(const Args& a, TcSmem& s) {
         s.Wout[i] = k < HID ? Wo[c * HID + k] : 0.f;
     }
     if (threadIdx.x < 4) s.bout[threadIdx.x] = threadIdx.x < nt.C ? a.params[nt.offbout() + threadIdx.x] : 0.f;
-    for (int i = threadIdx.x; i < a.tl.TP * HPAD; i += blockDim.x) s.Cp[i] = 0.f;  // columns >= 52 stay 0 forever
 }
 
-// Phase 0 of a tile: fetch Cp[j][o] (precomputed for every pixel by the prep kernel) into shared memory; for the affine
-// gradient (match backward) also beta[j][2pe] = sin/cos(coords.B)
-__device__ inline void tile_prologue(const Args& a, TcSmem& s, const TileIdx& ti, bool need_beta) {
-    const Net& nt = a.net;
-    const int pe = nt.pe;
-    if (need_beta) {
-        if (a.has_aff && threadIdx.x == 0) affine_consts(a.aff, ti.d, s.affc);
-        __syncthreads();
-        for (int i = threadIdx.x; i < ti.np * pe; i += blockDim.x) {
-            const int j = i / pe, m = i % pe;
-            const float2 c = transformed_coord(a, s.affc, ti.p0 + j);
-            float sn, cs;
-            sincosf(c.x * a.B[m] + c.y * a.B[pe + m], &sn, &cs);
-            s.beta[j * 2 * pe + m] = sn;
-            s.beta[j * 2 * pe + pe + m] = cs;
-        }
-    }
-    const float4* src = reinterpret_cast<const float4*>(a.Cpg + ((size_t)ti.d * a.tl.P + ti.p0) * SHP);
-    for (int i = threadIdx.x; i < ti.np * (SHP / 4); i += blockDim.x)
-        reinterpret_cast<float4*>(s.Cp + (i / (SHP / 4)) * HPAD)[i % (SHP / 4)] = __ldg(src + i);
-    __syncthreads();
-}
-
-// h1 = tanh(A[n] + Cp[j]) for this thread's 16 columns (A[n][50] = ONE_SEED from the prep kernel -> constant-1 feature)
-template <bool FAST>
-__device__ __forceinline__ void layer0_to_tile(const Args& a, const TcSmem& s, uint8_t* tile, int row, int quarter, float actf, int n, int nl, int j) {
-    const float2* Cj = reinterpret_cast<const float2*>(s.Cp + j * HPAD + quarter * 16);
-    const float2 act2 = make_float2(actf, actf);
-    float2 v[8];
-    if (s.As != nullptr) {
-        const float* An = s.As + nl * SHP;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int o = quarter * 16 + 2 * q;  // SHP is even: a pair never straddles the end of the row
-            const float2 av = o < SHP ? *reinterpret_cast<const float2*>(An + o) : make_float2(0.f, 0.f);
-            v[q] = mul2(act_tanh2<FAST>(add2(av, Cj[q])), act2);
-        }
-    } else {
-        const float* An = a.Avec + (size_t)n * SHP;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int o = quarter * 16 + 2 * q;
-            const float2 av = o < SHP ? __ldg(reinterpret_cast<const float2*>(An + o)) : make_float2(0.f, 0.f);
-            v[q] = mul2(act_tanh2<FAST>(add2(av, Cj[q])), act2);
-        }
-    }
-    store_chunk2(tile, row, 2 * quarter, v);
-    store_chunk2(tile, row, 2 * quarter + 1, v + 4);
-}
-
-// D(tmem_d)[128 x 64] = A . B^T with split-bf16 operands: hi*hi + lo*hi + hi*lo.  A K-major [128 x 64]; B is a [64 x 64] weight tile,
-// K-major (b_transposed = 0: forward) or read MN-major (b_transposed = 1: data gradient).  Issued by ONE thread.
-__device__ __forceinline__ void issue_rows_x_weights(uint32_t tmem_d, const uint8_t* a_tile, const uint8_t* w_tile, int b_transposed) {
+// ---------------------------------------------------------------------------------------------------------------
+// MMA issue (ONE thread)
+// ---------------------------------------------------------------------------------------------------------------
+// k-step kc (16 features) of D(tmem_d)[128 x 64] (+)= A . B^T, split-bf16: hi*hi + lo*hi + hi*lo.  A K-major [128 x 64]; B a [64 x 64]
+// weight tile, K-major (b_transposed = 0: forward) or read MN-major (b_transposed = 1: data gradient).
+__device__ __forceinline__ void issue_kstep(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, int kc, int b_transposed) {
     const uint32_t idesc = instr_desc(FMT_BF16, 128, HPAD, 0, b_transposed);
-    uint64_t ah = smem_desc(smem_u32(a_tile), 128 * 16, 128);
-    uint64_t bh = b_transposed ? smem_desc(smem_u32(w_tile), 128, HPAD * 16) : smem_desc(smem_u32(w_tile), HPAD * 16, 128);
-    const uint64_t a_step = (2 * 128 * 16) >> 4, b_step = (b_transposed ? 256 : 2 * HPAD * 16) >> 4;  // start-address field is in 16-byte units
-    const uint64_t a_lo = TILE_HALF >> 4, b_lo = WT_HALF >> 4;
-#pragma unroll 1
-    for (int ks = 0; ks < 4; ++ks) {  // K = 16 per MMA
-        mma_f16(tmem_d, ah, bh, idesc, ks > 0);
-        mma_f16(tmem_d, ah + a_lo, bh, idesc, 1);
-        mma_f16(tmem_d, ah, bh + b_lo, idesc, 1);
-        ah += a_step, bh += b_step;
-    }
+    const uint64_t ah = smem_desc(a_addr + (uint32_t)kc * (2 * 128 * 16), 128 * 16, 128);
+    const uint64_t bh = b_transposed ? smem_desc(w_addr + (uint32_t)kc * 256, 128, HPAD * 16) : smem_desc(w_addr + (uint32_t)kc * (2 * HPAD * 16), HPAD * 16, 128);
+    const uint64_t a_lo = TILE_HALF >> 4, b_lo = WT_HALF >> 4;  // the start-address field is in 16-byte units
+    mma_f16(tmem_d, ah, bh, idesc, kc > 0);
+    mma_f16(tmem_d, ah + a_lo, bh, idesc, 1);
+    mma_f16(tmem_d, ah, bh + b_lo, idesc, 1);
 }
 
-// D(tmem_d)[64 (M=64 lane layout) x n_cols] (+)= X^T . Y over the 128 rows: X a [128 x 64] tile, Y a [128 x 64] tile or the [128 x 8] dy tile,
-// both read MN-major
-__device__ __forceinline__ void issue_transposed_product(uint32_t tmem_d, const uint8_t* x_tile, const uint8_t* y_tile, int n_cols, uint32_t y_half,
-                                                         bool zero_first) {
-    const uint32_t idesc = instr_desc(FMT_BF16, 64, n_cols, 1, 1);
-    uint64_t xh = smem_desc(smem_u32(x_tile), 128, 128 * 16), yh = smem_desc(smem_u32(y_tile), 128, 128 * 16);
-    const uint64_t x_lo = TILE_HALF >> 4, y_lo = y_half >> 4;
-#pragma unroll 1
-    for (int ks = 0; ks < 8; ++ks) {  // 16 rows per MMA
-        mma_f16(tmem_d, xh, yh, idesc, (ks > 0 || !zero_first) ? 1u : 0u);
-        mma_f16(tmem_d, xh + x_lo, yh, idesc, 1);
-        mma_f16(tmem_d, xh, yh + y_lo, idesc, 1);
-        xh += 256 >> 4, yh += 256 >> 4;
+// D(tmem_d)[128 x 128] (+)= [X_hi | X_lo]^T . [Y_hi | Y_lo] over the 128 rows: both [128 x 64](hi, lo) tiles read MN-major, 8 MMAs of 16 rows
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t x_addr, uint32_t y_addr, bool zero_first) {
+    const uint32_t idesc = instr_desc(FMT_BF16, 128, 128, 1, 1);
+    uint64_t xd = smem_desc(x_addr, 128, 128 * 16), yd = smem_desc(y_addr, 128, 128 * 16);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        mma_f16(tmem_d, xd, yd, idesc, (ks > 0 || !zero_first) ? 1u : 0u);
+        xd += 256 >> 4, yd += 256 >> 4;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// forward
+// epilogue building blocks.  Epilogue thread = (row, column group g of NG): warps q, q+4, q+8, .. own TMEM lanes 32q..32q+31; group g
+// owns the 16-byte chunks (8 features) {g, g+NG, g+2NG, ..} < 8 of the row, so that the MMA k-chunks (16 features = chunks 2kc, 2kc+1)
+// complete progressively.  Chunk 6 has 4 live features (48..51), chunk 7 none (always written as zeros).
 // ---------------------------------------------------------------------------------------------------------------
+template <int NP>
+using np_t = std::integral_constant<int, NP>;
+
+__device__ __forceinline__ void arrive_chunk(uint64_t* bar, int lane) {
+    fence_proxy_async();  // this thread's generic-proxy tile writes -> visible to the tensor core's async-proxy reads
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+struct RowCtx {
+    int row, lane, q, g;   // TMEM lane / tile row, lane in warp, lane quarter, column group
+    uint32_t lane_taddr;   // (32 q) << 16
+};
+__device__ __forceinline__ RowCtx row_ctx() {
+    RowCtx r;
+    const int warp = threadIdx.x >> 5;
+    r.lane = threadIdx.x & 31, r.q = warp & 3, r.g = warp >> 2;
+    r.row = 32 * r.q + r.lane;
+    r.lane_taddr = (uint32_t)(32 * r.q) << 16;
+    return r;
+}
+
+// this thread's accumulator columns: v[8 i .. 8 i + 7] = features of chunk g + NG i
+template <int NG>
+__device__ __forceinline__ void load_acc(uint32_t acc, int g, float* v) {
+#pragma unroll
+    for (int i = 0; i < 8 / NG; ++i) {
+        const int c = g + NG * i;
+        if (c < 6) tmem_ld8(acc + 8 * c, v + 8 * i);
+        else if (c == 6) tmem_ld4(acc + 48, v + 8 * i);
+    }
+    tmem_ld_wait();
+    fence_before_sync();  // orders these loads before the MMAs that overwrite the accumulator after a later barrier
+}
+
+// layer 0: z0 = A[n] + Cp[j] for this thread's features (A[n][50] = ONE_SEED from the prep kernel -> constant-1 feature)
+template <int NG>
+__device__ __forceinline__ void load_layer0(const float* An, const float* Cj, int g, float* v) {
+#pragma unroll
+    for (int i = 0; i < 8 / NG; ++i) {
+        const int c = g + NG * i;
+        if (c < 7) {  // SHP = 52: chunk 6 holds features 48..51
+            const float4 x = *reinterpret_cast<const float4*>(An + 8 * c), y = *reinterpret_cast<const float4*>(Cj + 8 * c);
+            v[8 * i] = x.x + y.x, v[8 * i + 1] = x.y + y.y, v[8 * i + 2] = x.z + y.z, v[8 * i + 3] = x.w + y.w;
+        }
+        if (c < 6) {
+            const float4 x = *reinterpret_cast<const float4*>(An + 8 * c + 4), y = *reinterpret_cast<const float4*>(Cj + 8 * c + 4);
+            v[8 * i + 4] = x.x + y.x, v[8 * i + 5] = x.y + y.y, v[8 * i + 6] = x.z + y.z, v[8 * i + 7] = x.w + y.w;
+        }
+    }
+}
+
+// Applies op(np, i, chunk, vals) to every chunk of this thread, stores it as split-bf16 into `dst` and signals its k-chunk.
+template <int NG, typename Op>
+__device__ __forceinline__ void transform_store(float2* v, uint8_t* dst, const RowCtx& rc, uint64_t* kbar, Op&& op) {
+#pragma unroll
+    for (int i = 0; i < 8 / NG; ++i) {
+        const int c = rc.g + NG * i;
+        if (c < 6) {
+            op(np_t<4>{}, i, c, v + 4 * i);
+            store_chunk2<4>(dst, rc.row, c, v + 4 * i);
+        } else if (c == 6) {
+            op(np_t<2>{}, i, c, v + 4 * i);
+            store_chunk2<2>(dst, rc.row, c, v + 4 * i);
+        } else {
+            store_chunk_zero(dst, rc.row, c);
+        }
+        arrive_chunk(kbar + (c >> 1), rc.lane);
+    }
+}
+
+// cp.async of the tile's layer-0 coordinate parts Cp[j][0..SHP) (contiguous, 16-byte aligned rows) into a staging slot
+__device__ __forceinline__ void stage_tile_inputs(const Args& a, const TileIdx& ti, float* cps_slot, int ne) {
+    const float* src = a.Cpg + ((size_t)ti.d * a.tl.P + ti.p0) * SHP;
+    for (int i = threadIdx.x; i < ti.np * (SHP / 4); i += ne) cp_async16(cps_slot + 4 * i, src + 4 * i);
+}
+
+__device__ __forceinline__ void init_barriers(uint64_t* bars, int warps_per_kchunk) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) mbar_init(&bars[BAR_K + k], warps_per_kchunk);
+    mbar_init(&bars[BAR_ACC], 1), mbar_init(&bars[BAR_ACC + 1], 1), mbar_init(&bars[BAR_DONE], 1);
+    mbar_fence_init();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward: 8 epilogue warps (2 column groups) + the MMA warp, two CTAs per SM
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int NG_F = 2, NE_F = 128 * NG_F, NT_F = NE_F + 32;
+
 template <bool FAST, int C>
-__global__ void __launch_bounds__(NT, 2) inr_fwd_tc_kernel(Args a) {
+__global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
+    constexpr int NG = NG_F, NE = NE_F, NCH = 8 / NG;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    TcSmem s(smem_raw, a.net, a.tl, 1);
     const Net& nt = a.net;
     const Tiling& tl = a.tl;
-    const int t = threadIdx.x, warp = t >> 5;
-    const int row = t & 127, quarter = warp >> 2;
-    const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(quarter * 16);
-    const int L = nt.nl;
+    TcSmem s(smem_raw, nt, tl, 1, false, NG);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     load_weight_tiles(a, s);
     if (s.As != nullptr && tl.nChunks == 1)
-        for (int i = t; i < tl.NC * SHP; i += NT) s.As[i] = a.Avec[i];
-    if (warp == 0) tmem_alloc(s.tmem, 64);
-    if (t == 0) {
-        mbar_init(&s.bars[0], 1);
-        mbar_fence_init();
-    }
+        for (int i = t; i < tl.NC * SHP; i += NT_F) s.As[i] = a.Avec[i];
+    if (warp == NE / 32) tmem_alloc(s.tmem, TM_COLS_FWD);
+    if (t == 0) init_barriers(s.bars, 8);
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tm = *s.tmem;
-    uint32_t phase = 0;
+    const int myTiles = (tl.numTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     uint8_t* T = s.tiles;
-    for (int tile = blockIdx.x; tile < tl.numTiles; tile += gridDim.x) {
-        const TileIdx ti = decode_tile(tl, tile);
-        if (s.As != nullptr && tl.nChunks > 1)
-            for (int i = t; i < ti.nn * SHP; i += NT) s.As[i] = a.Avec[(size_t)ti.n0 * SHP + i];
-        tile_prologue(a, s, ti, false);
-        const int nl = row / tl.TP, j = row % tl.TP;
-        const bool active = nl < ti.nn && j < ti.np;
-        const float actf = active ? 1.f : 0.f;
-        layer0_to_tile<FAST>(a, s, T, row, quarter, actf, active ? ti.n0 + nl : 0, active ? nl : 0, active ? j : 0);
-#pragma unroll 1
-        for (int l = 1; l < L; ++l) {
-            fence_proxy_async();
-            fence_before_sync();
-            __syncthreads();
-            if (t == 0) {
-                fence_after_sync();
-                issue_rows_x_weights(tm + TM_ACC, T, s.wt + (size_t)(l - 1) * WT_BYTES, 0);
-                mma_commit(&s.bars[0]);
-            }
-            mbar_wait(&s.bars[0], phase);
-            phase ^= 1;
-            fence_after_sync();
-            float2 v[8];
-            tmem_ld16(tm + TM_ACC + lane_addr, reinterpret_cast<float*>(v));
-            tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = act_tanh2<FAST>(v[q]);  // inactive rows: h_1 == 0 (bias feature too) => z == 0 => tanh == 0
-            if (l < L - 1) {
-                store_chunk2(T, row, 2 * quarter, v);
-                store_chunk2(T, row, 2 * quarter + 1, v + 4);
-            } else {  // output layer: partial dot products of this thread's 16 features
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const float2* w = reinterpret_cast<const float2*>(s.Wout + c * HPAD + quarter * 16);
-                    float2 y = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) y = fma2(v[q], w[q], y);
-                    s.scratch[(row * 4 + quarter) * C + c] = y.x + y.y;
-                }
-            }
-        }
-        fence_before_sync();
-        __syncthreads();
-        if (quarter == 0 && active) {
-            const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + nl)) * C) * tl.P + ti.p0 + j;
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float* yp = s.scratch + (row * 4) * C + c;
-                const float y = s.bout[c] + ((yp[0] + yp[C]) + (yp[2 * C] + yp[3 * C]));
-                a.img[base + (size_t)c * tl.P] = act_tanh<FAST>(y);
-            }
-        }
-        __syncthreads();  // scratch / Cp / the tile buffer are rewritten by the next tile
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tm, 64);
-}
 
-// ---------------------------------------------------------------------------------------------------------------
-// backward
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int STG = 132;  // row stride (floats) of the fp32 staging panel stage[o][row] for dz_0
-
-template <bool FAST, int C>
-__global__ void __launch_bounds__(NT, 1) inr_bwd_tc_kernel(Args a) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const Net& nt = a.net;
-    const Tiling& tl = a.tl;
-    const int L = nt.nl;  // hidden layers; activation tiles T[0..L-1] hold h_1..h_L, one extra rotating tile X = T[L]
-    TcSmem s(smem_raw, nt, tl, L + 1);
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const int row = t & 127, quarter = warp >> 2;
-    const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(quarter * 16);
-    const bool want_w = a.want_weights != 0;
-    load_weight_tiles(a, s);
-    if (s.As != nullptr)
-        for (int i = t; i < tl.NC * SHP; i += NT) s.As[i] = a.Avec[i];
-    if (warp == 0) tmem_alloc(s.tmem, TM_COLS);
-    if (t == 0) {
-        mbar_init(&s.bars[0], 1);
-        mbar_init(&s.bars[1], 1);
-        mbar_fence_init();
-    }
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tm = *s.tmem;
-    const uint32_t tm_dwout = TM_DW + (uint32_t)(L - 1) * 64;
-    uint32_t ph_acc = 0, ph_done = 0;
-    bool first = true;
-    auto Tile = [&](int i) { return s.tiles + (size_t)i * TILE_BYTES; };
-    // dz_0 is staged in fp32 ([o][row], conflict-free) in the tile that held h_2: it is not an MMA operand.  L == 2 has no free
-    // tile before the last data-gradient epilogue, so the staging panel then lives in X's successor: host guarantees L >= 3 here.
-    float* stage = reinterpret_cast<float*>(Tile(1));
-    // dA[n][o] accumulators of this thread: entries e = t + NT*q  ->  (n = e / HID, o = e % HID); N <= 40 (host check)
-    constexpr int DA_PER_THREAD = 4;
-    float dA[DA_PER_THREAD] = {0.f, 0.f, 0.f, 0.f};
-
-    for (int tile = blockIdx.x; tile < tl.numTiles; tile += gridDim.x) {
-        const TileIdx ti = decode_tile(tl, tile);
-        tile_prologue(a, s, ti, a.want_affine != 0);
-        const int nl = row / tl.TP, j = row % tl.TP;
-        const bool active = nl < ti.nn && j < ti.np;
-        const float actf = active ? 1.f : 0.f;
-        if (!first) {  // every MMA of the previous tile (they read the tiles we are about to overwrite) has completed
-            mbar_wait(&s.bars[1], ph_done);
-            ph_done ^= 1;
-            fence_after_sync();
-        }
-        // ---- forward recompute: h_1 (CUDA cores), h_2..h_L (tensor cores), all kept as tiles
-        layer0_to_tile<FAST>(a, s, Tile(0), row, quarter, actf, active ? ti.n0 + nl : 0, active ? nl : 0, active ? j : 0);
+    if (warp == NE / 32) {
+        if (lane == 0) {  // ---- MMA issuer: stage st computes z_{st+1} = h_{st+1} W^T into accumulator st&1 as the chunks of h_{st+1} arrive
+            const uint32_t t_addr = smem_u32(T), w_addr = smem_u32(s.wt);
+            uint32_t pk = 0;
+            for (int it = 0; it < myTiles; ++it) {
 #pragma unroll 1
-        for (int l = 1; l < L; ++l) {
-            fence_proxy_async();
-            fence_before_sync();
-            __syncthreads();
-            if (t == 0) {
+                for (int st = 0; st < LH - 1; ++st) {
+                    const uint32_t acc = tm + TM_ACC + (uint32_t)(st & 1) * 64;
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) {
+                        mbar_wait(&s.bars[BAR_K + kc], pk);
+                        fence_after_sync();
+                        issue_kstep(acc, t_addr, w_addr + (uint32_t)st * WT_BYTES, kc, 0);
+                    }
+                    pk ^= 1;
+                    mma_commit(&s.bars[BAR_ACC + (st & 1)]);
+                }
+            }
+        }
+    } else {  // ---- epilogue threads
+        const RowCtx rc = row_ctx();
+        uint32_t pa0 = 0, pa1 = 0;
+        const bool multi_chunk = tl.nChunks > 1;
+        if (myTiles > 0) stage_tile_inputs(a, decode_tile(tl, blockIdx.x), s.Cps, NE);
+        cp_async_commit();
+        const int nl = rc.row / tl.TP, j = rc.row % tl.TP;
+        for (int it = 0; it < myTiles; ++it) {
+            const TileIdx ti = decode_tile(tl, blockIdx.x + it * gridDim.x);
+            cp_async_wait<0>();
+            named_bar_sync(1, NE);  // staged Cp visible; every epilogue thread is done with the previous tile's scratch
+            if (it + 1 < myTiles) stage_tile_inputs(a, decode_tile(tl, blockIdx.x + (it + 1) * gridDim.x), s.Cps + ((it + 1) & 1) * tl.TP * SHP, NE);
+            cp_async_commit();
+            const float* Cps = s.Cps + (it & 1) * tl.TP * SHP;
+            const bool active = nl < ti.nn && j < ti.np;
+            const float* An = (s.As != nullptr && !multi_chunk) ? s.As + (active ? nl : 0) * SHP : a.Avec + (size_t)(ti.n0 + (active ? nl : 0)) * SHP;
+            const float* Cj = Cps + (active ? j : 0) * SHP;
+            auto tanh_op = [&](auto np, int, int, float2* x) {
+#pragma unroll
+                for (int p = 0; p < decltype(np)::value; ++p) x[p] = act_tanh2<FAST>(x[p]);
+            };
+            auto l0_op = [&](auto np, int, int, float2* x) {
+#pragma unroll
+                for (int p = 0; p < decltype(np)::value; ++p) {
+                    x[p] = act_tanh2<FAST>(x[p]);
+                    if (!active) x[p] = make_float2(0.f, 0.f);  // inactive rows: h_1 == 0 (bias feature too) => every later z == 0 => tanh == 0
+                }
+            };
+            float2 v[4 * NCH];
+            float* vf = reinterpret_cast<float*>(v);
+            // h_1 (the tile buffer is free: the accumulator of the previous tile's last layer was waited for)
+            load_layer0<NG>(An, Cj, rc.g, vf);
+            transform_store<NG>(v, T, rc, &s.bars[BAR_K], l0_op);
+#pragma unroll 1
+            for (int st = 0; st < LH - 1; ++st) {
+                const uint32_t acc = tm + TM_ACC + (uint32_t)(st & 1) * 64 + rc.lane_taddr;
+                if (st & 1) {
+                    mbar_wait(&s.bars[BAR_ACC + 1], pa1);
+                    pa1 ^= 1;
+                } else {
+                    mbar_wait(&s.bars[BAR_ACC], pa0);
+                    pa0 ^= 1;
+                }
                 fence_after_sync();
-                issue_rows_x_weights(tm + TM_ACC, Tile(l - 1), s.wt + (size_t)(l - 1) * WT_BYTES, 0);
-                mma_commit(&s.bars[0]);
-            }
-            mbar_wait(&s.bars[0], ph_acc);
-            ph_acc ^= 1;
-            fence_after_sync();
-            float2 v[8];
-            tmem_ld16(tm + TM_ACC + lane_addr, reinterpret_cast<float*>(v));
-            tmem_ld_wait();
+                load_acc<NG>(acc, rc.g, vf);
+                if (st < LH - 2) {  // h_{st+2} in place (every MMA that read the old tile has completed)
+                    transform_store<NG>(v, T, rc, &s.bars[BAR_K], tanh_op);
+                } else {  // last hidden layer: h_LH stays in registers; output layer on CUDA cores
+                    float y[C];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = act_tanh2<FAST>(v[q]);  // inactive rows: h_1 == 0 (bias feature too) => z == 0 => tanh == 0
-            store_chunk2(Tile(l), row, 2 * quarter, v);
-            store_chunk2(Tile(l), row, 2 * quarter + 1, v + 4);
-            if (l == L - 1) {  // output layer: partial dot products of this thread's 16 features of h_L
+                    for (int c = 0; c < C; ++c) y[c] = 0.f;
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    const float2* w = reinterpret_cast<const float2*>(s.Wout + c * HPAD + quarter * 16);
-                    float2 y = make_float2(0.f, 0.f);
+                    for (int i = 0; i < NCH; ++i) {
+                        const int ch = rc.g + NG * i;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) y = fma2(v[q], w[q], y);
-                    s.scratch[(row * 4 + quarter) * C + c] = y.x + y.y;
-                }
-            }
-        }
-        __syncthreads();
-        // ---- output layer (CUDA cores): y, dy = g (1 - y^2), dz_{L-1} = (Wout^T dy) (1 - h_L^2) -> tile X; dy -> dy tile
-        {
-            float dy[4] = {0.f, 0.f, 0.f, 0.f};
-            const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + (active ? nl : 0))) * C) * tl.P + ti.p0 + (active ? j : 0);
+                        for (int p = 0; p < 4; ++p) {
+                            if (ch < 6 || (ch == 6 && p < 2)) {
+                                const float2 h = act_tanh2<FAST>(v[4 * i + p]);
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                const float* yp = s.scratch + (row * 4) * C + c;
-                const float y = act_tanh<FAST>(s.bout[c] + ((yp[0] + yp[C]) + (yp[2 * C] + yp[3 * C])));
-                const float g = active ? a.g_img[base + (size_t)c * tl.P] : 0.f;
-                dy[c] = g * (1.f - y * y);
-            }
-            float2 hv[8], v[8];
-            load_chunk2(Tile(L - 1), row, 2 * quarter, hv);
-            load_chunk2(Tile(L - 1), row, 2 * quarter + 1, hv + 4);
+                                for (int c = 0; c < C; ++c) {
+                                    const float2 w = *reinterpret_cast<const float2*>(s.Wout + c * HPAD + 8 * ch + 2 * p);
+                                    y[c] = fmaf(h.x, w.x, fmaf(h.y, w.y, y[c]));
+                                }
+                            }
+                        }
+                    }
+                    if (rc.g != 0) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float2 dh = make_float2(0.f, 0.f);
+                        for (int c = 0; c < C; ++c) s.scratch[(rc.row * NG + rc.g) * C + c] = y[c];
+                    }
+                    named_bar_sync(2 + rc.q, 32 * NG);  // the warps of this lane quarter
+                    if (rc.g == 0 && active) {
+                        const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + nl)) * C) * tl.P + ti.p0 + j;
 #pragma unroll
-                for (int c = 0; c < C; ++c)
-                    dh = fma2(reinterpret_cast<const float2*>(s.Wout + c * HPAD + quarter * 16)[q], make_float2(dy[c], dy[c]), dh);
-                // dh (1 - h^2); padding columns: Wout == 0; constant-1 column: 1 - 1 == 0
-                v[q] = fma2(mul2(dh, mul2(hv[q], hv[q])), make_float2(-1.f, -1.f), dh);
-            }
-            store_chunk2(Tile(L), row, 2 * quarter, v);
-            store_chunk2(Tile(L), row, 2 * quarter + 1, v + 4);
-            if (want_w && quarter == 0) {  // dy as a [128 x 8] split-bf16 tile (one 16-byte chunk per row)
-                uint32_t hi[2], lo[2];
+                        for (int c = 0; c < C; ++c) {
+                            float yy = y[c];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(dy[2 * q], dy[2 * q + 1]);
-                    const float2 hf = __bfloat1622float2(h2);
-                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(dy[2 * q] - hf.x, dy[2 * q + 1] - hf.y);
-                    hi[q] = *reinterpret_cast<const uint32_t*>(&h2), lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
-                }
-                *reinterpret_cast<uint4*>(s.dy + row * 16) = make_uint4(hi[0], hi[1], 0u, 0u);
-                *reinterpret_cast<uint4*>(s.dy + DY_HALF + row * 16) = make_uint4(lo[0], lo[1], 0u, 0u);
-            }
-        }
-        // ---- layers L-1 .. 1.  dz_l sits in tile `src`; h_l in Tile(l-1); dz_{l-1} goes to `dst` (a tile no pending MMA reads)
-        int src = L, dst = L - 1;
-#pragma unroll 1
-        for (int l = L - 1; l >= 1; --l) {
-            fence_proxy_async();
-            fence_before_sync();
-            __syncthreads();
-            if (t == 0) {
-                fence_after_sync();
-                if (want_w && l == L - 1)  // output layer: dWout[c][i] (dbout in column ONE_COL) = sum_r h_L[r][i] dy[r][c]
-                    issue_transposed_product(tm + tm_dwout, Tile(L - 1), s.dy, 8, DY_HALF, first);
-                issue_rows_x_weights(tm + TM_ACC, Tile(src), s.wt + (size_t)(l - 1) * WT_BYTES, 1);
-                mma_commit(&s.bars[0]);
-                if (want_w)  // dW_l[o][i] (bias gradient in column ONE_COL) += sum_r dz_l[r][o] h_l[r][i]; overlaps the epilogue below
-                    issue_transposed_product(tm + TM_DW + (uint32_t)(l - 1) * 64, Tile(src), Tile(l - 1), HPAD, TILE_HALF, first);
-                if (l == 1) mma_commit(&s.bars[1]);
-            }
-            mbar_wait(&s.bars[0], ph_acc);
-            ph_acc ^= 1;
-            fence_after_sync();
-            // dz_{l-1}[k] = dh_l[k] (1 - h_l[k]^2)   (h_l[50] == 1 zeroes the bias column; padding columns of W are 0)
-            float2 v[8], hv[8];
-            tmem_ld16(tm + TM_ACC + lane_addr, reinterpret_cast<float*>(v));
-            load_chunk2(Tile(l - 1), row, 2 * quarter, hv);
-            load_chunk2(Tile(l - 1), row, 2 * quarter + 1, hv + 4);
-            tmem_ld_wait();
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = fma2(mul2(v[q], mul2(hv[q], hv[q])), make_float2(-1.f, -1.f), v[q]);
-            if (l > 1) {
-                store_chunk2(Tile(dst), row, 2 * quarter, v);
-                store_chunk2(Tile(dst), row, 2 * quarter + 1, v + 4);
-            } else {  // dz_0 feeds only CUDA-core reductions: stage it in fp32 (the tile of h_2 is free: dW_2's MMAs completed before bar 0 fired)
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    stage[(quarter * 16 + 2 * q) * STG + row] = v[q].x;
-                    stage[(quarter * 16 + 2 * q + 1) * STG + row] = v[q].y;
-                }
-            }
-            // rotate: the old src is free once the NEXT step's data-gradient MMAs (issued after this step's dW MMAs) have completed
-            src = dst;
-            dst = (src == L) ? L - 1 : L;
-        }
-        __syncthreads();  // dz_0 staged
-        // ---- layer 0: G0[j][o] = sum_n dz0, dA[n][o] += sum_j dz0   (CUDA cores, fp32 staging panel)
-        float* G0s = s.scratch;
-        for (int i = t; i < ti.np * SHP; i += NT) {
-            const int o = i / ti.np, jj = i % ti.np;  // consecutive lanes -> consecutive pixels of one feature row
-            float sum = 0.f;
-            if (o < HID) {
-                const float* zr = stage + o * STG + jj;
-                for (int n = 0; n < ti.nn; ++n) sum += zr[n * tl.TP];
-            }
-            G0s[jj * SHP + o] = sum;
-        }
-        if (want_w) {
-#pragma unroll
-            for (int q = 0; q < DA_PER_THREAD; ++q) {
-                const int e = t + NT * q;
-                if (e < ti.nn * HID) {
-                    const int o = e / ti.nn, n = e % ti.nn;  // NOTE: entry order (o-major) is this kernel's private convention, see the read-out
-                    const float* zr = stage + o * STG + n * tl.TP;
-                    float sum = 0.f;
-                    for (int jj = 0; jj < ti.np; ++jj) sum += zr[jj];
-                    dA[q] += sum;
-                }
-            }
-        }
-        __syncthreads();
-        if (want_w) {
-            float* gdst = a.G0 + ((size_t)ti.d * tl.P + ti.p0) * SHP;
-            for (int i = t; i < ti.np * SHP; i += NT) gdst[i] = G0s[i];
-        }
-        if (a.want_affine) {
-            const int pe = nt.pe;
-            for (int i = t; i < ti.np * pe; i += NT) {
-                const int jj = i / pe, m = i % pe;
-                const float4* ws_ = reinterpret_cast<const float4*>(a.W0cT + (size_t)m * SHP);
-                const float4* wc_ = reinterpret_cast<const float4*>(a.W0cT + (size_t)(pe + m) * SHP);
-                const float4* g4 = reinterpret_cast<const float4*>(G0s + jj * SHP);
-                float ds = 0.f, dc = 0.f;
-                for (int o4 = 0; o4 < SHP / 4; ++o4) {
-                    const float4 g = g4[o4], a4 = __ldg(ws_ + o4), b4 = __ldg(wc_ + o4);
-                    ds += g.x * a4.x + g.y * a4.y + g.z * a4.z + g.w * a4.w;
-                    dc += g.x * b4.x + g.y * b4.y + g.z * b4.z + g.w * b4.w;
-                }
-                const float sn = s.beta[jj * 2 * pe + m], cs = s.beta[jj * 2 * pe + pe + m];
-                s.beta[jj * 2 * pe + m] = ds * cs - dc * sn;  // d/dphi
-            }
-            __syncthreads();
-            float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (t < ti.np) {
-                float g0 = 0.f, g1 = 0.f;
-                for (int m = 0; m < pe; ++m) {
-                    const float dphi = s.beta[t * 2 * pe + m];
-                    g0 = fmaf(dphi, a.B[m], g0);
-                    g1 = fmaf(dphi, a.B[pe + m], g1);
-                }
-                const int p = ti.p0 + t;
-                const float r0 = a.coords[2 * p] - s.affc[6], r1 = a.coords[2 * p + 1] - s.affc[7];
-                v[0] = g0, v[1] = g1, v[2] = g0 * r0, v[3] = g0 * r1, v[4] = g1 * r0, v[5] = g1 * r1;
-            }
-            if (t < 32) {  // TP <= 8: the first warp holds every contribution
-#pragma unroll
-                for (int q = 0; q < 6; ++q) v[q] = warp_sum(v[q]);
-                if (t == 0) {
-                    float* pdst = a.affpart + ((size_t)ti.d * tl.tilesP + ti.p0 / tl.TP) * 6;
-                    for (int q = 0; q < 6; ++q) pdst[q] = v[q];
-                }
-            }
-        }
-        first = false;
-        __syncthreads();
-    }
-    // ---- drain: wait for the last tile's MMAs, then read the weight-gradient accumulators out of TMEM
-    if (!first) {
-        mbar_wait(&s.bars[1], ph_done);
-        fence_after_sync();
-    }
-    if (want_w) {
-        float* part = a.partials + (size_t)blockIdx.x * partial_size(nt, tl, SHP);
-        float* p_dW = part;
-        float* p_db = part + (size_t)(L - 1) * HID * HID;
-        float* p_dWout = p_db + (size_t)(L - 1) * SHP;
-        float* p_dA = p_dWout + (size_t)C * SHP + 4;
-        if (warp < 4) {  // M=64 accumulator layout: row o -> lane (o/16)*32 + o%16
-            const int o = 16 * warp + lane;
-            const uint32_t lb = (uint32_t)(warp * 32) << 16;
-#pragma unroll 1
-            for (int l = 1; l < L; ++l) {
-#pragma unroll 1
-                for (int g = 0; g < 4; ++g) {
-                    float v[16];
-                    tmem_ld16(tm + TM_DW + (uint32_t)(l - 1) * 64 + lb + g * 16, v);
-                    tmem_ld_wait();
-                    if (lane < 16 && o < HID) {
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) {
-                            const int i = g * 16 + q;
-                            if (i < HID) p_dW[(size_t)(l - 1) * HID * HID + o * HID + i] = v[q];
-                            else if (i == ONE_COL) p_db[(l - 1) * SHP + o] = v[q];
+                            for (int gg = 1; gg < NG; ++gg) yy += s.scratch[(rc.row * NG + gg) * C + c];
+                            a.img[base + (size_t)c * tl.P] = act_tanh<FAST>(s.bout[c] + yy);
                         }
                     }
                 }
             }
-            float v[16];
-            tmem_ld16(tm + tm_dwout + lb, v);
-            tmem_ld_wait();
-            if (lane < 16) {  // row i = o of D[i][c]
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    if (o < HID) p_dWout[c * SHP + o] = v[c];
-                    else if (o == ONE_COL) p_dWout[C * SHP + c] = v[c];
-                }
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < DA_PER_THREAD; ++q) {
-            const int e = t + NT * q;
-            if (e < tl.NC * HID) p_dA[(e % tl.NC) * SHP + e / tl.NC] = dA[q];  // e = o * N + n (single latent chunk: nn == NC == N)
         }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tm, TM_COLS);
+    if (warp == NE / 32) tmem_dealloc(tm, TM_COLS_FWD);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// backward: 16 epilogue warps (4 column groups) + the MMA warp, one CTA per SM
+// ---------------------------------------------------------------------------------------------------------------
+// tile buffer roles; buffer of role r in iteration `it` = (r + 2 it) % 5: the rotation makes every reuse hazard-free by commit ordering
+constexpr int ROLE_H1 = 0, ROLE_DA = 3, ROLE_DB = 4;
+constexpr int NG_B = 4, NE_B = 128 * NG_B, NT_B = NE_B + 32;
+constexpr int MAX_DA = 4;   // dA[n][o] accumulators per epilogue thread: N * 50 <= 4 * 512  (N <= 40)
+
+template <bool FAST, int C>
+__global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
+    constexpr int NG = NG_B, NE = NE_B, NCH = 8 / NG;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const Net& nt = a.net;
+    const Tiling& tl = a.tl;
+    TcSmem s(smem_raw, nt, tl, NBUF_BWD, a.want_affine != 0, NG);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const bool want_w = a.want_weights != 0;
+    load_weight_tiles(a, s);
+    if (s.As != nullptr)
+        for (int i = t; i < tl.NC * SHP; i += NT_B) s.As[i] = a.Avec[i];
+    if (warp == NE / 32) tmem_alloc(s.tmem, TM_COLS_BWD);
+    if (t == 0) init_barriers(s.bars, 8);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = *s.tmem;
+    const int myTiles = (tl.numTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == NE / 32) {
+        if (lane == 0) {  // ---- MMA issuer
+            const uint32_t tiles_addr = smem_u32(s.tiles), w_addr = smem_u32(s.wt);
+            uint32_t pk = 0;
+            for (int it = 0; it < myTiles; ++it) {
+                const int rot = (2 * it) % NBUF_BWD;
+                auto buf = [&](int role) { return tiles_addr + (uint32_t)((role + rot) % NBUF_BWD) * TILE_BYTES; };
+                int st = 0;
+                // forward recompute: z_l = h_l W_l^T, l = 1..3 (operand h_l = role l-1)
+#pragma unroll 1
+                for (int l = 1; l < LH; ++l, ++st) {
+                    const uint32_t acc = tm + TM_ACC + (uint32_t)(st & 1) * 64;
+                    const uint32_t hb = buf(ROLE_H1 + l - 1);
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) {
+                        mbar_wait(&s.bars[BAR_K + kc], pk);
+                        fence_after_sync();
+                        LMR_TRACE(1, (it * 6 + st) * 5 + kc);
+                        issue_kstep(acc, hb, w_addr + (uint32_t)(l - 1) * WT_BYTES, kc, 0);
+                    }
+                    pk ^= 1;
+                    mma_commit(&s.bars[BAR_ACC + (st & 1)]);
+                    LMR_TRACE(1, (it * 6 + st) * 5 + 4);
+                }
+                // backward: dh_l = dz_l W_l (operand dz_l alternates DA, DB, DA), then dW_l += dz_l^T h_l behind it
+#pragma unroll 1
+                for (int l = LH - 1; l >= 1; --l, ++st) {
+                    const uint32_t acc = tm + TM_ACC + (uint32_t)(st & 1) * 64;
+                    const uint32_t dz = buf(((LH - 1 - l) & 1) ? ROLE_DB : ROLE_DA);
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) {
+                        mbar_wait(&s.bars[BAR_K + kc], pk);
+                        fence_after_sync();
+                        LMR_TRACE(1, (it * 6 + st) * 5 + kc);
+                        issue_kstep(acc, dz, w_addr + (uint32_t)(l - 1) * WT_BYTES, kc, 1);
+                    }
+                    pk ^= 1;
+                    mma_commit(&s.bars[BAR_ACC + (st & 1)]);
+                    LMR_TRACE(1, (it * 6 + st) * 5 + 4);
+                    if (want_w) issue_wgrad(tm + TM_DW + (uint32_t)(l - 1) * 128, dz, buf(ROLE_H1 + l - 1), it == 0);
+                }
+            }
+            mma_commit(&s.bars[BAR_DONE]);
+        }
+    } else {  // ---- epilogue threads
+        const RowCtx rc = row_ctx();
+        uint32_t pa0 = 0, pa1 = 0;
+        auto wait_acc = [&](int st) {
+            if (st & 1) {
+                mbar_wait(&s.bars[BAR_ACC + 1], pa1);
+                pa1 ^= 1;
+            } else {
+                mbar_wait(&s.bars[BAR_ACC], pa0);
+                pa0 ^= 1;
+            }
+            fence_after_sync();
+        };
+        const int TP = tl.TP;
+        const int nl = rc.row / TP, j = rc.row % TP;
+        // layer-0 reduction work items of this thread (index arithmetic hoisted out of the tile loop)
+        const int g0_o = t / TP, g0_j = t % TP;                 // G0[j][o] item: t < TP * SHP
+        int da_o[MAX_DA], da_n[MAX_DA];                         // dA[n][o] items: e = t + NE q < N * HID  (o-major: e = o * N + n)
+        float dA[MAX_DA];
+#pragma unroll
+        for (int q = 0; q < MAX_DA; ++q) {
+            const int e = t + NE * q;
+            da_o[q] = e / tl.NC, da_n[q] = e % tl.NC, dA[q] = 0.f;
+        }
+        float wacc[C][8 * NCH], bacc[C];  // this row's running sums of dy_c h_LH[k] and dy_c over the CTA's tiles
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            bacc[c] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8 * NCH; ++k) wacc[c][k] = 0.f;
+        }
+        if (myTiles > 0) stage_tile_inputs(a, decode_tile(tl, blockIdx.x), s.Cps, NE);
+        cp_async_commit();
+
+        for (int it = 0; it < myTiles; ++it) {
+            const TileIdx ti = decode_tile(tl, blockIdx.x + it * gridDim.x);
+            const int rot = (2 * it) % NBUF_BWD;
+            auto buf = [&](int role) { return s.tiles + (size_t)((role + rot) % NBUF_BWD) * TILE_BYTES; };
+            cp_async_wait<0>();
+            named_bar_sync(1, NE);  // staged Cp visible; every epilogue thread is done with the previous tile's staging panel / scratch
+            if (it + 1 < myTiles) stage_tile_inputs(a, decode_tile(tl, blockIdx.x + (it + 1) * gridDim.x), s.Cps + ((it + 1) & 1) * TP * SHP, NE);
+            cp_async_commit();
+            if (t == 0) LMR_TRACE(0, it * 20 + 0);
+            const float* Cps = s.Cps + (it & 1) * TP * SHP;
+            const bool active = nl < ti.nn && j < ti.np;
+            const float* An = s.As != nullptr ? s.As + (active ? nl : 0) * SHP : a.Avec + (size_t)(active ? nl : 0) * SHP;
+            const float* Cj = Cps + (active ? j : 0) * SHP;
+            // upstream gradient of this row (consumed after the last forward layer)
+            float g[C];
+            {
+                const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + (active ? nl : 0))) * C) * tl.P + ti.p0 + (active ? j : 0);
+#pragma unroll
+                for (int c = 0; c < C; ++c) g[c] = active ? __ldg(a.g_img + base + (size_t)c * tl.P) : 0.f;
+            }
+            if (a.want_affine) {  // beta[j][2pe] = sin/cos(coords . B) of the tile's pixels (consumed after the staging barrier below)
+                const int pe = nt.pe;
+                float cst[10];
+                affine_consts(a.aff, ti.d, cst);
+                for (int i = t; i < ti.np * pe; i += NE) {
+                    const int jj = i / pe, m = i % pe;
+                    const float2 c = transformed_coord(a, cst, ti.p0 + jj);
+                    float sn, cs;
+                    sincosf(c.x * a.B[m] + c.y * a.B[pe + m], &sn, &cs);
+                    s.beta[jj * 2 * pe + m] = sn;
+                    s.beta[jj * 2 * pe + pe + m] = cs;
+                }
+            }
+            auto tanh_op = [&](auto np, int, int, float2* x) {
+#pragma unroll
+                for (int p = 0; p < decltype(np)::value; ++p) x[p] = act_tanh2<FAST>(x[p]);
+            };
+            auto l0_op = [&](auto np, int, int, float2* x) {
+#pragma unroll
+                for (int p = 0; p < decltype(np)::value; ++p) {
+                    x[p] = act_tanh2<FAST>(x[p]);
+                    if (!active) x[p] = make_float2(0.f, 0.f);
+                }
+            };
+            float2 v[4 * NCH];
+            float* vf = reinterpret_cast<float*>(v);
+
+            // ---- forward recompute: h_1 (CUDA cores), h_2, h_3 (tensor cores) kept as tiles
+            load_layer0<NG>(An, Cj, rc.g, vf);
+            transform_store<NG>(v, buf(ROLE_H1), rc, &s.bars[BAR_K], l0_op);
+            if (t == 0) LMR_TRACE(0, it * 20 + 1);
+            int st = 0;
+#pragma unroll 1
+            for (int l = 1; l < LH - 1; ++l, ++st) {
+                wait_acc(st);
+                if (t == 0) LMR_TRACE(0, it * 20 + 2 + 2 * st);
+                load_acc<NG>(tm + TM_ACC + (uint32_t)(st & 1) * 64 + rc.lane_taddr, rc.g, vf);
+                transform_store<NG>(v, buf(ROLE_H1 + l), rc, &s.bars[BAR_K], tanh_op);
+                if (t == 0) LMR_TRACE(0, it * 20 + 3 + 2 * st);
+            }
+            // ---- last hidden layer + output layer (CUDA cores): h_4 in registers, y, dy = g (1 - y^2), dz_3 = (Wout^T dy)(1 - h_4^2) -> DA
+            {
+                wait_acc(st);
+                if (t == 0) LMR_TRACE(0, it * 20 + 2 + 2 * st);
+                load_acc<NG>(tm + TM_ACC + (uint32_t)(st & 1) * 64 + rc.lane_taddr, rc.g, vf);
+                float y[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) y[c] = 0.f;
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int ch = rc.g + NG * i;
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        if (ch < 6 || (ch == 6 && p < 2)) {
+                            v[4 * i + p] = act_tanh2<FAST>(v[4 * i + p]);
+#pragma unroll
+                            for (int c = 0; c < C; ++c) {
+                                const float2 w = *reinterpret_cast<const float2*>(s.Wout + c * HPAD + 8 * ch + 2 * p);
+                                y[c] = fmaf(v[4 * i + p].x, w.x, fmaf(v[4 * i + p].y, w.y, y[c]));
+                            }
+                        } else {
+                            v[4 * i + p] = make_float2(0.f, 0.f);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) s.scratch[(rc.row * NG + rc.g) * C + c] = y[c];
+                named_bar_sync(2 + rc.q, 32 * NG);  // the warps of this lane quarter exchange their partial dot products
+                float dy[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    float ys = 0.f;
+#pragma unroll
+                    for (int gg = 0; gg < NG; ++gg) ys += s.scratch[(rc.row * NG + gg) * C + c];
+                    const float yy = act_tanh<FAST>(s.bout[c] + ys);
+                    dy[c] = g[c] * (1.f - yy * yy);
+                    bacc[c] += dy[c];
+                }
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int ch = rc.g + NG * i;
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        float2 dh = make_float2(0.f, 0.f);
+                        const float2 h = v[4 * i + p];
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const float2 d2 = make_float2(dy[c], dy[c]);
+                            if (want_w) {
+                                const float2 wa = fma2(h, d2, make_float2(wacc[c][8 * i + 2 * p], wacc[c][8 * i + 2 * p + 1]));
+                                wacc[c][8 * i + 2 * p] = wa.x, wacc[c][8 * i + 2 * p + 1] = wa.y;
+                            }
+                            dh = fma2(*reinterpret_cast<const float2*>(s.Wout + c * HPAD + 8 * ch + 2 * p), d2, dh);
+                        }
+                        // dh (1 - h^2); padding columns: Wout == 0; constant-1 column: 1 - 1 == 0
+                        v[4 * i + p] = fma2(mul2(dh, mul2(h, h)), make_float2(-1.f, -1.f), dh);
+                    }
+                }
+                auto id_op = [&](auto, int, int, float2*) {};
+                transform_store<NG>(v, buf(ROLE_DA), rc, &s.bars[BAR_K], id_op);
+                ++st;
+                if (t == 0) LMR_TRACE(0, it * 20 + 1 + 2 * st);
+            }
+            // ---- layers 3, 2: dz_{l-1} = dh_l (1 - h_l^2) -> the other gradient tile   (h_l[50] == 1 zeroes the bias column)
+#pragma unroll 1
+            for (int l = LH - 1; l >= 2; --l, ++st) {
+                const uint8_t* Hl = buf(ROLE_H1 + l - 1);
+                uint8_t* dst = buf(((LH - l) & 1) ? ROLE_DB : ROLE_DA);
+                float2 hv[4 * NCH];  // h_l of this thread's features, fetched while the data-gradient MMAs run
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int ch = rc.g + NG * i;
+                    if (ch < 6) load_chunk2<4>(Hl, rc.row, ch, hv + 4 * i);
+                    else if (ch == 6) load_chunk2<2>(Hl, rc.row, ch, hv + 4 * i);
+                }
+                wait_acc(st);
+                if (t == 0) LMR_TRACE(0, it * 20 + 2 + 2 * st);
+                load_acc<NG>(tm + TM_ACC + (uint32_t)(st & 1) * 64 + rc.lane_taddr, rc.g, vf);
+                auto dz_op = [&](auto np, int i, int, float2* x) {
+#pragma unroll
+                    for (int p = 0; p < decltype(np)::value; ++p) x[p] = fma2(mul2(x[p], mul2(hv[4 * i + p], hv[4 * i + p])), make_float2(-1.f, -1.f), x[p]);
+                };
+                transform_store<NG>(v, dst, rc, &s.bars[BAR_K], dz_op);
+                if (t == 0) LMR_TRACE(0, it * 20 + 3 + 2 * st);
+            }
+            // ---- layer 1: dz_0 = dh_1 (1 - h_1^2) feeds only CUDA-core reductions: fp32 staging panel stage[o][row] in the free gradient tile
+            float* stage = reinterpret_cast<float*>(buf(ROLE_DB));
+            {
+                const uint8_t* H1 = buf(ROLE_H1);
+                float2 hv[4 * NCH];
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int ch = rc.g + NG * i;
+                    if (ch < 6) load_chunk2<4>(H1, rc.row, ch, hv + 4 * i);
+                    else if (ch == 6) load_chunk2<2>(H1, rc.row, ch, hv + 4 * i);
+                }
+                wait_acc(st);
+                if (t == 0) LMR_TRACE(0, it * 20 + 2 + 2 * st);
+                load_acc<NG>(tm + TM_ACC + (uint32_t)(st & 1) * 64 + rc.lane_taddr, rc.g, vf);
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int ch = rc.g + NG * i;
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        if (ch < 6 || (ch == 6 && p < 2)) {
+                            const float2 x = v[4 * i + p];
+                            const float2 d = fma2(mul2(x, mul2(hv[4 * i + p], hv[4 * i + p])), make_float2(-1.f, -1.f), x);
+                            const int o = 8 * ch + 2 * p;
+                            stage[o * 128 + rc.row] = d.x;
+                            stage[(o + 1) * 128 + rc.row] = d.y;
+                        }
+                    }
+                }
+            }
+            if (t == 0) LMR_TRACE(0, it * 20 + 14);
+            named_bar_sync(1, NE);  // dz_0 staged (and beta written)
+            if (t == 0) LMR_TRACE(0, it * 20 + 15);
+            // ---- layer 0: G0[j][o] = sum_n dz0, dA[n][o] += sum_j dz0   (CUDA cores; all loads of an item are independent)
+            float* G0s = s.scratch;
+            if (t < TP * SHP) {
+                float sum = 0.f;
+                if (g0_o < HID && g0_j < ti.np) {
+                    const float* zr = stage + g0_o * 128 + g0_j;
+                    float s0 = 0.f, s1 = 0.f;
+                    int n = 0;
+                    for (; n + 1 < ti.nn; n += 2) s0 += zr[n * TP], s1 += zr[(n + 1) * TP];
+                    if (n < ti.nn) s0 += zr[n * TP];
+                    sum = s0 + s1;
+                }
+                G0s[g0_j * SHP + g0_o] = sum;
+            }
+            if (want_w) {
+#pragma unroll
+                for (int q = 0; q < MAX_DA; ++q) {
+                    if (da_o[q] < HID && da_n[q] < ti.nn) {
+                        const float* zr = stage + da_o[q] * 128 + da_n[q] * TP;
+                        float sum = 0.f;
+#pragma unroll
+                        for (int jj = 0; jj < TP_CAP_TC; ++jj)
+                            if (jj < ti.np) sum += zr[jj];
+                        dA[q] += sum;
+                    }
+                }
+            }
+            named_bar_sync(1, NE);
+            if (t == 0) LMR_TRACE(0, it * 20 + 16);
+            if (want_w) {
+                float* gdst = a.G0 + ((size_t)ti.d * tl.P + ti.p0) * SHP;
+                for (int i = t; i < ti.np * SHP; i += NE) gdst[i] = G0s[i];
+            }
+            if (a.want_affine) {
+                const int pe = nt.pe;
+                for (int i = t; i < ti.np * pe; i += NE) {
+                    const int jj = i / pe, m = i % pe;
+                    const float4* ws_ = reinterpret_cast<const float4*>(a.W0cT + (size_t)m * SHP);
+                    const float4* wc_ = reinterpret_cast<const float4*>(a.W0cT + (size_t)(pe + m) * SHP);
+                    const float4* g4 = reinterpret_cast<const float4*>(G0s + jj * SHP);
+                    float ds = 0.f, dc = 0.f;
+                    for (int o4 = 0; o4 < SHP / 4; ++o4) {
+                        const float4 gg = g4[o4], a4 = __ldg(ws_ + o4), b4 = __ldg(wc_ + o4);
+                        ds += gg.x * a4.x + gg.y * a4.y + gg.z * a4.z + gg.w * a4.w;
+                        dc += gg.x * b4.x + gg.y * b4.y + gg.z * b4.z + gg.w * b4.w;
+                    }
+                    const float sn = s.beta[jj * 2 * pe + m], cs = s.beta[jj * 2 * pe + pe + m];
+                    s.beta[jj * 2 * pe + m] = ds * cs - dc * sn;  // d/dphi
+                }
+                named_bar_sync(1, NE);
+                if (t < 32) {  // TP <= 8: the first warp holds every contribution
+                    float w6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (t < ti.np) {
+                        float g0 = 0.f, g1 = 0.f;
+                        for (int m = 0; m < pe; ++m) {
+                            const float dphi = s.beta[t * 2 * pe + m];
+                            g0 = fmaf(dphi, a.B[m], g0);
+                            g1 = fmaf(dphi, a.B[pe + m], g1);
+                        }
+                        const int p = ti.p0 + t;
+                        const float tc0 = a.aff.tc ? a.aff.tc[0] : 0.f, tc1 = a.aff.tc ? a.aff.tc[1] : 0.f;
+                        const float r0 = a.coords[2 * p] - tc0, r1 = a.coords[2 * p + 1] - tc1;
+                        w6[0] = g0, w6[1] = g1, w6[2] = g0 * r0, w6[3] = g0 * r1, w6[4] = g1 * r0, w6[5] = g1 * r1;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) w6[q] = warp_sum(w6[q]);
+                    if (t == 0) {
+                        float* pdst = a.affpart + ((size_t)ti.d * tl.tilesP + ti.p0 / TP) * 6;
+                        for (int q = 0; q < 6; ++q) pdst[q] = w6[q];
+                    }
+                }
+            }
+        }
+        // ---- drain: wait for every MMA, then read the weight-gradient accumulators out of TMEM and write this CTA's partial
+        mbar_wait(&s.bars[BAR_DONE], 0);
+        fence_after_sync();
+        if (want_w) {
+            float* part = a.partials + (size_t)blockIdx.x * partial_size(nt, tl, SHP);
+            float* p_dW = part;
+            float* p_db = part + (size_t)(LH - 1) * HID * HID;
+            float* p_dWout = p_db + (size_t)(LH - 1) * SHP;
+            float* p_dA = p_dWout + (size_t)C * SHP + 4;
+            float* red = reinterpret_cast<float*>(s.tiles);  // [128][53] fp32 (any tile buffer: all MMAs are done)
+            constexpr int RS = 53;
+#pragma unroll 1
+            for (int l = 1; l < LH; ++l) {
+                // D[m][n]: m = dz feature (hi 0..63 | lo 64..127), n = h feature (hi 0..63 | lo 64..127); dW = D_hh + D_hl + D_lh
+                const uint32_t dw = tm + TM_DW + (uint32_t)(l - 1) * 128 + rc.lane_taddr;
+                float x[8 * NCH], y2[8 * NCH];
+                load_acc<NG>(dw, rc.g, x);
+                load_acc<NG>(dw + 64, rc.g, y2);
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int ch = rc.g + NG * i;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (ch < 6 || (ch == 6 && k < 4)) red[rc.row * RS + 8 * ch + k] = rc.row < 64 ? x[8 * i + k] + y2[8 * i + k] : x[8 * i + k];
+                }
+                named_bar_sync(1, NE);
+                for (int i = t; i < HID * (HID + 1); i += NE) {
+                    const int o = i / (HID + 1), k = i % (HID + 1);
+                    const float val = red[o * RS + k] + red[(64 + o) * RS + k];
+                    if (k < HID) p_dW[(size_t)(l - 1) * HID * HID + o * HID + k] = val;
+                    else p_db[(l - 1) * SHP + o] = val;  // column ONE_COL: sum_r dz_l[r][o] * 1
+                }
+                named_bar_sync(1, NE);
+            }
+            // output layer: column sums over the 128 rows of this thread's running products
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int ch = rc.g + NG * i;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (ch < 6 || (ch == 6 && k < 4)) red[(8 * ch + k) * 128 + rc.row] = wacc[c][8 * i + k];
+                }
+                if (rc.g == 0) red[52 * 128 + rc.row] = bacc[c];
+                named_bar_sync(1, NE);
+                if (t < 53) {
+                    const float* src = red + t * 128;
+                    float s0 = 0.f, s1 = 0.f;
+                    for (int r = 0; r < 128; r += 2) s0 += src[r], s1 += src[r + 1];
+                    if (t < HID) p_dWout[c * SHP + t] = s0 + s1;
+                    else if (t == 52) p_dWout[C * SHP + c] = s0 + s1;
+                }
+                named_bar_sync(1, NE);
+            }
+#pragma unroll
+            for (int q = 0; q < MAX_DA; ++q)
+                if (da_o[q] < HID) p_dA[da_n[q] * SHP + da_o[q]] = dA[q];
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == NE / 32) tmem_dealloc(tm, TM_COLS_BWD);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -643,7 +881,7 @@ __global__ void __launch_bounds__(NT, 1) inr_bwd_tc_kernel(Args a) {
 // ---------------------------------------------------------------------------------------------------------------
 static int check_tc(const Net& nt) {
     LMR_CHECK_ARG(nt.hid == HID, "tensor-core path: hidden width %d not supported (50)", nt.hid);
-    LMR_CHECK_ARG(nt.nl >= 3 && nt.nl <= 4, "tensor-core path: n_hidden %d out of range [3,4]", nt.nl);
+    LMR_CHECK_ARG(nt.nl == LH, "tensor-core path: n_hidden %d not supported (%d); use the fp32 path", nt.nl, LH);
     LMR_CHECK_ARG(nt.pe <= 64, "tensor-core path: pe_dim %d > 64", nt.pe);
     return 0;
 }
@@ -675,7 +913,7 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
     a.img = img;
     a.want_cp = 1;
     if (int rc = launch_prep<50>(a, st)) return rc;
-    TcSmem s(nullptr, nt, tl, 1);
+    TcSmem s(nullptr, nt, tl, 1, false, NG_F);
     const size_t smem = s.bytes + 1024;
     const int grid_x = tl.numTiles < 2 * num_sms() ? tl.numTiles : 2 * num_sms();
     static size_t cache[2][5] = {};
@@ -683,7 +921,7 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
 #define LMR_FWD_CASE(FASTV, CV)                                                                          \
     if (fast == FASTV && nt.C == CV) {                                                                   \
         if (int rc = set_smem(inr_fwd_tc_kernel<FASTV, CV>, smem, &cache[FASTV][CV])) return rc;        \
-        inr_fwd_tc_kernel<FASTV, CV><<<grid_x, NT, smem, st>>>(a);                                       \
+        inr_fwd_tc_kernel<FASTV, CV><<<grid_x, NT_F, smem, st>>>(a);                                       \
     }
     LMR_FWD_CASE(false, 1) LMR_FWD_CASE(false, 2) LMR_FWD_CASE(false, 3) LMR_FWD_CASE(false, 4)
     LMR_FWD_CASE(true, 1) LMR_FWD_CASE(true, 2) LMR_FWD_CASE(true, 3) LMR_FWD_CASE(true, 4)
@@ -718,7 +956,14 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     a.want_weights = g_params != nullptr, a.want_affine = want_aff;
     a.want_cp = 1;
     if (int rc = launch_prep<50>(a, st)) return rc;
-    TcSmem s(nullptr, nt, tl, nt.nl + 1);
+    static const bool tracing = getenv("LMR_TC_TRACE") != nullptr;
+    static long long* trace_dev = nullptr;
+    if (tracing) {
+        if (trace_dev == nullptr) cudaMalloc(&trace_dev, 1024 * sizeof(long long));
+        cudaMemsetAsync(trace_dev, 0, 1024 * sizeof(long long), st);
+        a.trace = trace_dev;
+    }
+    TcSmem s(nullptr, nt, tl, NBUF_BWD, want_aff, NG_B);
     const size_t smem = s.bytes + 1024;
     LMR_CHECK_ARG(smem <= 227 * 1024, "inr_backward (tensor-core path): needs %zu bytes of shared memory (> 227 KB)", smem);
     static size_t cache[2][5] = {};
@@ -726,12 +971,25 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
 #define LMR_BWD_CASE(FASTV, CV)                                                                          \
     if (fast == FASTV && nt.C == CV) {                                                                   \
         if (int rc = set_smem(inr_bwd_tc_kernel<FASTV, CV>, smem, &cache[FASTV][CV])) return rc;        \
-        inr_bwd_tc_kernel<FASTV, CV><<<wl.gridMain, NT, smem, st>>>(a);                                  \
+        inr_bwd_tc_kernel<FASTV, CV><<<wl.gridMain, NT_B, smem, st>>>(a);                                  \
     }
     LMR_BWD_CASE(false, 1) LMR_BWD_CASE(false, 2) LMR_BWD_CASE(false, 3) LMR_BWD_CASE(false, 4)
     LMR_BWD_CASE(true, 1) LMR_BWD_CASE(true, 2) LMR_BWD_CASE(true, 3) LMR_BWD_CASE(true, 4)
 #undef LMR_BWD_CASE
     LMR_LAUNCH_OK();
+    if (tracing) {  // debug only: synchronises and prints CTA 0's pipeline time line (cycles relative to its first stamp)
+        static long long h[1024];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        const long long t0 = h[0];
+        for (int it = 0; it < 3; ++it) {
+            fprintf(stderr, "[trace] tile %d  E:", it);
+            for (int e = 0; e < 17; ++e) fprintf(stderr, " %lld", h[it * 20 + e] ? h[it * 20 + e] - t0 : -1);
+            fprintf(stderr, "\n[trace] tile %d  M:", it);
+            for (int e = 0; e < 30; ++e) fprintf(stderr, " %lld%s", h[512 + it * 30 + e] ? h[512 + it * 30 + e] - t0 : -1, e % 5 == 4 ? " |" : "");
+            fprintf(stderr, "\n");
+        }
+    }
     if (a.want_weights) {
         float* l0part = reinterpret_cast<float*>(static_cast<char*>(ws) + wl.l0part);
         const size_t smem0 = (size_t)L0_CHUNK * (SHP + 2 * nt.pe) * sizeof(float);
