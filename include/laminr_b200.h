@@ -151,6 +151,25 @@ int lmr_simclr_bwd(const float* img, const float* mask, const float* K, const fl
                    int C, int HW, float pmin, float pmax, float* g_img, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Fused learn-stage objective, forward AND backward in ONE launch -- replaces, for a simulated template neuron, the chain
+ * img_transf -> SingleNeuronModel -> apply_mask -> SimCLROnGrid.reg_term -> loss -> autograd back to the INR output
+ * (laminr/inv_temp_learn_match.py:187-204; same maths as lmr_constrain_* + lmr_simresp_* + lmr_simclr_* above):
+ *     z = constrain(x);  act_n = (elu(max_f <sum_c z_n, w_f>) + 1)/2 + act_eps;  reg = simclr(mask(z))
+ *     loss = -mean_n(act_n / mei_act) + g_reg[0] * reg        (g_reg = -reg_scale, a device scalar)
+ *     g_x  = d loss / d x
+ * x, z, g_x: [N, C, HW];  bank: [F, HW] filters of the template neuron;  stats [N,2], rmax [N], argmax [N], Kmat [N,N] nullable.
+ * The workspace must be zero-initialised once before its first use (it holds the software grid-barrier state) and must not be shared by
+ * launches that may run concurrently.  lmr_learn_objective_workspace_bytes returns 0 when the configuration does not fit the fused
+ * kernel (use the unfused entry points then).
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t lmr_learn_objective_workspace_bytes(int N, int C, int HW, int F);
+int lmr_learn_objective(int mode, const float* x, int N, int C, int HW, float target, float mean, int has_min, float pmin, int has_max,
+                        float pmax, float eps_con, const float* bank, int F, float act_eps, float mei_act, const float* mask,
+                        const float* pos, const float* neg, float temperature, float eps_clr, const float* g_reg, float* z, float* stats,
+                        float* act, float* rmax, int* argmax, float* reg, float* Kmat, float* loss, float* g_x, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Adam -- torch.optim.Adam(lr, betas, eps) single-tensor update (used on template.func / coordinate_transform
  * parameters, inv_temp_learn_match.py:162,335).  `step` is a device int32 holding the number of steps already
  * taken; it is incremented by the call (graph-capturable).  One flat tensor per call.

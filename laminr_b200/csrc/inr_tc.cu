@@ -149,7 +149,7 @@ __device__ __forceinline__ void load_chunk2(const uint8_t* tile, int r, int c, f
 struct TcSmem {
     uint8_t* tiles;   // ntiles x TILE_BYTES
     uint8_t* wt;      // (LH-1) x WT_BYTES
-    float *Cps, *beta, *Wout, *bout, *scratch, *As;  // Cps: 2 x [TP][SHP] staged layer-0 coordinate parts; scratch: y partials [128][NG][C] / G0s [TP][SHP]
+    float *Cps, *beta, *Wout, *bout, *scratch, *As;  // Cps: 2 x [TP][56] staged layer-0 coordinate parts; scratch: y partials [128][NG][C] / G0s [TP][SHP]
     uint64_t* bars;
     uint32_t* tmem;
     size_t bytes;
@@ -162,7 +162,7 @@ struct TcSmem {
         };
         tiles = take((size_t)ntiles * TILE_BYTES);
         wt = take((size_t)(LH - 1) * WT_BYTES);
-        Cps = reinterpret_cast<float*>(take((size_t)2 * tl.TP * SHP * 4));
+        Cps = reinterpret_cast<float*>(take((size_t)2 * tl.TP * 56 * 4));
         beta = reinterpret_cast<float*>(take(want_beta ? (size_t)tl.TP * 2 * nt.pe * 4 : 0));
         Wout = reinterpret_cast<float*>(take((size_t)nt.C * HPAD * 4));
         bout = reinterpret_cast<float*>(take(16));
@@ -171,7 +171,7 @@ struct TcSmem {
         bars = reinterpret_cast<uint64_t*>(take(NBARS * 8));
         tmem = reinterpret_cast<uint32_t*>(take(16));
         // A[n] rows staged in shared memory when they fit (L1 is almost entirely carved out for shared memory here)
-        As = tl.NC <= 24 ? reinterpret_cast<float*>(take((size_t)tl.NC * SHP * 4)) : nullptr;
+        As = tl.NC <= 24 ? reinterpret_cast<float*>(take((size_t)tl.NC * 56 * 4)) : nullptr;
         bytes = p - base;
     }
 };
@@ -207,16 +207,27 @@ __device__ inline void load_weight_tiles(const Args& a, TcSmem& s) {
 // ---------------------------------------------------------------------------------------------------------------
 // MMA issue (ONE thread)
 // ---------------------------------------------------------------------------------------------------------------
-// k-step kc (16 features) of D(tmem_d)[128 x 64] (+)= A . B^T, split-bf16: hi*hi + lo*hi + hi*lo.  A K-major [128 x 64]; B a [64 x 64]
-// weight tile, K-major (b_transposed = 0: forward) or read MN-major (b_transposed = 1: data gradient).
-__device__ __forceinline__ void issue_kstep(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, int kc, int b_transposed) {
-    const uint32_t idesc = instr_desc(FMT_BF16, 128, HPAD, 0, b_transposed);
-    const uint64_t ah = smem_desc(a_addr + (uint32_t)kc * (2 * 128 * 16), 128 * 16, 128);
-    const uint64_t bh = b_transposed ? smem_desc(w_addr + (uint32_t)kc * 256, 128, HPAD * 16) : smem_desc(w_addr + (uint32_t)kc * (2 * HPAD * 16), HPAD * 16, 128);
-    const uint64_t a_lo = TILE_HALF >> 4, b_lo = WT_HALF >> 4;  // the start-address field is in 16-byte units
-    mma_f16(tmem_d, ah, bh, idesc, kc > 0);
-    mma_f16(tmem_d, ah + a_lo, bh, idesc, 1);
-    mma_f16(tmem_d, ah, bh + b_lo, idesc, 1);
+// Descriptors of one stage D[128 x 64] = A . B^T with split-bf16 operands.  A K-major [128 x 64]; B a [64 x 64] weight tile, K-major
+// (b_transposed = 0: forward) or read MN-major (b_transposed = 1: data gradient).
+struct StageDesc {
+    uint64_t ah, bh;    // hi halves, k-step 0
+    uint64_t b_step;    // per k-step advance of the B descriptor (16-byte units)
+    uint32_t idesc;
+};
+__device__ __forceinline__ StageDesc make_stage(uint32_t a_addr, uint32_t w_addr, int b_transposed) {
+    StageDesc d;
+    d.idesc = instr_desc(FMT_BF16, 128, HPAD, 0, b_transposed);
+    d.ah = smem_desc(a_addr, 128 * 16, 128);
+    d.bh = b_transposed ? smem_desc(w_addr, 128, HPAD * 16) : smem_desc(w_addr, HPAD * 16, 128);
+    d.b_step = (b_transposed ? 256 : 2 * HPAD * 16) >> 4;
+    return d;
+}
+// k-step kc (16 features): hi*hi + lo*hi + hi*lo
+__device__ __forceinline__ void issue_kstep(uint32_t tmem_d, const StageDesc& d, int kc) {
+    const uint64_t ah = d.ah + (uint64_t)kc * ((2 * 128 * 16) >> 4), bh = d.bh + (uint64_t)kc * d.b_step;
+    mma_f16(tmem_d, ah, bh, d.idesc, kc > 0);
+    mma_f16(tmem_d, ah + (TILE_HALF >> 4), bh, d.idesc, 1);
+    mma_f16(tmem_d, ah, bh + (WT_HALF >> 4), d.idesc, 1);
 }
 
 // D(tmem_d)[128 x 128] (+)= [X_hi | X_lo]^T . [Y_hi | Y_lo] over the 128 rows: both [128 x 64](hi, lo) tiles read MN-major, 8 MMAs of 16 rows
@@ -233,10 +244,10 @@ __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t x_addr, ui
 // ---------------------------------------------------------------------------------------------------------------
 // epilogue building blocks.  Epilogue thread = (row, column group g of NG): warps q, q+4, q+8, .. own TMEM lanes 32q..32q+31; group g
 // owns the 16-byte chunks (8 features) {g, g+NG, g+2NG, ..} < 8 of the row, so that the MMA k-chunks (16 features = chunks 2kc, 2kc+1)
-// complete progressively.  Chunk 6 has 4 live features (48..51), chunk 7 none (always written as zeros).
+// complete progressively.  Chunk 6 has 4 live features (48..51): its other 4 are exact zeros by construction (zero weight rows /
+// zero-padded layer-0 tables), so it is processed like any other chunk; chunk 7 has none and is written as zeros.
 // ---------------------------------------------------------------------------------------------------------------
-template <int NP>
-using np_t = std::integral_constant<int, NP>;
+constexpr int SHS = 56;  // row stride (floats) of the layer-0 tables in shared memory: SHP = 52 live columns + 4 zeros
 
 __device__ __forceinline__ void arrive_chunk(uint64_t* bar, int lane) {
     fence_proxy_async();  // this thread's generic-proxy tile writes -> visible to the tensor core's async-proxy reads
@@ -257,14 +268,13 @@ __device__ __forceinline__ RowCtx row_ctx() {
     return r;
 }
 
-// this thread's accumulator columns: v[8 i .. 8 i + 7] = features of chunk g + NG i
+// this thread's accumulator columns: v[8 i .. 8 i + 7] = features of chunk g + NG i  (chunk 7 is never read)
 template <int NG>
 __device__ __forceinline__ void load_acc(uint32_t acc, int g, float* v) {
 #pragma unroll
     for (int i = 0; i < 8 / NG; ++i) {
         const int c = g + NG * i;
-        if (c < 6) tmem_ld8(acc + 8 * c, v + 8 * i);
-        else if (c == 6) tmem_ld4(acc + 48, v + 8 * i);
+        if (c < 7) tmem_ld8(acc + 8 * c, v + 8 * i);
     }
     tmem_ld_wait();
     fence_before_sync();  // orders these loads before the MMAs that overwrite the accumulator after a later barrier
@@ -276,29 +286,52 @@ __device__ __forceinline__ void load_layer0(const float* An, const float* Cj, in
 #pragma unroll
     for (int i = 0; i < 8 / NG; ++i) {
         const int c = g + NG * i;
-        if (c < 7) {  // SHP = 52: chunk 6 holds features 48..51
-            const float4 x = *reinterpret_cast<const float4*>(An + 8 * c), y = *reinterpret_cast<const float4*>(Cj + 8 * c);
-            v[8 * i] = x.x + y.x, v[8 * i + 1] = x.y + y.y, v[8 * i + 2] = x.z + y.z, v[8 * i + 3] = x.w + y.w;
-        }
-        if (c < 6) {
-            const float4 x = *reinterpret_cast<const float4*>(An + 8 * c + 4), y = *reinterpret_cast<const float4*>(Cj + 8 * c + 4);
-            v[8 * i + 4] = x.x + y.x, v[8 * i + 5] = x.y + y.y, v[8 * i + 6] = x.z + y.z, v[8 * i + 7] = x.w + y.w;
+        if (c < 7) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float4 x = *reinterpret_cast<const float4*>(An + 8 * c + 4 * h), y = *reinterpret_cast<const float4*>(Cj + 8 * c + 4 * h);
+                v[8 * i + 4 * h] = x.x + y.x, v[8 * i + 4 * h + 1] = x.y + y.y, v[8 * i + 4 * h + 2] = x.z + y.z, v[8 * i + 4 * h + 3] = x.w + y.w;
+            }
         }
     }
 }
 
-// Applies op(np, i, chunk, vals) to every chunk of this thread, stores it as split-bf16 into `dst` and signals its k-chunk.
-template <int NG, typename Op>
-__device__ __forceinline__ void transform_store(float2* v, uint8_t* dst, const RowCtx& rc, uint64_t* kbar, Op&& op) {
+// tanh in two phases so that the MUFU work of the next chunk is issued before the stores / barrier arrive of the current one
+template <bool FAST>
+__device__ __forceinline__ void tanh_begin(float2* x) {  // 4 pairs
+    if (!FAST) {
 #pragma unroll
-    for (int i = 0; i < 8 / NG; ++i) {
+        for (int p = 0; p < 4; ++p) {
+            const float2 t = mul2(x[p], make_float2(2.885390081777927f, 2.885390081777927f));
+            x[p] = add2(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.f, 1.f));
+        }
+    }
+}
+template <bool FAST>
+__device__ __forceinline__ void tanh_end(float2* x) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        if (FAST) x[p] = make_float2(tanh_mufu(x[p].x), tanh_mufu(x[p].y));
+        else x[p] = fma2(make_float2(-2.f, -2.f), make_float2(rcp_approx(x[p].x), rcp_approx(x[p].y)), make_float2(1.f, 1.f));
+    }
+}
+
+// v -> tanh(v) (zeroed for inactive rows), stored as split-bf16 chunks into `dst`, k-chunks signalled as they complete
+template <int NG, bool FAST>
+__device__ __forceinline__ void tanh_store(float2* v, uint8_t* dst, const RowCtx& rc, uint64_t* kbar, bool active) {
+    constexpr int NCH = 8 / NG;
+    if (rc.g < 7) tanh_begin<FAST>(v);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
         const int c = rc.g + NG * i;
-        if (c < 6) {
-            op(np_t<4>{}, i, c, v + 4 * i);
+        if (i + 1 < NCH && c + NG < 7) tanh_begin<FAST>(v + 4 * (i + 1));
+        if (c < 7) {
+            tanh_end<FAST>(v + 4 * i);
+            if (!active) {
+#pragma unroll
+                for (int p = 0; p < 4; ++p) v[4 * i + p] = make_float2(0.f, 0.f);
+            }
             store_chunk2<4>(dst, rc.row, c, v + 4 * i);
-        } else if (c == 6) {
-            op(np_t<2>{}, i, c, v + 4 * i);
-            store_chunk2<2>(dst, rc.row, c, v + 4 * i);
         } else {
             store_chunk_zero(dst, rc.row, c);
         }
@@ -306,10 +339,25 @@ __device__ __forceinline__ void transform_store(float2* v, uint8_t* dst, const R
     }
 }
 
-// cp.async of the tile's layer-0 coordinate parts Cp[j][0..SHP) (contiguous, 16-byte aligned rows) into a staging slot
+// plain store of already final values
+template <int NG>
+__device__ __forceinline__ void plain_store(float2* v, uint8_t* dst, const RowCtx& rc, uint64_t* kbar) {
+#pragma unroll
+    for (int i = 0; i < 8 / NG; ++i) {
+        const int c = rc.g + NG * i;
+        if (c < 7) store_chunk2<4>(dst, rc.row, c, v + 4 * i);
+        else store_chunk_zero(dst, rc.row, c);
+        arrive_chunk(kbar + (c >> 1), rc.lane);
+    }
+}
+
+// cp.async of the tile's layer-0 coordinate parts Cp[j][0..SHP) (contiguous, 16-byte aligned rows) into a staging slot of row stride SHS
 __device__ __forceinline__ void stage_tile_inputs(const Args& a, const TileIdx& ti, float* cps_slot, int ne) {
     const float* src = a.Cpg + ((size_t)ti.d * a.tl.P + ti.p0) * SHP;
-    for (int i = threadIdx.x; i < ti.np * (SHP / 4); i += ne) cp_async16(cps_slot + 4 * i, src + 4 * i);
+    for (int i = threadIdx.x; i < ti.np * (SHP / 4); i += ne) {
+        const int jj = i / (SHP / 4), k4 = i % (SHP / 4);
+        cp_async16(cps_slot + jj * SHS + 4 * k4, src + jj * SHP + 4 * k4);
+    }
 }
 
 __device__ __forceinline__ void init_barriers(uint64_t* bars, int warps_per_kchunk) {
@@ -317,6 +365,16 @@ __device__ __forceinline__ void init_barriers(uint64_t* bars, int warps_per_kchu
     for (int k = 0; k < 4; ++k) mbar_init(&bars[BAR_K + k], warps_per_kchunk);
     mbar_init(&bars[BAR_ACC], 1), mbar_init(&bars[BAR_ACC + 1], 1), mbar_init(&bars[BAR_DONE], 1);
     mbar_fence_init();
+}
+
+// zero-padded shared-memory copies of the layer-0 tables
+__device__ __forceinline__ void init_layer0_tables(const Args& a, TcSmem& s, bool load_as, int nthreads) {
+    for (int i = threadIdx.x; i < 2 * a.tl.TP * SHS; i += nthreads) s.Cps[i] = 0.f;
+    if (s.As != nullptr)
+        for (int i = threadIdx.x; i < a.tl.NC * SHS; i += nthreads) {
+            const int n = i / SHS, k = i % SHS;
+            s.As[i] = (load_as && k < SHP) ? a.Avec[(size_t)n * SHP + k] : 0.f;
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -332,9 +390,9 @@ __global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
     const Tiling& tl = a.tl;
     TcSmem s(smem_raw, nt, tl, 1, false, NG);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const bool multi_chunk = tl.nChunks > 1;
     load_weight_tiles(a, s);
-    if (s.As != nullptr && tl.nChunks == 1)
-        for (int i = t; i < tl.NC * SHP; i += NT_F) s.As[i] = a.Avec[i];
+    init_layer0_tables(a, s, !multi_chunk, NT_F);
     if (warp == NE / 32) tmem_alloc(s.tmem, TM_COLS_FWD);
     if (t == 0) init_barriers(s.bars, 8);
     fence_proxy_async();
@@ -353,11 +411,12 @@ __global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
 #pragma unroll 1
                 for (int st = 0; st < LH - 1; ++st) {
                     const uint32_t acc = tm + TM_ACC + (uint32_t)(st & 1) * 64;
+                    const StageDesc sd = make_stage(t_addr, w_addr + (uint32_t)st * WT_BYTES, 0);
 #pragma unroll
                     for (int kc = 0; kc < 4; ++kc) {
                         mbar_wait(&s.bars[BAR_K + kc], pk);
                         fence_after_sync();
-                        issue_kstep(acc, t_addr, w_addr + (uint32_t)st * WT_BYTES, kc, 0);
+                        issue_kstep(acc, sd, kc);
                     }
                     pk ^= 1;
                     mma_commit(&s.bars[BAR_ACC + (st & 1)]);
@@ -367,7 +426,6 @@ __global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
     } else {  // ---- epilogue threads
         const RowCtx rc = row_ctx();
         uint32_t pa0 = 0, pa1 = 0;
-        const bool multi_chunk = tl.nChunks > 1;
         if (myTiles > 0) stage_tile_inputs(a, decode_tile(tl, blockIdx.x), s.Cps, NE);
         cp_async_commit();
         const int nl = rc.row / tl.TP, j = rc.row % tl.TP;
@@ -375,28 +433,26 @@ __global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
             const TileIdx ti = decode_tile(tl, blockIdx.x + it * gridDim.x);
             cp_async_wait<0>();
             named_bar_sync(1, NE);  // staged Cp visible; every epilogue thread is done with the previous tile's scratch
-            if (it + 1 < myTiles) stage_tile_inputs(a, decode_tile(tl, blockIdx.x + (it + 1) * gridDim.x), s.Cps + ((it + 1) & 1) * tl.TP * SHP, NE);
+            if (it + 1 < myTiles) stage_tile_inputs(a, decode_tile(tl, blockIdx.x + (it + 1) * gridDim.x), s.Cps + ((it + 1) & 1) * tl.TP * SHS, NE);
             cp_async_commit();
-            const float* Cps = s.Cps + (it & 1) * tl.TP * SHP;
+            const float* Cps = s.Cps + (it & 1) * tl.TP * SHS;
             const bool active = nl < ti.nn && j < ti.np;
-            const float* An = (s.As != nullptr && !multi_chunk) ? s.As + (active ? nl : 0) * SHP : a.Avec + (size_t)(ti.n0 + (active ? nl : 0)) * SHP;
-            const float* Cj = Cps + (active ? j : 0) * SHP;
-            auto tanh_op = [&](auto np, int, int, float2* x) {
-#pragma unroll
-                for (int p = 0; p < decltype(np)::value; ++p) x[p] = act_tanh2<FAST>(x[p]);
-            };
-            auto l0_op = [&](auto np, int, int, float2* x) {
-#pragma unroll
-                for (int p = 0; p < decltype(np)::value; ++p) {
-                    x[p] = act_tanh2<FAST>(x[p]);
-                    if (!active) x[p] = make_float2(0.f, 0.f);  // inactive rows: h_1 == 0 (bias feature too) => every later z == 0 => tanh == 0
-                }
-            };
             float2 v[4 * NCH];
             float* vf = reinterpret_cast<float*>(v);
             // h_1 (the tile buffer is free: the accumulator of the previous tile's last layer was waited for)
-            load_layer0<NG>(An, Cj, rc.g, vf);
-            transform_store<NG>(v, T, rc, &s.bars[BAR_K], l0_op);
+            if (s.As != nullptr && !multi_chunk) {
+                load_layer0<NG>(s.As + (active ? nl : 0) * SHS, Cps + (active ? j : 0) * SHS, rc.g, vf);
+            } else {  // A[n] rows from global memory (row stride SHP: the 4 padding features of chunk 6 come out as garbage x 0 weights)
+                const float* An = a.Avec + (size_t)(ti.n0 + (active ? nl : 0)) * SHP;
+                const float* Cj = Cps + (active ? j : 0) * SHS;
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int c = rc.g + NG * i;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) vf[8 * i + k] = (8 * c + k < SHP) ? An[8 * c + k] + Cj[8 * c + k] : 0.f;
+                }
+            }
+            tanh_store<NG, FAST>(v, T, rc, &s.bars[BAR_K], active);
 #pragma unroll 1
             for (int st = 0; st < LH - 1; ++st) {
                 const uint32_t acc = tm + TM_ACC + (uint32_t)(st & 1) * 64 + rc.lane_taddr;
@@ -409,8 +465,8 @@ __global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
                 }
                 fence_after_sync();
                 load_acc<NG>(acc, rc.g, vf);
-                if (st < LH - 2) {  // h_{st+2} in place (every MMA that read the old tile has completed)
-                    transform_store<NG>(v, T, rc, &s.bars[BAR_K], tanh_op);
+                if (st < LH - 2) {  // h_{st+2} in place (every MMA that read the old tile has completed); inactive rows: z == 0 => tanh == 0
+                    tanh_store<NG, FAST>(v, T, rc, &s.bars[BAR_K], true);
                 } else {  // last hidden layer: h_LH stays in registers; output layer on CUDA cores
                     float y[C];
 #pragma unroll
@@ -418,9 +474,9 @@ __global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
 #pragma unroll
                     for (int i = 0; i < NCH; ++i) {
                         const int ch = rc.g + NG * i;
+                        if (ch < 7) {
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            if (ch < 6 || (ch == 6 && p < 2)) {
+                            for (int p = 0; p < 4; ++p) {
                                 const float2 h = act_tanh2<FAST>(v[4 * i + p]);
 #pragma unroll
                                 for (int c = 0; c < C; ++c) {
@@ -432,7 +488,7 @@ __global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
                     }
                     if (rc.g != 0) {
 #pragma unroll
-                        for (int c = 0; c < C; ++c) s.scratch[(rc.row * NG + rc.g) * C + c] = y[c];
+                        for (int c = 0; c < C; ++c) s.scratch[(rc.g * 128 + rc.row) * C + c] = y[c];
                     }
                     named_bar_sync(2 + rc.q, 32 * NG);  // the warps of this lane quarter
                     if (rc.g == 0 && active) {
@@ -441,7 +497,7 @@ __global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
                         for (int c = 0; c < C; ++c) {
                             float yy = y[c];
 #pragma unroll
-                            for (int gg = 1; gg < NG; ++gg) yy += s.scratch[(rc.row * NG + gg) * C + c];
+                            for (int gg = 1; gg < NG; ++gg) yy += s.scratch[(gg * 128 + rc.row) * C + c];
                             a.img[base + (size_t)c * tl.P] = act_tanh<FAST>(s.bout[c] + yy);
                         }
                     }
@@ -461,6 +517,7 @@ __global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
 constexpr int ROLE_H1 = 0, ROLE_DA = 3, ROLE_DB = 4;
 constexpr int NG_B = 4, NE_B = 128 * NG_B, NT_B = NE_B + 32;
 constexpr int MAX_DA = 4;   // dA[n][o] accumulators per epilogue thread: N * 50 <= 4 * 512  (N <= 40)
+constexpr int STG = 53;     // row stride (floats) of the fp32 staging panel stage[row][o] of dz_0 (odd: conflict-free both ways)
 
 template <bool FAST, int C>
 __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
@@ -472,8 +529,7 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const bool want_w = a.want_weights != 0;
     load_weight_tiles(a, s);
-    if (s.As != nullptr)
-        for (int i = t; i < tl.NC * SHP; i += NT_B) s.As[i] = a.Avec[i];
+    init_layer0_tables(a, s, true, NT_B);
     if (warp == NE / 32) tmem_alloc(s.tmem, TM_COLS_BWD);
     if (t == 0) init_barriers(s.bars, 8);
     fence_proxy_async();
@@ -495,13 +551,13 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
 #pragma unroll 1
                 for (int l = 1; l < LH; ++l, ++st) {
                     const uint32_t acc = tm + TM_ACC + (uint32_t)(st & 1) * 64;
-                    const uint32_t hb = buf(ROLE_H1 + l - 1);
+                    const StageDesc sd = make_stage(buf(ROLE_H1 + l - 1), w_addr + (uint32_t)(l - 1) * WT_BYTES, 0);
 #pragma unroll
                     for (int kc = 0; kc < 4; ++kc) {
                         mbar_wait(&s.bars[BAR_K + kc], pk);
                         fence_after_sync();
                         LMR_TRACE(1, (it * 6 + st) * 5 + kc);
-                        issue_kstep(acc, hb, w_addr + (uint32_t)(l - 1) * WT_BYTES, kc, 0);
+                        issue_kstep(acc, sd, kc);
                     }
                     pk ^= 1;
                     mma_commit(&s.bars[BAR_ACC + (st & 1)]);
@@ -512,12 +568,13 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
                 for (int l = LH - 1; l >= 1; --l, ++st) {
                     const uint32_t acc = tm + TM_ACC + (uint32_t)(st & 1) * 64;
                     const uint32_t dz = buf(((LH - 1 - l) & 1) ? ROLE_DB : ROLE_DA);
+                    const StageDesc sd = make_stage(dz, w_addr + (uint32_t)(l - 1) * WT_BYTES, 1);
 #pragma unroll
                     for (int kc = 0; kc < 4; ++kc) {
                         mbar_wait(&s.bars[BAR_K + kc], pk);
                         fence_after_sync();
                         LMR_TRACE(1, (it * 6 + st) * 5 + kc);
-                        issue_kstep(acc, dz, w_addr + (uint32_t)(l - 1) * WT_BYTES, kc, 1);
+                        issue_kstep(acc, sd, kc);
                     }
                     pk ^= 1;
                     mma_commit(&s.bars[BAR_ACC + (st & 1)]);
@@ -542,15 +599,11 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
         };
         const int TP = tl.TP;
         const int nl = rc.row / TP, j = rc.row % TP;
-        // layer-0 reduction work items of this thread (index arithmetic hoisted out of the tile loop)
-        const int g0_o = t / TP, g0_j = t % TP;                 // G0[j][o] item: t < TP * SHP
-        int da_o[MAX_DA], da_n[MAX_DA];                         // dA[n][o] items: e = t + NE q < N * HID  (o-major: e = o * N + n)
+        // layer-0 reduction work items of this thread: G0[jj][o] (t < TP * SHP, o fastest); dA[n][o] entries e = t + NE q = n * HID + o
+        const int g0_j = t / SHP, g0_o = t % SHP;
         float dA[MAX_DA];
 #pragma unroll
-        for (int q = 0; q < MAX_DA; ++q) {
-            const int e = t + NE * q;
-            da_o[q] = e / tl.NC, da_n[q] = e % tl.NC, dA[q] = 0.f;
-        }
+        for (int q = 0; q < MAX_DA; ++q) dA[q] = 0.f;
         float wacc[C][8 * NCH], bacc[C];  // this row's running sums of dy_c h_LH[k] and dy_c over the CTA's tiles
 #pragma unroll
         for (int c = 0; c < C; ++c) {
@@ -567,13 +620,11 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
             auto buf = [&](int role) { return s.tiles + (size_t)((role + rot) % NBUF_BWD) * TILE_BYTES; };
             cp_async_wait<0>();
             named_bar_sync(1, NE);  // staged Cp visible; every epilogue thread is done with the previous tile's staging panel / scratch
-            if (it + 1 < myTiles) stage_tile_inputs(a, decode_tile(tl, blockIdx.x + (it + 1) * gridDim.x), s.Cps + ((it + 1) & 1) * TP * SHP, NE);
+            if (it + 1 < myTiles) stage_tile_inputs(a, decode_tile(tl, blockIdx.x + (it + 1) * gridDim.x), s.Cps + ((it + 1) & 1) * TP * SHS, NE);
             cp_async_commit();
             if (t == 0) LMR_TRACE(0, it * 20 + 0);
-            const float* Cps = s.Cps + (it & 1) * TP * SHP;
+            const float* Cps = s.Cps + (it & 1) * TP * SHS;
             const bool active = nl < ti.nn && j < ti.np;
-            const float* An = s.As != nullptr ? s.As + (active ? nl : 0) * SHP : a.Avec + (size_t)(active ? nl : 0) * SHP;
-            const float* Cj = Cps + (active ? j : 0) * SHP;
             // upstream gradient of this row (consumed after the last forward layer)
             float g[C];
             {
@@ -594,23 +645,23 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
                     s.beta[jj * 2 * pe + pe + m] = cs;
                 }
             }
-            auto tanh_op = [&](auto np, int, int, float2* x) {
-#pragma unroll
-                for (int p = 0; p < decltype(np)::value; ++p) x[p] = act_tanh2<FAST>(x[p]);
-            };
-            auto l0_op = [&](auto np, int, int, float2* x) {
-#pragma unroll
-                for (int p = 0; p < decltype(np)::value; ++p) {
-                    x[p] = act_tanh2<FAST>(x[p]);
-                    if (!active) x[p] = make_float2(0.f, 0.f);
-                }
-            };
             float2 v[4 * NCH];
             float* vf = reinterpret_cast<float*>(v);
 
             // ---- forward recompute: h_1 (CUDA cores), h_2, h_3 (tensor cores) kept as tiles
-            load_layer0<NG>(An, Cj, rc.g, vf);
-            transform_store<NG>(v, buf(ROLE_H1), rc, &s.bars[BAR_K], l0_op);
+            if (s.As != nullptr) {
+                load_layer0<NG>(s.As + (active ? nl : 0) * SHS, Cps + (active ? j : 0) * SHS, rc.g, vf);
+            } else {
+                const float* An = a.Avec + (size_t)(active ? nl : 0) * SHP;
+                const float* Cj = Cps + (active ? j : 0) * SHS;
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int c = rc.g + NG * i;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) vf[8 * i + k] = (8 * c + k < SHP) ? An[8 * c + k] + Cj[8 * c + k] : 0.f;
+                }
+            }
+            tanh_store<NG, FAST>(v, buf(ROLE_H1), rc, &s.bars[BAR_K], active);
             if (t == 0) LMR_TRACE(0, it * 20 + 1);
             int st = 0;
 #pragma unroll 1
@@ -618,7 +669,7 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
                 wait_acc(st);
                 if (t == 0) LMR_TRACE(0, it * 20 + 2 + 2 * st);
                 load_acc<NG>(tm + TM_ACC + (uint32_t)(st & 1) * 64 + rc.lane_taddr, rc.g, vf);
-                transform_store<NG>(v, buf(ROLE_H1 + l), rc, &s.bars[BAR_K], tanh_op);
+                tanh_store<NG, FAST>(v, buf(ROLE_H1 + l), rc, &s.bars[BAR_K], true);
                 if (t == 0) LMR_TRACE(0, it * 20 + 3 + 2 * st);
             }
             // ---- last hidden layer + output layer (CUDA cores): h_4 in registers, y, dy = g (1 - y^2), dz_3 = (Wout^T dy)(1 - h_4^2) -> DA
@@ -632,29 +683,28 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
 #pragma unroll
                 for (int i = 0; i < NCH; ++i) {
                     const int ch = rc.g + NG * i;
+                    if (ch < 7) {
+                        tanh_begin<FAST>(v + 4 * i);
+                        tanh_end<FAST>(v + 4 * i);
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        if (ch < 6 || (ch == 6 && p < 2)) {
-                            v[4 * i + p] = act_tanh2<FAST>(v[4 * i + p]);
+                        for (int p = 0; p < 4; ++p) {
 #pragma unroll
                             for (int c = 0; c < C; ++c) {
                                 const float2 w = *reinterpret_cast<const float2*>(s.Wout + c * HPAD + 8 * ch + 2 * p);
                                 y[c] = fmaf(v[4 * i + p].x, w.x, fmaf(v[4 * i + p].y, w.y, y[c]));
                             }
-                        } else {
-                            v[4 * i + p] = make_float2(0.f, 0.f);
                         }
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < C; ++c) s.scratch[(rc.row * NG + rc.g) * C + c] = y[c];
+                for (int c = 0; c < C; ++c) s.scratch[(rc.g * 128 + rc.row) * C + c] = y[c];
                 named_bar_sync(2 + rc.q, 32 * NG);  // the warps of this lane quarter exchange their partial dot products
                 float dy[C];
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
                     float ys = 0.f;
 #pragma unroll
-                    for (int gg = 0; gg < NG; ++gg) ys += s.scratch[(rc.row * NG + gg) * C + c];
+                    for (int gg = 0; gg < NG; ++gg) ys += s.scratch[(gg * 128 + rc.row) * C + c];
                     const float yy = act_tanh<FAST>(s.bout[c] + ys);
                     dy[c] = g[c] * (1.f - yy * yy);
                     bacc[c] += dy[c];
@@ -662,92 +712,77 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
 #pragma unroll
                 for (int i = 0; i < NCH; ++i) {
                     const int ch = rc.g + NG * i;
+                    if (ch < 7) {
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        float2 dh = make_float2(0.f, 0.f);
-                        const float2 h = v[4 * i + p];
+                        for (int p = 0; p < 4; ++p) {
+                            float2 dh = make_float2(0.f, 0.f);
+                            const float2 h = v[4 * i + p];
 #pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const float2 d2 = make_float2(dy[c], dy[c]);
-                            if (want_w) {
-                                const float2 wa = fma2(h, d2, make_float2(wacc[c][8 * i + 2 * p], wacc[c][8 * i + 2 * p + 1]));
-                                wacc[c][8 * i + 2 * p] = wa.x, wacc[c][8 * i + 2 * p + 1] = wa.y;
+                            for (int c = 0; c < C; ++c) {
+                                const float2 d2 = make_float2(dy[c], dy[c]);
+                                if (want_w) {
+                                    const float2 wa = fma2(h, d2, make_float2(wacc[c][8 * i + 2 * p], wacc[c][8 * i + 2 * p + 1]));
+                                    wacc[c][8 * i + 2 * p] = wa.x, wacc[c][8 * i + 2 * p + 1] = wa.y;
+                                }
+                                dh = fma2(*reinterpret_cast<const float2*>(s.Wout + c * HPAD + 8 * ch + 2 * p), d2, dh);
                             }
-                            dh = fma2(*reinterpret_cast<const float2*>(s.Wout + c * HPAD + 8 * ch + 2 * p), d2, dh);
+                            // dh (1 - h^2); padding columns: Wout == 0; constant-1 column: 1 - 1 == 0
+                            v[4 * i + p] = fma2(mul2(dh, mul2(h, h)), make_float2(-1.f, -1.f), dh);
                         }
-                        // dh (1 - h^2); padding columns: Wout == 0; constant-1 column: 1 - 1 == 0
-                        v[4 * i + p] = fma2(mul2(dh, mul2(h, h)), make_float2(-1.f, -1.f), dh);
                     }
                 }
-                auto id_op = [&](auto, int, int, float2*) {};
-                transform_store<NG>(v, buf(ROLE_DA), rc, &s.bars[BAR_K], id_op);
+                plain_store<NG>(v, buf(ROLE_DA), rc, &s.bars[BAR_K]);
                 ++st;
                 if (t == 0) LMR_TRACE(0, it * 20 + 1 + 2 * st);
             }
-            // ---- layers 3, 2: dz_{l-1} = dh_l (1 - h_l^2) -> the other gradient tile   (h_l[50] == 1 zeroes the bias column)
+            // ---- layers 3, 2, 1: dz_{l-1} = dh_l (1 - h_l^2)   (h_l[50] == 1 zeroes the bias column).  dz_2, dz_1 -> the other gradient tile;
+            //      dz_0 feeds only CUDA-core reductions: fp32 staging panel stage[row][o] in the free gradient tile
+            float* stage = reinterpret_cast<float*>(buf(ROLE_DB));
 #pragma unroll 1
-            for (int l = LH - 1; l >= 2; --l, ++st) {
+            for (int l = LH - 1; l >= 1; --l, ++st) {
                 const uint8_t* Hl = buf(ROLE_H1 + l - 1);
-                uint8_t* dst = buf(((LH - l) & 1) ? ROLE_DB : ROLE_DA);
                 float2 hv[4 * NCH];  // h_l of this thread's features, fetched while the data-gradient MMAs run
 #pragma unroll
-                for (int i = 0; i < NCH; ++i) {
-                    const int ch = rc.g + NG * i;
-                    if (ch < 6) load_chunk2<4>(Hl, rc.row, ch, hv + 4 * i);
-                    else if (ch == 6) load_chunk2<2>(Hl, rc.row, ch, hv + 4 * i);
-                }
-                wait_acc(st);
-                if (t == 0) LMR_TRACE(0, it * 20 + 2 + 2 * st);
-                load_acc<NG>(tm + TM_ACC + (uint32_t)(st & 1) * 64 + rc.lane_taddr, rc.g, vf);
-                auto dz_op = [&](auto np, int i, int, float2* x) {
-#pragma unroll
-                    for (int p = 0; p < decltype(np)::value; ++p) x[p] = fma2(mul2(x[p], mul2(hv[4 * i + p], hv[4 * i + p])), make_float2(-1.f, -1.f), x[p]);
-                };
-                transform_store<NG>(v, dst, rc, &s.bars[BAR_K], dz_op);
-                if (t == 0) LMR_TRACE(0, it * 20 + 3 + 2 * st);
-            }
-            // ---- layer 1: dz_0 = dh_1 (1 - h_1^2) feeds only CUDA-core reductions: fp32 staging panel stage[o][row] in the free gradient tile
-            float* stage = reinterpret_cast<float*>(buf(ROLE_DB));
-            {
-                const uint8_t* H1 = buf(ROLE_H1);
-                float2 hv[4 * NCH];
-#pragma unroll
-                for (int i = 0; i < NCH; ++i) {
-                    const int ch = rc.g + NG * i;
-                    if (ch < 6) load_chunk2<4>(H1, rc.row, ch, hv + 4 * i);
-                    else if (ch == 6) load_chunk2<2>(H1, rc.row, ch, hv + 4 * i);
-                }
+                for (int i = 0; i < NCH; ++i)
+                    if (rc.g + NG * i < 7) load_chunk2<4>(Hl, rc.row, rc.g + NG * i, hv + 4 * i);
                 wait_acc(st);
                 if (t == 0) LMR_TRACE(0, it * 20 + 2 + 2 * st);
                 load_acc<NG>(tm + TM_ACC + (uint32_t)(st & 1) * 64 + rc.lane_taddr, rc.g, vf);
 #pragma unroll
-                for (int i = 0; i < NCH; ++i) {
-                    const int ch = rc.g + NG * i;
+                for (int i = 0; i < NCH; ++i)
+                    if (rc.g + NG * i < 7) {
 #pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        if (ch < 6 || (ch == 6 && p < 2)) {
-                            const float2 x = v[4 * i + p];
-                            const float2 d = fma2(mul2(x, mul2(hv[4 * i + p], hv[4 * i + p])), make_float2(-1.f, -1.f), x);
-                            const int o = 8 * ch + 2 * p;
-                            stage[o * 128 + rc.row] = d.x;
-                            stage[(o + 1) * 128 + rc.row] = d.y;
+                        for (int p = 0; p < 4; ++p) v[4 * i + p] = fma2(mul2(v[4 * i + p], mul2(hv[4 * i + p], hv[4 * i + p])), make_float2(-1.f, -1.f), v[4 * i + p]);
+                    }
+                if (l >= 2) {
+                    plain_store<NG>(v, buf(((LH - l) & 1) ? ROLE_DB : ROLE_DA), rc, &s.bars[BAR_K]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NCH; ++i) {
+                        const int ch = rc.g + NG * i;
+                        if (ch < 7) {
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                const int o = 8 * ch + 2 * p;
+                                if (o < STG - 1) stage[rc.row * STG + o] = v[4 * i + p].x, stage[rc.row * STG + o + 1] = v[4 * i + p].y;
+                            }
                         }
                     }
                 }
+                if (t == 0) LMR_TRACE(0, it * 20 + 3 + 2 * st);
             }
-            if (t == 0) LMR_TRACE(0, it * 20 + 14);
             named_bar_sync(1, NE);  // dz_0 staged (and beta written)
             if (t == 0) LMR_TRACE(0, it * 20 + 15);
-            // ---- layer 0: G0[j][o] = sum_n dz0, dA[n][o] += sum_j dz0   (CUDA cores; all loads of an item are independent)
+            // ---- layer 0: G0[j][o] = sum_n dz0, dA[n][o] += sum_j dz0   (CUDA cores; consecutive lanes -> consecutive features: conflict-free)
             float* G0s = s.scratch;
             if (t < TP * SHP) {
                 float sum = 0.f;
                 if (g0_o < HID && g0_j < ti.np) {
-                    const float* zr = stage + g0_o * 128 + g0_j;
+                    const float* zr = stage + g0_j * STG + g0_o;
                     float s0 = 0.f, s1 = 0.f;
                     int n = 0;
-                    for (; n + 1 < ti.nn; n += 2) s0 += zr[n * TP], s1 += zr[(n + 1) * TP];
-                    if (n < ti.nn) s0 += zr[n * TP];
+                    for (; n + 1 < ti.nn; n += 2) s0 += zr[n * TP * STG], s1 += zr[(n + 1) * TP * STG];
+                    if (n < ti.nn) s0 += zr[n * TP * STG];
                     sum = s0 + s1;
                 }
                 G0s[g0_j * SHP + g0_o] = sum;
@@ -755,12 +790,13 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
             if (want_w) {
 #pragma unroll
                 for (int q = 0; q < MAX_DA; ++q) {
-                    if (da_o[q] < HID && da_n[q] < ti.nn) {
-                        const float* zr = stage + da_o[q] * 128 + da_n[q] * TP;
+                    const int e = t + NE * q, n = e / HID, o = e % HID;
+                    if (n < ti.nn) {
+                        const float* zr = stage + n * TP * STG + o;
                         float sum = 0.f;
 #pragma unroll
                         for (int jj = 0; jj < TP_CAP_TC; ++jj)
-                            if (jj < ti.np) sum += zr[jj];
+                            if (jj < ti.np) sum += zr[jj * STG];
                         dA[q] += sum;
                     }
                 }
@@ -820,8 +856,8 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
             float* p_db = part + (size_t)(LH - 1) * HID * HID;
             float* p_dWout = p_db + (size_t)(LH - 1) * SHP;
             float* p_dA = p_dWout + (size_t)C * SHP + 4;
-            float* red = reinterpret_cast<float*>(s.tiles);  // [128][53] fp32 (any tile buffer: all MMAs are done)
-            constexpr int RS = 53;
+            float* red = reinterpret_cast<float*>(s.tiles);  // [128][57] fp32 (any tile buffer: all MMAs are done)
+            constexpr int RS = 57;
 #pragma unroll 1
             for (int l = 1; l < LH; ++l) {
                 // D[m][n]: m = dz feature (hi 0..63 | lo 64..127), n = h feature (hi 0..63 | lo 64..127); dW = D_hh + D_hl + D_lh
@@ -832,9 +868,10 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
 #pragma unroll
                 for (int i = 0; i < NCH; ++i) {
                     const int ch = rc.g + NG * i;
+                    if (ch < 7) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (ch < 6 || (ch == 6 && k < 4)) red[rc.row * RS + 8 * ch + k] = rc.row < 64 ? x[8 * i + k] + y2[8 * i + k] : x[8 * i + k];
+                        for (int k = 0; k < 8; ++k) red[rc.row * RS + 8 * ch + k] = rc.row < 64 ? x[8 * i + k] + y2[8 * i + k] : x[8 * i + k];
+                    }
                 }
                 named_bar_sync(1, NE);
                 for (int i = t; i < HID * (HID + 1); i += NE) {
@@ -845,20 +882,21 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
                 }
                 named_bar_sync(1, NE);
             }
-            // output layer: column sums over the 128 rows of this thread's running products
+            // output layer: column sums over the 128 rows of this thread's running products   (red as [57][129]; row 56 = sum of dy)
 #pragma unroll 1
             for (int c = 0; c < C; ++c) {
 #pragma unroll
                 for (int i = 0; i < NCH; ++i) {
                     const int ch = rc.g + NG * i;
+                    if (ch < 7) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (ch < 6 || (ch == 6 && k < 4)) red[(8 * ch + k) * 128 + rc.row] = wacc[c][8 * i + k];
+                        for (int k = 0; k < 8; ++k) red[(8 * ch + k) * 129 + rc.row] = wacc[c][8 * i + k];
+                    }
                 }
-                if (rc.g == 0) red[52 * 128 + rc.row] = bacc[c];
+                if (rc.g == 0) red[56 * 129 + rc.row] = bacc[c];
                 named_bar_sync(1, NE);
                 if (t < 53) {
-                    const float* src = red + t * 128;
+                    const float* src = red + (t == 52 ? 56 : t) * 129;
                     float s0 = 0.f, s1 = 0.f;
                     for (int r = 0; r < 128; r += 2) s0 += src[r], s1 += src[r + 1];
                     if (t < HID) p_dWout[c * SHP + t] = s0 + s1;
@@ -867,8 +905,10 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
                 named_bar_sync(1, NE);
             }
 #pragma unroll
-            for (int q = 0; q < MAX_DA; ++q)
-                if (da_o[q] < HID) p_dA[da_n[q] * SHP + da_o[q]] = dA[q];
+            for (int q = 0; q < MAX_DA; ++q) {
+                const int e = t + NE * q, n = e / HID, o = e % HID;
+                if (n < tl.NC) p_dA[n * SHP + o] = dA[q];
+            }
         }
     }
     fence_before_sync();

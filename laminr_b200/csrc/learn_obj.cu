@@ -1,0 +1,456 @@
+// Fused learn-stage objective: ONE persistent launch for everything between the INR forward and the INR backward of a learn step
+// (reference laminr/inv_temp_learn_match.py:187-204 with FixEnergyNormClip / StandardizeClip (laminr/utils/img_transforms.py:5-65),
+// SingleNeuronModel over a simulated neuron (laminr/utils/general.py:5-12, neuron_models/utils/simulated_model.py:8-17), apply_mask
+// (laminr/utils/mask.py:7-22) and SimCLROnGrid.reg_term (laminr/contrastive_loss.py:139-154)), forward AND backward:
+//
+//     z = constrain(x);  act_n = (elu(max_f <z_n, w_f>) + 1)/2 + eps;  reg = simclr(mask(z));
+//     loss = -mean_n(act_n / mei_act) + g_reg * reg           (g_reg = -reg_scale, a device scalar)
+//     g_x  = d loss / d x
+//
+// Every stage is HBM/L2-bound scan/reduce work on 0.8-3.2 MB, so the cost of the unfused version is launch latency (12 launches).  Here
+// each CTA owns one pixel slice of ALL N images (kept in shared memory across the phases); per-image and gram reductions go through
+// per-CTA partials in global memory, a software grid barrier (all CTAs co-resident: cooperative launch, grid <= #SMs) and a fixed-order
+// (deterministic) combine.  4 grid barriers (5 in STD mode).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace lmr {
+namespace lobj {
+
+constexpr int NT = 256;
+
+struct Params {
+    int mode, N, C, HW, F;
+    float target, mean, pmin, pmax, eps_con;
+    int has_min, has_max;
+    const float* x;        // [N, C, HW]
+    const float* bank;     // [F, HW] filters of the template neuron
+    float act_eps, inv_mei_act;
+    const float* mask;     // [HW]
+    const float* pos;      // [N, N]
+    const float* neg;      // [N, N]
+    float T, eps_clr, c0, g1, g2;
+    const float* g_reg;    // device scalar: d loss / d reg
+    float *z, *stats, *act, *rmax, *reg, *Kmat, *loss, *g_x;
+    int* argmax;
+    // workspace
+    unsigned int* sync;    // [0] arrival counter (monotonic), [1] launch epoch
+    float *part_a, *part_b, *fin, *part_c;
+    int PS;                // pixels per slice
+};
+
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// all CTAs of the (co-resident) grid arrive, then continue.  `target` = arrivals expected since the counter was zero.
+__device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        while ((int)(ld_acquire(counter) - target) < 0) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float masked_value(float x, float m, float c0, float g1, float g2) {
+    // rescale(x, pmin, pmax, -1, 1) * mask, then rescale back (same op order as mask.py:7-22)
+    const float r = (x - c0) * g1 + 0.f;
+    return (r * m - 0.f) * g2 + c0;
+}
+__device__ __forceinline__ float clamp_pass(float y, int has_min, float pmin, int has_max, float pmax) {
+    return ((!has_min || y >= pmin) && (!has_max || y <= pmax)) ? 1.f : 0.f;  // torch.clamp backward: inclusive
+}
+
+// one warp sums `count` values spaced `stride` apart in a fixed order (lane partials, then a shuffle tree): deterministic
+__device__ __forceinline__ float warp_strided_sum(const float* src, int count, size_t stride, int lane) {
+    float s0 = 0.f;
+    for (int i = lane; i < count; i += 32) s0 += __ldcg(src + (size_t)i * stride);  // written by other CTAs of this launch: bypass L1
+    return warp_sum(s0);
+}
+
+__global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
+    extern __shared__ __align__(16) float sm[];
+    const int N = p.N, C = p.C, HW = p.HW, F = p.F, NC = N * C;
+    const int G = gridDim.x, b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, NW = NT / 32;
+    const int PS = p.PS, PSP = PS | 1;
+    const int p0 = b * PS, np = max(0, min(PS, HW - p0));
+    float* xs = sm;                    // [NC][PSP]  x
+    float* xm = xs + NC * PSP;         // [NC][PSP]  masked z
+    float* gy = xm + NC * PSP;         // [NC][PSP]  gradient wrt the pre-clamp image
+    float* ws = gy + NC * PSP;         // [F][PSP]   filter slice
+    float* zs = ws + F * PSP;          // [N][PSP]   sum_c z
+    float* mk = zs + N * PSP;          // [PSP]
+    float* sd = mk + PSP;              // [N]
+    float* mu = sd + N;                // [N]
+    float* coef = mu + N;              // [N]  g_act * 1/2 * elu'(rmax)
+    float* dotu = coef + N;            // [N][2]
+    int* amax = reinterpret_cast<int*>(dotu + 2 * N);  // [N]
+    float* fin = reinterpret_cast<float*>(amax + N);   // [N*F + N*N]
+    float* cosm = fin + N * F + N * N; // [N][N]
+    float* Sm = cosm + N * N;          // [N][N]
+    float* rho = Sm + N * N;           // [N]
+    float* rowc = rho + N;             // [N][4]
+    float* Ks = rowc + 4 * N;          // [N][N]
+    __shared__ float scratch[40];
+    const unsigned int epoch = ld_acquire(p.sync + 1);
+    const unsigned int nbar = p.mode == LMR_CONSTRAIN_NORM ? 4u : 5u;
+    unsigned int bar_no = 0;
+    auto barrier = [&]() {
+        ++bar_no;
+        grid_sync(p.sync, (epoch * nbar + bar_no) * (unsigned int)G);
+    };
+
+    // ---- phase 0: load the slice, per-image statistics
+    for (int i = t; i < NC * PS; i += NT) {
+        const int r = i / PS, e = i % PS;
+        xs[r * PSP + e] = e < np ? p.x[(size_t)r * HW + p0 + e] : 0.f;
+    }
+    for (int i = t; i < F * PS; i += NT) {
+        const int f = i / PS, e = i % PS;
+        ws[f * PSP + e] = e < np ? __ldg(p.bank + (size_t)f * HW + p0 + e) : 0.f;
+    }
+    for (int e = t; e < PS; e += NT) mk[e] = e < np ? p.mask[p0 + e] : 0.f;
+    __syncthreads();
+    if (p.mode == LMR_CONSTRAIN_NORM) {
+        for (int n = warp; n < N; n += NW) {
+            float acc = 0.f;
+            for (int i = lane; i < C * PS; i += 32) {
+                const int c = i / PS, e = i % PS;
+                const float u = xs[(n * C + c) * PSP + e] - p.mean;
+                acc += e < np ? u * u : 0.f;
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) p.part_a[(size_t)b * N + n] = acc;
+        }
+        barrier();
+        for (int n = warp; n < N; n += NW) {
+            const float tot = warp_strided_sum(p.part_a + n, G, N, lane);
+            if (lane == 0) sd[n] = sqrtf(tot), mu[n] = 0.f;
+        }
+    } else {
+        for (int n = warp; n < N; n += NW) {
+            float acc = 0.f;
+            for (int i = lane; i < C * PS; i += 32) {
+                const int c = i / PS, e = i % PS;
+                acc += e < np ? xs[(n * C + c) * PSP + e] : 0.f;
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) p.part_a[(size_t)b * N + n] = acc;
+        }
+        barrier();
+        for (int n = warp; n < N; n += NW) {
+            const float tot = warp_strided_sum(p.part_a + n, G, N, lane);
+            if (lane == 0) mu[n] = tot / (float)(C * HW);
+        }
+        __syncthreads();
+        for (int n = warp; n < N; n += NW) {
+            float acc = 0.f;
+            for (int i = lane; i < C * PS; i += 32) {
+                const int c = i / PS, e = i % PS;
+                const float u = xs[(n * C + c) * PSP + e] - mu[n];
+                acc += e < np ? u * u : 0.f;
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) p.part_c[(size_t)b * 2 * N + n] = acc;
+        }
+        barrier();
+        for (int n = warp; n < N; n += NW) {
+            const float tot = warp_strided_sum(p.part_c + n, G, 2 * N, lane);
+            if (lane == 0) sd[n] = sqrtf(tot / (float)(C * HW - 1));  // unbiased (Tensor.std default)
+        }
+    }
+    __syncthreads();
+    if (b == 0 && p.stats != nullptr)
+        for (int n = t; n < N; n += NT) p.stats[2 * n] = sd[n], p.stats[2 * n + 1] = mu[n];
+
+    // ---- phase 1: z (written out), sum_c z, masked z; partial responses and partial gram
+    for (int i = t; i < NC * PS; i += NT) {
+        const int r = i / PS, e = i % PS, n = r / C;
+        float y;
+        if (p.mode == LMR_CONSTRAIN_NORM) y = (xs[r * PSP + e] - p.mean) / (sd[n] + p.eps_con) * p.target + p.mean;
+        else y = p.target * (xs[r * PSP + e] - mu[n]) / (sd[n] + p.eps_con) + p.mean;
+        if (p.has_min) y = fmaxf(y, p.pmin);
+        if (p.has_max) y = fminf(y, p.pmax);
+        if (e < np) {
+            p.z[(size_t)r * HW + p0 + e] = y;
+            xm[r * PSP + e] = masked_value(y, mk[e], p.c0, p.g1, p.g2);
+            gy[r * PSP + e] = y;  // z, until phase 3 overwrites it
+        } else {
+            xm[r * PSP + e] = 0.f, gy[r * PSP + e] = 0.f;
+        }
+    }
+    __syncthreads();
+    for (int i = t; i < N * PS; i += NT) {
+        const int n = i / PS, e = i % PS;
+        float v = 0.f;
+        for (int c = 0; c < C; ++c) v += gy[(n * C + c) * PSP + e];
+        zs[n * PSP + e] = v;
+    }
+    __syncthreads();
+    {
+        float* outR = p.part_b + (size_t)b * (N * F + N * N);
+        for (int i = t; i < N * F; i += NT) {
+            const int n = i / F, f = i % F;
+            const float* a = zs + n * PSP;
+            const float* w = ws + f * PSP;
+            float s0 = 0.f, s1 = 0.f;
+            int e = 0;
+            for (; e + 1 < PS; e += 2) s0 = fmaf(a[e], w[e], s0), s1 = fmaf(a[e + 1], w[e + 1], s1);
+            if (e < PS) s0 = fmaf(a[e], w[e], s0);
+            outR[i] = s0 + s1;
+        }
+        float* outG = outR + N * F;
+        for (int pr = t; pr < N * N; pr += NT) {
+            const int i = pr / N, j = pr % N;
+            if (j < i) continue;
+            float s0 = 0.f, s1 = 0.f;
+            for (int c = 0; c < C; ++c) {
+                const float* a = xm + (i * C + c) * PSP;
+                const float* w = xm + (j * C + c) * PSP;
+                int e = 0;
+                for (; e + 1 < PS; e += 2) s0 = fmaf(a[e], w[e], s0), s1 = fmaf(a[e + 1], w[e + 1], s1);
+                if (e < PS) s0 = fmaf(a[e], w[e], s0);
+            }
+            outG[i * N + j] = s0 + s1;
+            outG[j * N + i] = s0 + s1;
+        }
+    }
+    barrier();
+    // ---- phase 2: two-level combine of the partials (value v is summed by CTA v % G), then everybody reads the totals
+    {
+        const int nval = N * F + N * N;
+        for (int v = b + G * warp; v < nval; v += G * NW) {
+            const float tot = warp_strided_sum(p.part_b + v, G, (size_t)nval, lane);
+            if (lane == 0) p.fin[v] = tot;
+        }
+    }
+    barrier();
+    {
+        const int nval = N * F + N * N;
+        for (int v = t; v < nval; v += NT) fin[v] = __ldcg(p.fin + v);
+    }
+    __syncthreads();
+    const float g_reg = p.g_reg[0];
+    // responses: first maximum wins (torch.max), act = (elu(m)+1)/2 + eps
+    for (int n = t; n < N; n += NT) {
+        float best = -INFINITY;
+        int bi = 0;
+        for (int f = 0; f < F; ++f) {
+            const float r = fin[n * F + f];
+            if (r > best) best = r, bi = f;
+        }
+        const float e = best > 0.f ? best : expm1f(best);
+        const float act = (e + 1.f) / 2.f + p.act_eps;
+        amax[n] = bi;
+        coef[n] = (-p.inv_mei_act / (float)N) * 0.5f * (best > 0.f ? 1.f : expf(best));
+        rho[n] = act;  // parked until the loss is formed below
+        if (b == 0) {
+            p.act[n] = act;
+            if (p.rmax) p.rmax[n] = best;
+            if (p.argmax) p.argmax[n] = bi;
+        }
+    }
+    __syncthreads();
+    float act_sum = 0.f;
+    if (t == 0)
+        for (int n = 0; n < N; ++n) act_sum += rho[n];
+    __syncthreads();
+    // contrastive term and its backward coefficient matrix K (same maths as post.cu simclr_finalize_kernel)
+    const float* gram = fin + N * F;
+    for (int i = t; i < N; i += NT) rho[i] = sqrtf(gram[i * N + i]);
+    __syncthreads();
+    for (int pr = t; pr < N * N; pr += NT) {
+        const int i = pr / N, j = pr % N;
+        const float c = gram[pr] / (rho[i] * rho[j]);
+        cosm[pr] = c;
+        Sm[pr] = expf(c / p.T);
+    }
+    __syncthreads();
+    float logsum = 0.f;
+    for (int i = t; i < N; i += NT) {
+        float ps = 0.f, np_ = 0.f, ns = 0.f, nn = 0.f;
+        for (int j = 0; j < N; ++j) {
+            ps = fmaf(Sm[i * N + j], p.pos[i * N + j], ps), np_ += p.pos[i * N + j];
+            ns = fmaf(Sm[i * N + j], p.neg[i * N + j], ns), nn += p.neg[i * N + j];
+        }
+        const float num = (ps == 0.f ? 0.f : ps / np_) + p.eps_clr;
+        const float den = (ns == 0.f ? 0.f : ns / nn) + p.eps_clr;
+        logsum += logf(num / den);
+        rowc[i * 4 + 0] = ps == 0.f ? 0.f : (p.T / (2.f * N)) / (np_ * num);
+        rowc[i * 4 + 1] = ns == 0.f ? 0.f : (p.T / (2.f * N)) / (nn * den);
+    }
+    logsum = block_sum(logsum, scratch);
+    if (b == 0 && t == 0) {
+        const float reg = logsum / (float)N * p.T / 2.f;
+        p.reg[0] = reg;
+        p.loss[0] = -(act_sum * p.inv_mei_act) / (float)N + g_reg * reg;
+    }
+    __syncthreads();
+    for (int pr = t; pr < N * N; pr += NT) {
+        const int i = pr / N;
+        Sm[pr] = (p.pos[pr] * rowc[i * 4] - p.neg[pr] * rowc[i * 4 + 1]) * Sm[pr] / p.T;  // Gamma_ij = A_ij S_ij / T
+    }
+    __syncthreads();
+    for (int i = t; i < N; i += NT) {
+        float kap = 0.f;
+        for (int j = 0; j < N; ++j) kap = fmaf(Sm[i * N + j] + Sm[j * N + i], cosm[i * N + j], kap);
+        rowc[i * 4 + 3] = kap;
+    }
+    __syncthreads();
+    for (int pr = t; pr < N * N; pr += NT) {
+        const int i = pr / N, j = pr % N;
+        float k = (Sm[i * N + j] + Sm[j * N + i]) / (rho[i] * rho[j]);
+        if (i == j) k -= rowc[i * 4 + 3] / (rho[i] * rho[i]);
+        Ks[pr] = k;
+        if (b == 0 && p.Kmat) p.Kmat[pr] = k;
+    }
+    __syncthreads();
+
+    // ---- phase 3: g_z = response backward + contrastive backward; gradient wrt the pre-clamp image; per-image sums for the projection
+    for (int i = t; i < NC * PS; i += NT) {
+        const int r = i / PS, e = i % PS, n = r / C, c = r % C;
+        float v = 0.f;
+        if (e < np) {
+            const float m = mk[e];
+            float acc = 0.f;
+            for (int jn = 0; jn < N; ++jn) acc = fmaf(Ks[n * N + jn], xm[(jn * C + c) * PSP + e], acc);
+            const float gz = coef[n] * ws[amax[n] * PSP + e] + g_reg * (p.g1 * m * p.g2) * acc;
+            float u, y;
+            if (p.mode == LMR_CONSTRAIN_NORM) u = xs[r * PSP + e] - p.mean, y = u / (sd[n] + p.eps_con) * p.target + p.mean;
+            else u = xs[r * PSP + e] - mu[n], y = p.target * u / (sd[n] + p.eps_con) + p.mean;
+            v = gz * clamp_pass(y, p.has_min, p.pmin, p.has_max, p.pmax);
+        }
+        gy[r * PSP + e] = v;
+    }
+    __syncthreads();
+    for (int n = warp; n < N; n += NW) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int i = lane; i < C * PS; i += 32) {
+            const int c = i / PS, e = i % PS;
+            const float g = gy[(n * C + c) * PSP + e];
+            const float u = xs[(n * C + c) * PSP + e] - (p.mode == LMR_CONSTRAIN_NORM ? p.mean : mu[n]);
+            a0 += g;
+            a1 = fmaf(g, e < np ? u : 0.f, a1);
+        }
+        a0 = warp_sum(a0), a1 = warp_sum(a1);
+        if (lane == 0) p.part_c[(size_t)b * 2 * N + n] = a0, p.part_c[(size_t)b * 2 * N + N + n] = a1;
+    }
+    barrier();
+    for (int n = warp; n < N; n += NW) {
+        const float a0 = warp_strided_sum(p.part_c + n, G, 2 * N, lane);
+        const float a1 = warp_strided_sum(p.part_c + N + n, G, 2 * N, lane);
+        if (lane == 0) dotu[2 * n] = a0, dotu[2 * n + 1] = a1;
+    }
+    __syncthreads();
+    // ---- phase 4: g_x   NORM: k gy - target dot / ((s+eps)^2 s) u ;  STD: k (gy - mean(gy)) - target dot / ((sd+eps)^2 (n-1) sd) (x-mu)
+    for (int i = t; i < NC * PS; i += NT) {
+        const int r = i / PS, e = i % PS, n = r / C;
+        if (e >= np) continue;
+        const float s_ = sd[n];
+        const float k = p.target / (s_ + p.eps_con);
+        const float denom = (s_ + p.eps_con) * (s_ + p.eps_con) * s_ * (p.mode == LMR_CONSTRAIN_NORM ? 1.f : (float)(C * HW - 1));
+        const float c2 = p.target * dotu[2 * n + 1] / denom;
+        const float gmean = p.mode == LMR_CONSTRAIN_NORM ? 0.f : dotu[2 * n] / (float)(C * HW);
+        const float u = xs[r * PSP + e] - (p.mode == LMR_CONSTRAIN_NORM ? p.mean : mu[n]);
+        p.g_x[(size_t)r * HW + p0 + e] = k * (gy[r * PSP + e] - gmean) - c2 * u;
+    }
+    // the epoch word is only written here, after every CTA has passed the last barrier (all of them read it at kernel start)
+    if (b == 0 && t == 0) {
+        __threadfence();
+        p.sync[1] = epoch + 1;
+    }
+}
+
+static size_t smem_floats(int N, int C, int F, int PS) {
+    const int PSP = PS | 1, NC = N * C;
+    return (size_t)3 * NC * PSP + (size_t)F * PSP + (size_t)N * PSP + PSP + 6 * (size_t)N + (size_t)N /*amax*/ + (size_t)N * F + N * N + 3 * (size_t)N * N + 5 * (size_t)N + 16;
+}
+
+struct Plan {
+    int G, PS;
+    size_t smem, off_a, off_b, off_fin, off_c, total;
+};
+
+static bool make_plan(int N, int C, int HW, int F, Plan* pl) {
+    const int sms = num_sms();
+    int G = sms;
+    int PS = (HW + G - 1) / G;
+    if (PS < 16) PS = 16;  // tiny images: fewer CTAs
+    G = (HW + PS - 1) / PS;
+    pl->G = G, pl->PS = PS;
+    pl->smem = smem_floats(N, C, F, PS) * sizeof(float);
+    size_t off = 256;  // sync words
+    auto take = [&](size_t nfl) {
+        size_t r = off;
+        off += align_up(nfl * sizeof(float), 256);
+        return r;
+    };
+    pl->off_a = take((size_t)G * N);
+    pl->off_b = take((size_t)G * (N * F + N * N));
+    pl->off_fin = take((size_t)N * F + N * N);
+    pl->off_c = take((size_t)G * 2 * N);
+    pl->total = off;
+    return pl->smem <= 200 * 1024 && N <= 64 && F <= 128;
+}
+
+}  // namespace lobj
+}  // namespace lmr
+
+using namespace lmr;
+
+extern "C" size_t lmr_learn_objective_workspace_bytes(int N, int C, int HW, int F) {
+    lobj::Plan pl;
+    if (!lobj::make_plan(N, C, HW, F, &pl)) return 0;
+    return pl.total;
+}
+
+extern "C" int lmr_learn_objective(int mode, const float* x, int N, int C, int HW, float target, float mean, int has_min, float pmin, int has_max,
+                                   float pmax, float eps_con, const float* bank, int F, float act_eps, float mei_act, const float* mask,
+                                   const float* pos, const float* neg, float temperature, float eps_clr, const float* g_reg, float* z,
+                                   float* stats, float* act, float* rmax, int* argmax, float* reg, float* Kmat, float* loss, float* g_x,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+    LMR_CHECK_ARG(mode == LMR_CONSTRAIN_NORM || mode == LMR_CONSTRAIN_STD, "learn_objective: bad mode %d", mode);
+    LMR_CHECK_ARG(N >= 2 && C >= 1 && HW >= 1 && F >= 1, "learn_objective: bad sizes N=%d C=%d HW=%d F=%d", N, C, HW, F);
+    LMR_CHECK_ARG(x && bank && mask && pos && neg && g_reg && z && act && reg && loss && g_x, "learn_objective: null pointer");
+    lobj::Plan pl;
+    LMR_CHECK_ARG(lobj::make_plan(N, C, HW, F, &pl), "learn_objective: configuration N=%d C=%d HW=%d F=%d does not fit the fused kernel (use the unfused ops)", N, C,
+                  HW, F);
+    if (workspace_bytes < pl.total) {
+        set_error("learn_objective: workspace %zu < %zu bytes", workspace_bytes, pl.total);
+        return LMR_ERR_WORKSPACE;
+    }
+    lobj::Params p;
+    p.mode = mode, p.N = N, p.C = C, p.HW = HW, p.F = F;
+    p.target = target, p.mean = mean, p.pmin = pmin, p.pmax = pmax, p.eps_con = eps_con, p.has_min = has_min, p.has_max = has_max;
+    p.x = x, p.bank = bank, p.act_eps = act_eps, p.inv_mei_act = 1.f / mei_act, p.mask = mask, p.pos = pos, p.neg = neg;
+    p.T = temperature, p.eps_clr = eps_clr;
+    // apply_mask: rescale(x, pmin, pmax, -1, 1) then back (mask.py:7-22); without bounds the mask multiplies the raw image
+    if (has_min && has_max) p.c0 = (pmin + pmax) / 2.f, p.g1 = 2.f / (pmax - pmin), p.g2 = (pmax - pmin) / 2.f;
+    else p.c0 = 0.f, p.g1 = 1.f, p.g2 = 1.f;
+    p.g_reg = g_reg;
+    p.z = z, p.stats = stats, p.act = act, p.rmax = rmax, p.argmax = argmax, p.reg = reg, p.Kmat = Kmat, p.loss = loss, p.g_x = g_x;
+    char* base = static_cast<char*>(workspace);
+    p.sync = reinterpret_cast<unsigned int*>(base);
+    p.part_a = reinterpret_cast<float*>(base + pl.off_a), p.part_b = reinterpret_cast<float*>(base + pl.off_b);
+    p.fin = reinterpret_cast<float*>(base + pl.off_fin), p.part_c = reinterpret_cast<float*>(base + pl.off_c);
+    p.PS = pl.PS;
+    static size_t cache = 0;
+    if (pl.smem > cache) {
+        LMR_CUDA_OK(cudaFuncSetAttribute(lobj::learn_objective_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+        cache = pl.smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(pl.G), cfg.blockDim = dim3(lobj::NT), cfg.dynamicSmemBytes = pl.smem, cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;  // guarantees that all CTAs are co-resident (the software grid barrier needs it)
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    LMR_CUDA_OK(cudaLaunchKernelEx(&cfg, lobj::learn_objective_kernel, p));
+    return 0;
+}

@@ -65,7 +65,11 @@ class LearnStepper:
         self.ws_resp = _ws(lib.lmr_simresp_workspace_bytes(1, N, model.packed_filters.shape[1], P), dev)
         self.ws_clr = _ws(lib.lmr_simclr_workspace_bytes(N, Cc, P), dev)
         self.use_graph, self.graph, self.eval_graph = use_graph, None, None
-        self.kernels_per_step = 20
+        # fused objective (one persistent launch for constraint + response + contrastive, forward and backward) when it fits
+        self.bank = model.packed_filters[int(neuron_idx), :int(model.nfilt[int(neuron_idx)].item())].contiguous()
+        self.loss_buf = torch.zeros(1, **f32)
+        self.ws_obj = ops.learn_objective_workspace(N, Cc, P, self.bank.shape[0], dev)
+        self.kernels_per_step = 9 if self.ws_obj is not None else 20
 
     def set_reg_scale(self, reg_scale):
         self.g_reg.fill_(-float(reg_scale))
@@ -81,8 +85,19 @@ class LearnStepper:
 
     def _train(self):
         t, c, N, Cc, P = self.t, self.con, self.N, self.C, self.P
-        self._forward()
         r = self.reg_mod
+        if self.ws_obj is not None:
+            ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, out=self.img_pre.view(1, N, Cc, P),
+                                precision=self.precision, workspace=self.ws_fwd)
+            ops.raw_learn_objective(c.mode, self.img_pre, c.target, c.mean, c.pmin, c.pmax, c.eps, self.bank, self.model.eps, self.mei_act, self.mask,
+                                    r.flat_neighbor_mask_pos, r.flat_neighbor_mask_neg, r.temperature, r.eps, self.g_reg, self.z, self.act.view(-1),
+                                    self.reg, self.loss_buf, self.g_x, self.ws_obj, stats=self.stats, rmax=self.rmax.view(-1), argmax=self.argmax.view(-1),
+                                    K=self.K)
+            ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, self.g_x.view(1, N, Cc, P), want_params=True,
+                                 precision=self.precision, workspace=self.ws_bwd, g_params=self.g_flat)
+            ops.raw_adam_step(self.flat, self.g_flat, self.m, self.v, self.step_count, lr=self.lr)
+            return
+        self._forward()
         ops.raw_simclr_fwd(self.z, self.mask, N, Cc, P, self.pixel_min, self.pixel_max, r.flat_neighbor_mask_pos, r.flat_neighbor_mask_neg,
                            r.temperature, r.eps, reg=self.reg, K=self.K, workspace=self.ws_clr)
         ops.raw_simresp_bwd(self.g_act, self.rmax, self.argmax, 0, N, 1, Cc, P, self.model.packed_filters, self.nog, self.g_z, accumulate=False)

@@ -334,6 +334,29 @@ def simclr_reg(img, mask, pmin, pmax, pos, neg, T, eps=1e-6):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# fused learn-stage objective (forward + backward in one launch)
+# ------------------------------------------------------------------------------------------------------------------
+def learn_objective_workspace(N, Cc, HW, F, device):
+    """Zero-initialised workspace of lmr_learn_objective, or None when the configuration does not fit the fused kernel."""
+    nbytes = _lib.load().lmr_learn_objective_workspace_bytes(int(N), int(Cc), int(HW), int(F))
+    return None if nbytes == 0 else torch.zeros(int(nbytes), dtype=torch.uint8, device=device)
+
+
+def raw_learn_objective(mode, x, target, mean, pmin, pmax, eps_con, bank, act_eps, mei_act, mask, pos, neg, T, eps_clr, g_reg, z, act, reg, loss, g_x,
+                        workspace, stats=None, rmax=None, argmax=None, K=None):
+    """x [N,C,H,W] -> z, act [N], reg [1], loss [1], g_x = d loss / d x.  bank [F,HW]: filters of the template neuron."""
+    lib = _lib.load()
+    _require_cuda(x, bank, mask, pos, neg, g_reg)
+    N, Cc = x.shape[0], x.shape[1]
+    HW = x[0, 0].numel()
+    check(lib.lmr_learn_objective(int(mode), _ptr(x), N, Cc, HW, float(target), float(mean), int(pmin is not None), float(pmin or 0.0),
+                                  int(pmax is not None), float(pmax or 0.0), float(eps_con), _ptr(bank), int(bank.shape[0]), float(act_eps),
+                                  float(mei_act), _ptr(mask), _ptr(pos), _ptr(neg), float(T), float(eps_clr), _ptr(g_reg), _ptr(z), _ptr(stats),
+                                  _ptr(act), _ptr(rmax), _ptr(argmax), _ptr(reg), _ptr(K), _ptr(loss), _ptr(g_x), _ptr(workspace), workspace.numel(),
+                                  _stream()))
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # Adam / MEI
 # ------------------------------------------------------------------------------------------------------------------
 def raw_adam_step(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):

@@ -272,3 +272,42 @@ def test_match_step_golden(ops):
     _, g_aff = ops.raw_inr_backward(desc, params, B, auxB, grid, coords, None, aff, g_x.reshape(D, N, 1, P), want_params=False, want_affine=True)
     for got, key in zip(g_aff, ("d_angles", "d_scalings", "d_shears", "d_translation")):
         assert relerr(got.cpu().numpy().reshape(d[key].shape), d[key]) < 2e-3, (key, relerr(got.cpu().numpy().reshape(d[key].shape), d[key]))
+
+
+@pytest.mark.parametrize("res", [20, 100])
+@pytest.mark.parametrize("mode,target", [(0, 1.0), (1, 0.05)])
+def test_fused_learn_objective_equals_unfused_chain(ops, res, mode, target):
+    """lmr_learn_objective (one persistent launch, software grid barriers) == constrain + simresp + simclr forward/backward chain; replayed
+    several times on the same workspace (the barrier state must survive back-to-back launches)."""
+    d = golden(f"learn_step_{res}")
+    N, P = 20, res * res
+    rng = np.random.RandomState(3)
+    x = dev(d["img_pre"] if res == 20 else rng.randn(N, 1, res, res).astype(np.float32) * 0.3).reshape(N, 1, res, res)
+    bank = O.demo1_banks([res, res])[2]  # 60 filters
+    packed, nfilt = _pack_banks([bank])
+    packed, nfilt, nog = dev(packed), dev(nfilt, torch.int32), torch.zeros(1, dtype=torch.int32, device="cuda")
+    pos, neg = (dev(a) for a in O.pos_neg_masks(N, 0.1, True))
+    mask, mei_act, reg_scale = dev(d["mask"]), 1.07, 1.6
+    z, stats = ops.raw_constrain_fwd(mode, x, target, 0.0, -1.0, 1.0, 1e-12)
+    act, rmax, argmax = ops.raw_simresp_fwd(z, 0, N, 1, 1, P, packed, nfilt, nog, 1e-6)
+    reg, K = ops.raw_simclr_fwd(z, mask, N, 1, P, -1.0, 1.0, pos, neg, 0.3, 1e-6)
+    loss = -(act[0] / mei_act).mean() - reg_scale * reg[0]
+    g_z = torch.empty_like(z)
+    ops.raw_simresp_bwd(torch.full((1, N), -1.0 / (N * mei_act), device="cuda"), rmax, argmax, 0, N, 1, 1, P, packed, nog, g_z)
+    ops.raw_simclr_bwd(z, mask, K, torch.ones(1, device="cuda"), -reg_scale, N, 1, P, -1.0, 1.0, g_z, accumulate=True)
+    g_x = ops.raw_constrain_bwd(mode, x, g_z, stats, target, 0.0, -1.0, 1.0, 1e-12)
+    ws = ops.learn_objective_workspace(N, 1, P, bank.shape[0], "cuda")
+    assert ws is not None
+    z2, gx2 = torch.empty_like(z), torch.empty_like(z)
+    act2, reg2, loss2 = torch.empty(N, device="cuda"), torch.empty(1, device="cuda"), torch.empty(1, device="cuda")
+    g_reg = torch.full((1,), -reg_scale, device="cuda")
+    for _ in range(3):
+        gx2.zero_()
+        ops.raw_learn_objective(mode, x, target, 0.0, -1.0, 1.0, 1e-12, dev(bank.reshape(len(bank), -1)), 1e-6, mei_act, mask, pos, neg, 0.3, 1e-6, g_reg,
+                                z2, act2, reg2, loss2, gx2, ws)
+        torch.cuda.synchronize()
+        assert relerr(z2.cpu().numpy(), z.cpu().numpy()) < 1e-6
+        assert relerr(act2.cpu().numpy(), act[0].cpu().numpy()) < 1e-6
+        assert abs(reg2.item() - reg.item()) < 2e-5 * abs(reg.item())
+        assert abs(loss2.item() - loss.item()) < 2e-5 * abs(loss.item())
+        assert relerr(gx2.cpu().numpy(), g_x.cpu().numpy()) < 2e-4, relerr(gx2.cpu().numpy(), g_x.cpu().numpy())
