@@ -103,6 +103,16 @@ int lmr_inr_backward(const lmr_inr_desc* desc, const float* params, const float*
                      float* g_scalings, float* g_shears, float* g_translation, void* workspace,
                      size_t workspace_bytes, int precision, void* stream);
 
+/* lmr_inr_backward that takes the per-step tables (latent encoding, separable layer-0 parts) from `forward_workspace`, the workspace of the
+ * lmr_inr_forward call that produced the images whose gradient g_img is.  The caller guarantees identical desc / params / B / auxB / grid /
+ * coords / coord_shift / affine / D / precision and that the forward workspace has not been overwritten since; saves one launch per step.
+ * LMR_PREC_FP32 ignores the forward workspace and recomputes. */
+int lmr_inr_backward_after_forward(const lmr_inr_desc* desc, const float* params, const float* B, const float* auxB, const float* grid, int N,
+                                   const float* coords, int P, const float* coord_shift, const lmr_affine* affine, int D, const float* g_img,
+                                   float* g_params, float* g_angles, float* g_scalings, float* g_shears, float* g_translation,
+                                   void* workspace, size_t workspace_bytes, const void* forward_workspace,
+                                   size_t forward_workspace_bytes, int precision, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Image-constraint projection -- replaces FixEnergyNormClip / StandardizeClip (laminr/utils/img_transforms.py:5-65)
  * and, with eps = 1e-9, the non-differentiable ChangeNorm/ChangeStats + ClipRange (featurevis/ops.py:294-307,441-481).
@@ -171,8 +181,8 @@ int lmr_learn_objective(int mode, const float* x, int N, int C, int HW, float ta
 
 /* ------------------------------------------------------------------------------------------------------------
  * Adam -- torch.optim.Adam(lr, betas, eps) single-tensor update (used on template.func / coordinate_transform
- * parameters, inv_temp_learn_match.py:162,335).  `step` is a device int32 holding the number of steps already
- * taken; it is incremented by the call (graph-capturable).  One flat tensor per call.
+ * parameters, inv_temp_learn_match.py:162,335).  `step` is a device int32[2]: [0] holds the number of steps already
+ * taken and is incremented by the call (graph-capturable), [1] is scratch and must be zero-initialised.  One flat tensor per call.
  * ---------------------------------------------------------------------------------------------------------- */
 int lmr_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int n, float lr, float beta1,
                   float beta2, float eps, int* step, void* stream);

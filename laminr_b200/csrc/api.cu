@@ -38,7 +38,7 @@ namespace tc {
 int forward(const lmr_inr_desc*, const float*, const float*, const float*, const float*, int, const float*, int, const float*, const lmr_affine*, int,
             float*, void*, size_t, int, cudaStream_t);
 int backward(const lmr_inr_desc*, const float*, const float*, const float*, const float*, int, const float*, int, const float*, const lmr_affine*, int,
-             const float*, float*, float*, float*, float*, float*, void*, size_t, int, cudaStream_t);
+             const float*, float*, float*, float*, float*, float*, void*, size_t, int, cudaStream_t, const void*, size_t);
 size_t workspace_bytes(const lmr_inr_desc*, int, int, int, bool);
 }  // namespace tc
 
@@ -95,7 +95,20 @@ extern "C" int lmr_inr_backward(const lmr_inr_desc* desc, const float* params, c
                               g_translation, ws, ws_bytes, st);
     if (precision == LMR_PREC_BF16X3_FAST || precision == LMR_PREC_BF16X3)
         return tc::backward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, g_img, g_params, g_angles, g_scalings, g_shears,
-                            g_translation, ws, ws_bytes, precision, st);
+                            g_translation, ws, ws_bytes, precision, st, nullptr, 0);
     set_error("inr_backward: unknown precision %d", precision);
     return LMR_ERR_INVALID;
+}
+
+extern "C" int lmr_inr_backward_after_forward(const lmr_inr_desc* desc, const float* params, const float* B, const float* auxB, const float* grid,
+                                              int N, const float* coords, int P, const float* coord_shift, const lmr_affine* affine, int D,
+                                              const float* g_img, float* g_params, float* g_angles, float* g_scalings, float* g_shears,
+                                              float* g_translation, void* ws, size_t ws_bytes, const void* forward_workspace,
+                                              size_t forward_workspace_bytes, int precision, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (precision == LMR_PREC_BF16X3_FAST || precision == LMR_PREC_BF16X3)
+        return tc::backward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, g_img, g_params, g_angles, g_scalings, g_shears,
+                            g_translation, ws, ws_bytes, precision, st, forward_workspace, forward_workspace_bytes);
+    return lmr_inr_backward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, g_img, g_params, g_angles, g_scalings, g_shears,
+                            g_translation, ws, ws_bytes, precision, stream);  // the fp32 path recomputes its tables
 }

@@ -56,7 +56,9 @@ struct Args {
     float* Avec;   // [N, HP]
     float* W0cT;   // [2*pe, HP]
     float* Cpg;    // [D*P, HP]  layer-0 coordinate part Cp[d,p][o] = sum_k beta[d,p][k] W0c[o][k]   (tensor-core path)
+    float* betaG;  // [D*P, 2*pe] sin/cos(coords.B) (tensor-core path, D == 1: consumed by the layer-0 weight-gradient kernel), else null
     int want_cp;
+    int ppb;       // pixels per prep / l0 block
     // forward
     float* img;  // [D,N,C,P]
     // backward
@@ -114,7 +116,15 @@ __device__ inline float2 transformed_coord(const Args& a, const float* affc, int
 //   block  N           packed transpose W0cT[k][o] of W0's coordinate block
 //   blocks (N, ...)    (want_cp) 64 pixels each: beta = sin/cos(coords.B) (inr.py:390-397), Cp[d,p][o] = sum_k beta[k] W0c[o][k]
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int PREP_PIX = 64;
+constexpr int PREP_PPB_MAX = 72;  // pixels per block (multiple of 4)
+
+static inline int choose_ppb(int total_pixels) {
+    int ppb = (total_pixels + num_sms() - 1) / num_sms();
+    ppb = (ppb + 3) / 4 * 4;
+    if (ppb < 16) ppb = 16;
+    if (ppb > PREP_PPB_MAX) ppb = PREP_PPB_MAX;
+    return ppb;
+}
 
 template <int HID>
 __global__ void __launch_bounds__(256) prep_all_kernel(Args a) {
@@ -137,56 +147,134 @@ __global__ void __launch_bounds__(256) prep_all_kernel(Args a) {
         }
         __syncthreads();
         const float* b0 = a.params + nt.offb(0);
-        for (int o = warp; o < HP; o += blockDim.x / 32) {  // one warp per output: coalesced reads of W0's row
-            float acc = 0.f;
-            if (o < HID) {
-                const float* w = W0 + (size_t)o * nt.in_dim + 1;
-                for (int k = lane; k < na; k += 32) acc = fmaf(w[k], als[k], acc);
-                acc = warp_sum(acc) + b0[o];
-            } else if (o == HID) {
-                acc = 20.f;  // tanh(20) == 1 in fp32: the tensor-core path keeps a constant-1 feature (bias column) in slot HID
+        // one warp per output (coalesced reads of W0's row); the rows of a warp's outputs are fetched together (latency-bound otherwise)
+        constexpr int MAXO = (HP + 7) / 8, MAXK = 8;  // 8 warps; na <= 256 = 32 * MAXK
+        float wv[MAXO][MAXK];
+#pragma unroll
+        for (int x = 0; x < MAXO; ++x) {
+            const int o = warp + 8 * x;
+#pragma unroll
+            for (int y = 0; y < MAXK; ++y) {
+                const int k = lane + 32 * y;
+                wv[x][y] = (o < HID && k < na) ? W0[(size_t)o * nt.in_dim + 1 + k] : 0.f;
             }
+        }
+#pragma unroll
+        for (int x = 0; x < MAXO; ++x) {
+            const int o = warp + 8 * x;
+            if (o >= HP) continue;
+            float acc = 0.f;
+#pragma unroll
+            for (int y = 0; y < MAXK; ++y) {
+                const int k = lane + 32 * y;
+                if (k < na) acc = fmaf(wv[x][y], als[k], acc);
+            }
+            acc = warp_sum(acc);
+            if (o < HID) acc += b0[o];
+            else if (o == HID) acc = 20.f;  // tanh(20) == 1 in fp32: the tensor-core path keeps a constant-1 feature (bias column) in slot HID
+            else acc = 0.f;
             if (lane == 0) a.Avec[(size_t)bid * HP + o] = acc;
         }
     } else if (bid == N) {
-        for (int i = t; i < HID * nb; i += blockDim.x) {  // coalesced read over k
-            const int o = i / nb, k = i % nb;
-            a.W0cT[(size_t)k * HP + o] = W0[(size_t)o * nt.in_dim + 1 + na + k];
+        if (!a.want_cp) {  // fp32 path: no pixel blocks; the tensor-core path's first pixel block writes W0cT from its shared-memory copy
+            constexpr int U = 8;
+            for (int i0 = t; i0 < HID * nb; i0 += U * 256) {
+                float w[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * 256;
+                    w[u] = i < HID * nb ? W0[(size_t)(i / nb) * nt.in_dim + 1 + na + i % nb] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * 256;
+                    if (i < HID * nb) a.W0cT[(size_t)(i % nb) * HP + i / nb] = w[u];
+                }
+            }
+            for (int i = t; i < nb * (HP - HID); i += blockDim.x) a.W0cT[(size_t)(i / (HP - HID)) * HP + HID + i % (HP - HID)] = 0.f;
         }
-        for (int i = t; i < nb * (HP - HID); i += blockDim.x) a.W0cT[(size_t)(i / (HP - HID)) * HP + HID + i % (HP - HID)] = 0.f;
     } else {
+        // pixels [q0, q0 + nq): beta (kept k-major in shared memory: 4 pixels per float4), then a register-blocked 4 pixel x 4 output GEMM.
+        // Every global read of the block is issued up front (the block is latency-bound otherwise).
+        const int ppb = a.ppb;
         float* Wc = psm;             // [nb][HP]
-        float* bet = Wc + nb * HP;   // [PREP_PIX][nb]
+        float* bet = Wc + nb * HP;   // [nb][ppb]
+        __shared__ float cst[2][10];
+        __shared__ float2 cxy[PREP_PPB_MAX];
+        __shared__ float Bsm[2 * 64];
         const int total = a.tl.D * a.tl.P;
-        const int q0 = (bid - N - 1) * PREP_PIX, nq = min(PREP_PIX, total - q0);
-        for (int i = t; i < HID * nb; i += blockDim.x) {
-            const int o = i / nb, k = i % nb;
-            Wc[k * HP + o] = W0[(size_t)o * nt.in_dim + 1 + na + k];
+        const int q0 = (bid - N - 1) * ppb, nq = min(ppb, total - q0);
+        const int d0 = q0 / a.tl.P;
+        if (a.has_aff && t < 2 && d0 + t < a.tl.D) affine_consts(a.aff, d0 + t, cst[t]);  // a block usually spans at most two targets
+        if (t >= 64 && t < 64 + nb) Bsm[t - 64] = a.B[t - 64];
+        {
+            constexpr int U = 10;
+            for (int i0 = t; i0 < HID * nb; i0 += U * 256) {
+                float w[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * 256;
+                    w[u] = i < HID * nb ? W0[(size_t)(i / nb) * nt.in_dim + 1 + na + i % nb] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u * 256;
+                    if (i < HID * nb) Wc[(i % nb) * HP + i / nb] = w[u];
+                }
+            }
         }
         for (int i = t; i < nb * (HP - HID); i += blockDim.x) Wc[(i / (HP - HID)) * HP + HID + i % (HP - HID)] = 0.f;
-        for (int i = t; i < nq * pe; i += blockDim.x) {
-            const int jj = i / pe, m = i % pe;
-            const int q = q0 + jj;
-            float cst[10];
-            if (a.has_aff) affine_consts(a.aff, q / a.tl.P, cst);
-            const float2 c = transformed_coord(a, cst, q % a.tl.P);
-            float sn, cs;
-            sincosf(c.x * a.B[m] + c.y * a.B[pe + m], &sn, &cs);
-            bet[jj * nb + m] = sn, bet[jj * nb + pe + m] = cs;
+        __syncthreads();
+        if (bid == N + 1)  // packed transpose W0cT[k][o] of W0's coordinate block (consumed by the match backward)
+            for (int i = t; i < nb * HP; i += blockDim.x) a.W0cT[i] = Wc[i];
+        if (t < nq) {  // transformed coordinates of the block's pixels, once per pixel
+            const int q = q0 + t;
+            float loc[10];
+            const float* cc = cst[0];
+            if (a.has_aff) {
+                const int dq = q / a.tl.P - d0;
+                if (dq < 2) cc = cst[dq];
+                else affine_consts(a.aff, q / a.tl.P, loc), cc = loc;  // tiny images: a block may span more than two targets
+            }
+            cxy[t] = transformed_coord(a, cc, q % a.tl.P);
         }
         __syncthreads();
-        for (int i = t; i < nq * (HP / 4); i += blockDim.x) {
-            const int jj = i / (HP / 4), o4 = i % (HP / 4);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            const float* bj = bet + jj * nb;
-            const float4* w = reinterpret_cast<const float4*>(Wc) + o4;
+        for (int i = t; i < pe * ppb; i += blockDim.x) {
+            const int m = i / ppb, jj = i % ppb;
+            float sn = 0.f, cs = 0.f;
+            if (jj < nq) {
+                const float2 c = cxy[jj];
+                sincosf(c.x * Bsm[m] + c.y * Bsm[pe + m], &sn, &cs);
+            }
+            bet[m * ppb + jj] = sn, bet[(pe + m) * ppb + jj] = cs;
+        }
+        __syncthreads();
+        if (a.betaG != nullptr) {  // pixel-major copy for the layer-0 weight-gradient kernel (coalesced over k)
+            for (int i = t; i < nq * nb; i += blockDim.x) {
+                const int jj = i / nb, k = i % nb;
+                a.betaG[(size_t)(q0 + jj) * nb + k] = bet[k * ppb + jj];
+            }
+        }
+        const int npg = ppb / 4, nog = HP / 4;
+        if (t < npg * nog) {
+            const int pg = t / nog, og = t % nog;
+            float4 acc[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) acc[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4* bp = reinterpret_cast<const float4*>(bet) + pg;
+            const float4* wp = reinterpret_cast<const float4*>(Wc) + og;
 #pragma unroll 4
             for (int k = 0; k < nb; ++k) {
-                const float bk = bj[k];
-                const float4 ww = w[k * (HP / 4)];
-                acc.x = fmaf(bk, ww.x, acc.x), acc.y = fmaf(bk, ww.y, acc.y), acc.z = fmaf(bk, ww.z, acc.z), acc.w = fmaf(bk, ww.w, acc.w);
+                const float4 bb = bp[k * npg];
+                const float4 ww = wp[k * nog];
+                acc[0].x = fmaf(bb.x, ww.x, acc[0].x), acc[0].y = fmaf(bb.x, ww.y, acc[0].y), acc[0].z = fmaf(bb.x, ww.z, acc[0].z), acc[0].w = fmaf(bb.x, ww.w, acc[0].w);
+                acc[1].x = fmaf(bb.y, ww.x, acc[1].x), acc[1].y = fmaf(bb.y, ww.y, acc[1].y), acc[1].z = fmaf(bb.y, ww.z, acc[1].z), acc[1].w = fmaf(bb.y, ww.w, acc[1].w);
+                acc[2].x = fmaf(bb.z, ww.x, acc[2].x), acc[2].y = fmaf(bb.z, ww.y, acc[2].y), acc[2].z = fmaf(bb.z, ww.z, acc[2].z), acc[2].w = fmaf(bb.z, ww.w, acc[2].w);
+                acc[3].x = fmaf(bb.w, ww.x, acc[3].x), acc[3].y = fmaf(bb.w, ww.y, acc[3].y), acc[3].z = fmaf(bb.w, ww.z, acc[3].z), acc[3].w = fmaf(bb.w, ww.w, acc[3].w);
             }
-            reinterpret_cast<float4*>(a.Cpg + (size_t)(q0 + jj) * HP)[o4] = acc;
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+                if (4 * pg + x < nq) reinterpret_cast<float4*>(a.Cpg + (size_t)(q0 + 4 * pg + x) * HP)[og] = acc[x];
         }
     }
 }
@@ -211,72 +299,82 @@ __device__ inline TileIdx decode_tile(const Tiling& tl, int tile) {
 // ---------------------------------------------------------------------------------------------------------------
 // learn: layer-0 coordinate block  dW0c[o][k] = sum_{d,p} G0[d,p][o] beta[d,p][k]   (split over pixel chunks)
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int L0_CHUNK = 64;
+constexpr int L0_THREADS = 352;
 
 template <int HID>
-__global__ void __launch_bounds__(256) l0_partial_kernel(Args a, float* l0part /*[grid, HID*2pe]*/) {
+__global__ void __launch_bounds__(L0_THREADS) l0_partial_kernel(Args a, float* l0part /*[grid, HID*2pe]*/) {
     constexpr int HP = (HID + 3) / 4 * 4;
     extern __shared__ __align__(16) float sm[];
     const Net& nt = a.net;
-    const int pe = nt.pe, nb = 2 * pe;
-    float* Gs = sm;                      // [L0_CHUNK][HP]
-    float* Bs = Gs + L0_CHUNK * HP;      // [L0_CHUNK][nb]
+    const int pe = nt.pe, nb = 2 * pe, ppb = a.ppb;
+    float* Gs = sm;                  // [ppb][HP]
+    float* Bs = Gs + ppb * HP;       // [ppb][nb]   (pixel-major: 4 consecutive k per float4)
     const int total = a.tl.D * a.tl.P;   // learn: D == 1 and no affine, but keep it general (coords of target d)
-    const int nchunks = (total + L0_CHUNK - 1) / L0_CHUNK;
-    // entries: o-block of 5 x k-block of 4
-    const int nOB = HID / 5, nKB = nb / 4;
-    const int e = threadIdx.x;
-    const bool owner = e < nOB * nKB;
-    const int ob = e % nOB, kb = e / nOB;
-    float acc[5][4];
+    const int nchunks = (total + ppb - 1) / ppb;
+    // register block: 4 outputs x 4 encoding features
+    const int nOG = HP / 4, nKG = nb / 4;
+    const int t = threadIdx.x;
+    const bool owner = t < nOG * nKG;
+    const int og = t % nOG, kg = t / nOG;
+    float4 acc[4];
 #pragma unroll
-    for (int x = 0; x < 5; ++x)
-#pragma unroll
-        for (int y = 0; y < 4; ++y) acc[x][y] = 0.f;
-    __shared__ float affc[10];
+    for (int x = 0; x < 4; ++x) acc[x] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
-        const int q0 = ch * L0_CHUNK, nq = min(L0_CHUNK, total - q0);
+        const int q0 = ch * ppb, nq = min(ppb, total - q0);
         __syncthreads();
-        for (int i = threadIdx.x; i < nq * HP; i += blockDim.x) Gs[i] = a.G0[(size_t)q0 * HP + i];
-        for (int i = threadIdx.x; i < nq * pe; i += blockDim.x) {
-            const int jj = i / pe, m = i % pe;
-            const int q = q0 + jj, p = q % a.tl.P;
-            float2 c;
-            if (a.has_aff) {
+        for (int i = t; i < nq * HP / 4; i += blockDim.x) reinterpret_cast<float4*>(Gs)[i] = reinterpret_cast<const float4*>(a.G0 + (size_t)q0 * HP)[i];
+        if (a.betaG != nullptr) {
+            for (int i = t; i < nq * nb / 4; i += blockDim.x) reinterpret_cast<float4*>(Bs)[i] = reinterpret_cast<const float4*>(a.betaG + (size_t)q0 * nb)[i];
+        } else {
+            for (int i = t; i < nq * pe; i += blockDim.x) {
+                const int jj = i / pe, m = i % pe;
+                const int q = q0 + jj, p = q % a.tl.P;
                 float cst[10];
-                affine_consts(a.aff, q / a.tl.P, cst);
-                c = transformed_coord(a, cst, p);
-            } else {
-                c = transformed_coord(a, affc, p);
+                if (a.has_aff) affine_consts(a.aff, q / a.tl.P, cst);
+                const float2 c = transformed_coord(a, cst, p);
+                float sn, cs;
+                sincosf(c.x * a.B[m] + c.y * a.B[pe + m], &sn, &cs);
+                Bs[jj * nb + m] = sn, Bs[jj * nb + pe + m] = cs;
             }
-            float sn, cs;
-            sincosf(c.x * a.B[m] + c.y * a.B[pe + m], &sn, &cs);
-            Bs[jj * nb + m] = sn, Bs[jj * nb + pe + m] = cs;
         }
         __syncthreads();
         if (owner) {
+            const float4* gp = reinterpret_cast<const float4*>(Gs) + og;
+            const float4* bp = reinterpret_cast<const float4*>(Bs) + kg;
+#pragma unroll 4
             for (int jj = 0; jj < nq; ++jj) {
-                float g[5];
-#pragma unroll
-                for (int x = 0; x < 5; ++x) g[x] = Gs[jj * HP + ob * 5 + x];
-                const float4 b = *reinterpret_cast<const float4*>(Bs + jj * nb + kb * 4);
-#pragma unroll
-                for (int x = 0; x < 5; ++x) {
-                    acc[x][0] = fmaf(g[x], b.x, acc[x][0]);
-                    acc[x][1] = fmaf(g[x], b.y, acc[x][1]);
-                    acc[x][2] = fmaf(g[x], b.z, acc[x][2]);
-                    acc[x][3] = fmaf(g[x], b.w, acc[x][3]);
-                }
+                const float4 g = gp[jj * nOG], b = bp[jj * nKG];
+                acc[0].x = fmaf(g.x, b.x, acc[0].x), acc[0].y = fmaf(g.x, b.y, acc[0].y), acc[0].z = fmaf(g.x, b.z, acc[0].z), acc[0].w = fmaf(g.x, b.w, acc[0].w);
+                acc[1].x = fmaf(g.y, b.x, acc[1].x), acc[1].y = fmaf(g.y, b.y, acc[1].y), acc[1].z = fmaf(g.y, b.z, acc[1].z), acc[1].w = fmaf(g.y, b.w, acc[1].w);
+                acc[2].x = fmaf(g.z, b.x, acc[2].x), acc[2].y = fmaf(g.z, b.y, acc[2].y), acc[2].z = fmaf(g.z, b.z, acc[2].z), acc[2].w = fmaf(g.z, b.w, acc[2].w);
+                acc[3].x = fmaf(g.w, b.x, acc[3].x), acc[3].y = fmaf(g.w, b.y, acc[3].y), acc[3].z = fmaf(g.w, b.z, acc[3].z), acc[3].w = fmaf(g.w, b.w, acc[3].w);
             }
         }
     }
     if (owner) {
         float* dst = l0part + (size_t)blockIdx.x * HID * nb;
 #pragma unroll
-        for (int x = 0; x < 5; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) dst[(ob * 5 + x) * nb + kb * 4 + y] = acc[x][y];
+        for (int x = 0; x < 4; ++x)
+            if (4 * og + x < HID) reinterpret_cast<float4*>(dst + (size_t)(4 * og + x) * nb)[kg] = acc[x];
     }
+}
+
+// sum of `count` values spaced `stride` apart: 8 independent chains (the loads are L2 round trips), combined in a fixed order
+__device__ __forceinline__ float strided_sum8(const float* src, int count, size_t stride) {
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int b = 0;
+    for (; b + 8 <= count; b += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] += src[(size_t)(b + u) * stride];
+    }
+    for (int u = 0; b < count; ++b, ++u) s[u] += src[(size_t)b * stride];
+    return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+
+__device__ __forceinline__ float quad_sum(float v) {  // lanes 4k..4k+3 -> (v0 + v1) + (v2 + v3) on every lane of the quad
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
 }
 
 // learn: deterministic reductions of the per-CTA partials into g_params (torch layout).
@@ -291,15 +389,16 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(Args a, const floa
     const int L = nt.nl, na = 2 * nt.ape, nb = 2 * nt.pe;
     const size_t total = nt.count();
     const size_t offA = (size_t)(L - 1) * HID * HID + (size_t)(L - 1) * HP + (size_t)nt.C * HP + 4;
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= total + (size_t)tl.N * HP) return;
+    // 4 consecutive lanes share one output element: lane `sub` sums the partials b = sub (mod 4), then a fixed-order quad combine
+    const size_t gid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t i = gid >> 2;
+    const int sub = (int)(gid & 3);
+    if (i >= total + (size_t)tl.N * HP) return;  // whole quads leave together (the bound is per element)
     if (i >= total) {  // dAred
         const size_t e = i - total;
-        float s0 = 0.f, s1 = 0.f;
-        int b = 0;
-        for (; b + 1 < nPartMain; b += 2) s0 += a.partials[b * psz + offA + e], s1 += a.partials[(b + 1) * psz + offA + e];
-        if (b < nPartMain) s0 += a.partials[b * psz + offA + e];
-        a.dAred[e] = s0 + s1;
+        const float part = strided_sum8(a.partials + offA + e + (size_t)sub * psz, (nPartMain - sub + 3) / 4, 4 * psz);
+        const float tot = quad_sum(part);
+        if (sub == 0) a.dAred[e] = tot;
         return;
     }
     const float* src = a.partials;
@@ -308,7 +407,7 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(Args a, const floa
     if (i < nt.size0()) {
         if (i >= (size_t)nt.hid * nt.in_dim) return;  // b0: finish_w0a
         const int o = i / nt.in_dim, col = i % nt.in_dim;
-        if (col < 1 + na) return;                      // template / latent columns: finish_w0a
+        if (col < 1 + na) return;                      // template / latent columns: finish_w0a   (quad-uniform exits)
         src = l0part, off = (size_t)o * nb + (col - 1 - na), stride = (size_t)HID * nb, nPart = nPartL0;
     } else if (i < nt.offWout()) {
         const size_t r = i - nt.size0();
@@ -320,11 +419,9 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(Args a, const floa
         const size_t base = (size_t)(L - 1) * HID * HID + (size_t)(L - 1) * HP;
         off = r < (size_t)nt.C * HID ? base + (r / HID) * HP + (r % HID) : base + (size_t)nt.C * HP + (r - (size_t)nt.C * HID);
     }
-    float s0 = 0.f, s1 = 0.f;
-    int b = 0;
-    for (; b + 1 < nPart; b += 2) s0 += src[b * stride + off], s1 += src[(b + 1) * stride + off];
-    if (b < nPart) s0 += src[b * stride + off];
-    g_params[i] = s0 + s1;
+    const float part = strided_sum8(src + off + (size_t)sub * stride, (nPart - sub + 3) / 4, 4 * stride);
+    const float tot = quad_sum(part);
+    if (sub == 0) g_params[i] = tot;
 }
 
 template <int HID>
@@ -394,8 +491,8 @@ static __global__ void finish_affine_kernel(Args a, float* g_angles, float* g_sc
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 struct WsLayout {
-    size_t alpha, Avec, W0cT, Cpg, G0, partials, l0part, affpart, dAred, total;
-    int gridMain, gridL0;
+    size_t alpha, Avec, W0cT, Cpg, betaG, G0, partials, l0part, affpart, dAred, total;
+    int gridMain, gridL0, ppb;
 };
 
 static inline WsLayout ws_layout(const Net& nt, const Tiling& tl, bool bwd, bool want_cp = false) {
@@ -411,9 +508,11 @@ static inline WsLayout ws_layout(const Net& nt, const Tiling& tl, bool bwd, bool
     w.Avec = take((size_t)tl.N * HP);
     w.W0cT = take((size_t)2 * nt.pe * HP);
     w.Cpg = want_cp ? take((size_t)tl.D * tl.P * HP) : 0;
+    w.betaG = (want_cp && tl.D == 1) ? take((size_t)tl.P * 2 * nt.pe) : 0;  // identical prefix in the forward and backward layouts
     w.gridMain = tl.numTiles < num_sms() ? tl.numTiles : num_sms();
     const int total = tl.D * tl.P;
-    const int nchunks = (total + L0_CHUNK - 1) / L0_CHUNK;
+    w.ppb = choose_ppb(total);
+    const int nchunks = (total + w.ppb - 1) / w.ppb;
     w.gridL0 = nchunks < num_sms() ? nchunks : num_sms();
     w.G0 = w.partials = w.l0part = w.affpart = w.dAred = 0;
     if (bwd) {
@@ -457,7 +556,9 @@ static inline int fill_args(Args& a, const Net& nt, const Tiling& tl, const floa
     a.Avec = reinterpret_cast<float*>(base + wl.Avec);
     a.W0cT = reinterpret_cast<float*>(base + wl.W0cT);
     a.Cpg = reinterpret_cast<float*>(base + wl.Cpg);
+    a.betaG = wl.betaG ? reinterpret_cast<float*>(base + wl.betaG) : nullptr;
     a.want_cp = 0;
+    a.ppb = wl.ppb;
     a.dAred = reinterpret_cast<float*>(base + wl.dAred);
     a.G0 = reinterpret_cast<float*>(base + wl.G0);
     a.partials = reinterpret_cast<float*>(base + wl.partials);
@@ -471,15 +572,29 @@ template <int HID>
 static int launch_prep(const Args& a, cudaStream_t st) {
     constexpr int HP = (HID + 3) / 4 * 4;
     const int nb = 2 * a.net.pe;
-    const int cp_blocks = a.want_cp ? (a.tl.D * a.tl.P + PREP_PIX - 1) / PREP_PIX : 0;
+    const int cp_blocks = a.want_cp ? (a.tl.D * a.tl.P + a.ppb - 1) / a.ppb : 0;
     size_t smem = (size_t)2 * a.net.ape * sizeof(float);
-    if (a.want_cp) smem = ((size_t)nb * HP + (size_t)PREP_PIX * nb) * sizeof(float);
+    if (a.want_cp) smem = ((size_t)nb * HP + (size_t)nb * a.ppb) * sizeof(float);
     static size_t cache = 0;
-    if (smem > 48 * 1024 && smem > cache) {
+    if (smem > 40 * 1024 && smem > cache) {  // static shared memory counts against the 48 KB default limit too
         LMR_CUDA_OK(cudaFuncSetAttribute(prep_all_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cache = smem;
     }
     prep_all_kernel<HID><<<a.tl.N + 1 + cp_blocks, 256, smem, st>>>(a);
+    LMR_LAUNCH_OK();
+    return 0;
+}
+
+template <int HID>
+static int launch_l0_partial(const Args& a, float* l0part, int grid_l0, cudaStream_t st) {
+    constexpr int HP = (HID + 3) / 4 * 4;
+    const size_t smem = (size_t)a.ppb * (HP + 2 * a.net.pe) * sizeof(float);
+    static size_t cache = 0;
+    if (smem > 40 * 1024 && smem > cache) {
+        LMR_CUDA_OK(cudaFuncSetAttribute(l0_partial_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cache = smem;
+    }
+    l0_partial_kernel<HID><<<grid_l0, L0_THREADS, smem, st>>>(a, l0part);
     LMR_LAUNCH_OK();
     return 0;
 }
@@ -489,7 +604,7 @@ template <int HID>
 static int launch_finish_weights(const Args& a, const float* l0part, int nPartMain, int nPartL0, float* g_params, cudaStream_t st) {
     constexpr int HP = (HID + 3) / 4 * 4;
     const size_t n1 = a.net.count() + (size_t)a.tl.N * HP;
-    reduce_partials_kernel<HID><<<(int)((n1 + 127) / 128), 128, 0, st>>>(a, l0part, nPartMain, nPartL0, g_params);
+    reduce_partials_kernel<HID><<<(int)((4 * n1 + 127) / 128), 128, 0, st>>>(a, l0part, nPartMain, nPartL0, g_params);
     LMR_LAUNCH_OK();
     const int n2 = HID * (1 + 2 * a.net.ape) + HID;
     finish_w0a_kernel<HID><<<(n2 + 127) / 128, 128, 0, st>>>(a, g_params);

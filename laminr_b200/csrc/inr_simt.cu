@@ -472,14 +472,7 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     LMR_LAUNCH_OK();
     if (a.want_weights) {
         float* l0part = reinterpret_cast<float*>(static_cast<char*>(ws) + wl.l0part);
-        const size_t smem0 = (size_t)L0_CHUNK * (Smem<50>::HP + 2 * nt.pe) * sizeof(float);
-        static size_t smem_set_l0 = 0;
-        if (smem0 > smem_set_l0) {
-            LMR_CUDA_OK(cudaFuncSetAttribute(l0_partial_kernel<50>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-            smem_set_l0 = smem0;
-        }
-        l0_partial_kernel<50><<<wl.gridL0, 256, smem0, st>>>(a, l0part);
-        LMR_LAUNCH_OK();
+        if (int rc = launch_l0_partial<50>(a, l0part, wl.gridL0, st)) return rc;
         if (int rc = launch_finish_weights<50>(a, l0part, wl.gridMain, wl.gridL0, g_params, st)) return rc;
     }
     if (want_aff) {

@@ -972,7 +972,8 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
 
 int backward(const lmr_inr_desc* desc, const float* params, const float* B, const float* auxB, const float* grid, int N, const float* coords,
              int P, const float* coord_shift, const lmr_affine* affine, int D, const float* g_img, float* g_params, float* g_angles,
-             float* g_scalings, float* g_shears, float* g_translation, void* ws, size_t ws_bytes, int precision, cudaStream_t st) {
+             float* g_scalings, float* g_shears, float* g_translation, void* ws, size_t ws_bytes, int precision, cudaStream_t st,
+             const void* fwd_ws, size_t fwd_ws_bytes) {
     Net nt;
     if (int rc = make_net(desc, &nt)) return rc;
     if (int rc = check_tc(nt)) return rc;
@@ -995,7 +996,16 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     a.g_img = g_img;
     a.want_weights = g_params != nullptr, a.want_affine = want_aff;
     a.want_cp = 1;
-    if (int rc = launch_prep<50>(a, st)) return rc;
+    if (fwd_ws != nullptr) {  // the per-step tables of the forward call that produced these images are still valid: no preparation launch
+        const WsLayout wf = ws_layout(nt, tl, false, true);
+        LMR_CHECK_ARG(fwd_ws_bytes >= wf.total, "inr_backward: forward workspace %zu < %zu bytes", fwd_ws_bytes, wf.total);
+        char* fb = static_cast<char*>(const_cast<void*>(fwd_ws));
+        a.alpha = reinterpret_cast<float*>(fb + wf.alpha), a.Avec = reinterpret_cast<float*>(fb + wf.Avec);
+        a.W0cT = reinterpret_cast<float*>(fb + wf.W0cT), a.Cpg = reinterpret_cast<float*>(fb + wf.Cpg);
+        a.betaG = wf.betaG ? reinterpret_cast<float*>(fb + wf.betaG) : nullptr;
+    } else if (int rc = launch_prep<50>(a, st)) {
+        return rc;
+    }
     static const bool tracing = getenv("LMR_TC_TRACE") != nullptr;
     static long long* trace_dev = nullptr;
     if (tracing) {
@@ -1032,11 +1042,7 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     }
     if (a.want_weights) {
         float* l0part = reinterpret_cast<float*>(static_cast<char*>(ws) + wl.l0part);
-        const size_t smem0 = (size_t)L0_CHUNK * (SHP + 2 * nt.pe) * sizeof(float);
-        static size_t c2 = 0;
-        if (int rc = set_smem(l0_partial_kernel<50>, smem0, &c2)) return rc;
-        l0_partial_kernel<50><<<wl.gridL0, 256, smem0, st>>>(a, l0part);
-        LMR_LAUNCH_OK();
+        if (int rc = launch_l0_partial<50>(a, l0part, wl.gridL0, st)) return rc;
         if (int rc = launch_finish_weights<50>(a, l0part, wl.gridMain, wl.gridL0, g_params, st)) return rc;
     }
     if (want_aff) {

@@ -51,8 +51,7 @@ __device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int ta
     if (threadIdx.x == 0) {
         __threadfence();
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-        while ((int)(ld_acquire(counter) - target) < 0) {
-        }
+        while ((int)(ld_acquire(counter) - target) < 0) __nanosleep(32);
         __threadfence();
     }
     __syncthreads();
@@ -67,11 +66,29 @@ __device__ __forceinline__ float clamp_pass(float y, int has_min, float pmin, in
     return ((!has_min || y >= pmin) && (!has_max || y <= pmax)) ? 1.f : 0.f;  // torch.clamp backward: inclusive
 }
 
-// one warp sums `count` values spaced `stride` apart in a fixed order (lane partials, then a shuffle tree): deterministic
-__device__ __forceinline__ float warp_strided_sum(const float* src, int count, size_t stride, int lane) {
-    float s0 = 0.f;
-    for (int i = lane; i < count; i += 32) s0 += __ldcg(src + (size_t)i * stride);  // written by other CTAs of this launch: bypass L1
-    return warp_sum(s0);
+// 8 consecutive lanes sum `count` values spaced `stride` apart in a fixed order (all loads of a lane in flight together, then a shuffle
+// tree): deterministic.  The values were written by other CTAs of this launch: the loads bypass L1.
+constexpr int GRP = 8, MAXLD = 20;  // up to GRP * MAXLD = 160 partials (grid <= 148 CTAs)
+__device__ __forceinline__ float group_strided_sum(const float* src, int count, size_t stride, int lane) {
+    const int sub = lane & (GRP - 1);
+    float v[MAXLD];
+#pragma unroll
+    for (int u = 0; u < MAXLD; ++u) {
+        const int i = sub + GRP * u;
+        v[u] = i < count ? __ldcg(src + (size_t)i * stride) : 0.f;
+    }
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int u = 0; u < MAXLD; u += 2) s0 += v[u], s1 += v[u + 1];
+    s0 += s1;
+    const unsigned gmask = 0xffu << (lane & ~(GRP - 1));  // only this 8-lane group takes part (other groups of the warp may be idle)
+    s0 += __shfl_xor_sync(gmask, s0, 1);
+    s0 += __shfl_xor_sync(gmask, s0, 2);
+    s0 += __shfl_xor_sync(gmask, s0, 4);
+    return s0;
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
 
 __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
@@ -89,14 +106,17 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     float* sd = mk + PSP;              // [N]
     float* mu = sd + N;                // [N]
     float* coef = mu + N;              // [N]  g_act * 1/2 * elu'(rmax)
-    float* dotu = coef + N;            // [N][2]
-    int* amax = reinterpret_cast<int*>(dotu + 2 * N);  // [N]
+    float* dotu = coef + N;            // [NC][2] per (image, channel) row
+    float* dotn = dotu + 2 * NC;       // [N][2]  per image, over all CTAs
+    int* amax = reinterpret_cast<int*>(dotn + 2 * N);  // [N]
     float* fin = reinterpret_cast<float*>(amax + N);   // [N*F + N*N]
     float* cosm = fin + N * F + N * N; // [N][N]
     float* Sm = cosm + N * N;          // [N][N]
     float* rho = Sm + N * N;           // [N]
     float* rowc = rho + N;             // [N][4]
     float* Ks = rowc + 4 * N;          // [N][N]
+    float* posS = Ks + N * N;          // [N][N]
+    float* negS = posS + N * N;        // [N][N]
     __shared__ float scratch[40];
     const unsigned int epoch = ld_acquire(p.sync + 1);
     const unsigned int nbar = p.mode == LMR_CONSTRAIN_NORM ? 4u : 5u;
@@ -106,63 +126,74 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
         grid_sync(p.sync, (epoch * nbar + bar_no) * (unsigned int)G);
     };
 
-    // ---- phase 0: load the slice, per-image statistics
-    for (int i = t; i < NC * PS; i += NT) {
-        const int r = i / PS, e = i % PS;
-        xs[r * PSP + e] = e < np ? p.x[(size_t)r * HW + p0 + e] : 0.f;
+    // ---- phase 0: load the slice (every global read in flight at once: cp.async, 4 bytes each), per-image statistics
+#pragma unroll 1
+    for (int r = warp; r < NC; r += NW) {
+        const float* src = p.x + (size_t)r * HW + p0;
+        for (int e = lane; e < PS; e += 32) {
+            if (e < np) cp_async4(xs + r * PSP + e, src + e);
+            else xs[r * PSP + e] = 0.f;
+        }
     }
-    for (int i = t; i < F * PS; i += NT) {
-        const int f = i / PS, e = i % PS;
-        ws[f * PSP + e] = e < np ? __ldg(p.bank + (size_t)f * HW + p0 + e) : 0.f;
+#pragma unroll 1
+    for (int f = warp; f < F; f += NW) {
+        const float* src = p.bank + (size_t)f * HW + p0;
+        for (int e = lane; e < PS; e += 32) {
+            if (e < np) cp_async4(ws + f * PSP + e, src + e);
+            else ws[f * PSP + e] = 0.f;
+        }
     }
-    for (int e = t; e < PS; e += NT) mk[e] = e < np ? p.mask[p0 + e] : 0.f;
+    for (int e = t; e < PS; e += NT) {
+        if (e < np) cp_async4(mk + e, p.mask + p0 + e);
+        else mk[e] = 0.f;
+    }
+    for (int i = t; i < N * N; i += NT) cp_async4(posS + i, p.pos + i), cp_async4(negS + i, p.neg + i);
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (p.mode == LMR_CONSTRAIN_NORM) {
         for (int n = warp; n < N; n += NW) {
             float acc = 0.f;
-            for (int i = lane; i < C * PS; i += 32) {
-                const int c = i / PS, e = i % PS;
-                const float u = xs[(n * C + c) * PSP + e] - p.mean;
-                acc += e < np ? u * u : 0.f;
-            }
+            for (int c = 0; c < C; ++c)
+                for (int e = lane; e < np; e += 32) {
+                    const float u = xs[(n * C + c) * PSP + e] - p.mean;
+                    acc = fmaf(u, u, acc);
+                }
             acc = warp_sum(acc);
             if (lane == 0) p.part_a[(size_t)b * N + n] = acc;
         }
         barrier();
-        for (int n = warp; n < N; n += NW) {
-            const float tot = warp_strided_sum(p.part_a + n, G, N, lane);
-            if (lane == 0) sd[n] = sqrtf(tot), mu[n] = 0.f;
+        for (int n = t / GRP; n < N; n += NT / GRP) {
+            const float tot = group_strided_sum(p.part_a + n, G, N, lane);
+            if ((lane & (GRP - 1)) == 0) sd[n] = sqrtf(tot), mu[n] = 0.f;
         }
     } else {
         for (int n = warp; n < N; n += NW) {
             float acc = 0.f;
-            for (int i = lane; i < C * PS; i += 32) {
-                const int c = i / PS, e = i % PS;
-                acc += e < np ? xs[(n * C + c) * PSP + e] : 0.f;
-            }
+            for (int c = 0; c < C; ++c)
+                for (int e = lane; e < np; e += 32) acc += xs[(n * C + c) * PSP + e];
             acc = warp_sum(acc);
             if (lane == 0) p.part_a[(size_t)b * N + n] = acc;
         }
         barrier();
-        for (int n = warp; n < N; n += NW) {
-            const float tot = warp_strided_sum(p.part_a + n, G, N, lane);
-            if (lane == 0) mu[n] = tot / (float)(C * HW);
+        for (int n = t / GRP; n < N; n += NT / GRP) {
+            const float tot = group_strided_sum(p.part_a + n, G, N, lane);
+            if ((lane & (GRP - 1)) == 0) mu[n] = tot / (float)(C * HW);
         }
         __syncthreads();
         for (int n = warp; n < N; n += NW) {
             float acc = 0.f;
-            for (int i = lane; i < C * PS; i += 32) {
-                const int c = i / PS, e = i % PS;
-                const float u = xs[(n * C + c) * PSP + e] - mu[n];
-                acc += e < np ? u * u : 0.f;
-            }
+            for (int c = 0; c < C; ++c)
+                for (int e = lane; e < np; e += 32) {
+                    const float u = xs[(n * C + c) * PSP + e] - mu[n];
+                    acc = fmaf(u, u, acc);
+                }
             acc = warp_sum(acc);
             if (lane == 0) p.part_c[(size_t)b * 2 * N + n] = acc;
         }
         barrier();
-        for (int n = warp; n < N; n += NW) {
-            const float tot = warp_strided_sum(p.part_c + n, G, 2 * N, lane);
-            if (lane == 0) sd[n] = sqrtf(tot / (float)(C * HW - 1));  // unbiased (Tensor.std default)
+        for (int n = t / GRP; n < N; n += NT / GRP) {
+            const float tot = group_strided_sum(p.part_c + n, G, 2 * N, lane);
+            if ((lane & (GRP - 1)) == 0) sd[n] = sqrtf(tot / (float)(C * HW - 1));  // unbiased (Tensor.std default)
         }
     }
     __syncthreads();
@@ -170,64 +201,79 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
         for (int n = t; n < N; n += NT) p.stats[2 * n] = sd[n], p.stats[2 * n + 1] = mu[n];
 
     // ---- phase 1: z (written out), sum_c z, masked z; partial responses and partial gram
-    for (int i = t; i < NC * PS; i += NT) {
-        const int r = i / PS, e = i % PS, n = r / C;
-        float y;
-        if (p.mode == LMR_CONSTRAIN_NORM) y = (xs[r * PSP + e] - p.mean) / (sd[n] + p.eps_con) * p.target + p.mean;
-        else y = p.target * (xs[r * PSP + e] - mu[n]) / (sd[n] + p.eps_con) + p.mean;
-        if (p.has_min) y = fmaxf(y, p.pmin);
-        if (p.has_max) y = fminf(y, p.pmax);
-        if (e < np) {
-            p.z[(size_t)r * HW + p0 + e] = y;
-            xm[r * PSP + e] = masked_value(y, mk[e], p.c0, p.g1, p.g2);
-            gy[r * PSP + e] = y;  // z, until phase 3 overwrites it
-        } else {
-            xm[r * PSP + e] = 0.f, gy[r * PSP + e] = 0.f;
+#pragma unroll 1
+    for (int r = warp; r < NC; r += NW) {
+        const int n = r / C;
+        const float sdn = sd[n] + p.eps_con, mun = mu[n];
+        float* zdst = p.z + (size_t)r * HW + p0;
+        for (int e = lane; e < PS; e += 32) {
+            float y;
+            if (p.mode == LMR_CONSTRAIN_NORM) y = (xs[r * PSP + e] - p.mean) / sdn * p.target + p.mean;
+            else y = p.target * (xs[r * PSP + e] - mun) / sdn + p.mean;
+            if (p.has_min) y = fmaxf(y, p.pmin);
+            if (p.has_max) y = fminf(y, p.pmax);
+            if (e < np) {
+                zdst[e] = y;
+                xm[r * PSP + e] = masked_value(y, mk[e], p.c0, p.g1, p.g2);
+                gy[r * PSP + e] = y;  // z, until phase 3 overwrites it
+            } else {
+                xm[r * PSP + e] = 0.f, gy[r * PSP + e] = 0.f;
+            }
         }
     }
     __syncthreads();
-    for (int i = t; i < N * PS; i += NT) {
-        const int n = i / PS, e = i % PS;
-        float v = 0.f;
-        for (int c = 0; c < C; ++c) v += gy[(n * C + c) * PSP + e];
-        zs[n * PSP + e] = v;
-    }
+#pragma unroll 1
+    for (int n = warp; n < N; n += NW)
+        for (int e = lane; e < PS; e += 32) {
+            float v = 0.f;
+            for (int c = 0; c < C; ++c) v += gy[(n * C + c) * PSP + e];
+            zs[n * PSP + e] = v;
+        }
     __syncthreads();
     {
         float* outR = p.part_b + (size_t)b * (N * F + N * N);
-        for (int i = t; i < N * F; i += NT) {
-            const int n = i / F, f = i % F;
-            const float* a = zs + n * PSP;
-            const float* w = ws + f * PSP;
-            float s0 = 0.f, s1 = 0.f;
-            int e = 0;
-            for (; e + 1 < PS; e += 2) s0 = fmaf(a[e], w[e], s0), s1 = fmaf(a[e + 1], w[e + 1], s1);
-            if (e < PS) s0 = fmaf(a[e], w[e], s0);
-            outR[i] = s0 + s1;
-        }
         float* outG = outR + N * F;
-        for (int pr = t; pr < N * N; pr += NT) {
-            const int i = pr / N, j = pr % N;
-            if (j < i) continue;
-            float s0 = 0.f, s1 = 0.f;
-            for (int c = 0; c < C; ++c) {
-                const float* a = xm + (i * C + c) * PSP;
-                const float* w = xm + (j * C + c) * PSP;
+        // responses: warp -> image n, lanes -> filters (row stride PSP is odd: conflict-free)
+#pragma unroll 1
+        for (int n = warp; n < N; n += NW) {
+            const float* a = zs + n * PSP;
+#pragma unroll 1
+            for (int f = lane; f < F; f += 32) {
+                const float* w = ws + f * PSP;
+                float s0 = 0.f, s1 = 0.f;
                 int e = 0;
+#pragma unroll 4
                 for (; e + 1 < PS; e += 2) s0 = fmaf(a[e], w[e], s0), s1 = fmaf(a[e + 1], w[e + 1], s1);
                 if (e < PS) s0 = fmaf(a[e], w[e], s0);
+                outR[n * F + f] = s0 + s1;
             }
-            outG[i * N + j] = s0 + s1;
-            outG[j * N + i] = s0 + s1;
+        }
+        // gram: warp -> image i, lanes -> images j >= i
+#pragma unroll 1
+        for (int i = warp; i < N; i += NW) {
+#pragma unroll 1
+            for (int j = i + lane; j < N; j += 32) {
+                float s0 = 0.f, s1 = 0.f;
+                for (int c = 0; c < C; ++c) {
+                    const float* a = xm + (i * C + c) * PSP;
+                    const float* w = xm + (j * C + c) * PSP;
+                    int e = 0;
+#pragma unroll 4
+                    for (; e + 1 < PS; e += 2) s0 = fmaf(a[e], w[e], s0), s1 = fmaf(a[e + 1], w[e + 1], s1);
+                    if (e < PS) s0 = fmaf(a[e], w[e], s0);
+                }
+                outG[i * N + j] = s0 + s1;
+                outG[j * N + i] = s0 + s1;
+            }
         }
     }
     barrier();
     // ---- phase 2: two-level combine of the partials (value v is summed by CTA v % G), then everybody reads the totals
     {
         const int nval = N * F + N * N;
-        for (int v = b + G * warp; v < nval; v += G * NW) {
-            const float tot = warp_strided_sum(p.part_b + v, G, (size_t)nval, lane);
-            if (lane == 0) p.fin[v] = tot;
+        for (int v = b + G * (t / GRP); v < nval; v += G * (NT / GRP)) {
+            const float tot = group_strided_sum(p.part_b + v, G, (size_t)nval, lane);
+            if ((lane & (GRP - 1)) == 0) p.fin[v] = tot;
         }
     }
     barrier();
@@ -276,8 +322,8 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     for (int i = t; i < N; i += NT) {
         float ps = 0.f, np_ = 0.f, ns = 0.f, nn = 0.f;
         for (int j = 0; j < N; ++j) {
-            ps = fmaf(Sm[i * N + j], p.pos[i * N + j], ps), np_ += p.pos[i * N + j];
-            ns = fmaf(Sm[i * N + j], p.neg[i * N + j], ns), nn += p.neg[i * N + j];
+            ps = fmaf(Sm[i * N + j], posS[i * N + j], ps), np_ += posS[i * N + j];
+            ns = fmaf(Sm[i * N + j], negS[i * N + j], ns), nn += negS[i * N + j];
         }
         const float num = (ps == 0.f ? 0.f : ps / np_) + p.eps_clr;
         const float den = (ns == 0.f ? 0.f : ns / nn) + p.eps_clr;
@@ -294,7 +340,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     __syncthreads();
     for (int pr = t; pr < N * N; pr += NT) {
         const int i = pr / N;
-        Sm[pr] = (p.pos[pr] * rowc[i * 4] - p.neg[pr] * rowc[i * 4 + 1]) * Sm[pr] / p.T;  // Gamma_ij = A_ij S_ij / T
+        Sm[pr] = (posS[pr] * rowc[i * 4] - negS[pr] * rowc[i * 4 + 1]) * Sm[pr] / p.T;  // Gamma_ij = A_ij S_ij / T
     }
     __syncthreads();
     for (int i = t; i < N; i += NT) {
@@ -313,52 +359,58 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     __syncthreads();
 
     // ---- phase 3: g_z = response backward + contrastive backward; gradient wrt the pre-clamp image; per-image sums for the projection
-    for (int i = t; i < NC * PS; i += NT) {
-        const int r = i / PS, e = i % PS, n = r / C, c = r % C;
-        float v = 0.f;
-        if (e < np) {
-            const float m = mk[e];
-            float acc = 0.f;
-            for (int jn = 0; jn < N; ++jn) acc = fmaf(Ks[n * N + jn], xm[(jn * C + c) * PSP + e], acc);
-            const float gz = coef[n] * ws[amax[n] * PSP + e] + g_reg * (p.g1 * m * p.g2) * acc;
-            float u, y;
-            if (p.mode == LMR_CONSTRAIN_NORM) u = xs[r * PSP + e] - p.mean, y = u / (sd[n] + p.eps_con) * p.target + p.mean;
-            else u = xs[r * PSP + e] - mu[n], y = p.target * u / (sd[n] + p.eps_con) + p.mean;
-            v = gz * clamp_pass(y, p.has_min, p.pmin, p.has_max, p.pmax);
-        }
-        gy[r * PSP + e] = v;
-    }
-    __syncthreads();
-    for (int n = warp; n < N; n += NW) {
+#pragma unroll 1
+    for (int r = warp; r < NC; r += NW) {
+        const int n = r / C, c = r % C;
+        const float sdn = sd[n] + p.eps_con, mun = p.mode == LMR_CONSTRAIN_NORM ? p.mean : mu[n];
+        const float cf = coef[n];
+        const float* wsel = ws + amax[n] * PSP;
         float a0 = 0.f, a1 = 0.f;
-        for (int i = lane; i < C * PS; i += 32) {
-            const int c = i / PS, e = i % PS;
-            const float g = gy[(n * C + c) * PSP + e];
-            const float u = xs[(n * C + c) * PSP + e] - (p.mode == LMR_CONSTRAIN_NORM ? p.mean : mu[n]);
-            a0 += g;
-            a1 = fmaf(g, e < np ? u : 0.f, a1);
+        for (int e = lane; e < PS; e += 32) {
+            float v = 0.f;
+            if (e < np) {
+                const float m = mk[e];
+                float acc = 0.f;
+#pragma unroll 4
+                for (int jn = 0; jn < N; ++jn) acc = fmaf(Ks[n * N + jn], xm[(jn * C + c) * PSP + e], acc);
+                const float gz = cf * wsel[e] + g_reg * (p.g1 * m * p.g2) * acc;
+                const float u = xs[r * PSP + e] - mun;
+                float y;
+                if (p.mode == LMR_CONSTRAIN_NORM) y = u / sdn * p.target + p.mean;
+                else y = p.target * u / sdn + p.mean;
+                v = gz * clamp_pass(y, p.has_min, p.pmin, p.has_max, p.pmax);
+                a0 += v;
+                a1 = fmaf(v, u, a1);
+            }
+            gy[r * PSP + e] = v;
         }
         a0 = warp_sum(a0), a1 = warp_sum(a1);
-        if (lane == 0) p.part_c[(size_t)b * 2 * N + n] = a0, p.part_c[(size_t)b * 2 * N + N + n] = a1;
+        if (lane == 0) dotu[2 * r] = a0, dotu[2 * r + 1] = a1;  // per (image, channel) row; combined over channels below
+    }
+    __syncthreads();
+    for (int n = t; n < N; n += NT) {
+        float a0 = 0.f, a1 = 0.f;
+        for (int c = 0; c < C; ++c) a0 += dotu[2 * (n * C + c)], a1 += dotu[2 * (n * C + c) + 1];
+        p.part_c[(size_t)b * 2 * N + n] = a0, p.part_c[(size_t)b * 2 * N + N + n] = a1;
     }
     barrier();
-    for (int n = warp; n < N; n += NW) {
-        const float a0 = warp_strided_sum(p.part_c + n, G, 2 * N, lane);
-        const float a1 = warp_strided_sum(p.part_c + N + n, G, 2 * N, lane);
-        if (lane == 0) dotu[2 * n] = a0, dotu[2 * n + 1] = a1;
+    for (int n = t / GRP; n < 2 * N; n += NT / GRP) {  // part_c rows are [a0[0..N) | a1[0..N)]
+        const float tot = group_strided_sum(p.part_c + n, G, 2 * N, lane);
+        if ((lane & (GRP - 1)) == 0) dotn[n < N ? 2 * n : 2 * (n - N) + 1] = tot;
     }
     __syncthreads();
     // ---- phase 4: g_x   NORM: k gy - target dot / ((s+eps)^2 s) u ;  STD: k (gy - mean(gy)) - target dot / ((sd+eps)^2 (n-1) sd) (x-mu)
-    for (int i = t; i < NC * PS; i += NT) {
-        const int r = i / PS, e = i % PS, n = r / C;
-        if (e >= np) continue;
+#pragma unroll 1
+    for (int r = warp; r < NC; r += NW) {
+        const int n = r / C;
         const float s_ = sd[n];
         const float k = p.target / (s_ + p.eps_con);
         const float denom = (s_ + p.eps_con) * (s_ + p.eps_con) * s_ * (p.mode == LMR_CONSTRAIN_NORM ? 1.f : (float)(C * HW - 1));
-        const float c2 = p.target * dotu[2 * n + 1] / denom;
-        const float gmean = p.mode == LMR_CONSTRAIN_NORM ? 0.f : dotu[2 * n] / (float)(C * HW);
-        const float u = xs[r * PSP + e] - (p.mode == LMR_CONSTRAIN_NORM ? p.mean : mu[n]);
-        p.g_x[(size_t)r * HW + p0 + e] = k * (gy[r * PSP + e] - gmean) - c2 * u;
+        const float c2 = p.target * dotn[2 * n + 1] / denom;
+        const float gmean = p.mode == LMR_CONSTRAIN_NORM ? 0.f : dotn[2 * n] / (float)(C * HW);
+        const float mun = p.mode == LMR_CONSTRAIN_NORM ? p.mean : mu[n];
+        float* dst = p.g_x + (size_t)r * HW + p0;
+        for (int e = lane; e < np; e += 32) dst[e] = k * (gy[r * PSP + e] - gmean) - c2 * (xs[r * PSP + e] - mun);
     }
     // the epoch word is only written here, after every CTA has passed the last barrier (all of them read it at kernel start)
     if (b == 0 && t == 0) {
@@ -369,7 +421,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
 
 static size_t smem_floats(int N, int C, int F, int PS) {
     const int PSP = PS | 1, NC = N * C;
-    return (size_t)3 * NC * PSP + (size_t)F * PSP + (size_t)N * PSP + PSP + 6 * (size_t)N + (size_t)N /*amax*/ + (size_t)N * F + N * N + 3 * (size_t)N * N + 5 * (size_t)N + 16;
+    return (size_t)3 * NC * PSP + (size_t)F * PSP + (size_t)N * PSP + PSP + 6 * (size_t)N + 2 * (size_t)NC + (size_t)N /*amax*/ + (size_t)N * F + N * N + 5 * (size_t)N * N + 5 * (size_t)N + 16;
 }
 
 struct Plan {

@@ -401,6 +401,34 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }
 __global__ void counter_inc_kernel(int* c) { c[0] += 1; }
 
+// one-launch variant: every CTA reads the step counter at its start; the LAST CTA to finish (ticket in step[1]) publishes the
+// incremented counter and re-arms the ticket.  step: int32[2] = {steps taken, ticket (0 between launches)}.
+__global__ void __launch_bounds__(256) adam_ticket_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                          int n, float lr, float b1, float b2, float eps, int* __restrict__ step) {
+    const int t = *reinterpret_cast<volatile int*>(step) + 1;
+    const float bc1 = 1.f - powf(b1, (float)t);
+    const float bc2 = 1.f - powf(b2, (float)t);
+    const float step_size = lr / bc1;
+    const float bc2_sqrt = sqrtf(bc2);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float gi = g[i];
+        const float mi = m[i] + (gi - m[i]) * (1.f - b1);  // lerp_
+        const float vi = v[i] * b2 + (1.f - b2) * gi * gi;  // mul_ + addcmul_
+        m[i] = mi, v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - step_size * (mi / denom);  // addcdiv_
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(step + 1, 1) == (int)gridDim.x - 1) {
+            step[1] = 0;
+            step[0] = t;
+        }
+    }
+}
+
 // ===============================================================================================================
 // Batched MEI gradient ascent (reference featurevis/core.py:54-136 with SGD, laminr/utils/mei.py:33-59)
 // One CTA per neuron; the image lives in shared memory for all iterations; filters stream from L2/HBM.
@@ -646,7 +674,12 @@ extern "C" int lmr_adam_step(float* p, const float* g, float* m, float* v, int n
                              void* stream) {
     LMR_CHECK_ARG(n >= 1 && step != nullptr, "adam: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int blocks = n < 256 * 1024 ? (n + 255) / 256 : 1024;
+    if (n <= 256 * 1024) {  // one thread per element, one launch
+        adam_ticket_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, step);
+        LMR_LAUNCH_OK();
+        return 0;
+    }
+    const int blocks = 1024;
     adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, step);
     LMR_LAUNCH_OK();
     counter_inc_kernel<<<1, 1, 0, st>>>(step);

@@ -57,7 +57,7 @@ class LearnStepper:
         self.g_reg = torch.full((1,), -float(reg_scale), **f32)  # d loss / d reg = -reg_scale (host float, changes between epochs)
         self.g_flat = torch.zeros_like(self.flat)
         self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
-        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.step_count = torch.zeros(2, dtype=torch.int32, device=dev)  # [steps taken, ticket scratch]
         d = template._desc
         self.ws_fwd = _ws(lib.lmr_inr_forward_workspace_bytes(C.byref(d), N, P, 1), dev)
         self.ws_bwd = _ws(lib.lmr_inr_backward_workspace_bytes(C.byref(d), N, P, 1), dev)
@@ -69,7 +69,7 @@ class LearnStepper:
         self.bank = model.packed_filters[int(neuron_idx), :int(model.nfilt[int(neuron_idx)].item())].contiguous()
         self.loss_buf = torch.zeros(1, **f32)
         self.ws_obj = ops.learn_objective_workspace(N, Cc, P, self.bank.shape[0], dev)
-        self.kernels_per_step = 9 if self.ws_obj is not None else 20
+        self.kernels_per_step = 8 if self.ws_obj is not None else 19
 
     def set_reg_scale(self, reg_scale):
         self.g_reg.fill_(-float(reg_scale))
@@ -94,7 +94,7 @@ class LearnStepper:
                                     self.reg, self.loss_buf, self.g_x, self.ws_obj, stats=self.stats, rmax=self.rmax.view(-1), argmax=self.argmax.view(-1),
                                     K=self.K)
             ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, self.g_x.view(1, N, Cc, P), want_params=True,
-                                 precision=self.precision, workspace=self.ws_bwd, g_params=self.g_flat)
+                                 precision=self.precision, workspace=self.ws_bwd, g_params=self.g_flat, forward_workspace=self.ws_fwd)
             ops.raw_adam_step(self.flat, self.g_flat, self.m, self.v, self.step_count, lr=self.lr)
             return
         self._forward()
@@ -174,7 +174,7 @@ class MatchStepper:
         self.grads = [torch.zeros_like(p) for p in self.params]
         self.m = [torch.zeros_like(p) for p in self.params]
         self.v = [torch.zeros_like(p) for p in self.params]
-        self.steps = [torch.zeros(1, dtype=torch.int32, device=dev) for _ in self.params]
+        self.steps = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in self.params]
         d = template._desc
         self.ws_fwd = _ws(lib.lmr_inr_forward_workspace_bytes(C.byref(d), N, P, D), dev)
         self.ws_bwd = _ws(lib.lmr_inr_backward_workspace_bytes(C.byref(d), N, P, D), dev)
@@ -202,7 +202,7 @@ class MatchStepper:
                               out=self.g_x.view(D * N, Cc, P), workspace=self.ws_con)
         ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, self._affine(), self.g_x.view(D, N, Cc, P),
                              want_params=False, want_affine=True, precision=self.precision, workspace=self.ws_bwd,
-                             g_affine=(self.grads[0], self.grads[1], self.grads[2], self.grads[3].view(D, 2)))
+                             g_affine=(self.grads[0], self.grads[1], self.grads[2], self.grads[3].view(D, 2)), forward_workspace=self.ws_fwd)
         for p, g, m, v, s, tr in zip(self.params, self.grads, self.m, self.v, self.steps, self.trainable):
             if tr:
                 ops.raw_adam_step(p.data, g, m, v, s, lr=self.lr)

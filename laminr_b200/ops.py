@@ -108,8 +108,9 @@ def raw_inr_forward(desc, params, B, auxB, grid, coords, coord_shift, affine, ou
 
 
 def raw_inr_backward(desc, params, B, auxB, grid, coords, coord_shift, affine, g_img, want_params=True, want_affine=False,
-                     precision=None, workspace=None, g_params=None, g_affine=None):
-    """-> (g_params flat | None, (g_angles, g_scalings, g_shears, g_translation) | None)."""
+                     precision=None, workspace=None, g_params=None, g_affine=None, forward_workspace=None):
+    """-> (g_params flat | None, (g_angles, g_scalings, g_shears, g_translation) | None).
+    forward_workspace: workspace of the raw_inr_forward call on the same inputs (its per-step tables are reused: one launch less)."""
     lib = _lib.load()
     _require_cuda(params, g_img)
     N, P = grid.numel(), coords.shape[0]
@@ -124,11 +125,13 @@ def raw_inr_backward(desc, params, B, auxB, grid, coords, coord_shift, affine, g
         workspace = _workspace(lib.lmr_inr_backward_workspace_bytes(C.byref(desc), N, P, D), dev)
     aff = affine.struct() if affine is not None else None
     ga = g_affine if want_affine else (None, None, None, None)
-    check(lib.lmr_inr_backward(
-        C.byref(desc), _ptr(params), _ptr(B), _ptr(auxB), _ptr(grid), N, _ptr(coords), P, _ptr(coord_shift),
-        C.byref(aff) if aff is not None else None, D, _ptr(_f32c(g_img)), _ptr(g_params if want_params else None),
-        _ptr(ga[0]), _ptr(ga[1]), _ptr(ga[2]), _ptr(ga[3]), _ptr(workspace), workspace.numel(), precision_code(precision), _stream(),
-    ))
+    common = (C.byref(desc), _ptr(params), _ptr(B), _ptr(auxB), _ptr(grid), N, _ptr(coords), P, _ptr(coord_shift),
+              C.byref(aff) if aff is not None else None, D, _ptr(_f32c(g_img)), _ptr(g_params if want_params else None),
+              _ptr(ga[0]), _ptr(ga[1]), _ptr(ga[2]), _ptr(ga[3]), _ptr(workspace), workspace.numel())
+    if forward_workspace is not None:
+        check(lib.lmr_inr_backward_after_forward(*common, _ptr(forward_workspace), forward_workspace.numel(), precision_code(precision), _stream()))
+    else:
+        check(lib.lmr_inr_backward(*common, precision_code(precision), _stream()))
     return (g_params if want_params else None), (g_affine if want_affine else None)
 
 
@@ -360,8 +363,11 @@ def raw_learn_objective(mode, x, target, mean, pmin, pmax, eps_con, bank, act_ep
 # Adam / MEI
 # ------------------------------------------------------------------------------------------------------------------
 def raw_adam_step(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    """step: int32[2] device tensor {steps taken, scratch (zero)}; incremented by the call."""
     lib = _lib.load()
     _require_cuda(p, g, m, v, step)
+    if step.numel() < 2 or step.dtype != torch.int32:
+        raise ValueError("raw_adam_step: `step` must be an int32 tensor with 2 elements ([steps taken, zero-initialised scratch])")
     check(lib.lmr_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(b1), float(b2), float(eps), _ptr(step), _stream()))
 
 

@@ -90,7 +90,7 @@ def test_fused_learn_trajectory_matches_reference(L, use_graph):
     np.testing.assert_allclose(losses, d["losses"], rtol=1e-3)
     np.testing.assert_allclose(means, d["means"], rtol=1e-3)
     assert max(abs(a - b) / abs(b) for a, b in zip(losses, d["losses"])) < 2e-4  # what fp32 achieves
-    assert st.step_count.item() == 30
+    assert st.step_count[0].item() == 30
     dW, db = split_flat(st.flat.cpu().numpy(), d, prefix="final_")
     for l in range(5):
         assert relerr(dW[l], d[f"final_W{l}"]) < 1e-2, l
