@@ -2,6 +2,7 @@
 // descriptors, the prep kernels (latent encoding, separable layer-0 pieces), the affine coordinate transform, the layer-0
 // weight-gradient kernel and the deterministic final reductions.  Global workspace arrays use a row stride of SHP = 52.
 #pragma once
+#include <cuda_bf16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -56,6 +57,7 @@ struct Args {
     float* Avec;   // [N, HP]
     float* W0cT;   // [2*pe, HP]
     float* Cpg;    // [D*P, HP]  layer-0 coordinate part Cp[d,p][o] = sum_k beta[d,p][k] W0c[o][k]   (tensor-core path)
+    unsigned char* wtimg;  // (nl-1) x 16 KB: split-bf16 (hi | lo) K-major core-matrix images of the hidden weight tiles (tensor-core path)
     float* betaG;  // [D*P, 2*pe] sin/cos(coords.B) (tensor-core path, D == 1: consumed by the layer-0 weight-gradient kernel), else null
     int want_cp;
     int ppb;       // pixels per prep / l0 block
@@ -192,6 +194,32 @@ __global__ void __launch_bounds__(256) prep_all_kernel(Args a) {
                 }
             }
             for (int i = t; i < nb * (HP - HID); i += blockDim.x) a.W0cT[(size_t)(i / (HP - HID)) * HP + HID + i % (HP - HID)] = 0.f;
+        }
+    } else if (a.want_cp && bid >= N + 1 + (a.tl.D * a.tl.P + a.ppb - 1) / a.ppb) {
+        // weight-tile images: W_l[o][k] for k < HID, column HID = bias b_l[o], entry [HID][HID] = 20 (regenerates the constant-1 feature
+        // through tanh), rest 0; bf16 hi and lo = bf16(v - hi) halves in the no-swizzle K-major core-matrix layout of a [64 x 64] tile.
+        constexpr int U = 4;
+        const int wb = bid - (N + 1 + (a.tl.D * a.tl.P + a.ppb - 1) / a.ppb);
+        float v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = wb * (U * 256) + u * 256 + t, l = e / 4096 + 1, i = e % 4096, o = i / 64, k = i % 64;
+            v[u] = 0.f;
+            if (l < nt.nl) {
+                if (o < HID) v[u] = k < HID ? a.params[nt.offW(l) + o * HID + k] : (k == HID ? a.params[nt.offb(l) + o] : 0.f);
+                else if (o == HID && k == HID) v[u] = 20.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = wb * (U * 256) + u * 256 + t, l = e / 4096 + 1, i = e % 4096, o = i / 64, k = i % 64;
+            if (l < nt.nl) {
+                const __nv_bfloat16 hi = __float2bfloat16(v[u]);
+                const __nv_bfloat16 lo = __float2bfloat16(v[u] - __bfloat162float(hi));
+                unsigned char* dst = a.wtimg + (size_t)(l - 1) * 16384 + ((o & 7) * 16 + (o >> 3) * 128 + (k >> 3) * 1024) + (k & 7) * 2;
+                *reinterpret_cast<__nv_bfloat16*>(dst) = hi;
+                *reinterpret_cast<__nv_bfloat16*>(dst + 8192) = lo;
+            }
         }
     } else {
         // pixels [q0, q0 + nq): beta (kept k-major in shared memory: 4 pixels per float4), then a register-blocked 4 pixel x 4 output GEMM.
@@ -491,7 +519,7 @@ static __global__ void finish_affine_kernel(Args a, float* g_angles, float* g_sc
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 struct WsLayout {
-    size_t alpha, Avec, W0cT, Cpg, betaG, G0, partials, l0part, affpart, dAred, total;
+    size_t alpha, Avec, W0cT, wtimg, Cpg, betaG, G0, partials, l0part, affpart, dAred, total;
     int gridMain, gridL0, ppb;
 };
 
@@ -507,6 +535,7 @@ static inline WsLayout ws_layout(const Net& nt, const Tiling& tl, bool bwd, bool
     w.alpha = take((size_t)tl.N * 2 * nt.ape);
     w.Avec = take((size_t)tl.N * HP);
     w.W0cT = take((size_t)2 * nt.pe * HP);
+    w.wtimg = want_cp ? take((size_t)(nt.nl - 1) * 16384 / 4) : 0;
     w.Cpg = want_cp ? take((size_t)tl.D * tl.P * HP) : 0;
     w.betaG = (want_cp && tl.D == 1) ? take((size_t)tl.P * 2 * nt.pe) : 0;  // identical prefix in the forward and backward layouts
     w.gridMain = tl.numTiles < num_sms() ? tl.numTiles : num_sms();
@@ -555,6 +584,7 @@ static inline int fill_args(Args& a, const Net& nt, const Tiling& tl, const floa
     a.alpha = reinterpret_cast<float*>(base + wl.alpha);
     a.Avec = reinterpret_cast<float*>(base + wl.Avec);
     a.W0cT = reinterpret_cast<float*>(base + wl.W0cT);
+    a.wtimg = reinterpret_cast<unsigned char*>(base + wl.wtimg);
     a.Cpg = reinterpret_cast<float*>(base + wl.Cpg);
     a.betaG = wl.betaG ? reinterpret_cast<float*>(base + wl.betaG) : nullptr;
     a.want_cp = 0;
@@ -580,7 +610,8 @@ static int launch_prep(const Args& a, cudaStream_t st) {
         LMR_CUDA_OK(cudaFuncSetAttribute(prep_all_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cache = smem;
     }
-    prep_all_kernel<HID><<<a.tl.N + 1 + cp_blocks, 256, smem, st>>>(a);
+    const int wt_blocks = a.want_cp ? ((a.net.nl - 1) * 4096 + 1023) / 1024 : 0;
+    prep_all_kernel<HID><<<a.tl.N + 1 + cp_blocks + wt_blocks, 256, smem, st>>>(a);
     LMR_LAUNCH_OK();
     return 0;
 }

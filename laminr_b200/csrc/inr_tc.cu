@@ -171,7 +171,7 @@ struct TcSmem {
         bars = reinterpret_cast<uint64_t*>(take(NBARS * 8));
         tmem = reinterpret_cast<uint32_t*>(take(16));
         // A[n] rows staged in shared memory when they fit (L1 is almost entirely carved out for shared memory here)
-        As = tl.NC <= 24 ? reinterpret_cast<float*>(take((size_t)tl.NC * 56 * 4)) : nullptr;
+        As = (tl.NC <= 24 && ng > 1) ? reinterpret_cast<float*>(take((size_t)tl.NC * 56 * 4)) : nullptr;
         bytes = p - base;
     }
 };
@@ -180,28 +180,16 @@ struct TcSmem {
 // entry [50][50] = ONE_SEED (regenerates the constant-1 feature), rest 0.  Also the fp32 output layer.
 __device__ inline void load_weight_tiles(const Args& a, TcSmem& s) {
     const Net& nt = a.net;
-    for (int l = 1; l < LH; ++l) {
-        const float* W = a.params + nt.offW(l);
-        const float* b = a.params + nt.offb(l);
-        uint8_t* dst = s.wt + (size_t)(l - 1) * WT_BYTES;
-        for (int i = threadIdx.x; i < HPAD * HPAD; i += blockDim.x) {
-            const int o = i / HPAD, k = i % HPAD;
-            float v = 0.f;
-            if (o < HID) v = k < HID ? W[o * HID + k] : (k == ONE_COL ? b[o] : 0.f);
-            else if (o == ONE_COL && k == ONE_COL) v = ONE_SEED;
-            const __nv_bfloat16 hi = __float2bfloat16(v);
-            const __nv_bfloat16 lo = __float2bfloat16(v - __bfloat162float(hi));
-            const uint32_t off = tile_off(o, k >> 3, HPAD) + (k & 7) * 2;
-            *reinterpret_cast<__nv_bfloat16*>(dst + off) = hi;
-            *reinterpret_cast<__nv_bfloat16*>(dst + WT_HALF + off) = lo;
-        }
-    }
+    // the split-bf16 tile images were built once by the prep kernel: a straight 16-byte copy, every chunk in flight at once
+    for (int i = threadIdx.x; i < (LH - 1) * WT_BYTES / 16; i += blockDim.x) cp_async16(s.wt + 16 * i, a.wtimg + 16 * i);
+    cp_async_commit();
     const float* Wo = a.params + nt.offWout();
     for (int i = threadIdx.x; i < nt.C * HPAD; i += blockDim.x) {
         const int c = i / HPAD, k = i % HPAD;
         s.Wout[i] = k < HID ? Wo[c * HID + k] : 0.f;
     }
     if (threadIdx.x < 4) s.bout[threadIdx.x] = threadIdx.x < nt.C ? a.params[nt.offbout() + threadIdx.x] : 0.f;
+    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -508,6 +496,177 @@ __global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
     fence_before_sync();
     __syncthreads();
     if (warp == NE / 32) tmem_dealloc(tm, TM_COLS_FWD);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward, operand tiles in TENSOR MEMORY: 4 epilogue warps (thread = one row, all 52 features) + the MMA warp, FOUR CTAs per SM.
+// The activation tile never touches shared memory: the epilogue writes the split-bf16 operand with tcgen05.st (hi: 32 columns, lo: 32
+// columns) and the MMAs take A from TMEM (tcgen05.mma [d], [a], b-desc): no generic->async proxy fence on the critical path, only the
+// 6 KB of weights per MMA are fetched from shared memory (32 cycles per MMA instead of 48), and four independent tiles per SM hide the
+// epilogue <-> MMA hand-over latencies.  Shared memory per CTA = the weight tiles (48 KB) + the layer-0 tables.
+// TMEM columns per CTA (128): [0,64) accumulator, [64,96) A hi, [96,128) A lo.  Feature chunk 7 (columns 56..63) of A stays zero.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int NE_T = 128, NT_T = NE_T + 32;
+constexpr uint32_t TM_T_ACC = 0, TM_T_AHI = 64, TM_T_ALO = 96, TM_T_COLS = 128;
+
+// split 16 floats (8 pairs) into bf16 hi / lo words and write them to the A operand columns of k-chunk kc
+__device__ __forceinline__ void store_kchunk_tmem(uint32_t a_hi, uint32_t a_lo, int kc, const float2* v) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[q].x, v[q].y);
+        const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h2);
+        const float2 hf = make_float2(__uint_as_float(hw << 16), __uint_as_float(hw & 0xffff0000u));
+        const float2 d = fma2(hf, make_float2(-1.f, -1.f), v[q]);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(d.x, d.y);
+        hi[q] = hw;
+        lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    tmem_st8(a_hi + 8 * kc, hi);
+    tmem_st8(a_lo + 8 * kc, lo);
+}
+__device__ __forceinline__ void arrive_kchunk_tmem(uint64_t* bar, int lane) {
+    tmem_st_wait();
+    fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+
+template <bool FAST, int C>
+__global__ void __launch_bounds__(NT_T, 4) inr_fwd_ts_kernel(Args a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const Net& nt = a.net;
+    const Tiling& tl = a.tl;
+    TcSmem s(smem_raw, nt, tl, 0, false, 1);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const bool multi_chunk = tl.nChunks > 1;
+    load_weight_tiles(a, s);
+    init_layer0_tables(a, s, !multi_chunk, NT_T);
+    if (warp == NE_T / 32) tmem_alloc(s.tmem, TM_T_COLS);
+    if (t == 0) init_barriers(s.bars, 4);
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = *s.tmem;
+    const int myTiles = (tl.numTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == NE_T / 32) {
+        if (lane == 0) {  // ---- MMA issuer
+            const uint32_t w_addr = smem_u32(s.wt);
+            const uint32_t idesc = instr_desc(FMT_BF16, 128, HPAD, 0, 0);
+            uint32_t pk = 0;
+            for (int it = 0; it < myTiles; ++it) {
+#pragma unroll 1
+                for (int st = 0; st < LH - 1; ++st) {
+                    const uint64_t bh0 = smem_desc(w_addr + (uint32_t)st * WT_BYTES, HPAD * 16, 128);
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) {
+                        mbar_wait(&s.bars[BAR_K + kc], pk);
+                        fence_after_sync();
+                        const uint64_t bh = bh0 + (uint64_t)kc * ((2 * HPAD * 16) >> 4);
+                        mma_f16_ts(tm + TM_T_ACC, tm + TM_T_AHI + 8 * kc, bh, idesc, kc > 0);
+                        mma_f16_ts(tm + TM_T_ACC, tm + TM_T_ALO + 8 * kc, bh, idesc, 1);
+                        mma_f16_ts(tm + TM_T_ACC, tm + TM_T_AHI + 8 * kc, bh + (WT_HALF >> 4), idesc, 1);
+                    }
+                    pk ^= 1;
+                    mma_commit(&s.bars[BAR_ACC]);
+                }
+            }
+        }
+    } else {  // ---- epilogue threads: thread = row
+        const int row = t;
+        const uint32_t lane_taddr = (uint32_t)(32 * warp) << 16;
+        const uint32_t a_hi = tm + TM_T_AHI + lane_taddr, a_lo = tm + TM_T_ALO + lane_taddr, acc = tm + TM_T_ACC + lane_taddr;
+        {  // feature chunk 7 of the operand (columns 56..63) is never produced: zero it once
+            const uint32_t z[4] = {0u, 0u, 0u, 0u};
+            tmem_st4(a_hi + 28, z);
+            tmem_st4(a_lo + 28, z);
+            tmem_st_wait();
+        }
+        uint32_t pa = 0;
+        if (myTiles > 0) stage_tile_inputs(a, decode_tile(tl, blockIdx.x), s.Cps, NE_T);
+        cp_async_commit();
+        const int nl = row / tl.TP, j = row % tl.TP;
+        for (int it = 0; it < myTiles; ++it) {
+            const TileIdx ti = decode_tile(tl, blockIdx.x + it * gridDim.x);
+            cp_async_wait<0>();
+            named_bar_sync(1, NE_T);
+            if (it + 1 < myTiles) stage_tile_inputs(a, decode_tile(tl, blockIdx.x + (it + 1) * gridDim.x), s.Cps + ((it + 1) & 1) * tl.TP * SHS, NE_T);
+            cp_async_commit();
+            const float* Cj = s.Cps + (it & 1) * tl.TP * SHS;
+            const bool active = nl < ti.nn && j < ti.np;
+            Cj += (active ? j : 0) * SHS;
+            const bool as_smem = s.As != nullptr && !multi_chunk;
+            const float* An = as_smem ? s.As + (active ? nl : 0) * SHS : a.Avec + (size_t)(ti.n0 + (active ? nl : 0)) * SHP;
+            // ---- h_1 = tanh(A[n] + Cp[j]) -> operand (the previous tile's last accumulator was waited for: the operand columns are free)
+#pragma unroll 1
+            for (int kc = 0; kc < 4; ++kc) {
+                float2 v[8];
+                float* vf = reinterpret_cast<float*>(v);
+                const int ncol = kc < 3 ? 16 : 8;  // chunk 6 (features 48..55: 4 live + 4 zero) only; chunk 7 stays zero
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int col = 16 * kc + k;
+                    float z0 = 0.f;
+                    if (k < ncol) z0 = (as_smem ? An[col] : (col < SHP ? An[col] : 0.f)) + Cj[col];
+                    vf[k] = z0;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    v[q] = act_tanh2<FAST>(v[q]);
+                    if (!active || 2 * q >= ncol) v[q] = make_float2(0.f, 0.f);
+                }
+                store_kchunk_tmem(a_hi, a_lo, kc, v);
+                arrive_kchunk_tmem(&s.bars[BAR_K + kc], lane);
+            }
+#pragma unroll 1
+            for (int st = 0; st < LH - 1; ++st) {
+                mbar_wait(&s.bars[BAR_ACC], pa);
+                pa ^= 1;
+                fence_after_sync();
+                float2 v[26];
+                float* vf = reinterpret_cast<float*>(v);
+                tmem_ld16(acc, vf);
+                tmem_ld16(acc + 16, vf + 16);
+                tmem_ld16(acc + 32, vf + 32);
+                tmem_ld4(acc + 48, vf + 48);
+                tmem_ld_wait();
+                fence_before_sync();
+                if (st < LH - 2) {
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) {
+                        float2 w[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) w[q] = (8 * kc + q < 26) ? act_tanh2<FAST>(v[8 * kc + q]) : make_float2(0.f, 0.f);
+                        store_kchunk_tmem(a_hi, a_lo, kc, w);
+                        arrive_kchunk_tmem(&s.bars[BAR_K + kc], lane);
+                    }
+                } else {  // output layer on CUDA cores
+                    float y[C];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) y[c] = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 26; ++q) {
+                        const float2 h = act_tanh2<FAST>(v[q]);
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const float2 w = *reinterpret_cast<const float2*>(s.Wout + c * HPAD + 2 * q);
+                            y[c] = fmaf(h.x, w.x, fmaf(h.y, w.y, y[c]));
+                        }
+                    }
+                    if (active) {
+                        const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + nl)) * C) * tl.P + ti.p0 + j;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) a.img[base + (size_t)c * tl.P] = act_tanh<FAST>(s.bout[c] + y[c]);
+                    }
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == NE_T / 32) tmem_dealloc(tm, TM_T_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -953,15 +1112,32 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
     a.img = img;
     a.want_cp = 1;
     if (int rc = launch_prep<50>(a, st)) return rc;
+    static const bool smem_operands = getenv("LMR_FWD_SMEM") != nullptr;  // development switch: operand tiles in shared memory
+    const bool fast = precision == LMR_PREC_BF16X3_FAST;
+    if (!smem_operands) {
+        TcSmem s(nullptr, nt, tl, 0, false, 1);
+        const size_t smem = s.bytes + 1024;
+        const int grid_x = tl.numTiles < 4 * num_sms() ? tl.numTiles : 4 * num_sms();
+        static size_t cache[2][5] = {};
+#define LMR_FWD_TS_CASE(FASTV, CV)                                                                       \
+    if (fast == FASTV && nt.C == CV) {                                                                   \
+        if (int rc = set_smem(inr_fwd_ts_kernel<FASTV, CV>, smem, &cache[FASTV][CV])) return rc;        \
+        inr_fwd_ts_kernel<FASTV, CV><<<grid_x, NT_T, smem, st>>>(a);                                     \
+    }
+        LMR_FWD_TS_CASE(false, 1) LMR_FWD_TS_CASE(false, 2) LMR_FWD_TS_CASE(false, 3) LMR_FWD_TS_CASE(false, 4)
+        LMR_FWD_TS_CASE(true, 1) LMR_FWD_TS_CASE(true, 2) LMR_FWD_TS_CASE(true, 3) LMR_FWD_TS_CASE(true, 4)
+#undef LMR_FWD_TS_CASE
+        LMR_LAUNCH_OK();
+        return 0;
+    }
     TcSmem s(nullptr, nt, tl, 1, false, NG_F);
     const size_t smem = s.bytes + 1024;
     const int grid_x = tl.numTiles < 2 * num_sms() ? tl.numTiles : 2 * num_sms();
     static size_t cache[2][5] = {};
-    const bool fast = precision == LMR_PREC_BF16X3_FAST;
 #define LMR_FWD_CASE(FASTV, CV)                                                                          \
     if (fast == FASTV && nt.C == CV) {                                                                   \
         if (int rc = set_smem(inr_fwd_tc_kernel<FASTV, CV>, smem, &cache[FASTV][CV])) return rc;        \
-        inr_fwd_tc_kernel<FASTV, CV><<<grid_x, NT_F, smem, st>>>(a);                                       \
+        inr_fwd_tc_kernel<FASTV, CV><<<grid_x, NT_F, smem, st>>>(a);                                     \
     }
     LMR_FWD_CASE(false, 1) LMR_FWD_CASE(false, 2) LMR_FWD_CASE(false, 3) LMR_FWD_CASE(false, 4)
     LMR_FWD_CASE(true, 1) LMR_FWD_CASE(true, 2) LMR_FWD_CASE(true, 3) LMR_FWD_CASE(true, 4)
@@ -1002,6 +1178,7 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
         char* fb = static_cast<char*>(const_cast<void*>(fwd_ws));
         a.alpha = reinterpret_cast<float*>(fb + wf.alpha), a.Avec = reinterpret_cast<float*>(fb + wf.Avec);
         a.W0cT = reinterpret_cast<float*>(fb + wf.W0cT), a.Cpg = reinterpret_cast<float*>(fb + wf.Cpg);
+        a.wtimg = reinterpret_cast<unsigned char*>(fb + wf.wtimg);
         a.betaG = wf.betaG ? reinterpret_cast<float*>(fb + wf.betaG) : nullptr;
     } else if (int rc = launch_prep<50>(a, st)) {
         return rc;
