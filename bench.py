@@ -350,7 +350,7 @@ def run_ours(args):
             "back_to_back": {"value": world * K / (b2b_ms / 1e3), "unit": "steps/s", "ms_per_step": b2b_ms / K, "note": "K graph replays in one event pair, no L2 flush (the loop as it runs)"},
             "e2e": {"value": world * K / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": 4 * N_LATENTS, "d2h_bytes_per_step": 4},
             "gpu_launches": int(stepper.kernels_per_step * K),
-            "roofline": {"bound": "tensor", "kernel": "lmr_inr_backward launch group (inr_bwd_kernel dominant)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "kernel": "lmr_inr_backward launch group (inr_bwd_tc_kernel dominant; + layer-0 weight gradient and partial reduction launches)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf, "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback",
                          "algorithmic_gflop": bwd_f / 1e9, "ms": bwd_ms, "forward": {"algorithmic_gflop": fwd_f / 1e9, "ms": fwd_ms, "achieved": fwd_f / (fwd_ms * 1e-3) / 1e12}},
             "cpu_baseline": cpu, "clocks": clocks, "match": match,
@@ -367,7 +367,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--res", type=int, default=100)
-    ap.add_argument("--precision", default=None, choices=[None, "fp32", "bf16x3", "bf16x3_fast"])
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16x3_fast"],
+                    help="INR hidden-layer arithmetic: bf16x3 = tcgen05 split-bf16 x3 (fp32-class, default), fp32 = CUDA cores")
     ap.add_argument("--match-targets", type=int, default=32, help="targets per GPU for the extra match measurement (0 = skip)")
     ap.add_argument("--match-steps", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -1,0 +1,153 @@
+"""Multi-GPU sharding of the match stage and the MEI sweep: one process per GPU (`torchrun`), `torch.distributed` over NCCL.
+
+The reference has no distributed code; what shards naturally:
+  * `InvarianceManifold.match` -- target neuron d's 7 affine scalars interact with other targets only through the `1/D` scale of
+    the loss (laminr/inv_temp_learn_match.py:363) and the GLOBAL early-stop mean (:368).  Each rank aligns a contiguous block of
+    targets; the loss keeps the global 1/D (so per-parameter gradients, and Adam's epsilon, see exactly the unsharded values) and the
+    stop rule sees the all-reduced (sum, min, max) of the normalised activations -- one 3-float all-reduce per epoch.  Every rank then
+    runs the same number of epochs, draws the same jitter (rank 0's CPU RNG state is broadcast), and the sharded result equals the
+    unsharded one per target.
+  * `get_mei_dict` -- fully independent per neuron (laminr/utils/mei.py:98-119).
+  * `learn` does NOT shard (one template, one 20-image batch): template learning runs on one GPU and the template is broadcast.
+Collectives: broadcast of the template state (~72 KB) before, gather of images / activations after.  Nothing on the per-step path.
+
+The plumbing functions (`shard_bounds`, `broadcast_module_state`, `make_stop_reduce`, `gather_ragged`) take plain tensors and any
+backend, so they are covered by world_size-2 gloo tests on CPU; the compute itself is CUDA-only.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items, world_size, rank):
+    """Contiguous block [lo, hi) of rank `rank`: the first n % world ranks get one extra item."""
+    base, extra = divmod(int(n_items), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def broadcast_module_state(module, src=0):
+    """In-place broadcast of every parameter and buffer of `module` from rank `src` (the template INR after `learn`)."""
+    world, _ = _world()
+    if world == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src)
+
+
+def broadcast_rng_state(src=0, device=None):
+    """Every rank continues with rank `src`'s CPU generator state: the jittered latent grids (laminr/utils/training.py:42-46) and MEI
+    starting images (laminr/utils/mei.py:33) are drawn on the CPU generator, so the ranks must agree on it."""
+    world, rank = _world()
+    if world == 1:
+        return
+    state = torch.get_rng_state()
+    buf = state.clone().to(device) if (device is not None and dist.get_backend() == "nccl") else state.clone()
+    dist.broadcast(buf, src=src)
+    torch.set_rng_state(buf.cpu())
+
+
+def make_stop_reduce(device=None):
+    """-> f(sum, min, max) all-reducing the three floats over the ranks (SUM, MIN, MAX): the global stop rule of `match` (:368-375)."""
+    world, _ = _world()
+    if world == 1:
+        return None
+
+    def reduce(a_sum, a_min, a_max):
+        t = torch.tensor([a_sum, -a_min, a_max], dtype=torch.float64, device=device)
+        s = t[:1].clone()
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        m = t[1:].clone()
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)  # max(-min) = -min: one MAX all-reduce serves both
+        return float(s[0]), -float(m[0]), float(m[1])
+
+    return reduce
+
+
+def gather_ragged(local, n_total, dst=0):
+    """Concatenates per-rank blocks along dim 0 (block sizes from `shard_bounds`) on rank `dst`; returns None elsewhere.
+    `local` is this rank's block (may be empty) of a tensor whose dim-0 length over all ranks is `n_total`."""
+    world, rank = _world()
+    if world == 1:
+        return local
+    sizes = [shard_bounds(n_total, world, r)[1] - shard_bounds(n_total, world, r)[0] for r in range(world)]
+    nmax = max(sizes)
+    pad = torch.zeros((nmax,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    if dist.get_backend() == "nccl":  # NCCL has no gather-to-one for ragged lists: all ranks send, rank dst receives
+        if rank == dst:
+            bufs[dst].copy_(pad)
+            reqs = [dist.irecv(bufs[r], src=r) for r in range(world) if r != dst]
+            for q in reqs:
+                q.wait()
+        else:
+            dist.send(pad, dst=dst)
+    else:  # gloo gathers host tensors only
+        dev = pad.device
+        host = [b.cpu() for b in bufs] if rank == dst else None
+        dist.gather(pad.cpu(), gather_list=host, dst=dst)
+        bufs = [h.to(dev) for h in host] if rank == dst else None
+    if rank != dst:
+        return None
+    return torch.cat([bufs[r][: sizes[r]] for r in range(world)], dim=0)
+
+
+def match_sharded(im, target_neuron_idxs, **match_kwargs):
+    """`InvarianceManifold.match` with the targets sharded over the ranks.  Call on every rank with the same arguments after `learn`
+    ran on rank 0 (any rank may hold an untrained copy of the template: it is overwritten by rank 0's).
+    Returns (images [D,N,C,H,W], activations [D,N]) as NumPy arrays on rank 0, (None, None) elsewhere."""
+    world, rank = _world()
+    device = next(im.template.parameters()).device
+    targets = list(target_neuron_idxs)
+    D = len(targets)
+    if world == 1:
+        return im.match(targets, **match_kwargs)
+    tni = torch.tensor([int(getattr(im, "template_neuron_idx", -1))], dtype=torch.int64, device=device)
+    dist.broadcast(tni, src=0)
+    im.template_neuron_idx = int(tni.item())
+    broadcast_module_state(im.template, src=0)
+    broadcast_rng_state(src=0, device=device)
+    lo, hi = shard_bounds(D, world, rank)
+    if hi == lo:
+        raise ValueError(f"match_sharded: {D} targets cannot be split over {world} ranks (every rank needs at least one target)")
+    imgs, acts = im.match(targets[lo:hi], _total_targets=D, _stop_reduce=make_stop_reduce(device), **match_kwargs)
+    g_img = gather_ragged(torch.from_numpy(np.ascontiguousarray(imgs)).to(device), D)
+    g_act = gather_ragged(torch.from_numpy(np.ascontiguousarray(acts)).to(device), D)
+    if rank != 0:
+        return None, None
+    return g_img.cpu().numpy(), g_act.cpu().numpy()
+
+
+def get_mei_dict_sharded(model, input_shape, pixel_value_lower_bound, pixel_value_upper_bound, neuron_idxs=None, **kwargs):
+    """`get_mei_dict` with the neurons sharded over the ranks; the full dict (keyed by enumeration index like the reference,
+    laminr/utils/mei.py:114) is returned on EVERY rank (it is the input of `InvarianceManifold`)."""
+    from .utils.mei import get_mei_dict
+
+    world, rank = _world()
+    if neuron_idxs is None:
+        if not hasattr(model, "n_neurons"):
+            raise ValueError("get_mei_dict_sharded: pass neuron_idxs for models without `n_neurons`")
+        neuron_idxs = list(range(int(model.n_neurons)))
+    neuron_idxs = list(neuron_idxs)
+    if world == 1:
+        return get_mei_dict(model, input_shape, pixel_value_lower_bound, pixel_value_upper_bound, neuron_idxs=neuron_idxs, **kwargs)
+    lo, hi = shard_bounds(len(neuron_idxs), world, rank)
+    # the reference draws one initial image per neuron, in order, from the CPU generator (mei.py:33): skip the draws of lower ranks
+    items = list(model.parameters()) + list(model.buffers())
+    broadcast_rng_state(src=0, device=items[0].device if items else None)
+    if lo > 0:
+        torch.randn(lo, *input_shape)
+    local = get_mei_dict(model, input_shape, pixel_value_lower_bound, pixel_value_upper_bound, neuron_idxs=neuron_idxs[lo:hi], **kwargs)
+    parts = [None] * world
+    dist.all_gather_object(parts, {lo + k: v for k, v in local.items()})
+    out = {}
+    for part in parts:
+        out.update(part)
+    return dict(sorted(out.items()))

@@ -1,0 +1,99 @@
+"""Host-side logic of the multi-GPU sharding (laminr_b200/dist.py) on CPU: world_size-2 `gloo` process group.
+The collectives carry plain tensors, so the plumbing (shard bounds, template broadcast, RNG agreement, global stop-rule reduce,
+ragged gather) is exercised exactly as under NCCL; the CUDA compute is covered by the -m gpu tests."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_targets, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from laminr_b200 import dist as D
+        from laminr_b200.utils.training import ImprovementChecker, JitteringGridDatamodule
+
+        # --- template broadcast: rank 0's parameters / buffers win
+        torch.manual_seed(100 + rank)
+        mod = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 1))
+        mod.register_buffer("B", torch.randn(2, 4))
+        D.broadcast_module_state(mod, src=0)
+        # --- RNG agreement: the jittered grids are drawn on the CPU generator
+        D.broadcast_rng_state(src=0)
+        dm = JitteringGridDatamodule(1, 20, 3)
+        grids = torch.stack(list(dm.train_dataloader()))
+        # --- global stop rule: per-rank partial (sum, min, max) -> identical global decision on every rank
+        lo, hi = D.shard_bounds(n_targets, world, rank)
+        rng = np.random.RandomState(7)
+        curves = np.cumsum(rng.rand(40, n_targets) * np.clip(np.linspace(0.03, -0.03, 40), 0, None)[:, None], axis=0)  # saturating per-target activations
+        reduce = D.make_stop_reduce()
+        chk, stopped_at, means = ImprovementChecker(patience=5, ignore_diff_smaller_than=1e-3), None, []
+        for epoch in range(40):
+            a = curves[epoch, lo:hi]
+            s, mn, mx = reduce(float(a.sum()), float(a.min()), float(a.max()))
+            means.append(s / n_targets)
+            assert abs(mn - curves[epoch].min()) < 1e-12 and abs(mx - curves[epoch].max()) < 1e-12
+            if not chk.is_increasing(s / n_targets):
+                stopped_at = epoch
+                break
+        # --- ragged gather of per-target results
+        local = torch.arange(lo, hi, dtype=torch.float32)[:, None, None] * torch.ones(1, 3, 2)
+        full = D.gather_ragged(local, n_targets, dst=0)
+        q.put((rank, [p.detach().clone() for p in mod.parameters()] + [mod.B.clone()], grids, stopped_at, means, None if full is None else full.clone(), (lo, hi)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_targets", [5, 8])
+def test_sharded_match_plumbing_world2(n_targets):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_targets, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (r0, state0, grids0, stop0, means0, full0, b0), (r1, state1, grids1, stop1, means1, full1, b1) = res
+    for a, b in zip(state0, state1):
+        assert torch.equal(a, b)                       # broadcast template state
+    assert torch.equal(grids0, grids1)                 # same jitter on every rank
+    assert stop0 == stop1 and stop0 is not None        # same (global) stop epoch
+    np.testing.assert_allclose(means0, means1, rtol=0, atol=0)
+    # unsharded reference of the stop rule
+    from laminr_b200.utils.training import ImprovementChecker
+    rng = np.random.RandomState(7)
+    curves = np.cumsum(rng.rand(40, n_targets) * np.clip(np.linspace(0.03, -0.03, 40), 0, None)[:, None], axis=0)
+    chk, want = ImprovementChecker(patience=5, ignore_diff_smaller_than=1e-3), None
+    for epoch in range(40):
+        if not chk.is_increasing(float(curves[epoch].sum()) / n_targets):
+            want = epoch
+            break
+    assert stop0 == want
+    assert b0[1] == b1[0] and b0[0] == 0 and b1[1] == n_targets and (b0[1] - b0[0]) - (b1[1] - b1[0]) in (0, 1)
+    assert full1 is None
+    assert torch.equal(full0[:, 0, 0], torch.arange(n_targets, dtype=torch.float32)) and full0.shape == (n_targets, 3, 2)
+
+
+def test_shard_bounds_cover_everything():
+    from laminr_b200.dist import shard_bounds
+    for n in (1, 7, 8, 1023):
+        for w in (1, 2, 4, 8):
+            b = [shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
