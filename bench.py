@@ -318,6 +318,41 @@ def run_ours(args):
         match = {"metric": "match target-steps/sec (one Adam step of one target's affine transform)", "value": Dloc * world * mk / (mt.item() / 1e3),
                  "unit": "target-steps/s", "targets_per_gpu": Dloc, "steps": mk, "ms_per_step": mt.item() / mk,
                  "algorithmic_gflop_per_target_step": 2 * algorithmic_flops(res)[0] / 1e9}
+        # ---- whole match() call (BASELINE metric 2: target neurons aligned/sec): 60-angle init sweep + a FIXED number of epochs (so that the number is
+        #      not hostage to the early-stop) + final snapshot and D2H of the aligned images; targets sharded over the ranks, global 1/D and stop rule
+        from laminr_b200.dist import make_stop_reduce
+        im2.template_neuron_idx = 0
+        epochs = args.match_epochs
+        import contextlib, io
+        barrier()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stderr(io.StringIO()):  # tqdm bars
+            imgs, acts_m = im2.match(targets, num_epochs=epochs, patience=10 ** 9, _total_targets=Dloc * world, _stop_reduce=make_stop_reduce(dev))
+        torch.cuda.synchronize()
+        mt2 = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(mt2, op=dist.ReduceOp.MAX)
+        match["aligned"] = {"metric": "target neurons aligned/sec (whole match(): 60-angle sweep + epochs + result gather to host)", "value": Dloc * world / mt2.item(),
+                            "unit": "neurons/s", "epochs": int(im2.match_epochs_run), "seconds": mt2.item(), "targets_total": Dloc * world,
+                            "result_shape": list(imgs.shape)}
+        # ---- MEI sweep (BASELINE config 5): batched gradient ascent, 1000 iterations, neurons sharded over the ranks
+        from laminr_b200.utils.mei import batched_simulated_meis
+        nmei = Dloc + 1
+        x0 = torch.randn(nmei, 1, res, res).to(dev)
+        batched_simulated_meis(pop, list(range(nmei)), x0, -1.0, 1.0, norm=1.0, num_iterations=10)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _, fev = batched_simulated_meis(pop, list(range(nmei)), x0, -1.0, 1.0, norm=1.0, num_iterations=1000)
+        b.record()
+        barrier()
+        mt3 = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(mt3, op=dist.ReduceOp.MAX)
+        mei_bytes = (20 * res * res * 4 + 3 * res * res * 4) * 1000 * nmei  # F*P*4 + 3*C*P*4 per neuron-iteration
+        match["mei"] = {"metric": "MEIs/sec (1000 ascent iterations each, batched)", "value": nmei * world / (mt3.item() / 1e3), "unit": "MEIs/s",
+                        "neurons_per_gpu": nmei, "ms": mt3.item(), "final_activation_mean": float(fev[:, -1].mean().item()),
+                        "algorithmic_GBps_per_gpu": mei_bytes / (mt3.item() / 1e3) / 1e9}
 
     # ---- reduce over ranks (max time), CPU baseline on rank 0 at N == 1
     tt = torch.tensor([step_ms, b2b_ms, e2e_s * 1e3], device=dev)
@@ -371,6 +406,7 @@ def main():
                     help="INR hidden-layer arithmetic: bf16x3 = tcgen05 split-bf16 x3 (fp32-class, default), fp32 = CUDA cores")
     ap.add_argument("--match-targets", type=int, default=32, help="targets per GPU for the extra match measurement (0 = skip)")
     ap.add_argument("--match-steps", type=int, default=20)
+    ap.add_argument("--match-epochs", type=int, default=30, help="epochs of the whole-match() measurement (fixed; the early stop is disabled)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

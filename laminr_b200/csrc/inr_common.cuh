@@ -473,13 +473,123 @@ __global__ void __launch_bounds__(128) finish_w0a_kernel(Args a, float* g_params
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// match: gradient wrt the transformed coordinates and its per-target moments, pixel-parallel:
+//   DS[p][k] = sum_o G0[p][o] W0c[o][k]  (k < pe: sine columns, k >= pe: cosine columns);  dphi[p][m] = DS[p][m] cos(phi) - DS[p][pe+m] sin(phi)
+//   G[p] = sum_m dphi[p][m] B[:, m];  partial[d][blk] = sum_p (G0, G1, G0 r0, G0 r1, G1 r0, G1 r1),  r = coords_p - tc
+// One block = `ppb` pixels of ONE target; register-blocked 4 pixel x 4 column GEMM like the prep kernel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int AFF_THREADS = 448;
+
+template <int HID>
+__global__ void __launch_bounds__(AFF_THREADS) affine_grad_kernel(Args a) {
+    constexpr int HP = (HID + 3) / 4 * 4;
+    extern __shared__ __align__(16) float sm[];
+    const Net& nt = a.net;
+    const int pe = nt.pe, nb = 2 * pe, ppb = a.ppb, na = 2 * nt.ape;
+    const int d = blockIdx.y, blk = blockIdx.x, t = threadIdx.x;
+    const int p0 = blk * ppb, nq = min(ppb, a.tl.P - p0);
+    float* Wt = sm;                 // [HP][nb]   W0c[o][k] (rows HID.. are zero)
+    float* Gt = Wt + HP * nb;       // [HP][ppb]  G0 transposed (4 pixels per float4)
+    float* DS = Gt + HP * ppb;      // [ppb][nb]
+    __shared__ float cst[10];
+    __shared__ float2 cxy[PREP_PPB_MAX];
+    __shared__ float Bsm[2 * 64];
+    __shared__ float red[6][AFF_THREADS / 32];
+    if (t == 0) affine_consts(a.aff, d, cst);
+    if (t >= 64 && t < 64 + nb) Bsm[t - 64] = a.B[t - 64];
+    for (int i = t; i < HP * nb; i += AFF_THREADS) {
+        const int o = i / nb, k = i % nb;
+        Wt[i] = o < HID ? a.params[(size_t)o * nt.in_dim + 1 + na + k] : 0.f;
+    }
+    const float* gsrc = a.G0 + ((size_t)d * a.tl.P + p0) * HP;
+    for (int i = t; i < ppb * HP; i += AFF_THREADS) {
+        const int jj = i / HP, o = i % HP;
+        Gt[o * ppb + jj] = jj < nq ? gsrc[i] : 0.f;
+    }
+    __syncthreads();
+    if (t < nq) cxy[t] = transformed_coord(a, cst, p0 + t);
+    const int npg = ppb / 4, nkg = nb / 4;
+    if (t < npg * nkg) {
+        const int pg = t / nkg, kg = t % nkg;
+        float4 acc[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) acc[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* gp = reinterpret_cast<const float4*>(Gt) + pg;
+        const float4* wp = reinterpret_cast<const float4*>(Wt) + kg;
+#pragma unroll 4
+        for (int o = 0; o < HID; ++o) {
+            const float4 g = gp[o * npg], w = wp[o * nkg];
+            acc[0].x = fmaf(g.x, w.x, acc[0].x), acc[0].y = fmaf(g.x, w.y, acc[0].y), acc[0].z = fmaf(g.x, w.z, acc[0].z), acc[0].w = fmaf(g.x, w.w, acc[0].w);
+            acc[1].x = fmaf(g.y, w.x, acc[1].x), acc[1].y = fmaf(g.y, w.y, acc[1].y), acc[1].z = fmaf(g.y, w.z, acc[1].z), acc[1].w = fmaf(g.y, w.w, acc[1].w);
+            acc[2].x = fmaf(g.z, w.x, acc[2].x), acc[2].y = fmaf(g.z, w.y, acc[2].y), acc[2].z = fmaf(g.z, w.z, acc[2].z), acc[2].w = fmaf(g.z, w.w, acc[2].w);
+            acc[3].x = fmaf(g.w, w.x, acc[3].x), acc[3].y = fmaf(g.w, w.y, acc[3].y), acc[3].z = fmaf(g.w, w.z, acc[3].z), acc[3].w = fmaf(g.w, w.w, acc[3].w);
+        }
+#pragma unroll
+        for (int x = 0; x < 4; ++x) reinterpret_cast<float4*>(DS + (size_t)(4 * pg + x) * nb)[kg] = acc[x];
+    }
+    __syncthreads();
+    // dphi and its projection on B, pixel by pixel: 8 lanes per pixel, fixed-order combine
+    float v6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    {
+        const int sub = t & 7;
+        for (int jj = t >> 3; jj < nq; jj += AFF_THREADS / 8) {
+            const float2 c = cxy[jj];
+            float g0 = 0.f, g1 = 0.f;
+            for (int m = sub; m < pe; m += 8) {
+                float sn, cs;
+                sincosf(c.x * Bsm[m] + c.y * Bsm[pe + m], &sn, &cs);
+                const float dphi = DS[jj * nb + m] * cs - DS[jj * nb + pe + m] * sn;
+                g0 = fmaf(dphi, Bsm[m], g0);
+                g1 = fmaf(dphi, Bsm[pe + m], g1);
+            }
+            const unsigned gmask = 0xffu << ((t & 31) & ~7);
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) g0 += __shfl_xor_sync(gmask, g0, o), g1 += __shfl_xor_sync(gmask, g1, o);
+            if (sub == 0) {
+                const int p = p0 + jj;
+                const float r0 = a.coords[2 * p] - cst[6], r1 = a.coords[2 * p + 1] - cst[7];
+                v6[0] += g0, v6[1] += g1, v6[2] += g0 * r0, v6[3] += g0 * r1, v6[4] += g1 * r0, v6[5] += g1 * r1;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const float w = warp_sum(v6[q]);
+        if ((t & 31) == 0) red[q][t >> 5] = w;
+    }
+    __syncthreads();
+    if (t < 6) {
+        float sum = 0.f;
+        for (int w = 0; w < AFF_THREADS / 32; ++w) sum += red[t][w];
+        a.affpart[((size_t)d * gridDim.x + blk) * 6 + t] = sum;
+    }
+}
+
+template <int HID>
+static int launch_affine_grad(const Args& a, int* nblk_out, cudaStream_t st) {
+    constexpr int HP = (HID + 3) / 4 * 4;
+    const int nb = 2 * a.net.pe;
+    const int nblk = (a.tl.P + a.ppb - 1) / a.ppb;
+    const size_t smem = ((size_t)HP * nb + (size_t)HP * a.ppb + (size_t)a.ppb * nb) * sizeof(float);
+    static size_t cache = 0;
+    if (smem > 40 * 1024 && smem > cache) {
+        LMR_CUDA_OK(cudaFuncSetAttribute(affine_grad_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cache = smem;
+    }
+    affine_grad_kernel<HID><<<dim3(nblk, a.tl.D), AFF_THREADS, smem, st>>>(a);
+    LMR_LAUNCH_OK();
+    *nblk_out = nblk;
+    return 0;
+}
+
 // match: per-target reduction of the tile partials and chain rule to the 7 affine scalars
-static __global__ void finish_affine_kernel(Args a, float* g_angles, float* g_scalings, float* g_shears, float* g_translation) {
+static __global__ void finish_affine_kernel(Args a, int npart, float* g_angles, float* g_scalings, float* g_shears, float* g_translation) {
     const int d = blockIdx.x;
     __shared__ float scratch[40];
     float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int i = threadIdx.x; i < a.tl.tilesP; i += blockDim.x) {
-        const float* src = a.affpart + ((size_t)d * a.tl.tilesP + i) * 6;
+    for (int i = threadIdx.x; i < npart; i += blockDim.x) {
+        const float* src = a.affpart + ((size_t)d * npart + i) * 6;
 #pragma unroll
         for (int q = 0; q < 6; ++q) v[q] += src[q];
     }

@@ -476,7 +476,7 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
         if (int rc = launch_finish_weights<50>(a, l0part, wl.gridMain, wl.gridL0, g_params, st)) return rc;
     }
     if (want_aff) {
-        finish_affine_kernel<<<D, 128, 0, st>>>(a, g_angles, g_scalings, g_shears, g_translation);
+        finish_affine_kernel<<<D, 128, 0, st>>>(a, tl.tilesP, g_angles, g_scalings, g_shears, g_translation);
         LMR_LAUNCH_OK();
     }
     return 0;

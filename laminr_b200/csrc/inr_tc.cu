@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const Net& nt = a.net;
     const Tiling& tl = a.tl;
-    TcSmem s(smem_raw, nt, tl, NBUF_BWD, a.want_affine != 0, NG);
+    TcSmem s(smem_raw, nt, tl, NBUF_BWD, false, NG);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const bool want_w = a.want_weights != 0;
     load_weight_tiles(a, s);
@@ -790,19 +790,6 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
                 const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + (active ? nl : 0))) * C) * tl.P + ti.p0 + (active ? j : 0);
 #pragma unroll
                 for (int c = 0; c < C; ++c) g[c] = active ? __ldg(a.g_img + base + (size_t)c * tl.P) : 0.f;
-            }
-            if (a.want_affine) {  // beta[j][2pe] = sin/cos(coords . B) of the tile's pixels (consumed after the staging barrier below)
-                const int pe = nt.pe;
-                float cst[10];
-                affine_consts(a.aff, ti.d, cst);
-                for (int i = t; i < ti.np * pe; i += NE) {
-                    const int jj = i / pe, m = i % pe;
-                    const float2 c = transformed_coord(a, cst, ti.p0 + jj);
-                    float sn, cs;
-                    sincosf(c.x * a.B[m] + c.y * a.B[pe + m], &sn, &cs);
-                    s.beta[jj * 2 * pe + m] = sn;
-                    s.beta[jj * 2 * pe + pe + m] = cs;
-                }
             }
             float2 v[4 * NCH];
             float* vf = reinterpret_cast<float*>(v);
@@ -933,10 +920,10 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
             named_bar_sync(1, NE);  // dz_0 staged (and beta written)
             if (t == 0) LMR_TRACE(0, it * 20 + 15);
             // ---- layer 0: G0[j][o] = sum_n dz0, dA[n][o] += sum_j dz0   (CUDA cores; consecutive lanes -> consecutive features: conflict-free)
-            float* G0s = s.scratch;
-            if (t < TP * SHP) {
+            // G0 goes straight to global memory: it is consumed by the layer-0 weight-gradient kernel (learn) / the coordinate-gradient kernel (match)
+            if (t < TP * SHP && g0_j < ti.np) {
                 float sum = 0.f;
-                if (g0_o < HID && g0_j < ti.np) {
+                if (g0_o < HID) {
                     const float* zr = stage + g0_j * STG + g0_o;
                     float s0 = 0.f, s1 = 0.f;
                     int n = 0;
@@ -944,7 +931,7 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
                     if (n < ti.nn) s0 += zr[n * TP * STG];
                     sum = s0 + s1;
                 }
-                G0s[g0_j * SHP + g0_o] = sum;
+                a.G0[((size_t)ti.d * tl.P + ti.p0 + g0_j) * SHP + g0_o] = sum;
             }
             if (want_w) {
 #pragma unroll
@@ -960,51 +947,7 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
                     }
                 }
             }
-            named_bar_sync(1, NE);
             if (t == 0) LMR_TRACE(0, it * 20 + 16);
-            if (want_w) {
-                float* gdst = a.G0 + ((size_t)ti.d * tl.P + ti.p0) * SHP;
-                for (int i = t; i < ti.np * SHP; i += NE) gdst[i] = G0s[i];
-            }
-            if (a.want_affine) {
-                const int pe = nt.pe;
-                for (int i = t; i < ti.np * pe; i += NE) {
-                    const int jj = i / pe, m = i % pe;
-                    const float4* ws_ = reinterpret_cast<const float4*>(a.W0cT + (size_t)m * SHP);
-                    const float4* wc_ = reinterpret_cast<const float4*>(a.W0cT + (size_t)(pe + m) * SHP);
-                    const float4* g4 = reinterpret_cast<const float4*>(G0s + jj * SHP);
-                    float ds = 0.f, dc = 0.f;
-                    for (int o4 = 0; o4 < SHP / 4; ++o4) {
-                        const float4 gg = g4[o4], a4 = __ldg(ws_ + o4), b4 = __ldg(wc_ + o4);
-                        ds += gg.x * a4.x + gg.y * a4.y + gg.z * a4.z + gg.w * a4.w;
-                        dc += gg.x * b4.x + gg.y * b4.y + gg.z * b4.z + gg.w * b4.w;
-                    }
-                    const float sn = s.beta[jj * 2 * pe + m], cs = s.beta[jj * 2 * pe + pe + m];
-                    s.beta[jj * 2 * pe + m] = ds * cs - dc * sn;  // d/dphi
-                }
-                named_bar_sync(1, NE);
-                if (t < 32) {  // TP <= 8: the first warp holds every contribution
-                    float w6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (t < ti.np) {
-                        float g0 = 0.f, g1 = 0.f;
-                        for (int m = 0; m < pe; ++m) {
-                            const float dphi = s.beta[t * 2 * pe + m];
-                            g0 = fmaf(dphi, a.B[m], g0);
-                            g1 = fmaf(dphi, a.B[pe + m], g1);
-                        }
-                        const int p = ti.p0 + t;
-                        const float tc0 = a.aff.tc ? a.aff.tc[0] : 0.f, tc1 = a.aff.tc ? a.aff.tc[1] : 0.f;
-                        const float r0 = a.coords[2 * p] - tc0, r1 = a.coords[2 * p + 1] - tc1;
-                        w6[0] = g0, w6[1] = g1, w6[2] = g0 * r0, w6[3] = g0 * r1, w6[4] = g1 * r0, w6[5] = g1 * r1;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) w6[q] = warp_sum(w6[q]);
-                    if (t == 0) {
-                        float* pdst = a.affpart + ((size_t)ti.d * tl.tilesP + ti.p0 / TP) * 6;
-                        for (int q = 0; q < 6; ++q) pdst[q] = w6[q];
-                    }
-                }
-            }
         }
         // ---- drain: wait for every MMA, then read the weight-gradient accumulators out of TMEM and write this CTA's partial
         mbar_wait(&s.bars[BAR_DONE], 0);
@@ -1190,7 +1133,7 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
         cudaMemsetAsync(trace_dev, 0, 1024 * sizeof(long long), st);
         a.trace = trace_dev;
     }
-    TcSmem s(nullptr, nt, tl, NBUF_BWD, want_aff, NG_B);
+    TcSmem s(nullptr, nt, tl, NBUF_BWD, false, NG_B);
     const size_t smem = s.bytes + 1024;
     LMR_CHECK_ARG(smem <= 227 * 1024, "inr_backward (tensor-core path): needs %zu bytes of shared memory (> 227 KB)", smem);
     static size_t cache[2][5] = {};
@@ -1222,8 +1165,10 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
         if (int rc = launch_l0_partial<50>(a, l0part, wl.gridL0, st)) return rc;
         if (int rc = launch_finish_weights<50>(a, l0part, wl.gridMain, wl.gridL0, g_params, st)) return rc;
     }
-    if (want_aff) {
-        finish_affine_kernel<<<D, 128, 0, st>>>(a, g_angles, g_scalings, g_shears, g_translation);
+    if (want_aff) {  // the tile kernel wrote G0[d,p][o] = sum_n dz0: coordinate gradient and its moments pixel-parallel, then the 7 scalars per target
+        int nblk = 0;
+        if (int rc = launch_affine_grad<50>(a, &nblk, st)) return rc;
+        finish_affine_kernel<<<D, 128, 0, st>>>(a, nblk, g_angles, g_scalings, g_shears, g_translation);
         LMR_LAUNCH_OK();
     }
     return 0;
