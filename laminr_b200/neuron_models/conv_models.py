@@ -1,0 +1,201 @@
+"""Stacked-conv core + Gaussian readout response models (BASELINE config 4).
+
+Host-side mirrors of the three neuralpredictors classes the LAMINR pipeline can be pointed at:
+  * `Stacked2dCore`      -- neuralpredictors/layers/cores/conv2d.py:33-278 (plain `nn.Conv2d` + eval-mode BatchNorm + shifted ELU per
+                            layer; the features of the layers in `stack` are concatenated)
+  * `FullGaussian2d`     -- neuralpredictors/layers/readouts/gaussian.py:210-599 (one learned position per neuron, bilinear read of the
+                            feature map there, dot with a per-neuron feature vector, + bias)
+  * `FiringRateEncoder`  -- neuralpredictors/layers/encoders/firing_rate.py:4-61 (core -> readout -> elu(x + offset) + 1)
+Same constructor arguments (the subset the pipeline uses), same parameter / buffer names and the same RNG draw order, so a seed
+gives the reference's weights and a reference state_dict loads unchanged.  Variants that LAMINR never instantiates for this
+configuration (depth-separable / attention convolutions, skip > 1, grid predictors, shared features) raise NotImplementedError.
+
+STATUS: these modules compose stock PyTorch operators (cuDNN convolutions, `grid_sample`): config 4 therefore runs on the GENERIC
+path of `InvarianceManifold` (our INR / constraint / contrastive kernels + autograd around this model).  Hand-written sm_100a
+kernels for the convolution stack (tcgen05 implicit GEMM, BN folded, ELU epilogue, data-gradient) and the 4-tap readout are the
+next row of SURVEY 8 to be built; nothing here is on the fused path yet.
+"""
+import warnings
+from collections import OrderedDict
+from collections.abc import Iterable
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+
+class AdaptiveELU(nn.Module):
+    """elu(x - xshift) + yshift  (neuralpredictors/layers/activations.py:31-51)."""
+
+    def __init__(self, xshift, yshift):
+        super().__init__()
+        self.xshift, self.yshift = xshift, yshift
+
+    def forward(self, x):
+        return F.elu(x - self.xshift) + self.yshift
+
+
+class _LaplaceBuffer(nn.Module):
+    """Holds the 3x3 Laplace filter buffer the reference core registers for its (training-only) input regulariser, so that state_dict
+    keys match (`_input_weights_regularizer.laplace.filter`, neuralpredictors/regularizers.py:12-17,136-159)."""
+
+    def __init__(self):
+        super().__init__()
+        self.laplace = nn.Module()
+        self.laplace.register_buffer("filter", torch.tensor([[0.0, -1.0, 0.0], [-1.0, 4.0, -1.0], [0.0, -1.0, 0.0]])[None, None])
+
+
+class Stacked2dCore(nn.Module):
+    def __init__(self, input_channels, hidden_channels, input_kern, hidden_kern, layers=3, gamma_hidden=0, gamma_input=0.0, skip=0, stride=1,
+                 final_nonlinearity=True, elu_shift=(0, 0), bias=True, momentum=0.1, pad_input=True, hidden_padding=None, batch_norm=True,
+                 batch_norm_scale=True, independent_bn_bias=True, hidden_dilation=1, laplace_padding=0, input_regularizer="LaplaceL2", stack=None,
+                 use_avg_reg=True, depth_separable=False, attention_conv=False, linear=False):
+        super().__init__()
+        if depth_separable or attention_conv or skip > 1 or not independent_bn_bias or input_regularizer != "LaplaceL2":
+            raise NotImplementedError("laminr_b200 Stacked2dCore: only plain convolutions with the default batch-norm arrangement are mirrored")
+        self._input_weights_regularizer = _LaplaceBuffer()
+        self.num_layers, self.input_channels, self.hidden_channels = layers, input_channels, hidden_channels
+        self.gamma_input, self.gamma_hidden, self.skip, self.stride = gamma_input, gamma_hidden, skip, stride
+        self.input_kern, self.hidden_dilation, self.final_nonlinearity = input_kern, hidden_dilation, final_nonlinearity
+        self.elu_xshift, self.elu_yshift = elu_shift
+        self.bias, self.momentum, self.pad_input, self.batch_norm, self.linear = bias, momentum, pad_input, batch_norm, linear
+        self.stack = range(layers) if stack is None else ([*range(layers)[stack:]] if isinstance(stack, int) else stack)
+        self.hidden_kern = list(hidden_kern) if isinstance(hidden_kern, Iterable) else [hidden_kern] * (layers - 1)
+        self.hidden_padding = hidden_padding
+
+        self.features = nn.Sequential()
+        for l in range(layers):  # conv2d.py:202-234
+            layer = OrderedDict()
+            if l == 0:
+                # first conv: zero-padded k//2 only if pad_input; no conv bias when batch norm carries it (:204-210)
+                layer["conv"] = nn.Conv2d(input_channels, hidden_channels, input_kern, padding=input_kern // 2 if pad_input else 0,
+                                          bias=bias and not batch_norm)
+            else:
+                if self.hidden_padding is None:  # NB: computed once, from the first hidden kernel (:220-222)
+                    self.hidden_padding = ((self.hidden_kern[l - 1] - 1) * hidden_dilation + 1) // 2
+                layer["conv"] = nn.Conv2d(hidden_channels, hidden_channels, self.hidden_kern[l - 1], stride=stride, padding=self.hidden_padding,
+                                          dilation=hidden_dilation, bias=bias)
+            if batch_norm:
+                layer["norm"] = nn.BatchNorm2d(hidden_channels, momentum=momentum)
+            if not linear and (l < layers - 1 or final_nonlinearity):
+                layer["nonlin"] = AdaptiveELU(self.elu_xshift, self.elu_yshift)
+            self.features.add_module(f"layer{l}", nn.Sequential(layer))
+        for m in self.modules():  # Core.init_conv (cores/base.py:17-30), module order
+            if isinstance(m, nn.Conv2d):
+                nn.init.xavier_normal_(m.weight.data)
+                if m.bias is not None:
+                    m.bias.data.fill_(0)
+
+    def forward(self, x):
+        ret = []
+        for feat in self.features:
+            x = feat(x)
+            ret.append(x)
+        return torch.cat([ret[i] for i in self.stack], dim=1)
+
+    @property
+    def outchannels(self):
+        return len(self.features) * self.hidden_channels
+
+
+class FullGaussian2d(nn.Module):
+    def __init__(self, in_shape, outdims, bias, init_mu_range=0.1, init_sigma=1, batch_sample=True, align_corners=True, gauss_type="full",
+                 grid_mean_predictor=None, shared_features=None, shared_grid=None, source_grid=None, mean_activity=None, feature_reg_weight=1.0,
+                 **kwargs):
+        super().__init__()
+        if grid_mean_predictor is not None or shared_features is not None or shared_grid is not None:
+            raise NotImplementedError("laminr_b200 FullGaussian2d: grid predictors / shared features or grids are not mirrored")
+        if init_mu_range > 1.0 or init_mu_range <= 0.0 or init_sigma <= 0.0:
+            raise ValueError("either init_mu_range doesn't belong to [0.0, 1.0] or init_sigma_range is non-positive")
+        if gauss_type not in ("full", "uncorrelated", "isotropic"):
+            raise ValueError(f'gauss_type "{gauss_type}" not known')
+        self.in_shape, self.outdims, self.batch_sample, self.align_corners = in_shape, outdims, batch_sample, align_corners
+        self.gauss_type, self.init_mu_range, self.init_sigma, self.mean_activity = gauss_type, init_mu_range, init_sigma, mean_activity
+        self.feature_reg_weight = feature_reg_weight
+        c = in_shape[0]
+        self.grid_shape = (1, outdims, 1, 2)
+        sigma_shape = {"full": (1, outdims, 2, 2), "uncorrelated": (1, outdims, 1, 2), "isotropic": (1, outdims, 1, 1)}[gauss_type]
+        self._mu = nn.Parameter(torch.empty(*self.grid_shape))
+        self.sigma = nn.Parameter(torch.empty(*sigma_shape))
+        self._features = nn.Parameter(torch.empty(1, c, 1, outdims))
+        self.bias = nn.Parameter(torch.empty(outdims)) if bias else None
+        # gaussian.py:452-469: mu ~ U(+-init_mu_range), sigma ~ U(+-init_sigma) ('full') or the constant, features = 1/c, bias = mean activity or 0
+        self._mu.data.uniform_(-init_mu_range, init_mu_range)
+        if gauss_type != "full":
+            self.sigma.data.fill_(init_sigma)
+        else:
+            self.sigma.data.uniform_(-init_sigma, init_sigma)
+        self._features.data.fill_(1 / c)
+        if self.bias is not None:
+            if mean_activity is None:
+                warnings.warn("Readout is NOT initialized with mean activity but with 0!")
+                self.bias.data.fill_(0)
+            else:
+                self.bias.data = mean_activity
+
+    @property
+    def mu(self):
+        return self._mu
+
+    @property
+    def features(self):
+        return self._features
+
+    def sample_grid(self, batch_size, sample=None):
+        """gaussian.py:396-429.  Eval mode (what LAMINR must run in): grid = clamp(mu); mu itself is clamped in place."""
+        with torch.no_grad():
+            self._mu.clamp_(min=-1, max=1)
+        shape = (batch_size,) + self.grid_shape[1:]
+        sample = self.training if sample is None else sample
+        norm = self._mu.new_empty(*shape).normal_() if sample else self._mu.new_zeros(*shape)
+        if self.gauss_type != "full":
+            return torch.clamp(norm * self.sigma + self._mu, min=-1, max=1)
+        return torch.clamp(torch.einsum("ancd,bnid->bnic", self.sigma, norm) + self._mu, min=-1, max=1)
+
+    def forward(self, x, sample=None, shift=None, out_idx=None, **kwargs):
+        N, c, w, h = x.size()
+        if tuple(self.in_shape) != (c, w, h):
+            warnings.warn("the specified feature map dimension is not the readout's expected input dimension")
+        feat, bias, outdims = self._features.view(1, c, self.outdims), self.bias, self.outdims
+        grid = self.sample_grid(N, sample) if self.batch_sample else self.sample_grid(1, sample).expand(N, outdims, 1, 2)
+        if out_idx is not None:
+            if isinstance(out_idx, np.ndarray) and out_idx.dtype == bool:
+                out_idx = np.where(out_idx)[0]
+            feat, grid = feat[:, :, out_idx], grid[:, out_idx]
+            bias = bias[out_idx] if bias is not None else None
+            outdims = len(out_idx)
+        if shift is not None:
+            grid = grid + shift[:, None, None, :]
+        y = F.grid_sample(x, grid, align_corners=self.align_corners)  # grid[..., 0] indexes width; bilinear, zero padding
+        y = (y.squeeze(-1) * feat).sum(1).view(N, outdims)
+        return y + bias if bias is not None else y
+
+
+class FiringRateEncoder(nn.Module):
+    def __init__(self, core, readout, *, shifter=None, modulator=None, elu_offset=0.0):
+        super().__init__()
+        if shifter is not None or modulator is not None:
+            raise NotImplementedError("laminr_b200 FiringRateEncoder: shifter / modulator branches are not mirrored")
+        self.core, self.readout, self.shifter, self.modulator, self.offset = core, readout, None, None, elu_offset
+
+    def forward(self, inputs, *args, shift=None, detach_core=False, **kwargs):
+        x = self.core(inputs)
+        if detach_core:
+            x = x.detach()
+        kwargs.pop("data_key", None)
+        x = self.readout(x, shift=shift, **kwargs)
+        return F.elu(x + self.offset) + 1
+
+
+def conv_core_gaussian_model(input_shape=(1, 200, 200), n_neurons=128, hidden_channels=32, input_kern=9, hidden_kern=7, layers=3, seed=0):
+    """BASELINE config 4: random-init stacked-conv core (1 -> 32 channels, kernels 9/7/7, last layer read out) + full-Gaussian
+    readout with `n_neurons` outputs, as a firing-rate encoder in EVAL mode (batch-norm running statistics, readout at its mean positions)."""
+    torch.manual_seed(seed)
+    c, h, w = input_shape
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        core = Stacked2dCore(input_channels=c, hidden_channels=hidden_channels, input_kern=input_kern, hidden_kern=hidden_kern, layers=layers, stack=-1,
+                             pad_input=True)
+        readout = FullGaussian2d(in_shape=(hidden_channels, h, w), outdims=n_neurons, bias=True)
+    return FiringRateEncoder(core, readout).eval()

@@ -50,7 +50,9 @@ def _worker(rank, world, port, n_targets, q):
         # --- ragged gather of per-target results
         local = torch.arange(lo, hi, dtype=torch.float32)[:, None, None] * torch.ones(1, 3, 2)
         full = D.gather_ragged(local, n_targets, dst=0)
-        q.put((rank, [p.detach().clone() for p in mod.parameters()] + [mod.B.clone()], grids, stopped_at, means, None if full is None else full.clone(), (lo, hi)))
+        # numpy payloads are pickled by value; torch tensors would travel as shared-memory handles that die with this process
+        q.put((rank, [p.detach().numpy().copy() for p in mod.parameters()] + [mod.B.numpy().copy()], grids.numpy().copy(), stopped_at, means,
+               None if full is None else full.numpy().copy(), (lo, hi)))
     finally:
         dist.destroy_process_group()
 
@@ -69,8 +71,8 @@ def test_sharded_match_plumbing_world2(n_targets):
         assert p.exitcode == 0
     (r0, state0, grids0, stop0, means0, full0, b0), (r1, state1, grids1, stop1, means1, full1, b1) = res
     for a, b in zip(state0, state1):
-        assert torch.equal(a, b)                       # broadcast template state
-    assert torch.equal(grids0, grids1)                 # same jitter on every rank
+        assert np.array_equal(a, b)                    # broadcast template state
+    assert np.array_equal(grids0, grids1)              # same jitter on every rank
     assert stop0 == stop1 and stop0 is not None        # same (global) stop epoch
     np.testing.assert_allclose(means0, means1, rtol=0, atol=0)
     # unsharded reference of the stop rule
@@ -85,7 +87,7 @@ def test_sharded_match_plumbing_world2(n_targets):
     assert stop0 == want
     assert b0[1] == b1[0] and b0[0] == 0 and b1[1] == n_targets and (b0[1] - b0[0]) - (b1[1] - b1[0]) in (0, 1)
     assert full1 is None
-    assert torch.equal(full0[:, 0, 0], torch.arange(n_targets, dtype=torch.float32)) and full0.shape == (n_targets, 3, 2)
+    assert np.array_equal(full0[:, 0, 0], np.arange(n_targets, dtype=np.float32)) and full0.shape == (n_targets, 3, 2)
 
 
 def test_shard_bounds_cover_everything():
