@@ -373,12 +373,85 @@ def case_trajectory(laminr):
     np.savez_compressed(os.path.join(OUT, "learn_traj_20.npz"), **d)
 
 
+def export_convcore_arrays(model):
+    """Flat arrays of a FiringRateEncoder(Stacked2dCore, FullGaussian2d) in eval mode (the layout oracle.convcore_oracle.model_from_arrays reads)."""
+    core, ro = model.core, model.readout
+    d = dict(n_layers=np.int64(len(core.features)), xs=np.float64(core.elu_xshift), ys=np.float64(core.elu_yshift), offset=np.float64(model.offset),
+             align_corners=np.bool_(ro.align_corners), mu=npy(ro.mu).reshape(-1, 2), features=npy(ro.features).reshape(ro.features.shape[1], -1))
+    if ro.bias is not None:
+        d["bias"] = npy(ro.bias)
+    for l, feat in enumerate(core.features):
+        d[f"w{l}"] = npy(feat.conv.weight)
+        if feat.conv.bias is not None:
+            d[f"b{l}"] = npy(feat.conv.bias)
+        if hasattr(feat, "norm"):
+            d[f"bn{l}_mean"], d[f"bn{l}_var"] = npy(feat.norm.running_mean), npy(feat.norm.running_var)
+            d[f"bn{l}_gamma"], d[f"bn{l}_beta"], d[f"bn{l}_eps"] = npy(feat.norm.weight), npy(feat.norm.bias), np.float64(feat.norm.eps)
+        d[f"nonlin{l}"] = np.bool_(hasattr(feat, "nonlin"))
+    return d
+
+
+def case_convcore(laminr):
+    """FiringRateEncoder(Stacked2dCore, FullGaussian2d).eval() from the reference's vendored neuralpredictors: responses of all neurons,
+    and the input gradient of sum_b g_b * act[b, neuron_b] (what SingleNeuronModel + autograd give the learn / match / MEI loops)."""
+    import warnings
+
+    from neuralpredictors.layers.cores.conv2d import Stacked2dCore
+    from neuralpredictors.layers.encoders.firing_rate import FiringRateEncoder
+    from neuralpredictors.layers.readouts.gaussian import FullGaussian2d
+
+    cfgs = (
+        # name, C_in, hidden, k_in, k_hid, layers, (H, W), n_neurons, B, final_nonlin, elu_shift, offset, align_corners
+        ("convcore_a", 1, 8, 9, 7, 3, (40, 40), 6, 4, True, (0, 0), 0.0, True),       # config-4 kernel sizes, small frame: cones clipped by every border
+        ("convcore_b", 2, 4, 5, 3, 2, (24, 30), 5, 3, False, (0.3, 0.1), 0.2, True),  # 2 input channels, non-square, linear last layer, shifted ELU
+        ("convcore_c", 1, 12, 3, 3, 4, (17, 13), 4, 2, True, (0, 0), -0.1, False),    # 4 layers, align_corners=False
+    )
+    for name, cin, hc, kin, khid, L, (H, W), n, B, fnl, shift, off, ac in cfgs:
+        torch.manual_seed(11)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            core = Stacked2dCore(input_channels=cin, hidden_channels=hc, input_kern=kin, hidden_kern=khid, layers=L, stack=-1, pad_input=True,
+                                 final_nonlinearity=fnl, elu_shift=shift)
+            ro = FullGaussian2d(in_shape=(hc, H, W), outdims=n, bias=True, align_corners=ac)
+        g = torch.Generator().manual_seed(5)
+        with torch.no_grad():  # a trained-looking state: non-trivial batch-norm statistics, biases, feature vectors and positions
+            for feat in core.features:
+                feat.norm.running_mean.copy_(torch.randn(hc, generator=g) * 0.3)
+                feat.norm.running_var.copy_(torch.rand(hc, generator=g) * 1.5 + 0.25)
+                feat.norm.weight.copy_(torch.rand(hc, generator=g) + 0.5)
+                feat.norm.bias.copy_(torch.randn(hc, generator=g) * 0.2)
+                feat.conv.weight.mul_(2.0)
+                if feat.conv.bias is not None:
+                    feat.conv.bias.copy_(torch.randn(hc, generator=g) * 0.1)
+            ro._features.copy_(torch.randn(ro._features.shape, generator=g) * 0.5)
+            ro.bias.copy_(torch.randn(n, generator=g) * 0.2)
+            mu = torch.rand(1, n, 1, 2, generator=g) * 2 - 1
+            mu[0, 0, 0] = torch.tensor([1.0, -1.0])     # exactly on two borders
+            mu[0, 1, 0] = torch.tensor([-0.97, 0.99])   # cone clipped by two borders
+            mu[0, 2, 0] = torch.tensor([1.3, 0.2])      # outside: clamped by sample_grid
+            ro._mu.copy_(mu)
+        model = FiringRateEncoder(core, ro, elu_offset=off).eval()
+        x = (torch.randn(B, cin, H, W, generator=g) * 0.5).requires_grad_(True)
+        neuron_of_image = torch.tensor([(3 * b + 1) % n for b in range(B)])
+        neuron_of_image[0] = 0
+        g_act = torch.randn(B, generator=g)
+        acts = model(x)
+        (acts[torch.arange(B), neuron_of_image] * g_act).sum().backward()
+        d = export_convcore_arrays(model)   # after the forward: sample_grid clamps mu in place (gaussian.py:408)
+        d.update(x=npy(x), acts=npy(acts), neuron_of_image=neuron_of_image.numpy(), g_act=npy(g_act), g_x=npy(x.grad))
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     laminr = import_reference()
     torch.set_num_threads(os.cpu_count())
+    import sys
+    only = set(sys.argv[1:])
     for fn in (case_inr, case_match_inr, case_constrain, case_simresp, case_banks_100, case_simclr, case_training_utils,
-               case_adam, case_mei, case_learn_match_steps, case_trajectory):
+               case_adam, case_mei, case_learn_match_steps, case_trajectory, case_convcore):
+        if only and fn.__name__ not in only:
+            continue
         fn(laminr)
         print("wrote", fn.__name__)
 

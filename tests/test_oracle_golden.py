@@ -215,3 +215,25 @@ def test_learn_trajectory():
             b[l], mb[l], vb[l] = O.adam_step(b[l], out["db"][l], mb[l], vb[l], i + 1)
     for l in range(5):
         assert relerr(W[l], d[f"final_W{l}"]) < 1e-2, l
+
+
+@pytest.mark.parametrize("name", ["convcore_a", "convcore_b", "convcore_c"])
+def test_convcore_oracle_against_reference(name):
+    """Stacked-conv core + Gaussian readout + firing-rate encoder (row a-9): all-neuron responses and the input gradient of the
+    selected-neuron responses, as produced by the reference's vendored neuralpredictors modules."""
+    from oracle import convcore_oracle as CO
+
+    d = golden(name)
+    model = CO.model_from_arrays(d)
+    acts_all = CO.model_forward(d["x"], model)
+    assert relerr(acts_all, d["acts"]) < TOL
+    act, g_x, acts_all2 = CO.response_and_grad(d["x"], model, d["neuron_of_image"], d["g_act"])
+    B = d["x"].shape[0]
+    assert relerr(act, d["acts"][np.arange(B), d["neuron_of_image"]]) < TOL
+    assert relerr(g_x, d["g_x"]) < 5e-5
+    np.testing.assert_allclose(acts_all2, acts_all)
+    # the gradient is confined to the receptive-field cone of the selected neuron (what the CUDA path exploits)
+    k_total = sum(L["w"].shape[-1] - 1 for L in model["layers"]) + 2
+    for b in range(B):
+        nz = np.argwhere(np.abs(d["g_x"][b]).sum(0) > 0)
+        assert nz[:, 0].max() - nz[:, 0].min() + 1 <= k_total and nz[:, 1].max() - nz[:, 1].min() + 1 <= k_total
