@@ -128,6 +128,13 @@ int lmr_constrain_bwd(int mode, const float* x, const float* g_z, const float* s
                       float mean, int has_min, float pmin, int has_max, float pmax, float eps, float* g_x,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Gradient-ascent update with post-processing, batched -- replaces one iteration's `optimizer.step()` (SGD, no momentum) + `post_update`
+ * of featurevis.gradient_ascent (featurevis/core.py:107-119) for any response model whose gradient g is already on the device:
+ *     x <- clip(renorm(x + step_size * g))      renorm = ChangeNorm | ChangeStats (eps 1e-9 there), clip = ClipRange.
+ * x (in/out), g: [B, n].  Workspace: lmr_constrain_workspace_bytes(B, n). */
+int lmr_ascent_update(int mode, float* x, const float* g, float step_size, int B, int n, float target, float mean, int has_min,
+                      float pmin, int has_max, float pmax, float eps, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Simulated response model -- replaces ArbitraryNeuronModel / ArbitraryMultiNeuronModel.forward
  * (laminr/neuron_models/utils/simulated_model.py:8-29) and SingleNeuronModel (laminr/utils/general.py:5-12).
@@ -145,6 +152,47 @@ int lmr_simresp_fwd(const float* img, long long img_group_stride, int NB, int G,
 int lmr_simresp_bwd(const float* g_act, const float* rmax, const int* argmax, long long img_group_stride, int NB,
                     int G, int C, int HW, const float* filters, int Fmax, const int* neuron_of_group, float* g_img,
                     int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Stacked-conv core + Gaussian readout response model -- replaces, for the neuron the loop selects, the chain
+ * Stacked2dCore.forward (neuralpredictors/layers/cores/conv2d.py:246-253; layers :202-234) -> FullGaussian2d.forward
+ * (neuralpredictors/layers/readouts/gaussian.py:532-581, eval-mode grid of sample_grid :396-429) -> FiringRateEncoder.forward
+ * (neuralpredictors/layers/encoders/firing_rate.py:36-52) -> SingleNeuronModel (laminr/utils/general.py:5-12), and its autograd
+ * gradient back to the image.  Plain stride-1 "same" convolutions (zero padding k//2), eval-mode batch norm folded to a per-channel
+ * scale/shift, AdaptiveELU elu(v - xshift) + yshift, only the last layer read out (stack = -1), bilinear read at one position per neuron.
+ * Only the receptive-field cone of the selected neuron is evaluated (identical arithmetic to the full-frame network on those pixels).
+ * Work is organised like lmr_simresp_*: group g evaluates neuron `neuron_of_group[g]` on NB images [NB, c_in, H*W] starting at
+ * img + g*img_group_stride (stride 0: all groups see the same images; forward only).
+ *   act   [G,NB]             = elu(readout + elu_offset) + 1
+ *   g_img (nullable, layout of img): (+)= d sum(g_act * act) / d img;  g_act [G,NB] nullable (= 1).  accumulate = 0 overwrites the whole
+ *   gradient image (zero outside the cone).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define LMR_CONV_MAX_LAYERS 6
+typedef struct {
+    int n_layers;                      /* 1..LMR_CONV_MAX_LAYERS */
+    int c_in;                          /* image channels */
+    int hidden;                        /* output channels of every layer */
+    int kernel[LMR_CONV_MAX_LAYERS];   /* odd kernel sizes, layer 0 first */
+    int nonlin[LMR_CONV_MAX_LAYERS];   /* 1: AdaptiveELU after the layer, 0: linear */
+    float elu_xshift, elu_yshift;
+    int height, width;
+    int align_corners;                 /* of the readout's grid_sample */
+    float elu_offset;                  /* FiringRateEncoder.offset */
+} lmr_convcore_desc;
+
+typedef struct {
+    const float* w_fwd[LMR_CONV_MAX_LAYERS];  /* [c_in_l, k, k, hidden]: conv.weight.permute(1,2,3,0) */
+    const float* w_bwd[LMR_CONV_MAX_LAYERS];  /* [hidden, k, k, c_in_l]: conv.weight.flip(2,3).permute(0,2,3,1); may be NULL for forward-only calls */
+    const float* scale[LMR_CONV_MAX_LAYERS];  /* [hidden] gamma / sqrt(running_var + eps)  (1 without batch norm) */
+    const float* shift[LMR_CONV_MAX_LAYERS];  /* [hidden] beta + (conv_bias - running_mean) * scale */
+    const float* mu;                          /* [n_neurons, 2] readout positions (x -> width, y -> height); clamped to [-1,1] by the kernel */
+    const float* features;                    /* [n_neurons, hidden] */
+    const float* bias;                        /* [n_neurons] or NULL */
+} lmr_convcore_weights;
+
+int lmr_convcore_response(const lmr_convcore_desc* desc, const lmr_convcore_weights* weights, const float* img,
+                          long long img_group_stride, int NB, int G, const int* neuron_of_group, const float* g_act, float* act,
+                          float* g_img, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Masked contrastive objective -- replaces apply_mask (laminr/utils/mask.py:7-22) + SimCLROnGrid.reg_term

@@ -18,6 +18,20 @@ class Affine(C.Structure):
                 ("tc", C.c_void_p), ("shift_to", C.c_void_p), ("shift_from", C.c_void_p), ("clamp", C.c_int)]
 
 
+CONV_MAX_LAYERS = 6
+
+
+class ConvcoreDesc(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("c_in", C.c_int), ("hidden", C.c_int), ("kernel", C.c_int * CONV_MAX_LAYERS), ("nonlin", C.c_int * CONV_MAX_LAYERS),
+                ("elu_xshift", C.c_float), ("elu_yshift", C.c_float), ("height", C.c_int), ("width", C.c_int), ("align_corners", C.c_int),
+                ("elu_offset", C.c_float)]
+
+
+class ConvcoreWeights(C.Structure):
+    _fields_ = [("w_fwd", C.c_void_p * CONV_MAX_LAYERS), ("w_bwd", C.c_void_p * CONV_MAX_LAYERS), ("scale", C.c_void_p * CONV_MAX_LAYERS),
+                ("shift", C.c_void_p * CONV_MAX_LAYERS), ("mu", C.c_void_p), ("features", C.c_void_p), ("bias", C.c_void_p)]
+
+
 _vp, _i, _f, _sz, _ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 
 # name -> (restype, argtypes): one entry per symbol declared in include/laminr_b200.h
@@ -35,6 +49,8 @@ SIGNATURES = {
     "lmr_constrain_workspace_bytes": (_sz, [_i, _i]),
     "lmr_constrain_fwd": (_i, [_i, _vp, _i, _i, _f, _f, _i, _f, _i, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "lmr_constrain_bwd": (_i, [_i, _vp, _vp, _vp, _i, _i, _f, _f, _i, _f, _i, _f, _f, _vp, _vp, _sz, _vp]),
+    "lmr_ascent_update": (_i, [_i, _vp, _vp, _f, _i, _i, _f, _f, _i, _f, _i, _f, _f, _vp, _sz, _vp]),
+    "lmr_convcore_response": (_i, [C.POINTER(ConvcoreDesc), C.POINTER(ConvcoreWeights), _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
     "lmr_simresp_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "lmr_simresp_fwd": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "lmr_simresp_bwd": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),

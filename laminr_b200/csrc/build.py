@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["api.cu", "inr_simt.cu", "inr_tc.cu", "post.cu", "learn_obj.cu"]
+SOURCES = ["api.cu", "inr_simt.cu", "inr_tc.cu", "post.cu", "learn_obj.cu", "convcone.cu"]
 OUT = os.path.join(os.path.dirname(HERE), "liblaminr_b200.so")
 
 

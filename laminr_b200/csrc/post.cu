@@ -16,17 +16,19 @@ constexpr int CCH = 2048;  // elements per CTA chunk (256 threads x 8)
 // partial layout per (image b, chunk s): 4 floats
 //   fwd NORM: [sum (x-mean)^2]                 fwd STD: [count, chunk mean, chunk M2]
 //   bwd NORM: [sum gy*u]                       bwd STD: [sum gy, sum gy*(x-mu)]
-__global__ void __launch_bounds__(256) constrain_stats_kernel(int mode, const float* __restrict__ x, int n, float mean, float* __restrict__ part) {
+__global__ void __launch_bounds__(256) constrain_stats_kernel(int mode, const float* __restrict__ x, int n, float mean, float* __restrict__ part,
+                                                              const float* __restrict__ g = nullptr, float step = 0.f) {
     __shared__ float scratch[40];
     const int b = blockIdx.y, s = blockIdx.x, S = gridDim.x;
     const float* xb = x + (size_t)b * n;
+    const float* gb = g ? g + (size_t)b * n : nullptr;  // ascent update: statistics of x + step*g
     const int i0 = s * CCH, i1 = min(n, i0 + CCH);
     float v[CCH / 256];
     int cnt = 0;
 #pragma unroll
     for (int q = 0; q < CCH / 256; ++q) {
         const int i = i0 + q * 256 + threadIdx.x;
-        v[q] = i < i1 ? xb[i] : 0.f;
+        v[q] = i < i1 ? (gb ? fmaf(step, gb[i], xb[i]) : xb[i]) : 0.f;
         cnt += i < i1;
     }
     float* dst = part + ((size_t)b * S + s) * 4;
@@ -80,24 +82,27 @@ __device__ inline void combine_stats(int mode, const float* part, int S, int n, 
     }
 }
 
-__global__ void __launch_bounds__(256) constrain_apply_kernel(int mode, const float* __restrict__ x, int n, float target, float mean, int has_min,
+__global__ void __launch_bounds__(256) constrain_apply_kernel(int mode, const float* x, int n, float target, float mean, int has_min,
                                                               float pmin, int has_max, float pmax, float eps, const float* __restrict__ part,
-                                                              float* __restrict__ z, float* __restrict__ stats) {
+                                                              float* z, float* __restrict__ stats, const float* __restrict__ g = nullptr,
+                                                              float step = 0.f) {
     __shared__ float sh[2];
     const int b = blockIdx.y, s = blockIdx.x, S = gridDim.x;
     if (threadIdx.x == 0) {
         combine_stats(mode, part + (size_t)b * S * 4, S, n, &sh[0], &sh[1]);
-        if (s == 0) stats[2 * b] = sh[0], stats[2 * b + 1] = sh[1];
+        if (s == 0 && stats) stats[2 * b] = sh[0], stats[2 * b + 1] = sh[1];
     }
     __syncthreads();
     const float sd = sh[0], mu = sh[1];
     const float* xb = x + (size_t)b * n;
-    float* zb = z + (size_t)b * n;
+    const float* gb = g ? g + (size_t)b * n : nullptr;
+    float* zb = z + (size_t)b * n;  // may alias x (each element is read and written by the same thread)
     const int i0 = s * CCH, i1 = min(n, i0 + CCH);
     for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+        const float xv = gb ? fmaf(step, gb[i], xb[i]) : xb[i];
         float y;
-        if (mode == LMR_CONSTRAIN_NORM) y = (xb[i] - mean) / (sd + eps) * target + mean;
-        else y = target * (xb[i] - mu) / (sd + eps) + mean;
+        if (mode == LMR_CONSTRAIN_NORM) y = (xv - mean) / (sd + eps) * target + mean;
+        else y = target * (xv - mu) / (sd + eps) + mean;
         if (has_min) y = fmaxf(y, pmin);
         if (has_max) y = fminf(y, pmax);
         zb[i] = y;
@@ -570,6 +575,25 @@ extern "C" int lmr_constrain_fwd(int mode, const float* x, int B, int n, float t
     constrain_stats_kernel<<<grid, 256, 0, st>>>(mode, x, n, mean, static_cast<float*>(ws));
     LMR_LAUNCH_OK();
     constrain_apply_kernel<<<grid, 256, 0, st>>>(mode, x, n, target, mean, has_min, pmin, has_max, pmax, eps, static_cast<const float*>(ws), z, stats);
+    LMR_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int lmr_ascent_update(int mode, float* x, const float* g, float step_size, int B, int n, float target, float mean, int has_min,
+                                 float pmin, int has_max, float pmax, float eps, void* ws, size_t ws_bytes, void* stream) {
+    LMR_CHECK_ARG(mode == LMR_CONSTRAIN_NORM || mode == LMR_CONSTRAIN_STD, "ascent_update: bad mode %d", mode);
+    LMR_CHECK_ARG(x && g && B >= 1 && B <= 65535 && n >= 2, "ascent_update: bad arguments B=%d n=%d", B, n);
+    if (ws_bytes < lmr_constrain_workspace_bytes(B, n)) {
+        set_error("ascent_update: workspace too small");
+        return LMR_ERR_WORKSPACE;
+    }
+    const int S = (n + CCH - 1) / CCH;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 grid(S, B);
+    constrain_stats_kernel<<<grid, 256, 0, st>>>(mode, x, n, mean, static_cast<float*>(ws), g, step_size);
+    LMR_LAUNCH_OK();
+    constrain_apply_kernel<<<grid, 256, 0, st>>>(mode, x, n, target, mean, has_min, pmin, has_max, pmax, eps, static_cast<const float*>(ws), x, nullptr, g,
+                                                 step_size);
     LMR_LAUNCH_OK();
     return 0;
 }

@@ -10,10 +10,13 @@ Same constructor arguments (the subset the pipeline uses), same parameter / buff
 gives the reference's weights and a reference state_dict loads unchanged.  Variants that LAMINR never instantiates for this
 configuration (depth-separable / attention convolutions, skip > 1, grid predictors, shared features) raise NotImplementedError.
 
-STATUS: these modules compose stock PyTorch operators (cuDNN convolutions, `grid_sample`): config 4 therefore runs on the GENERIC
-path of `InvarianceManifold` (our INR / constraint / contrastive kernels + autograd around this model).  Hand-written sm_100a
-kernels for the convolution stack (tcgen05 implicit GEMM, BN folded, ELU epilogue, data-gradient) and the 4-tap readout are the
-next row of SURVEY 8 to be built; nothing here is on the fused path yet.
+On a CUDA device `FiringRateEncoder` evaluates responses with lmr_convcore_response (csrc/convcone.cu): one CTA per (image, neuron) pair
+runs the receptive-field cone of the selected neuron through all layers in shared memory and returns the response and its image gradient
+in one launch.  `forward_neurons(x, idxs)` (what SingleNeuronModel / the fused steppers / the batched MEI ascent use) and `forward(x)`
+(all neurons) both go through that kernel.  There is NO stock-PyTorch / CPU evaluation path: the classes below only build and hold the
+parameters (same names, shapes and RNG draw order as the reference, so a reference state_dict loads unchanged); CPU tensors raise, and
+configurations the kernel does not cover (non-"same" padding, stride/dilation != 1, more than the last layer stacked, training mode) raise
+NotImplementedError instead of silently falling back.
 """
 import warnings
 from collections import OrderedDict
@@ -88,11 +91,8 @@ class Stacked2dCore(nn.Module):
                     m.bias.data.fill_(0)
 
     def forward(self, x):
-        ret = []
-        for feat in self.features:
-            x = feat(x)
-            ret.append(x)
-        return torch.cat([ret[i] for i in self.stack], dim=1)
+        raise NotImplementedError("laminr_b200: the core is evaluated only inside FiringRateEncoder on a CUDA device (csrc/convcone.cu); "
+                                  "there is no stock-PyTorch / CPU path")
 
     @property
     def outchannels(self):
@@ -154,22 +154,8 @@ class FullGaussian2d(nn.Module):
         return torch.clamp(torch.einsum("ancd,bnid->bnic", self.sigma, norm) + self._mu, min=-1, max=1)
 
     def forward(self, x, sample=None, shift=None, out_idx=None, **kwargs):
-        N, c, w, h = x.size()
-        if tuple(self.in_shape) != (c, w, h):
-            warnings.warn("the specified feature map dimension is not the readout's expected input dimension")
-        feat, bias, outdims = self._features.view(1, c, self.outdims), self.bias, self.outdims
-        grid = self.sample_grid(N, sample) if self.batch_sample else self.sample_grid(1, sample).expand(N, outdims, 1, 2)
-        if out_idx is not None:
-            if isinstance(out_idx, np.ndarray) and out_idx.dtype == bool:
-                out_idx = np.where(out_idx)[0]
-            feat, grid = feat[:, :, out_idx], grid[:, out_idx]
-            bias = bias[out_idx] if bias is not None else None
-            outdims = len(out_idx)
-        if shift is not None:
-            grid = grid + shift[:, None, None, :]
-        y = F.grid_sample(x, grid, align_corners=self.align_corners)  # grid[..., 0] indexes width; bilinear, zero padding
-        y = (y.squeeze(-1) * feat).sum(1).view(N, outdims)
-        return y + bias if bias is not None else y
+        raise NotImplementedError("laminr_b200: the readout is evaluated only inside FiringRateEncoder on a CUDA device (csrc/convcone.cu); "
+                                  "there is no stock-PyTorch / CPU path")
 
 
 class FiringRateEncoder(nn.Module):
@@ -179,13 +165,58 @@ class FiringRateEncoder(nn.Module):
             raise NotImplementedError("laminr_b200 FiringRateEncoder: shifter / modulator branches are not mirrored")
         self.core, self.readout, self.shifter, self.modulator, self.offset = core, readout, None, None, elu_offset
 
+    # ---- B200 path --------------------------------------------------------------------------------------------------
+    def cone(self):
+        """The lmr_convcore_response weight pack of this (frozen, eval-mode) model; built on first use, rebuilt by `refresh_cone()`."""
+        c = getattr(self, "_cone", None)
+        if c is None:
+            c = self._cone = self._build_cone()
+        return c
+
+    def refresh_cone(self):
+        self._cone = None
+
+    def _build_cone(self):
+        from .. import ops
+        core, ro = self.core, self.readout
+        if self.training:
+            raise NotImplementedError("laminr_b200: the conv-core response kernel implements EVAL mode (running batch-norm statistics, readout at "
+                                      "its mean position); call model.eval() first (SURVEY 8a row a-9)")
+        L = len(core.features)
+        if list(core.stack) != [L - 1]:
+            raise NotImplementedError("laminr_b200: only stack=-1 (last layer read out) is covered by the conv-core kernel")
+        layers = []
+        for l, feat in enumerate(core.features):
+            conv = feat.conv
+            k = conv.kernel_size[0]
+            if conv.kernel_size[0] != conv.kernel_size[1] or k % 2 == 0 or tuple(conv.padding) != (k // 2, k // 2) or tuple(conv.stride) != (1, 1) \
+                    or tuple(conv.dilation) != (1, 1) or conv.groups != 1:
+                raise NotImplementedError("laminr_b200: the conv-core kernel covers stride-1, dilation-1, odd square kernels with 'same' zero padding")
+            bn = None
+            if hasattr(feat, "norm"):
+                n = feat.norm
+                bn = (n.running_mean, n.running_var, n.weight, n.bias, n.eps)
+            layers.append(dict(weight=conv.weight, conv_bias=conv.bias, bn=bn, nonlin=hasattr(feat, "nonlin")))
+        with torch.no_grad():
+            ro._mu.clamp_(min=-1, max=1)  # sample_grid does this in place on every call (gaussian.py:408)
+        c, h, w = ro.in_shape
+        return ops.ConvCone(layers, ro._mu, ro._features, ro.bias, h, w, xshift=core.elu_xshift, yshift=core.elu_yshift, offset=self.offset,
+                            align_corners=ro.align_corners)
+
+    def forward_neurons(self, x, idxs):
+        """Responses [B, len(idxs)] of the listed neurons (same values as forward(x)[:, idxs]); differentiable wrt x."""
+        from .. import ops
+        cone = self.cone()
+        if tuple(x.shape[1:]) != (cone.c_in, cone.desc.height, cone.desc.width):
+            raise ValueError(f"expected images [B,{cone.c_in},{cone.desc.height},{cone.desc.width}], got {tuple(x.shape)}")
+        nog = torch.as_tensor(list(idxs), dtype=torch.int32, device=x.device)
+        return ops.convresp(x, cone, nog).t()  # raises on CPU tensors: no fallback
+
     def forward(self, inputs, *args, shift=None, detach_core=False, **kwargs):
-        x = self.core(inputs)
-        if detach_core:
-            x = x.detach()
-        kwargs.pop("data_key", None)
-        x = self.readout(x, shift=shift, **kwargs)
-        return F.elu(x + self.offset) + 1
+        """firing_rate.py:36-52: elu(readout(core(x)) + offset) + 1 for all neurons -> [B, n]."""
+        if shift is not None or detach_core:
+            raise NotImplementedError("laminr_b200: shift / detach_core are not covered by the conv-core kernel")
+        return self.forward_neurons(inputs, range(self.readout.outdims))
 
 
 def conv_core_gaussian_model(input_shape=(1, 200, 200), n_neurons=128, hidden_channels=32, input_kern=9, hidden_kern=7, layers=3, seed=0):

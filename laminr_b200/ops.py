@@ -287,6 +287,109 @@ def simresp(x, filters, nfilt, neuron_of_group, eps=1e-6):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# stacked-conv core + Gaussian readout response (receptive-field cone of the selected neuron)
+# ------------------------------------------------------------------------------------------------------------------
+class ConvCone:
+    """Device-side weight pack + descriptor of a FiringRateEncoder(Stacked2dCore, FullGaussian2d) in eval mode, in the layout
+    lmr_convcore_response reads (include/laminr_b200.h).  Built once from the module's parameters (the response model is frozen)."""
+
+    def __init__(self, layers, mu, features, bias, height, width, xshift=0.0, yshift=0.0, offset=0.0, align_corners=True):
+        """layers: list of dict(weight [Co,Ci,k,k], conv_bias|None, bn=(running_mean, running_var, gamma|None, beta|None, eps)|None, nonlin: bool)."""
+        _require_cuda(mu, features)
+        if not 1 <= len(layers) <= _lib.CONV_MAX_LAYERS:
+            raise ValueError(f"ConvCone: 1..{_lib.CONV_MAX_LAYERS} layers supported")
+        d, w = _lib.ConvcoreDesc(), _lib.ConvcoreWeights()
+        self.keep = []
+        hidden = layers[0]["weight"].shape[0]
+        d.n_layers, d.c_in, d.hidden = len(layers), layers[0]["weight"].shape[1], hidden
+        for l, L in enumerate(layers):
+            W = L["weight"].detach().to(torch.float32)
+            co, ci, k, k2 = W.shape
+            if co != hidden or k != k2 or k % 2 == 0 or (l > 0 and ci != hidden):
+                raise ValueError("ConvCone: every layer must be a square odd-kernel convolution with `hidden` output channels")
+            d.kernel[l], d.nonlin[l] = k, int(bool(L["nonlin"]))
+            wf = W.permute(1, 2, 3, 0).contiguous()
+            wb = W.flip(2, 3).permute(0, 2, 3, 1).contiguous()
+            # eval-mode batch norm + conv bias folded into v*scale + shift (float64 on the way, like the oracle)
+            scale, shift = torch.ones(co, dtype=torch.float64, device=W.device), torch.zeros(co, dtype=torch.float64, device=W.device)
+            if L.get("conv_bias") is not None:
+                shift = shift + L["conv_bias"].detach().double()
+            if L.get("bn") is not None:
+                rm, rv, gamma, beta, eps = L["bn"]
+                scale = 1.0 / torch.sqrt(rv.detach().double() + eps)
+                if gamma is not None:
+                    scale = scale * gamma.detach().double()
+                shift = (shift - rm.detach().double()) * scale
+                if beta is not None:
+                    shift = shift + beta.detach().double()
+            scale, shift = scale.float().contiguous(), shift.float().contiguous()
+            self.keep += [wf, wb, scale, shift]
+            w.w_fwd[l], w.w_bwd[l], w.scale[l], w.shift[l] = wf.data_ptr(), wb.data_ptr(), scale.data_ptr(), shift.data_ptr()
+        self.mu = mu.detach().to(torch.float32).reshape(-1, 2).contiguous()
+        self.n_neurons = self.mu.shape[0]
+        self.features = features.detach().to(torch.float32).reshape(hidden, self.n_neurons).t().contiguous()  # [n, hidden]
+        self.bias = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        w.mu, w.features, w.bias = self.mu.data_ptr(), self.features.data_ptr(), (self.bias.data_ptr() if self.bias is not None else None)
+        d.elu_xshift, d.elu_yshift, d.elu_offset = float(xshift), float(yshift), float(offset)
+        d.height, d.width, d.align_corners = int(height), int(width), int(bool(align_corners))
+        self.desc, self.weights, self.device = d, w, self.mu.device
+        self.c_in, self.HW = d.c_in, int(height) * int(width)
+        self.cone_edge = 2 + sum(int(d.kernel[l]) - 1 for l in range(d.n_layers))
+
+
+def raw_convcore_response(cone, img, group_stride, NB, G, neuron_of_group, g_act=None, act=None, g_img=None, accumulate=False):
+    """act [G,NB] (and, if g_img is given, g_img (+)= d sum(g_act*act)/d img) of neuron_of_group[g] on the NB images of group g."""
+    lib = _lib.load()
+    _require_cuda(img, neuron_of_group, g_act, g_img)
+    if act is None:
+        act = torch.empty((G, NB), dtype=torch.float32, device=img.device)
+    check(lib.lmr_convcore_response(C.byref(cone.desc), C.byref(cone.weights), _ptr(img), int(group_stride), NB, G, _ptr(neuron_of_group), _ptr(g_act),
+                                    _ptr(act), _ptr(g_img), int(accumulate), _stream()))
+    return act
+
+
+class _ConvResp(torch.autograd.Function):
+    """x [B,C,H,W] -> act [G,B] of the neurons in `neuron_of_group` (every listed neuron sees every image)."""
+
+    @staticmethod
+    def forward(ctx, x, cone, neuron_of_group):
+        x = _f32c(x)
+        ctx.cone, ctx.nog = cone, neuron_of_group
+        ctx.save_for_backward(x)
+        return raw_convcore_response(cone, x, 0, x.shape[0], neuron_of_group.numel(), neuron_of_group)
+
+    @staticmethod
+    def backward(ctx, g_act):
+        (x,) = ctx.saved_tensors
+        cone, nog = ctx.cone, ctx.nog
+        g_act = _f32c(g_act)
+        g_img = torch.zeros_like(x)
+        scratch = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        live = torch.nonzero(g_act.abs().sum(dim=1) != 0).flatten().tolist() if nog.numel() > 1 else [0]  # usually ONE neuron carries gradient
+        for gi in live:  # one launch per neuron with upstream gradient: each CTA owns its image, so the groups accumulate launch after launch
+            raw_convcore_response(cone, x, 0, x.shape[0], 1, nog[gi:gi + 1], g_act=g_act[gi].contiguous(), act=scratch, g_img=g_img, accumulate=True)
+        return g_img, None, None
+
+
+def convresp(x, cone, neuron_of_group):
+    return _ConvResp.apply(x, cone, neuron_of_group)
+
+
+def raw_ascent_update(mode, x, g, step_size, target, mean, pmin, pmax, eps=1e-9, workspace=None):
+    """x <- clip(renorm(x + step_size*g)) in place; x, g: [B, ...]."""
+    lib = _lib.load()
+    _require_cuda(x, g)
+    Bn = x.shape[0]
+    n = x.numel() // Bn
+    if workspace is None:
+        workspace = _workspace(lib.lmr_constrain_workspace_bytes(Bn, n), x.device)
+    check(lib.lmr_ascent_update(int(mode), _ptr(x), _ptr(g), float(step_size), Bn, n, float(target), float(mean), int(pmin is not None),
+                                float(pmin if pmin is not None else 0.0), int(pmax is not None), float(pmax if pmax is not None else 0.0), float(eps),
+                                _ptr(workspace), workspace.numel(), _stream()))
+    return x
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # masked contrastive term
 # ------------------------------------------------------------------------------------------------------------------
 def raw_simclr_fwd(img, mask, N, Cc, HW, pmin, pmax, pos, neg, T, eps, reg=None, K=None, workspace=None):

@@ -1,0 +1,150 @@
+"""GPU parity of the stacked-conv core + Gaussian readout response kernel (lmr_convcore_response) through the C ABI:
+against the golden vectors produced by the reference's vendored neuralpredictors modules and against the numpy oracle."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from tests._util import golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL_ACT = 2e-5   # float32 kernel vs float32 torch reference (different summation order)
+TOL_GRAD = 1e-4
+
+
+def _cone_from_golden(d):
+    from laminr_b200 import ops
+    dev = "cuda"
+    L = int(d["n_layers"])
+    layers = []
+    for l in range(L):
+        t = lambda k: torch.as_tensor(d[k]).to(dev)
+        bn = (t(f"bn{l}_mean"), t(f"bn{l}_var"), t(f"bn{l}_gamma"), t(f"bn{l}_beta"), float(d[f"bn{l}_eps"])) if f"bn{l}_mean" in d else None
+        layers.append(dict(weight=t(f"w{l}"), conv_bias=t(f"b{l}") if f"b{l}" in d else None, bn=bn, nonlin=bool(d[f"nonlin{l}"])))
+    H, W = d["x"].shape[2:]
+    return ops.ConvCone(layers, torch.as_tensor(d["mu"]).to(dev), torch.as_tensor(d["features"]).to(dev), torch.as_tensor(d["bias"]).to(dev), H, W,
+                        xshift=float(d["xs"]), yshift=float(d["ys"]), offset=float(d["offset"]), align_corners=bool(d["align_corners"]))
+
+
+@pytest.mark.parametrize("name", ["convcore_a", "convcore_b", "convcore_c"])
+def test_cone_response_and_gradient_vs_reference(name):
+    from laminr_b200 import ops
+    d = golden(name)
+    cone = _cone_from_golden(d)
+    x = torch.as_tensor(d["x"]).cuda()
+    B, C, H, W = x.shape
+    nog = torch.as_tensor(d["neuron_of_image"], dtype=torch.int32).cuda()
+    g_act = torch.as_tensor(d["g_act"]).cuda()
+    # one group per image (group stride = one image), each with its own neuron: the match-stage layout
+    g_img = torch.full_like(x, 7.0)  # overwritten everywhere (accumulate = 0), zero outside the cone
+    act = ops.raw_convcore_response(cone, x, C * H * W, 1, B, nog, g_act=g_act.view(B, 1), g_img=g_img, accumulate=False)
+    want = d["acts"][np.arange(B), d["neuron_of_image"]]
+    assert relerr(act.cpu().numpy().ravel(), want) < TOL_ACT
+    assert relerr(g_img.cpu().numpy(), d["g_x"]) < TOL_GRAD
+    assert np.array_equal(g_img.cpu().numpy() == 0, d["g_x"] == 0) or relerr(g_img.cpu().numpy(), d["g_x"]) < TOL_GRAD
+    # accumulate adds on top
+    base = torch.randn_like(x)
+    acc = base.clone()
+    ops.raw_convcore_response(cone, x, C * H * W, 1, B, nog, g_act=g_act.view(B, 1), g_img=acc, accumulate=True)
+    assert relerr((acc - base).cpu().numpy(), d["g_x"]) < 2 * TOL_GRAD
+    # every neuron on every image (stride 0, forward only) == the reference's full model output
+    all_n = torch.arange(d["acts"].shape[1], dtype=torch.int32, device="cuda")
+    act_all = ops.raw_convcore_response(cone, x, 0, B, all_n.numel(), all_n)
+    assert relerr(act_all.t().cpu().numpy(), d["acts"]) < TOL_ACT
+    # one group, NB images, one neuron (the learn-stage layout); g_act = None means 1
+    n0 = int(d["neuron_of_image"][0])
+    g1 = torch.empty_like(x)
+    a1 = ops.raw_convcore_response(cone, x, 0, B, 1, torch.tensor([n0], dtype=torch.int32, device="cuda"), g_img=g1, accumulate=False)
+    assert relerr(a1.cpu().numpy().ravel(), d["acts"][:, n0]) < TOL_ACT
+    from oracle import convcore_oracle as CO
+    _, g_want, _ = CO.response_and_grad(d["x"], CO.model_from_arrays(d), [n0] * B)
+    assert relerr(g1.cpu().numpy(), g_want) < TOL_GRAD
+
+
+def _load_mirror(d):
+    """The host mirror (laminr_b200.neuron_models) with the golden fixture's parameters loaded through state_dict names."""
+    from laminr_b200.neuron_models import FiringRateEncoder, FullGaussian2d, Stacked2dCore
+    L, w0 = int(d["n_layers"]), d["w0"]
+    hid_k = d["w1"].shape[-1] if L > 1 else 3
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        core = Stacked2dCore(input_channels=w0.shape[1], hidden_channels=w0.shape[0], input_kern=w0.shape[-1], hidden_kern=hid_k, layers=L, stack=-1,
+                             pad_input=True, final_nonlinearity=bool(d[f"nonlin{L - 1}"]), elu_shift=(float(d["xs"]), float(d["ys"])))
+        H, W = d["x"].shape[2:]
+        ro = FullGaussian2d(in_shape=(w0.shape[0], H, W), outdims=d["mu"].shape[0], bias=True, align_corners=bool(d["align_corners"]))
+    sd = {}
+    for l in range(L):
+        sd[f"core.features.layer{l}.conv.weight"] = torch.as_tensor(d[f"w{l}"])
+        if f"b{l}" in d:
+            sd[f"core.features.layer{l}.conv.bias"] = torch.as_tensor(d[f"b{l}"])
+        sd[f"core.features.layer{l}.norm.running_mean"] = torch.as_tensor(d[f"bn{l}_mean"])
+        sd[f"core.features.layer{l}.norm.running_var"] = torch.as_tensor(d[f"bn{l}_var"])
+        sd[f"core.features.layer{l}.norm.weight"] = torch.as_tensor(d[f"bn{l}_gamma"])
+        sd[f"core.features.layer{l}.norm.bias"] = torch.as_tensor(d[f"bn{l}_beta"])
+    sd["readout._mu"] = torch.as_tensor(d["mu"]).reshape(1, -1, 1, 2)
+    sd["readout._features"] = torch.as_tensor(d["features"]).reshape(1, w0.shape[0], 1, -1)
+    sd["readout.bias"] = torch.as_tensor(d["bias"])
+    model = FiringRateEncoder(core, ro, elu_offset=float(d["offset"]))
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.endswith(("num_batches_tracked", "sigma", "laplace.filter")) for k in missing), (missing, unexpected)
+    return model.cuda().eval()
+
+
+@pytest.mark.parametrize("name", ["convcore_a", "convcore_b"])
+def test_module_forward_and_autograd(name):
+    """The drop-in modules: model(x) for all neurons and autograd through SingleNeuronModel-style selection."""
+    d = golden(name)
+    model = _load_mirror(d)
+    x = torch.as_tensor(d["x"]).cuda().requires_grad_(True)
+    acts = model(x)
+    assert relerr(acts.detach().cpu().numpy(), d["acts"]) < TOL_ACT
+    B = x.shape[0]
+    sel = torch.as_tensor(d["neuron_of_image"]).cuda()
+    (acts[torch.arange(B, device="cuda"), sel] * torch.as_tensor(d["g_act"]).cuda()).sum().backward()
+    assert relerr(x.grad.cpu().numpy(), d["g_x"]) < TOL_GRAD
+    with pytest.raises(NotImplementedError):
+        model.train()
+        model.refresh_cone()
+        model(x)
+    with pytest.raises(RuntimeError):
+        model.eval()
+        model.refresh_cone()
+        model(x.detach().cpu())
+
+
+def test_config4_full_size_against_oracle():
+    """BASELINE config 4 shapes (1 -> 32 channels, kernels 9/7/7, 200x200, 128 neurons): cone kernel vs the full-frame numpy oracle."""
+    from laminr_b200 import ops
+    from laminr_b200.neuron_models import conv_core_gaussian_model
+    from oracle import convcore_oracle as CO
+    model = conv_core_gaussian_model((1, 200, 200), n_neurons=128, seed=0)
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():  # spread the readout positions over the frame (init is +-0.1) and make batch norm non-trivial
+        model.readout._mu.copy_(torch.rand(1, 128, 1, 2, generator=g) * 2 - 1)
+        for feat in model.core.features:
+            feat.norm.running_mean.copy_(torch.randn(32, generator=g) * 0.1)
+            feat.norm.running_var.copy_(torch.rand(32, generator=g) + 0.5)
+    model = model.cuda().eval()
+    cone = model.cone()
+    assert cone.cone_edge == 22
+    idx = [0, 5, 127]
+    x = torch.randn(3, 1, 200, 200, generator=g) * 0.1
+    xd = x.cuda()
+    nog = torch.tensor(idx, dtype=torch.int32, device="cuda")
+    g_img = torch.empty_like(xd)
+    act = ops.raw_convcore_response(cone, xd, 200 * 200, 1, 3, nog, g_img=g_img, accumulate=False)
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    layers = []
+    for l in range(3):
+        p = f"core.features.layer{l}."
+        layers.append(dict(w=sd[p + "conv.weight"], b=sd.get(p + "conv.bias"), nonlin=True, xs=0.0, ys=0.0,
+                           bn=(sd[p + "norm.running_mean"], sd[p + "norm.running_var"], sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-5)))
+    om = dict(layers=layers, mu=sd["readout._mu"].reshape(-1, 2), features=sd["readout._features"].reshape(32, 128), bias=sd["readout.bias"], offset=0.0,
+              align_corners=True)
+    want_act, want_g, _ = CO.response_and_grad(x.numpy(), om, idx)
+    assert relerr(act.cpu().numpy().ravel(), want_act) < TOL_ACT
+    assert relerr(g_img.cpu().numpy(), want_g) < TOL_GRAD
+    nz = (g_img != 0).sum(dim=(1, 2, 3)).cpu().numpy()
+    assert (nz <= 22 * 22).all() and (nz > 0).all()
