@@ -26,6 +26,56 @@ class _Constraint:
         self.pmin, self.pmax = img_transf.pixel_min, img_transf.pixel_max
 
 
+class _SimulatedResponse:
+    """Response backend for `ArbitraryMultiNeuronModel` populations (lmr_simresp_*)."""
+    launches_fwd, launches_fwd_bwd = 2, 3
+
+    def __init__(self, model, D, N, P, dev):
+        self.model = model
+        self.rmax = torch.empty((D, N), dtype=torch.float32, device=dev)
+        self.argmax = torch.empty((D, N), dtype=torch.int32, device=dev)
+        self.ws = _ws(_lib.load().lmr_simresp_workspace_bytes(D, N, model.packed_filters.shape[1], P), dev)
+
+    def forward(self, z, stride, N, D, Cc, P, nog, act):
+        m = self.model
+        ops.raw_simresp_fwd(z, stride, N, D, Cc, P, m.packed_filters, m.nfilt, nog, m.eps, out=(act, self.rmax, self.argmax), workspace=self.ws)
+
+    def forward_backward(self, z, stride, N, D, Cc, P, nog, g_act, act, g_z, accumulate):
+        self.forward(z, stride, N, D, Cc, P, nog, act)
+        ops.raw_simresp_bwd(g_act, self.rmax, self.argmax, stride, N, D, Cc, P, self.model.packed_filters, nog, g_z, accumulate=accumulate)
+
+
+class _ConvResponse:
+    """Response backend for FiringRateEncoder(Stacked2dCore, FullGaussian2d): lmr_convcore_response evaluates the selected neuron's
+    receptive-field cone, forward and image gradient in ONE launch (the upstream gradient of the loops is a constant per image)."""
+    launches_fwd, launches_fwd_bwd = 1, 1
+
+    def __init__(self, model, D, N, P, dev):
+        self.cone = model.cone()
+        if self.cone.HW != P:
+            raise ValueError("response model and template resolution differ")
+
+    def forward(self, z, stride, N, D, Cc, P, nog, act):
+        ops.raw_convcore_response(self.cone, z, stride, N, D, nog, act=act)
+
+    def forward_backward(self, z, stride, N, D, Cc, P, nog, g_act, act, g_z, accumulate):
+        ops.raw_convcore_response(self.cone, z, stride, N, D, nog, g_act=g_act, act=act, g_img=g_z, accumulate=accumulate)
+
+
+def response_backend(model, D, N, P, dev):
+    from .neuron_models.utils.simulated_model import ArbitraryMultiNeuronModel
+    if isinstance(model, ArbitraryMultiNeuronModel):
+        return _SimulatedResponse(model, D, N, P, dev)
+    if hasattr(model, "cone"):
+        return _ConvResponse(model, D, N, P, dev)
+    raise TypeError("fused path: unsupported response model %s" % type(model).__name__)
+
+
+def fused_response_supported(model):
+    from .neuron_models.utils.simulated_model import ArbitraryMultiNeuronModel
+    return isinstance(model, ArbitraryMultiNeuronModel) or hasattr(model, "cone")
+
+
 class LearnStepper:
     def __init__(self, template, img_transf, model, neuron_idx, rf_mask, mei_act, grid_reg, pixel_min, pixel_max, n_grid, lr=1e-3,
                  reg_scale=2.0, precision=None, use_graph=True):
@@ -50,8 +100,8 @@ class LearnStepper:
         self.g_z = torch.empty_like(self.img_pre)
         self.g_x = torch.empty_like(self.img_pre)
         self.stats = torch.empty((N, 2), **f32)
-        self.act, self.rmax = torch.empty((1, N), **f32), torch.empty((1, N), **f32)
-        self.argmax = torch.empty((1, N), dtype=torch.int32, device=dev)
+        self.act = torch.empty((1, N), **f32)
+        self.resp = response_backend(model, 1, N, P, dev)
         self.reg, self.K = torch.empty(1, **f32), torch.empty((N, N), **f32)
         self.g_act = torch.full((1, N), -1.0 / (N * self.mei_act), **f32)
         self.g_reg = torch.full((1,), -float(reg_scale), **f32)  # d loss / d reg = -reg_scale (host float, changes between epochs)
@@ -62,14 +112,16 @@ class LearnStepper:
         self.ws_fwd = _ws(lib.lmr_inr_forward_workspace_bytes(C.byref(d), N, P, 1), dev)
         self.ws_bwd = _ws(lib.lmr_inr_backward_workspace_bytes(C.byref(d), N, P, 1), dev)
         self.ws_con = _ws(lib.lmr_constrain_workspace_bytes(N, Cc * P), dev)
-        self.ws_resp = _ws(lib.lmr_simresp_workspace_bytes(1, N, model.packed_filters.shape[1], P), dev)
         self.ws_clr = _ws(lib.lmr_simclr_workspace_bytes(N, Cc, P), dev)
         self.use_graph, self.graph, self.eval_graph = use_graph, None, None
-        # fused objective (one persistent launch for constraint + response + contrastive, forward and backward) when it fits
-        self.bank = model.packed_filters[int(neuron_idx), :int(model.nfilt[int(neuron_idx)].item())].contiguous()
+        # fused objective (one persistent launch for constraint + response + contrastive, forward and backward) for simulated neurons when it fits
         self.loss_buf = torch.zeros(1, **f32)
-        self.ws_obj = ops.learn_objective_workspace(N, Cc, P, self.bank.shape[0], dev)
-        self.kernels_per_step = 8 if self.ws_obj is not None else 19
+        self.ws_obj = None
+        if isinstance(self.resp, _SimulatedResponse):
+            self.bank = model.packed_filters[int(neuron_idx), :int(model.nfilt[int(neuron_idx)].item())].contiguous()
+            self.ws_obj = ops.learn_objective_workspace(N, Cc, P, self.bank.shape[0], dev)
+        # inr fwd (2) + [objective (1) | constrain fwd (2) + simclr fwd (2) + simclr bwd (1) + response + constrain bwd (2)] + inr bwd (4) + adam (1)
+        self.kernels_per_step = 8 if self.ws_obj is not None else 14 + self.resp.launches_fwd_bwd
 
     def set_reg_scale(self, reg_scale):
         self.g_reg.fill_(-float(reg_scale))
@@ -80,8 +132,7 @@ class LearnStepper:
         ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, out=self.img_pre.view(1, N, Cc, P),
                             precision=self.precision, workspace=self.ws_fwd)
         ops.raw_constrain_fwd(c.mode, self.img_pre, c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.z, stats=self.stats, workspace=self.ws_con)
-        ops.raw_simresp_fwd(self.z, 0, N, 1, Cc, P, self.model.packed_filters, self.model.nfilt, self.nog, self.model.eps,
-                            out=(self.act, self.rmax, self.argmax), workspace=self.ws_resp)
+        self.resp.forward(self.z, 0, N, 1, Cc, P, self.nog, self.act)
 
     def _train(self):
         t, c, N, Cc, P = self.t, self.con, self.N, self.C, self.P
@@ -91,20 +142,22 @@ class LearnStepper:
                                 precision=self.precision, workspace=self.ws_fwd)
             ops.raw_learn_objective(c.mode, self.img_pre, c.target, c.mean, c.pmin, c.pmax, c.eps, self.bank, self.model.eps, self.mei_act, self.mask,
                                     r.flat_neighbor_mask_pos, r.flat_neighbor_mask_neg, r.temperature, r.eps, self.g_reg, self.z, self.act.view(-1),
-                                    self.reg, self.loss_buf, self.g_x, self.ws_obj, stats=self.stats, rmax=self.rmax.view(-1), argmax=self.argmax.view(-1),
-                                    K=self.K)
+                                    self.reg, self.loss_buf, self.g_x, self.ws_obj, stats=self.stats, rmax=self.resp.rmax.view(-1),
+                                    argmax=self.resp.argmax.view(-1), K=self.K)
             ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, self.g_x.view(1, N, Cc, P), want_params=True,
                                  precision=self.precision, workspace=self.ws_bwd, g_params=self.g_flat, forward_workspace=self.ws_fwd)
             ops.raw_adam_step(self.flat, self.g_flat, self.m, self.v, self.step_count, lr=self.lr)
             return
-        self._forward()
+        ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, out=self.img_pre.view(1, N, Cc, P),
+                            precision=self.precision, workspace=self.ws_fwd)
+        ops.raw_constrain_fwd(c.mode, self.img_pre, c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.z, stats=self.stats, workspace=self.ws_con)
         ops.raw_simclr_fwd(self.z, self.mask, N, Cc, P, self.pixel_min, self.pixel_max, r.flat_neighbor_mask_pos, r.flat_neighbor_mask_neg,
                            r.temperature, r.eps, reg=self.reg, K=self.K, workspace=self.ws_clr)
-        ops.raw_simresp_bwd(self.g_act, self.rmax, self.argmax, 0, N, 1, Cc, P, self.model.packed_filters, self.nog, self.g_z, accumulate=False)
-        ops.raw_simclr_bwd(self.z, self.mask, self.K, self.g_reg, 1.0, N, Cc, P, self.pixel_min, self.pixel_max, self.g_z, accumulate=True)
+        ops.raw_simclr_bwd(self.z, self.mask, self.K, self.g_reg, 1.0, N, Cc, P, self.pixel_min, self.pixel_max, self.g_z, accumulate=False)
+        self.resp.forward_backward(self.z, 0, N, 1, Cc, P, self.nog, self.g_act, self.act, self.g_z, True)  # response and its gradient, added to g_z
         ops.raw_constrain_bwd(c.mode, self.img_pre, self.g_z, self.stats, c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.g_x, workspace=self.ws_con)
         ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, self.g_x.view(1, N, Cc, P), want_params=True,
-                             precision=self.precision, workspace=self.ws_bwd, g_params=self.g_flat)
+                             precision=self.precision, workspace=self.ws_bwd, g_params=self.g_flat, forward_workspace=self.ws_fwd)
         ops.raw_adam_step(self.flat, self.g_flat, self.m, self.v, self.step_count, lr=self.lr)
 
     def _capture(self, fn):
@@ -164,8 +217,8 @@ class MatchStepper:
         self.g_z = torch.empty_like(self.img_pre)
         self.g_x = torch.empty_like(self.img_pre)
         self.stats = torch.empty((D * N, 2), **f32)
-        self.act, self.rmax = torch.empty((D, N), **f32), torch.empty((D, N), **f32)
-        self.argmax = torch.empty((D, N), dtype=torch.int32, device=dev)
+        self.act = torch.empty((D, N), **f32)
+        self.resp = response_backend(model, D, N, P, dev)
         self.g_act = (-1.0 / (N * self.Dtot * self.mei_acts))[:, None].expand(D, N).contiguous()
         self.aff_mod = template.coordinate_transform.transforms.Affine
         a = self.aff_mod
@@ -179,25 +232,27 @@ class MatchStepper:
         self.ws_fwd = _ws(lib.lmr_inr_forward_workspace_bytes(C.byref(d), N, P, D), dev)
         self.ws_bwd = _ws(lib.lmr_inr_backward_workspace_bytes(C.byref(d), N, P, D), dev)
         self.ws_con = _ws(lib.lmr_constrain_workspace_bytes(D * N, Cc * P), dev)
-        self.ws_resp = _ws(lib.lmr_simresp_workspace_bytes(D, N, model.packed_filters.shape[1], P), dev)
         self.use_graph, self.graph = use_graph, None
 
     def _affine(self):
         return self.t.affine_args()
 
-    def _forward(self):
+    def _images(self):
         t, c, N, D, Cc, P = self.t, self.con, self.N, self.D, self.C, self.P
         ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, self._affine(), out=self.img_pre.view(D, N, Cc, P),
                             precision=self.precision, workspace=self.ws_fwd)
         ops.raw_constrain_fwd(c.mode, self.img_pre.view(D * N, Cc, P), c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.z.view(D * N, Cc, P),
                               stats=self.stats, workspace=self.ws_con)
-        ops.raw_simresp_fwd(self.z, N * Cc * P, N, D, Cc, P, self.model.packed_filters, self.model.nfilt, self.nog, self.model.eps,
-                            out=(self.act, self.rmax, self.argmax), workspace=self.ws_resp)
+
+    def _forward(self):
+        N, D, Cc, P = self.N, self.D, self.C, self.P
+        self._images()
+        self.resp.forward(self.z, N * Cc * P, N, D, Cc, P, self.nog, self.act)
 
     def _train(self):
         t, c, N, D, Cc, P = self.t, self.con, self.N, self.D, self.C, self.P
-        self._forward()
-        ops.raw_simresp_bwd(self.g_act, self.rmax, self.argmax, N * Cc * P, N, D, Cc, P, self.model.packed_filters, self.nog, self.g_z, accumulate=False)
+        self._images()
+        self.resp.forward_backward(self.z, N * Cc * P, N, D, Cc, P, self.nog, self.g_act, self.act, self.g_z, False)
         ops.raw_constrain_bwd(c.mode, self.img_pre.view(D * N, Cc, P), self.g_z.view(D * N, Cc, P), self.stats, c.target, c.mean, c.pmin, c.pmax, c.eps,
                               out=self.g_x.view(D * N, Cc, P), workspace=self.ws_con)
         ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, self._affine(), self.g_x.view(D, N, Cc, P),

@@ -5,7 +5,8 @@ Mirror of the reference interface laminr/inv_temp_learn_match.py:23-650: same co
 The loops keep the reference's control flow exactly (scheduler, stop rules, RNG draw order); what changes is what
 runs inside a step:
 
-  * simulated populations (`neuron_models.simulated*`) take the FUSED path (laminr_b200/fused.py): a fixed sequence
+  * simulated populations (`neuron_models.simulated*`) and conv-core + Gaussian-readout encoders (`neuron_models.FiringRateEncoder`)
+    take the FUSED path (laminr_b200/fused.py): a fixed sequence
     of C-ABI launches on static buffers, CUDA-graph replayed, no autograd, no per-step host sync;
   * any other `nn.Module` response model takes the GENERIC path: the same fused INR / constraint / contrastive
     operators, composed by stock autograd around the user's model.
@@ -18,7 +19,7 @@ from torch import nn
 from tqdm import tqdm
 
 from .contrastive_loss import SimCLROnGrid
-from .fused import LearnStepper, MatchStepper
+from .fused import LearnStepper, MatchStepper, fused_response_supported
 from .inr import INRTemplates
 from .neuron_models.utils.simulated_model import ArbitraryMultiNeuronModel
 from .utils.general import SingleNeuronModel, infer_device
@@ -65,7 +66,7 @@ class InvarianceManifold:
 
     # ------------------------------------------------------------------------------------------------------------------
     def _fused_ok(self, gaussian_blur=None):
-        return isinstance(self.response_predicting_model, ArbitraryMultiNeuronModel) and gaussian_blur is None
+        return fused_response_supported(self.response_predicting_model) and gaussian_blur is None
 
     @staticmethod
     def _blur(sigma):

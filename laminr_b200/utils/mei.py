@@ -56,6 +56,29 @@ def batched_simulated_meis(model, neuron_idxs, initial_images, pixel_min, pixel_
     return x, fevals
 
 
+def batched_conv_meis(model, neuron_idxs, initial_images, pixel_min, pixel_max, std=None, norm=None, step_size=10, num_iterations=1000):
+    """Gradient ascent for all listed neurons of a conv-core + Gaussian-readout encoder at once: per iteration ONE launch of
+    lmr_convcore_response (response and image gradient of every neuron's receptive-field cone) and ONE lmr_ascent_update
+    (x <- clip(renorm(x + step*g))), no host sync (featurevis/core.py:54-136 driven as in laminr/utils/mei.py:33-59).
+    initial_images: [G,C,H,W] BEFORE the first post-update.  Returns (meis [G,C,H,W], fevals [G, iters+1]) as device tensors."""
+    _check(std, norm)
+    mean = (pixel_min + pixel_max) / 2
+    cone = model.cone()
+    x = initial_images.to(torch.float32).contiguous().clone()
+    G, per_img = x.shape[0], x[0].numel()
+    nog = torch.as_tensor(list(neuron_idxs), dtype=torch.int32, device=x.device)
+    mode, target = (_lib.MODE_STD, std) if std is not None else (_lib.MODE_NORM, norm)
+    ws = torch.empty(max(int(_lib.load().lmr_constrain_workspace_bytes(G, per_img)), 16), dtype=torch.uint8, device=x.device)
+    _ops.raw_constrain_fwd(mode, x, target, mean, pixel_min, pixel_max, 1e-9, out=x, workspace=ws)  # post_update(initial_image), mei.py:42
+    fev = torch.empty((num_iterations + 1, G), dtype=torch.float32, device=x.device)
+    g = torch.empty_like(x)
+    for it in range(num_iterations):
+        _ops.raw_convcore_response(cone, x, per_img, 1, G, nog, act=fev[it], g_img=g, accumulate=False)
+        _ops.raw_ascent_update(mode, x, g, step_size, target, mean, pixel_min, pixel_max, eps=1e-9, workspace=ws)
+    _ops.raw_convcore_response(cone, x, per_img, 1, G, nog, act=fev[num_iterations])
+    return x, fev.t().contiguous()
+
+
 def get_mei_dict(response_predicting_model, input_shape, pixel_value_lower_bound, pixel_value_upper_bound, neuron_idxs=None, required_img_std=None,
                  required_img_norm=None, gb=None, zscore=0.3, step_size=10, num_iterations=1000, print_iters=1001, device=None):
     if device is None:
@@ -65,12 +88,14 @@ def get_mei_dict(response_predicting_model, input_shape, pixel_value_lower_bound
         neuron_idxs = list(range(response_predicting_model(initial_image).shape[1]))
 
     meis_dict = {}
-    if isinstance(response_predicting_model, ArbitraryMultiNeuronModel) and gb is None:
+    batched = (batched_simulated_meis if isinstance(response_predicting_model, ArbitraryMultiNeuronModel) else
+               batched_conv_meis if hasattr(response_predicting_model, "cone") else None)
+    if batched is not None and gb is None:
         _check(required_img_std, required_img_norm)
         mean = (pixel_value_lower_bound + pixel_value_upper_bound) / 2
         # one CPU draw per neuron, in index order (mei.py:33 inside the loop of :98)
         x0 = torch.cat([torch.randn(1, *input_shape, dtype=torch.float32) for _ in neuron_idxs]).to(device) + mean
-        meis, fevals = batched_simulated_meis(response_predicting_model, neuron_idxs, x0, pixel_value_lower_bound, pixel_value_upper_bound,
+        meis, fevals = batched(response_predicting_model, neuron_idxs, x0, pixel_value_lower_bound, pixel_value_upper_bound,
                                               std=required_img_std, norm=required_img_norm, step_size=step_size, num_iterations=num_iterations)
         meis_host, acts_host = meis.cpu(), fevals[:, -1].cpu().tolist()
         for idx, neuron_idx in enumerate(neuron_idxs):

@@ -428,25 +428,30 @@ def simclr_reg_bwd(cache, pos, neg, T):
 # ----------------------------------------------------------------------------------------------------------------
 
 
-def learn_step(weights, biases, B, auxB, grid, coords, img_res, filters, rf_mask, mei_act, reg_scale, norm, pmin, pmax, pos, neg, T):
+def learn_step(weights, biases, B, auxB, grid, coords, img_res, filters, rf_mask, mei_act, reg_scale, norm, pmin, pmax, pos, neg, T, response=None):
     """One `learn` hot step up to (and excluding) the optimiser: inv_temp_learn_match.py:187-207.
 
-    Returns dict(loss, acts (normalised), sim, img_pre, img_post, dW, db).
+    `response(z, g_act) -> (act[N], g_z)` replaces the simulated filter bank when given (e.g. the conv-core oracle,
+    oracle/convcore_oracle.py:response_and_grad).  Returns dict(loss, acts (normalised), sim, img_pre, img_post, dW, db).
     """
     dt = weights[0].dtype
     mean = (pmin + pmax) / 2
     img_pre, cache = inr_forward(weights, biases, B, auxB, grid, coords[None], img_res, keep=True)
     x = img_pre[0]  # [N,C,H,W]
     z, ccache = constrain_norm_fwd(x, norm, mean, pmin, pmax)
-    act, rcache = simresp_fwd(z, filters)
+    N = len(x)
+    g_act = np.full(N, -1.0 / (N * mei_act), dt)
+    if response is not None:
+        act, g_z = response(z, g_act)
+        act, g_z = act.astype(dt), g_z.astype(dt)
+    else:
+        act, rcache = simresp_fwd(z, filters)
+        g_z = simresp_bwd(g_act, rcache, z.shape, filters)
     acts = act / dt.type(mei_act)
     xm = apply_mask(z, rf_mask, pmin, pmax)
     sim, scache = simclr_reg_fwd(xm, pos, neg, T)
     loss = -acts.mean() - dt.type(reg_scale) * sim
     # backward
-    N = len(x)
-    g_act = np.full(N, -1.0 / (N * mei_act), dt)
-    g_z = simresp_bwd(g_act, rcache, z.shape, filters)
     g_xm = simclr_reg_bwd(scache, pos, neg, T).reshape(z.shape) * dt.type(-reg_scale)
     g_z = g_z + g_xm * rf_mask.astype(dt)  # d apply_mask / dx = gain_in * mask * gain_out = mask
     g_x = constrain_norm_bwd(g_z, ccache, norm, pmin, pmax)
@@ -454,7 +459,7 @@ def learn_step(weights, biases, B, auxB, grid, coords, img_res, filters, rf_mask
     return dict(loss=loss, acts=acts, sim=sim, img_pre=x, img_post=z, dW=grads["dW"], db=grads["db"], g_img_pre=g_x)
 
 
-def match_step(weights, biases, B, auxB, grid, coords, img_res, banks, mei_acts, affine, shifts, norm, pmin, pmax, clamp=True):
+def match_step(weights, biases, B, auxB, grid, coords, img_res, banks, mei_acts, affine, shifts, norm, pmin, pmax, clamp=True, responses=None):
     """One `match` hot step: inv_temp_learn_match.py:352-365.  banks: list of [F,H,W] for the D targets.
 
     affine = dict(angles[D], scalings[D,2], shears[D,2], translation[D,2]); shifts = (shift_to, tc, shift_from).
@@ -473,9 +478,13 @@ def match_step(weights, biases, B, auxB, grid, coords, img_res, banks, mei_acts,
     acts_dn = np.zeros((D, N), dt)
     g_z = np.zeros_like(zs)
     for d in range(D):
+        g_act = np.full(N, -1.0 / (N * D * mei_acts[d]), dt)
+        if responses is not None:  # responses[d](z, g_act) -> (act[N], g_z): any other response model (conv-core oracle)
+            acts_dn[d], g_z[d] = responses[d](zs[d], g_act)
+            continue
         a, rc = simresp_fwd(zs[d], banks[d])
         acts_dn[d] = a
-        g_z[d] = simresp_bwd(np.full(N, -1.0 / (N * D * mei_acts[d]), dt), rc, zs[d].shape, banks[d])
+        g_z[d] = simresp_bwd(g_act, rc, zs[d].shape, banks[d])
     acts = acts_dn.mean(1) / mei_acts.astype(dt)
     loss = -acts.mean()
     g_x = constrain_norm_bwd(g_z.reshape(z.shape), ccache, norm, pmin, pmax).reshape(img_pre.shape)

@@ -442,6 +442,89 @@ def case_convcore(laminr):
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **d)
 
 
+def case_conv_learn_match(laminr):
+    """One learn hot step and one match hot step of the reference's InvarianceManifold with a conv-core + Gaussian-readout response model
+    (FiringRateEncoder(Stacked2dCore, FullGaussian2d).eval(), BASELINE config 4 at a small size)."""
+    import warnings
+
+    from laminr.contrastive_loss import SimCLROnGrid
+    from laminr.utils.general import SingleNeuronModel
+    from laminr.utils.mask import apply_mask
+    from neuralpredictors.layers.cores.conv2d import Stacked2dCore
+    from neuralpredictors.layers.encoders.firing_rate import FiringRateEncoder
+    from neuralpredictors.layers.readouts.gaussian import FullGaussian2d
+
+    res, hc, n = 24, 8, 3
+    torch.manual_seed(21)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        core = Stacked2dCore(input_channels=1, hidden_channels=hc, input_kern=5, hidden_kern=3, layers=3, stack=-1, pad_input=True)
+        ro = FullGaussian2d(in_shape=(hc, res, res), outdims=n, bias=True)
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        for feat in core.features:
+            feat.norm.running_mean.copy_(torch.randn(hc, generator=g) * 0.2)
+            feat.norm.running_var.copy_(torch.rand(hc, generator=g) + 0.5)
+            feat.norm.weight.copy_(torch.rand(hc, generator=g) + 0.5)
+            feat.norm.bias.copy_(torch.randn(hc, generator=g) * 0.2)
+            feat.conv.weight.mul_(3.0)
+        ro._features.copy_(torch.randn(ro._features.shape, generator=g))
+        ro._mu.copy_(torch.tensor([[0.2, 0.2], [-0.2, -0.2], [-0.2, 0.2]]).reshape(1, n, 1, 2))  # (x, y): the synthetic RF centres below
+    model = FiringRateEncoder(core, ro).eval()
+    meis = synthetic_meis(model, res, g)
+    for i in meis:
+        meis[i]["activation"] = 1.25 + 0.1 * i
+    torch.manual_seed(0)
+    im = laminr.InvarianceManifold(model, meis, required_img_norm=2.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+    with torch.no_grad():
+        for p in im.template.func.parameters():
+            p.add_(torch.randn(p.shape, generator=g) * 0.1)
+    N = 20
+    grid = (torch.linspace(0, 2 * np.pi, N + 1)[:-1] + np.pi / N + 0.0123).reshape(N, 1)
+    reg = SimCLROnGrid(1, N, 0.1, 0.3, True)
+    img_pre, img_post, _acts, _ = im.forward(grid, im.template, im.img_transforms, SingleNeuronModel(model, 0), return_template=True)
+    acts = _acts / meis[0]["activation"]
+    sim = reg.reg_term(apply_mask(img_post, torch.from_numpy(meis[0]["mask"]), -1.0, 1.0))
+    loss = -acts.mean() - 2 * sim
+    loss.backward()
+    d = template_arrays(im.template)
+    d.update({"m_" + k: v for k, v in export_convcore_arrays(model).items()})
+    d.update(grid=npy(grid)[:, 0], mask=meis[0]["mask"], loss=npy(loss), sim=npy(sim), acts=npy(acts).reshape(-1), img_pre=npy(img_pre).reshape(N, -1),
+             img_post=npy(img_post).reshape(N, -1), reg_scale=np.float32(2.0), mei_act=np.float64(meis[0]["activation"]), norm=np.float64(2.0))
+    for l in range(5):
+        d[f"dW{l}"] = npy(getattr(im.template.func, f"layer{l}").weight.grad)
+        d[f"db{l}"] = npy(getattr(im.template.func, f"layer{l}").bias.grad)
+    # ---- match step on targets [1, 2]
+    targets = [1, 2]
+    im.template_neuron_idx, im.target_neuron_idxs = 0, targets
+    t = im.template
+    for p in t.func.parameters():
+        p.grad = None
+    t.initialize_coordinate_transform(2, True, False, 0.1, True, True, False, True)
+    rf = {k: np.array([v["center_pos"]["x"], v["center_pos"]["y"]], np.float32) for k, v in meis.items()}
+    t.register_coords_shifts(torch.from_numpy(rf[0]), torch.from_numpy(np.array([rf[k] for k in targets])))
+    aff = t.coordinate_transform.transforms.Affine
+    with torch.no_grad():
+        aff.angles.copy_(torch.tensor([0.7, 4.1]))
+        aff.scalings.copy_(torch.tensor([[1.1, 0.9], [0.8, 1.2]]))
+        aff.shears.copy_(torch.tensor([[0.05, -0.02], [-0.1, 0.08]]))
+        aff.translation.copy_(torch.tensor([[[0.03, -0.04]], [[-0.05, 0.02]]]))
+    t.train()
+    loc = np.arange(2)
+    img_pre, img_post, _acts, _ = im.forward(grid, t, im.img_transforms, model, return_template=False, other_neurons_loc_in_list=loc,
+                                             other_neurons_loc_in_model=targets)
+    rel = _acts[range(2), :, range(2)]
+    mei_acts = torch.tensor([meis[k]["activation"] for k in targets])
+    acts = rel.mean(dim=1) / mei_acts
+    loss = -acts.mean()
+    loss.backward()
+    d.update(match_loss=npy(loss), match_acts=npy(acts), match_acts_dn=npy(rel), match_img_post=npy(img_post), angles=npy(aff.angles),
+             scalings=npy(aff.scalings), shears=npy(aff.shears), translation=npy(aff.translation)[:, 0], d_angles=npy(aff.angles.grad),
+             d_scalings=npy(aff.scalings.grad), d_shears=npy(aff.shears.grad), d_translation=npy(aff.translation.grad)[:, 0], template_xy=rf[0],
+             target_xy=np.array([rf[k] for k in targets]), mei_acts=npy(mei_acts), targets=np.array(targets))
+    np.savez_compressed(os.path.join(OUT, "conv_learn_match_24.npz"), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     laminr = import_reference()
@@ -449,7 +532,7 @@ def main():
     import sys
     only = set(sys.argv[1:])
     for fn in (case_inr, case_match_inr, case_constrain, case_simresp, case_banks_100, case_simclr, case_training_utils,
-               case_adam, case_mei, case_learn_match_steps, case_trajectory, case_convcore):
+               case_adam, case_mei, case_learn_match_steps, case_trajectory, case_convcore, case_conv_learn_match):
         if only and fn.__name__ not in only:
             continue
         fn(laminr)

@@ -148,3 +148,120 @@ def test_config4_full_size_against_oracle():
     assert relerr(g_img.cpu().numpy(), want_g) < TOL_GRAD
     nz = (g_img != 0).sum(dim=(1, 2, 3)).cpu().numpy()
     assert (nz <= 22 * 22).all() and (nz > 0).all()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# the learn / match hot steps and the MEI ascent driven by the conv-core encoder
+# ----------------------------------------------------------------------------------------------------------------------
+def _mirror_from_prefixed(d, prefix="m_"):
+    sub = {k[len(prefix):]: v for k, v in d.items() if k.startswith(prefix)}
+    sub["x"] = np.zeros((1, sub["w0"].shape[1], 24, 24), np.float32)  # only the frame size is read from it
+    return _load_mirror(sub)
+
+
+def _conv_manifold(d, precision):
+    import laminr_b200 as L
+    model = _mirror_from_prefixed(d)
+    res = 24
+    yy, xx = np.meshgrid(np.arange(res) + 0.5, np.arange(res) + 0.5, indexing="ij")
+    meis = {}
+    for i, (cx, cy) in enumerate([(0.6 * res, 0.6 * res), (0.4 * res, 0.4 * res), (0.4 * res, 0.6 * res)]):
+        mask = np.exp(-0.5 * (((xx - cx) / (0.16 * res)) ** 2 + ((yy - cy) / (0.16 * res)) ** 2)).astype(np.float32)
+        meis[i] = dict(mei=np.zeros((1, res, res), np.float32), activation=1.25 + 0.1 * i, mask=mask, center_pos=dict(x=cx, y=cy))
+    np.testing.assert_allclose(meis[0]["mask"], d["mask"], atol=1e-7)
+    torch.manual_seed(0)
+    im = L.InvarianceManifold(model, meis, required_img_norm=float(d["norm"]), pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0, precision=precision)
+    sd = {f"func.layer{l}.weight": torch.from_numpy(d[f"W{l}"]) for l in range(5)}
+    sd.update({f"func.layer{l}.bias": torch.from_numpy(d[f"b{l}"]) for l in range(5)})
+    sd.update(B=torch.from_numpy(d["B"]), auxB=torch.from_numpy(d["auxB"]))
+    im.template.load_state_dict(sd, strict=False)
+    return model, meis, im
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_conv_fused_learn_and_match_step_vs_reference(precision, use_graph):
+    from laminr_b200.contrastive_loss import SimCLROnGrid
+    from laminr_b200.fused import LearnStepper, MatchStepper
+    d = golden("conv_learn_match_24")
+    model, meis, im = _conv_manifold(d, precision)
+    assert im._fused_ok()
+    reg = SimCLROnGrid(1, 20, 0.1, 0.3, True).cuda()
+    st = LearnStepper(im.template, im.img_transforms, model, 0, d["mask"], float(d["mei_act"]), reg, -1.0, 1.0, 20, lr=1e-3, reg_scale=2.0,
+                      precision=precision, use_graph=use_graph)
+    flat0 = st.flat.clone()
+    grid = torch.from_numpy(d["grid"]).cuda()
+    for rep in range(3 if use_graph else 1):  # eager step, capture, replay: restore the parameters in between so that every step is the same step
+        st.flat.copy_(flat0)
+        st.m.zero_(), st.v.zero_(), st.step_count.zero_()
+        st.step(grid)
+    torch.cuda.synchronize()
+    assert abs(st.loss().item() - d["loss"]) < 1e-4 * abs(d["loss"])
+    assert relerr(st.last_acts().cpu().numpy(), d["acts"]) < 5e-5
+    assert relerr(st.z.cpu().numpy().reshape(20, -1), d["img_post"]) < 1e-4
+    from tests._util import split_flat
+    dW, db = split_flat(st.g_flat.cpu().numpy(), d)
+    for l in range(5):
+        assert relerr(dW[l], d[f"dW{l}"]) < 5e-3, l
+        assert relerr(db[l], d[f"db{l}"]) < 5e-3, l
+    # ---- match step on targets [1, 2]
+    st.flat.copy_(flat0)
+    targets = [int(k) for k in d["targets"]]
+    t = im.template
+    t.initialize_coordinate_transform(2, True, False, 0.1, True, True, False, True)
+    rf = {k: np.array([v["center_pos"]["x"], v["center_pos"]["y"]], np.float32) for k, v in meis.items()}
+    t.register_coords_shifts(torch.from_numpy(rf[0]).cuda(), torch.from_numpy(np.array([rf[k] for k in targets])).cuda())
+    aff = t.coordinate_transform.transforms.Affine
+    with torch.no_grad():
+        aff.angles.copy_(torch.from_numpy(d["angles"])), aff.scalings.copy_(torch.from_numpy(d["scalings"]))
+        aff.shears.copy_(torch.from_numpy(d["shears"])), aff.translation.copy_(torch.from_numpy(d["translation"]).reshape(2, 1, 2))
+    ms = MatchStepper(t, im.img_transforms, model, targets, d["mei_acts"], 20, lr=1e-3, precision=precision, use_graph=False)
+    ms.step(grid)
+    torch.cuda.synchronize()
+    assert relerr(ms.act.cpu().numpy(), d["match_acts_dn"]) < 5e-5
+    assert relerr(ms.z.cpu().numpy(), d["match_img_post"]) < 1e-4
+    for got, key in zip(ms.grads, ("d_angles", "d_scalings", "d_shears", "d_translation")):
+        assert relerr(got.cpu().numpy().reshape(d[key].shape), d[key]) < 5e-3, key
+
+
+def test_conv_generic_autograd_path_vs_reference():
+    """The drop-in modules composed by stock autograd (what a user-written loop would do) reproduce the reference's learn-step gradients."""
+    from laminr_b200.contrastive_loss import SimCLROnGrid
+    from laminr_b200.utils.general import SingleNeuronModel
+    d = golden("conv_learn_match_24")
+    model, meis, im = _conv_manifold(d, "fp32")
+    grid = torch.from_numpy(d["grid"]).reshape(-1, 1).cuda()
+    reg = SimCLROnGrid(1, 20, 0.1, 0.3, True).cuda()
+    _, img_post, _acts, _ = im.forward(grid, im.template, im.img_transforms, SingleNeuronModel(model, 0), return_template=True)
+    acts = _acts / float(d["mei_act"])
+    loss = -acts.mean() - 2 * reg.masked_reg_term(img_post, torch.from_numpy(d["mask"]).cuda(), -1.0, 1.0)
+    loss.backward()
+    assert abs(loss.item() - d["loss"]) < 5e-5 * abs(d["loss"])
+    for l in range(5):
+        assert relerr(getattr(im.template.func, f"layer{l}").weight.grad.cpu().numpy(), d[f"dW{l}"]) < 3e-3, l
+
+
+def test_conv_batched_mei_ascent_vs_oracle():
+    """get_mei_dict's batched ascent for the conv encoder == the oracle's per-neuron loop (x <- clip(renorm(x + lr*g)))."""
+    from laminr_b200.utils.mei import batched_conv_meis
+    from oracle import convcore_oracle as CO
+    from oracle import laminr_oracle as O
+    d = golden("convcore_a")
+    model = _load_mirror(d)
+    om = CO.model_from_arrays(d)
+    n, iters = d["mu"].shape[0], 12
+    rng = np.random.RandomState(4)
+    x0 = rng.randn(n, 1, 40, 40).astype(np.float32)
+    for kw in (dict(norm=6.0), dict(std=0.2)):
+        meis, fev = batched_conv_meis(model, list(range(n)), torch.from_numpy(x0).cuda(), -1.0, 1.0, step_size=10, num_iterations=iters, **kw)
+        post = (lambda x: np.clip(O.change_norm(x, kw["norm"], 0.0), -1, 1)) if "norm" in kw else (lambda x: np.clip(O.change_stats(x, kw["std"], 0.0), -1, 1))
+        x = post(x0.copy())
+        want_f = []
+        for _ in range(iters):
+            act, g, _ = CO.response_and_grad(x, om, list(range(n)))
+            want_f.append(act)
+            x = post((x + np.float32(10) * g.astype(np.float32)).astype(np.float32)).astype(np.float32)
+        want_f.append(CO.response_and_grad(x, om, list(range(n)))[0])
+        assert fev.shape == (n, iters + 1)
+        assert relerr(fev.cpu().numpy(), np.stack(want_f, 1)) < 1e-4
+        assert relerr(meis.cpu().numpy(), x) < 1e-4

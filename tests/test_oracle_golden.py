@@ -237,3 +237,40 @@ def test_convcore_oracle_against_reference(name):
     for b in range(B):
         nz = np.argwhere(np.abs(d["g_x"][b]).sum(0) > 0)
         assert nz[:, 0].max() - nz[:, 0].min() + 1 <= k_total and nz[:, 1].max() - nz[:, 1].min() + 1 <= k_total
+
+
+def _conv_response(model, neuron):
+    from oracle import convcore_oracle as CO
+
+    def response(z, g_act):
+        act, g_z, _ = CO.response_and_grad(z, model, [neuron] * len(z), g_act)
+        return act, g_z
+    return response
+
+
+def test_conv_learn_and_match_step():
+    """Learn / match hot steps of the reference's InvarianceManifold driven by a conv-core + Gaussian-readout encoder (config 4, small)."""
+    from oracle import convcore_oracle as CO
+
+    d = golden("conv_learn_match_24")
+    W, b = net_params(d)
+    res = (24, 24)
+    model = CO.model_from_arrays(d, prefix="m_")
+    pos, neg = O.pos_neg_masks(20, 0.1, True)
+    out = O.learn_step(W, b, d["B"], d["auxB"], d["grid"], d["coords"], res, None, d["mask"], float(d["mei_act"]), 2.0, float(d["norm"]), -1.0, 1.0,
+                       pos, neg, 0.3, response=_conv_response(model, 0))
+    assert abs(out["loss"] - d["loss"]) < 2e-5 * abs(d["loss"])
+    assert relerr(out["acts"], d["acts"]) < 1e-5
+    assert relerr(out["img_post"].reshape(20, -1), d["img_post"]) < TOL
+    for l in range(5):
+        assert relerr(out["dW"][l], d[f"dW{l}"]) < 2e-3, l
+        assert relerr(out["db"][l], d[f"db{l}"]) < 2e-3, l
+    shifts = O.coords_shifts(d["template_xy"], d["target_xy"], res)
+    aff = dict(angles=d["angles"], scalings=d["scalings"], shears=d["shears"], translation=d["translation"])
+    out = O.match_step(W, b, d["B"], d["auxB"], d["grid"], d["coords"], res, None, d["mei_acts"].astype(np.float32), aff, shifts, float(d["norm"]), -1.0, 1.0,
+                       responses=[_conv_response(model, int(k)) for k in d["targets"]])
+    assert abs(out["loss"] - d["match_loss"]) < 2e-5 * abs(d["match_loss"])
+    assert relerr(out["acts_dn"], d["match_acts_dn"]) < 1e-5
+    assert relerr(out["img_post"], d["match_img_post"]) < TOL
+    for k in ("d_angles", "d_scalings", "d_shears", "d_translation"):
+        assert relerr(out[k], d[k]) < 1e-3, k
