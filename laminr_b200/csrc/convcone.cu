@@ -9,26 +9,32 @@
 // positions (zero padding honoured by forcing every position outside the frame to 0), ~1000x fewer FLOPs at 200x200.
 // fp32 CUDA-core FMAs (the cone is ~10 MFMA per image: far below the INR generator's cost, and exact fp32 keeps parity tight).
 //
-// Convolutions run as register-blocked items (CB output channels x XB adjacent pixels per thread, sliding input window in registers,
-// weights as warp-uniform 128-bit loads that stay in L1), split over input-channel ranges when a layer has few pixels; the partial sums are
-// combined in a fixed order (deterministic).  The data-gradient convolutions reuse the same routine on flipped, transposed weights with a
-// virtual zero border.
+// Convolutions run as register-blocked items (CB output channels x XB adjacent pixels per thread; the K weight vectors and the XB+K-1 input
+// values of a kernel row are loaded up front and the K*CB*XB FMAs run from registers), split over input-channel ranges when a layer has few
+// pixels; the partial sums are combined in a fixed order (deterministic).  The data-gradient convolutions reuse the same routine on flipped,
+// transposed weights with a virtual zero border.
+//
+// When there are fewer (image, neuron) pairs than SMs (the learn stage: 20 images) each pair is spread over a thread-block CLUSTER: every CTA
+// of the cluster computes a contiguous slice of each layer's (pixel block, channel block) items and writes its finished activations /
+// gradients into the shared memory of ALL CTAs of the cluster (distributed shared memory), with one cluster barrier per layer.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace lmr {
 namespace cone {
 
 constexpr int NT = 512;
 constexpr int MAXL = LMR_CONV_MAX_LAYERS;
+constexpr int TILE = 16;  // outputs per item: CB channels x XB pixels
 
 __host__ __device__ inline int pick_cb(int co) { return (co % 4 == 0) ? 4 : (co % 2 == 0) ? 2 : 1; }
-__host__ __device__ inline int ksplit_for(int So, int Co, int Cin) {
-    const int cb = pick_cb(Co), xb = 16 / cb;
-    const int items = So * ((So + xb - 1) / xb) * (Co / cb);
-    int ks = NT / items;
-    if (ks < 1) ks = 1;
-    if (ks > Cin) ks = Cin;
-    return ks;
+// number of (pixel block, channel block) items of a convolution with So x So outputs and Co channels
+__host__ __device__ inline int flat_items(int So, int Co) {
+    const int cb = pick_cb(Co), xb = TILE / cb;
+    return So * ((So + xb - 1) / xb) * (Co / cb);
 }
 
 struct Plan {
@@ -46,26 +52,24 @@ __host__ __device__ inline void make_plan(const lmr_convcore_desc& d, bool with_
     auto take = [&](int n) { int o = off; off += (n + 3) & ~3; return o; };
     p.off_in = take(d.c_in * p.Sin * p.Sin);
     for (int l = 0; l < L; ++l) p.off_a[l] = take(d.hidden * p.S[l] * p.S[l]);
-    int scratch = 0;
-    for (int l = 0; l < L; ++l) {  // forward convolutions
-        const int cin = l == 0 ? d.c_in : d.hidden;
-        const int n = ksplit_for(p.S[l], d.hidden, cin) * d.hidden * p.S[l] * p.S[l];
-        scratch = n > scratch ? n : scratch;
+    int items = NT;  // partial-sum scratch: TILE floats per (item, channel split); splits never push the count beyond max(NT, items)
+    for (int l = 0; l < L; ++l) {
+        const int n = flat_items(p.S[l], d.hidden);
+        items = n > items ? n : items;
     }
     if (with_grad) {
         for (int l = 0; l < L; ++l) p.off_g[l] = take(d.hidden * p.S[l] * p.S[l]);
         p.off_gin = take(d.c_in * p.Sin * p.Sin);
-        for (int l = 0; l < L; ++l) {  // data-gradient convolutions: out = input window of layer l
-            const int cout = l == 0 ? d.c_in : d.hidden, So = l == 0 ? p.Sin : p.S[l - 1];
-            const int n = ksplit_for(So, cout, d.hidden) * cout * So * So;
-            scratch = n > scratch ? n : scratch;
+        for (int l = 0; l < L; ++l) {
+            const int n = flat_items(l == 0 ? p.Sin : p.S[l - 1], l == 0 ? d.c_in : d.hidden);
+            items = n > items ? n : items;
         }
     } else {
         for (int l = 0; l < L; ++l) p.off_g[l] = 0;
         p.off_gin = 0;
     }
-    p.off_scratch = take(scratch);
-    p.total = off;
+    p.off_scratch = take(items * TILE);
+    p.total = off + 64;  // slack: unchecked forward reads of ragged pixel blocks may run a few floats past the last buffer
 }
 
 struct Args {
@@ -83,15 +87,19 @@ struct Args {
 
 // Partial sums of a stride-1 correlation: out[co, y, x] = sum_{ci in split, ky, kx} in[ci, y + ky - vp, x + kx - vp] * Wt[ci, ky, kx, co], input taken
 // as 0 outside [0,Sin)^2 (vp = 0: "valid" forward convolution of the window; vp = k-1: "full" data-gradient convolution).
-// scratch[ks][co][y*So + x] receives the partial sum of input-channel range ks.
-template <int CB>
-__device__ __forceinline__ void conv_items(const float* __restrict__ in, int Cin, int Sin, int vp, int So, int Co, int k,
-                                           const float* __restrict__ Wt, float* __restrict__ scratch, int ksplit) {
-    constexpr int XB = 16 / CB;
-    const int nseg = (So + XB - 1) / XB, nsp = So * nseg, ncb = Co / CB;
-    const int nitems = nsp * ncb * ksplit;
+// This CTA computes the items [lo, hi) of the flat (pixel block, channel block) space (channel block fastest), each split over `ksplit`
+// input-channel ranges; scratch[(ks*(hi-lo) + item-lo)*TILE + c*XB + j] receives the partial sums.
+// K > 0: kernel size known at compile time (rows preloaded into registers); K == 0: any size (sliding window).
+template <int CB, int K>
+__device__ __forceinline__ void conv_items(const float* __restrict__ in, int Cin, int Sin, int vp, int So, int Co, int kdyn, const float* __restrict__ Wt,
+                                           float* __restrict__ scratch, int lo, int hi, int ksplit) {
+    constexpr int XB = TILE / CB;
+    const int k = K > 0 ? K : kdyn;
+    const int nseg = (So + XB - 1) / XB, ncb = Co / CB;
+    const int nloc = hi - lo, nitems = nloc * ksplit;
     for (int item = threadIdx.x; item < nitems; item += NT) {
-        const int sp = item % nsp, t = item / nsp, cb = t % ncb, ks = t / ncb;
+        const int ks = item / nloc, fl = lo + item - ks * nloc;
+        const int sp = fl / ncb, cb = fl - sp * ncb;
         const int y = sp / nseg, x0 = (sp - y * nseg) * XB;
         const int c_lo = ks * Cin / ksplit, c_hi = (ks + 1) * Cin / ksplit;
         float acc[CB][XB];
@@ -101,56 +109,103 @@ __device__ __forceinline__ void conv_items(const float* __restrict__ in, int Cin
             for (int j = 0; j < XB; ++j) acc[c][j] = 0.f;
         const int kx_lo = max(0, vp - x0 - (XB - 1)), kx_hi = min(k, vp - x0 + Sin);
         const int ky_lo = max(0, vp - y), ky_hi = min(k, vp - y + Sin);
+        const int xb = x0 - vp;
         for (int ci = c_lo; ci < c_hi; ++ci) {
             const float* plane = in + ci * Sin * Sin;
             for (int ky = ky_lo; ky < ky_hi; ++ky) {
                 const float* row = plane + (y + ky - vp) * Sin;
                 const float* wrow = Wt + ((size_t)(ci * k + ky) * k) * Co + cb * CB;
-                float r[XB];
-                const int base = x0 + kx_lo - vp;
+                if constexpr (K > 0) {
+                    constexpr int RW = XB + K - 1;
+                    float wv[K][CB];
 #pragma unroll
-                for (int j = 0; j < XB - 1; ++j) {
-                    const int ix = base + j;
-                    r[j + 1] = (ix >= 0 && ix < Sin) ? row[ix] : 0.f;
-                }
-#pragma unroll 4
-                for (int kx = kx_lo; kx < kx_hi; ++kx) {
-#pragma unroll
-                    for (int j = 0; j < XB - 1; ++j) r[j] = r[j + 1];
-                    const int ix = x0 + kx - vp + XB - 1;
-                    r[XB - 1] = (ix >= 0 && ix < Sin) ? row[ix] : 0.f;
-                    float wv[CB];
-                    if (CB == 4) {
-                        const float4 q = __ldg(reinterpret_cast<const float4*>(wrow + kx * Co));
-                        wv[0] = q.x, wv[1 % CB] = q.y, wv[2 % CB] = q.z, wv[3 % CB] = q.w;
-                    } else if (CB == 2) {
-                        const float2 q = __ldg(reinterpret_cast<const float2*>(wrow + kx * Co));
-                        wv[0] = q.x, wv[1 % CB] = q.y;
-                    } else {
-                        wv[0] = __ldg(wrow + kx * Co);
+                    for (int kx = 0; kx < K; ++kx) {
+                        if constexpr (CB == 4) {
+                            const float4 q = __ldg(reinterpret_cast<const float4*>(wrow + kx * Co));
+                            wv[kx][0] = q.x, wv[kx][1] = q.y, wv[kx][2] = q.z, wv[kx][3] = q.w;
+                        } else if constexpr (CB == 2) {
+                            const float2 q = __ldg(reinterpret_cast<const float2*>(wrow + kx * Co));
+                            wv[kx][0] = q.x, wv[kx][1] = q.y;
+                        } else {
+                            wv[kx][0] = __ldg(wrow + kx * Co);
+                        }
                     }
+                    float r[RW];
+                    if (vp == 0) {  // forward: every read of a valid output pixel is inside the window; ragged blocks read (finite or not) junk
+#pragma unroll                      // that only reaches accumulators which are never stored
+                        for (int j = 0; j < RW; ++j) r[j] = row[xb + j];
 #pragma unroll
-                    for (int c = 0; c < CB; ++c)
+                        for (int kx = 0; kx < K; ++kx)
 #pragma unroll
-                        for (int j = 0; j < XB; ++j) acc[c][j] = fmaf(wv[c], r[j], acc[c][j]);
+                            for (int c = 0; c < CB; ++c)
+#pragma unroll
+                                for (int j = 0; j < XB; ++j) acc[c][j] = fmaf(wv[kx][c], r[j + kx], acc[c][j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < RW; ++j) {
+                            const int ix = xb + j;
+                            r[j] = (ix >= 0 && ix < Sin) ? row[ix] : 0.f;
+                        }
+#pragma unroll
+                        for (int kx = 0; kx < K; ++kx) {
+                            if (kx < kx_lo || kx >= kx_hi) continue;  // taps that only see the virtual zero border
+#pragma unroll
+                            for (int c = 0; c < CB; ++c)
+#pragma unroll
+                                for (int j = 0; j < XB; ++j) acc[c][j] = fmaf(wv[kx][c], r[j + kx], acc[c][j]);
+                        }
+                    }
+                } else {
+                    float r[XB];
+                    const int base = x0 + kx_lo - vp;
+#pragma unroll
+                    for (int j = 0; j < XB - 1; ++j) {
+                        const int ix = base + j;
+                        r[j + 1] = (ix >= 0 && ix < Sin) ? row[ix] : 0.f;
+                    }
+#pragma unroll 4
+                    for (int kx = kx_lo; kx < kx_hi; ++kx) {
+#pragma unroll
+                        for (int j = 0; j < XB - 1; ++j) r[j] = r[j + 1];
+                        const int ix = x0 + kx - vp + XB - 1;
+                        r[XB - 1] = (ix >= 0 && ix < Sin) ? row[ix] : 0.f;
+                        float wv[CB];
+#pragma unroll
+                        for (int c = 0; c < CB; ++c) wv[c] = __ldg(wrow + kx * Co + c);
+#pragma unroll
+                        for (int c = 0; c < CB; ++c)
+#pragma unroll
+                            for (int j = 0; j < XB; ++j) acc[c][j] = fmaf(wv[c], r[j], acc[c][j]);
+                    }
                 }
             }
         }
+        float* o = scratch + (size_t)item * TILE;
 #pragma unroll
-        for (int c = 0; c < CB; ++c) {
-            float* o = scratch + ((size_t)(ks * Co + cb * CB + c) * So + y) * So + x0;
+        for (int c = 0; c < CB; ++c)
 #pragma unroll
-            for (int j = 0; j < XB; ++j)
-                if (x0 + j < So) o[j] = acc[c][j];
-        }
+            for (int j = 0; j < XB; ++j) o[c * XB + j] = acc[c][j];
     }
 }
 
-__device__ __forceinline__ void conv_dispatch(const float* in, int Cin, int Sin, int vp, int So, int Co, int k, const float* Wt, float* scratch, int ksplit) {
+template <int CB>
+__device__ __forceinline__ void conv_by_k(const float* in, int Cin, int Sin, int vp, int So, int Co, int k, const float* Wt, float* scratch, int lo,
+                                          int hi, int ksplit) {
+    switch (k) {
+        case 3: conv_items<CB, 3>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit); break;
+        case 5: conv_items<CB, 5>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit); break;
+        case 7: conv_items<CB, 7>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit); break;
+        case 9: conv_items<CB, 9>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit); break;
+        default: conv_items<CB, 0>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit);
+    }
+}
+
+__device__ __forceinline__ void conv_dispatch(const float* in, int Cin, int Sin, int vp, int So, int Co, int k, const float* Wt, float* scratch, int lo,
+                                              int hi, int ksplit) {
     const int cb = pick_cb(Co);
-    if (cb == 4) conv_items<4>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, ksplit);
-    else if (cb == 2) conv_items<2>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, ksplit);
-    else conv_items<1>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, ksplit);
+    if (cb == 4) conv_by_k<4>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit);
+    else if (cb == 2) conv_by_k<2>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit);
+    else conv_by_k<1>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit);
 }
 
 __device__ __forceinline__ float elu_shifted(float v, float xs, float ys) {
@@ -163,17 +218,63 @@ __device__ __forceinline__ float elu_grad_from_out(float out, float ys) {
     return t > 0.f ? 1.f : t + 1.f;
 }
 
+enum { EPI_FWD = 0, EPI_BWD = 1, EPI_PLAIN = 2 };
+
+// Combines the channel-split partial sums of this CTA's items in a fixed order, applies the layer epilogue and writes the results into `dst`
+// (layout [Co][So][So]) of EVERY CTA of the cluster.
+//   EPI_FWD:   v*scale[c] + shift[c], optional shifted ELU, 0 outside the frame (= the next layer's zero padding)
+//   EPI_BWD:   v * scale[c] * elu'(aout) , 0 outside the frame   (gradient wrt the pre-batch-norm output of the layer below)
+//   EPI_PLAIN: v
+__device__ __forceinline__ void reduce_store(cg::cluster_group& cl, int CS, const float* scratch, int lo, int hi, int ksplit, int So, int Co, float* dst, int mode,
+                                             const float* __restrict__ scale, const float* __restrict__ shift, int nonlin, float xs, float ys,
+                                             const float* aout, int oy, int ox, int H, int W) {
+    const int CB = pick_cb(Co), XB = TILE / CB;
+    const int nseg = (So + XB - 1) / XB, ncb = Co / CB, nloc = hi - lo;
+    for (int e = threadIdx.x; e < nloc * TILE; e += NT) {
+        const int li = e / TILE, q = e - li * TILE, cc = q / XB, j = q - cc * XB;
+        const int fl = lo + li, sp = fl / ncb, cb = fl - sp * ncb;
+        const int y = sp / nseg, x = (sp - y * nseg) * XB + j;
+        if (x >= So) continue;
+        const int c = cb * CB + cc;
+        float v = 0.f;
+        for (int s = 0; s < ksplit; ++s) v += scratch[(size_t)(s * nloc + li) * TILE + q];
+        const int idx = (c * So + y) * So + x;
+        if (mode != EPI_PLAIN) {
+            if (mode == EPI_FWD) {
+                v = fmaf(v, __ldg(scale + c), __ldg(shift + c));
+                if (nonlin) v = elu_shifted(v, xs, ys);
+            } else {
+                v *= __ldg(scale + c) * (nonlin ? elu_grad_from_out(aout[idx], ys) : 1.f);
+            }
+            const int gy = oy + y, gx = ox + x;
+            if (!(gy >= 0 && gy < H && gx >= 0 && gx < W)) v = 0.f;
+        }
+        if (CS == 1) dst[idx] = v;
+        else
+            for (int r = 0; r < CS; ++r) *cl.map_shared_rank(dst + idx, r) = v;
+    }
+}
+
+__device__ __forceinline__ int ksplit_for(int nloc, int Cin) {
+    int ks = nloc > 0 ? NT / nloc : 1;
+    if (ks < 1) ks = 1;
+    if (ks > Cin) ks = Cin;
+    return ks;
+}
+
 __global__ void __launch_bounds__(NT, 1) convcone_kernel(const Args a) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float s_tap[4];
     __shared__ float s_red[40];
-    __shared__ float s_gy;
+    cg::cluster_group cl = cg::this_cluster();
+    const int CS = (int)cl.num_blocks(), rank = (int)cl.block_rank();
     const lmr_convcore_desc& d = a.d;
     const int L = d.n_layers, H = d.height, W = d.width, P = H * W, Hc = d.hidden, Cin = d.c_in;
     const bool with_grad = a.g_img != nullptr;
     Plan pl;
     make_plan(d, with_grad, pl);
-    const int g = blockIdx.x / a.NB, b = blockIdx.x - g * a.NB;
+    const int pair = blockIdx.x / CS;  // (group, image) pair of this cluster
+    const int g = pair / a.NB, b = pair - g * a.NB;
     const int neuron = a.neuron_of_group[g];
     const size_t img_off = (size_t)g * (size_t)a.group_stride + (size_t)b * Cin * P;
     const float* img = a.img + img_off;
@@ -201,48 +302,41 @@ __global__ void __launch_bounds__(NT, 1) convcone_kernel(const Args a) {
     const int iy0 = oy[0] - d.kernel[0] / 2, ix0 = ox[0] - d.kernel[0] / 2;
     const int Sin = pl.Sin;
 
-    // ---- input window
+    // ---- input window (every CTA of the cluster keeps its own copy)
     float* win = sm + pl.off_in;
     for (int i = tid; i < Cin * Sin * Sin; i += NT) {
         const int c = i / (Sin * Sin), r = i - c * Sin * Sin, y = r / Sin, x = r - y * Sin;
         const int gy = iy0 + y, gx = ix0 + x;
         win[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(img + (size_t)c * P + gy * W + gx) : 0.f;
     }
-    __syncthreads();
+    for (int i = tid; i < 64; i += NT) sm[pl.total - 64 + i] = 0.f;
+    cl.sync();  // also: every CTA of the cluster is running before the first remote shared-memory write
 
     // ---- forward through the layers
     float* scratch = sm + pl.off_scratch;
     for (int l = 0; l < L; ++l) {
         const int cin = l == 0 ? Cin : Hc, So = pl.S[l], Si = l == 0 ? Sin : pl.S[l - 1], k = d.kernel[l];
         const float* in = l == 0 ? win : sm + pl.off_a[l - 1];
-        const int ks = ksplit_for(So, Hc, cin);
-        conv_dispatch(in, cin, Si, 0, So, Hc, k, a.w.w_fwd[l], scratch, ks);
+        const int nflat = flat_items(So, Hc), lo = rank * nflat / CS, hi = (rank + 1) * nflat / CS;
+        const int ks = ksplit_for(hi - lo, cin);
+        conv_dispatch(in, cin, Si, 0, So, Hc, k, a.w.w_fwd[l], scratch, lo, hi, ks);
         __syncthreads();
-        float* out = sm + pl.off_a[l];
-        const int n = Hc * So * So;
-        for (int i = tid; i < n; i += NT) {
-            const int c = i / (So * So), r = i - c * So * So, y = r / So, x = r - y * So;
-            float v = 0.f;
-            for (int s = 0; s < ks; ++s) v += scratch[s * n + i];
-            v = fmaf(v, __ldg(a.w.scale[l] + c), __ldg(a.w.shift[l] + c));
-            if (d.nonlin[l]) v = elu_shifted(v, d.elu_xshift, d.elu_yshift);
-            const int gy = oy[l] + y, gx = ox[l] + x;
-            out[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? v : 0.f;  // outside the frame = the next layer's zero padding
-        }
-        __syncthreads();
+        reduce_store(cl, CS, scratch, lo, hi, ks, So, Hc, sm + pl.off_a[l], EPI_FWD, a.w.scale[l], a.w.shift[l], d.nonlin[l], d.elu_xshift, d.elu_yshift, nullptr,
+                     oy[l], ox[l], H, W);
+        cl.sync();
     }
 
-    // ---- readout + encoder nonlinearity
+    // ---- readout + encoder nonlinearity (every CTA holds the full top window; rank 0 reports)
     const float* top = sm + pl.off_a[L - 1];  // [Hc][2][2]
     float part = 0.f;
     for (int i = tid; i < Hc * 4; i += NT) part += top[i] * s_tap[i & 3] * __ldg(a.w.features + (size_t)neuron * Hc + (i >> 2));
     const float ysum = block_sum(part, s_red) + (a.w.bias ? __ldg(a.w.bias + neuron) : 0.f);
     const float pre = ysum + d.elu_offset;
-    if (tid == 0) a.act[blockIdx.x] = (pre > 0.f ? pre : expm1f(pre)) + 1.f;
+    if (tid == 0 && rank == 0) a.act[pair] = (pre > 0.f ? pre : expm1f(pre)) + 1.f;
     if (!with_grad) return;
 
     // ---- backward: d(g_act * act) / d image
-    const float gy_ = (a.g_act ? a.g_act[blockIdx.x] : 1.f) * (pre > 0.f ? 1.f : expf(pre));
+    const float gy_ = (a.g_act ? a.g_act[pair] : 1.f) * (pre > 0.f ? 1.f : expf(pre));
     {
         float* gl = sm + pl.off_g[L - 1];
         for (int i = tid; i < Hc * 4; i += NT) {
@@ -257,42 +351,28 @@ __global__ void __launch_bounds__(NT, 1) convcone_kernel(const Args a) {
     for (int l = L - 1; l >= 0; --l) {
         // gradient wrt the input window of layer l = full correlation of g[l] (pre-batch-norm gradient) with the flipped kernel
         const int cout = l == 0 ? Cin : Hc, So = l == 0 ? Sin : pl.S[l - 1], Si = pl.S[l], k = d.kernel[l];
-        const int ks = ksplit_for(So, cout, Hc);
-        conv_dispatch(sm + pl.off_g[l], Hc, Si, k - 1, So, cout, k, a.w.w_bwd[l], scratch, ks);
+        const int nflat = flat_items(So, cout), lo = rank * nflat / CS, hi = (rank + 1) * nflat / CS;
+        const int ks = ksplit_for(hi - lo, Hc);
+        conv_dispatch(sm + pl.off_g[l], Hc, Si, k - 1, So, cout, k, a.w.w_bwd[l], scratch, lo, hi, ks);
         __syncthreads();
-        const int n = cout * So * So;
-        if (l > 0) {
-            float* gout = sm + pl.off_g[l - 1];
-            const float* aout = sm + pl.off_a[l - 1];
-            for (int i = tid; i < n; i += NT) {
-                const int c = i / (So * So), r = i - c * So * So, y = r / So, x = r - y * So;
-                float v = 0.f;
-                for (int s = 0; s < ks; ++s) v += scratch[s * n + i];
-                v *= __ldg(a.w.scale[l - 1] + c) * (d.nonlin[l - 1] ? elu_grad_from_out(aout[i], d.elu_yshift) : 1.f);
-                const int gyy = oy[l - 1] + y, gxx = ox[l - 1] + x;
-                gout[i] = (gyy >= 0 && gyy < H && gxx >= 0 && gxx < W) ? v : 0.f;
-            }
-        } else {
-            float* gin = sm + pl.off_gin;
-            for (int i = tid; i < n; i += NT) {
-                float v = 0.f;
-                for (int s = 0; s < ks; ++s) v += scratch[s * n + i];
-                gin[i] = v;
-            }
-        }
-        __syncthreads();
+        if (l > 0)
+            reduce_store(cl, CS, scratch, lo, hi, ks, So, cout, sm + pl.off_g[l - 1], EPI_BWD, a.w.scale[l - 1], nullptr, d.nonlin[l - 1], d.elu_xshift,
+                         d.elu_yshift, sm + pl.off_a[l - 1], oy[l - 1], ox[l - 1], H, W);
+        else
+            reduce_store(cl, CS, scratch, lo, hi, ks, So, cout, sm + pl.off_gin, EPI_PLAIN, nullptr, nullptr, 0, 0.f, 0.f, nullptr, 0, 0, H, W);
+        cl.sync();
     }
-    // ---- write the image gradient (this CTA owns the whole image: no atomics)
+    // ---- write the image gradient (this cluster owns the whole image: no atomics; the CTAs interleave)
     float* gimg = a.g_img + img_off;
     const float* gin = sm + pl.off_gin;
     if (a.accumulate) {
-        for (int i = tid; i < Cin * Sin * Sin; i += NT) {
+        for (int i = rank * NT + tid; i < Cin * Sin * Sin; i += NT * CS) {
             const int c = i / (Sin * Sin), r = i - c * Sin * Sin, y = r / Sin, x = r - y * Sin;
             const int gyy = iy0 + y, gxx = ix0 + x;
             if (gyy >= 0 && gyy < H && gxx >= 0 && gxx < W) gimg[(size_t)c * P + gyy * W + gxx] += gin[i];
         }
     } else {
-        for (int i = tid; i < Cin * P; i += NT) {
+        for (int i = rank * NT + tid; i < Cin * P; i += NT * CS) {
             const int c = i / P, r = i - c * P, gyy = r / W, gxx = r - gyy * W;
             const int y = gyy - iy0, x = gxx - ix0;
             gimg[i] = (y >= 0 && y < Sin && x >= 0 && x < Sin) ? gin[(c * Sin + y) * Sin + x] : 0.f;
@@ -325,10 +405,39 @@ extern "C" int lmr_convcore_response(const lmr_convcore_desc* desc, const lmr_co
     LMR_CHECK_ARG(smem <= 220 * 1024, "convcore_response: the receptive-field cone needs %zu bytes of shared memory (> 220 KB)", smem);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     LMR_CUDA_OK(cudaFuncSetAttribute(cone::convcone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // cluster size: spread each (image, neuron) pair over as many SMs as still leaves every pair resident at once (a cluster lives inside one
+    // GPC, so the driver is asked how many clusters of each size fit; cached per shared-memory size)
+    const int pairs = G * NB;
+    static int cached_smem = -1, max_active[9];
+    if (cached_smem != (int)smem) {
+        for (int c = 2; c <= 8; ++c) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3((unsigned)(c * 64)), q.blockDim = dim3(cone::NT), q.dynamicSmemBytes = smem;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = (unsigned)c, qa[0].val.clusterDim.y = 1, qa[0].val.clusterDim.z = 1;
+            q.attrs = qa, q.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, cone::convcone_kernel, &q) != cudaSuccess) n = 0, (void)cudaGetLastError();
+            max_active[c] = n;
+        }
+        cached_smem = (int)smem;
+    }
+    int cs = 1;
+    for (int c = 8; c >= 2; --c)
+        if (max_active[c] >= pairs) {
+            cs = c;
+            break;
+        }
     cone::Args a;
     a.d = d, a.w = *weights, a.img = img, a.group_stride = img_group_stride, a.NB = NB, a.G = G, a.neuron_of_group = neuron_of_group;
     a.g_act = g_act, a.act = act, a.g_img = g_img, a.accumulate = accumulate;
-    cone::convcone_kernel<<<G * NB, cone::NT, smem, st>>>(a);
-    LMR_LAUNCH_OK();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(pairs * cs)), cfg.blockDim = dim3(cone::NT), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    LMR_CUDA_OK(cudaLaunchKernelEx(&cfg, cone::convcone_kernel, a));
     return 0;
 }
