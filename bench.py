@@ -176,6 +176,129 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# BASELINE config 4 (extra): random-init stacked-conv core + Gaussian readout, 200x200, 128 neurons
+# ----------------------------------------------------------------------------------------------------------------------
+def conv_meis(model, res, n):
+    """Synthetic meis_dict for the conv encoder: Gaussian-bump RF masks at the readout positions."""
+    mu = model.readout._mu.detach().cpu().numpy().reshape(-1, 2).clip(-1, 1)
+    yy, xx = np.meshgrid(np.arange(res) + 0.5, np.arange(res) + 0.5, indexing="ij")
+    out = {}
+    for i in range(n):
+        cx, cy = (mu[i, 0] + 1) / 2 * (res - 1) + 0.5, (mu[i, 1] + 1) / 2 * (res - 1) + 0.5
+        mask = np.exp(-0.5 * (((xx - cx) / (0.08 * res)) ** 2 + ((yy - cy) / (0.08 * res)) ** 2)).astype(np.float32)
+        out[i] = dict(mei=np.zeros((1, res, res), np.float32), activation=1.0, mask=mask, center_pos=dict(x=float(cx), y=float(cy)))
+    return out
+
+
+def bench_conv(args, dev, world, rank, barrier, flush):
+    import contextlib
+    import io
+    import warnings
+
+    import torch
+    import torch.distributed as dist
+
+    import laminr_b200 as L
+    from laminr_b200.contrastive_loss import SimCLROnGrid
+    from laminr_b200.fused import LearnStepper, MatchStepper
+    from laminr_b200.utils.mei import batched_conv_meis
+    from laminr_b200.utils.training import JitteringGridDatamodule
+
+    res, n_neurons, K = args.conv_res, 128, max(3, min(args.steps, args.conv_steps))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = L.neuron_models.conv_core_gaussian_model((1, res, res), n_neurons=n_neurons, seed=0).to(dev).eval()
+    Dloc = args.conv_targets
+    meis = conv_meis(model, res, Dloc + 1)
+    norm = 0.05 * res
+    torch.manual_seed(0)
+    im = L.InvarianceManifold(model, meis, required_img_norm=norm, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0, precision=args.precision)
+    reg = SimCLROnGrid(1, N_LATENTS, 0.1, 0.3, True).to(dev)
+    st = LearnStepper(im.template, im.img_transforms, model, 0, meis[0]["mask"], 1.0, reg, -1.0, 1.0, N_LATENTS, lr=1e-3, reg_scale=2.0,
+                      precision=args.precision, use_graph=True)
+    grids = torch.stack(list(JitteringGridDatamodule(1, N_LATENTS, K + 3).train_dataloader())).reshape(K + 3, N_LATENTS).to(dev)
+    for i in range(3):
+        st.step(grids[i])
+    barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    for i in range(K):
+        flush.fill_(float(i))
+        starts[i].record()
+        st.step(grids[3 + i])
+        ends[i].record()
+    barrier()
+    t_learn = torch.tensor([sum(s.elapsed_time(e) for s, e in zip(starts, ends))], device=dev)
+    # ---- match hot step: targets 1..Dloc per GPU
+    targets = list(range(1, Dloc + 1))
+    t = im.template
+    t.initialize_coordinate_transform(Dloc, True, False, 0.1, True, True, False, True)
+    rfs = torch.tensor([[meis[i]["center_pos"]["x"], meis[i]["center_pos"]["y"]] for i in range(Dloc + 1)], dtype=torch.float32, device=dev)
+    t.register_coords_shifts(rfs[0], rfs[1:])
+    ms = MatchStepper(t, im.img_transforms, model, targets, np.ones(Dloc, np.float32), N_LATENTS, total_targets=Dloc * world, precision=args.precision,
+                      use_graph=True)
+    mk = max(3, min(K, args.match_steps))
+    for i in range(3):
+        ms.step(grids[i])
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(mk):
+        ms.step(grids[3 + (i % K)])
+    b.record()
+    barrier()
+    t_match = torch.tensor([a.elapsed_time(b)], device=dev)
+    # ---- MEI ascent for all 128 neurons of this rank's replica (1000 iterations, batched)
+    x0 = torch.randn(n_neurons, 1, res, res).to(dev)
+    batched_conv_meis(model, list(range(n_neurons)), x0, -1.0, 1.0, norm=norm, num_iterations=5)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    _, fev = batched_conv_meis(model, list(range(n_neurons)), x0, -1.0, 1.0, norm=norm, num_iterations=1000)
+    b.record()
+    barrier()
+    t_mei = torch.tensor([a.elapsed_time(b)], device=dev)
+    tt = torch.cat([t_learn, t_match, t_mei])
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_learn, t_match, t_mei = tt.tolist()
+    if rank != 0:
+        return None
+    fwd_f, bwd_f = algorithmic_flops(res)
+    out = {"workload": f"BASELINE configs[3]: random-init Stacked2dCore(1->32, kernels 9/7/7, 3 layers) + FullGaussian2d({n_neurons}) encoder, {res}x{res}",
+           "learn": {"metric": f"INR opt steps/sec (learn, {res}x{res}, conv-core response)", "value": world * K / (t_learn / 1e3), "unit": "steps/s", "steps": K,
+                     "ms_per_step": t_learn / K, "algorithmic_gflop_inr": (fwd_f + bwd_f) / 1e9, "gpu_launches_per_step": st.kernels_per_step},
+           "match": {"metric": "match target-steps/sec", "value": Dloc * world * mk / (t_match / 1e3), "unit": "target-steps/s", "targets_per_gpu": Dloc,
+                     "steps": mk, "ms_per_step": t_match / mk},
+           "mei": {"metric": "MEIs/sec (1000 ascent iterations each, batched)", "value": n_neurons * world / (t_mei / 1e3), "unit": "MEIs/s",
+                   "neurons_per_gpu": n_neurons, "ms": t_mei, "final_activation_mean": float(fev[:, -1].mean().item())},
+           "cpu_baseline": None}
+    if world == 1 and not args.no_cpu_baseline:
+        # the reference's op sequence on the host cores (full-frame convolutions, all neurons read out): torch-CPU port, 2 timed steps
+        from laminr_b200.neuron_models.conv_models import export_arrays
+        from oracle import laminr_oracle as O
+        from oracle.torch_port import ConvResponsePort, LearnPort
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        sd = {k: v.detach().cpu().numpy() for k, v in im.template.state_dict().items()}
+        W = [sd[f"func.layer{l}.weight"] for l in range(5)]
+        bb = [sd[f"func.layer{l}.bias"] for l in range(5)]
+        pos, neg = O.pos_neg_masks(N_LATENTS, 0.1, True)
+        port = LearnPort(W, bb, sd["B"], sd["auxB"], sd["coords"].reshape(-1, 2), None, meis[0]["mask"], 1.0, pos, neg, norm=norm, res=(res, res),
+                         anomaly_mode=True, response=ConvResponsePort(export_arrays(model), 0))
+        g = grids.cpu().numpy()
+        port.step(g[0])
+        t0 = time.perf_counter()
+        n_cpu = 2
+        for i in range(n_cpu):
+            port.step(g[1 + i])
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "steps/s", "cores": threads, "kind": "port",
+                               "sample": f"{n_cpu} learn steps at {res}x{res} with the conv encoder ({dt:.1f} s), torch-CPU port of the reference op sequence, anomaly mode on as shipped"}
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -354,6 +477,9 @@ def run_ours(args):
                         "neurons_per_gpu": nmei, "ms": mt3.item(), "final_activation_mean": float(fev[:, -1].mean().item()),
                         "algorithmic_GBps_per_gpu": mei_bytes / (mt3.item() / 1e3) / 1e9}
 
+    # ---- BASELINE config 4 (extra): conv-core encoder at 200x200
+    conv = bench_conv(args, dev, world, rank, barrier, flush) if args.conv_res > 0 else None
+
     # ---- reduce over ranks (max time), CPU baseline on rank 0 at N == 1
     tt = torch.tensor([step_ms, b2b_ms, e2e_s * 1e3], device=dev)
     if world > 1:
@@ -388,7 +514,7 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "lmr_inr_backward launch group (inr_bwd_tc_kernel dominant; + layer-0 weight gradient and partial reduction launches)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf, "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback",
                          "algorithmic_gflop": bwd_f / 1e9, "ms": bwd_ms, "forward": {"algorithmic_gflop": fwd_f / 1e9, "ms": fwd_ms, "achieved": fwd_f / (fwd_ms * 1e-3) / 1e12}},
-            "cpu_baseline": cpu, "clocks": clocks, "match": match,
+            "cpu_baseline": cpu, "clocks": clocks, "match": match, "conv": conv,
         }
         print(json.dumps(line))
     if world > 1:
@@ -408,6 +534,9 @@ def main():
     ap.add_argument("--match-steps", type=int, default=20)
     ap.add_argument("--match-epochs", type=int, default=30, help="epochs of the whole-match() measurement (fixed; the early stop is disabled)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv-res", type=int, default=200, help="resolution of the extra conv-core (BASELINE config 4) measurement (0 = skip)")
+    ap.add_argument("--conv-steps", type=int, default=100)
+    ap.add_argument("--conv-targets", type=int, default=8, help="match targets per GPU in the conv-core measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

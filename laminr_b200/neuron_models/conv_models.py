@@ -219,6 +219,26 @@ class FiringRateEncoder(nn.Module):
         return self.forward_neurons(inputs, range(self.readout.outdims))
 
 
+def export_arrays(model):
+    """Flat numpy export of a FiringRateEncoder(Stacked2dCore, FullGaussian2d) (the layout oracle.convcore_oracle.model_from_arrays and
+    oracle.torch_port.ConvResponsePort read; same keys as oracle/make_golden.py:export_convcore_arrays writes for the reference's modules)."""
+    core, ro = model.core, model.readout
+    npy = lambda t: t.detach().cpu().numpy().copy()
+    d = dict(n_layers=np.int64(len(core.features)), xs=np.float64(core.elu_xshift), ys=np.float64(core.elu_yshift), offset=np.float64(model.offset),
+             align_corners=np.bool_(ro.align_corners), mu=npy(ro._mu).reshape(-1, 2).clip(-1, 1), features=npy(ro._features).reshape(ro._features.shape[1], -1))
+    if ro.bias is not None:
+        d["bias"] = npy(ro.bias)
+    for l, feat in enumerate(core.features):
+        d[f"w{l}"] = npy(feat.conv.weight)
+        if feat.conv.bias is not None:
+            d[f"b{l}"] = npy(feat.conv.bias)
+        if hasattr(feat, "norm"):
+            d[f"bn{l}_mean"], d[f"bn{l}_var"] = npy(feat.norm.running_mean), npy(feat.norm.running_var)
+            d[f"bn{l}_gamma"], d[f"bn{l}_beta"], d[f"bn{l}_eps"] = npy(feat.norm.weight), npy(feat.norm.bias), np.float64(feat.norm.eps)
+        d[f"nonlin{l}"] = np.bool_(hasattr(feat, "nonlin"))
+    return d
+
+
 def conv_core_gaussian_model(input_shape=(1, 200, 200), n_neurons=128, hidden_channels=32, input_kern=9, hidden_kern=7, layers=3, seed=0):
     """BASELINE config 4: random-init stacked-conv core (1 -> 32 channels, kernels 9/7/7, last layer read out) + full-Gaussian
     readout with `n_neurons` outputs, as a firing-rate encoder in EVAL mode (batch-norm running statistics, readout at its mean positions)."""

@@ -274,3 +274,21 @@ def test_conv_learn_and_match_step():
     assert relerr(out["img_post"], d["match_img_post"]) < TOL
     for k in ("d_angles", "d_scalings", "d_shears", "d_translation"):
         assert relerr(out[k], d[k]) < 1e-3, k
+
+
+def test_torch_port_conv_response_matches_reference():
+    """The torch-CPU port used as bench.py's CPU baseline for config 4 (oracle/torch_port.py) reproduces the reference's learn step."""
+    import torch
+    from oracle.torch_port import ConvResponsePort, LearnPort
+
+    d = golden("conv_learn_match_24")
+    W, b = net_params(d)
+    pos, neg = O.pos_neg_masks(20, 0.1, True)
+    port = LearnPort(W, b, d["B"], d["auxB"], d["coords"], None, d["mask"], float(d["mei_act"]), pos, neg, norm=float(d["norm"]), res=(24, 24),
+                     response=ConvResponsePort(d, 0, prefix="m_"))
+    loss, acts, _ = port.loss(d["grid"])
+    assert abs(float(loss) - d["loss"]) < 2e-5 * abs(d["loss"])
+    assert relerr(acts.detach().numpy(), d["acts"]) < 1e-5
+    loss.backward()
+    for l in range(5):
+        assert relerr(port.W[l].grad.numpy(), d[f"dW{l}"]) < 1e-3, l
