@@ -475,33 +475,64 @@ __device__ inline void mei_post(float* xs, int n, int mode, float target, float 
     __syncthreads();
 }
 
-// r[f] = sum_p (sum_c x[c][p]) w_f[p]; returns via rs[] (smem), one warp per filter
-__device__ inline void mei_dots(const float* xs, int C, int HW, const float* __restrict__ bank, int F, float* rs) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const bool vec = (HW % 4) == 0;
-    for (int f = warp; f < F; f += nw) {
-        const float* w = bank + (size_t)f * HW;
-        float acc = 0.f;
-        if (vec) {
-            const float4* w4 = reinterpret_cast<const float4*>(w);
-            for (int q = lane; q < HW / 4; q += 32) {
-                const float4 ww = __ldg(w4 + q);
-                float4 xv = reinterpret_cast<const float4*>(xs)[q];
+// r[f] = sum_p (sum_c x[c][p]) w_f[p] -> rs[f] (smem).  All threads stream every filter together (coalesced 128-bit loads), FB filters at a
+// time so that each image quad read from shared memory serves FB filters and FB x 2 independent global loads are in flight per thread
+// (the bank streams from L2/HBM once per iteration: this loop is the bandwidth-bound part of the ascent).  Per-warp partial sums are
+// combined in a fixed order.  `part`: [Fmax][MEI_THREADS/32] floats of shared memory.
+constexpr int MEI_FB = 4;
+__device__ inline void mei_dots(const float* xs, int C, int HW, const float* __restrict__ bank, int F, float* rs, float* part) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = MEI_THREADS / 32;
+    if ((HW % 4) == 0) {
+        const int HW4 = HW / 4;
+        const float4* xs4 = reinterpret_cast<const float4*>(xs);
+        for (int f0 = 0; f0 < F; f0 += MEI_FB) {
+            float acc[MEI_FB];
+            const float4* w4[MEI_FB];
+#pragma unroll
+            for (int b = 0; b < MEI_FB; ++b) {
+                acc[b] = 0.f;
+                w4[b] = reinterpret_cast<const float4*>(bank + (size_t)min(f0 + b, F - 1) * HW);  // ragged last block: recompute the last filter
+            }
+#pragma unroll 2
+            for (int q = threadIdx.x; q < HW4; q += MEI_THREADS) {
+                float4 ww[MEI_FB];
+#pragma unroll
+                for (int b = 0; b < MEI_FB; ++b) ww[b] = __ldg(w4[b] + q);
+                float4 xv = xs4[q];
                 for (int c = 1; c < C; ++c) {
-                    const float4 t = reinterpret_cast<const float4*>(xs + (size_t)c * HW)[q];
+                    const float4 t = xs4[(size_t)c * HW4 + q];
                     xv.x += t.x, xv.y += t.y, xv.z += t.z, xv.w += t.w;
                 }
-                acc = fmaf(xv.x, ww.x, acc), acc = fmaf(xv.y, ww.y, acc), acc = fmaf(xv.z, ww.z, acc), acc = fmaf(xv.w, ww.w, acc);
+#pragma unroll
+                for (int b = 0; b < MEI_FB; ++b)
+                    acc[b] = fmaf(xv.x, ww[b].x, fmaf(xv.y, ww[b].y, fmaf(xv.z, ww[b].z, fmaf(xv.w, ww[b].w, acc[b]))));
             }
-        } else {
-            for (int p = lane; p < HW; p += 32) {
+#pragma unroll
+            for (int b = 0; b < MEI_FB; ++b) {
+                const float v = warp_sum(acc[b]);
+                if (lane == 0 && f0 + b < F) part[(f0 + b) * NW + warp] = v;
+            }
+        }
+    } else {
+        for (int f = 0; f < F; ++f) {
+            const float* w = bank + (size_t)f * HW;
+            float acc = 0.f;
+            for (int p = threadIdx.x; p < HW; p += MEI_THREADS) {
                 float xv = xs[p];
                 for (int c = 1; c < C; ++c) xv += xs[(size_t)c * HW + p];
                 acc = fmaf(xv, __ldg(w + p), acc);
             }
+            acc = warp_sum(acc);
+            if (lane == 0) part[f * NW + warp] = acc;
         }
-        acc = warp_sum(acc);
-        if (lane == 0) rs[f] = acc;
+    }
+    __syncthreads();
+    for (int f = threadIdx.x; f < F; f += MEI_THREADS) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v += part[f * NW + w];
+        rs[f] = v;
     }
     __syncthreads();
 }
@@ -518,12 +549,13 @@ __global__ void __launch_bounds__(MEI_THREADS) mei_kernel(float* __restrict__ x,
     const int F = nfilt[neuron];
     const float* bank = filters + (size_t)neuron * Fmax * HW;
     float* rs = xs + ((n + 3) / 4 * 4);
+    float* part = rs + ((Fmax + 3) / 4 * 4);  // [Fmax][MEI_THREADS/32]
     float* xg = x + (size_t)g * n;
     for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = xg[i];
     __syncthreads();
     if (apply_post_first) mei_post(xs, n, mode, target, mean, pmin, pmax, scratch);
     for (int it = 0; it <= iters; ++it) {
-        mei_dots(xs, C, HW, bank, F, rs);
+        mei_dots(xs, C, HW, bank, F, rs, part);
         if (threadIdx.x == 0) {
             float best = -INFINITY;
             int bi = 0;
@@ -716,7 +748,7 @@ extern "C" int lmr_mei_ascent(float* x, int G, int C, int HW, const float* filte
                               int apply_post_first, float* fevals, void* stream) {
     LMR_CHECK_ARG(G >= 1 && C >= 1 && HW >= 2 && iters >= 0, "mei: bad sizes");
     LMR_CHECK_ARG(mode == LMR_CONSTRAIN_NORM || mode == LMR_CONSTRAIN_STD, "mei: bad mode %d", mode);
-    const size_t smem = ((size_t)(C * HW + 3) / 4 * 4 + Fmax) * sizeof(float);
+    const size_t smem = ((size_t)(C * HW + 3) / 4 * 4 + (size_t)(Fmax + 3) / 4 * 4 + (size_t)Fmax * (MEI_THREADS / 32)) * sizeof(float);
     LMR_CHECK_ARG(smem <= 200 * 1024, "mei: image of %d floats does not fit the shared-memory resident kernel", C * HW);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     static size_t smem_set = 0;

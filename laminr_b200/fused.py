@@ -188,6 +188,8 @@ class LearnStepper:
 
     def loss(self):
         """loss of the last training step (device scalar): -mean(act/a*) - reg_scale * reg  (inv_temp_learn_match.py:204)."""
+        if self.ws_obj is not None:
+            return self.loss_buf[0]  # written by the fused objective kernel itself
         return -(self.act[0] / self.mei_act).mean() + self.g_reg[0] * self.reg[0]
 
     def last_acts(self):

@@ -72,7 +72,7 @@ class LearnPort:
             torch.autograd.set_detect_anomaly(True)
         loss.backward()
         self.opt.step()
-        return float(loss)
+        return float(loss.detach())
 
 
 class ConvResponsePort:
