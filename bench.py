@@ -516,7 +516,11 @@ def run_ours(args):
             "e2e": {"value": world * K / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": 4 * N_LATENTS, "d2h_bytes_per_step": 4},
             "gpu_launches": int(stepper.kernels_per_step * K),
             "roofline": {"bound": "tensor", "kernel": "lmr_inr_backward launch group (inr_bwd_tc_kernel dominant; + layer-0 weight gradient and partial reduction launches)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved / peak_tf, "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback",
+                         "frac": achieved / peak_tf,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of inr_bwd_tc_kernel, one `ncu --set full` capture of this workload
+                         # (profiles/r1b_ncu_inr_bwd_tc.md: 2.995 MB read, 0 written -- inputs and the 0.8 MB gradient image are L2-resident)
+                         "traffic": 2995456 if (res == 100 and args.precision != "fp32") else None, "traffic_unit": "bytes per launch (ncu, DRAM)",
+                         "peak_source": "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback",
                          "algorithmic_gflop": bwd_f / 1e9, "ms": bwd_ms, "forward": {"algorithmic_gflop": fwd_f / 1e9, "ms": fwd_ms, "achieved": fwd_f / (fwd_ms * 1e-3) / 1e12}},
             "cpu_baseline": cpu, "clocks": clocks, "match": match, "conv": conv,
         }

@@ -246,6 +246,24 @@ int lmr_mei_ascent(float* x, int G, int C, int HW, const float* filters, int Fma
                    const int* neuron_of_group, float step_size, int iters, int mode, float target, float mean,
                    float pmin, float pmax, float act_eps, int apply_post_first, float* fevals, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * RF masks on the device -- replaces create_mask (laminr/utils/mask.py:25-64; scipy.ndimage + skimage.morphology on
+ * the host, once per neuron, mei.py:56), batched over G channel-averaged MEIs [G,H,W] (H*W < 65536):
+ *   |z-score| > zscore_thresh -> binary closing (`closing_iters` dilations then erosions, 3x3 cross, outside = 0)
+ *   -> largest 8-connected component (ties: first in raster order) -> convex hull of the pixel edge mid-points,
+ *   tested at pixel centres (closed, exact integer arithmetic) -> separable Gaussian blur (scipy 'reflect',
+ *   float64 accumulation in scipy's summation order, float32 between the axes).
+ * blur_weights: device double[blur_radius+1], w[j] = weight of offset +-(blur_radius - j), w[blur_radius] = centre
+ *   (scipy: radius = int(4*sigma + 0.5), normalised exp(-0.5 (k/sigma)^2)).
+ * mask_out: [G,H,W] float32.  stats: uint32[G,4] = {hull pixel count, sum of hull row indices, sum of hull column
+ *   indices, flag}; centroid (mask.py:61) = sums / count + 0.5; flag = 1 when nothing exceeds the threshold (the
+ *   reference raises there: argmax of an empty sequence).
+ * ---------------------------------------------------------------------------------------------------------- */
+size_t lmr_create_mask_workspace_bytes(int G, int H, int W);
+int lmr_create_mask(const float* mei, int G, int H, int W, float zscore_thresh, int closing_iters,
+                    const double* blur_weights, int blur_radius, float* mask_out, unsigned* stats, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

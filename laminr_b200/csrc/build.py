@@ -5,7 +5,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["api.cu", "inr_simt.cu", "inr_tc.cu", "post.cu", "learn_obj.cu", "convcone.cu"]
+SOURCES = ["api.cu", "inr_simt.cu", "inr_tc.cu", "post.cu", "learn_obj.cu", "convcone.cu", "mask.cu"]
+OBJ_DIR = os.path.join(HERE, "_obj")  # git-ignored object cache: only changed translation units are recompiled
 OUT = os.path.join(os.path.dirname(HERE), "liblaminr_b200.so")
 
 
@@ -18,15 +19,35 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _stale(obj, src, headers):
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    return any(os.path.getmtime(d) > t for d in [src] + headers)
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
+    from concurrent.futures import ThreadPoolExecutor
+
     nvcc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-I" + os.path.join(ROOT, "include"),
-           "-Xcompiler", "-fPIC", "-shared", "-o", OUT] + [os.path.join(HERE, s) for s in SOURCES]
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-Xcompiler", "-fPIC"]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.run(cmd, check=True)
+        flags.append("-Xptxas=-v")
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".cuh")] + [os.path.join(ROOT, "include", "laminr_b200.h")]
+    objs, jobs = [], []
+    for s in SOURCES:
+        src, obj = os.path.join(HERE, s), os.path.join(OBJ_DIR, s[:-3] + ".o")
+        objs.append(obj)
+        if force or verbose or _stale(obj, src, headers):
+            jobs.append([nvcc] + flags + ["-c", src, "-o", obj])
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as ex:
+        for r in ex.map(lambda c: subprocess.run(c), jobs):
+            if r.returncode != 0:
+                raise subprocess.CalledProcessError(r.returncode, r.args)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs, check=True)
     return OUT
 
 

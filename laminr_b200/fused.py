@@ -114,6 +114,7 @@ class LearnStepper:
         self.ws_con = _ws(lib.lmr_constrain_workspace_bytes(N, Cc * P), dev)
         self.ws_clr = _ws(lib.lmr_simclr_workspace_bytes(N, Cc, P), dev)
         self.use_graph, self.graph, self.eval_graph = use_graph, None, None
+        self.side = torch.cuda.Stream(device=dev)
         # fused objective (one persistent launch for constraint + response + contrastive, forward and backward) for simulated neurons when it fits
         self.loss_buf = torch.zeros(1, **f32)
         self.ws_obj = None
@@ -151,10 +152,16 @@ class LearnStepper:
         ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, out=self.img_pre.view(1, N, Cc, P),
                             precision=self.precision, workspace=self.ws_fwd)
         ops.raw_constrain_fwd(c.mode, self.img_pre, c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.z, stats=self.stats, workspace=self.ws_con)
+        # the response (+ its image gradient -> g_z) and the contrastive forward are independent: run them side by side (the response of a
+        # 20-image batch occupies a fraction of the SMs), then add the contrastive gradient on top
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self.resp.forward_backward(self.z, 0, N, 1, Cc, P, self.nog, self.g_act, self.act, self.g_z, False)
         ops.raw_simclr_fwd(self.z, self.mask, N, Cc, P, self.pixel_min, self.pixel_max, r.flat_neighbor_mask_pos, r.flat_neighbor_mask_neg,
                            r.temperature, r.eps, reg=self.reg, K=self.K, workspace=self.ws_clr)
-        ops.raw_simclr_bwd(self.z, self.mask, self.K, self.g_reg, 1.0, N, Cc, P, self.pixel_min, self.pixel_max, self.g_z, accumulate=False)
-        self.resp.forward_backward(self.z, 0, N, 1, Cc, P, self.nog, self.g_act, self.act, self.g_z, True)  # response and its gradient, added to g_z
+        main.wait_stream(self.side)
+        ops.raw_simclr_bwd(self.z, self.mask, self.K, self.g_reg, 1.0, N, Cc, P, self.pixel_min, self.pixel_max, self.g_z, accumulate=True)
         ops.raw_constrain_bwd(c.mode, self.img_pre, self.g_z, self.stats, c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.g_x, workspace=self.ws_con)
         ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, self.g_x.view(1, N, Cc, P), want_params=True,
                              precision=self.precision, workspace=self.ws_bwd, g_params=self.g_flat, forward_workspace=self.ws_fwd)

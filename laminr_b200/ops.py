@@ -485,3 +485,35 @@ def raw_mei_ascent(x, filters, nfilt, neuron_of_group, step_size, iters, mode, t
                              int(mode), float(target), float(mean), float(pmin), float(pmax), float(act_eps), int(apply_post_first),
                              _ptr(fevals), _stream()))
     return fevals
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# RF masks (create_mask, laminr/utils/mask.py:25-64) on the device
+# --------------------------------------------------------------------------------------------------------------------
+def gaussian_blur_weights(sigma, truncate=4.0):
+    """scipy.ndimage.gaussian_filter1d's kernel (float64): radius = int(truncate*sigma + 0.5), normalised exp(-0.5 (k/sigma)^2).
+    Returned outermost tap first, centre last (the layout lmr_create_mask takes)."""
+    import numpy as np
+
+    radius = int(truncate * float(sigma) + 0.5)
+    k = np.arange(-radius, radius + 1)
+    phi = np.exp(-0.5 / (float(sigma) * float(sigma)) * k.astype(np.float64) ** 2)
+    phi = phi / phi.sum()
+    return phi[: radius + 1].copy(), radius
+
+
+def raw_create_mask(mei, zscore_thresh, closing_iters, gaussian_sigma, mask_out=None, stats=None, workspace=None):
+    """mei: [G,H,W] float32 (channel-averaged MEIs).  Returns (mask [G,H,W] float32, stats int64 [G,4] =
+    hull pixel count, row-index sum, column-index sum, empty flag)."""
+    lib = _lib.load()
+    _require_cuda(mei)
+    mei = _f32c(mei)
+    G, H, W = mei.shape
+    w, radius = gaussian_blur_weights(gaussian_sigma)
+    w_dev = torch.from_numpy(w).to(mei.device)
+    mask_out = torch.empty_like(mei) if mask_out is None else mask_out
+    stats = torch.empty((G, 4), dtype=torch.int32, device=mei.device) if stats is None else stats
+    ws = _workspace(lib.lmr_create_mask_workspace_bytes(G, H, W), mei.device) if workspace is None else workspace
+    check(lib.lmr_create_mask(_ptr(mei), G, H, W, float(zscore_thresh), int(closing_iters), _ptr(w_dev), radius, _ptr(mask_out), _ptr(stats), _ptr(ws),
+                              ws.numel(), _stream()))
+    return mask_out, stats

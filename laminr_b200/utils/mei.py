@@ -13,7 +13,7 @@ from ..featurevis import ops as fops
 from ..featurevis.utils import Compose
 from ..neuron_models.utils.simulated_model import ArbitraryMultiNeuronModel
 from .general import SingleNeuronModel, infer_device
-from .mask import create_mask
+from .mask import create_mask, create_masks
 
 
 def _check(std, norm):
@@ -97,11 +97,12 @@ def get_mei_dict(response_predicting_model, input_shape, pixel_value_lower_bound
         x0 = torch.cat([torch.randn(1, *input_shape, dtype=torch.float32) for _ in neuron_idxs]).to(device) + mean
         meis, fevals = batched(response_predicting_model, neuron_idxs, x0, pixel_value_lower_bound, pixel_value_upper_bound,
                                               std=required_img_std, norm=required_img_norm, step_size=step_size, num_iterations=num_iterations)
-        meis_host, acts_host = meis.cpu(), fevals[:, -1].cpu().tolist()
+        # all RF masks in one launch group on the device (the reference: one scipy/skimage host pass per neuron, mei.py:56)
+        masks, centres = create_masks(meis.mean(dim=1), zscore_thresh=zscore)
+        meis_host, acts_host, masks_host = meis.cpu(), fevals[:, -1].cpu().tolist(), masks.cpu()
         for idx, neuron_idx in enumerate(neuron_idxs):
             print(f"neuron_idx = {neuron_idx}: neuron number {idx}/{len(neuron_idxs)}")
-            mask, mask_center = create_mask(meis_host[idx].mean(dim=0), return_mask_centroid=True, zscore_thresh=zscore)
-            meis_dict[idx] = {"mei": meis_host[idx].numpy(), "activation": acts_host[idx], "mask": mask.numpy(), "center_pos": mask_center}
+            meis_dict[idx] = {"mei": meis_host[idx].numpy(), "activation": acts_host[idx], "mask": masks_host[idx].numpy(), "center_pos": centres[idx]}
         return meis_dict
 
     for idx, neuron_idx in enumerate(neuron_idxs):

@@ -525,6 +525,26 @@ def case_conv_learn_match(laminr):
     np.savez_compressed(os.path.join(OUT, "conv_learn_match_24.npz"), **d)
 
 
+def case_create_mask(laminr):
+    """The reference's own create_mask (mask.py:25-64; skimage's label / convex_hull_image through the import stubs of ref_harness) on
+    seeded MEI-like images: 16 at 40x40, 4 at 100x100, 2 at 37x53 (non-square), thresholds 0.3 (get_mei_dict's) and 1.5 (the default)."""
+    from laminr.utils.mask import create_mask
+    from oracle.mask_oracle import synthetic_meis
+
+    d = {}
+    for tag, (n, H, W, seed) in dict(a=(16, 40, 40, 1), b=(4, 100, 100, 2), c=(2, 37, 53, 3)).items():
+        meis = synthetic_meis(n, H, W, seed)
+        for zt in (0.3, 1.5):
+            masks, cents = [], []
+            for i in range(n):
+                m, c = create_mask(torch.from_numpy(meis[i])[None], zscore_thresh=zt, return_mask_centroid=True)
+                masks.append(npy(m)), cents.append([c["y"], c["x"]])
+            d[f"{tag}_mask_z{zt}"] = np.stack(masks)
+            d[f"{tag}_centre_z{zt}"] = np.array(cents, np.float64)
+        d[f"{tag}_shape_seed"] = np.array([n, H, W, seed])
+    np.savez_compressed(os.path.join(OUT, "create_mask.npz"), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     laminr = import_reference()
@@ -532,7 +552,7 @@ def main():
     import sys
     only = set(sys.argv[1:])
     for fn in (case_inr, case_match_inr, case_constrain, case_simresp, case_banks_100, case_simclr, case_training_utils,
-               case_adam, case_mei, case_learn_match_steps, case_trajectory, case_convcore, case_conv_learn_match):
+               case_adam, case_mei, case_learn_match_steps, case_trajectory, case_convcore, case_conv_learn_match, case_create_mask):
         if only and fn.__name__ not in only:
             continue
         fn(laminr)

@@ -176,6 +176,7 @@ def test_mei_argument_errors(L):
         L.get_mei_dict(m, [1, 8, 8], -1.0, 1.0, neuron_idxs=[0], required_img_std=1.0, required_img_norm=1.0)
 
 
+@pytest.mark.gpu
 def test_create_mask_centroid(L):
     from laminr_b200.utils.mask import create_mask
     yy, xx = np.meshgrid(np.arange(40), np.arange(40), indexing="ij")
