@@ -459,27 +459,28 @@ def run_ours(args):
                             "unit": "neurons/s", "epochs": int(im2.match_epochs_run), "seconds": mt2.item(), "targets_total": Dloc * world,
                             "result_shape": list(imgs.shape)}
         # ---- MEI sweep (BASELINE config 5): batched gradient ascent, 1000 iterations, neurons sharded over the ranks
-        from laminr_b200.utils.mei import batched_simulated_meis
         nmei = args.mei_neurons  # BASELINE configs[4]: 128 neurons per GPU
-        if nmei != Dloc + 1:
-            pop = L.neuron_models.simulated_population(nmei, img_res=[res, res], seed=2000 + rank).to(dev)
-        x0 = torch.randn(nmei, 1, res, res).to(dev)
-        batched_simulated_meis(pop, list(range(nmei)), x0, -1.0, 1.0, norm=1.0, num_iterations=10)
-        barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        _, fev = batched_simulated_meis(pop, list(range(nmei)), x0, -1.0, 1.0, norm=1.0, num_iterations=1000)
-        b.record()
-        barrier()
-        mt3 = torch.tensor([a.elapsed_time(b)], device=dev)
-        if world > 1:
-            dist.all_reduce(mt3, op=dist.ReduceOp.MAX)
-        mei_bytes = (20 * res * res * 4 + 3 * res * res * 4) * 1000 * nmei  # F*P*4 + 3*C*P*4 per neuron-iteration
-        match["mei"] = {"metric": "MEIs/sec (1000 ascent iterations each, batched)", "value": nmei * world / (mt3.item() / 1e3), "unit": "MEIs/s",
-                        "neurons_per_gpu": nmei, "ms": mt3.item(), "final_activation_mean": float(fev[:, -1].mean().item()),
-                        "algorithmic_GBps_per_gpu": mei_bytes / (mt3.item() / 1e3) / 1e9,
-                        "note": "the per-GPU filter bank (neurons x 20 x HW x 4 B) is re-read every iteration; at 128 neurons x 100x100 it is 102 MB and mostly "
-                                "L2-resident (126 MB L2), so the algorithmic rate can exceed the HBM copy peak"}
+        if nmei > 0:
+            from laminr_b200.utils.mei import batched_simulated_meis
+            if nmei != Dloc + 1:
+                pop = L.neuron_models.simulated_population(nmei, img_res=[res, res], seed=2000 + rank).to(dev)
+            x0 = torch.randn(nmei, 1, res, res).to(dev)
+            batched_simulated_meis(pop, list(range(nmei)), x0, -1.0, 1.0, norm=1.0, num_iterations=10)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _, fev = batched_simulated_meis(pop, list(range(nmei)), x0, -1.0, 1.0, norm=1.0, num_iterations=1000)
+            b.record()
+            barrier()
+            mt3 = torch.tensor([a.elapsed_time(b)], device=dev)
+            if world > 1:
+                dist.all_reduce(mt3, op=dist.ReduceOp.MAX)
+            mei_bytes = (20 * res * res * 4 + 3 * res * res * 4) * 1000 * nmei  # F*P*4 + 3*C*P*4 per neuron-iteration
+            match["mei"] = {"metric": "MEIs/sec (1000 ascent iterations each, batched)", "value": nmei * world / (mt3.item() / 1e3), "unit": "MEIs/s",
+                            "neurons_per_gpu": nmei, "ms": mt3.item(), "final_activation_mean": float(fev[:, -1].mean().item()),
+                            "algorithmic_GBps_per_gpu": mei_bytes / (mt3.item() / 1e3) / 1e9,
+                            "note": "the per-GPU filter bank (neurons x 20 x HW x 4 B) is re-read every iteration; at 128 neurons x 100x100 it is 102 MB and mostly "
+                                    "L2-resident (126 MB L2), so the algorithmic rate can exceed the HBM copy peak"}
 
     # ---- BASELINE config 4 (extra): conv-core encoder at 200x200
     conv = bench_conv(args, dev, world, rank, barrier, flush) if args.conv_res > 0 else None

@@ -696,6 +696,7 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
     TcSmem s(smem_raw, nt, tl, NBUF_BWD, false, NG);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const bool want_w = a.want_weights != 0;
+    if (t == 0) LMR_TRACE(0, 500);
     load_weight_tiles(a, s);
     init_layer0_tables(a, s, true, NT_B);
     if (warp == NE / 32) tmem_alloc(s.tmem, TM_COLS_BWD);
@@ -706,6 +707,7 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
     fence_after_sync();
     const uint32_t tm = *s.tmem;
     const int myTiles = (tl.numTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    if (t == 0) LMR_TRACE(0, 501);
 
     if (warp == NE / 32) {
         if (lane == 0) {  // ---- MMA issuer
@@ -781,13 +783,48 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
         }
         if (myTiles > 0) stage_tile_inputs(a, decode_tile(tl, blockIdx.x), s.Cps, NE);
         cp_async_commit();
+        // ---- layer 0 of a finished tile (CUDA cores; consecutive lanes -> consecutive features: conflict-free), DEFERRED into the next tile's
+        //      first two accumulator waits (software pipelining; the panel stage[row][o] of dz_0 sits in a buffer the next tile does not write
+        //      before its own dz_2):
+        //      G0[j][o] = sum_n dz0 goes straight to global memory (consumed by the layer-0 weight-gradient kernel / the coordinate-gradient
+        //      kernel in match);  dA[n][o] += sum_j dz0 stays in registers
+        auto reduce_g0 = [&](const TileIdx& tp, const float* stage) {
+            if (t < TP * SHP && g0_j < tp.np) {
+                float sum = 0.f;
+                if (g0_o < HID) {
+                    const float* zr = stage + g0_j * STG + g0_o;
+                    float s0 = 0.f, s1 = 0.f;
+                    int n = 0;
+                    for (; n + 1 < tp.nn; n += 2) s0 += zr[n * TP * STG], s1 += zr[(n + 1) * TP * STG];
+                    if (n < tp.nn) s0 += zr[n * TP * STG];
+                    sum = s0 + s1;
+                }
+                a.G0[((size_t)tp.d * tl.P + tp.p0 + g0_j) * SHP + g0_o] = sum;
+            }
+        };
+        auto reduce_dA = [&](const TileIdx& tp, const float* stage) {
+#pragma unroll
+            for (int q = 0; q < MAX_DA; ++q) {
+                const int e = t + NE * q, n = e / HID, o = e % HID;
+                if (n < tp.nn) {
+                    const float* zr = stage + n * TP * STG + o;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < TP_CAP_TC; ++jj)
+                        if (jj < tp.np) sum += zr[jj * STG];
+                    dA[q] += sum;
+                }
+            }
+        };
+        TileIdx ti_prev = {0, 0, 0, 0, 0};
+        const float* stage_prev = nullptr;
 
         for (int it = 0; it < myTiles; ++it) {
             const TileIdx ti = decode_tile(tl, blockIdx.x + it * gridDim.x);
             const int rot = (2 * it) % NBUF_BWD;
             auto buf = [&](int role) { return s.tiles + (size_t)((role + rot) % NBUF_BWD) * TILE_BYTES; };
             cp_async_wait<0>();
-            named_bar_sync(1, NE);  // staged Cp visible; every epilogue thread is done with the previous tile's staging panel / scratch
+            named_bar_sync(1, NE);  // staged Cp visible; the previous tile's dz_0 panel is complete; everybody is done with its scratch
             if (it + 1 < myTiles) stage_tile_inputs(a, decode_tile(tl, blockIdx.x + (it + 1) * gridDim.x), s.Cps + ((it + 1) & 1) * TP * SHS, NE);
             cp_async_commit();
             if (t == 0) LMR_TRACE(0, it * 20 + 0);
@@ -818,9 +855,11 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
             }
             tanh_store<NG, FAST>(v, buf(ROLE_H1), rc, &s.bars[BAR_K], active);
             if (t == 0) LMR_TRACE(0, it * 20 + 1);
+            if (it > 0) reduce_g0(ti_prev, stage_prev);  // while the tensor pipe computes z_2
             int st = 0;
 #pragma unroll 1
             for (int l = 1; l < LH - 1; ++l, ++st) {
+                if (l == 2 && it > 0 && want_w) reduce_dA(ti_prev, stage_prev);  // while the tensor pipe computes z_3
                 wait_acc(st);
                 if (t == 0) LMR_TRACE(0, it * 20 + 2 + 2 * st);
                 load_acc<NG>(tm + TM_ACC + (uint32_t)(st & 1) * 64 + rc.lane_taddr, rc.g, vf);
@@ -891,8 +930,10 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
                 if (t == 0) LMR_TRACE(0, it * 20 + 1 + 2 * st);
             }
             // ---- layers 3, 2, 1: dz_{l-1} = dh_l (1 - h_l^2)   (h_l[50] == 1 zeroes the bias column).  dz_2, dz_1 -> the other gradient tile;
-            //      dz_0 feeds only CUDA-core reductions: fp32 staging panel stage[row][o] in the free gradient tile
-            float* stage = reinterpret_cast<float*>(buf(ROLE_DB));
+            //      dz_0 feeds only CUDA-core reductions: fp32 staging panel stage[row][o]
+            // (h_2's buffer: its last reader, the dW_2 product, completed before the dh_1 accumulator this step waits for; the buffer is not
+            //  written again before the NEXT tile's dz_2, so the panel outlives the deferred reductions)
+            float* stage = reinterpret_cast<float*>(buf(ROLE_H1 + 1));
 #pragma unroll 1
             for (int l = LH - 1; l >= 1; --l, ++st) {
                 const uint8_t* Hl = buf(ROLE_H1 + l - 1);
@@ -926,41 +967,20 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
                 }
                 if (t == 0) LMR_TRACE(0, it * 20 + 3 + 2 * st);
             }
-            named_bar_sync(1, NE);  // dz_0 staged (and beta written)
-            if (t == 0) LMR_TRACE(0, it * 20 + 15);
-            // ---- layer 0: G0[j][o] = sum_n dz0, dA[n][o] += sum_j dz0   (CUDA cores; consecutive lanes -> consecutive features: conflict-free)
-            // G0 goes straight to global memory: it is consumed by the layer-0 weight-gradient kernel (learn) / the coordinate-gradient kernel (match)
-            if (t < TP * SHP && g0_j < ti.np) {
-                float sum = 0.f;
-                if (g0_o < HID) {
-                    const float* zr = stage + g0_j * STG + g0_o;
-                    float s0 = 0.f, s1 = 0.f;
-                    int n = 0;
-                    for (; n + 1 < ti.nn; n += 2) s0 += zr[n * TP * STG], s1 += zr[(n + 1) * TP * STG];
-                    if (n < ti.nn) s0 += zr[n * TP * STG];
-                    sum = s0 + s1;
-                }
-                a.G0[((size_t)ti.d * tl.P + ti.p0 + g0_j) * SHP + g0_o] = sum;
-            }
-            if (want_w) {
-#pragma unroll
-                for (int q = 0; q < MAX_DA; ++q) {
-                    const int e = t + NE * q, n = e / HID, o = e % HID;
-                    if (n < ti.nn) {
-                        const float* zr = stage + n * TP * STG + o;
-                        float sum = 0.f;
-#pragma unroll
-                        for (int jj = 0; jj < TP_CAP_TC; ++jj)
-                            if (jj < ti.np) sum += zr[jj * STG];
-                        dA[q] += sum;
-                    }
-                }
-            }
+            ti_prev = ti, stage_prev = stage;
             if (t == 0) LMR_TRACE(0, it * 20 + 16);
         }
+        if (myTiles > 0) {  // the last tile's layer 0
+            named_bar_sync(1, NE);
+            reduce_g0(ti_prev, stage_prev);
+            if (want_w) reduce_dA(ti_prev, stage_prev);
+            named_bar_sync(1, NE);  // the drain reuses the tile buffers
+        }
         // ---- drain: wait for every MMA, then read the weight-gradient accumulators out of TMEM and write this CTA's partial
+        if (t == 0) LMR_TRACE(0, 502);
         mbar_wait(&s.bars[BAR_DONE], 0);
         fence_after_sync();
+        if (t == 0) LMR_TRACE(0, 503);
         if (want_w) {
             float* part = a.partials + (size_t)blockIdx.x * partial_size(nt, tl, SHP);
             float* p_dW = part;
@@ -1021,6 +1041,7 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
                 if (n < tl.NC) p_dA[n * SHP + o] = dA[q];
             }
         }
+        if (t == 0) LMR_TRACE(0, 504);
     }
     fence_before_sync();
     __syncthreads();
@@ -1161,6 +1182,11 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
         cudaStreamSynchronize(st);
         cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
         const long long t0 = h[0];
+        fprintf(stderr, "[trace] CTA 0 (cycles rel. to first tile start): entry %lld  prologue done %lld  tiles done %lld  MMAs done %lld  drain done %lld\n", h[500] - t0,
+                h[501] - t0, h[502] - t0, h[503] - t0, h[504] - t0);
+        fprintf(stderr, "[trace] tile starts:");
+        for (int it = 0; it < 24 && (it == 0 || h[it * 20]); ++it) fprintf(stderr, " %lld", h[it * 20] - t0);
+        fprintf(stderr, "\n");
         for (int it = 0; it < 3; ++it) {
             fprintf(stderr, "[trace] tile %d  E:", it);
             for (int e = 0; e < 17; ++e) fprintf(stderr, " %lld", h[it * 20 + e] ? h[it * 20 + e] - t0 : -1);
