@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -60,7 +61,8 @@ struct Args {
     unsigned char* wtimg;  // (nl-1) x 16 KB: split-bf16 (hi | lo) K-major core-matrix images of the hidden weight tiles (tensor-core path)
     float* betaG;  // [D*P, 2*pe] sin/cos(coords.B) (tensor-core path, D == 1: consumed by the layer-0 weight-gradient kernel), else null
     int want_cp;
-    int ppb;       // pixels per prep / l0 block
+    int ppb;       // pixels per l0 / affine-gradient block
+    int ppb_prep;  // pixels per prep block (two blocks per SM: the prep blocks are latency-bound)
     // forward
     float* img;  // [D,N,C,P]
     // backward
@@ -120,8 +122,8 @@ __device__ inline float2 transformed_coord(const Args& a, const float* affc, int
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int PREP_PPB_MAX = 72;  // pixels per block (multiple of 4)
 
-static inline int choose_ppb(int total_pixels) {
-    int ppb = (total_pixels + num_sms() - 1) / num_sms();
+static inline int choose_ppb(int total_pixels, int blocks_per_sm = 1) {
+    int ppb = (total_pixels + blocks_per_sm * num_sms() - 1) / (blocks_per_sm * num_sms());
     ppb = (ppb + 3) / 4 * 4;
     if (ppb < 16) ppb = 16;
     if (ppb > PREP_PPB_MAX) ppb = PREP_PPB_MAX;
@@ -195,11 +197,11 @@ __global__ void __launch_bounds__(256) prep_all_kernel(Args a) {
             }
             for (int i = t; i < nb * (HP - HID); i += blockDim.x) a.W0cT[(size_t)(i / (HP - HID)) * HP + HID + i % (HP - HID)] = 0.f;
         }
-    } else if (a.want_cp && bid >= N + 1 + (a.tl.D * a.tl.P + a.ppb - 1) / a.ppb) {
+    } else if (a.want_cp && bid >= N + 1 + (a.tl.D * a.tl.P + a.ppb_prep - 1) / a.ppb_prep) {
         // weight-tile images: W_l[o][k] for k < HID, column HID = bias b_l[o], entry [HID][HID] = 20 (regenerates the constant-1 feature
         // through tanh), rest 0; bf16 hi and lo = bf16(v - hi) halves in the no-swizzle K-major core-matrix layout of a [64 x 64] tile.
         constexpr int U = 4;
-        const int wb = bid - (N + 1 + (a.tl.D * a.tl.P + a.ppb - 1) / a.ppb);
+        const int wb = bid - (N + 1 + (a.tl.D * a.tl.P + a.ppb_prep - 1) / a.ppb_prep);
         float v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(256) prep_all_kernel(Args a) {
     } else {
         // pixels [q0, q0 + nq): beta (kept k-major in shared memory: 4 pixels per float4), then a register-blocked 4 pixel x 4 output GEMM.
         // Every global read of the block is issued up front (the block is latency-bound otherwise).
-        const int ppb = a.ppb;
+        const int ppb = a.ppb_prep;
         float* Wc = psm;             // [nb][HP]
         float* bet = Wc + nb * HP;   // [nb][ppb]
         __shared__ float cst[2][10];
@@ -699,6 +701,7 @@ static inline int fill_args(Args& a, const Net& nt, const Tiling& tl, const floa
     a.betaG = wl.betaG ? reinterpret_cast<float*>(base + wl.betaG) : nullptr;
     a.want_cp = 0;
     a.ppb = wl.ppb;
+    a.ppb_prep = choose_ppb(tl.D * tl.P, 2);
     a.dAred = reinterpret_cast<float*>(base + wl.dAred);
     a.G0 = reinterpret_cast<float*>(base + wl.G0);
     a.partials = reinterpret_cast<float*>(base + wl.partials);
@@ -712,9 +715,9 @@ template <int HID>
 static int launch_prep(const Args& a, cudaStream_t st) {
     constexpr int HP = (HID + 3) / 4 * 4;
     const int nb = 2 * a.net.pe;
-    const int cp_blocks = a.want_cp ? (a.tl.D * a.tl.P + a.ppb - 1) / a.ppb : 0;
+    const int cp_blocks = a.want_cp ? (a.tl.D * a.tl.P + a.ppb_prep - 1) / a.ppb_prep : 0;
     size_t smem = (size_t)2 * a.net.ape * sizeof(float);
-    if (a.want_cp) smem = ((size_t)nb * HP + (size_t)nb * a.ppb) * sizeof(float);
+    if (a.want_cp) smem = ((size_t)nb * HP + (size_t)nb * a.ppb_prep) * sizeof(float);
     static size_t cache = 0;
     if (smem > 40 * 1024 && smem > cache) {  // static shared memory counts against the 48 KB default limit too
         LMR_CUDA_OK(cudaFuncSetAttribute(prep_all_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

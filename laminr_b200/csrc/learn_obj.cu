@@ -12,13 +12,14 @@
 // per-CTA partials in global memory, a software grid barrier (all CTAs co-resident: cooperative launch, grid <= #SMs) and a fixed-order
 // (deterministic) combine.  4 grid barriers (5 in STD mode).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace lmr {
 namespace lobj {
 
-constexpr int NT = 256;
+constexpr int NT = 512;  // 16 warps: the phases are latency-bound scans over a 68-pixel slice of 20 images, flattened over all threads
 
 struct Params {
     int mode, N, C, HW, F;
@@ -38,6 +39,7 @@ struct Params {
     unsigned int* sync;    // [0] arrival counter (monotonic), [1] launch epoch
     float *part_a, *part_b, *fin, *part_c;
     int PS;                // pixels per slice
+    long long* trace;      // debug (LMR_OBJ_TRACE=1): CTA 0's phase time stamps (globaltimer ns), else null
 };
 
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
@@ -91,6 +93,14 @@ __device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
 
+__device__ __forceinline__ void stamp(const Params& p, int idx) {
+    if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        long long tns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+        p.trace[idx] = tns;
+    }
+}
+
 __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     extern __shared__ __align__(16) float sm[];
     const int N = p.N, C = p.C, HW = p.HW, F = p.F, NC = N * C;
@@ -117,8 +127,9 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     float* Ks = rowc + 4 * N;          // [N][N]
     float* posS = Ks + N * N;          // [N][N]
     float* negS = posS + N * N;        // [N][N]
-    __shared__ float scratch[40];
+    stamp(p, 0);
     const unsigned int epoch = ld_acquire(p.sync + 1);
+    const float g_reg = __ldg(p.g_reg);  // issued up front: an L2 round trip that would otherwise sit on the critical path after barrier 3
     const unsigned int nbar = p.mode == LMR_CONSTRAIN_NORM ? 4u : 5u;
     unsigned int bar_no = 0;
     auto barrier = [&]() {
@@ -150,6 +161,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     for (int i = t; i < N * N; i += NT) cp_async4(posS + i, p.pos + i), cp_async4(negS + i, p.neg + i);
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    stamp(p, 1);
     if (p.mode == LMR_CONSTRAIN_NORM) {
         for (int n = warp; n < N; n += NW) {
             float acc = 0.f;
@@ -200,74 +212,73 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     if (b == 0 && p.stats != nullptr)
         for (int n = t; n < N; n += NT) p.stats[2 * n] = sd[n], p.stats[2 * n + 1] = mu[n];
 
-    // ---- phase 1: z (written out), sum_c z, masked z; partial responses and partial gram
+    stamp(p, 2);
+    // ---- phase 1: z (written out), sum_c z, masked z; partial responses and partial gram  (work items flattened over all threads)
 #pragma unroll 1
-    for (int r = warp; r < NC; r += NW) {
-        const int n = r / C;
-        const float sdn = sd[n] + p.eps_con, mun = mu[n];
-        float* zdst = p.z + (size_t)r * HW + p0;
-        for (int e = lane; e < PS; e += 32) {
-            float y;
-            if (p.mode == LMR_CONSTRAIN_NORM) y = (xs[r * PSP + e] - p.mean) / sdn * p.target + p.mean;
-            else y = p.target * (xs[r * PSP + e] - mun) / sdn + p.mean;
-            if (p.has_min) y = fmaxf(y, p.pmin);
-            if (p.has_max) y = fminf(y, p.pmax);
-            if (e < np) {
-                zdst[e] = y;
-                xm[r * PSP + e] = masked_value(y, mk[e], p.c0, p.g1, p.g2);
-                gy[r * PSP + e] = y;  // z, until phase 3 overwrites it
-            } else {
-                xm[r * PSP + e] = 0.f, gy[r * PSP + e] = 0.f;
-            }
+    for (int i = t; i < NC * PS; i += NT) {
+        const int r = i / PS, e = i - r * PS, n = r / C;
+        const float sdn = sd[n] + p.eps_con;
+        float y;
+        if (p.mode == LMR_CONSTRAIN_NORM) y = (xs[r * PSP + e] - p.mean) / sdn * p.target + p.mean;
+        else y = p.target * (xs[r * PSP + e] - mu[n]) / sdn + p.mean;
+        if (p.has_min) y = fmaxf(y, p.pmin);
+        if (p.has_max) y = fminf(y, p.pmax);
+        if (e < np) {
+            p.z[(size_t)r * HW + p0 + e] = y;
+            xm[r * PSP + e] = masked_value(y, mk[e], p.c0, p.g1, p.g2);
+            gy[r * PSP + e] = y;  // z, until phase 3 overwrites it
+        } else {
+            xm[r * PSP + e] = 0.f, gy[r * PSP + e] = 0.f;
         }
     }
     __syncthreads();
 #pragma unroll 1
-    for (int n = warp; n < N; n += NW)
-        for (int e = lane; e < PS; e += 32) {
-            float v = 0.f;
-            for (int c = 0; c < C; ++c) v += gy[(n * C + c) * PSP + e];
-            zs[n * PSP + e] = v;
-        }
+    for (int i = t; i < N * PS; i += NT) {
+        const int n = i / PS, e = i - n * PS;
+        float v = 0.f;
+        for (int c = 0; c < C; ++c) v += gy[(n * C + c) * PSP + e];
+        zs[n * PSP + e] = v;
+    }
     __syncthreads();
     {
         float* outR = p.part_b + (size_t)b * (N * F + N * N);
         float* outG = outR + N * F;
-        // responses: warp -> image n, lanes -> filters (row stride PSP is odd: conflict-free)
+        // one thread per (image, filter) response and per (i <= j) gram entry; rows have the odd stride PSP: conflict-free across filters
 #pragma unroll 1
-        for (int n = warp; n < N; n += NW) {
-            const float* a = zs + n * PSP;
-#pragma unroll 1
-            for (int f = lane; f < F; f += 32) {
+        for (int it = t; it < N * F + N * N; it += NT) {
+            if (it < N * F) {
+                const int n = it / F, f = it - n * F;
+                const float* a = zs + n * PSP;
                 const float* w = ws + f * PSP;
-                float s0 = 0.f, s1 = 0.f;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
                 int e = 0;
-#pragma unroll 4
-                for (; e + 1 < PS; e += 2) s0 = fmaf(a[e], w[e], s0), s1 = fmaf(a[e + 1], w[e + 1], s1);
-                if (e < PS) s0 = fmaf(a[e], w[e], s0);
-                outR[n * F + f] = s0 + s1;
-            }
-        }
-        // gram: warp -> image i, lanes -> images j >= i
-#pragma unroll 1
-        for (int i = warp; i < N; i += NW) {
-#pragma unroll 1
-            for (int j = i + lane; j < N; j += 32) {
-                float s0 = 0.f, s1 = 0.f;
+#pragma unroll 2
+                for (; e + 3 < PS; e += 4)
+                    s0 = fmaf(a[e], w[e], s0), s1 = fmaf(a[e + 1], w[e + 1], s1), s2 = fmaf(a[e + 2], w[e + 2], s2), s3 = fmaf(a[e + 3], w[e + 3], s3);
+                for (; e < PS; ++e) s0 = fmaf(a[e], w[e], s0);
+                outR[it] = (s0 + s1) + (s2 + s3);
+            } else {
+                const int pr = it - N * F, i = pr / N, j = pr - i * N;
+                if (j < i) continue;
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
                 for (int c = 0; c < C; ++c) {
                     const float* a = xm + (i * C + c) * PSP;
                     const float* w = xm + (j * C + c) * PSP;
                     int e = 0;
-#pragma unroll 4
-                    for (; e + 1 < PS; e += 2) s0 = fmaf(a[e], w[e], s0), s1 = fmaf(a[e + 1], w[e + 1], s1);
-                    if (e < PS) s0 = fmaf(a[e], w[e], s0);
+#pragma unroll 2
+                    for (; e + 3 < PS; e += 4)
+                        s0 = fmaf(a[e], w[e], s0), s1 = fmaf(a[e + 1], w[e + 1], s1), s2 = fmaf(a[e + 2], w[e + 2], s2), s3 = fmaf(a[e + 3], w[e + 3], s3);
+                    for (; e < PS; ++e) s0 = fmaf(a[e], w[e], s0);
                 }
-                outG[i * N + j] = s0 + s1;
-                outG[j * N + i] = s0 + s1;
+                const float g = (s0 + s1) + (s2 + s3);
+                outG[i * N + j] = g;
+                outG[j * N + i] = g;
             }
         }
     }
+    stamp(p, 3);
     barrier();
+    stamp(p, 4);
     // ---- phase 2: two-level combine of the partials (value v is summed by CTA v % G), then everybody reads the totals
     {
         const int nval = N * F + N * N;
@@ -276,81 +287,97 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
             if ((lane & (GRP - 1)) == 0) p.fin[v] = tot;
         }
     }
+    stamp(p, 5);
     barrier();
+    stamp(p, 6);
     {
         const int nval = N * F + N * N;
         for (int v = t; v < nval; v += NT) fin[v] = __ldcg(p.fin + v);
     }
     __syncthreads();
-    const float g_reg = p.g_reg[0];
-    // responses: first maximum wins (torch.max), act = (elu(m)+1)/2 + eps
-    for (int n = t; n < N; n += NT) {
+    // responses: first maximum wins (torch.max), act = (elu(m)+1)/2 + eps.  8 lanes per image scan the filters f = sub, sub + 8, ..; ties go to the
+    // lower filter index in the lane-local scan and in the shuffle combine
+    for (int n = t / GRP; n < N; n += NT / GRP) {
+        const int sub = lane & (GRP - 1);
         float best = -INFINITY;
-        int bi = 0;
-        for (int f = 0; f < F; ++f) {
+        int bi = 0x7fffffff;
+        for (int f = sub; f < F; f += GRP) {
             const float r = fin[n * F + f];
             if (r > best) best = r, bi = f;
         }
-        const float e = best > 0.f ? best : expm1f(best);
-        const float act = (e + 1.f) / 2.f + p.act_eps;
-        amax[n] = bi;
-        coef[n] = (-p.inv_mei_act / (float)N) * 0.5f * (best > 0.f ? 1.f : expf(best));
-        rho[n] = act;  // parked until the loss is formed below
-        if (b == 0) {
-            p.act[n] = act;
-            if (p.rmax) p.rmax[n] = best;
-            if (p.argmax) p.argmax[n] = bi;
+        const unsigned gmask = 0xffu << (lane & ~(GRP - 1));
+#pragma unroll
+        for (int o = 1; o < GRP; o <<= 1) {
+            const float ob = __shfl_xor_sync(gmask, best, o);
+            const int oi = __shfl_xor_sync(gmask, bi, o);
+            if (ob > best || (ob == best && oi < bi)) best = ob, bi = oi;
         }
+        if (sub == 0) {
+            if (bi == 0x7fffffff) bi = 0;  // every response is NaN / -inf: torch.max returns index 0 of the first maximum
+            const float e = best > 0.f ? best : expm1f(best);
+            const float act = (e + 1.f) / 2.f + p.act_eps;
+            amax[n] = bi;
+            coef[n] = (-p.inv_mei_act / (float)N) * 0.5f * (best > 0.f ? 1.f : expf(best));
+            rho[n] = act;  // parked until the loss is formed below
+            if (b == 0) {
+                p.act[n] = act;
+                if (p.rmax) p.rmax[n] = best;
+                if (p.argmax) p.argmax[n] = bi;
+            }
+        }
+    }
+    // contrastive term and its backward coefficient matrix K (same maths as post.cu simclr_finalize_kernel)
+    const float* gram = fin + N * F;
+    for (int pr = t; pr < N * N; pr += NT) {
+        const int i = pr / N, j = pr - i * N;
+        const float c = gram[pr] / (sqrtf(gram[i * N + i]) * sqrtf(gram[j * N + j]));
+        cosm[pr] = c;
+        Sm[pr] = expf(c / p.T);
     }
     __syncthreads();
     float act_sum = 0.f;
     if (t == 0)
         for (int n = 0; n < N; ++n) act_sum += rho[n];
     __syncthreads();
-    // contrastive term and its backward coefficient matrix K (same maths as post.cu simclr_finalize_kernel)
-    const float* gram = fin + N * F;
     for (int i = t; i < N; i += NT) rho[i] = sqrtf(gram[i * N + i]);
-    __syncthreads();
-    for (int pr = t; pr < N * N; pr += NT) {
-        const int i = pr / N, j = pr % N;
-        const float c = gram[pr] / (rho[i] * rho[j]);
-        cosm[pr] = c;
-        Sm[pr] = expf(c / p.T);
-    }
-    __syncthreads();
-    float logsum = 0.f;
-    for (int i = t; i < N; i += NT) {
+    // one warp per row: masked row sums of S over the lanes (fixed shuffle tree: deterministic)
+    for (int i = warp; i < N; i += NW) {
         float ps = 0.f, np_ = 0.f, ns = 0.f, nn = 0.f;
-        for (int j = 0; j < N; ++j) {
+        for (int j = lane; j < N; j += 32) {
             ps = fmaf(Sm[i * N + j], posS[i * N + j], ps), np_ += posS[i * N + j];
             ns = fmaf(Sm[i * N + j], negS[i * N + j], ns), nn += negS[i * N + j];
         }
-        const float num = (ps == 0.f ? 0.f : ps / np_) + p.eps_clr;
-        const float den = (ns == 0.f ? 0.f : ns / nn) + p.eps_clr;
-        logsum += logf(num / den);
-        rowc[i * 4 + 0] = ps == 0.f ? 0.f : (p.T / (2.f * N)) / (np_ * num);
-        rowc[i * 4 + 1] = ns == 0.f ? 0.f : (p.T / (2.f * N)) / (nn * den);
+        ps = warp_sum(ps), np_ = warp_sum(np_), ns = warp_sum(ns), nn = warp_sum(nn);
+        if (lane == 0) {
+            const float num = (ps == 0.f ? 0.f : ps / np_) + p.eps_clr;
+            const float den = (ns == 0.f ? 0.f : ns / nn) + p.eps_clr;
+            rowc[i * 4 + 0] = ps == 0.f ? 0.f : (p.T / (2.f * N)) / (np_ * num);
+            rowc[i * 4 + 1] = ns == 0.f ? 0.f : (p.T / (2.f * N)) / (nn * den);
+            rowc[i * 4 + 2] = logf(num / den);
+        }
     }
-    logsum = block_sum(logsum, scratch);
+    __syncthreads();
     if (b == 0 && t == 0) {
+        float logsum = 0.f;
+        for (int i = 0; i < N; ++i) logsum += rowc[i * 4 + 2];
         const float reg = logsum / (float)N * p.T / 2.f;
         p.reg[0] = reg;
         p.loss[0] = -(act_sum * p.inv_mei_act) / (float)N + g_reg * reg;
     }
-    __syncthreads();
     for (int pr = t; pr < N * N; pr += NT) {
         const int i = pr / N;
         Sm[pr] = (posS[pr] * rowc[i * 4] - negS[pr] * rowc[i * 4 + 1]) * Sm[pr] / p.T;  // Gamma_ij = A_ij S_ij / T
     }
     __syncthreads();
-    for (int i = t; i < N; i += NT) {
+    for (int i = warp; i < N; i += NW) {
         float kap = 0.f;
-        for (int j = 0; j < N; ++j) kap = fmaf(Sm[i * N + j] + Sm[j * N + i], cosm[i * N + j], kap);
-        rowc[i * 4 + 3] = kap;
+        for (int j = lane; j < N; j += 32) kap = fmaf(Sm[i * N + j] + Sm[j * N + i], cosm[i * N + j], kap);
+        kap = warp_sum(kap);
+        if (lane == 0) rowc[i * 4 + 3] = kap;
     }
     __syncthreads();
     for (int pr = t; pr < N * N; pr += NT) {
-        const int i = pr / N, j = pr % N;
+        const int i = pr / N, j = pr - i * N;
         float k = (Sm[i * N + j] + Sm[j * N + i]) / (rho[i] * rho[j]);
         if (i == j) k -= rowc[i * 4 + 3] / (rho[i] * rho[i]);
         Ks[pr] = k;
@@ -358,31 +385,41 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     }
     __syncthreads();
 
+    stamp(p, 7);
     // ---- phase 3: g_z = response backward + contrastive backward; gradient wrt the pre-clamp image; per-image sums for the projection
 #pragma unroll 1
-    for (int r = warp; r < NC; r += NW) {
-        const int n = r / C, c = r % C;
-        const float sdn = sd[n] + p.eps_con, mun = p.mode == LMR_CONSTRAIN_NORM ? p.mean : mu[n];
-        const float cf = coef[n];
-        const float* wsel = ws + amax[n] * PSP;
-        float a0 = 0.f, a1 = 0.f;
-        for (int e = lane; e < PS; e += 32) {
-            float v = 0.f;
-            if (e < np) {
-                const float m = mk[e];
-                float acc = 0.f;
-#pragma unroll 4
-                for (int jn = 0; jn < N; ++jn) acc = fmaf(Ks[n * N + jn], xm[(jn * C + c) * PSP + e], acc);
-                const float gz = cf * wsel[e] + g_reg * (p.g1 * m * p.g2) * acc;
-                const float u = xs[r * PSP + e] - mun;
-                float y;
-                if (p.mode == LMR_CONSTRAIN_NORM) y = u / sdn * p.target + p.mean;
-                else y = p.target * u / sdn + p.mean;
-                v = gz * clamp_pass(y, p.has_min, p.pmin, p.has_max, p.pmax);
-                a0 += v;
-                a1 = fmaf(v, u, a1);
+    for (int i = t; i < NC * PS; i += NT) {
+        const int r = i / PS, e = i - r * PS, n = r / C, c = r - n * C;
+        float v = 0.f;
+        if (e < np) {
+            const float sdn = sd[n] + p.eps_con, mun = p.mode == LMR_CONSTRAIN_NORM ? p.mean : mu[n];
+            const float* kr = Ks + n * N;
+            const float* xc = xm + c * PSP + e;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int jn = 0;
+            for (; jn + 3 < N; jn += 4) {
+                a0 = fmaf(kr[jn], xc[(jn * C) * PSP], a0), a1 = fmaf(kr[jn + 1], xc[((jn + 1) * C) * PSP], a1);
+                a2 = fmaf(kr[jn + 2], xc[((jn + 2) * C) * PSP], a2), a3 = fmaf(kr[jn + 3], xc[((jn + 3) * C) * PSP], a3);
             }
-            gy[r * PSP + e] = v;
+            for (; jn < N; ++jn) a0 = fmaf(kr[jn], xc[(jn * C) * PSP], a0);
+            const float acc = (a0 + a1) + (a2 + a3);
+            const float gz = coef[n] * ws[amax[n] * PSP + e] + g_reg * (p.g1 * mk[e] * p.g2) * acc;
+            const float u = xs[r * PSP + e] - mun;
+            float y;
+            if (p.mode == LMR_CONSTRAIN_NORM) y = u / sdn * p.target + p.mean;
+            else y = p.target * u / sdn + p.mean;
+            v = gz * clamp_pass(y, p.has_min, p.pmin, p.has_max, p.pmax);
+        }
+        gy[r * PSP + e] = v;
+    }
+    __syncthreads();
+    for (int r = warp; r < NC; r += NW) {
+        const float mun = p.mode == LMR_CONSTRAIN_NORM ? p.mean : mu[r / C];
+        float a0 = 0.f, a1 = 0.f;
+        for (int e = lane; e < np; e += 32) {
+            const float v = gy[r * PSP + e];
+            a0 += v;
+            a1 = fmaf(v, xs[r * PSP + e] - mun, a1);
         }
         a0 = warp_sum(a0), a1 = warp_sum(a1);
         if (lane == 0) dotu[2 * r] = a0, dotu[2 * r + 1] = a1;  // per (image, channel) row; combined over channels below
@@ -393,7 +430,9 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
         for (int c = 0; c < C; ++c) a0 += dotu[2 * (n * C + c)], a1 += dotu[2 * (n * C + c) + 1];
         p.part_c[(size_t)b * 2 * N + n] = a0, p.part_c[(size_t)b * 2 * N + N + n] = a1;
     }
+    stamp(p, 8);
     barrier();
+    stamp(p, 9);
     for (int n = t / GRP; n < 2 * N; n += NT / GRP) {  // part_c rows are [a0[0..N) | a1[0..N)]
         const float tot = group_strided_sum(p.part_c + n, G, 2 * N, lane);
         if ((lane & (GRP - 1)) == 0) dotn[n < N ? 2 * n : 2 * (n - N) + 1] = tot;
@@ -401,17 +440,18 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     __syncthreads();
     // ---- phase 4: g_x   NORM: k gy - target dot / ((s+eps)^2 s) u ;  STD: k (gy - mean(gy)) - target dot / ((sd+eps)^2 (n-1) sd) (x-mu)
 #pragma unroll 1
-    for (int r = warp; r < NC; r += NW) {
-        const int n = r / C;
+    for (int i = t; i < NC * PS; i += NT) {
+        const int r = i / PS, e = i - r * PS, n = r / C;
+        if (e >= np) continue;
         const float s_ = sd[n];
         const float k = p.target / (s_ + p.eps_con);
         const float denom = (s_ + p.eps_con) * (s_ + p.eps_con) * s_ * (p.mode == LMR_CONSTRAIN_NORM ? 1.f : (float)(C * HW - 1));
         const float c2 = p.target * dotn[2 * n + 1] / denom;
         const float gmean = p.mode == LMR_CONSTRAIN_NORM ? 0.f : dotn[2 * n] / (float)(C * HW);
         const float mun = p.mode == LMR_CONSTRAIN_NORM ? p.mean : mu[n];
-        float* dst = p.g_x + (size_t)r * HW + p0;
-        for (int e = lane; e < np; e += 32) dst[e] = k * (gy[r * PSP + e] - gmean) - c2 * (xs[r * PSP + e] - mun);
+        p.g_x[(size_t)r * HW + p0 + e] = k * (gy[r * PSP + e] - gmean) - c2 * (xs[r * PSP + e] - mun);
     }
+    stamp(p, 10);
     // the epoch word is only written here, after every CTA has passed the last barrier (all of them read it at kernel start)
     if (b == 0 && t == 0) {
         __threadfence();
@@ -492,6 +532,13 @@ extern "C" int lmr_learn_objective(int mode, const float* x, int N, int C, int H
     p.part_a = reinterpret_cast<float*>(base + pl.off_a), p.part_b = reinterpret_cast<float*>(base + pl.off_b);
     p.fin = reinterpret_cast<float*>(base + pl.off_fin), p.part_c = reinterpret_cast<float*>(base + pl.off_c);
     p.PS = pl.PS;
+    static const bool tracing = getenv("LMR_OBJ_TRACE") != nullptr;
+    static long long* trace_dev = nullptr;
+    p.trace = nullptr;
+    if (tracing) {
+        if (trace_dev == nullptr) cudaMalloc(&trace_dev, 16 * sizeof(long long));
+        p.trace = trace_dev;
+    }
     static size_t cache = 0;
     if (pl.smem > cache) {
         LMR_CUDA_OK(cudaFuncSetAttribute(lobj::learn_objective_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
@@ -504,5 +551,12 @@ extern "C" int lmr_learn_objective(int mode, const float* x, int N, int C, int H
     attr[0].val.cooperative = 1;  // guarantees that all CTAs are co-resident (the software grid barrier needs it)
     cfg.attrs = attr, cfg.numAttrs = 1;
     LMR_CUDA_OK(cudaLaunchKernelEx(&cfg, lobj::learn_objective_kernel, p));
+    if (tracing) {  // debug only: synchronises and prints CTA 0's phase time line
+        long long h[16];
+        cudaStreamSynchronize(cfg.stream);
+        cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[obj trace] ns since entry: loaded %lld | stats+bar1 %lld | phase1 done %lld | bar2 %lld | combine %lld | bar3 %lld | finalize %lld | phase3 %lld | bar4 %lld | end %lld\n",
+                h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0], h[9] - h[0], h[10] - h[0]);
+    }
     return 0;
 }
