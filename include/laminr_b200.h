@@ -264,6 +264,17 @@ int lmr_create_mask(const float* mei, int G, int H, int W, float zscore_thresh, 
                     const double* blur_weights, int blur_radius, float* mask_out, unsigned* stats, void* workspace,
                     size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Gaussian blur -- replaces featurevis.ops.GaussianBlur (featurevis/ops.py:378-423), the gradient preconditioner
+ * behind get_mei_dict(gb=) (laminr/utils/mei.py:44-45) and learn(gaussian_blur_sigma=) (inv_temp_learn_match.py:158):
+ * F.pad(pad_mode) + depthwise correlation along y with wy, then along x with wx, result scaled by inv_norm.
+ * x, out: [B, H, W] float32 planes (B = batch * channels).  wy: [2 hy + 1], wx: [2 hx + 1] float32 windows
+ * (exp(-0.5 (k / sigma)^2), h = max(round(sigma * truncate), 1)); inv_norm = 1 / (sum(wy) * sum(wx)).
+ * pad_mode: 0 constant (zeros), 1 reflect (torch semantics, needs h < size), 2 replicate.  workspace: B*H*W floats.
+ * ---------------------------------------------------------------------------------------------------------- */
+int lmr_gaussian_blur(const float* x, int B, int H, int W, const float* wy, int hy, const float* wx, int hx,
+                      int pad_mode, float inv_norm, float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

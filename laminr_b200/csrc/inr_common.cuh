@@ -29,11 +29,11 @@ struct Tiling {
     int N, P, D, NC, TP, tilesP, nChunks, numTiles;
 };
 
-static inline Tiling make_tiling(int N, int P, int D, int tp_cap) {
+static inline Tiling make_tiling(int N, int P, int D, int tp_cap, int rows = TR_MAX) {
     Tiling t;
     t.N = N, t.P = P, t.D = D;
-    t.NC = N < TR_MAX ? N : TR_MAX;
-    t.TP = TR_MAX / t.NC;
+    t.NC = N < rows ? N : rows;
+    t.TP = rows / t.NC;
     if (t.TP > tp_cap) t.TP = tp_cap;
     if (t.TP > P) t.TP = P;
     t.tilesP = (P + t.TP - 1) / t.TP;
@@ -73,6 +73,7 @@ struct Args {
     float* dAred;     // [N, HP]  sum over CTAs of the dA partials
     int want_weights, want_affine;
     long long* trace;  // debug: per-event clock64 stamps of CTA 0 (LMR_TC_TRACE=1), else null
+    int stagger;       // two-stream backward: cycles by which stream 1 starts behind stream 0
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -658,7 +659,7 @@ static inline WsLayout ws_layout(const Net& nt, const Tiling& tl, bool bwd, bool
     w.G0 = w.partials = w.l0part = w.affpart = w.dAred = 0;
     if (bwd) {
         w.G0 = take((size_t)tl.D * tl.P * HP);
-        w.partials = take((size_t)w.gridMain * partial_size(nt, tl, HP));
+        w.partials = take((size_t)2 * w.gridMain * partial_size(nt, tl, HP));  // the two-stream tensor-core backward writes one partial per stream
         w.l0part = take((size_t)w.gridL0 * nt.hid * 2 * nt.pe);
         w.affpart = take((size_t)tl.D * tl.tilesP * 6);
         w.dAred = take((size_t)tl.N * HP);
@@ -708,6 +709,7 @@ static inline int fill_args(Args& a, const Net& nt, const Tiling& tl, const floa
     a.affpart = reinterpret_cast<float*>(base + wl.affpart);
     a.img = nullptr, a.g_img = nullptr, a.want_weights = 0, a.want_affine = 0;
     a.trace = nullptr;
+    a.stagger = 0;
     return 0;
 }
 

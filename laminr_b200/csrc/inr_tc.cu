@@ -190,7 +190,8 @@ struct TcSmem {
 
 // weights of hidden layers 1..LH-1 as split-bf16 K-major tiles: W_l[o][k] for k < 50, column 50 = bias b_l[o],
 // entry [50][50] = ONE_SEED (regenerates the constant-1 feature), rest 0.  Also the fp32 output layer.
-__device__ inline void load_weight_tiles(const Args& a, TcSmem& s) {
+template <class SmemT>
+__device__ inline void load_weight_tiles(const Args& a, SmemT& s) {
     const Net& nt = a.net;
     // the split-bf16 tile images were built once by the prep kernel: a straight 16-byte copy, every chunk in flight at once
     for (int i = threadIdx.x; i < (LH - 1) * WT_BYTES / 16; i += blockDim.x) cp_async16(s.wt + 16 * i, a.wtimg + 16 * i);
@@ -308,6 +309,22 @@ template <bool FAST>
 __device__ __forceinline__ void tanh_end(float2* x) {
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
+        if (FAST) x[p] = make_float2(tanh_mufu(x[p].x), tanh_mufu(x[p].y));
+        else x[p] = fma2(make_float2(-2.f, -2.f), rcp_fma2(x[p]), make_float2(1.f, 1.f));
+    }
+}
+
+template <bool FAST, int NP>
+__device__ __forceinline__ void tanh_begin_n(float2* x) {
+    if (!FAST) {
+#pragma unroll
+        for (int p = 0; p < NP; ++p) x[p] = exp2x_plus1(x[p]);
+    }
+}
+template <bool FAST, int NP>
+__device__ __forceinline__ void tanh_end_n(float2* x) {
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
         if (FAST) x[p] = make_float2(tanh_mufu(x[p].x), tanh_mufu(x[p].y));
         else x[p] = fma2(make_float2(-2.f, -2.f), rcp_fma2(x[p]), make_float2(1.f, 1.f));
     }
@@ -683,13 +700,16 @@ __global__ void __launch_bounds__(NT_T, 4) inr_fwd_ts_kernel(Args a) {
 // ---------------------------------------------------------------------------------------------------------------
 // tile buffer roles; buffer of role r in iteration `it` = (r + 2 it) % 5: the rotation makes every reuse hazard-free by commit ordering
 constexpr int ROLE_H1 = 0, ROLE_DA = 3, ROLE_DB = 4;
-constexpr int NG_B = 4, NE_B = 128 * NG_B, NT_B = NE_B + 32;
+// NG = 4 column groups: two chunks = 16 values per thread and step, 16 epilogue warps.  (Measured alternative, removed: 7 groups = one chunk
+// per thread, 28 epilogue warps at 64 registers: 153 us instead of 124 us for the 100x100 learn step -- the per-thread fixed costs of a step
+// (accumulator wait, TMEM load, proxy fence, barrier arrive) do not shrink with the chunk count.)
+constexpr int NG_B = 4;
 constexpr int MAX_DA = 4;   // dA[n][o] accumulators per epilogue thread: N * 50 <= 4 * 512  (N <= 40)
 constexpr int STG = 53;     // row stride (floats) of the fp32 staging panel stage[row][o] of dz_0 (odd: conflict-free both ways)
 
-template <bool FAST, int C>
-__global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
-    constexpr int NG = NG_B, NE = NE_B, NCH = 8 / NG;
+template <bool FAST, int C, int NG>
+__global__ void __launch_bounds__(128 * NG + 32, 1) inr_bwd_tc_kernel(Args a) {
+    constexpr int NE = 128 * NG, NT_B = NE + 32, NCH = 8 / NG;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const Net& nt = a.net;
     const Tiling& tl = a.tl;
@@ -1049,6 +1069,549 @@ __global__ void __launch_bounds__(NT_B, 1) inr_bwd_tc_kernel(Args a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// backward, TWO tile streams per CTA.  The single-stream kernel above is a serial chain per tile (epilogue -> MMA -> epilogue ...): the
+// epilogue warps idle ~30 % of the time waiting for accumulators and the tensor pipe idles while they work.  Shared memory (5 operand tiles
+// per tile in flight) rules out a second 128-row tile, so here a tile has 64 rows (M = 64 MMAs, 16 KB operand tiles) and the CTA runs two
+// independent streams, each with 8 epilogue warps + its own MMA-issuing warp, barriers, five rotating tiles and weight-gradient accumulators;
+// while one stream waits for the tensor pipe the other one computes.
+//   * M = 64, cta_group::1: row m of D sits in TMEM lane 32 (m / 16) + m % 16, i.e. 16 lanes of every 32-lane subpartition.  Stream s puts its
+//     accumulators at lane offset 16 s: both streams share the same 2 x 64 ping-pong columns.
+//   * epilogue thread mapping: tcgen05.ld.16x256b (16 lanes x 8 columns -> 32 threads): thread (r8 = lane / 4, t4 = lane % 4) of the warp in
+//     subpartition q and column group cg holds rows 16 q + r8 and 16 q + r8 + 8, features 8 c + 2 t4 + {0, 1} of the chunks c = cg, cg + 2,
+//     cg + 4, cg + 6 (16 values per step, like the 128-row kernel); operand stores are 4-byte (a warp writes one full 128-byte core matrix).
+//   * weight gradient: TWO M128 x N64 x K16 MMAs per 16 rows, [dz_hi | dz_lo]^T h_hi and [dz_hi | dz_lo]^T h_lo into the SAME 64 columns:
+//     lanes 0..63 accumulate hi*hi + hi*lo, lanes 64..127 lo*hi + lo*lo; dW = the sum of the two halves.  64 TMEM columns per layer instead
+//     of 128, so that two streams fit: 128 (accumulators) + 2 x 3 x 64 = 512 columns.
+// ---------------------------------------------------------------------------------------------------------------
+namespace b2 {
+constexpr int R = 64;                        // rows per tile
+constexpr int THALF = R * HPAD * 2;          // bytes of the hi (or lo) half of an operand tile: 8 KB
+constexpr int TBYTES = 2 * THALF;            // 16 KB
+constexpr int NS = 2;                        // tile streams per CTA
+constexpr int NE = 256;                      // epilogue threads per stream (8 warps: 4 subpartitions x 2 column groups)
+constexpr int NT = NS * NE + NS * 32;        // + one MMA-issuing warp per stream
+constexpr uint32_t TM_ACC2 = 0;              // 2 x 64 columns (ping-pong), shared by the streams (lane offset 16 s)
+constexpr uint32_t TM_DW2 = 128;             // + 192 s + 64 (l - 1)
+constexpr int BPS = 8;                       // mbarriers per stream (BAR_K 0..3, BAR_ACC 4..5, BAR_DONE 6)
+constexpr int MAX_DA2 = 8;                   // dA[n][o] accumulators per epilogue thread: N * 50 <= 8 * 256  (N <= 40)
+constexpr int STG2 = 53;                     // row stride (floats) of the fp32 dz_0 panel
+constexpr int RS2 = 65;                      // row stride of the drain panel red[128][65]
+
+struct Smem {
+    uint8_t* tiles;   // NS x NBUF_BWD x TBYTES
+    uint8_t* wt;      // (LH-1) x WT_BYTES
+    float *Cps, *Wout, *bout, *scratch, *As;   // Cps: [NS][2][TP][SHS]; scratch: [NS][2][R][C] partial output-layer dot products
+    uint64_t* bars;   // NS x BPS
+    uint32_t* tmem;
+    size_t bytes;
+    __host__ __device__ Smem(uint8_t* base, const Net& nt, const Tiling& tl) {
+        uint8_t* p = base;
+        auto take = [&](size_t n) {
+            uint8_t* r = p;
+            p += (n + 127) / 128 * 128;
+            return r;
+        };
+        tiles = take((size_t)NS * NBUF_BWD * TBYTES);
+        wt = take((size_t)(LH - 1) * WT_BYTES);
+        Cps = reinterpret_cast<float*>(take((size_t)NS * 2 * tl.TP * 56 * 4));
+        Wout = reinterpret_cast<float*>(take((size_t)nt.C * HPAD * 4));
+        bout = reinterpret_cast<float*>(take(16));
+        scratch = reinterpret_cast<float*>(take((size_t)NS * 2 * R * nt.C * 4));
+        bars = reinterpret_cast<uint64_t*>(take(NS * BPS * 8));
+        tmem = reinterpret_cast<uint32_t*>(take(16));
+        As = reinterpret_cast<float*>(take((size_t)tl.NC * 56 * 4));
+        bytes = p - base;
+    }
+};
+
+__device__ __forceinline__ void tmem_ld_16x256b(uint32_t taddr, float* v) {  // 16 lanes x 8 columns: (row lane/4: v0 v1) (row lane/4 + 8: v2 v3), columns 2 (lane%4) + {0,1}
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+
+struct StageDesc2 {
+    uint64_t ah, bh, b_step;
+    uint32_t idesc;
+};
+__device__ __forceinline__ StageDesc2 make_stage2(uint32_t a_addr, uint32_t w_addr, int b_transposed) {
+    StageDesc2 d;
+    d.idesc = instr_desc(FMT_BF16, R, HPAD, 0, b_transposed);
+    d.ah = smem_desc(a_addr, R * 16, 128);
+    d.bh = b_transposed ? smem_desc(w_addr, 128, HPAD * 16) : smem_desc(w_addr, HPAD * 16, 128);
+    d.b_step = (b_transposed ? 256 : 2 * HPAD * 16) >> 4;
+    return d;
+}
+__device__ __forceinline__ void issue_kstep2(uint32_t tmem_d, const StageDesc2& d, int kc) {
+    const uint64_t ah = d.ah + (uint64_t)kc * ((2 * R * 16) >> 4), bh = d.bh + (uint64_t)kc * d.b_step;
+    mma_f16(tmem_d, ah, bh, d.idesc, kc > 0);
+    mma_f16(tmem_d, ah + (THALF >> 4), bh, d.idesc, 1);
+    mma_f16(tmem_d, ah, bh + (WT_HALF >> 4), d.idesc, 1);
+}
+// D[128 x 64] (+)= [X_hi | X_lo]^T . (Y_hi, then Y_lo) over the 64 rows: tiles read MN-major, 4 x 2 MMAs of 16 rows
+__device__ __forceinline__ void issue_wgrad2(uint32_t tmem_d, uint32_t x_addr, uint32_t y_addr, bool zero_first) {
+    const uint32_t idesc = instr_desc(FMT_BF16, 128, HPAD, 1, 1);
+    uint64_t xd = smem_desc(x_addr, 128, R * 16), yh = smem_desc(y_addr, 128, R * 16), yl = smem_desc(y_addr + THALF, 128, R * 16);
+#pragma unroll
+    for (int ks = 0; ks < R / 16; ++ks) {
+        mma_f16(tmem_d, xd, yh, idesc, (ks > 0 || !zero_first) ? 1u : 0u);
+        mma_f16(tmem_d, xd, yl, idesc, 1u);
+        xd += 256 >> 4, yh += 256 >> 4, yl += 256 >> 4;
+    }
+}
+
+struct Ctx {
+    int lane, q, cg, r8, t4, r0, r1, et;   // subpartition, column group, row-in-8, pair-in-chunk, the two tile rows, thread index within the stream
+    uint32_t lane_taddr;                   // (32 q + 16 s) << 16
+};
+
+// split a pair into bf16 hi / lo words and store them at (row r, chunk c, pair t4)
+__device__ __forceinline__ void store_pair(uint8_t* tile, int r, int c, int t4, float2 v) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v.x, v.y);
+    const uint32_t hw = *reinterpret_cast<const uint32_t*>(&h2);
+    const float2 hf = make_float2(__uint_as_float(hw << 16), __uint_as_float(hw & 0xffff0000u));
+    const float2 d = fma2(hf, make_float2(-1.f, -1.f), v);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(d.x, d.y);
+    const uint32_t off = tile_off(r, c, R) + 4 * t4;
+    *reinterpret_cast<uint32_t*>(tile + off) = hw;
+    *reinterpret_cast<uint32_t*>(tile + THALF + off) = *reinterpret_cast<const uint32_t*>(&l2);
+}
+__device__ __forceinline__ float2 load_pair(const uint8_t* tile, int r, int c, int t4) {
+    const uint32_t off = tile_off(r, c, R) + 4 * t4;
+    const uint32_t h = *reinterpret_cast<const uint32_t*>(tile + off), l = *reinterpret_cast<const uint32_t*>(tile + THALF + off);
+    return add2(make_float2(__uint_as_float(h << 16), __uint_as_float(h & 0xffff0000u)), make_float2(__uint_as_float(l << 16), __uint_as_float(l & 0xffff0000u)));
+}
+// v[2 i + h]: pair of row h, chunk cg + 2 i.  Stores the 4 chunks in two half-steps (chunks cg, cg + 2 -> k-chunks 0, 1; then cg + 4, cg + 6 -> 2, 3);
+// chunk 7 (cg == 1, i == 3) is the all-zero padding chunk
+template <bool TANH, bool FAST>
+__device__ __forceinline__ void store_step(float2* v, uint8_t* dst, const Ctx& cx, uint64_t* kbar, bool act0, bool act1) {
+    if (TANH) tanh_begin<FAST>(v);
+#pragma unroll
+    for (int hs = 0; hs < 2; ++hs) {
+        if (TANH && hs == 0) tanh_begin<FAST>(v + 4);
+        if (TANH) tanh_end<FAST>(v + 4 * hs);
+#pragma unroll
+        for (int ii = 0; ii < 2; ++ii) {
+            const int i = 2 * hs + ii, c = cx.cg + 2 * i;
+            if (c < 7) {
+                store_pair(dst, cx.r0, c, cx.t4, act0 ? v[2 * i] : make_float2(0.f, 0.f));
+                store_pair(dst, cx.r1, c, cx.t4, act1 ? v[2 * i + 1] : make_float2(0.f, 0.f));
+            } else {
+                const uint32_t o0 = tile_off(cx.r0, c, R) + 4 * cx.t4, o1 = tile_off(cx.r1, c, R) + 4 * cx.t4;
+                *reinterpret_cast<uint32_t*>(dst + o0) = 0u, *reinterpret_cast<uint32_t*>(dst + THALF + o0) = 0u;
+                *reinterpret_cast<uint32_t*>(dst + o1) = 0u, *reinterpret_cast<uint32_t*>(dst + THALF + o1) = 0u;
+            }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (cx.lane == 0) mbar_arrive(kbar + 2 * hs), mbar_arrive(kbar + 2 * hs + 1);
+    }
+}
+// this thread's accumulator values: v[2 i + h] = pair of row h, chunk cg + 2 i  (chunk 7 is never read)
+__device__ __forceinline__ void load_acc2(uint32_t acc, int cg, float* vf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = cg + 2 * i;
+        if (c < 7) tmem_ld_16x256b(acc + 8 * c, vf + 4 * i);
+    }
+    tmem_ld_wait();
+    fence_before_sync();
+}
+}  // namespace b2
+
+template <bool FAST, int C>
+__global__ void __launch_bounds__(b2::NT, 1) inr_bwd2_kernel(Args a) {
+    using namespace b2;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const Net& nt = a.net;
+    const Tiling& tl = a.tl;  // 64-row tiling
+    Smem s(smem_raw, nt, tl);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const bool want_w = a.want_weights != 0;
+    const int TP = tl.TP;
+    if (t == 0) LMR_TRACE(0, 500);
+    load_weight_tiles(a, s);
+    for (int i = t; i < NS * 2 * TP * SHS; i += NT) s.Cps[i] = 0.f;
+    for (int i = t; i < tl.NC * SHS; i += NT) {
+        const int n = i / SHS, k = i % SHS;
+        s.As[i] = k < SHP ? a.Avec[(size_t)n * SHP + k] : 0.f;
+    }
+    if (warp == NS * NE / 32) tmem_alloc(s.tmem, 512);
+    if (t == 0) {
+        for (int st = 0; st < NS; ++st) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mbar_init(&s.bars[st * BPS + BAR_K + k], NE / 32);
+            mbar_init(&s.bars[st * BPS + BAR_ACC], 1), mbar_init(&s.bars[st * BPS + BAR_ACC + 1], 1), mbar_init(&s.bars[st * BPS + BAR_DONE], 1);
+        }
+        mbar_fence_init();
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = *s.tmem;
+    const int sidx = warp >= NS * NE / 32 ? warp - NS * NE / 32 : warp / (NE / 32);  // stream of this warp
+    uint64_t* bars = s.bars + sidx * BPS;
+    uint8_t* tiles = s.tiles + (size_t)sidx * NBUF_BWD * TBYTES;
+    const int first = (int)blockIdx.x * NS + sidx, stride = (int)gridDim.x * NS;
+    const int myTiles = first < tl.numTiles ? (tl.numTiles - first + stride - 1) / stride : 0;
+    const uint32_t acc_base = tm + TM_ACC2 + ((uint32_t)(16 * sidx) << 16);
+    const uint32_t dw_base = tm + TM_DW2 + (uint32_t)sidx * 192;
+
+    if (warp >= NS * NE / 32) {
+        if (lane == 0) {  // ---- MMA issuer of stream sidx
+            const uint32_t tiles_addr = smem_u32(tiles), w_addr = smem_u32(s.wt);
+            uint32_t pk = 0;
+            for (int it = 0; it < myTiles; ++it) {
+                const int rot = (2 * it) % NBUF_BWD;
+                auto buf = [&](int role) { return tiles_addr + (uint32_t)((role + rot) % NBUF_BWD) * TBYTES; };
+                int st = 0;
+#pragma unroll 1
+                for (int l = 1; l < LH; ++l, ++st) {  // forward recompute: z_{l+1} = h_l W_l^T
+                    const uint32_t acc = acc_base + (uint32_t)(st & 1) * 64;
+                    const StageDesc2 sd = make_stage2(buf(ROLE_H1 + l - 1), w_addr + (uint32_t)(l - 1) * WT_BYTES, 0);
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) {
+                        mbar_wait(&bars[BAR_K + kc], pk);
+                        fence_after_sync();
+                        issue_kstep2(acc, sd, kc);
+                    }
+                    pk ^= 1;
+                    mma_commit(&bars[BAR_ACC + (st & 1)]);
+                }
+#pragma unroll 1
+                for (int l = LH - 1; l >= 1; --l, ++st) {  // dh_l = dz_l W_l, then dW_l += dz_l^T h_l behind it
+                    const uint32_t acc = acc_base + (uint32_t)(st & 1) * 64;
+                    const uint32_t dz = buf(((LH - 1 - l) & 1) ? ROLE_DB : ROLE_DA);
+                    const StageDesc2 sd = make_stage2(dz, w_addr + (uint32_t)(l - 1) * WT_BYTES, 1);
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) {
+                        mbar_wait(&bars[BAR_K + kc], pk);
+                        fence_after_sync();
+                        issue_kstep2(acc, sd, kc);
+                    }
+                    pk ^= 1;
+                    mma_commit(&bars[BAR_ACC + (st & 1)]);
+                    if (want_w) issue_wgrad2(dw_base + (uint32_t)(l - 1) * 64, dz, buf(ROLE_H1 + l - 1), it == 0);
+                }
+            }
+            mma_commit(&bars[BAR_DONE]);
+        }
+    } else {  // ---- epilogue threads of stream sidx
+        Ctx cx;
+        {
+            const int w = warp & (NE / 32 - 1);
+            cx.lane = lane, cx.q = w & 3, cx.cg = w >> 2, cx.r8 = lane >> 2, cx.t4 = lane & 3;
+            cx.r0 = 16 * cx.q + cx.r8, cx.r1 = cx.r0 + 8;
+            cx.et = t - sidx * NE;
+            cx.lane_taddr = (uint32_t)(32 * cx.q) << 16;
+        }
+        const int et = cx.et, bar_id = 1 + sidx;
+        float* Cps_s = s.Cps + (size_t)sidx * 2 * TP * SHS;
+        float* scr = s.scratch + (size_t)sidx * 2 * R * C;
+        uint32_t pa0 = 0, pa1 = 0;
+        auto wait_acc = [&](int st) {
+            if (st & 1) {
+                mbar_wait(&bars[BAR_ACC + 1], pa1);
+                pa1 ^= 1;
+            } else {
+                mbar_wait(&bars[BAR_ACC], pa0);
+                pa0 ^= 1;
+            }
+            fence_after_sync();
+        };
+        auto stage_inputs = [&](const TileIdx& ti, float* slot) {
+            const float* src = a.Cpg + ((size_t)ti.d * tl.P + ti.p0) * SHP;
+            for (int i = et; i < ti.np * (SHP / 4); i += NE) {
+                const int jj = i / (SHP / 4), k4 = i % (SHP / 4);
+                cp_async16(slot + jj * SHS + 4 * k4, src + jj * SHP + 4 * k4);
+            }
+        };
+        const int nl0 = cx.r0 / TP, j0 = cx.r0 % TP, nl1 = cx.r1 / TP, j1 = cx.r1 % TP;
+        float dA[MAX_DA2];
+#pragma unroll
+        for (int q = 0; q < MAX_DA2; ++q) dA[q] = 0.f;
+        float wacc[C][8], bacc[C];  // running sums of dy_c h_4[k] over this thread's rows and tiles (k: its 8 features), and of dy_c
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            bacc[c] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) wacc[c][k] = 0.f;
+        }
+        // layer 0 of a finished tile, deferred into the next tile's first two accumulator waits (see the single-stream kernel)
+        auto reduce_g0 = [&](const TileIdx& tp, const float* stage) {
+            for (int e = et; e < tp.np * SHP; e += NE) {
+                const int jj = e / SHP, o = e % SHP;
+                float sum = 0.f;
+                if (o < HID) {
+                    const float* zr = stage + jj * STG2 + o;
+                    float s0 = 0.f, s1 = 0.f;
+                    int n = 0;
+                    for (; n + 1 < tp.nn; n += 2) s0 += zr[n * TP * STG2], s1 += zr[(n + 1) * TP * STG2];
+                    if (n < tp.nn) s0 += zr[n * TP * STG2];
+                    sum = s0 + s1;
+                }
+                a.G0[((size_t)tp.d * tl.P + tp.p0 + jj) * SHP + o] = sum;
+            }
+        };
+        auto reduce_dA = [&](const TileIdx& tp, const float* stage) {
+#pragma unroll
+            for (int q = 0; q < MAX_DA2; ++q) {
+                const int e = et + NE * q, n = e / HID, o = e % HID;
+                if (n < tp.nn) {
+                    const float* zr = stage + n * TP * STG2 + o;
+                    float sum = 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < TP_CAP_TC; ++jj)
+                        if (jj < tp.np) sum += zr[jj * STG2];
+                    dA[q] += sum;
+                }
+            }
+        };
+        TileIdx ti_prev = {0, 0, 0, 0, 0};
+        const float* stage_prev = nullptr;
+        if (myTiles > 0) stage_inputs(decode_tile(tl, first), Cps_s);
+        cp_async_commit();
+        if (sidx == 1 && a.stagger > 0) {  // start half a step out of phase: the streams do identical work and would otherwise compute and wait together
+            const long long t0 = clock64();
+            while (clock64() - t0 < a.stagger) {
+            }
+        }
+
+        for (int it = 0; it < myTiles; ++it) {
+            const TileIdx ti = decode_tile(tl, first + it * stride);
+            const int rot = (2 * it) % NBUF_BWD;
+            auto buf = [&](int role) { return tiles + (size_t)((role + rot) % NBUF_BWD) * TBYTES; };
+            cp_async_wait<0>();
+            named_bar_sync(bar_id, NE);  // staged Cp visible; the previous tile's dz_0 panel is complete
+            if (it + 1 < myTiles) stage_inputs(decode_tile(tl, first + (it + 1) * stride), Cps_s + ((it + 1) & 1) * TP * SHS);
+            cp_async_commit();
+            if (cx.et == 0) LMR_TRACE(sidx, it * 16 + 0);
+            const float* Cps = Cps_s + (it & 1) * TP * SHS;
+            const bool act0 = nl0 < ti.nn && j0 < ti.np, act1 = nl1 < ti.nn && j1 < ti.np;
+            float g[2][C];  // upstream gradient of the two rows
+            {
+                const size_t b0 = (((size_t)ti.d * tl.N + (ti.n0 + (act0 ? nl0 : 0))) * C) * tl.P + ti.p0 + (act0 ? j0 : 0);
+                const size_t b1 = (((size_t)ti.d * tl.N + (ti.n0 + (act1 ? nl1 : 0))) * C) * tl.P + ti.p0 + (act1 ? j1 : 0);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    g[0][c] = act0 ? __ldg(a.g_img + b0 + (size_t)c * tl.P) : 0.f;
+                    g[1][c] = act1 ? __ldg(a.g_img + b1 + (size_t)c * tl.P) : 0.f;
+                }
+            }
+            float2 v[8];
+            float* vf = reinterpret_cast<float*>(v);
+            // ---- forward recompute: h_1 (CUDA cores), h_2, h_3 (tensor cores) kept as tiles
+            {
+                const float* A0 = s.As + (act0 ? nl0 : 0) * SHS + 2 * cx.t4;
+                const float* A1 = s.As + (act1 ? nl1 : 0) * SHS + 2 * cx.t4;
+                const float* C0 = Cps + (act0 ? j0 : 0) * SHS + 2 * cx.t4;
+                const float* C1 = Cps + (act1 ? j1 : 0) * SHS + 2 * cx.t4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = cx.cg + 2 * i;
+                    if (c < 7) {
+                        v[2 * i] = add2(*reinterpret_cast<const float2*>(A0 + 8 * c), *reinterpret_cast<const float2*>(C0 + 8 * c));
+                        v[2 * i + 1] = add2(*reinterpret_cast<const float2*>(A1 + 8 * c), *reinterpret_cast<const float2*>(C1 + 8 * c));
+                    }
+                }
+            }
+            store_step<true, FAST>(v, buf(ROLE_H1), cx, &bars[BAR_K], act0, act1);
+            if (cx.et == 0) LMR_TRACE(sidx, it * 16 + 1);
+            if (it > 0) reduce_g0(ti_prev, stage_prev);  // while the tensor pipe computes z_2
+            int st = 0;
+#pragma unroll 1
+            for (int l = 1; l < LH - 1; ++l, ++st) {
+                if (l == 2 && it > 0 && want_w) reduce_dA(ti_prev, stage_prev);  // while the tensor pipe computes z_3
+                wait_acc(st);
+                if (cx.et == 0) LMR_TRACE(sidx, it * 16 + 2 + 2 * st);
+                load_acc2(acc_base + (uint32_t)(st & 1) * 64 + cx.lane_taddr, cx.cg, vf);
+                store_step<true, FAST>(v, buf(ROLE_H1 + l), cx, &bars[BAR_K], true, true);  // inactive rows: z == 0 => tanh == 0
+                if (cx.et == 0) LMR_TRACE(sidx, it * 16 + 3 + 2 * st);
+            }
+            // ---- last hidden layer + output layer (CUDA cores): h_4 in registers, y, dy = g (1 - y^2), dz_3 = (Wout^T dy)(1 - h_4^2) -> DA
+            {
+                wait_acc(st);
+                if (cx.et == 0) LMR_TRACE(sidx, it * 16 + 2 + 2 * st);
+                load_acc2(acc_base + (uint32_t)(st & 1) * 64 + cx.lane_taddr, cx.cg, vf);
+                float y[2][C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) y[0][c] = 0.f, y[1][c] = 0.f;
+                tanh_begin<FAST>(v);
+                if (cx.cg + 6 < 7) tanh_begin<FAST>(v + 4);
+                else tanh_begin_n<FAST, 2>(v + 4);
+                tanh_end<FAST>(v);
+                if (cx.cg + 6 < 7) tanh_end<FAST>(v + 4);
+                else tanh_end_n<FAST, 2>(v + 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ch = cx.cg + 2 * i;
+                    if (ch < 7) {
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const float2 w = *reinterpret_cast<const float2*>(s.Wout + c * HPAD + 8 * ch + 2 * cx.t4);
+                            y[0][c] = fmaf(v[2 * i].x, w.x, fmaf(v[2 * i].y, w.y, y[0][c]));
+                            y[1][c] = fmaf(v[2 * i + 1].x, w.x, fmaf(v[2 * i + 1].y, w.y, y[1][c]));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {  // the 4 lanes of a quad share the rows
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        y[h][c] += __shfl_xor_sync(0xffffffffu, y[h][c], 1);
+                        y[h][c] += __shfl_xor_sync(0xffffffffu, y[h][c], 2);
+                    }
+                    if (cx.t4 == 0) scr[(cx.cg * R + cx.r0) * C + c] = y[0][c], scr[(cx.cg * R + cx.r1) * C + c] = y[1][c];
+                }
+                named_bar_sync(3 + 4 * sidx + cx.q, 64);  // the two column-group warps of this subpartition exchange their partial dot products
+                float dy[2][C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = h ? cx.r1 : cx.r0;
+                        const float ys = scr[(0 * R + r) * C + c] + scr[(1 * R + r) * C + c];
+                        const float yy = act_tanh<FAST>(s.bout[c] + ys);
+                        dy[h][c] = g[h][c] * (1.f - yy * yy);
+                    }
+                    bacc[c] += dy[0][c] + dy[1][c];
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ch = cx.cg + 2 * i;
+                    if (ch < 7) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            float2 dh = make_float2(0.f, 0.f);
+                            const float2 hh = v[2 * i + h];
+#pragma unroll
+                            for (int c = 0; c < C; ++c) {
+                                const float2 d2 = make_float2(dy[h][c], dy[h][c]);
+                                if (want_w) {
+                                    const float2 wa = fma2(hh, d2, make_float2(wacc[c][2 * i], wacc[c][2 * i + 1]));
+                                    wacc[c][2 * i] = wa.x, wacc[c][2 * i + 1] = wa.y;
+                                }
+                                dh = fma2(*reinterpret_cast<const float2*>(s.Wout + c * HPAD + 8 * ch + 2 * cx.t4), d2, dh);
+                            }
+                            v[2 * i + h] = fma2(mul2(dh, mul2(hh, hh)), make_float2(-1.f, -1.f), dh);  // padding columns: Wout == 0; constant-1 column: 1 - 1 == 0
+                        }
+                    }
+                }
+                store_step<false, FAST>(v, buf(ROLE_DA), cx, &bars[BAR_K], true, true);
+                if (cx.et == 0) LMR_TRACE(sidx, it * 16 + 3 + 2 * st);
+                ++st;
+            }
+            // ---- layers 3, 2, 1: dz_{l-1} = dh_l (1 - h_l^2).  dz_2, dz_1 -> the other gradient tile; dz_0 -> fp32 panel stage[row][o] in h_2's
+            //      buffer (free by then, and not written again before the NEXT tile's dz_2: it outlives the deferred reductions)
+            float* stage = reinterpret_cast<float*>(buf(ROLE_H1 + 1));
+#pragma unroll 1
+            for (int l = LH - 1; l >= 1; --l, ++st) {
+                const uint8_t* Hl = buf(ROLE_H1 + l - 1);
+                float2 hv[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (cx.cg + 2 * i < 7) hv[2 * i] = load_pair(Hl, cx.r0, cx.cg + 2 * i, cx.t4), hv[2 * i + 1] = load_pair(Hl, cx.r1, cx.cg + 2 * i, cx.t4);
+                wait_acc(st);
+                if (cx.et == 0) LMR_TRACE(sidx, it * 16 + 2 + 2 * st);
+                load_acc2(acc_base + (uint32_t)(st & 1) * 64 + cx.lane_taddr, cx.cg, vf);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (cx.cg + 2 * i < 7) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) v[2 * i + h] = fma2(mul2(v[2 * i + h], mul2(hv[2 * i + h], hv[2 * i + h])), make_float2(-1.f, -1.f), v[2 * i + h]);
+                    }
+                if (l >= 2) {
+                    store_step<false, FAST>(v, buf(((LH - l) & 1) ? ROLE_DB : ROLE_DA), cx, &bars[BAR_K], true, true);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int o = 8 * (cx.cg + 2 * i) + 2 * cx.t4;
+                        if (o < STG2 - 1) {
+                            stage[cx.r0 * STG2 + o] = v[2 * i].x, stage[cx.r0 * STG2 + o + 1] = v[2 * i].y;
+                            stage[cx.r1 * STG2 + o] = v[2 * i + 1].x, stage[cx.r1 * STG2 + o + 1] = v[2 * i + 1].y;
+                        }
+                    }
+                }
+            }
+            if (cx.et == 0) LMR_TRACE(sidx, it * 16 + 14);
+            ti_prev = ti, stage_prev = stage;
+        }
+        if (cx.et == 0) LMR_TRACE(sidx, 501);
+        if (myTiles > 0) {  // the last tile's layer 0
+            named_bar_sync(bar_id, NE);
+            reduce_g0(ti_prev, stage_prev);
+            if (want_w) reduce_dA(ti_prev, stage_prev);
+        }
+        // ---- drain: wait for every MMA of the stream, read its weight-gradient accumulators out of TMEM, write the stream's partial
+        mbar_wait(&bars[BAR_DONE], 0);
+        fence_after_sync();
+        named_bar_sync(bar_id, NE);  // the drain reuses the tile buffers
+        if (cx.et == 0) LMR_TRACE(sidx, 502);
+        if (want_w) {
+            float* part = a.partials + (size_t)((int)blockIdx.x * NS + sidx) * partial_size(nt, tl, SHP);
+            float* p_dW = part;
+            float* p_db = part + (size_t)(LH - 1) * HID * HID;
+            float* p_dWout = p_db + (size_t)(LH - 1) * SHP;
+            float* p_dA = p_dWout + (size_t)C * SHP + 4;
+            float* red = reinterpret_cast<float*>(tiles);  // [128][RS2] fp32 (33 KB of the stream's 80 KB)
+#pragma unroll 1
+            for (int l = 1; l < LH; ++l) {
+                // D[m][k]: m = dz feature (hi 0..63 | lo 64..127), k = h feature; dW[o][k] = D[o][k] + D[64 + o][k]  (myTiles == 0: never written, skip)
+                const uint32_t dw = dw_base + (uint32_t)(l - 1) * 64 + cx.lane_taddr + 32 * cx.cg;
+                float x[32];
+                if (myTiles > 0) {
+                    tmem_ld8(dw, x), tmem_ld8(dw + 8, x + 8), tmem_ld8(dw + 16, x + 16), tmem_ld8(dw + 24, x + 24);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) x[k] = 0.f;
+                }
+                const int m = 32 * cx.q + lane;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) red[m * RS2 + 32 * cx.cg + k] = x[k];
+                named_bar_sync(bar_id, NE);
+                for (int i = et; i < HID * (HID + 1); i += NE) {
+                    const int o = i / (HID + 1), k = i % (HID + 1);
+                    const float val = red[o * RS2 + k] + red[(64 + o) * RS2 + k];
+                    if (k < HID) p_dW[(size_t)(l - 1) * HID * HID + o * HID + k] = val;
+                    else p_db[(l - 1) * SHP + o] = val;  // column ONE_COL: sum_r dz_l[r][o] * 1
+                }
+                named_bar_sync(bar_id, NE);
+            }
+            // output layer: sums over the 32 threads (q, r8) that share (cg, t4) of their running products   (red as [57][33]; row 56 = sum of dy)
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+                const int slot = 8 * cx.q + cx.r8;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int f = 8 * (cx.cg + 2 * i) + 2 * cx.t4;
+                    if (f < 56) red[f * 33 + slot] = wacc[c][2 * i], red[(f + 1) * 33 + slot] = wacc[c][2 * i + 1];
+                }
+                if (cx.cg == 0 && cx.t4 == 0) red[56 * 33 + slot] = bacc[c];
+                named_bar_sync(bar_id, NE);
+                if (et < 53) {
+                    const float* src = red + (et == 52 ? 56 : et) * 33;
+                    float s0 = 0.f, s1 = 0.f;
+                    for (int r = 0; r < 32; r += 2) s0 += src[r], s1 += src[r + 1];
+                    if (et < HID) p_dWout[c * SHP + et] = s0 + s1;
+                    else if (et == 52) p_dWout[C * SHP + c] = s0 + s1;
+                }
+                named_bar_sync(bar_id, NE);
+            }
+#pragma unroll
+            for (int q = 0; q < MAX_DA2; ++q) {
+                const int e = et + NE * q, n = e / HID, o = e % HID;
+                if (n < tl.NC) p_dA[n * SHP + o] = dA[q];
+            }
+        }
+        if (cx.et == 0) LMR_TRACE(sidx, 503);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == NS * NE / 32) tmem_dealloc(tm, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static int check_tc(const Net& nt) {
@@ -1163,21 +1726,65 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
         cudaMemsetAsync(trace_dev, 0, 1024 * sizeof(long long), st);
         a.trace = trace_dev;
     }
-    TcSmem s(nullptr, nt, tl, NBUF_BWD, false, NG_B);
-    const size_t smem = s.bytes + 1024;
-    LMR_CHECK_ARG(smem <= 227 * 1024, "inr_backward (tensor-core path): needs %zu bytes of shared memory (> 227 KB)", smem);
-    static size_t cache[2][5] = {};
     const bool fast = precision == LMR_PREC_BF16X3_FAST;
-#define LMR_BWD_CASE(FASTV, CV)                                                                          \
+    // development switch (LMR_BWD_MODE=2): the two-stream 64-row kernel instead of the one-stream 128-row kernel (measured: 133 us vs 124 us for the
+    // 100x100 learn step on B200; kept because its pieces -- lane-interleaved M = 64 accumulators, the 16x256b epilogue mapping, the
+    // 64-column weight-gradient accumulators -- are the starting point of the next restructuring, and covered by the GPU parity tests)
+    static const int mode = getenv("LMR_BWD_MODE") ? atoi(getenv("LMR_BWD_MODE")) : 4;
+    const bool single_stream = mode != 2;
+    int n_partials = wl.gridMain;
+    if (!single_stream) {
+        const Tiling tl2 = make_tiling(N, P, D, TP_CAP_TC, b2::R);
+        a.tl = tl2;  // the kernels behind this one only read N, P, D and NC (== the 128-row tiling's for N <= 40)
+        static const int stagger = getenv("LMR_B2_STAGGER") ? atoi(getenv("LMR_B2_STAGGER")) : 0;
+        a.stagger = stagger;
+        b2::Smem s2(nullptr, nt, tl2);
+        const size_t smem = s2.bytes + 1024;
+        LMR_CHECK_ARG(smem <= 227 * 1024, "inr_backward (tensor-core path): needs %zu bytes of shared memory (> 227 KB)", smem);
+        const int grid2 = (tl2.numTiles + b2::NS - 1) / b2::NS < num_sms() ? (tl2.numTiles + b2::NS - 1) / b2::NS : num_sms();
+        n_partials = b2::NS * grid2;
+        static size_t cache2[2][5] = {};
+#define LMR_BWD2_CASE(FASTV, CV)                                                                         \
     if (fast == FASTV && nt.C == CV) {                                                                   \
-        if (int rc = set_smem(inr_bwd_tc_kernel<FASTV, CV>, smem, &cache[FASTV][CV])) return rc;        \
-        inr_bwd_tc_kernel<FASTV, CV><<<wl.gridMain, NT_B, smem, st>>>(a);                                  \
+        if (int rc = set_smem(inr_bwd2_kernel<FASTV, CV>, smem, &cache2[FASTV][CV])) return rc;         \
+        inr_bwd2_kernel<FASTV, CV><<<grid2, b2::NT, smem, st>>>(a);                                      \
     }
-    LMR_BWD_CASE(false, 1) LMR_BWD_CASE(false, 2) LMR_BWD_CASE(false, 3) LMR_BWD_CASE(false, 4)
-    LMR_BWD_CASE(true, 1) LMR_BWD_CASE(true, 2) LMR_BWD_CASE(true, 3) LMR_BWD_CASE(true, 4)
+        LMR_BWD2_CASE(false, 1) LMR_BWD2_CASE(false, 2) LMR_BWD2_CASE(false, 3) LMR_BWD2_CASE(false, 4)
+        LMR_BWD2_CASE(true, 1) LMR_BWD2_CASE(true, 2) LMR_BWD2_CASE(true, 3) LMR_BWD2_CASE(true, 4)
+#undef LMR_BWD2_CASE
+        LMR_LAUNCH_OK();
+    } else {
+        TcSmem s(nullptr, nt, tl, NBUF_BWD, false, NG_B);
+        const size_t smem = s.bytes + 1024;
+        LMR_CHECK_ARG(smem <= 227 * 1024, "inr_backward (tensor-core path): needs %zu bytes of shared memory (> 227 KB)", smem);
+        static size_t cache[2][5] = {};
+#define LMR_BWD_CASE(FASTV, CV)                                                                                  \
+    if (fast == FASTV && nt.C == CV) {                                                                           \
+        if (int rc = set_smem(inr_bwd_tc_kernel<FASTV, CV, NG_B>, smem, &cache[FASTV][CV])) return rc;           \
+        inr_bwd_tc_kernel<FASTV, CV, NG_B><<<wl.gridMain, 128 * NG_B + 32, smem, st>>>(a);                        \
+    }
+        LMR_BWD_CASE(false, 1) LMR_BWD_CASE(false, 2) LMR_BWD_CASE(false, 3) LMR_BWD_CASE(false, 4)
+        LMR_BWD_CASE(true, 1) LMR_BWD_CASE(true, 2) LMR_BWD_CASE(true, 3) LMR_BWD_CASE(true, 4)
 #undef LMR_BWD_CASE
-    LMR_LAUNCH_OK();
-    if (tracing) {  // debug only: synchronises and prints CTA 0's pipeline time line (cycles relative to its first stamp)
+        LMR_LAUNCH_OK();
+    }
+    if (tracing && !single_stream) {  // debug only: synchronises and prints the time lines of CTA 0's two streams (epilogue thread 0 of each)
+        static long long h[1024];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        const long long t0 = h[500];
+        for (int sx = 0; sx < 2; ++sx) {
+            const long long* hs = h + 512 * sx;
+            fprintf(stderr, "[trace2] stream %d: tiles done %lld  MMAs done %lld  drain done %lld;  tile starts:", sx, hs[501] - t0, hs[502] - t0, hs[503] - t0);
+            for (int it = 0; it < 30 && hs[it * 16]; ++it) fprintf(stderr, " %lld", hs[it * 16] - t0);
+            fprintf(stderr, "\n");
+            for (int it = 2; it < 4; ++it) {
+                fprintf(stderr, "[trace2] stream %d tile %d:", sx, it);
+                for (int e = 0; e < 15; ++e) fprintf(stderr, " %lld", hs[it * 16 + e] ? hs[it * 16 + e] - t0 : -1);
+                fprintf(stderr, "\n");
+            }
+        }
+    } else if (tracing) {  // debug only: synchronises and prints CTA 0's pipeline time line (cycles relative to its first stamp)
         static long long h[1024];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
@@ -1198,7 +1805,7 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     if (a.want_weights) {
         float* l0part = reinterpret_cast<float*>(static_cast<char*>(ws) + wl.l0part);
         if (int rc = launch_l0_partial<50>(a, l0part, wl.gridL0, st)) return rc;
-        if (int rc = launch_finish_weights<50>(a, l0part, wl.gridMain, wl.gridL0, g_params, st)) return rc;
+        if (int rc = launch_finish_weights<50>(a, l0part, n_partials, wl.gridL0, g_params, st)) return rc;
     }
     if (want_aff) {  // the tile kernel wrote G0[d,p][o] = sum_n dz0: coordinate gradient and its moments pixel-parallel, then the 7 scalars per target
         int nblk = 0;

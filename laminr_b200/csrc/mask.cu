@@ -251,6 +251,31 @@ __global__ void __launch_bounds__(256) blur_axis_kernel(const TIn* __restrict__ 
     }
 }
 
+// ---- featurevis.ops.GaussianBlur (featurevis/ops.py:378-423): F.pad(mode) followed by a depthwise 1-D correlation per axis, float32.
+// One launch per axis; taps accumulate in window order (k = -h .. h) in float32 like a direct convolution.
+//   pad_mode 0: constant 0;  1: torch 'reflect' (mirror WITHOUT repeating the edge pixel: -1 -> 1, n -> n - 2);  2: 'replicate' (clamp)
+__global__ void __launch_bounds__(256) gblur_axis_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W, int axis, int h,
+                                                          const float* __restrict__ w, int pad_mode, float scale) {
+    const int HW = H * W;
+    const size_t base = (size_t)blockIdx.y * HW;
+    const int n = axis == 0 ? H : W;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const int r = i / W, c = i - r * W;
+        const int p = axis == 0 ? r : c;
+        float acc = 0.f;
+        for (int k = -h; k <= h; ++k) {
+            int q = p + k;
+            float v = 0.f;
+            bool inside = q >= 0 && q < n;
+            if (!inside && pad_mode == 1) q = q < 0 ? -q : 2 * n - 2 - q, inside = true;
+            if (!inside && pad_mode == 2) q = q < 0 ? 0 : n - 1, inside = true;
+            if (inside) v = in[base + (axis == 0 ? (size_t)q * W + c : (size_t)r * W + q)];
+            acc = fmaf(w[k + h], v, acc);
+        }
+        out[base + i] = acc * scale;
+    }
+}
+
 }  // namespace mask
 }  // namespace lmr
 
@@ -287,6 +312,27 @@ extern "C" int lmr_create_mask(const float* mei, int G, int H, int W, float zsco
     mask::blur_axis_kernel<unsigned char><<<grid, 256, 0, st>>>(hull, tmp, H, W, 0, blur_radius, blur_weights);
     LMR_LAUNCH_OK();
     mask::blur_axis_kernel<float><<<grid, 256, 0, st>>>(tmp, mask_out, H, W, 1, blur_radius, blur_weights);
+    LMR_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int lmr_gaussian_blur(const float* x, int B, int H, int W, const float* wy, int hy, const float* wx, int hx, int pad_mode, float inv_norm,
+                                 float* out, void* ws, size_t ws_bytes, void* stream) {
+    LMR_CHECK_ARG(x && wy && wx && out && ws, "gaussian_blur: null argument");
+    LMR_CHECK_ARG(B >= 1 && B <= 65535 && H >= 1 && W >= 1 && hy >= 0 && hx >= 0, "gaussian_blur: bad sizes B=%d H=%d W=%d hy=%d hx=%d", B, H, W, hy, hx);
+    LMR_CHECK_ARG(pad_mode >= 0 && pad_mode <= 2, "gaussian_blur: pad_mode %d (0 constant, 1 reflect, 2 replicate)", pad_mode);
+    // torch.nn.functional.pad(mode='reflect') raises when the padding is not smaller than the dimension
+    LMR_CHECK_ARG(pad_mode != 1 || (hy < H && hx < W), "gaussian_blur: reflect padding (%d, %d) must be smaller than the image (%d, %d)", hy, hx, H, W);
+    if (ws_bytes < (size_t)B * H * W * sizeof(float)) {
+        set_error("gaussian_blur: workspace too small");
+        return LMR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* tmp = static_cast<float*>(ws);
+    dim3 grid((unsigned)((H * W + 255) / 256), (unsigned)B);
+    mask::gblur_axis_kernel<<<grid, 256, 0, st>>>(x, tmp, H, W, 0, hy, wy, pad_mode, 1.f);
+    LMR_LAUNCH_OK();
+    mask::gblur_axis_kernel<<<grid, 256, 0, st>>>(tmp, out, H, W, 1, hx, wx, pad_mode, inv_norm);
     LMR_LAUNCH_OK();
     return 0;
 }

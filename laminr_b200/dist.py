@@ -60,12 +60,12 @@ def make_stop_reduce(device=None):
         return None
 
     def reduce(a_sum, a_min, a_max):
-        t = torch.tensor([a_sum, -a_min, a_max], dtype=torch.float64, device=device)
-        s = t[:1].clone()
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        m = t[1:].clone()
-        dist.all_reduce(m, op=dist.ReduceOp.MAX)  # max(-min) = -min: one MAX all-reduce serves both
-        return float(s[0]), -float(m[0]), float(m[1])
+        # ONE collective per epoch: every rank gets every rank's (sum, min, max) and combines them in rank order (deterministic)
+        t = torch.tensor([a_sum, a_min, a_max], dtype=torch.float64, device=device)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        allr = torch.stack(parts).cpu()
+        return float(allr[:, 0].sum()), float(allr[:, 1].min()), float(allr[:, 2].max())
 
     return reduce
 
@@ -117,11 +117,19 @@ def match_sharded(im, target_neuron_idxs, **match_kwargs):
     lo, hi = shard_bounds(D, world, rank)
     if hi == lo:
         raise ValueError(f"match_sharded: {D} targets cannot be split over {world} ranks (every rank needs at least one target)")
-    imgs, acts = im.match(targets[lo:hi], _total_targets=D, _stop_reduce=make_stop_reduce(device), **match_kwargs)
-    g_img = gather_ragged(torch.from_numpy(np.ascontiguousarray(imgs)).to(device), D)
-    g_act = gather_ragged(torch.from_numpy(np.ascontiguousarray(acts)).to(device), D)
+    fused = im._fused_ok()
+    imgs, acts = im.match(targets[lo:hi], _total_targets=D, _stop_reduce=make_stop_reduce(device), _return_device=fused, **match_kwargs)
+    if not fused:  # generic autograd path: results come back as host arrays
+        imgs, acts = torch.from_numpy(np.ascontiguousarray(imgs)).to(device), torch.from_numpy(np.ascontiguousarray(acts)).to(device)
+    snaps = match_kwargs.get("save_results_every_n_epochs") is not None
+    if snaps:  # [snapshots, D_local, ...] -> the target axis first for the gather, and back
+        imgs, acts = imgs.transpose(0, 1).contiguous(), acts.transpose(0, 1).contiguous()
+    g_img = gather_ragged(imgs.reshape(hi - lo, *imgs.shape[1:]), D)
+    g_act = gather_ragged(acts.reshape(hi - lo, *acts.shape[1:]), D)
     if rank != 0:
         return None, None
+    if snaps:
+        g_img, g_act = g_img.transpose(0, 1), g_act.transpose(0, 1)
     return g_img.cpu().numpy(), g_act.cpu().numpy()
 
 

@@ -50,6 +50,18 @@ class ChangeStats(_Renorm):
 
 
 class GaussianBlur:
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError("laminr_b200: the GaussianBlur gradient preconditioner (gb= / gaussian_blur_sigma=) is a 'next' row "
-                                  "(SURVEY 8f-3); it is also broken in the reference on scipy >= 1.13")
+    """Blur with a Gaussian window -- mirror of featurevis.ops.GaussianBlur (featurevis/ops.py:378-423; same arguments), evaluated by
+    lmr_gaussian_blur.  The reference builds the window with `scipy.signal.gaussian`, which no longer exists in scipy >= 1.13 (it is
+    `scipy.signal.windows.gaussian`); the window here is the same exp(-0.5 (k / sigma)^2)."""
+
+    def __init__(self, sigma, decay_factor=None, truncate=4, pad_mode="reflect"):
+        self.sigma = sigma if isinstance(sigma, tuple) else (sigma,) * 2
+        self.decay_factor = decay_factor
+        self.truncate = truncate
+        self.pad_mode = pad_mode
+
+    def __call__(self, x, iteration=None):
+        from .. import ops as _ops
+
+        sigma = self.sigma if self.decay_factor is None else tuple(s + self.decay_factor * (iteration - 1) for s in self.sigma)
+        return _ops.raw_gaussian_blur(x, sigma[0], sigma[1], truncate=self.truncate, pad_mode=self.pad_mode)

@@ -171,6 +171,8 @@ class InvarianceManifold:
         imgs, a = snapshot()
         if save_results_every_n_epochs is not None:
             images_list.append(imgs), acts_list.append(a)
+            if torch.is_tensor(imgs):
+                return torch.stack(images_list), torch.stack(acts_list)
             return np.stack(images_list), np.stack(acts_list)
         return imgs, a
 
@@ -182,7 +184,7 @@ class InvarianceManifold:
               only_affine_coordinate_transformation=True, stochastic_coordinate_transformation=False, allow_scale_coordinate_transformation=True,
               allow_shear_coordinate_transformation=True, uniform_scale_coordinate_transformation=False,
               init_noise_scale_coordinate_transformation=0.1, coordinate_transform_clamp_boundaries=True, verbose=False,
-              save_results_every_n_epochs=None, _total_targets=None, _stop_reduce=None):
+              save_results_every_n_epochs=None, _total_targets=None, _stop_reduce=None, _return_device=False):
         """`_total_targets` / `_stop_reduce` are used by laminr_b200.dist when the targets are sharded over GPUs: the loss keeps
         the global 1/D scale (:363) and the stop rule sees the global mean activation (:368)."""
         num_targets = len(target_neuron_idxs)
@@ -226,6 +228,8 @@ class InvarianceManifold:
         def snapshot():
             if fused:
                 act = stepper.evaluate(grid)
+                if _return_device:  # laminr_b200.dist gathers the blocks over NCCL before the one copy to the host
+                    return stepper.z.clone(), act.clone()
                 return stepper.z.cpu().numpy(), act.cpu().numpy()
             return self.get_matched_images_and_activations(grid, template, loc_in_list, loc_in_model)
 
@@ -272,6 +276,8 @@ class InvarianceManifold:
         imgs, a = snapshot()
         if save_results_every_n_epochs is not None:
             images_list.append(imgs), acts_list.append(a)
+            if torch.is_tensor(imgs):
+                return torch.stack(images_list), torch.stack(acts_list)
             return np.stack(images_list), np.stack(acts_list)
         return imgs, a
 

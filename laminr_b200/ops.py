@@ -517,3 +517,38 @@ def raw_create_mask(mei, zscore_thresh, closing_iters, gaussian_sigma, mask_out=
     check(lib.lmr_create_mask(_ptr(mei), G, H, W, float(zscore_thresh), int(closing_iters), _ptr(w_dev), radius, _ptr(mask_out), _ptr(stats), _ptr(ws),
                               ws.numel(), _stream()))
     return mask_out, stats
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Gaussian blur (featurevis.ops.GaussianBlur, featurevis/ops.py:378-423)
+# --------------------------------------------------------------------------------------------------------------------
+PAD_MODES = {"constant": 0, "reflect": 1, "replicate": 2}
+
+
+def gaussian_window(sigma, truncate=4):
+    """The window featurevis builds with scipy.signal.gaussian(2 h + 1, std=sigma): exp(-0.5 (k / sigma)^2), h = max(round(sigma * truncate), 1)."""
+    import numpy as np
+
+    h = max(int(round(sigma * truncate)), 1)
+    k = np.arange(2 * h + 1, dtype=np.float64) - h
+    return np.exp(-0.5 * (k / float(sigma)) ** 2), h
+
+
+def raw_gaussian_blur(x, sigma_y, sigma_x, truncate=4, pad_mode="reflect", out=None):
+    """x: [..., H, W] float32 on CUDA; every leading dimension is a plane.  Returns the blurred tensor (same shape)."""
+    if pad_mode not in PAD_MODES:
+        raise ValueError(f"pad_mode {pad_mode!r}: valid values are 'constant', 'reflect' and 'replicate'")
+    lib = _lib.load()
+    _require_cuda(x)
+    x = _f32c(x)
+    H, W = x.shape[-2:]
+    B = x.numel() // (H * W)
+    wy, hy = gaussian_window(sigma_y, truncate)
+    wx, hx = gaussian_window(sigma_x, truncate)
+    wy_t, wx_t = torch.as_tensor(wy, dtype=torch.float32), torch.as_tensor(wx, dtype=torch.float32)
+    inv_norm = 1.0 / float(wy_t.sum() * wx_t.sum())  # float32 sums, like featurevis (ops.py:420)
+    out = torch.empty_like(x) if out is None else out
+    ws = torch.empty(x.numel(), dtype=torch.float32, device=x.device)
+    check(lib.lmr_gaussian_blur(_ptr(x), B, H, W, _ptr(wy_t.to(x.device)), hy, _ptr(wx_t.to(x.device)), hx, PAD_MODES[pad_mode], inv_norm, _ptr(out), _ptr(ws),
+                                ws.numel() * 4, _stream()))
+    return out

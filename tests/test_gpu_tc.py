@@ -115,3 +115,19 @@ def test_tc_learn_trajectory(ops, mode):
     dW, db = split_flat(st.flat.cpu().numpy(), d, prefix="final_")
     for l in range(5):
         assert relerr(dW[l], d[f"final_W{l}"]) < 1e-2, (l, relerr(dW[l], d[f"final_W{l}"]))
+
+
+def test_two_stream_backward_variant_parity():
+    """The two-stream 64-row backward kernel (development switch LMR_BWD_MODE=2, csrc/inr_tc.cu inr_bwd2_kernel) passes the same parity tests as the
+    default one-stream kernel.  The switch is read once per process, so the tests of this file are re-run in a child process."""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("LMR_BWD_MODE"):
+        pytest.skip("already running under a backward-variant switch")
+    env = dict(os.environ, LMR_BWD_MODE="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"], env=env, cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
