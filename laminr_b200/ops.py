@@ -549,6 +549,6 @@ def raw_gaussian_blur(x, sigma_y, sigma_x, truncate=4, pad_mode="reflect", out=N
     inv_norm = 1.0 / float(wy_t.sum() * wx_t.sum())  # float32 sums, like featurevis (ops.py:420)
     out = torch.empty_like(x) if out is None else out
     ws = torch.empty(x.numel(), dtype=torch.float32, device=x.device)
-    check(lib.lmr_gaussian_blur(_ptr(x), B, H, W, _ptr(wy_t.to(x.device)), hy, _ptr(wx_t.to(x.device)), hx, PAD_MODES[pad_mode], inv_norm, _ptr(out), _ptr(ws),
-                                ws.numel() * 4, _stream()))
+    wy_d, wx_d = wy_t.to(x.device), wx_t.to(x.device)  # named: the device copies must outlive the pointer extraction
+    check(lib.lmr_gaussian_blur(_ptr(x), B, H, W, _ptr(wy_d), hy, _ptr(wx_d), hx, PAD_MODES[pad_mode], inv_norm, _ptr(out), _ptr(ws), ws.numel() * 4, _stream()))
     return out

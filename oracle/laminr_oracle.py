@@ -509,6 +509,31 @@ def adam_step(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# Gaussian blur, the optional gradient preconditioner (featurevis/ops.py:378-423)
+# ----------------------------------------------------------------------------------------------------------------
+def gaussian_blur(x, sigma, truncate=4, pad_mode="reflect"):
+    """featurevis.ops.GaussianBlur.__call__ without decay (ops.py:398-423).  x: [B,C,H,W].  The window is scipy.signal.gaussian(2h+1, std)
+    = exp(-0.5 (k/std)^2) (ops.py:409-412), cast to x's dtype; F.pad's modes map to numpy's: 'reflect' -> 'reflect' (no edge repeat),
+    'replicate' -> 'edge', 'constant' -> zeros (ops.py:417); depthwise y then x correlation (:418-421); division by the product of the
+    window sums (:422)."""
+    sig = sigma if isinstance(sigma, tuple) else (sigma,) * 2
+    x = np.asarray(x)
+    hy, hx = max(int(round(sig[0] * truncate)), 1), max(int(round(sig[1] * truncate)), 1)
+    wy = np.exp(-0.5 * ((np.arange(2 * hy + 1) - hy) / sig[0]) ** 2).astype(x.dtype)
+    wx = np.exp(-0.5 * ((np.arange(2 * hx + 1) - hx) / sig[1]) ** 2).astype(x.dtype)
+    mode = {"reflect": "reflect", "replicate": "edge", "constant": "constant"}[pad_mode]
+    xp = np.pad(x, ((0, 0), (0, 0), (hy, hy), (hx, hx)), mode=mode)
+    H, W = x.shape[-2:]
+    by = np.zeros(xp.shape[:2] + (H, xp.shape[3]), x.dtype)
+    for k in range(2 * hy + 1):
+        by += wy[k] * xp[:, :, k:k + H, :]
+    bx = np.zeros(x.shape, x.dtype)
+    for k in range(2 * hx + 1):
+        bx += wx[k] * by[:, :, :, k:k + W]
+    return bx / (wy.sum() * wx.sum())
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # MEI gradient ascent  (featurevis/core.py:54-136 with SGD; laminr/utils/mei.py:9-71)
 # ----------------------------------------------------------------------------------------------------------------
 

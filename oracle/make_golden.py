@@ -299,6 +299,25 @@ def case_learn_match_steps(laminr):
 
         if res != 20:
             continue
+        # ---- the same learn step with the Gaussian-blur gradient preconditioner (learn(gaussian_blur_sigma=1.0): a backward hook on img_post,
+        #      inv_temp_learn_match.py:158,524-525); `scipy.signal.gaussian` is aliased to scipy.signal.windows.gaussian (gone from scipy >= 1.13)
+        import scipy.signal
+        import scipy.signal.windows
+
+        if not hasattr(scipy.signal, "gaussian"):
+            scipy.signal.gaussian = scipy.signal.windows.gaussian
+        import featurevis.ops as fops
+
+        for p_ in im.template.func.parameters():
+            p_.grad = None
+        _, img_post_b, _acts_b, _ = im.forward(grid, im.template, im.img_transforms, SingleNeuronModel(model, 0), gb=fops.GaussianBlur(1.0), return_template=True)
+        loss_b = -(_acts_b / meis[0]["activation"]).mean() - 2 * reg.reg_term(apply_mask(img_post_b, torch.from_numpy(meis[0]["mask"]), -1.0, 1.0))
+        loss_b.backward()
+        db_ = dict(loss=npy(loss_b))
+        for l in range(5):
+            db_[f"dW{l}"] = npy(getattr(im.template.func, f"layer{l}").weight.grad)
+            db_[f"db{l}"] = npy(getattr(im.template.func, f"layer{l}").bias.grad)
+        np.savez_compressed(os.path.join(OUT, "learn_step_20_gb.npz"), **db_)
         # ---- match step on targets [1, 2]
         targets = [1, 2]
         im.template_neuron_idx = 0
@@ -545,6 +564,32 @@ def case_create_mask(laminr):
     np.savez_compressed(os.path.join(OUT, "create_mask.npz"), **d)
 
 
+def case_gaussian_blur(laminr):
+    """featurevis.ops.GaussianBlur of the reference (ops.py:378-423) on seeded images.  The reference calls `scipy.signal.gaussian`, which
+    scipy >= 1.13 only provides as `scipy.signal.windows.gaussian`: the alias is restored here (nothing else is patched)."""
+    import scipy.signal
+    import scipy.signal.windows
+
+    if not hasattr(scipy.signal, "gaussian"):
+        scipy.signal.gaussian = scipy.signal.windows.gaussian
+    import featurevis.ops as fops
+
+    d = {}
+    rng = np.random.RandomState(5)
+    cases = dict(a=((3, 1, 20, 24), 1.0, 4, "reflect"), b=((2, 2, 17, 9), (1.5, 0.6), 4, "reflect"), c=((2, 1, 12, 12), 2.0, 3, "replicate"),
+                 e=((1, 1, 30, 30), 0.4, 4, "constant"), f=((1, 1, 100, 100), 1.5, 4, "reflect"))
+    for tag, (shape, sigma, trunc, mode) in cases.items():
+        x = rng.randn(*shape).astype(np.float32)
+        y = fops.GaussianBlur(sigma, truncate=trunc, pad_mode=mode)(torch.from_numpy(x))
+        d[f"{tag}_x"], d[f"{tag}_y"] = x, npy(y)
+        d[f"{tag}_cfg"] = np.array([sigma[0] if isinstance(sigma, tuple) else sigma, sigma[1] if isinstance(sigma, tuple) else sigma, trunc,
+                                    {"constant": 0, "reflect": 1, "replicate": 2}[mode]], np.float64)
+    # decay: sigma + decay_factor * (iteration - 1)  (ops.py:403-406)
+    x = rng.randn(1, 1, 16, 16).astype(np.float32)
+    d["g_x"], d["g_y"] = x, npy(fops.GaussianBlur(1.0, decay_factor=0.25)(torch.from_numpy(x), iteration=3))
+    np.savez_compressed(os.path.join(OUT, "gaussian_blur.npz"), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     laminr = import_reference()
@@ -552,7 +597,7 @@ def main():
     import sys
     only = set(sys.argv[1:])
     for fn in (case_inr, case_match_inr, case_constrain, case_simresp, case_banks_100, case_simclr, case_training_utils,
-               case_adam, case_mei, case_learn_match_steps, case_trajectory, case_convcore, case_conv_learn_match, case_create_mask):
+               case_adam, case_mei, case_learn_match_steps, case_trajectory, case_convcore, case_conv_learn_match, case_create_mask, case_gaussian_blur):
         if only and fn.__name__ not in only:
             continue
         fn(laminr)
