@@ -41,6 +41,12 @@ typedef enum {
                                  TMEM, tanh from ex2/rcp (~1e-7): fp32-class results; layer 0 and the output layer stay on CUDA cores */
 } lmr_precision;
 
+/* Flag, OR-ed into `precision` of lmr_inr_forward AND of the matching lmr_inr_backward_after_forward (tensor-core modes only): the forward
+ * keeps the split-bf16 operand tiles of the hidden activations h_1..h_3 in its workspace (numTiles x 3 x 32 KB: 160 MB for one 20 x 100 x 100
+ * image set) and the backward loads them with bulk async copies instead of recomputing the forward per tile.  The forward workspace must
+ * then have lmr_inr_forward_workspace_bytes_keep(...) bytes. */
+#define LMR_PREC_KEEP_ACTIVATIONS 0x100
+
 typedef enum { LMR_CONSTRAIN_NORM = 0, LMR_CONSTRAIN_STD = 1 } lmr_constrain_mode;
 
 int lmr_abi_version(void);
@@ -85,6 +91,7 @@ typedef struct {
 size_t lmr_inr_params_count(const lmr_inr_desc* desc);
 size_t lmr_inr_forward_workspace_bytes(const lmr_inr_desc* desc, int N, int P, int D);
 size_t lmr_inr_backward_workspace_bytes(const lmr_inr_desc* desc, int N, int P, int D);
+size_t lmr_inr_forward_workspace_bytes_keep(const lmr_inr_desc* desc, int N, int P, int D);  /* with LMR_PREC_KEEP_ACTIVATIONS */
 
 /* img[D,N,C,P] = INR(grid[N] latents, coords[P,2] (y,x) pixel coordinates).
  * coord_shift: optional [2] added to coords (centralize_template, inr.py:329-335), learn stage only. */

@@ -6,6 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblaminr_b200.so")
 
 PREC_FP32, PREC_BF16X3_FAST, PREC_BF16X3 = 0, 1, 2
+PREC_KEEP_ACTIVATIONS = 0x100  # flag: the forward keeps the hidden activations' operand tiles for the backward (include/laminr_b200.h)
 MODE_NORM, MODE_STD = 0, 1
 
 
@@ -42,6 +43,7 @@ SIGNATURES = {
     "lmr_inr_params_count": (_sz, [C.POINTER(InrDesc)]),
     "lmr_inr_forward_workspace_bytes": (_sz, [C.POINTER(InrDesc), _i, _i, _i]),
     "lmr_inr_backward_workspace_bytes": (_sz, [C.POINTER(InrDesc), _i, _i, _i]),
+    "lmr_inr_forward_workspace_bytes_keep": (_sz, [C.POINTER(InrDesc), _i, _i, _i]),
     "lmr_inr_forward": (_i, [C.POINTER(InrDesc), _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, C.POINTER(Affine), _i, _vp, _vp, _sz, _i, _vp]),
     "lmr_inr_backward": (_i, [C.POINTER(InrDesc), _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, C.POINTER(Affine), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "lmr_inr_backward_after_forward": (_i, [C.POINTER(InrDesc), _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, C.POINTER(Affine), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,

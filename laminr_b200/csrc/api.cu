@@ -39,7 +39,7 @@ int forward(const lmr_inr_desc*, const float*, const float*, const float*, const
             float*, void*, size_t, int, cudaStream_t);
 int backward(const lmr_inr_desc*, const float*, const float*, const float*, const float*, int, const float*, int, const float*, const lmr_affine*, int,
              const float*, float*, float*, float*, float*, float*, void*, size_t, int, cudaStream_t, const void*, size_t);
-size_t workspace_bytes(const lmr_inr_desc*, int, int, int, bool);
+size_t workspace_bytes(const lmr_inr_desc*, int, int, int, bool, bool keep_act = false);
 }  // namespace tc
 
 }  // namespace lmr
@@ -70,6 +70,9 @@ static size_t max_sz(size_t a, size_t b) { return a > b ? a : b; }
 extern "C" size_t lmr_inr_forward_workspace_bytes(const lmr_inr_desc* desc, int N, int P, int D) {
     return max_sz(simt::workspace_bytes(desc, N, P, D, false), tc::workspace_bytes(desc, N, P, D, false));
 }
+extern "C" size_t lmr_inr_forward_workspace_bytes_keep(const lmr_inr_desc* desc, int N, int P, int D) {
+    return max_sz(simt::workspace_bytes(desc, N, P, D, false), tc::workspace_bytes(desc, N, P, D, false, true));
+}
 extern "C" size_t lmr_inr_backward_workspace_bytes(const lmr_inr_desc* desc, int N, int P, int D) {
     return max_sz(simt::workspace_bytes(desc, N, P, D, true), tc::workspace_bytes(desc, N, P, D, true));
 }
@@ -78,8 +81,9 @@ extern "C" int lmr_inr_forward(const lmr_inr_desc* desc, const float* params, co
                                const float* coords, int P, const float* coord_shift, const lmr_affine* affine, int D, float* img, void* ws,
                                size_t ws_bytes, int precision, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (precision == LMR_PREC_FP32) return simt::forward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, img, ws, ws_bytes, st);
-    if (precision == LMR_PREC_BF16X3_FAST || precision == LMR_PREC_BF16X3)
+    const int mode = precision & ~LMR_PREC_KEEP_ACTIVATIONS;  // the flag is passed on to the tensor-core path, ignored by the fp32 path
+    if (mode == LMR_PREC_FP32) return simt::forward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, img, ws, ws_bytes, st);
+    if (mode == LMR_PREC_BF16X3_FAST || mode == LMR_PREC_BF16X3)
         return tc::forward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, img, ws, ws_bytes, precision, st);
     set_error("inr_forward: unknown precision %d", precision);
     return LMR_ERR_INVALID;
@@ -106,9 +110,10 @@ extern "C" int lmr_inr_backward_after_forward(const lmr_inr_desc* desc, const fl
                                               float* g_translation, void* ws, size_t ws_bytes, const void* forward_workspace,
                                               size_t forward_workspace_bytes, int precision, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (precision == LMR_PREC_BF16X3_FAST || precision == LMR_PREC_BF16X3)
+    const int mode = precision & ~LMR_PREC_KEEP_ACTIVATIONS;
+    if (mode == LMR_PREC_BF16X3_FAST || mode == LMR_PREC_BF16X3)
         return tc::backward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, g_img, g_params, g_angles, g_scalings, g_shears,
                             g_translation, ws, ws_bytes, precision, st, forward_workspace, forward_workspace_bytes);
     return lmr_inr_backward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, g_img, g_params, g_angles, g_scalings, g_shears,
-                            g_translation, ws, ws_bytes, precision, stream);  // the fp32 path recomputes its tables
+                            g_translation, ws, ws_bytes, mode, stream);  // the fp32 path recomputes its tables
 }

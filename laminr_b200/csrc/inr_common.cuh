@@ -60,6 +60,7 @@ struct Args {
     float* Cpg;    // [D*P, HP]  layer-0 coordinate part Cp[d,p][o] = sum_k beta[d,p][k] W0c[o][k]   (tensor-core path)
     unsigned char* wtimg;  // (nl-1) x 16 KB: split-bf16 (hi | lo) K-major core-matrix images of the hidden weight tiles (tensor-core path)
     float* betaG;  // [D*P, 2*pe] sin/cos(coords.B) (tensor-core path, D == 1: consumed by the layer-0 weight-gradient kernel), else null
+    unsigned char* hsave;  // [numTiles, nl-1, 32 KB] operand-tile images of h_1..h_{nl-1} kept by the forward for the backward (tensor-core path, opt-in), else null
     int want_cp;
     int ppb;       // pixels per l0 / affine-gradient block
     int ppb_prep;  // pixels per prep block (two blocks per SM: the prep blocks are latency-bound)
@@ -632,11 +633,11 @@ static __global__ void finish_affine_kernel(Args a, int npart, float* g_angles, 
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 struct WsLayout {
-    size_t alpha, Avec, W0cT, wtimg, Cpg, betaG, G0, partials, l0part, affpart, dAred, total;
+    size_t alpha, Avec, W0cT, wtimg, Cpg, betaG, hsave, G0, partials, l0part, affpart, dAred, total;
     int gridMain, gridL0, ppb;
 };
 
-static inline WsLayout ws_layout(const Net& nt, const Tiling& tl, bool bwd, bool want_cp = false) {
+static inline WsLayout ws_layout(const Net& nt, const Tiling& tl, bool bwd, bool want_cp = false, bool keep_act = false) {
     const int HP = (nt.hid + 3) / 4 * 4;
     WsLayout w;
     size_t off = 0;
@@ -651,6 +652,7 @@ static inline WsLayout ws_layout(const Net& nt, const Tiling& tl, bool bwd, bool
     w.wtimg = want_cp ? take((size_t)(nt.nl - 1) * 16384 / 4) : 0;
     w.Cpg = want_cp ? take((size_t)tl.D * tl.P * HP) : 0;
     w.betaG = (want_cp && tl.D == 1) ? take((size_t)tl.P * 2 * nt.pe) : 0;  // identical prefix in the forward and backward layouts
+    w.hsave = (want_cp && keep_act && !bwd) ? take((size_t)tl.numTiles * (nt.nl - 1) * 32768 / 4) : 0;  // forward layout only (a suffix of it)
     w.gridMain = tl.numTiles < num_sms() ? tl.numTiles : num_sms();
     const int total = tl.D * tl.P;
     w.ppb = choose_ppb(total);
@@ -710,6 +712,7 @@ static inline int fill_args(Args& a, const Net& nt, const Tiling& tl, const floa
     a.img = nullptr, a.g_img = nullptr, a.want_weights = 0, a.want_affine = 0;
     a.trace = nullptr;
     a.stagger = 0;
+    a.hsave = wl.hsave ? reinterpret_cast<unsigned char*>(base + wl.hsave) : nullptr;
     return 0;
 }
 

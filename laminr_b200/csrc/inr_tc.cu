@@ -60,7 +60,10 @@ constexpr uint32_t TM_COLS_BWD = 512, TM_COLS_FWD = 128;
 constexpr int BAR_K = 0;      // [0..3] k-chunk kc of the operand tile under construction is complete (epilogue warps -> MMA thread)
 constexpr int BAR_ACC = 4;    // [4..5] accumulator ready (tcgen05.commit -> epilogue threads)
 constexpr int BAR_DONE = 6;   // every MMA of the CTA has completed
-constexpr int NBARS = 8;
+constexpr int BAR_LAND = 8;   // [8..10] kept-activation tile h_1 / h_2 / h_3 of the current tile has landed (bulk copy -> everyone)
+constexpr int BAR_FREE = 11;  // [11..12] the buffers of the next tile's h_3 / of its h_2 and h_1 are free (tcgen05.commit -> loader thread)
+constexpr int BAR_EPI = 13;   // every epilogue warp has finished the current tile (epilogue warps -> loader thread)
+constexpr int NBARS = 16;
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -536,7 +539,9 @@ constexpr int NE_T = 128, NT_T = NE_T + 32;
 constexpr uint32_t TM_T_ACC = 0, TM_T_AHI = 64, TM_T_ALO = 96, TM_T_COLS = 128;
 
 // split 16 floats (8 pairs) into bf16 hi / lo words and write them to the A operand columns of k-chunk kc
-__device__ __forceinline__ void store_kchunk_tmem(uint32_t a_hi, uint32_t a_lo, int kc, const float2* v) {
+// `gimg` (nullable): this layer's 32 KB operand-tile image in global memory (same layout as the shared-memory tiles of the backward), written
+// for the backward when the activations are kept (LMR_PREC_KEEP_ACTIVATIONS)
+__device__ __forceinline__ void store_kchunk_tmem(uint32_t a_hi, uint32_t a_lo, int kc, const float2* v, uint8_t* gimg = nullptr, int row = 0) {
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -550,6 +555,14 @@ __device__ __forceinline__ void store_kchunk_tmem(uint32_t a_hi, uint32_t a_lo, 
     }
     tmem_st8(a_hi + 8 * kc, hi);
     tmem_st8(a_lo + 8 * kc, lo);
+    if (gimg != nullptr) {
+        const uint32_t o0 = tile_off(row, 2 * kc, 128), o1 = tile_off(row, 2 * kc + 1, 128);
+        // streaming stores: 160 MB per 20 x 100 x 100 image set, read once by the backward -- keep them from evicting the step's working set from L2
+        __stcs(reinterpret_cast<uint4*>(gimg + o0), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+        __stcs(reinterpret_cast<uint4*>(gimg + o1), make_uint4(hi[4], hi[5], hi[6], hi[7]));
+        __stcs(reinterpret_cast<uint4*>(gimg + TILE_HALF + o0), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+        __stcs(reinterpret_cast<uint4*>(gimg + TILE_HALF + o1), make_uint4(lo[4], lo[5], lo[6], lo[7]));
+    }
 }
 __device__ __forceinline__ void arrive_kchunk_tmem(uint64_t* bar, int lane) {
     tmem_st_wait();
@@ -625,6 +638,7 @@ __global__ void __launch_bounds__(NT_T, 4) inr_fwd_ts_kernel(Args a) {
             Cj += (active ? j : 0) * SHS;
             const bool as_smem = s.As != nullptr && !multi_chunk;
             const float* An = as_smem ? s.As + (active ? nl : 0) * SHS : a.Avec + (size_t)(ti.n0 + (active ? nl : 0)) * SHP;
+            uint8_t* gimg = a.hsave != nullptr ? a.hsave + (size_t)(blockIdx.x + it * gridDim.x) * (LH - 1) * TILE_BYTES : nullptr;  // h_1 | h_2 | h_3
             // ---- h_1 = tanh(A[n] + Cp[j]) -> operand (the previous tile's last accumulator was waited for: the operand columns are free)
 #pragma unroll 1
             for (int kc = 0; kc < 4; ++kc) {
@@ -643,7 +657,7 @@ __global__ void __launch_bounds__(NT_T, 4) inr_fwd_ts_kernel(Args a) {
                     v[q] = act_tanh2<FAST>(v[q]);
                     if (!active || 2 * q >= ncol) v[q] = make_float2(0.f, 0.f);
                 }
-                store_kchunk_tmem(a_hi, a_lo, kc, v);
+                store_kchunk_tmem(a_hi, a_lo, kc, v, gimg, row);
                 arrive_kchunk_tmem(&s.bars[BAR_K + kc], lane);
             }
 #pragma unroll 1
@@ -665,7 +679,7 @@ __global__ void __launch_bounds__(NT_T, 4) inr_fwd_ts_kernel(Args a) {
                         float2 w[8];
 #pragma unroll
                         for (int q = 0; q < 8; ++q) w[q] = (8 * kc + q < 26) ? act_tanh2<FAST>(v[8 * kc + q]) : make_float2(0.f, 0.f);
-                        store_kchunk_tmem(a_hi, a_lo, kc, w);
+                        store_kchunk_tmem(a_hi, a_lo, kc, w, gimg != nullptr ? gimg + (size_t)(st + 1) * TILE_BYTES : nullptr, row);
                         arrive_kchunk_tmem(&s.bars[BAR_K + kc], lane);
                     }
                 } else {  // output layer on CUDA cores
@@ -707,9 +721,11 @@ constexpr int NG_B = 4;
 constexpr int MAX_DA = 4;   // dA[n][o] accumulators per epilogue thread: N * 50 <= 4 * 512  (N <= 40)
 constexpr int STG = 53;     // row stride (floats) of the fp32 staging panel stage[row][o] of dz_0 (odd: conflict-free both ways)
 
-template <bool FAST, int C, int NG>
-__global__ void __launch_bounds__(128 * NG + 32, 1) inr_bwd_tc_kernel(Args a) {
-    constexpr int NE = 128 * NG, NT_B = NE + 32, NCH = 8 / NG;
+// LOADH: the forward kept the operand tiles of h_1..h_3 (Args::hsave): no recompute; a loader thread streams the three 32 KB tiles of the next tile
+// into the buffers as the tensor pipe releases them, the per-tile chain shrinks from 6 MMA stages / 7 epilogue steps to 4 / 4.
+template <bool FAST, int C, int NG, bool LOADH>
+__global__ void __launch_bounds__(128 * NG + 64, 1) inr_bwd_tc_kernel(Args a) {
+    constexpr int NE = 128 * NG, NT_B = NE + 64, NCH = 8 / NG;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const Net& nt = a.net;
     const Tiling& tl = a.tl;
@@ -720,7 +736,13 @@ __global__ void __launch_bounds__(128 * NG + 32, 1) inr_bwd_tc_kernel(Args a) {
     load_weight_tiles(a, s);
     init_layer0_tables(a, s, true, NT_B);
     if (warp == NE / 32) tmem_alloc(s.tmem, TM_COLS_BWD);
-    if (t == 0) init_barriers(s.bars, 8);
+    if (t == 0) {
+        init_barriers(s.bars, 8);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) mbar_init(&s.bars[BAR_LAND + k], 1);
+        mbar_init(&s.bars[BAR_EPI], NE / 32);
+        mbar_fence_init();
+    }
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -728,6 +750,28 @@ __global__ void __launch_bounds__(128 * NG + 32, 1) inr_bwd_tc_kernel(Args a) {
     const uint32_t tm = *s.tmem;
     const int myTiles = (tl.numTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (t == 0) LMR_TRACE(0, 501);
+
+    if (warp == NE / 32 + 1) {  // (idle without LOADH)
+        if (LOADH && lane == 0) {  // ---- loader: h_3, h_2, h_1 of every tile, each as soon as its buffer is free
+            const uint64_t pol = l2_policy_evict_first();  // read once
+            for (int it = 0; it < myTiles; ++it) {
+                const int rot = (2 * it) % NBUF_BWD;
+                auto buf = [&](int role) { return s.tiles + (size_t)((role + rot) % NBUF_BWD) * TILE_BYTES; };
+                const uint8_t* src = a.hsave + (size_t)(blockIdx.x + it * gridDim.x) * (LH - 1) * TILE_BYTES;
+                if (it > 0) mbar_wait(&s.bars[BAR_FREE], (uint32_t)(it - 1) & 1);      // dW_2 of the previous tile done: its dz_2 buffer = this h_3 buffer
+                mbar_arrive_expect_tx(&s.bars[BAR_LAND + 2], TILE_BYTES);
+                bulk_copy_g2s(buf(ROLE_H1 + 2), src + 2 * (size_t)TILE_BYTES, TILE_BYTES, &s.bars[BAR_LAND + 2], pol);
+                if (it > 0) mbar_wait(&s.bars[BAR_FREE + 1], (uint32_t)(it - 1) & 1);  // every MMA of the previous tile done
+                mbar_arrive_expect_tx(&s.bars[BAR_LAND + 1], TILE_BYTES);
+                bulk_copy_g2s(buf(ROLE_H1 + 1), src + (size_t)TILE_BYTES, TILE_BYTES, &s.bars[BAR_LAND + 1], pol);
+                // h_1 last: its landing barrier is the only one a slow epilogue thread of the previous tile may still be waiting on (the dz_0 step
+                // signals nothing to the tensor pipe), so it is re-armed only after every epilogue warp has left that tile
+                if (it > 0) mbar_wait(&s.bars[BAR_EPI], (uint32_t)(it - 1) & 1);
+                mbar_arrive_expect_tx(&s.bars[BAR_LAND], TILE_BYTES);
+                bulk_copy_g2s(buf(ROLE_H1), src, TILE_BYTES, &s.bars[BAR_LAND], pol);
+            }
+        }
+    } else
 
     if (warp == NE / 32) {
         if (lane == 0) {  // ---- MMA issuer
@@ -737,9 +781,18 @@ __global__ void __launch_bounds__(128 * NG + 32, 1) inr_bwd_tc_kernel(Args a) {
                 const int rot = (2 * it) % NBUF_BWD;
                 auto buf = [&](int role) { return tiles_addr + (uint32_t)((role + rot) % NBUF_BWD) * TILE_BYTES; };
                 int st = 0;
+                if (LOADH) {  // z_4 = h_3 W_3^T from the kept tile: all four k-steps at once
+                    mbar_wait(&s.bars[BAR_LAND + 2], (uint32_t)it & 1);
+                    fence_after_sync();
+                    const StageDesc sd = make_stage(buf(ROLE_H1 + LH - 2), w_addr + (uint32_t)(LH - 2) * WT_BYTES, 0);
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) issue_kstep(tm + TM_ACC, sd, kc);
+                    mma_commit(&s.bars[BAR_ACC]);
+                    st = 1;
+                }
                 // forward recompute: z_l = h_l W_l^T, l = 1..3 (operand h_l = role l-1)
 #pragma unroll 1
-                for (int l = 1; l < LH; ++l, ++st) {
+                for (int l = 1; l < (LOADH ? 1 : LH); ++l, ++st) {
                     const uint32_t acc = tm + TM_ACC + (uint32_t)(st & 1) * 64;
                     const StageDesc sd = make_stage(buf(ROLE_H1 + l - 1), w_addr + (uint32_t)(l - 1) * WT_BYTES, 0);
 #pragma unroll
@@ -769,7 +822,14 @@ __global__ void __launch_bounds__(128 * NG + 32, 1) inr_bwd_tc_kernel(Args a) {
                     pk ^= 1;
                     mma_commit(&s.bars[BAR_ACC + (st & 1)]);
                     LMR_TRACE(1, (it * 6 + st) * 5 + 4);
-                    if (want_w) issue_wgrad(tm + TM_DW + (uint32_t)(l - 1) * 128, dz, buf(ROLE_H1 + l - 1), it == 0);
+                    if (want_w) {
+                        if (LOADH && l < LH - 1) {  // h_2 / h_1 of this tile may still be in flight (h_3 landed before z_4)
+                            mbar_wait(&s.bars[BAR_LAND + l - 1], (uint32_t)it & 1);
+                            fence_after_sync();
+                        }
+                        issue_wgrad(tm + TM_DW + (uint32_t)(l - 1) * 128, dz, buf(ROLE_H1 + l - 1), it == 0);
+                    }
+                    if (LOADH && l <= 2) mma_commit(&s.bars[BAR_FREE + (2 - l)]);  // l == 2: the dz_2 buffer is free; l == 1: every buffer of the tile
                 }
             }
             mma_commit(&s.bars[BAR_DONE]);
@@ -801,7 +861,7 @@ __global__ void __launch_bounds__(128 * NG + 32, 1) inr_bwd_tc_kernel(Args a) {
 #pragma unroll
             for (int k = 0; k < 8 * NCH; ++k) wacc[c][k] = 0.f;
         }
-        if (myTiles > 0) stage_tile_inputs(a, decode_tile(tl, blockIdx.x), s.Cps, NE);
+        if (!LOADH && myTiles > 0) stage_tile_inputs(a, decode_tile(tl, blockIdx.x), s.Cps, NE);
         cp_async_commit();
         // ---- layer 0 of a finished tile (CUDA cores; consecutive lanes -> consecutive features: conflict-free), DEFERRED into the next tile's
         //      first two accumulator waits (software pipelining; the panel stage[row][o] of dz_0 sits in a buffer the next tile does not write
@@ -845,7 +905,7 @@ __global__ void __launch_bounds__(128 * NG + 32, 1) inr_bwd_tc_kernel(Args a) {
             auto buf = [&](int role) { return s.tiles + (size_t)((role + rot) % NBUF_BWD) * TILE_BYTES; };
             cp_async_wait<0>();
             named_bar_sync(1, NE);  // staged Cp visible; the previous tile's dz_0 panel is complete; everybody is done with its scratch
-            if (it + 1 < myTiles) stage_tile_inputs(a, decode_tile(tl, blockIdx.x + (it + 1) * gridDim.x), s.Cps + ((it + 1) & 1) * TP * SHS, NE);
+            if (!LOADH && it + 1 < myTiles) stage_tile_inputs(a, decode_tile(tl, blockIdx.x + (it + 1) * gridDim.x), s.Cps + ((it + 1) & 1) * TP * SHS, NE);
             cp_async_commit();
             if (t == 0) LMR_TRACE(0, it * 20 + 0);
             const float* Cps = s.Cps + (it & 1) * TP * SHS;
@@ -860,6 +920,13 @@ __global__ void __launch_bounds__(128 * NG + 32, 1) inr_bwd_tc_kernel(Args a) {
             float2 v[4 * NCH];
             float* vf = reinterpret_cast<float*>(v);
 
+            int st = 0;
+            if (LOADH) {  // both deferred reductions of the previous tile while the tensor pipe computes z_4 from the kept h_3
+                if (it > 0) {
+                    reduce_g0(ti_prev, stage_prev);
+                    if (want_w) reduce_dA(ti_prev, stage_prev);
+                }
+            } else {
             // ---- forward recompute: h_1 (CUDA cores), h_2, h_3 (tensor cores) kept as tiles
             if (s.As != nullptr) {
                 load_layer0<NG>(s.As + (active ? nl : 0) * SHS, Cps + (active ? j : 0) * SHS, rc.g, vf);
@@ -876,7 +943,6 @@ __global__ void __launch_bounds__(128 * NG + 32, 1) inr_bwd_tc_kernel(Args a) {
             tanh_store<NG, FAST>(v, buf(ROLE_H1), rc, &s.bars[BAR_K], active);
             if (t == 0) LMR_TRACE(0, it * 20 + 1);
             if (it > 0) reduce_g0(ti_prev, stage_prev);  // while the tensor pipe computes z_2
-            int st = 0;
 #pragma unroll 1
             for (int l = 1; l < LH - 1; ++l, ++st) {
                 if (l == 2 && it > 0 && want_w) reduce_dA(ti_prev, stage_prev);  // while the tensor pipe computes z_3
@@ -886,6 +952,7 @@ __global__ void __launch_bounds__(128 * NG + 32, 1) inr_bwd_tc_kernel(Args a) {
                 tanh_store<NG, FAST>(v, buf(ROLE_H1 + l), rc, &s.bars[BAR_K], true);
                 if (t == 0) LMR_TRACE(0, it * 20 + 3 + 2 * st);
             }
+            }  // !LOADH
             // ---- last hidden layer + output layer (CUDA cores): h_4 in registers, y, dy = g (1 - y^2), dz_3 = (Wout^T dy)(1 - h_4^2) -> DA
             {
                 wait_acc(st);
@@ -957,6 +1024,7 @@ __global__ void __launch_bounds__(128 * NG + 32, 1) inr_bwd_tc_kernel(Args a) {
 #pragma unroll 1
             for (int l = LH - 1; l >= 1; --l, ++st) {
                 const uint8_t* Hl = buf(ROLE_H1 + l - 1);
+                if (LOADH) mbar_wait(&s.bars[BAR_LAND + l - 1], (uint32_t)it & 1);  // the kept tile of h_l has landed
                 float2 hv[4 * NCH];  // h_l of this thread's features, fetched while the data-gradient MMAs run
 #pragma unroll
                 for (int i = 0; i < NCH; ++i)
@@ -988,6 +1056,10 @@ __global__ void __launch_bounds__(128 * NG + 32, 1) inr_bwd_tc_kernel(Args a) {
                 if (t == 0) LMR_TRACE(0, it * 20 + 3 + 2 * st);
             }
             ti_prev = ti, stage_prev = stage;
+            if (LOADH) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.bars[BAR_EPI]);
+            }
             if (t == 0) LMR_TRACE(0, it * 20 + 16);
         }
         if (myTiles > 0) {  // the last tile's layer 0
@@ -1638,9 +1710,11 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
     if (int rc = check_tc(nt)) return rc;
     LMR_CHECK_ARG(N >= 1 && P >= 1 && D >= 1, "inr_forward: bad sizes N=%d P=%d D=%d", N, P, D);
     const Tiling tl = make_tiling(N, P, D, TP_CAP_TC);
-    const WsLayout wl = ws_layout(nt, tl, false, true);
+    const bool keep_act = (precision & LMR_PREC_KEEP_ACTIVATIONS) != 0;
+    precision &= ~LMR_PREC_KEEP_ACTIVATIONS;
+    const WsLayout wl = ws_layout(nt, tl, false, true, keep_act);
     if (ws_bytes < wl.total) {
-        set_error("inr_forward: workspace %zu < %zu bytes", ws_bytes, wl.total);
+        set_error("inr_forward: workspace %zu < %zu bytes%s", ws_bytes, wl.total, keep_act ? " (LMR_PREC_KEEP_ACTIVATIONS: lmr_inr_forward_workspace_bytes_keep)" : "");
         return LMR_ERR_WORKSPACE;
     }
     Args a;
@@ -1648,7 +1722,8 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
     a.img = img;
     a.want_cp = 1;
     if (int rc = launch_prep<50>(a, st)) return rc;
-    static const bool smem_operands = getenv("LMR_FWD_SMEM") != nullptr;  // development switch: operand tiles in shared memory
+    static const bool smem_operands_env = getenv("LMR_FWD_SMEM") != nullptr;  // development switch: operand tiles in shared memory
+    const bool smem_operands = smem_operands_env && !keep_act;
     const bool fast = precision == LMR_PREC_BF16X3_FAST;
     if (!smem_operands) {
         TcSmem s(nullptr, nt, tl, 0, false, 1);
@@ -1698,6 +1773,9 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
         LMR_CHECK_ARG(affine && affine->angles, "inr_backward: affine gradients requested without an affine transform");
     }
     const Tiling tl = make_tiling(N, P, D, TP_CAP_TC);
+    const bool keep_act = (precision & LMR_PREC_KEEP_ACTIVATIONS) != 0;
+    precision &= ~LMR_PREC_KEEP_ACTIVATIONS;
+    LMR_CHECK_ARG(!keep_act || fwd_ws != nullptr, "inr_backward: LMR_PREC_KEEP_ACTIVATIONS needs the forward workspace (lmr_inr_backward_after_forward)");
     const WsLayout wl = ws_layout(nt, tl, true, true);
     if (ws_bytes < wl.total) {
         set_error("inr_backward: workspace %zu < %zu bytes", ws_bytes, wl.total);
@@ -1709,13 +1787,14 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     a.want_weights = g_params != nullptr, a.want_affine = want_aff;
     a.want_cp = 1;
     if (fwd_ws != nullptr) {  // the per-step tables of the forward call that produced these images are still valid: no preparation launch
-        const WsLayout wf = ws_layout(nt, tl, false, true);
+        const WsLayout wf = ws_layout(nt, tl, false, true, keep_act);
         LMR_CHECK_ARG(fwd_ws_bytes >= wf.total, "inr_backward: forward workspace %zu < %zu bytes", fwd_ws_bytes, wf.total);
         char* fb = static_cast<char*>(const_cast<void*>(fwd_ws));
         a.alpha = reinterpret_cast<float*>(fb + wf.alpha), a.Avec = reinterpret_cast<float*>(fb + wf.Avec);
         a.W0cT = reinterpret_cast<float*>(fb + wf.W0cT), a.Cpg = reinterpret_cast<float*>(fb + wf.Cpg);
         a.wtimg = reinterpret_cast<unsigned char*>(fb + wf.wtimg);
         a.betaG = wf.betaG ? reinterpret_cast<float*>(fb + wf.betaG) : nullptr;
+        a.hsave = wf.hsave ? reinterpret_cast<unsigned char*>(fb + wf.hsave) : nullptr;
     } else if (int rc = launch_prep<50>(a, st)) {
         return rc;
     }
@@ -1731,7 +1810,8 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     // 100x100 learn step on B200; kept because its pieces -- lane-interleaved M = 64 accumulators, the 16x256b epilogue mapping, the
     // 64-column weight-gradient accumulators -- are the starting point of the next restructuring, and covered by the GPU parity tests)
     static const int mode = getenv("LMR_BWD_MODE") ? atoi(getenv("LMR_BWD_MODE")) : 4;
-    const bool single_stream = mode != 2;
+    const bool loadh = keep_act && a.hsave != nullptr;
+    const bool single_stream = mode != 2 || loadh;
     int n_partials = wl.gridMain;
     if (!single_stream) {
         const Tiling tl2 = make_tiling(N, P, D, TP_CAP_TC, b2::R);
@@ -1757,14 +1837,16 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
         TcSmem s(nullptr, nt, tl, NBUF_BWD, false, NG_B);
         const size_t smem = s.bytes + 1024;
         LMR_CHECK_ARG(smem <= 227 * 1024, "inr_backward (tensor-core path): needs %zu bytes of shared memory (> 227 KB)", smem);
-        static size_t cache[2][5] = {};
-#define LMR_BWD_CASE(FASTV, CV)                                                                                  \
-    if (fast == FASTV && nt.C == CV) {                                                                           \
-        if (int rc = set_smem(inr_bwd_tc_kernel<FASTV, CV, NG_B>, smem, &cache[FASTV][CV])) return rc;           \
-        inr_bwd_tc_kernel<FASTV, CV, NG_B><<<wl.gridMain, 128 * NG_B + 32, smem, st>>>(a);                        \
+        static size_t cache[2][2][5] = {};
+#define LMR_BWD_CASE(FASTV, CV, LOADV)                                                                                      \
+    if (fast == FASTV && nt.C == CV && loadh == LOADV) {                                                                    \
+        if (int rc = set_smem(inr_bwd_tc_kernel<FASTV, CV, NG_B, LOADV>, smem, &cache[LOADV][FASTV][CV])) return rc;        \
+        inr_bwd_tc_kernel<FASTV, CV, NG_B, LOADV><<<wl.gridMain, 128 * NG_B + 64, smem, st>>>(a);                            \
     }
-        LMR_BWD_CASE(false, 1) LMR_BWD_CASE(false, 2) LMR_BWD_CASE(false, 3) LMR_BWD_CASE(false, 4)
-        LMR_BWD_CASE(true, 1) LMR_BWD_CASE(true, 2) LMR_BWD_CASE(true, 3) LMR_BWD_CASE(true, 4)
+        LMR_BWD_CASE(false, 1, false) LMR_BWD_CASE(false, 2, false) LMR_BWD_CASE(false, 3, false) LMR_BWD_CASE(false, 4, false)
+        LMR_BWD_CASE(true, 1, false) LMR_BWD_CASE(true, 2, false) LMR_BWD_CASE(true, 3, false) LMR_BWD_CASE(true, 4, false)
+        LMR_BWD_CASE(false, 1, true) LMR_BWD_CASE(false, 2, true) LMR_BWD_CASE(false, 3, true) LMR_BWD_CASE(false, 4, true)
+        LMR_BWD_CASE(true, 1, true) LMR_BWD_CASE(true, 2, true) LMR_BWD_CASE(true, 3, true) LMR_BWD_CASE(true, 4, true)
 #undef LMR_BWD_CASE
         LMR_LAUNCH_OK();
     }
@@ -1816,10 +1898,10 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     return 0;
 }
 
-size_t workspace_bytes(const lmr_inr_desc* desc, int N, int P, int D, bool bwd) {
+size_t workspace_bytes(const lmr_inr_desc* desc, int N, int P, int D, bool bwd, bool keep_act) {
     Net nt;
     if (make_net(desc, &nt)) return 0;
-    return ws_layout(nt, make_tiling(N, P, D, TP_CAP_TC), bwd, true).total;
+    return ws_layout(nt, make_tiling(N, P, D, TP_CAP_TC), bwd, true, keep_act).total;
 }
 
 }  // namespace tc

@@ -11,6 +11,17 @@ from . import _lib
 from . import ops
 
 
+def _keep_activations(precision, workspace_bytes):
+    """Keep the hidden activations' operand tiles between the INR forward and backward of a training step (LMR_PREC_KEEP_ACTIVATIONS)?  Yes on
+    the tensor-core precisions when the enlarged forward workspace stays under LMR_KEEP_ACT_MAX_GIB (default 32 GiB of the 180 GB); the backward then
+    loads the tiles instead of recomputing the forward.  LMR_KEEP_ACT=0 switches it off."""
+    import os
+
+    if os.environ.get("LMR_KEEP_ACT", "1") == "0" or ops.precision_code(precision) == _lib.PREC_FP32:
+        return False
+    return workspace_bytes <= float(os.environ.get("LMR_KEEP_ACT_MAX_GIB", "32")) * 2 ** 30
+
+
 def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -109,7 +120,9 @@ class LearnStepper:
         self.m, self.v = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
         self.step_count = torch.zeros(2, dtype=torch.int32, device=dev)  # [steps taken, ticket scratch]
         d = template._desc
-        self.ws_fwd = _ws(lib.lmr_inr_forward_workspace_bytes(C.byref(d), N, P, 1), dev)
+        # the training forward keeps the operand tiles of the hidden activations for the backward (no recompute): 96 KB per 128-row tile
+        self.keep = _keep_activations(precision, ops.forward_workspace_bytes(d, N, P, 1, True))
+        self.ws_fwd = _ws(ops.forward_workspace_bytes(d, N, P, 1, self.keep), dev)
         self.ws_bwd = _ws(lib.lmr_inr_backward_workspace_bytes(C.byref(d), N, P, 1), dev)
         self.ws_con = _ws(lib.lmr_constrain_workspace_bytes(N, Cc * P), dev)
         self.ws_clr = _ws(lib.lmr_simclr_workspace_bytes(N, Cc, P), dev)
@@ -140,17 +153,17 @@ class LearnStepper:
         r = self.reg_mod
         if self.ws_obj is not None:
             ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, out=self.img_pre.view(1, N, Cc, P),
-                                precision=self.precision, workspace=self.ws_fwd)
+                                precision=self.precision, workspace=self.ws_fwd, keep_activations=self.keep)
             ops.raw_learn_objective(c.mode, self.img_pre, c.target, c.mean, c.pmin, c.pmax, c.eps, self.bank, self.model.eps, self.mei_act, self.mask,
                                     r.flat_neighbor_mask_pos, r.flat_neighbor_mask_neg, r.temperature, r.eps, self.g_reg, self.z, self.act.view(-1),
                                     self.reg, self.loss_buf, self.g_x, self.ws_obj, stats=self.stats, rmax=self.resp.rmax.view(-1),
                                     argmax=self.resp.argmax.view(-1), K=self.K)
             ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, self.g_x.view(1, N, Cc, P), want_params=True,
-                                 precision=self.precision, workspace=self.ws_bwd, g_params=self.g_flat, forward_workspace=self.ws_fwd)
+                                 precision=self.precision, workspace=self.ws_bwd, g_params=self.g_flat, forward_workspace=self.ws_fwd, keep_activations=self.keep)
             ops.raw_adam_step(self.flat, self.g_flat, self.m, self.v, self.step_count, lr=self.lr)
             return
         ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, out=self.img_pre.view(1, N, Cc, P),
-                            precision=self.precision, workspace=self.ws_fwd)
+                            precision=self.precision, workspace=self.ws_fwd, keep_activations=self.keep)
         ops.raw_constrain_fwd(c.mode, self.img_pre, c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.z, stats=self.stats, workspace=self.ws_con)
         # the response (+ its image gradient -> g_z) and the contrastive forward are independent: run them side by side (the response of a
         # 20-image batch occupies a fraction of the SMs), then add the contrastive gradient on top
@@ -164,7 +177,7 @@ class LearnStepper:
         ops.raw_simclr_bwd(self.z, self.mask, self.K, self.g_reg, 1.0, N, Cc, P, self.pixel_min, self.pixel_max, self.g_z, accumulate=True)
         ops.raw_constrain_bwd(c.mode, self.img_pre, self.g_z, self.stats, c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.g_x, workspace=self.ws_con)
         ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, self.g_x.view(1, N, Cc, P), want_params=True,
-                             precision=self.precision, workspace=self.ws_bwd, g_params=self.g_flat, forward_workspace=self.ws_fwd)
+                             precision=self.precision, workspace=self.ws_bwd, g_params=self.g_flat, forward_workspace=self.ws_fwd, keep_activations=self.keep)
         ops.raw_adam_step(self.flat, self.g_flat, self.m, self.v, self.step_count, lr=self.lr)
 
     def _capture(self, fn):
@@ -238,7 +251,8 @@ class MatchStepper:
         self.v = [torch.zeros_like(p) for p in self.params]
         self.steps = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in self.params]
         d = template._desc
-        self.ws_fwd = _ws(lib.lmr_inr_forward_workspace_bytes(C.byref(d), N, P, D), dev)
+        self.keep = _keep_activations(precision, ops.forward_workspace_bytes(d, N, P, D, True))
+        self.ws_fwd = _ws(ops.forward_workspace_bytes(d, N, P, D, self.keep), dev)
         self.ws_bwd = _ws(lib.lmr_inr_backward_workspace_bytes(C.byref(d), N, P, D), dev)
         self.ws_con = _ws(lib.lmr_constrain_workspace_bytes(D * N, Cc * P), dev)
         self.use_graph, self.graph = use_graph, None
@@ -246,10 +260,10 @@ class MatchStepper:
     def _affine(self):
         return self.t.affine_args()
 
-    def _images(self):
+    def _images(self, keep=False):
         t, c, N, D, Cc, P = self.t, self.con, self.N, self.D, self.C, self.P
         ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, self._affine(), out=self.img_pre.view(D, N, Cc, P),
-                            precision=self.precision, workspace=self.ws_fwd)
+                            precision=self.precision, workspace=self.ws_fwd, keep_activations=keep)
         ops.raw_constrain_fwd(c.mode, self.img_pre.view(D * N, Cc, P), c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.z.view(D * N, Cc, P),
                               stats=self.stats, workspace=self.ws_con)
 
@@ -260,13 +274,14 @@ class MatchStepper:
 
     def _train(self):
         t, c, N, D, Cc, P = self.t, self.con, self.N, self.D, self.C, self.P
-        self._images()
+        self._images(keep=self.keep)
         self.resp.forward_backward(self.z, N * Cc * P, N, D, Cc, P, self.nog, self.g_act, self.act, self.g_z, False)
         ops.raw_constrain_bwd(c.mode, self.img_pre.view(D * N, Cc, P), self.g_z.view(D * N, Cc, P), self.stats, c.target, c.mean, c.pmin, c.pmax, c.eps,
                               out=self.g_x.view(D * N, Cc, P), workspace=self.ws_con)
         ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, self._affine(), self.g_x.view(D, N, Cc, P),
                              want_params=False, want_affine=True, precision=self.precision, workspace=self.ws_bwd,
-                             g_affine=(self.grads[0], self.grads[1], self.grads[2], self.grads[3].view(D, 2)), forward_workspace=self.ws_fwd)
+                             g_affine=(self.grads[0], self.grads[1], self.grads[2], self.grads[3].view(D, 2)), forward_workspace=self.ws_fwd,
+                             keep_activations=self.keep)
         for p, g, m, v, s, tr in zip(self.params, self.grads, self.m, self.v, self.steps, self.trainable):
             if tr:
                 ops.raw_adam_step(p.data, g, m, v, s, lr=self.lr)

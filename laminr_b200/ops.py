@@ -89,28 +89,39 @@ def make_desc(hidden, n_hidden, pe_dim, aux_pe_dim, channels):
     return InrDesc(int(hidden), int(n_hidden), int(pe_dim), int(aux_pe_dim), int(channels))
 
 
-def raw_inr_forward(desc, params, B, auxB, grid, coords, coord_shift, affine, out=None, precision=None, workspace=None):
-    """-> img [D, N, C, P] (float32).  params: flat parameter vector (see header); grid [N]; coords [P,2]."""
+def forward_workspace_bytes(desc, N, P, D, keep_activations=False):
+    lib = _lib.load()
+    fn = lib.lmr_inr_forward_workspace_bytes_keep if keep_activations else lib.lmr_inr_forward_workspace_bytes
+    return int(fn(C.byref(desc), N, P, D))
+
+
+def raw_inr_forward(desc, params, B, auxB, grid, coords, coord_shift, affine, out=None, precision=None, workspace=None, keep_activations=False):
+    """-> img [D, N, C, P] (float32).  params: flat parameter vector (see header); grid [N]; coords [P,2].
+    keep_activations (tensor-core precisions): the forward keeps the operand tiles of the hidden activations in `workspace` (size:
+    forward_workspace_bytes(..., keep_activations=True)) for a raw_inr_backward(..., forward_workspace=workspace, keep_activations=True)."""
     lib = _lib.load()
     _require_cuda(params, B, auxB, grid, coords)
     N, P = grid.numel(), coords.shape[0]
     D = 1 if affine is None else affine.D
     if out is None:
         out = torch.empty((D, N, desc.channels, P), dtype=torch.float32, device=params.device)
+    prec = precision_code(precision)
+    keep = bool(keep_activations) and prec != _lib.PREC_FP32
     if workspace is None:
-        workspace = _workspace(lib.lmr_inr_forward_workspace_bytes(C.byref(desc), N, P, D), params.device)
+        workspace = _workspace(forward_workspace_bytes(desc, N, P, D, keep), params.device)
     aff = affine.struct() if affine is not None else None
     check(lib.lmr_inr_forward(
         C.byref(desc), _ptr(params), _ptr(B), _ptr(auxB), _ptr(grid), N, _ptr(coords), P, _ptr(coord_shift),
-        C.byref(aff) if aff is not None else None, D, _ptr(out), _ptr(workspace), workspace.numel(), precision_code(precision), _stream(),
+        C.byref(aff) if aff is not None else None, D, _ptr(out), _ptr(workspace), workspace.numel(), prec | (_lib.PREC_KEEP_ACTIVATIONS if keep else 0), _stream(),
     ))
     return out
 
 
 def raw_inr_backward(desc, params, B, auxB, grid, coords, coord_shift, affine, g_img, want_params=True, want_affine=False,
-                     precision=None, workspace=None, g_params=None, g_affine=None, forward_workspace=None):
+                     precision=None, workspace=None, g_params=None, g_affine=None, forward_workspace=None, keep_activations=False):
     """-> (g_params flat | None, (g_angles, g_scalings, g_shears, g_translation) | None).
-    forward_workspace: workspace of the raw_inr_forward call on the same inputs (its per-step tables are reused: one launch less)."""
+    forward_workspace: workspace of the raw_inr_forward call on the same inputs (its per-step tables are reused: one launch less);
+    keep_activations: that forward call kept the hidden activations' operand tiles there (no recompute in the backward)."""
     lib = _lib.load()
     _require_cuda(params, g_img)
     N, P = grid.numel(), coords.shape[0]
@@ -129,7 +140,10 @@ def raw_inr_backward(desc, params, B, auxB, grid, coords, coord_shift, affine, g
               C.byref(aff) if aff is not None else None, D, _ptr(_f32c(g_img)), _ptr(g_params if want_params else None),
               _ptr(ga[0]), _ptr(ga[1]), _ptr(ga[2]), _ptr(ga[3]), _ptr(workspace), workspace.numel())
     if forward_workspace is not None:
-        check(lib.lmr_inr_backward_after_forward(*common, _ptr(forward_workspace), forward_workspace.numel(), precision_code(precision), _stream()))
+        prec = precision_code(precision)
+        keep = bool(keep_activations) and prec != _lib.PREC_FP32
+        check(lib.lmr_inr_backward_after_forward(*common, _ptr(forward_workspace), forward_workspace.numel(), prec | (_lib.PREC_KEEP_ACTIVATIONS if keep else 0),
+                                                 _stream()))
     else:
         check(lib.lmr_inr_backward(*common, precision_code(precision), _stream()))
     return (g_params if want_params else None), (g_affine if want_affine else None)

@@ -117,6 +117,61 @@ def test_tc_learn_trajectory(ops, mode):
         assert relerr(dW[l], d[f"final_W{l}"]) < 1e-2, (l, relerr(dW[l], d[f"final_W{l}"]))
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_tc_kept_activations_backward(ops, mode):
+    """LMR_PREC_KEEP_ACTIVATIONS: the forward keeps the operand tiles of h_1..h_3 in its workspace and the backward loads them (bulk async copies)
+    instead of recomputing the forward.  Same gradients as the recompute path and as the reference: learn (D = 1, weight gradients, 1 and 2
+    channels, several tiles per CTA) and match (D = 2, affine gradients, with and without weight gradients)."""
+    for name, res, C in (("inr_12x10", (12, 10), 1), ("inr_9x16_c2", (9, 16), 2)):
+        d = golden(name)
+        desc = desc_for(ops, d, C)
+        args = (desc, dev(flat_params(d)), dev(d["B"]), dev(d["auxB"]), dev(d["grid"]), dev(d["coords"]), None, None)
+        N, P = len(d["grid"]), res[0] * res[1]
+        ws = torch.empty(ops.forward_workspace_bytes(desc, N, P, 1, True), dtype=torch.uint8, device="cuda")
+        img = ops.raw_inr_forward(*args, precision=mode, workspace=ws, keep_activations=True)
+        assert relerr(img.cpu().numpy().reshape(N, C, *res), d["out"]) < IMG_TOL[mode]
+        up = dev(d["upstream"]).reshape(1, N, C, -1)
+        g_keep, _ = ops.raw_inr_backward(*args, up, precision=mode, forward_workspace=ws, keep_activations=True)
+        g_rec, _ = ops.raw_inr_backward(*args, up, precision=mode)
+        assert relerr(g_keep.cpu().numpy(), g_rec.cpu().numpy()) < 1e-5
+        gw, gb = split_flat(g_keep.cpu().numpy(), d)
+        for l in range(5):
+            assert relerr(gw[l], d[f"dW{l}"]) < GRAD_TOL[mode] and relerr(gb[l], d[f"db{l}"]) < GRAD_TOL[mode], l
+    # a bigger image set: 45 x 41 pixels x 20 latents = 308 tiles (2-3 per CTA: the rolling prefetch of the next tile's activations is exercised)
+    d = golden("inr_12x10")
+    rng = np.random.RandomState(11)
+    res = (45, 41)
+    yy, xx = np.meshgrid(np.linspace(-1, 1, res[0]), np.linspace(-1, 1, res[1]), indexing="ij")
+    coords = dev(np.stack([yy, xx], -1).reshape(-1, 2).astype(np.float32))
+    grid = dev(np.linspace(0.1, 6.2, 20).astype(np.float32))
+    desc = desc_for(ops, d, 1)
+    args = (desc, dev(flat_params(d)), dev(d["B"]), dev(d["auxB"]), grid, coords, None, None)
+    P = res[0] * res[1]
+    ws = torch.empty(ops.forward_workspace_bytes(desc, 20, P, 1, True), dtype=torch.uint8, device="cuda")
+    up = dev(rng.randn(1, 20, 1, P).astype(np.float32))
+    for _ in range(2):  # twice on the same workspace
+        img_k = ops.raw_inr_forward(*args, precision=mode, workspace=ws, keep_activations=True)
+        g_keep, _ = ops.raw_inr_backward(*args, up, precision=mode, forward_workspace=ws, keep_activations=True)
+    img_r = ops.raw_inr_forward(*args, precision=mode)
+    g_rec, _ = ops.raw_inr_backward(*args, up, precision=mode)
+    assert torch.equal(img_k, img_r) and relerr(g_keep.cpu().numpy(), g_rec.cpu().numpy()) < 1e-5
+    # match: two targets with an affine transform
+    d = golden("match_inr_14x14")
+    aff = ops.AffineArgs(dev(d["angles"]), dev(d["scalings"]), dev(d["shears"]), dev(d["translation"]), tc=dev(d["tc"]), shift_to=dev(d["shift_to"]),
+                         shift_from=dev(d["shift_from"]), clamp=True)
+    desc = desc_for(ops, d, 1)
+    args = (desc, dev(flat_params(d)), dev(d["B"]), dev(d["auxB"]), dev(d["grid"]), dev(d["coords"]), None, aff)
+    D, N = d["out"].shape[:2]
+    ws = torch.empty(ops.forward_workspace_bytes(desc, N, d["coords"].shape[0], D, True), dtype=torch.uint8, device="cuda")
+    img = ops.raw_inr_forward(*args, precision=mode, workspace=ws, keep_activations=True)
+    assert relerr(img.cpu().numpy().reshape(d["out"].shape), d["out"]) < IMG_TOL[mode]
+    up = dev(d["upstream"]).reshape(D, N, 1, -1)
+    for want_params in (True, False):
+        _, g_aff = ops.raw_inr_backward(*args, up, want_params=want_params, want_affine=True, precision=mode, forward_workspace=ws, keep_activations=True)
+        for got, key in zip(g_aff, ("d_angles", "d_scalings", "d_shears", "d_translation")):
+            assert relerr(got.cpu().numpy().reshape(d[key].shape), d[key]) < GRAD_TOL[mode], key
+
+
 def test_two_stream_backward_variant_parity():
     """The two-stream 64-row backward kernel (development switch LMR_BWD_MODE=2, csrc/inr_tc.cu inr_bwd2_kernel) passes the same parity tests as the
     default one-stream kernel.  The switch is read once per process, so the tests of this file are re-run in a child process."""
