@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_LATENTS = 20
+TRAFFIC_BWD_KEEP = 164783360 + 4096768  # dram read + write of inr_bwd_tc_kernel with kept activations (profiles/r1e_ncu_inr_keep.md)
 
 
 def algorithmic_flops(res, N=N_LATENTS, h=50, pe=50, C=1):
@@ -382,25 +383,36 @@ def run_ours(args):
     from laminr_b200 import ops
     t = im.template
     gx = stepper.g_x.view(1, N_LATENTS, 1, res * res)
+    keep = bool(getattr(stepper, "keep", False))  # as in the step: the forward keeps the hidden activations' operand tiles, the backward loads them
     def bwd_only():
         ops.raw_inr_backward(t._desc, stepper.flat, t.B, t.auxB, stepper.grid, stepper.coords, None, None, gx, want_params=True,
-                             precision=args.precision, workspace=stepper.ws_bwd, g_params=stepper.g_flat)
+                             precision=args.precision, workspace=stepper.ws_bwd, g_params=stepper.g_flat,
+                             forward_workspace=stepper.ws_fwd if keep else None, keep_activations=keep)
     def fwd_only():
         ops.raw_inr_forward(t._desc, stepper.flat, t.B, t.auxB, stepper.grid, stepper.coords, None, None, out=stepper.img_pre.view(1, N_LATENTS, 1, res * res),
-                            precision=args.precision, workspace=stepper.ws_fwd)
+                            precision=args.precision, workspace=stepper.ws_fwd, keep_activations=keep)
+    fwd_only()  # the backward below reads this forward's workspace
     def time_fn(fn, reps=30):
         for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        # the launch group is replayed from a CUDA graph, as in the step: an eager replay from Python would time the host's launch calls
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
             fn()
         torch.cuda.synchronize()
         tot = 0.0
         for r in range(reps):
             flush.fill_(float(r))
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); fn(); b.record()
+            a.record(); g.replay(); b.record()
             torch.cuda.synchronize()
             tot += a.elapsed_time(b)
         return tot / reps
-    bwd_ms, fwd_ms = time_fn(bwd_only), time_fn(fwd_only)
+    fwd_ms = time_fn(fwd_only)
+    bwd_ms = time_fn(bwd_only)
 
     # ---- match hot step (extra): targets sharded over ranks, weak scaling (fixed targets per GPU)
     match = None
@@ -518,9 +530,11 @@ def run_ours(args):
             "gpu_launches": int(stepper.kernels_per_step * K),
             "roofline": {"bound": "tensor", "kernel": "lmr_inr_backward launch group (inr_bwd_tc_kernel dominant; + layer-0 weight gradient and partial reduction launches)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of inr_bwd_tc_kernel, one `ncu --set full` capture of this workload
-                         # (profiles/r1b_ncu_inr_bwd_tc.md: 2.995 MB read, 0 written -- inputs and the 0.8 MB gradient image are L2-resident)
-                         "traffic": 2995456 if (res == 100 and args.precision != "fp32") else None, "traffic_unit": "bytes per launch (ncu, DRAM)",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of inr_bwd_tc_kernel, one `ncu --set full` capture of this workload:
+                         # recompute variant 2.995 MB (profiles/r1b_ncu_inr_bwd_tc.md); kept-activation variant: the 160 MB of operand tiles it loads
+                         # (profiles/r1e_ncu_inr_keep.md)
+                         "traffic": (TRAFFIC_BWD_KEEP if keep else 2995456) if (res == 100 and args.precision != "fp32") else None,
+                         "traffic_unit": "bytes per launch (ncu, DRAM)", "kept_activations": keep,
                          "peak_source": "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback",
                          "algorithmic_gflop": bwd_f / 1e9, "ms": bwd_ms, "forward": {"algorithmic_gflop": fwd_f / 1e9, "ms": fwd_ms, "achieved": fwd_f / (fwd_ms * 1e-3) / 1e12}},
             "cpu_baseline": cpu, "clocks": clocks, "match": match, "conv": conv,

@@ -243,6 +243,14 @@ int lmr_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, i
                   float beta2, float eps, int* step, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Match epoch statistics -- replaces the host-driven reductions of the match loop (inv_temp_learn_match.py:361-362:
+ * acts_d = mean_n act[d,n,d] / mei_act_d; :368-371: their mean / min / max for the stop rule and the progress bar).
+ * act: [D,N], mei_act: [D]  ->  out3 = {sum_d acts_d, min_d acts_d, max_d acts_d} (the caller divides the sum by the
+ * GLOBAL number of targets, which differs from D when the targets are sharded over GPUs).
+ * ---------------------------------------------------------------------------------------------------------- */
+int lmr_match_epoch_stats(const float* act, const float* mei_act, int D, int N, float* out3, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * MEI gradient ascent -- replaces featurevis.gradient_ascent with SGD (featurevis/core.py:54-136) driven as in
  * generate_mei (laminr/utils/mei.py:33-59), batched over G neurons (the reference loops neurons sequentially,
  * mei.py:98-119):   x <- post(x + step_size * d act/dx),  post = ChangeNorm|ChangeStats -> ClipRange (eps 1e-9).

@@ -435,6 +435,34 @@ __global__ void __launch_bounds__(256) adam_ticket_kernel(float* __restrict__ p,
 }
 
 // ===============================================================================================================
+// match epoch statistics (laminr/inv_temp_learn_match.py:361-362,368-371): acts_d = mean_n act[d,n] / a*_d -> (sum_d, min_d, max_d).
+// One CTA; fixed summation order (deterministic).  Lets the stop rule read 12 bytes instead of driving five reductions from the host.
+// ===============================================================================================================
+__global__ void __launch_bounds__(256) match_stats_kernel(const float* __restrict__ act, const float* __restrict__ mei_act, int D, int N,
+                                                          float* __restrict__ out) {
+    __shared__ float ssum[256], smin[256], smax[256];
+    float s = 0.f, lo = INFINITY, hi = -INFINITY;
+    const float inv = 1.f / (float)N;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float a = 0.f;
+        for (int n = 0; n < N; ++n) a += act[(size_t)d * N + n];
+        a = a * inv / mei_act[d];
+        s += a, lo = fminf(lo, a), hi = fmaxf(hi, a);
+    }
+    ssum[threadIdx.x] = s, smin[threadIdx.x] = lo, smax[threadIdx.x] = hi;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) {
+            ssum[threadIdx.x] += ssum[threadIdx.x + w];
+            smin[threadIdx.x] = fminf(smin[threadIdx.x], smin[threadIdx.x + w]);
+            smax[threadIdx.x] = fmaxf(smax[threadIdx.x], smax[threadIdx.x + w]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = ssum[0], out[1] = smin[0], out[2] = smax[0];
+}
+
+// ===============================================================================================================
 // Batched MEI gradient ascent (reference featurevis/core.py:54-136 with SGD, laminr/utils/mei.py:33-59)
 // One CTA per neuron; the image lives in shared memory for all iterations; filters stream from L2/HBM.
 // ===============================================================================================================
@@ -722,6 +750,13 @@ extern "C" int lmr_simclr_bwd(const float* img, const float* mask, const float* 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int n = C * HW;
     simclr_bwd_kernel<<<(n + 127) / 128, 128, (size_t)N * N * sizeof(float), st>>>(img, mask, K, g_reg, scale, N, C, HW, c0, g1, g2, g_img, accumulate);
+    LMR_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int lmr_match_epoch_stats(const float* act, const float* mei_act, int D, int N, float* out3, void* stream) {
+    LMR_CHECK_ARG(act && mei_act && out3 && D >= 1 && N >= 1, "match_epoch_stats: bad arguments");
+    match_stats_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(act, mei_act, D, N, out3);
     LMR_LAUNCH_OK();
     return 0;
 }

@@ -256,6 +256,10 @@ class MatchStepper:
         self.ws_bwd = _ws(lib.lmr_inr_backward_workspace_bytes(C.byref(d), N, P, D), dev)
         self.ws_con = _ws(lib.lmr_constrain_workspace_bytes(D * N, Cc * P), dev)
         self.use_graph, self.graph = use_graph, None
+        # (sum, min, max) over the local targets of acts_d = mean_n act[d,n] / a*_d, written by the last launch of every step; the stop rule of the
+        # match loop reads these 12 bytes through a pinned buffer (one small copy + one stream synchronisation per epoch)
+        self.epoch = torch.zeros(3, **f32)
+        self.epoch_host = torch.zeros(3, dtype=torch.float32).pin_memory()
 
     def _affine(self):
         return self.t.affine_args()
@@ -285,6 +289,13 @@ class MatchStepper:
         for p, g, m, v, s, tr in zip(self.params, self.grads, self.m, self.v, self.steps, self.trainable):
             if tr:
                 ops.raw_adam_step(p.data, g, m, v, s, lr=self.lr)
+        ops.raw_match_epoch_stats(self.act, self.mei_acts, self.epoch)
+
+    def epoch_stats(self):
+        """(sum_d, min_d, max_d) of the last step's normalised activations acts_d (inv_temp_learn_match.py:362,368-371) as host floats."""
+        self.epoch_host.copy_(self.epoch, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return tuple(self.epoch_host.tolist())
 
     def step(self, grid_row):
         self.grid.copy_(grid_row.reshape(-1), non_blocking=True)

@@ -245,7 +245,6 @@ class InvarianceManifold:
                 input_grid = input_grid.to(device)
                 if fused:
                     stepper.step(input_grid)
-                    acts = stepper.normalised_acts()
                 else:
                     _, _, _acts, _ = self.forward(input_grid, template, self.img_transforms, self.response_predicting_model, return_template=False,
                                                   other_neurons_loc_in_list=loc_in_list, other_neurons_loc_in_model=loc_in_model)
@@ -257,7 +256,10 @@ class InvarianceManifold:
                     optimizer.step()
                 self.match_steps_taken += 1
 
-            a_sum, a_min, a_max = torch.stack([acts.sum(), acts.min(), acts.max()]).tolist()
+            if fused:  # written by the step's last launch (lmr_match_epoch_stats): 12 bytes, one synchronisation per epoch
+                a_sum, a_min, a_max = stepper.epoch_stats()
+            else:
+                a_sum, a_min, a_max = torch.stack([acts.sum(), acts.min(), acts.max()]).tolist()
             if _stop_reduce is not None:
                 a_sum, a_min, a_max = _stop_reduce(a_sum, a_min, a_max)
             a_mean = a_sum / d_total
@@ -377,6 +379,9 @@ class InvarianceManifold:
         desc = ("Finding best angle and translation for initalization" if find_best_translation and rotate_angle_and_scale else
                 "Finding best translation for initalization" if find_best_translation else "Finding best angle for initalization")
         table = np.zeros((len(angles), len(translations), len(translations), n))
+        # fused path: the candidates' mean activations stay on the device and come back in ONE copy after the sweep (the reference reads them
+        # back candidate by candidate, :641: 60 -- or 7,260 -- host synchronisations that leave the GPU idle between candidates)
+        dev_table = torch.empty(table.shape, dtype=torch.float32, device=device) if _stepper is not None else None
         with torch.no_grad():
             input_grid = grid_dataloader.grid.to(device)
             if rotate_angle_and_scale:
@@ -389,13 +394,16 @@ class InvarianceManifold:
                             aff.translation.data[:, 0, 0] = float(tx)
                             aff.translation.data[:, 0, 1] = float(ty)
                         if _stepper is not None:
-                            rel = _stepper.evaluate(input_grid).mean(dim=1)
+                            torch.mean(_stepper.evaluate(input_grid), dim=1, out=dev_table[i, j, k])
+                            continue
                         else:
                             _, _, _acts, _ = self.forward(input_grid, template, img_transforms, encoding_model, return_template=False,
                                                           other_neurons_loc_in_list=other_neurons_loc_in_list,
                                                           other_neurons_loc_in_model=other_neurons_loc_in_model)
                             rel = _acts[range(n), :, range(n)].mean(dim=1)
                         table[i, j, k, :] = rel.cpu().numpy()
+        if dev_table is not None:
+            table[...] = dev_table.cpu().numpy()
         best = np.argmax(table.reshape(-1, n), axis=0)
         bi, bj, bk = np.unravel_index(best, table.shape[:3])
         aff.angles.data.copy_(torch.from_numpy(angles[bi]).to(device))

@@ -488,6 +488,14 @@ def raw_adam_step(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
     check(lib.lmr_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(b1), float(b2), float(eps), _ptr(step), _stream()))
 
 
+def raw_match_epoch_stats(act, mei_act, out3):
+    """act [D,N], mei_act [D] -> out3 = (sum_d, min_d, max_d) of acts_d = mean_n act[d,n] / mei_act[d] (inv_temp_learn_match.py:361-371)."""
+    lib = _lib.load()
+    _require_cuda(act, mei_act, out3)
+    D, N = act.shape
+    check(lib.lmr_match_epoch_stats(_ptr(act), _ptr(mei_act), int(D), int(N), _ptr(out3), _stream()))
+
+
 def raw_mei_ascent(x, filters, nfilt, neuron_of_group, step_size, iters, mode, target, mean, pmin, pmax, act_eps=1e-6, apply_post_first=True):
     """x [G,C,H,W] in/out -> fevals [G, iters+1]."""
     lib = _lib.load()
