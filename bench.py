@@ -300,6 +300,51 @@ def bench_conv(args, dev, world, rank, barrier, flush):
     return out
 
 
+def cpu_mei(res, iters=200):
+    """CPU port of the MEI gradient ascent (featurevis/core.py:54-136 as driven by laminr/utils/mei.py:33-59) for ONE neuron (the reference loops
+    over neurons): numpy oracle, `iters` of the 1000 iterations timed and extrapolated."""
+    from oracle import laminr_oracle as O
+
+    bank = O.demo1_banks([res, res])[0]
+    x0 = np.random.RandomState(0).randn(1, 1, res, res).astype(np.float32)
+    O.mei_ascent(x0, bank, 10.0, 5, -1.0, 1.0, norm=1.0)
+    t0 = time.perf_counter()
+    O.mei_ascent(x0, bank, 10.0, iters, -1.0, 1.0, norm=1.0)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / (dt * 1000 / iters), "unit": "MEIs/s", "cores": 1, "kind": "port",
+            "sample": f"{iters} of 1000 ascent iterations of one demo1 neuron @{res}x{res} ({dt:.2f} s, extrapolated), numpy oracle"}
+
+
+def cpu_match_steps(res, n_steps, warmup, threads):
+    """CPU port of the match hot step (inv_temp_learn_match.py:352-365) for demo1 targets [1, 2]: the numpy oracle (BLAS threads), a bounded sample."""
+    from oracle import laminr_oracle as O
+
+    h, pe, ape, D = 50, 50, 50, 2
+    W = [np.random.RandomState(1).randn(h, 1 + 2 * ape + 2 * pe).astype(np.float32) * 0.1] + \
+        [np.random.RandomState(2 + l).randn(h, h).astype(np.float32) * 0.1 for l in range(3)] + [np.random.RandomState(9).randn(1, h).astype(np.float32) * 0.1]
+    b = [np.zeros(w.shape[0], np.float32) for w in W]
+    B = np.random.RandomState(10).randn(2, pe).astype(np.float32) * 10
+    auxB = np.random.RandomState(11).randn(2, ape).astype(np.float32) * 0.1
+    banks = O.demo1_banks([res, res])[1:3]
+    meis = synthetic_meis(res)
+    xy = lambda i: np.array([meis[i]["center_pos"]["x"], meis[i]["center_pos"]["y"]], np.float32)
+    shifts = O.coords_shifts(xy(0), np.stack([xy(1), xy(2)]), (res, res))
+    rs = np.random.RandomState(0)
+    aff = dict(angles=rs.uniform(0, 2 * np.pi, D).astype(np.float32), scalings=np.ones((D, 2), np.float32), shears=np.zeros((D, 2), np.float32),
+               translation=np.zeros((D, 2), np.float32))
+    grid = O.latent_grid(N_LATENTS)
+    coords = O.pixel_coords((res, res))
+    run = lambda: O.match_step(W, b, B, auxB, grid, coords, (res, res), banks, np.ones(D, np.float32), aff, shifts, 1.0, -1.0, 1.0)
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        run()
+    dt = time.perf_counter() - t0
+    return {"value": D * n_steps / dt, "unit": "target-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{n_steps} match steps of demo1 targets [1, 2] @{res}x{res} ({dt:.1f} s), numpy oracle (BLAS threads)"}
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
@@ -491,8 +536,36 @@ def run_ours(args):
             match["mei"] = {"metric": "MEIs/sec (1000 ascent iterations each, batched)", "value": nmei * world / (mt3.item() / 1e3), "unit": "MEIs/s",
                             "neurons_per_gpu": nmei, "ms": mt3.item(), "final_activation_mean": float(fev[:, -1].mean().item()),
                             "algorithmic_GBps_per_gpu": mei_bytes / (mt3.item() / 1e3) / 1e9,
+                            "cpu_baseline": cpu_mei(res) if (world == 1 and not args.no_cpu_baseline) else None,
                             "note": "the per-GPU filter bank (neurons x 20 x HW x 4 B) is re-read every iteration; at 128 neurons x 100x100 it is 102 MB and mostly "
                                     "L2-resident (126 MB L2), so the algorithmic rate can exceed the HBM copy peak"}
+
+    # ---- BASELINE configs[1] (extra, N == 1): demo1 match stage, template 0 -> targets [1, 2] at res x res on one B200, whole match() call
+    if match is not None and world == 1:
+        import contextlib, io
+        im.template_neuron_idx = 0
+        ep2 = 100
+        with contextlib.redirect_stderr(io.StringIO()):
+            im.match([1, 2], num_epochs=3, patience=10 ** 9)  # warm-up: allocations, graph capture
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            imgs2, _ = im.match([1, 2], num_epochs=ep2, patience=10 ** 9)
+            torch.cuda.synchronize()
+            dt2 = time.perf_counter() - t0
+            ms2 = im._match_stepper
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(50):
+                ms2.step(grids[Wm + (i % K)])
+            b.record()
+            torch.cuda.synchronize()
+        match["config2"] = {"workload": f"BASELINE configs[1]: demo1, template 0 -> targets [1, 2], {res}x{res}, 1 GPU",
+                            "aligned": {"value": 2 / dt2, "unit": "neurons/s", "seconds": dt2, "epochs": int(im.match_epochs_run),
+                                        "note": "whole match(): 60-angle sweep + a fixed number of epochs (early stop disabled) + result copy to the host",
+                                        "result_shape": list(imgs2.shape)},
+                            "step": {"value": 2 * 50 / (a.elapsed_time(b) / 1e3), "unit": "target-steps/s", "ms_per_step": a.elapsed_time(b) / 50}}
+        if not args.no_cpu_baseline:
+            match["config2"]["cpu_baseline"] = cpu_match_steps(res, 2, 1, os.cpu_count() or 1)
 
     # ---- BASELINE config 4 (extra): conv-core encoder at 200x200
     conv = bench_conv(args, dev, world, rank, barrier, flush) if args.conv_res > 0 else None

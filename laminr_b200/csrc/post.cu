@@ -178,21 +178,22 @@ constexpr int RIB = 8;    // images per register block
 // Rpart[g][s][b][f] = sum_{p in chunk s} (sum_c img[g,b,c,p]) * w[f][p]
 __global__ void __launch_bounds__(256) simresp_partial_kernel(const float* __restrict__ img, long long gstride, int NB, int C, int HW,
                                                               const float* __restrict__ filters, int Fmax, const int* __restrict__ nfilt,
-                                                              const int* __restrict__ neuron_of_group, float* __restrict__ Rpart) {
+                                                              const int* __restrict__ neuron_of_group, float* __restrict__ Rpart, int rch /* pixels per CTA, <= RCH */) {
     __shared__ float xs[RIB][RCH];
     const int s = blockIdx.x, S = gridDim.x, g = blockIdx.y;
     const int neuron = neuron_of_group[g];
     const int F = nfilt[neuron];
     const float* bank = filters + (size_t)neuron * Fmax * HW;
     const float* gimg = img + (size_t)g * gstride;
-    const int p0 = s * RCH, np = min(RCH, HW - p0);
+    const int p0 = s * rch, np = min(rch, HW - p0);
+    const int rsh = 31 - __clz(rch);  // rch is a power of two
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* out = Rpart + ((size_t)g * S + s) * NB * Fmax;
     for (int b0 = 0; b0 < NB; b0 += RIB) {
         const int nb = min(RIB, NB - b0);
         __syncthreads();
-        for (int i = threadIdx.x; i < RIB * RCH; i += 256) {
-            const int bb = i / RCH, p = i % RCH;
+        for (int i = threadIdx.x; i < RIB * rch; i += 256) {
+            const int bb = i >> rsh, p = i & (rch - 1);
             float v = 0.f;
             if (bb < nb && p < np) {
                 const float* src = gimg + ((size_t)(b0 + bb) * C) * HW + p0 + p;
@@ -219,24 +220,41 @@ __global__ void __launch_bounds__(256) simresp_partial_kernel(const float* __res
     }
 }
 
-__global__ void simresp_finalize_kernel(const float* __restrict__ Rpart, int S, int NB, int G, int Fmax, const int* __restrict__ nfilt,
-                                        const int* __restrict__ neuron_of_group, float eps, float* __restrict__ act, float* __restrict__ rmax,
-                                        int* __restrict__ argmax) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= G * NB) return;
+// one warp per (group, image): lanes own the filters f = lane, lane + 32, ..; each sums its filter's chunk partials in chunk order (deterministic),
+// then the warp takes the maximum with the lowest filter index on ties (torch.max returns the first maximum)
+__global__ void __launch_bounds__(128) simresp_finalize_kernel(const float* __restrict__ Rpart, int S, int NB, int G, int Fmax, const int* __restrict__ nfilt,
+                                                               const int* __restrict__ neuron_of_group, float eps, float* __restrict__ act,
+                                                               float* __restrict__ rmax, int* __restrict__ argmax) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= G * NB) return;  // whole warps leave together
     const int g = i / NB, b = i % NB;
     const int F = nfilt[neuron_of_group[g]];
     float best = -INFINITY;
-    int bi = 0;
-    for (int f = 0; f < F; ++f) {
-        float r = 0.f;
-        for (int s = 0; s < S; ++s) r += Rpart[(((size_t)g * S + s) * NB + b) * Fmax + f];
-        if (r > best) best = r, bi = f;  // strict: first maximum wins (torch.max)
+    int bi = 0x7fffffff;
+    for (int f = lane; f < F; f += 32) {
+        const float* src = Rpart + (((size_t)g * S) * NB + b) * Fmax + f;
+        float r4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains (the loads are L2 round trips), combined in a fixed order
+        int sidx = 0;
+        for (; sidx + 4 <= S; sidx += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) r4[u] += src[(size_t)(sidx + u) * NB * Fmax];
+        }
+        for (int u = 0; sidx < S; ++sidx, ++u) r4[u] += src[(size_t)sidx * NB * Fmax];
+        const float r = (r4[0] + r4[1]) + (r4[2] + r4[3]);
+        if (r > best) best = r, bi = f;  // strict: the lane's first maximum
     }
-    rmax[i] = best;
-    argmax[i] = bi;
-    const float e = best > 0.f ? best : expm1f(best);
-    act[i] = (e + 1.f) / 2.f + eps;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) best = ob, bi = oi;
+    }
+    if (lane == 0) {
+        rmax[i] = best;
+        argmax[i] = bi;
+        const float e = best > 0.f ? best : expm1f(best);
+        act[i] = (e + 1.f) / 2.f + eps;
+    }
 }
 
 // g_img[g,b,c,p] (+)= g_act * 1/2 * elu'(m) * w_{f*}[p]
@@ -678,8 +696,17 @@ extern "C" int lmr_constrain_bwd(int mode, const float* x, const float* g_z, con
     return 0;
 }
 
+// pixels per CTA of the response partials: 512 when the groups alone fill the machine, down to 128 for few groups (match with a handful of
+// targets, the learn step's single neuron) so that about two CTAs per SM exist.  A pure function of (G, HW): the workspace size follows from it.
+static inline int simresp_chunk(int G, int HW) {
+    int rch = RCH;
+    while (rch > RCH / 4 && (long long)G * ((HW + rch - 1) / rch) < 2 * 148) rch >>= 1;
+    return rch;
+}
+
 extern "C" size_t lmr_simresp_workspace_bytes(int G, int NB, int Fmax, int HW) {
-    const int S = (HW + RCH - 1) / RCH;
+    const int rch = simresp_chunk(G, HW);
+    const int S = (HW + rch - 1) / rch;
     return (size_t)G * S * NB * Fmax * sizeof(float);
 }
 
@@ -692,11 +719,12 @@ extern "C" int lmr_simresp_fwd(const float* img, long long gstride, int NB, int 
         set_error("simresp_fwd: workspace too small");
         return LMR_ERR_WORKSPACE;
     }
-    const int S = (HW + RCH - 1) / RCH;
+    const int rch = simresp_chunk(G, HW);
+    const int S = (HW + rch - 1) / rch;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    simresp_partial_kernel<<<dim3(S, G), 256, 0, st>>>(img, gstride, NB, C, HW, filters, Fmax, nfilt, neuron_of_group, static_cast<float*>(ws));
+    simresp_partial_kernel<<<dim3(S, G), 256, 0, st>>>(img, gstride, NB, C, HW, filters, Fmax, nfilt, neuron_of_group, static_cast<float*>(ws), rch);
     LMR_LAUNCH_OK();
-    simresp_finalize_kernel<<<(G * NB + 127) / 128, 128, 0, st>>>(static_cast<const float*>(ws), S, NB, G, Fmax, nfilt, neuron_of_group, eps, act, rmax,
+    simresp_finalize_kernel<<<(G * NB + 3) / 4, 128, 0, st>>>(static_cast<const float*>(ws), S, NB, G, Fmax, nfilt, neuron_of_group, eps, act, rmax,
                                                                    argmax);
     LMR_LAUNCH_OK();
     return 0;

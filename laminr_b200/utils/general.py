@@ -20,8 +20,8 @@ class SingleNeuronModel(nn.Module):
 
 
 def infer_device(module):
-    for param in module.parameters():
-        return param.device
-    for buffer in module.buffers():
-        return buffer.device
-    return torch.device("cpu")
+    """Device of the module's first parameter, else of its first buffer, else the CPU (general.py:15-20)."""
+    import itertools
+
+    first = next(itertools.chain(module.parameters(), module.buffers()), None)
+    return torch.device("cpu") if first is None else first.device

@@ -179,6 +179,19 @@ def test_adam_golden(ops):
     assert step.tolist() == [5, 0]
 
 
+@pytest.mark.parametrize("D,N", [(1, 20), (2, 20), (37, 7), (1024, 20)])
+def test_match_epoch_stats_vs_host_reductions(ops, D, N):
+    """lmr_match_epoch_stats == the reference's host-driven reductions of the match loop (inv_temp_learn_match.py:361-362,368-371):
+    acts_d = mean_n act[d,n] / mei_act_d, then their sum / min / max (float64 on the host as the yardstick)."""
+    rs = np.random.RandomState(D + N)
+    act = rs.rand(D, N).astype(np.float32) + 0.05
+    mei = (0.5 + rs.rand(D)).astype(np.float32)
+    out = torch.empty(3, device="cuda")
+    ops.raw_match_epoch_stats(dev(act), dev(mei), out)
+    a = act.astype(np.float64).mean(axis=1) / mei
+    np.testing.assert_allclose(out.cpu().numpy(), [a.sum(), a.min(), a.max()], rtol=2e-6)
+
+
 @pytest.mark.parametrize("tag,mode,target", [("norm", 0, 1.0), ("std", 1, 0.1)])
 def test_mei_golden(ops, tag, mode, target):
     d = golden("mei")
