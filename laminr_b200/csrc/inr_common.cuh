@@ -317,10 +317,12 @@ struct TileIdx {
 
 __device__ inline TileIdx decode_tile(const Tiling& tl, int tile) {
     TileIdx t;
-    const int chunk = tile % tl.nChunks;
-    const int rest = tile / tl.nChunks;
-    const int pb = rest % tl.tilesP;
-    t.d = rest / tl.tilesP;
+    // the common shapes need no division: one latent chunk (N latents fit the tile's rows) and, in learn, one target
+    int chunk = 0, rest = tile;
+    if (tl.nChunks != 1) chunk = tile % tl.nChunks, rest = tile / tl.nChunks;
+    int pb = rest;
+    t.d = 0;
+    if (rest >= tl.tilesP) t.d = rest / tl.tilesP, pb = rest - t.d * tl.tilesP;
     t.p0 = pb * tl.TP;
     t.n0 = chunk * tl.NC;
     t.np = min(tl.TP, tl.P - t.p0);

@@ -193,6 +193,9 @@ struct TcSmem {
 
 // weights of hidden layers 1..LH-1 as split-bf16 K-major tiles: W_l[o][k] for k < 50, column 50 = bias b_l[o],
 // entry [50][50] = ONE_SEED (regenerates the constant-1 feature), rest 0.  Also the fp32 output layer.
+// (role + rot) mod NBUF_BWD for role, rot in [0, NBUF_BWD): one compare + subtract instead of a division by a runtime-looking constant chain
+__device__ __forceinline__ int wrap_buf(int x) { return x >= NBUF_BWD ? x - NBUF_BWD : x; }
+
 template <class SmemT>
 __device__ inline void load_weight_tiles(const Args& a, SmemT& s) {
     const Net& nt = a.net;
@@ -756,7 +759,7 @@ __global__ void __launch_bounds__(128 * NG + 64, 1) inr_bwd_tc_kernel(Args a) {
             const uint64_t pol = l2_policy_evict_first();  // read once
             for (int it = 0; it < myTiles; ++it) {
                 const int rot = (2 * it) % NBUF_BWD;
-                auto buf = [&](int role) { return s.tiles + (size_t)((role + rot) % NBUF_BWD) * TILE_BYTES; };
+                auto buf = [&](int role) { return s.tiles + (size_t)wrap_buf(role + rot) * TILE_BYTES; };
                 const uint8_t* src = a.hsave + (size_t)(blockIdx.x + it * gridDim.x) * (LH - 1) * TILE_BYTES;
                 if (it > 0) mbar_wait(&s.bars[BAR_FREE], (uint32_t)(it - 1) & 1);      // dW_2 of the previous tile done: its dz_2 buffer = this h_3 buffer
                 mbar_arrive_expect_tx(&s.bars[BAR_LAND + 2], TILE_BYTES);
@@ -779,7 +782,7 @@ __global__ void __launch_bounds__(128 * NG + 64, 1) inr_bwd_tc_kernel(Args a) {
             uint32_t pk = 0;
             for (int it = 0; it < myTiles; ++it) {
                 const int rot = (2 * it) % NBUF_BWD;
-                auto buf = [&](int role) { return tiles_addr + (uint32_t)((role + rot) % NBUF_BWD) * TILE_BYTES; };
+                auto buf = [&](int role) { return tiles_addr + (uint32_t)wrap_buf(role + rot) * TILE_BYTES; };
                 int st = 0;
                 if (LOADH) {  // z_4 = h_3 W_3^T from the kept tile: all four k-steps at once
                     mbar_wait(&s.bars[BAR_LAND + 2], (uint32_t)it & 1);
@@ -902,7 +905,7 @@ __global__ void __launch_bounds__(128 * NG + 64, 1) inr_bwd_tc_kernel(Args a) {
         for (int it = 0; it < myTiles; ++it) {
             const TileIdx ti = decode_tile(tl, blockIdx.x + it * gridDim.x);
             const int rot = (2 * it) % NBUF_BWD;
-            auto buf = [&](int role) { return s.tiles + (size_t)((role + rot) % NBUF_BWD) * TILE_BYTES; };
+            auto buf = [&](int role) { return s.tiles + (size_t)wrap_buf(role + rot) * TILE_BYTES; };
             cp_async_wait<0>();
             named_bar_sync(1, NE);  // staged Cp visible; the previous tile's dz_0 panel is complete; everybody is done with its scratch
             if (!LOADH && it + 1 < myTiles) stage_tile_inputs(a, decode_tile(tl, blockIdx.x + (it + 1) * gridDim.x), s.Cps + ((it + 1) & 1) * TP * SHS, NE);
@@ -1335,7 +1338,7 @@ __global__ void __launch_bounds__(b2::NT, 1) inr_bwd2_kernel(Args a) {
             uint32_t pk = 0;
             for (int it = 0; it < myTiles; ++it) {
                 const int rot = (2 * it) % NBUF_BWD;
-                auto buf = [&](int role) { return tiles_addr + (uint32_t)((role + rot) % NBUF_BWD) * TBYTES; };
+                auto buf = [&](int role) { return tiles_addr + (uint32_t)wrap_buf(role + rot) * TBYTES; };
                 int st = 0;
 #pragma unroll 1
                 for (int l = 1; l < LH; ++l, ++st) {  // forward recompute: z_{l+1} = h_l W_l^T
@@ -1452,7 +1455,7 @@ __global__ void __launch_bounds__(b2::NT, 1) inr_bwd2_kernel(Args a) {
         for (int it = 0; it < myTiles; ++it) {
             const TileIdx ti = decode_tile(tl, first + it * stride);
             const int rot = (2 * it) % NBUF_BWD;
-            auto buf = [&](int role) { return tiles + (size_t)((role + rot) % NBUF_BWD) * TBYTES; };
+            auto buf = [&](int role) { return tiles + (size_t)wrap_buf(role + rot) * TBYTES; };
             cp_async_wait<0>();
             named_bar_sync(bar_id, NE);  // staged Cp visible; the previous tile's dz_0 panel is complete
             if (it + 1 < myTiles) stage_inputs(decode_tile(tl, first + (it + 1) * stride), Cps_s + ((it + 1) & 1) * TP * SHS);

@@ -59,12 +59,17 @@ def make_stop_reduce(device=None):
     if world == 1:
         return None
 
-    def reduce(a_sum, a_min, a_max):
-        # ONE collective per epoch: every rank gets every rank's (sum, min, max) and combines them in rank order (deterministic)
-        t = torch.tensor([a_sum, a_min, a_max], dtype=torch.float64, device=device)
+    def reduce(a_sum, a_min=None, a_max=None):
+        # ONE collective per epoch: every rank gets every rank's (sum, min, max) and combines them in rank order (deterministic).
+        # Called with three host floats, or with ONE 3-element tensor (the fused stepper's device-resident epoch statistics: the collective then
+        # runs device to device and the epoch costs a single copy to the host).
+        if torch.is_tensor(a_sum) and a_min is None:
+            t = a_sum.detach().reshape(3)
+        else:
+            t = torch.tensor([a_sum, a_min, a_max], dtype=torch.float64, device=device)
         parts = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(parts, t)
-        allr = torch.stack(parts).cpu()
+        allr = torch.stack(parts).cpu().double()
         return float(allr[:, 0].sum()), float(allr[:, 1].min()), float(allr[:, 2].max())
 
     return reduce

@@ -256,12 +256,14 @@ class InvarianceManifold:
                     optimizer.step()
                 self.match_steps_taken += 1
 
-            if fused:  # written by the step's last launch (lmr_match_epoch_stats): 12 bytes, one synchronisation per epoch
+            if fused and _stop_reduce is not None:  # sharded: the ranks exchange the device-resident statistics, one copy to the host
+                a_sum, a_min, a_max = _stop_reduce(stepper.epoch)
+            elif fused:  # written by the step's last launch (lmr_match_epoch_stats): 12 bytes, one synchronisation per epoch
                 a_sum, a_min, a_max = stepper.epoch_stats()
             else:
                 a_sum, a_min, a_max = torch.stack([acts.sum(), acts.min(), acts.max()]).tolist()
-            if _stop_reduce is not None:
-                a_sum, a_min, a_max = _stop_reduce(a_sum, a_min, a_max)
+                if _stop_reduce is not None:
+                    a_sum, a_min, a_max = _stop_reduce(a_sum, a_min, a_max)
             a_mean = a_sum / d_total
             is_increasing = improvement_checker.is_increasing(a_mean)
             desc = act_desc = f"Activation mean = {a_mean:.2f} (min = {a_min:.2f} max = {a_max:.2f})"
