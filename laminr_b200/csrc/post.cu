@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) simclr_gram_kernel(const float* __restric
 }
 
 // one CTA: reduce the gram, evaluate reg and the backward coefficient matrix K
-__global__ void __launch_bounds__(256) simclr_finalize_kernel(const float* __restrict__ Gpart, int S, int N, const float* __restrict__ pos,
+__global__ void __launch_bounds__(1024) simclr_finalize_kernel(const float* __restrict__ Gpart, int S, int N, const float* __restrict__ pos,
                                                               const float* __restrict__ neg, float T, float eps, float* __restrict__ reg,
                                                               float* __restrict__ K) {
     extern __shared__ float sm[];
@@ -327,16 +327,40 @@ __global__ void __launch_bounds__(256) simclr_finalize_kernel(const float* __res
     float* Sm = cosm + N * N;     // [N][N] exp(cos/T), later Gamma
     float* rho = Sm + N * N;      // [N]
     float* rowc = rho + N;        // [N][4]: a_pos, a_neg (row coefficients), log term, kappa
+    float* posS = rowc + 4 * N;   // [N][N] shared copies of the neighbour masks (the row loops below are serial chains: keep their loads on chip)
+    float* negS = posS + N * N;
     __shared__ float scratch[40];
-    for (int pr = threadIdx.x; pr < N * N; pr += 256) {
-        float acc = 0.f;
-        for (int s = 0; s < S; ++s) acc += Gpart[(size_t)s * N * N + pr];
-        cosm[pr] = acc;
+    // gram entries: the S chunk partials of an entry are split over G thread groups (coalesced across consecutive entries), each thread keeps eight
+    // independent chains in flight (the loads are L2 round trips); fixed-order combines -> deterministic
+    {
+        const int NN = N * N;
+        int G = (int)blockDim.x / NN;
+        G = G < 1 ? 1 : (G > 4 ? 4 : G);
+        auto part = [&](int g) { return g == 0 ? cosm : (g == 1 ? Sm : (g == 2 ? posS : negS)); };  // scratch until the masks are staged below
+        for (int item = threadIdx.x; item < G * NN; item += blockDim.x) {
+            const int g = item / NN, pr = item - g * NN;
+            float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int s = g;
+            for (; s + 7 * G < S; s += 8 * G) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a8[u] += Gpart[(size_t)(s + u * G) * NN + pr];
+            }
+            for (int u = 0; s < S; s += G, ++u) a8[u] += Gpart[(size_t)s * NN + pr];
+            part(g)[pr] = ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+        }
+        __syncthreads();
+        for (int pr = threadIdx.x; pr < NN; pr += blockDim.x) {
+            float tot = cosm[pr];
+            for (int g = 1; g < G; ++g) tot += part(g)[pr];
+            cosm[pr] = tot;
+        }
+        __syncthreads();
+        for (int pr = threadIdx.x; pr < NN; pr += blockDim.x) posS[pr] = pos[pr], negS[pr] = neg[pr];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < N; i += 256) rho[i] = sqrtf(cosm[i * N + i]);
+    for (int i = threadIdx.x; i < N; i += blockDim.x) rho[i] = sqrtf(cosm[i * N + i]);
     __syncthreads();
-    for (int pr = threadIdx.x; pr < N * N; pr += 256) {
+    for (int pr = threadIdx.x; pr < N * N; pr += blockDim.x) {
         const int i = pr / N, j = pr % N;
         const float c = cosm[pr] / (rho[i] * rho[j]);
         cosm[pr] = c;
@@ -344,11 +368,11 @@ __global__ void __launch_bounds__(256) simclr_finalize_kernel(const float* __res
     }
     __syncthreads();
     float logsum = 0.f;
-    for (int i = threadIdx.x; i < N; i += 256) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
         float ps = 0.f, np_ = 0.f, ns = 0.f, nn = 0.f;
         for (int j = 0; j < N; ++j) {
-            ps = fmaf(Sm[i * N + j], pos[i * N + j], ps), np_ += pos[i * N + j];
-            ns = fmaf(Sm[i * N + j], neg[i * N + j], ns), nn += neg[i * N + j];
+            ps = fmaf(Sm[i * N + j], posS[i * N + j], ps), np_ += posS[i * N + j];
+            ns = fmaf(Sm[i * N + j], negS[i * N + j], ns), nn += negS[i * N + j];
         }
         const float num = (ps == 0.f ? 0.f : ps / np_) + eps;
         const float den = (ns == 0.f ? 0.f : ns / nn) + eps;
@@ -360,19 +384,19 @@ __global__ void __launch_bounds__(256) simclr_finalize_kernel(const float* __res
     if (threadIdx.x == 0) reg[0] = logsum / (float)N * T / 2.f;
     __syncthreads();
     // Gamma_ij = A_ij S_ij / T
-    for (int pr = threadIdx.x; pr < N * N; pr += 256) {
+    for (int pr = threadIdx.x; pr < N * N; pr += blockDim.x) {
         const int i = pr / N;
-        Sm[pr] = (pos[pr] * rowc[i * 4] - neg[pr] * rowc[i * 4 + 1]) * Sm[pr] / T;
+        Sm[pr] = (posS[pr] * rowc[i * 4] - negS[pr] * rowc[i * 4 + 1]) * Sm[pr] / T;
     }
     __syncthreads();
     // kappa_i = sum_j Lambda_ij cos_ij, Lambda = Gamma + Gamma^T
-    for (int i = threadIdx.x; i < N; i += 256) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
         float kap = 0.f;
         for (int j = 0; j < N; ++j) kap = fmaf(Sm[i * N + j] + Sm[j * N + i], cosm[i * N + j], kap);
         rowc[i * 4 + 3] = kap;
     }
     __syncthreads();
-    for (int pr = threadIdx.x; pr < N * N; pr += 256) {
+    for (int pr = threadIdx.x; pr < N * N; pr += blockDim.x) {
         const int i = pr / N, j = pr % N;
         float k = (Sm[i * N + j] + Sm[j * N + i]) / (rho[i] * rho[j]);
         if (i == j) k -= rowc[i * 4 + 3] / (rho[i] * rho[i]);
@@ -765,8 +789,13 @@ extern "C" int lmr_simclr_fwd(const float* img, const float* mask, int N, int C,
     }
     simclr_gram_kernel<<<S, 256, smem1, st>>>(img, mask, N, C, HW, c0, g1, g2, static_cast<float*>(ws));
     LMR_LAUNCH_OK();
-    const size_t smem2 = ((size_t)2 * N * N + 5 * N) * sizeof(float);
-    simclr_finalize_kernel<<<1, 256, smem2, st>>>(static_cast<const float*>(ws), S, N, pos, neg, T, eps, reg, K);
+    const size_t smem2 = ((size_t)4 * N * N + 5 * N) * sizeof(float);
+    static size_t smem2_set = 0;
+    if (smem2 > 40 * 1024 && smem2 > smem2_set) {
+        LMR_CUDA_OK(cudaFuncSetAttribute(simclr_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        smem2_set = smem2;
+    }
+    simclr_finalize_kernel<<<1, 1024, smem2, st>>>(static_cast<const float*>(ws), S, N, pos, neg, T, eps, reg, K);
     LMR_LAUNCH_OK();
     return 0;
 }

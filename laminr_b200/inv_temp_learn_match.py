@@ -164,7 +164,7 @@ class InvarianceManifold:
                 break
             if verbose:
                 desc += f" | Contrastive reg scale = {reg_scale:.3f} | Epochs w/o improving = {reg_scheduler.num_epochs_no_improvement} (patience = {reg_scheduler.patience})"
-            pbar.set_description(desc)
+            pbar.set_description(desc, refresh=False)
         self.learn_epochs_run = epoch + 1
 
         self.template.eval()
@@ -235,17 +235,29 @@ class InvarianceManifold:
 
         images_list, acts_list = [], []
         self.match_steps_taken = 0
+        next_grids = None
         pbar = tqdm(range(num_epochs), bar_format=_BAR)
         for epoch in pbar:
             if save_results_every_n_epochs and epoch % save_results_every_n_epochs == 0:
                 imgs, a = snapshot()
                 images_list.append(imgs), acts_list.append(a)
-            template.train()
-            for input_grid in grid_dataloader.train_dataloader():
-                input_grid = input_grid.to(device)
-                if fused:
+            if not template.training:  # (the reference calls .train() every epoch, :350: a walk over the module tree; only the first one changes anything)
+                template.train()
+            if fused:
+                # The epoch's launches are queued first; the host then draws the NEXT epoch's jittered grids (same generator, same order as the
+                # reference: train_dataloader() then the iterator's base-seed draw) while the GPU works, and only then waits for this epoch's
+                # statistics.  If the stop rule fires, the generator is rewound to where the reference would have left it.
+                epoch_grids = next_grids if next_grids is not None else [g.to(device) for g in grid_dataloader.train_dataloader()]
+                for input_grid in epoch_grids:
                     stepper.step(input_grid)
-                else:
+                    self.match_steps_taken += 1
+                rng_before_next, next_grids = None, None
+                if epoch + 1 < num_epochs:
+                    rng_before_next = torch.get_rng_state()
+                    next_grids = [g.to(device) for g in grid_dataloader.train_dataloader()]
+            else:
+                for input_grid in grid_dataloader.train_dataloader():
+                    input_grid = input_grid.to(device)
                     _, _, _acts, _ = self.forward(input_grid, template, self.img_transforms, self.response_predicting_model, return_template=False,
                                                   other_neurons_loc_in_list=loc_in_list, other_neurons_loc_in_model=loc_in_model)
                     relevant = _acts[range(num_targets), :, range(num_targets)]
@@ -254,7 +266,7 @@ class InvarianceManifold:
                     optimizer.zero_grad()
                     loss.backward()
                     optimizer.step()
-                self.match_steps_taken += 1
+                    self.match_steps_taken += 1
 
             if fused and _stop_reduce is not None:  # sharded: the ranks exchange the device-resident statistics, one copy to the host
                 a_sum, a_min, a_max = _stop_reduce(stepper.epoch)
@@ -267,13 +279,15 @@ class InvarianceManifold:
             a_mean = a_sum / d_total
             is_increasing = improvement_checker.is_increasing(a_mean)
             desc = act_desc = f"Activation mean = {a_mean:.2f} (min = {a_min:.2f} max = {a_max:.2f})"
+            if not is_increasing and fused and rng_before_next is not None:
+                torch.set_rng_state(rng_before_next)  # the next epoch's draws were speculative
             if not is_increasing:
                 pbar.set_description("✅ Invariance matching is finished!" + " " + act_desc)
                 pbar.close()
                 break
             if verbose:
                 desc += f" | Epochs w/o improving = {improvement_checker.has_not_improved_counter} (patience: {improvement_checker.patience})"
-            pbar.set_description(desc)
+            pbar.set_description(desc, refresh=False)
         self.match_epochs_run = epoch + 1
 
         template.eval()

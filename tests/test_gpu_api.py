@@ -157,6 +157,24 @@ def test_match_api_fused_equals_generic_and_reference_step(L):
     assert np.allclose(outs[0][2][1], (1 / frac)[:, None], rtol=0.02)  # six Adam steps of 1e-3 later
 
 
+@pytest.mark.parametrize("kw,epochs", [(dict(num_epochs=4, patience=15), 4), (dict(num_epochs=50, patience=1, ignore_diff_smaller_than=1e9), 2)])
+def test_match_leaves_cpu_generator_like_the_reference_loop(L, kw, epochs):
+    """The fused match loop draws the next epoch's jitter while the GPU still runs the current one; whether the loop ends by exhausting num_epochs
+    or by the stop rule (:368-375), the CPU generator must end where the reference's loop (= the generic path) leaves it."""
+    d = golden("match_step_20")
+    states = []
+    for fused in (True, False):
+        model, im = _manifold(L, 20, d)
+        if not fused:
+            im._fused_ok = lambda gaussian_blur=None: False
+        im.template_neuron_idx = 0
+        torch.manual_seed(11)
+        im.match([1, 2], **kw)
+        assert im.match_epochs_run == epochs and im.match_steps_taken == epochs
+        states.append(torch.get_rng_state().clone())
+    assert torch.equal(states[0], states[1])
+
+
 def test_get_mei_dict_known_answer(L):
     """demo1 filters are unit-norm and images are constrained to norm 1, so the MEI activation is (elu(1)+1)/2 + 1e-6
     (the reference measures 1.0000009536743164 for all three neurons)."""
