@@ -326,6 +326,54 @@ class MatchStepper:
         self._forward()
         return self.act
 
+    def sweep(self, grid_row, angles, tx=None, ty=None, max_virtual=128):
+        """Mean activation [K, D] of every target under K candidate initialisations (angle_k, optionally translation (tx_k, ty_k)) of its affine
+        transform: the init sweep of `match` (inv_temp_learn_match.py:573-650), which the reference runs as K sequential no-grad forwards of all
+        targets.  The candidate only enters through the affine matrix, so (candidate, target) pairs are laid out as VIRTUAL targets and evaluated
+        `max_virtual` at a time by the same launches as `evaluate` (per-target arithmetic unchanged); with D >= max_virtual this is the reference's
+        loop, one candidate per pass, on the stepper's own buffers.  The table never leaves the device."""
+        t, c, N, D, Cc, P, dev = self.t, self.con, self.N, self.D, self.C, self.P, self.dev
+        lib = _lib.load()
+        import ctypes as C
+        f32 = dict(dtype=torch.float32, device=dev)
+        ang = torch.as_tensor(angles, **f32).reshape(-1)
+        K = ang.numel()
+        txd = None if tx is None else torch.as_tensor(tx, **f32).reshape(-1)
+        tyd = None if ty is None else torch.as_tensor(ty, **f32).reshape(-1)
+        per = max(1, int(max_virtual) // D)
+        out = torch.empty((K, D), **f32)
+        self.grid.copy_(grid_row.reshape(-1), non_blocking=True)
+        a = self.aff_mod
+        const = t._affine_const()
+        scal, shear = a.scalings.detach(), a.shears.detach()
+        trans0 = a.translation.detach().reshape(D, 2)
+        sf = const["shift_from"]
+        Dmax = min(per, K) * D
+        own = Dmax == D  # one candidate per pass: the stepper's own buffers
+        img = self.img_pre if own else torch.empty((Dmax, N, Cc, P), **f32)
+        z = self.z if own else torch.empty_like(img)
+        stats = self.stats if own else torch.empty((Dmax * N, 2), **f32)
+        act = self.act if own else torch.empty((Dmax, N), **f32)
+        ws_fwd = self.ws_fwd if own else _ws(ops.forward_workspace_bytes(t._desc, N, P, Dmax, False), dev)
+        ws_con = self.ws_con if own else _ws(lib.lmr_constrain_workspace_bytes(Dmax * N, Cc * P), dev)
+        resp = self.resp if own else response_backend(self.model, Dmax, N, P, dev)
+        for k0 in range(0, K, per):
+            nc = min(per, K - k0)
+            Dv = nc * D
+            trans = trans0.repeat(nc, 1)
+            if txd is not None:
+                trans[:, 0] = txd[k0:k0 + nc].repeat_interleave(D)
+                trans[:, 1] = tyd[k0:k0 + nc].repeat_interleave(D)
+            aff = ops.AffineArgs(ang[k0:k0 + nc].repeat_interleave(D), scal.repeat(nc, 1), shear.repeat(nc, 1), trans, tc=const["tc"],
+                                 shift_to=const["shift_to"], shift_from=None if sf is None else sf.reshape(D, 2).repeat(nc, 1), clamp=const["clamp"])
+            ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, aff, out=img.view(-1, N, Cc, P)[:Dv],
+                                precision=self.precision, workspace=ws_fwd)
+            ops.raw_constrain_fwd(c.mode, img.view(-1, Cc, P)[:Dv * N], c.target, c.mean, c.pmin, c.pmax, c.eps, out=z.view(-1, Cc, P)[:Dv * N],
+                                  stats=stats[:Dv * N], workspace=ws_con)
+            resp.forward(z, N * Cc * P, N, Dv, Cc, P, self.nog.repeat(nc), act[:Dv])
+            torch.mean(act[:Dv], dim=1, out=out[k0:k0 + nc].view(-1))
+        return out
+
     def normalised_acts(self):
         """acts_d = mean_n act[d,n] / a*_d of the last step (inv_temp_learn_match.py:362)."""
         return self.act.mean(dim=1) / self.mei_acts

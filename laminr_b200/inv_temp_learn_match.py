@@ -402,22 +402,22 @@ class InvarianceManifold:
             input_grid = grid_dataloader.grid.to(device)
             if rotate_angle_and_scale:
                 aff.scalings.data.copy_(inv_fraction)
-            for i, angle in enumerate(tqdm(angles, desc=desc, bar_format=_BAR)):
+            if _stepper is not None:
+                # all candidates x all targets as virtual targets of a few batched launches; candidate order == the loop's (i, j, k)
+                ii, jj, kk = np.meshgrid(np.arange(len(angles)), np.arange(len(translations)), np.arange(len(translations)), indexing="ij")
+                cand_t = (translations[jj.ravel()], translations[kk.ravel()]) if find_best_translation else (None, None)
+                dev_table.view(-1, n).copy_(_stepper.sweep(input_grid, angles[ii.ravel()], *cand_t))
+            for i, angle in enumerate(tqdm(angles, desc=desc, bar_format=_BAR) if _stepper is None else ()):  # generic autograd path: the reference's loop
                 aff.angles.data.fill_(float(angle))
                 for j, tx in enumerate(translations):
                     for k, ty in enumerate(translations):
                         if find_best_translation:
                             aff.translation.data[:, 0, 0] = float(tx)
                             aff.translation.data[:, 0, 1] = float(ty)
-                        if _stepper is not None:
-                            torch.mean(_stepper.evaluate(input_grid), dim=1, out=dev_table[i, j, k])
-                            continue
-                        else:
-                            _, _, _acts, _ = self.forward(input_grid, template, img_transforms, encoding_model, return_template=False,
-                                                          other_neurons_loc_in_list=other_neurons_loc_in_list,
-                                                          other_neurons_loc_in_model=other_neurons_loc_in_model)
-                            rel = _acts[range(n), :, range(n)].mean(dim=1)
-                        table[i, j, k, :] = rel.cpu().numpy()
+                        _, _, _acts, _ = self.forward(input_grid, template, img_transforms, encoding_model, return_template=False,
+                                                      other_neurons_loc_in_list=other_neurons_loc_in_list,
+                                                      other_neurons_loc_in_model=other_neurons_loc_in_model)
+                        table[i, j, k, :] = _acts[range(n), :, range(n)].mean(dim=1).cpu().numpy()
         if dev_table is not None:
             table[...] = dev_table.cpu().numpy()
         best = np.argmax(table.reshape(-1, n), axis=0)

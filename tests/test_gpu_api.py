@@ -175,6 +175,39 @@ def test_match_leaves_cpu_generator_like_the_reference_loop(L, kw, epochs):
     assert torch.equal(states[0], states[1])
 
 
+def test_batched_init_sweep_equals_candidate_loop(L):
+    """MatchStepper.sweep (all candidates x targets as virtual targets of batched launches) == one candidate per pass on the stepper's
+    own buffers == the reference's loop (set the angle / translation, evaluate all targets; inv_temp_learn_match.py:620-641)."""
+    d = golden("match_step_20")
+    model, im = _manifold(L, 20, d)
+    im.template_neuron_idx = 0
+    torch.manual_seed(3)
+    im.match([1, 2], num_epochs=1, patience=15)
+    st = im._match_stepper
+    grid = im._grid_for(20, "cuda")
+    aff = im.template.coordinate_transform.transforms.Affine
+    angles = np.linspace(0, 2 * np.pi, 8)[:-1].astype(np.float32)
+    tx = np.linspace(-0.1, 0.1, 7).astype(np.float32)
+    ty = tx[::-1].copy()
+    for with_t in (False, True):
+        cand = (tx, ty) if with_t else (None, None)
+        a = st.sweep(grid, angles, *cand, max_virtual=128).cpu().numpy()
+        b = st.sweep(grid, angles, *cand, max_virtual=1).cpu().numpy()
+        saved = [p.detach().clone() for p in (aff.angles, aff.translation)]
+        c = np.zeros_like(a)
+        with torch.no_grad():
+            for k in range(len(angles)):
+                aff.angles.data.fill_(float(angles[k]))
+                if with_t:
+                    aff.translation.data[:, 0, 0] = float(tx[k])
+                    aff.translation.data[:, 0, 1] = float(ty[k])
+                c[k] = st.evaluate(grid).mean(dim=1).cpu().numpy()
+            aff.angles.data.copy_(saved[0]), aff.translation.data.copy_(saved[1])
+        assert a.shape == (7, 2) and np.ptp(c, axis=0).min() > 1e-3  # the candidates matter
+        np.testing.assert_allclose(a, c, rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(b, c, rtol=2e-6, atol=1e-7)
+
+
 def test_get_mei_dict_known_answer(L):
     """demo1 filters are unit-norm and images are constrained to norm 1, so the MEI activation is (elu(1)+1)/2 + 1e-6
     (the reference measures 1.0000009536743164 for all three neurons)."""
