@@ -59,11 +59,12 @@ class _SimulatedResponse:
     """Response backend for `ArbitraryMultiNeuronModel` populations (lmr_simresp_*)."""
     launches_fwd, launches_fwd_bwd = 2, 3
 
-    def __init__(self, model, D, N, P, dev):
+    def __init__(self, model, D, N, P, dev, also=()):
         self.model = model
         self.rmax = torch.empty((D, N), dtype=torch.float32, device=dev)
         self.argmax = torch.empty((D, N), dtype=torch.int32, device=dev)
-        self.ws = _ws(_lib.load().lmr_simresp_workspace_bytes(D, N, model.packed_filters.shape[1], P), dev)
+        # the partials' chunk size depends on the number of groups of a call: size the workspace for every group count it will be called with
+        self.ws = _ws(max(_lib.load().lmr_simresp_workspace_bytes(g, N, model.packed_filters.shape[1], P) for g in (D,) + tuple(also) if g > 0), dev)
 
     def forward(self, z, stride, N, D, Cc, P, nog, act):
         m = self.model
@@ -79,7 +80,7 @@ class _ConvResponse:
     receptive-field cone, forward and image gradient in ONE launch (the upstream gradient of the loops is a constant per image)."""
     launches_fwd, launches_fwd_bwd = 1, 1
 
-    def __init__(self, model, D, N, P, dev):
+    def __init__(self, model, D, N, P, dev, also=()):
         self.cone = model.cone()
         if self.cone.HW != P:
             raise ValueError("response model and template resolution differ")
@@ -91,12 +92,12 @@ class _ConvResponse:
         ops.raw_convcore_response(self.cone, z, stride, N, D, nog, g_act=g_act, act=act, g_img=g_z, accumulate=accumulate)
 
 
-def response_backend(model, D, N, P, dev):
+def response_backend(model, D, N, P, dev, also=()):
     from .neuron_models.utils.simulated_model import ArbitraryMultiNeuronModel
     if isinstance(model, ArbitraryMultiNeuronModel):
-        return _SimulatedResponse(model, D, N, P, dev)
+        return _SimulatedResponse(model, D, N, P, dev, also)
     if hasattr(model, "cone"):
-        return _ConvResponse(model, D, N, P, dev)
+        return _ConvResponse(model, D, N, P, dev, also)
     raise TypeError("fused path: unsupported response model %s" % type(model).__name__)
 
 
@@ -253,7 +254,6 @@ class MatchStepper:
         self.g_x = torch.empty_like(self.img_pre)
         self.stats = torch.empty((D * N, 2), **f32)
         self.act = torch.empty((D, N), **f32)
-        self.resp = response_backend(model, D, N, P, dev)
         self.g_act = (-1.0 / (N * self.Dtot * self.mei_acts))[:, None].expand(D, N).contiguous()
         self.aff_mod = template.coordinate_transform.transforms.Affine
         a = self.aff_mod
@@ -264,9 +264,27 @@ class MatchStepper:
         self.v = [torch.zeros_like(p) for p in self.params]
         self.steps = [torch.zeros(2, dtype=torch.int32, device=dev) for _ in self.params]
         d = template._desc
+        # The training step walks the targets in blocks of `block` (all D when the kept activations of D targets fit the budget of
+        # LMR_KEEP_ACT_MAX_GIB; e.g. BASELINE config 3 with 1024 targets on one GPU: 154 MB per target at 100x100 -> blocks of ~210): forward (keeping the
+        # operand tiles), objective and backward of one block, then the next block on the same workspace; Adam once over all targets.  The no-grad
+        # passes (evaluate, sweep) keep nothing and run all targets at once.
+        import os
+        self.block = D
         self.keep = _keep_activations(precision, ops.forward_workspace_bytes(d, N, P, D, True))
-        self.ws_fwd = _ws(ops.forward_workspace_bytes(d, N, P, D, self.keep), dev)
-        self.ws_bwd = _ws(lib.lmr_inr_backward_workspace_bytes(C.byref(d), N, P, D), dev)
+        if not self.keep and ops.precision_code(precision) != _lib.PREC_FP32 and os.environ.get("LMR_KEEP_ACT", "1") != "0":
+            lo = 0
+            for b in range(1, D):  # largest block whose kept activations fit (the workspace grows linearly with the block)
+                if not _keep_activations(precision, ops.forward_workspace_bytes(d, N, P, b, True)):
+                    break
+                lo = b
+            if lo >= 1:
+                self.block, self.keep = lo, True
+        if os.environ.get("LMR_MATCH_BLOCK"):  # testing: force a block size
+            self.block = max(1, min(D, int(os.environ["LMR_MATCH_BLOCK"])))
+        Bk, rem = self.block, D % self.block
+        self.resp = response_backend(model, D, N, P, dev, also=(Bk, rem))
+        self.ws_fwd = _ws(max(ops.forward_workspace_bytes(d, N, P, D, False), ops.forward_workspace_bytes(d, N, P, Bk, self.keep)), dev)
+        self.ws_bwd = _ws(lib.lmr_inr_backward_workspace_bytes(C.byref(d), N, P, Bk), dev)
         self.ws_con = _ws(lib.lmr_constrain_workspace_bytes(D * N, Cc * P), dev)
         self.use_graph, self.graph = use_graph, None
         # (sum, min, max) over the local targets of acts_d = mean_n act[d,n] / a*_d, written by the last launch of every step; the stop rule of the
@@ -289,16 +307,34 @@ class MatchStepper:
         self._images()
         self.resp.forward(self.z, N * Cc * P, N, D, Cc, P, self.nog, self.act)
 
+    def _affine_block(self, b0, b1):
+        """Affine arguments of targets [b0, b1): views into the live parameters (a graph replay reads the updated values)."""
+        D = self.D
+        if b0 == 0 and b1 == D:
+            return self._affine()
+        a, const = self.aff_mod, self.t._affine_const()
+        sf = const["shift_from"]
+        return ops.AffineArgs(a.angles.detach()[b0:b1], a.scalings.detach()[b0:b1], a.shears.detach()[b0:b1], a.translation.detach().reshape(D, 2)[b0:b1],
+                              tc=const["tc"], shift_to=const["shift_to"], shift_from=None if sf is None else sf.reshape(D, 2)[b0:b1], clamp=const["clamp"])
+
     def _train(self):
         t, c, N, D, Cc, P = self.t, self.con, self.N, self.D, self.C, self.P
-        self._images(keep=self.keep)
-        self.resp.forward_backward(self.z, N * Cc * P, N, D, Cc, P, self.nog, self.g_act, self.act, self.g_z, False)
-        ops.raw_constrain_bwd(c.mode, self.img_pre.view(D * N, Cc, P), self.g_z.view(D * N, Cc, P), self.stats, c.target, c.mean, c.pmin, c.pmax, c.eps,
-                              out=self.g_x.view(D * N, Cc, P), workspace=self.ws_con)
-        ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, self._affine(), self.g_x.view(D, N, Cc, P),
-                             want_params=False, want_affine=True, precision=self.precision, workspace=self.ws_bwd,
-                             g_affine=(self.grads[0], self.grads[1], self.grads[2], self.grads[3].view(D, 2)), forward_workspace=self.ws_fwd,
-                             keep_activations=self.keep)
+        for b0 in range(0, D, self.block):
+            b1 = min(D, b0 + self.block)
+            Db = b1 - b0
+            aff = self._affine_block(b0, b1)
+            img, z, g_z, g_x = (x[b0:b1] for x in (self.img_pre, self.z, self.g_z, self.g_x))
+            ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, aff, out=img.view(Db, N, Cc, P), precision=self.precision,
+                                workspace=self.ws_fwd, keep_activations=self.keep)
+            ops.raw_constrain_fwd(c.mode, img.view(Db * N, Cc, P), c.target, c.mean, c.pmin, c.pmax, c.eps, out=z.view(Db * N, Cc, P),
+                                  stats=self.stats[b0 * N:b1 * N], workspace=self.ws_con)
+            self.resp.forward_backward(z, N * Cc * P, N, Db, Cc, P, self.nog[b0:b1], self.g_act[b0:b1], self.act[b0:b1], g_z, False)
+            ops.raw_constrain_bwd(c.mode, img.view(Db * N, Cc, P), g_z.view(Db * N, Cc, P), self.stats[b0 * N:b1 * N], c.target, c.mean, c.pmin, c.pmax,
+                                  c.eps, out=g_x.view(Db * N, Cc, P), workspace=self.ws_con)
+            ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, aff, g_x.view(Db, N, Cc, P), want_params=False,
+                                 want_affine=True, precision=self.precision, workspace=self.ws_bwd,
+                                 g_affine=(self.grads[0][b0:b1], self.grads[1][b0:b1], self.grads[2][b0:b1], self.grads[3].view(D, 2)[b0:b1]),
+                                 forward_workspace=self.ws_fwd, keep_activations=self.keep)
         for p, g, m, v, s, tr in zip(self.params, self.grads, self.m, self.v, self.steps, self.trainable):
             if tr:
                 ops.raw_adam_step(p.data, g, m, v, s, lr=self.lr)

@@ -175,6 +175,28 @@ def test_match_leaves_cpu_generator_like_the_reference_loop(L, kw, epochs):
     assert torch.equal(states[0], states[1])
 
 
+def test_match_step_in_target_blocks_equals_one_pass(L, monkeypatch):
+    """The match training step walks the targets in blocks when the kept activations of all targets exceed the memory budget (BASELINE config 3
+    on few GPUs); forced here with one target per block: same parameters and results as all targets in one pass."""
+    d = golden("match_step_20")
+    outs = []
+    for block in (None, "1"):
+        if block is None:
+            monkeypatch.delenv("LMR_MATCH_BLOCK", raising=False)
+        else:
+            monkeypatch.setenv("LMR_MATCH_BLOCK", block)
+        model, im = _manifold(L, 20, d)
+        im.template_neuron_idx = 0
+        torch.manual_seed(5)
+        imgs, acts = im.match([1, 2], num_epochs=5, patience=15)
+        assert im._match_stepper.block == (2 if block is None else 1)
+        aff = im.template.coordinate_transform.transforms.Affine
+        outs.append((imgs, acts, [p.detach().cpu().numpy().copy() for p in (aff.angles, aff.scalings, aff.shears, aff.translation)]))
+    for a, b in zip(outs[0][2], outs[1][2]):
+        np.testing.assert_allclose(a, b, rtol=1e-6, atol=1e-7)
+    assert relerr(outs[0][0], outs[1][0]) < 1e-6 and relerr(outs[0][1], outs[1][1]) < 1e-6
+
+
 def test_batched_init_sweep_equals_candidate_loop(L):
     """MatchStepper.sweep (all candidates x targets as virtual targets of batched launches) == one candidate per pass on the stepper's
     own buffers == the reference's loop (set the angle / translation, evaluate all targets; inv_temp_learn_match.py:620-641)."""
