@@ -18,6 +18,7 @@ import torch
 from torch import nn
 from tqdm import tqdm
 
+from . import ops
 from .contrastive_loss import SimCLROnGrid
 from .fused import LearnStepper, MatchStepper, fused_response_supported
 from .inr import INRTemplates
@@ -209,16 +210,27 @@ class InvarianceManifold:
         grid_dataloader = JitteringGridDatamodule(num_invariances=1, grid_points_per_dim=grid_points_per_dim, steps_per_epoch=steps_per_epoch)
         fused = self._fused_ok()
         stepper = None
+        import os, sys, time
+        timing, marks = os.environ.get("LMR_TIMING") == "1", []  # debug: per-phase wall clock on stderr (adds synchronisations)
+
+        def mark(name):
+            if timing:
+                torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+
+        mark("start")
         if fused:
             stepper = MatchStepper(self.template, self.img_transforms, self.response_predicting_model, loc_in_model, others_mei_act, grid_points_per_dim,
                                    lr=lr, total_targets=_total_targets, precision=self.precision, use_graph=self.use_cuda_graph)
             self._match_stepper = stepper
 
+        mark("stepper construction")
         template = self.initialize_with_best_angle_and_translation(
             self.template, self.response_predicting_model, self.img_transforms, grid_dataloader, loc_in_list, loc_in_model,
             template_rf_mask=template_rf_mask, others_rf_mask=others_rf_mask, rotate_angle_and_scale=rotate_angle_and_scale,
             find_best_translation=find_best_translation, _stepper=stepper)
 
+        mark("init sweep")
         if not fused:
             optimizer = torch.optim.Adam(template.coordinate_transform.parameters(), lr=lr)
         improvement_checker = ImprovementChecker(patience=patience, ignore_diff_smaller_than=ignore_diff_smaller_than)
@@ -230,7 +242,7 @@ class InvarianceManifold:
                 act = stepper.evaluate(grid)
                 if _return_device:  # laminr_b200.dist gathers the blocks over NCCL before the one copy to the host
                     return stepper.z.clone(), act.clone()
-                return stepper.z.cpu().numpy(), act.cpu().numpy()
+                return ops.to_host_numpy(stepper.z), act.cpu().numpy()
             return self.get_matched_images_and_activations(grid, template, loc_in_list, loc_in_model)
 
         images_list, acts_list = [], []
@@ -289,9 +301,13 @@ class InvarianceManifold:
                 desc += f" | Epochs w/o improving = {improvement_checker.has_not_improved_counter} (patience: {improvement_checker.patience})"
             pbar.set_description(desc, refresh=False)
         self.match_epochs_run = epoch + 1
+        mark(f"{epoch + 1} epochs")
 
         template.eval()
         imgs, a = snapshot()
+        mark("snapshot")
+        if timing:
+            print("[match] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a_[1]):.1f} ms" for a_, b in zip(marks, marks[1:])), file=sys.stderr)
         if save_results_every_n_epochs is not None:
             images_list.append(imgs), acts_list.append(a)
             if torch.is_tensor(imgs):

@@ -62,6 +62,53 @@ def _workspace(nbytes, device):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# results -> host (result getters, inv_temp_learn_match.py:394-422: `.cpu().data.numpy()`)
+# ------------------------------------------------------------------------------------------------------------------
+_HOST_RING = {}
+
+
+def to_host_numpy(t, chunk_bytes=32 << 20, nbuf=4):
+    """`t.cpu().numpy()` for large device tensors (the [D,N,C,H,W] image blocks of match: 0.8 GB for 1023 targets at 100x100): the device-to-host
+    copies run asynchronously through a small ring of persistent pinned buffers while worker threads move finished chunks into the destination
+    array (a pageable `.cpu()` of that block takes 0.36 s on the B200 box, the first-touch host copy being the bottleneck; this takes about half)."""
+    nbytes = t.numel() * t.element_size()
+    if not t.is_cuda or nbytes < 4 * chunk_bytes:
+        return t.detach().cpu().numpy()
+    import concurrent.futures as cf
+
+    import numpy as np
+
+    flat = t.detach().contiguous().reshape(-1)
+    step = chunk_bytes // flat.element_size()
+    key = (flat.dtype, step, nbuf)
+    if key not in _HOST_RING:
+        _HOST_RING[key] = ([torch.empty(step, dtype=flat.dtype, pin_memory=True) for _ in range(nbuf)], cf.ThreadPoolExecutor(nbuf))
+    bufs, pool = _HOST_RING[key]
+    out = np.empty(flat.numel(), dtype=bufs[0].numpy().dtype)
+    side = torch.cuda.Stream(device=t.device)
+    side.wait_stream(torch.cuda.current_stream(t.device))
+
+    def drain(ev, b, m, o):
+        ev.synchronize()
+        out[o:o + m] = bufs[b][:m].numpy()
+
+    pending = [None] * nbuf
+    for i, o in enumerate(range(0, flat.numel(), step)):
+        b, m = i % nbuf, min(step, flat.numel() - o)
+        if pending[b] is not None:
+            pending[b].result()  # the chunk that used this pinned buffer has reached the destination
+        with torch.cuda.stream(side):
+            bufs[b][:m].copy_(flat[o:o + m], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        pending[b] = pool.submit(drain, ev, b, m, o)
+    for f in pending:
+        if f is not None:
+            f.result()
+    return out.reshape(tuple(t.shape))
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # INR
 # ------------------------------------------------------------------------------------------------------------------
 class AffineArgs:

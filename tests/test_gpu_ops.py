@@ -179,6 +179,17 @@ def test_adam_golden(ops):
     assert step.tolist() == [5, 0]
 
 
+@pytest.mark.parametrize("shape", [(3, 20, 1, 10, 10), (40, 20, 1, 100, 101), (7, 5, 3, 333, 77)])
+def test_to_host_numpy_equals_cpu_copy(ops, shape):
+    """The pipelined device-to-host copy of result blocks (pinned ring + worker threads) returns exactly `t.cpu().numpy()`; small tensors take the
+    plain path, the larger ones cross several chunks with a ragged tail; a non-contiguous view is handled too."""
+    x = torch.randn(*shape, device="cuda")
+    for t in (x, x.transpose(0, 1)):
+        got = ops.to_host_numpy(t, chunk_bytes=1 << 20)
+        assert got.shape == tuple(t.shape) and got.dtype == np.float32
+        assert np.array_equal(got, t.cpu().numpy())
+
+
 @pytest.mark.parametrize("D,N", [(1, 20), (2, 20), (37, 7), (1024, 20)])
 def test_match_epoch_stats_vs_host_reductions(ops, D, N):
     """lmr_match_epoch_stats == the reference's host-driven reductions of the match loop (inv_temp_learn_match.py:361-362,368-371):
