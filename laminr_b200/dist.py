@@ -181,6 +181,8 @@ def get_mei_dict_sharded(model, input_shape, pixel_value_lower_bound, pixel_valu
     if lo > 0:
         torch.randn(lo, *input_shape)
     local = get_mei_dict(model, input_shape, pixel_value_lower_bound, pixel_value_upper_bound, neuron_idxs=neuron_idxs[lo:hi], **kwargs)
+    if hi < len(neuron_idxs):  # ... and of the higher ranks: every rank leaves the generator where the unsharded call would (same jitter in `learn`)
+        torch.randn(len(neuron_idxs) - hi, *input_shape)
     parts = [None] * world
     dist.all_gather_object(parts, {lo + k: v for k, v in local.items()})
     out = {}
