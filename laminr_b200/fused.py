@@ -366,8 +366,8 @@ class MatchStepper:
         """Mean activation [K, D] of every target under K candidate initialisations (angle_k, optionally translation (tx_k, ty_k)) of its affine
         transform: the init sweep of `match` (inv_temp_learn_match.py:573-650), which the reference runs as K sequential no-grad forwards of all
         targets.  The candidate only enters through the affine matrix, so (candidate, target) pairs are laid out as VIRTUAL targets and evaluated
-        `max_virtual` at a time by the same launches as `evaluate` (per-target arithmetic unchanged); with D >= max_virtual this is the reference's
-        loop, one candidate per pass, on the stepper's own buffers.  The table never leaves the device."""
+        `max_virtual` at a time by the same launches as `evaluate` (per-target arithmetic unchanged); with D > max_virtual / 8 this is the
+        reference's loop, one candidate per pass, on the stepper's own buffers.  The table never leaves the device."""
         t, c, N, D, Cc, P, dev = self.t, self.con, self.N, self.D, self.C, self.P, self.dev
         lib = _lib.load()
         import ctypes as C
@@ -376,7 +376,9 @@ class MatchStepper:
         K = ang.numel()
         txd = None if tx is None else torch.as_tensor(tx, **f32).reshape(-1)
         tyd = None if ty is None else torch.as_tensor(ty, **f32).reshape(-1)
-        per = max(1, int(max_virtual) // D)
+        per = int(max_virtual) // D
+        if per < 8:  # a pass over D >= max_virtual / 8 targets already fills the GPU for milliseconds: nothing to gain from extra buffers
+            per = 1
         out = torch.empty((K, D), **f32)
         self.grid.copy_(grid_row.reshape(-1), non_blocking=True)
         a = self.aff_mod
