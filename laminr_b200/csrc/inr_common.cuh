@@ -706,7 +706,8 @@ static inline int fill_args(Args& a, const Net& nt, const Tiling& tl, const floa
     a.betaG = wl.betaG ? reinterpret_cast<float*>(base + wl.betaG) : nullptr;
     a.want_cp = 0;
     a.ppb = wl.ppb;
-    a.ppb_prep = choose_ppb(tl.D * tl.P, 2);
+    static const int prep_bps = getenv("LMR_PREP_BPS") ? atoi(getenv("LMR_PREP_BPS")) : 2;  // prep blocks per SM (tuning knob; measured: 1 -> 22 us, 2 -> 16 us at 100x100)
+    a.ppb_prep = choose_ppb(tl.D * tl.P, prep_bps > 0 ? prep_bps : 2);
     a.dAred = reinterpret_cast<float*>(base + wl.dAred);
     a.G0 = reinterpret_cast<float*>(base + wl.G0);
     a.partials = reinterpret_cast<float*>(base + wl.partials);
