@@ -657,9 +657,10 @@ static inline WsLayout ws_layout(const Net& nt, const Tiling& tl, bool bwd, bool
     w.hsave = (want_cp && keep_act && !bwd) ? take((size_t)tl.numTiles * (nt.nl - 1) * 32768 / 4) : 0;  // forward layout only (a suffix of it)
     w.gridMain = tl.numTiles < num_sms() ? tl.numTiles : num_sms();
     const int total = tl.D * tl.P;
-    w.ppb = choose_ppb(total);
+    static const int l0_bps = getenv("LMR_L0_BPS") && atoi(getenv("LMR_L0_BPS")) > 0 ? atoi(getenv("LMR_L0_BPS")) : 1;  // l0 / affine-gradient blocks per SM (tuning knob)
+    w.ppb = choose_ppb(total, l0_bps);
     const int nchunks = (total + w.ppb - 1) / w.ppb;
-    w.gridL0 = nchunks < num_sms() ? nchunks : num_sms();
+    w.gridL0 = nchunks < l0_bps * num_sms() ? nchunks : l0_bps * num_sms();
     w.G0 = w.partials = w.l0part = w.affpart = w.dAred = 0;
     if (bwd) {
         w.G0 = take((size_t)tl.D * tl.P * HP);
