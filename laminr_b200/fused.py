@@ -22,6 +22,28 @@ def _keep_activations(precision, workspace_bytes):
     return workspace_bytes <= float(os.environ.get("LMR_KEEP_ACT_MAX_GIB", "32")) * 2 ** 30
 
 
+def match_block(precision, desc, N, P, D):
+    """-> (targets per block, keep activations?) of the match training step: all D targets when their kept operand tiles fit the budget, else the
+    largest block that does (the forward workspace grows linearly with the block), else -- fp32 path, LMR_KEEP_ACT=0, or not even one target fits --
+    all D targets with the recompute backward.  LMR_MATCH_BLOCK forces a block size (testing).  Pure host arithmetic on the C ABI's workspace sizes."""
+    import os
+
+    block, keep = D, _keep_activations(precision, ops.forward_workspace_bytes(desc, N, P, D, True))
+    if not keep and ops.precision_code(precision) != _lib.PREC_FP32 and os.environ.get("LMR_KEEP_ACT", "1") != "0":
+        lo, hi = 0, D  # invariant: a block of `lo` targets fits (0 = nothing known to fit), a block of `hi` does not
+        while hi - lo > 1:
+            mid = (lo + hi) // 2
+            if _keep_activations(precision, ops.forward_workspace_bytes(desc, N, P, mid, True)):
+                lo = mid
+            else:
+                hi = mid
+        if lo >= 1:
+            block, keep = lo, True
+    if os.environ.get("LMR_MATCH_BLOCK"):
+        block = max(1, min(D, int(os.environ["LMR_MATCH_BLOCK"])))
+    return block, keep
+
+
 def capture_graph(fn):
     """Stream-captures the launches of `fn` into a CUDA graph.  The raw capture API instead of the `torch.cuda.graph` context manager: that one
     synchronises the device, runs the Python garbage collector and empties the allocator cache around every capture (~15 ms, more than a whole
@@ -268,19 +290,7 @@ class MatchStepper:
         # LMR_KEEP_ACT_MAX_GIB; e.g. BASELINE config 3 with 1024 targets on one GPU: 154 MB per target at 100x100 -> blocks of ~210): forward (keeping the
         # operand tiles), objective and backward of one block, then the next block on the same workspace; Adam once over all targets.  The no-grad
         # passes (evaluate, sweep) keep nothing and run all targets at once.
-        import os
-        self.block = D
-        self.keep = _keep_activations(precision, ops.forward_workspace_bytes(d, N, P, D, True))
-        if not self.keep and ops.precision_code(precision) != _lib.PREC_FP32 and os.environ.get("LMR_KEEP_ACT", "1") != "0":
-            lo = 0
-            for b in range(1, D):  # largest block whose kept activations fit (the workspace grows linearly with the block)
-                if not _keep_activations(precision, ops.forward_workspace_bytes(d, N, P, b, True)):
-                    break
-                lo = b
-            if lo >= 1:
-                self.block, self.keep = lo, True
-        if os.environ.get("LMR_MATCH_BLOCK"):  # testing: force a block size
-            self.block = max(1, min(D, int(os.environ["LMR_MATCH_BLOCK"])))
+        self.block, self.keep = match_block(precision, d, N, P, D)
         Bk, rem = self.block, D % self.block
         self.resp = response_backend(model, D, N, P, dev, also=(Bk, rem))
         self.ws_fwd = _ws(max(ops.forward_workspace_bytes(d, N, P, D, False), ops.forward_workspace_bytes(d, N, P, Bk, self.keep)), dev)

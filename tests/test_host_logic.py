@@ -184,3 +184,41 @@ def test_create_mask_centroid(L):
     mask, c = create_mask(torch.from_numpy(mei), zscore_thresh=0.3, return_mask_centroid=True)
     assert mask.shape == (40, 40) and abs(c["x"] - 25.5) < 1.0 and abs(c["y"] - 12.5) < 1.0
     assert float(mask.max()) <= 1.0 + 1e-6 and float(mask[12, 25]) > 0.95 and float(mask[35, 3]) < 1e-3
+
+
+def test_match_block_selection(L, monkeypatch):
+    """Block size of the match training step (laminr_b200.fused.match_block): pure host arithmetic on the C ABI's workspace sizes."""
+    from laminr_b200 import ops
+    from laminr_b200.fused import match_block
+    d = ops.make_desc(50, 4, 50, 50, 1)
+    N, P = 20, 100 * 100
+    for k in ("LMR_KEEP_ACT", "LMR_KEEP_ACT_MAX_GIB", "LMR_MATCH_BLOCK"):
+        monkeypatch.delenv(k, raising=False)
+    # the kept operand tiles: 3 layers x 32 KB per 128-row tile, 6 pixels x 20 latents per tile (include/laminr_b200.h, LMR_PREC_KEEP_ACTIVATIONS)
+    per_target = ops.forward_workspace_bytes(d, N, P, 1, True) - ops.forward_workspace_bytes(d, N, P, 1, False)
+    assert per_target == -(-P // 6) * 3 * 32768
+    assert match_block("bf16x3", d, N, P, 32) == (32, True)          # 4.9 GiB of tiles: one pass
+    blk, keep = match_block("bf16x3", d, N, P, 1024)                  # BASELINE config 3 on one GPU: 157 GiB of tiles > 32 GiB budget
+    assert keep and 190 <= blk <= 210
+    assert ops.forward_workspace_bytes(d, N, P, blk, True) <= 32 * 2 ** 30 < ops.forward_workspace_bytes(d, N, P, blk + 1, True)
+    assert match_block("fp32", d, N, P, 1024) == (1024, False)        # CUDA-core path keeps nothing
+    monkeypatch.setenv("LMR_KEEP_ACT_MAX_GIB", "0.1")                 # not even one target fits: recompute backward, one pass
+    assert match_block("bf16x3", d, N, P, 8) == (8, False)
+    monkeypatch.setenv("LMR_KEEP_ACT_MAX_GIB", "2")
+    assert match_block("bf16x3", d, N, P, 32) == (12, True)
+    monkeypatch.setenv("LMR_KEEP_ACT", "0")
+    assert match_block("bf16x3", d, N, P, 32) == (32, False)
+    monkeypatch.setenv("LMR_MATCH_BLOCK", "5")
+    assert match_block("bf16x3", d, N, P, 32)[0] == 5
+
+
+def test_simresp_workspace_follows_the_group_count(L):
+    """The response partials' pixels-per-CTA depend on the number of groups of a call (about two CTAs per SM for few groups), so the workspace is
+    NOT monotonic in the group count: callers size it for every group count they use (fused._SimulatedResponse)."""
+    from laminr_b200 import _lib
+    lib = _lib.load()
+    NB, F, HW = 20, 20, 100 * 100
+    chunks = {g: lib.lmr_simresp_workspace_bytes(g, NB, F, HW) // (g * NB * F * 4) for g in range(1, 41)}
+    assert set(chunks.values()) == {20, 40, 79}                       # 512 / 256 / 128 pixels per CTA at 100 x 100
+    assert chunks[1] == 79 and chunks[8] == 40 and chunks[32] == 20
+    assert lib.lmr_simresp_workspace_bytes(7, NB, F, HW) > lib.lmr_simresp_workspace_bytes(8, NB, F, HW)
