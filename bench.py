@@ -13,7 +13,13 @@ One "step" is one pass of the learn hot path (reference laminr/inv_temp_learn_ma
   roofline : the INR backward launch group (dominant), algorithmic FLOPs / CUDA-event time vs measured bf16 peak.
   cpu_baseline : the reference's CPU path (torch-CPU port of its op sequence, oracle/torch_port.py; or the reference
              itself when /root/reference is mounted) on a bounded sample of the same workload.
-  match    : extra -- target-steps/s of the match hot step (:351-366), targets sharded over the N ranks.
+  api_learn: extra -- steps/s through the public call itself, InvarianceManifold.learn(0, num_max_epochs=20): stepper construction, graph
+             capture, per-epoch control logic and the final snapshot to the host included (rank 0).
+  match    : extra -- target-steps/s of the match hot step (:351-366), targets sharded over the N ranks (weak scaling, --match-targets per
+             GPU); `aligned` = target neurons aligned/s of a whole match() call (60-angle sweep + --match-epochs epochs + results on the host);
+             `mei` = MEIs/s of the batched ascent (BASELINE configs[4]) with a one-core numpy-port baseline; `config2` (N == 1) = BASELINE
+             configs[1], demo1 match of targets [1, 2], whole call and per step, with the numpy-port CPU baseline of the match step.
+  conv     : extra -- BASELINE configs[3]: learn / match / MEI with the conv-core + Gaussian-readout encoder at 200x200 and its CPU port baseline.
 N > 1: learn does not shard (one template) -> N independent replicas ("replicas only"); value = N*K / max-over-ranks time.
 """
 import argparse
