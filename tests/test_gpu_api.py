@@ -230,6 +230,49 @@ def test_batched_init_sweep_equals_candidate_loop(L):
         np.testing.assert_allclose(b, c, rtol=2e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("with_t", [False, True])
+def test_init_sweep_vs_reference_golden(L, with_t):
+    """Match initialisation sweep on the GPU (MatchStepper.sweep through initialize_with_best_angle_and_translation) against the table and the
+    final choice of the UNMODIFIED reference function (tests/golden/init_sweep_20.npz, oracle/make_golden_sweep.py): angle only (the `match` default,
+    60 candidates) and angle + translation (60 x 11 x 11 candidates)."""
+    from laminr_b200.fused import MatchStepper
+    from laminr_b200.utils.training import JitteringGridDatamodule
+    d = golden("init_sweep_20")
+    res, targets, tag = 20, [1, 2], "at" if with_t else "a"
+    model = L.neuron_models.simulated("demo1", img_res=[res, res]).cuda()
+    xy = np.concatenate([d["template_xy"][None], d["target_xy"]])
+    masks = np.concatenate([d["template_mask"][None], d["target_masks"]])
+    meis = {i: dict(mei=np.zeros((1, res, res), np.float32), activation=1.0 if i == 0 else float(d["mei_acts"][i - 1]), mask=masks[i],
+                    center_pos=dict(x=float(xy[i, 0]), y=float(xy[i, 1]))) for i in range(3)}
+    torch.manual_seed(0)
+    im = L.InvarianceManifold(model, meis, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+    sd = {f"func.layer{l}.weight": torch.from_numpy(d[f"W{l}"]) for l in range(5)}
+    sd.update({f"func.layer{l}.bias": torch.from_numpy(d[f"b{l}"]) for l in range(5)})
+    sd.update(B=torch.from_numpy(d["B"]), auxB=torch.from_numpy(d["auxB"]))
+    im.template.load_state_dict(sd, strict=False)
+    im.template_neuron_idx, im.target_neuron_idxs = 0, targets
+    t = im.template
+    t.initialize_coordinate_transform(2, True, False, 0.1, True, True, False, True)
+    t.register_coords_shifts(torch.from_numpy(d["template_xy"]).cuda(), torch.from_numpy(d["target_xy"]).cuda())
+    aff = t.coordinate_transform.transforms.Affine
+    with torch.no_grad():
+        aff.angles.copy_(torch.from_numpy(d["angles0"])), aff.scalings.copy_(torch.from_numpy(d["scalings0"]))
+        aff.shears.copy_(torch.from_numpy(d["shears0"])), aff.translation.copy_(torch.from_numpy(d["translation0"])[:, None, :])
+    st = MatchStepper(t, im.img_transforms, model, targets, d["mei_acts"].astype(np.float32), 20, precision=im.precision)
+    dl = JitteringGridDatamodule(num_invariances=1, grid_points_per_dim=20, steps_per_epoch=1)
+    im.initialize_with_best_angle_and_translation(t, model, im.img_transforms, dl, np.arange(2), targets, template_rf_mask=d["template_mask"],
+                                                  others_rf_mask=d["target_masks"], rotate_angle_and_scale=True, find_best_translation=with_t,
+                                                  _stepper=st)
+    np.testing.assert_array_equal(aff.angles.detach().cpu().numpy(), d[f"angles_{tag}"])
+    np.testing.assert_allclose(aff.scalings.detach().cpu().numpy(), d[f"scalings_{tag}"], rtol=1e-6)
+    np.testing.assert_allclose(aff.translation.detach().cpu().numpy()[:, 0], d[f"translation_{tag}"], rtol=0, atol=1e-7)
+    # the table itself (angle-only candidates at the scalings the sweep uses, the translation at its initial value)
+    if not with_t:
+        angles = np.linspace(0, 2 * np.pi, 61)[:-1].astype(np.float32)
+        got = st.sweep(dl.grid.cuda(), angles).cpu().numpy()
+        assert relerr(got, d["table_a"][:, 0, 0]) < 1e-4
+
+
 def test_get_mei_dict_known_answer(L):
     """demo1 filters are unit-norm and images are constrained to norm 1, so the MEI activation is (elu(1)+1)/2 + 1e-6
     (the reference measures 1.0000009536743164 for all three neurons)."""

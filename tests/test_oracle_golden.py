@@ -292,3 +292,45 @@ def test_torch_port_conv_response_matches_reference():
     loss.backward()
     for l in range(5):
         assert relerr(port.W[l].grad.numpy(), d[f"dW{l}"]) < 1e-3, l
+
+
+def test_init_sweep_table_and_choice():
+    """Match initialisation sweep (inv_temp_learn_match.py:573-650): the oracle's no-grad forward reproduces the table of mean activations the
+    UNMODIFIED reference function builds (recorded by oracle/make_golden_sweep.py), and the reference's final choice is the first maximum of that
+    table in (angle, tx, ty) order with the scalings set to template-mask / target-mask size on both axes."""
+    d = golden("init_sweep_20")
+    W, b = net_params(d)
+    res = (20, 20)
+    banks = [O.demo1_banks(list(res))[k] for k in d["targets"]]
+    shift_to, tc, shift_from = O.coords_shifts(d["template_xy"], d["target_xy"], res)
+    angles = np.linspace(0, 2 * np.pi, 61)[:-1].astype(np.float32)
+    trs = np.linspace(-0.1, 0.1, 11).astype(np.float32)
+    inv = (1.0 / (d["target_masks"].sum(axis=(1, 2)) / d["template_mask"].sum())).astype(np.float32)
+    for tag in ("a", "at"):
+        np.testing.assert_allclose(d[f"scalings_{tag}"], np.repeat(inv[:, None], 2, axis=1), rtol=1e-6)
+
+    def mean_acts(angle, trans):
+        M, _ = O.affine_matrices(np.full(2, angle, np.float32), d["scalings_a"], d["shears0"])
+        cdp = O.match_coords(d["coords"], M, trans, tc, shift_to, shift_from, True)
+        img = O.inr_forward(W, b, d["B"], d["auxB"], d["grid"], cdp, res)
+        D, N = img.shape[:2]
+        z, _ = O.constrain_norm_fwd(img.reshape((D * N,) + img.shape[2:]), 1.0, 0.0, -1.0, 1.0)
+        zs = z.reshape(img.shape)
+        return np.array([O.simresp_fwd(zs[k], banks[k])[0].mean() for k in range(D)])
+
+    # angle only (the `match` default): all 60 candidates; the translation keeps its (noisy) initial value
+    got = np.stack([mean_acts(a, d["translation0"]) for a in angles])
+    assert relerr(got, d["table_a"][:, 0, 0]) < 2e-5
+    for k in range(2):
+        assert angles[np.argmax(got[:, k])] == d["angles_a"][k] == angles[np.argmax(d["table_a"][:, 0, 0, k])]
+    np.testing.assert_array_equal(d["translation_a"], d["translation0"])
+    # angle + translation: a sub-grid of the 60 x 11 x 11 candidates, and the reference's choice == first maximum of ITS table
+    for i in range(0, 60, 10):
+        for j in (0, 5, 10):
+            for k in (0, 5, 10):
+                tr = np.tile(np.array([trs[j], trs[k]], np.float32), (2, 1))
+                np.testing.assert_allclose(mean_acts(angles[i], tr), d["table_at"][i, j, k], rtol=3e-5)
+    best = np.argmax(d["table_at"].reshape(-1, 2), axis=0)
+    bi, bj, bk = np.unravel_index(best, (60, 11, 11))
+    np.testing.assert_array_equal(d["angles_at"], angles[bi])
+    np.testing.assert_array_equal(d["translation_at"], np.stack([trs[bj], trs[bk]], axis=1))
