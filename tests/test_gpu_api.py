@@ -273,6 +273,25 @@ def test_init_sweep_vs_reference_golden(L, with_t):
         assert relerr(got, d["table_a"][:, 0, 0]) < 1e-4
 
 
+def test_get_mei_dict_vs_reference_call_100(L):
+    """`get_mei_dict` on demo1 at 100x100 (BASELINE configs[0], first call of the quick start) against the output of the UNMODIFIED reference call with
+    the same seeds (tests/golden/mei_dict_100.npz, oracle/make_golden_meis.py): activations, MEI images, RF masks and their centroids."""
+    d = golden("mei_dict_100")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    model = L.neuron_models.simulated("demo1", img_res=[100, 100]).cuda()
+    meis = L.get_mei_dict(model, [1, 100, 100], pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0, required_img_norm=1.0)
+    assert sorted(meis) == [0, 1, 2]
+    for i in range(3):
+        assert abs(float(meis[i]["activation"]) - d["activations"][i]) < 2e-6
+        assert relerr(np.asarray(meis[i]["mei"], np.float32), d["meis"][i].astype(np.float32)) < 3e-3  # float16 fixture (5e-4) + 1000 ascent steps
+        m, want = np.asarray(meis[i]["mask"], np.float32), d["masks"][i]
+        assert m.shape == want.shape == (100, 100)
+        assert (m > 0.5).sum() == (want > 0.5).sum()
+        assert np.abs(m - want).mean() < 1e-4 and np.abs(m - want).max() < 0.35  # at most a hull-boundary pixel apart
+        assert abs(meis[i]["center_pos"]["x"] - d["centers"][i, 0]) < 0.05 and abs(meis[i]["center_pos"]["y"] - d["centers"][i, 1]) < 0.05
+
+
 def test_get_mei_dict_known_answer(L):
     """demo1 filters are unit-norm and images are constrained to norm 1, so the MEI activation is (elu(1)+1)/2 + 1e-6
     (the reference measures 1.0000009536743164 for all three neurons)."""
