@@ -273,6 +273,34 @@ def test_init_sweep_vs_reference_golden(L, with_t):
         assert relerr(got, d["table_a"][:, 0, 0]) < 1e-4
 
 
+def test_match_call_vs_reference_call(L):
+    """A whole `match([1, 2], num_epochs=5)` call (transform initialisation, 60-angle sweep, five jittered Adam epochs, final snapshot) against the
+    same call of the UNMODIFIED reference with the same seeds (tests/golden/match_call_20.npz, oracle/make_golden_match_call.py): final affine
+    parameters, images and activations within the north star's tolerances, and the CPU generator left in the same state."""
+    d = golden("match_call_20")
+    res = 20
+    model = L.neuron_models.simulated("demo1", img_res=[res, res]).cuda()
+    meis = {i: dict(mei=np.zeros((1, res, res), np.float32), activation=float(d["mei_acts"][i]), mask=d["masks"][i],
+                    center_pos=dict(x=float(d["centers"][i, 0]), y=float(d["centers"][i, 1]))) for i in range(3)}
+    torch.manual_seed(0)
+    im = L.InvarianceManifold(model, meis, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+    sd = {f"func.layer{l}.weight": torch.from_numpy(d[f"W{l}"]) for l in range(5)}
+    sd.update({f"func.layer{l}.bias": torch.from_numpy(d[f"b{l}"]) for l in range(5)})
+    sd.update(B=torch.from_numpy(d["B"]), auxB=torch.from_numpy(d["auxB"]))
+    im.template.load_state_dict(sd, strict=False)
+    im.template_neuron_idx = 0
+    torch.manual_seed(5)
+    imgs, acts = im.match([1, 2], num_epochs=5)
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(d["rng_after"]))
+    aff = im.template.coordinate_transform.transforms.Affine
+    np.testing.assert_allclose(aff.angles.detach().cpu().numpy(), d["angles"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(aff.scalings.detach().cpu().numpy(), d["scalings"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(aff.shears.detach().cpu().numpy(), d["shears"], rtol=0, atol=2e-4)        # five Adam steps of 1e-3 from 0
+    np.testing.assert_allclose(aff.translation.detach().cpu().numpy()[:, 0], d["translation"], rtol=0, atol=2e-4)
+    assert imgs.shape == d["imgs"].shape and acts.shape == d["acts"].shape
+    assert relerr(imgs, d["imgs"]) < 1e-2 and relerr(acts, d["acts"]) < 1e-2  # north star: final images and activations within 1e-2 relative
+
+
 def test_get_mei_dict_vs_reference_call_100(L):
     """`get_mei_dict` on demo1 at 100x100 (BASELINE configs[0], first call of the quick start) against the output of the UNMODIFIED reference call with
     the same seeds (tests/golden/mei_dict_100.npz, oracle/make_golden_meis.py): activations, MEI images, RF masks and their centroids."""
