@@ -222,3 +222,70 @@ def test_simresp_workspace_follows_the_group_count(L):
     assert set(chunks.values()) == {20, 40, 79}                       # 512 / 256 / 128 pixels per CTA at 100 x 100
     assert chunks[1] == 79 and chunks[8] == 40 and chunks[32] == 20
     assert lib.lmr_simresp_workspace_bytes(7, NB, F, HW) > lib.lmr_simresp_workspace_bytes(8, NB, F, HW)
+
+
+def _header_prototypes():
+    """name -> (return type, [parameter type strings]) parsed from include/laminr_b200.h (comments stripped)."""
+    src = open(os.path.join(ROOT, "include", "laminr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", " ", src)
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(lmr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        ret, name, params = m.group(1).replace("LMR_API", "").strip(), m.group(2), " ".join(m.group(3).split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        out[name] = (ret, plist)
+    return out
+
+
+def _ctype_of(decl):
+    """C parameter declaration -> the ctypes type the binding must use."""
+    from laminr_b200 import _lib
+    if "*" in decl:
+        for struct, ct in (("lmr_inr_desc", _lib.InrDesc), ("lmr_affine", _lib.Affine), ("lmr_convcore_desc", _lib.ConvcoreDesc),
+                           ("lmr_convcore_weights", _lib.ConvcoreWeights)):
+            if re.search(rf"\b{struct}\b", decl):
+                return ctypes.POINTER(ct)
+        return ctypes.c_char_p if re.match(r"const char\s*\*$", decl) else ctypes.c_void_p
+    base = re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*$", "", decl).strip() or decl  # drop the parameter name
+    base = base.replace("const ", "").strip()
+    return {"int": ctypes.c_int, "float": ctypes.c_float, "size_t": ctypes.c_size_t, "long long": ctypes.c_longlong}[base]
+
+
+def test_ctypes_signatures_match_the_header_prototypes(L):
+    """Every prototype of include/laminr_b200.h against the ctypes binding: same parameter count and, position by position, the same C type class
+    (an int / float / size_t / pointer mix-up would corrupt the call frame silently)."""
+    from laminr_b200 import _lib
+    protos = _header_prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, (ret, params) in protos.items():
+        res, args = _lib.SIGNATURES[name]
+        assert len(args) == len(params), (name, len(args), len(params))
+        for i, (decl, got) in enumerate(zip(params, args)):
+            assert _ctype_of(decl) is got, (name, i, decl, got)
+        assert _ctype_of(ret + " x" if "*" not in ret else ret) is res, (name, ret, res)
+
+
+def test_host_only_abi_functions(L):
+    """The entry points that never touch the device: parameter count, workspace sizes (monotone in the extents; the kept-activation forward
+    needs room for three 32 KB operand tiles per 128 rows on top), and argument errors reported through lmr_last_error."""
+    from laminr_b200 import _lib
+    lib = _lib.load()
+    d1, d3 = _lib.InrDesc(50, 4, 50, 50, 1), _lib.InrDesc(50, 4, 50, 50, 3)
+    assert lib.lmr_inr_params_count(ctypes.byref(d1)) == 17801               # SURVEY 8a row a-11
+    assert lib.lmr_inr_params_count(ctypes.byref(d3)) == 17801 + 2 * 51
+    for fn in (lib.lmr_inr_forward_workspace_bytes, lib.lmr_inr_backward_workspace_bytes, lib.lmr_inr_forward_workspace_bytes_keep):
+        base = fn(ctypes.byref(d1), 20, 10000, 1)
+        assert base > 0
+        assert fn(ctypes.byref(d1), 20, 40000, 1) >= base and fn(ctypes.byref(d1), 40, 10000, 1) >= base
+        # D == 1 additionally holds the sin/cos(coords.B) table of the layer-0 weight gradient (learn); from D = 2 on the size grows with D
+        assert fn(ctypes.byref(d1), 20, 10000, 4) >= fn(ctypes.byref(d1), 20, 10000, 2) > 0
+    plain, keep = lib.lmr_inr_forward_workspace_bytes(ctypes.byref(d1), 20, 10000, 1), lib.lmr_inr_forward_workspace_bytes_keep(ctypes.byref(d1), 20, 10000, 1)
+    rows = 20 * 10000
+    assert keep - plain >= (rows // 128) * 3 * 32768
+    assert lib.lmr_constrain_workspace_bytes(20, 1) > 0 and lib.lmr_simclr_workspace_bytes(20, 1, 10000) > 0
+    assert lib.lmr_learn_objective_workspace_bytes(20, 1, 10000, 20) > 0 and lib.lmr_create_mask_workspace_bytes(3, 100, 100) > 0
+    # an unknown precision is rejected before anything is launched
+    rc = lib.lmr_inr_forward(ctypes.byref(d1), None, None, None, None, 20, None, 100, None, None, 1, None, None, 0, 77, None)
+    assert rc != 0 and b"precision" in lib.lmr_last_error()
+    with pytest.raises(_lib.LaminrB200Error, match="precision"):
+        _lib.check(rc)
