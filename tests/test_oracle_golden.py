@@ -334,3 +334,47 @@ def test_init_sweep_table_and_choice():
     bi, bj, bk = np.unravel_index(best, (60, 11, 11))
     np.testing.assert_array_equal(d["angles_at"], angles[bi])
     np.testing.assert_array_equal(d["translation_at"], np.stack([trs[bj], trs[bk]], axis=1))
+
+
+def test_learn_call_replayed_with_the_oracle_and_the_host_stream():
+    """The reference's whole `learn(0, steps_per_epoch=5, num_max_epochs=4)` call (tests/golden/learn_call_20.npz, oracle/make_golden_learn_call.py)
+    replayed from seeds alone: the product's CPU-side constructor (initial network, inr.py:49-51 draw order) and jittered-grid stream
+    (training.py:18-53) feed the numpy oracle's learn step + Adam; final network, images, activations and the generator state must be the call's."""
+    import torch
+    import laminr_b200 as L
+    from laminr_b200.utils.training import JitteringGridDatamodule
+    d = golden("learn_call_20")
+    res = 20
+    meis = {i: dict(mei=np.zeros((1, res, res), np.float32), activation=float(d["mei_acts"][i]), mask=d["masks"][i],
+                    center_pos=dict(x=float(d["centers"][i, 0]), y=float(d["centers"][i, 1]))) for i in range(3)}
+    torch.manual_seed(0)
+    im = L.InvarianceManifold(L.neuron_models.simulated("demo1", img_res=[res, res]), meis, device="cpu", required_img_norm=1.0,
+                              pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+    sd = {k: v.numpy().copy() for k, v in im.template.state_dict().items()}
+    W, b = [sd[f"func.layer{l}.weight"] for l in range(5)], [sd[f"func.layer{l}.bias"] for l in range(5)]
+    coords = sd["coords"].reshape(-1, 2)
+    mW, vW = [np.zeros_like(w) for w in W], [np.zeros_like(w) for w in W]
+    mb, vb = [np.zeros_like(x) for x in b], [np.zeros_like(x) for x in b]
+    pos, neg = O.pos_neg_masks(20, 0.1, True)
+    bank = O.demo1_banks([res, res])[0]
+    torch.manual_seed(11)
+    dm = JitteringGridDatamodule(num_invariances=1, grid_points_per_dim=20, steps_per_epoch=5)
+    dm.train_dataloader()  # the reference builds (and discards) one loader before the loop: one jitter draw (inv_temp_learn_match.py:137)
+    step = 0
+    for _ in range(4):
+        for g in dm.train_dataloader():
+            out = O.learn_step(W, b, sd["B"], sd["auxB"], g[:, 0].numpy(), coords, (res, res), bank, d["masks"][0], float(d["mei_acts"][0]), 2.0, 1.0,
+                               -1.0, 1.0, pos, neg, 0.3)
+            step += 1
+            for l in range(5):
+                W[l], mW[l], vW[l] = O.adam_step(W[l], out["dW"][l], mW[l], vW[l], step)
+                b[l], mb[l], vb[l] = O.adam_step(b[l], out["db"][l], mb[l], vb[l], step)
+    assert step == 20
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(d["short_rng_after"]))
+    for l in range(5):
+        assert relerr(W[l], d[f"short_W{l}"]) < 2e-3, l
+        assert relerr(b[l], d[f"short_b{l}"]) < 2e-2, l     # biases start at 0: twenty lr-sized steps, sign-ambiguous entries weigh more
+    final = O.learn_step(W, b, sd["B"], sd["auxB"], O.latent_grid(20), coords, (res, res), bank, d["masks"][0], float(d["mei_acts"][0]), 2.0, 1.0, -1.0,
+                         1.0, pos, neg, 0.3)
+    assert relerr(final["img_post"].reshape(d["short_imgs"].shape), d["short_imgs"]) < 1e-2
+    assert relerr(final["acts"], d["short_acts"]) < 1e-2
