@@ -9,7 +9,6 @@ lmr_inr_backward.
 """
 from collections import OrderedDict
 
-import numpy as np
 import torch
 from torch import nn
 

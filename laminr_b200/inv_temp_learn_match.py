@@ -22,7 +22,6 @@ from . import ops
 from .contrastive_loss import SimCLROnGrid
 from .fused import LearnStepper, MatchStepper, fused_response_supported
 from .inr import INRTemplates
-from .neuron_models.utils.simulated_model import ArbitraryMultiNeuronModel
 from .utils.general import SingleNeuronModel, infer_device
 from .utils.img_transforms import FixEnergyNormClip, StandardizeClip
 from .utils.training import ImprovementChecker, JitteringGridDatamodule, ParamReduceOnPlateau, check_activity_requirements

@@ -19,7 +19,7 @@ import os
 import numpy as np
 import torch
 
-from oracle.make_golden import OUT, npy, synthetic_meis, template_arrays
+from oracle.make_golden import OUT, synthetic_meis, template_arrays
 from oracle.ref_harness import import_reference
 
 

@@ -4,8 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import laminr_oracle as O
-from tests._util import golden, relerr, flat_params, split_flat
+from tests._util import golden, relerr, split_flat
 
 pytestmark = pytest.mark.gpu
 
