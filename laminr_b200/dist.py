@@ -119,6 +119,8 @@ def match_sharded(im, target_neuron_idxs, **match_kwargs):
     D = len(targets)
     if world == 1:
         return im.match(targets, **match_kwargs)
+    if D < world:  # decided from the arguments alone, so EVERY rank raises (a rank that raised alone would leave the others waiting in a collective)
+        raise ValueError(f"match_sharded: {D} targets cannot be split over {world} ranks (every rank needs at least one target)")
     import os, sys, time
     timing = os.environ.get("LMR_TIMING") == "1"  # debug: per-phase wall clock of rank 0 on stderr (adds synchronisations)
     marks = []
@@ -135,8 +137,6 @@ def match_sharded(im, target_neuron_idxs, **match_kwargs):
     broadcast_module_state(im.template, src=0)
     broadcast_rng_state(src=0, device=device)
     lo, hi = shard_bounds(D, world, rank)
-    if hi == lo:
-        raise ValueError(f"match_sharded: {D} targets cannot be split over {world} ranks (every rank needs at least one target)")
     fused = im._fused_ok()
     mark("broadcasts")
     imgs, acts = im.match(targets[lo:hi], _total_targets=D, _stop_reduce=make_stop_reduce(device), _return_device=fused, **match_kwargs)
@@ -180,7 +180,8 @@ def get_mei_dict_sharded(model, input_shape, pixel_value_lower_bound, pixel_valu
     broadcast_rng_state(src=0, device=items[0].device if items else None)
     if lo > 0:
         torch.randn(lo, *input_shape)
-    local = get_mei_dict(model, input_shape, pixel_value_lower_bound, pixel_value_upper_bound, neuron_idxs=neuron_idxs[lo:hi], **kwargs)
+    # fewer neurons than ranks: the ranks without a neuron only keep the generator in step and take part in the gather
+    local = get_mei_dict(model, input_shape, pixel_value_lower_bound, pixel_value_upper_bound, neuron_idxs=neuron_idxs[lo:hi], **kwargs) if hi > lo else {}
     if hi < len(neuron_idxs):  # ... and of the higher ranks: every rank leaves the generator where the unsharded call would (same jitter in `learn`)
         torch.randn(len(neuron_idxs) - hi, *input_shape)
     parts = [None] * world

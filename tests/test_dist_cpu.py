@@ -102,3 +102,60 @@ def test_shard_bounds_cover_everything():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _worker_small(rank, world, port, n_neurons, q):
+    """Fewer items than ranks / ragged MEI shards: no rank may be left alone in a collective."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from laminr_b200 import dist as D
+        import laminr_b200.utils.mei as mei_mod
+
+        shape = [1, 4, 4]
+
+        def fake_get_mei_dict(model, input_shape, lo_b, hi_b, neuron_idxs=None, **kw):
+            # like the real one: one starting image per neuron, in order, from the CPU generator (laminr/utils/mei.py:33); keys = enumeration index
+            x0 = torch.randn(len(neuron_idxs), *input_shape)
+            return {k: dict(idx=int(i), x0=x0[k].numpy().copy()) for k, i in enumerate(neuron_idxs)}
+
+        mei_mod.get_mei_dict = fake_get_mei_dict
+        torch.manual_seed(50 + rank)  # the ranks start out of step: rank 0's generator must win
+        out = D.get_mei_dict_sharded(torch.nn.Identity(), shape, -1.0, 1.0, neuron_idxs=list(range(10, 10 + n_neurons)))
+        after = torch.rand(2).numpy().copy()
+
+        class FakeManifold:
+            template = torch.nn.Linear(2, 2)
+
+        err = None
+        try:
+            D.match_sharded(FakeManifold(), [3] if world > 1 else [])
+        except ValueError as e:
+            err = str(e)
+        q.put((rank, {k: (v["idx"], v["x0"]) for k, v in out.items()}, after, err))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_neurons", [1, 5])
+def test_sharded_mei_dict_and_too_few_targets_world2(n_neurons):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_small, args=(r, world, port, n_neurons, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # the unsharded call: rank 0's seed, one draw of all starting images
+    torch.manual_seed(50)
+    x0 = torch.randn(n_neurons, 1, 4, 4).numpy()
+    want_after = torch.rand(2).numpy()
+    for rank, out, after, err in res:
+        assert list(out) == list(range(n_neurons))                                   # the full dict on EVERY rank, enumeration keys
+        for k in range(n_neurons):
+            assert out[k][0] == 10 + k and np.array_equal(out[k][1], x0[k])          # each neuron started from the image the unsharded call draws
+        assert np.array_equal(after, want_after)                                     # ... and the generator is left where that call leaves it
+        assert err is not None and "cannot be split" in err                          # one target over two ranks: every rank raises, nobody hangs
