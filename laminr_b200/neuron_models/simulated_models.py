@@ -5,14 +5,18 @@ Mirror of laminr/neuron_models/simulated_models.py:74-139 (`neuron2_generator`),
 element of the reference's tuple is a plotting grid (visualisation only, out of scope)."""
 import numpy as np
 
-from .utils.simulated_model import ArbitraryMultiNeuronModel, ArbitraryNeuronModel, generate_gabor_filter, random_transformation_matrices
+from .utils.simulated_model import (ArbitraryMultiNeuronModel, ArbitraryNeuronModel, gabor_geometry, generate_gabor_filter,
+                                    random_transformation_matrices)
 
 
 def phase_invariant_neuron_generator(loc, img_res, transformation_matrix=None, unit_norm=True, num_filters=32):
     filters = []
+    # the filters of the bank share centre, widths and transform: coordinates and envelope once, one cosine per phase (same values as a
+    # `generate_gabor_filter` call per phase, simulated_models.py:243-274)
+    xx, envelope = gabor_geometry(theta=0, width_x=0.14, width_y=0.14, center=loc, grid_size=img_res, transformation_matrix=transformation_matrix)
+    carrier = 2 * np.pi * 2.3 * xx
     for phase in np.linspace(0, 2 * np.pi, num_filters, endpoint=False):
-        gb = generate_gabor_filter(theta=0, width_x=0.14, width_y=0.14, frequency=2.3, phase=phase, center=loc, grid_size=img_res,
-                                   transformation_matrix=transformation_matrix)
+        gb = envelope * np.cos(carrier + phase)
         if unit_norm:
             gb = gb / np.linalg.norm(gb)
         filters.append(gb.astype(np.float32))
@@ -54,6 +58,12 @@ def simulated_population(n_neurons, img_res=[100, 100], seed=0, num_filters=20):
     np.random.seed(seed)
     mats = random_transformation_matrices(n_neurons)
     locs = np.random.uniform(-0.35, 0.35, size=(n_neurons, 2))
-    models = [phase_invariant_neuron_generator(locs[i], img_res, transformation_matrix=None if i == 0 else mats[i], num_filters=num_filters)[0]
-              for i in range(n_neurons)]
-    return ArbitraryMultiNeuronModel(models)
+    import torch
+    packed = torch.empty(n_neurons, num_filters, int(img_res[1]), int(img_res[0]))  # meshgrid 'xy': rows = grid_size[1]
+    models = []
+    for i in range(n_neurons):
+        m = phase_invariant_neuron_generator(locs[i], img_res, transformation_matrix=None if i == 0 else mats[i], num_filters=num_filters)[0]
+        packed[i].copy_(m.filters)
+        m.filters = packed[i]  # the per-neuron buffer becomes a view of the packed bank: one copy of the population in host memory
+        models.append(m)
+    return ArbitraryMultiNeuronModel(models, packed=packed)

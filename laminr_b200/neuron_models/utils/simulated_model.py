@@ -21,8 +21,10 @@ def _transform_pattern(xx, yy, mat, centre):
     return xr + px, yr + py
 
 
-def generate_gabor_filter(theta, width_x, width_y, frequency, phase, center, grid_size, transformation_matrix=None):
-    """Gaussian envelope x cosine carrier on a [-1,1]^2 grid ('xy' meshgrid: filter[i, j] has x = column j, y = row i)."""
+def gabor_geometry(theta, width_x, width_y, center, grid_size, transformation_matrix=None):
+    """The phase- and frequency-independent part of `generate_gabor_filter`: transformed x coordinates and the Gaussian envelope.  A bank whose
+    filters differ only in phase / frequency (phase_invariant_neuron_generator: 20..32 phases per neuron) computes this once; the per-filter values
+    are the same floating-point operations on the same operands, so the banks stay bit-identical to the reference's."""
     xx, yy = np.meshgrid(np.linspace(-1, 1, grid_size[0]), np.linspace(-1, 1, grid_size[1]))
     dx, dy = center
     xx, yy = xx - dx, yy - dy  # translate
@@ -31,6 +33,12 @@ def generate_gabor_filter(theta, width_x, width_y, frequency, phase, center, gri
     if transformation_matrix is not None:  # global transform about the image centre
         xx, yy = _transform_pattern(xx, yy, transformation_matrix, rot @ (0 - dx, 0 - dy))
     envelope = np.exp(-0.5 * (xx**2 / width_x**2 + yy**2 / width_y**2))
+    return xx, envelope
+
+
+def generate_gabor_filter(theta, width_x, width_y, frequency, phase, center, grid_size, transformation_matrix=None):
+    """Gaussian envelope x cosine carrier on a [-1,1]^2 grid ('xy' meshgrid: filter[i, j] has x = column j, y = row i)."""
+    xx, envelope = gabor_geometry(theta, width_x, width_y, center, grid_size, transformation_matrix)
     return envelope * np.cos(2 * np.pi * frequency * xx + phase)
 
 
@@ -68,14 +76,19 @@ class ArbitraryMultiNeuronModel(nn.Module):
     """Population of simulated neurons -> [B, n] (simulated_model.py:20-29).  The per-neuron banks are packed into one
     `[n, Fmax, H*W]` buffer (ragged banks padded by repeating their first filter: the max is unaffected)."""
 
-    def __init__(self, neuron_models_list):
+    def __init__(self, neuron_models_list, packed=None):
+        """`packed` (optional): a `[n, F, H, W]` tensor that already holds the banks (equal filter counts) and that the per-neuron `filters` buffers
+        are views of -- large populations are then built without a second copy of the bank (819 MB for 1024 neurons at 100x100)."""
         super().__init__()
         self.neuron_models_list = nn.ModuleList(neuron_models_list)
         banks = [m.filters for m in neuron_models_list]
         self.eps = neuron_models_list[0].eps
         fmax = max(b.shape[0] for b in banks)
         self.img_res = tuple(banks[0].shape[1:])
-        packed = torch.stack([torch.cat([b, b[:1].expand(fmax - b.shape[0], -1, -1)]) if b.shape[0] < fmax else b for b in banks])
+        if packed is None:
+            packed = torch.stack([torch.cat([b, b[:1].expand(fmax - b.shape[0], -1, -1)]) if b.shape[0] < fmax else b for b in banks])
+        elif tuple(packed.shape) != (len(banks), fmax) + self.img_res or any(b.shape[0] != fmax for b in banks):
+            raise ValueError("ArbitraryMultiNeuronModel: `packed` must be [n, F, H, W] with every neuron holding F filters")
         self.register_buffer("packed_filters", packed.reshape(len(banks), fmax, -1).contiguous(), persistent=False)
         self.register_buffer("nfilt", torch.tensor([b.shape[0] for b in banks], dtype=torch.int32), persistent=False)
         self.register_buffer("all_neurons", torch.arange(len(banks), dtype=torch.int32), persistent=False)
