@@ -76,8 +76,8 @@ def make_stop_reduce(device=None):
 
 
 def gather_ragged(local, n_total, dst=0):
-    """Concatenates per-rank blocks along dim 0 (block sizes from `shard_bounds`) on rank `dst`; returns None elsewhere.
-    `local` is this rank's block (may be empty) of a tensor whose dim-0 length over all ranks is `n_total`."""
+    """Concatenates per-rank blocks along dim 0 (block sizes from `shard_bounds`) on rank `dst` (returns None elsewhere), or on EVERY rank with
+    `dst=None`.  `local` is this rank's block (may be empty) of a tensor whose dim-0 length over all ranks is `n_total`."""
     world, rank = _world()
     if world == 1:
         return local
@@ -94,19 +94,22 @@ def gather_ragged(local, n_total, dst=0):
         # result, 0.8 GB for 1023 targets at 100x100, which only `dst` keeps.)
         full = torch.empty((world * nmax,) + tuple(pad.shape[1:]), dtype=pad.dtype, device=pad.device)
         dist.all_gather_into_tensor(full, pad)
-        if rank != dst:
+        if dst is not None and rank != dst:
             return None
         if all(sz == nmax for sz in sizes):
             return full
         return torch.cat([full[r * nmax: r * nmax + sizes[r]] for r in range(world)], dim=0)
     # gloo (CPU tests of the plumbing) gathers host tensors only
     dev = pad.device
-    host = [torch.empty_like(pad, device="cpu") for _ in range(world)] if rank == dst else None
-    dist.gather(pad.cpu(), gather_list=host, dst=dst)
-    bufs = [h.to(dev) for h in host] if rank == dst else None
-    if rank != dst:
-        return None
-    return torch.cat([bufs[r][: sizes[r]] for r in range(world)], dim=0)
+    if dst is None:
+        host = [torch.empty_like(pad, device="cpu") for _ in range(world)]
+        dist.all_gather(host, pad.cpu())
+    else:
+        host = [torch.empty_like(pad, device="cpu") for _ in range(world)] if rank == dst else None
+        dist.gather(pad.cpu(), gather_list=host, dst=dst)
+        if rank != dst:
+            return None
+    return torch.cat([host[r][: sizes[r]].to(dev) for r in range(world)], dim=0)
 
 
 def match_sharded(im, target_neuron_idxs, **match_kwargs):
@@ -184,9 +187,44 @@ def get_mei_dict_sharded(model, input_shape, pixel_value_lower_bound, pixel_valu
     local = get_mei_dict(model, input_shape, pixel_value_lower_bound, pixel_value_upper_bound, neuron_idxs=neuron_idxs[lo:hi], **kwargs) if hi > lo else {}
     if hi < len(neuron_idxs):  # ... and of the higher ranks: every rank leaves the generator where the unsharded call would (same jitter in `learn`)
         torch.randn(len(neuron_idxs) - hi, *input_shape)
-    parts = [None] * world
-    dist.all_gather_object(parts, {lo + k: v for k, v in local.items()})
-    out = {}
-    for part in parts:
-        out.update(part)
-    return dict(sorted(out.items()))
+    return _allgather_mei_entries(local, lo, len(neuron_idxs), items[0].device if items else torch.device("cpu"))
+
+
+_ENTRY_KEYS = ("mei", "activation", "mask", "center_pos")
+
+
+def _allgather_mei_entries(local, lo, n_total, device):
+    """Every rank's `{k: {"mei": ndarray, "activation": float, "mask": ndarray, "center_pos": {..: float}}}` -> the full dict (keys lo + k) on every
+    rank.  The arrays travel as three tensors (images, masks, float64 scalars) through one ragged all-gather each -- pickling the entries
+    (`all_gather_object`) cost more than the whole sharded ascent for 1024 neurons at 100x100 (82 MB of arrays, profiles/r1k_config3.md).  The ranks
+    first exchange a few bytes describing their entries; anything but uniform numpy entries falls back to the pickled gather, on all ranks alike."""
+    world, rank = _world()
+    vals = [local[k] for k in sorted(local)]
+
+    def describe(v):
+        if not (isinstance(v, dict) and tuple(v) == _ENTRY_KEYS and isinstance(v["mei"], np.ndarray) and isinstance(v["mask"], np.ndarray)
+                and isinstance(v["center_pos"], dict) and isinstance(v["activation"], (float, np.floating))
+                and all(isinstance(c, (float, np.floating)) for c in v["center_pos"].values())):
+            return None
+        return (v["mei"].dtype.str, v["mei"].shape, v["mask"].dtype.str, v["mask"].shape, tuple(v["center_pos"]))
+
+    descr = {describe(v) for v in vals}
+    metas = [None] * world
+    dist.all_gather_object(metas, (len(vals), sorted(descr, key=repr) if None not in descr else None))
+    kinds = {d for _, ds in metas if ds is not None for d in ds}
+    if any(n > 0 and ds is None for n, ds in metas) or len(kinds) != 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, {lo + k: v for k, v in local.items()})
+        out = {}
+        for part in parts:
+            out.update(part)
+        return dict(sorted(out.items()))
+    mei_dt, mei_shape, mask_dt, mask_shape, ckeys = next(iter(kinds))
+    dev = device if dist.get_backend() == "nccl" else torch.device("cpu")
+    pack = lambda arrs, dt, shape: torch.from_numpy(np.stack(arrs).astype(dt, copy=False) if arrs else np.empty((0,) + tuple(shape), dt)).to(dev)
+    mei = gather_ragged(pack([v["mei"] for v in vals], mei_dt, mei_shape), n_total, dst=None).cpu().numpy()
+    mask = gather_ragged(pack([v["mask"] for v in vals], mask_dt, mask_shape), n_total, dst=None).cpu().numpy()
+    scal = np.array([[v["activation"]] + [v["center_pos"][c] for c in ckeys] for v in vals], np.float64).reshape(len(vals), 1 + len(ckeys))
+    scal = gather_ragged(torch.from_numpy(scal).to(dev), n_total, dst=None).cpu().numpy()
+    return {k: {"mei": mei[k], "activation": float(scal[k, 0]), "mask": mask[k], "center_pos": {c: float(scal[k, 1 + j]) for j, c in enumerate(ckeys)}}
+            for k in range(n_total)}

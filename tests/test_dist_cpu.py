@@ -104,7 +104,7 @@ def test_shard_bounds_cover_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
-def _worker_small(rank, world, port, n_neurons, q):
+def _worker_small(rank, world, port, n_neurons, arrays, q):
     """Fewer items than ranks / ragged MEI shards: no rank may be left alone in a collective."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -117,7 +117,10 @@ def _worker_small(rank, world, port, n_neurons, q):
         def fake_get_mei_dict(model, input_shape, lo_b, hi_b, neuron_idxs=None, **kw):
             # like the real one: one starting image per neuron, in order, from the CPU generator (laminr/utils/mei.py:33); keys = enumeration index
             x0 = torch.randn(len(neuron_idxs), *input_shape)
-            return {k: dict(idx=int(i), x0=x0[k].numpy().copy()) for k, i in enumerate(neuron_idxs)}
+            if arrays:  # entries shaped like the real ones: they travel as tensors (images, masks, float64 scalars)
+                return {k: {"mei": x0[k].numpy().copy(), "activation": float(np.float32(i) / 3), "mask": x0[k, 0].numpy().copy() * 2,
+                            "center_pos": {"y": i + 0.1, "x": i / 7}} for k, i in enumerate(neuron_idxs)}
+            return {k: dict(idx=int(i), x0=x0[k].numpy().copy()) for k, i in enumerate(neuron_idxs)}  # anything else: pickled gather
 
         mei_mod.get_mei_dict = fake_get_mei_dict
         torch.manual_seed(50 + rank)  # the ranks start out of step: rank 0's generator must win
@@ -132,17 +135,25 @@ def _worker_small(rank, world, port, n_neurons, q):
             D.match_sharded(FakeManifold(), [3] if world > 1 else [])
         except ValueError as e:
             err = str(e)
+        if arrays:
+            for k, v in out.items():
+                i = 10 + k
+                assert tuple(v) == ("mei", "activation", "mask", "center_pos") and v["mei"].dtype == np.float32 and v["mei"].shape == (1, 4, 4)
+                assert type(v["activation"]) is float and v["activation"] == float(np.float32(i) / 3)
+                assert v["center_pos"] == {"y": i + 0.1, "x": i / 7} and list(v["center_pos"]) == ["y", "x"]
+                assert np.array_equal(v["mask"], v["mei"][0] * 2)
+            out = {k: dict(idx=10 + k, x0=v["mei"]) for k, v in out.items()}
         q.put((rank, {k: (v["idx"], v["x0"]) for k, v in out.items()}, after, err))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_neurons", [1, 5])
-def test_sharded_mei_dict_and_too_few_targets_world2(n_neurons):
+@pytest.mark.parametrize("n_neurons,arrays", [(1, False), (5, False), (1, True), (5, True)])
+def test_sharded_mei_dict_and_too_few_targets_world2(n_neurons, arrays):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker_small, args=(r, world, port, n_neurons, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker_small, args=(r, world, port, n_neurons, arrays, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r[0])
