@@ -1,0 +1,59 @@
+"""GPU parity of `InvarianceManifold.match` with NON-DEFAULT transform flags against whole calls of the unmodified reference with the same seeds
+(tests/golden/match_call_variants_20.npz, oracle/make_golden_match_call.py::VARIANTS): which of the seven affine scalars are parameters and their
+shapes (uniform scale = one scaling column, no shear / no scale = buffers Adam must not touch), the coordinate clamp switched off, no initialisation
+sweep with several steps per epoch, and the angle x translation sweep (7260 candidates).  (File name: sorted after the other GPU tests.)"""
+import numpy as np
+import pytest
+import torch
+
+from tests._util import golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = {
+    "uniform_noshear": dict(uniform_scale_coordinate_transformation=True, allow_shear_coordinate_transformation=False),
+    "noscale_noclamp": dict(allow_scale_coordinate_transformation=False, coordinate_transform_clamp_boundaries=False),
+    "nosweep_3steps": dict(rotate_angle_and_scale=False, steps_per_epoch=3),
+    "translation_sweep": dict(find_best_translation=True, num_epochs=2),
+}
+
+
+@pytest.fixture(scope="module")
+def L():
+    from laminr_b200.csrc import build
+    build.build()
+    import laminr_b200
+    return laminr_b200
+
+
+@pytest.mark.parametrize("tag", list(VARIANTS))
+def test_match_call_variant_vs_reference_call(L, tag):
+    d = golden("match_call_variants_20")
+    res = 20
+    model = L.neuron_models.simulated("demo1", img_res=[res, res]).cuda()
+    meis = {i: dict(mei=np.zeros((1, res, res), np.float32), activation=float(d["mei_acts"][i]), mask=d["masks"][i],
+                    center_pos=dict(x=float(d["centers"][i, 0]), y=float(d["centers"][i, 1]))) for i in range(3)}
+    torch.manual_seed(0)
+    im = L.InvarianceManifold(model, meis, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+    sd = {f"func.layer{l}.weight": torch.from_numpy(d[f"W{l}"]) for l in range(5)}
+    sd.update({f"func.layer{l}.bias": torch.from_numpy(d[f"b{l}"]) for l in range(5)})
+    sd.update(B=torch.from_numpy(d["B"]), auxB=torch.from_numpy(d["auxB"]))
+    im.template.load_state_dict(sd, strict=False)
+    im.template_neuron_idx = 0
+    kw = dict(VARIANTS[tag])
+    kw.setdefault("num_epochs", 5)
+    torch.manual_seed(5)
+    imgs, acts = im.match([1, 2], **kw)
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(d[f"{tag}_rng_after"]))
+    aff = im.template.coordinate_transform.transforms.Affine
+    names = {n for n, _ in aff.named_parameters()}
+    assert ("scalings" in names) == kw.get("allow_scale_coordinate_transformation", True)
+    assert ("shears" in names) == kw.get("allow_shear_coordinate_transformation", True)
+    assert aff.scalings.shape == d[f"{tag}_scalings"].shape and aff.shears.shape == d[f"{tag}_shears"].shape
+    # a handful of Adam steps of 1e-3 each: the parameters to half a step
+    np.testing.assert_allclose(aff.angles.detach().cpu().numpy(), d[f"{tag}_angles"], rtol=1e-4, atol=5e-4)
+    np.testing.assert_allclose(aff.scalings.detach().cpu().numpy(), d[f"{tag}_scalings"], rtol=1e-4, atol=5e-4)
+    np.testing.assert_allclose(aff.shears.detach().cpu().numpy(), d[f"{tag}_shears"], rtol=0, atol=5e-4)
+    np.testing.assert_allclose(aff.translation.detach().cpu().numpy()[:, 0], d[f"{tag}_translation"], rtol=0, atol=5e-4)
+    assert imgs.shape == d[f"{tag}_imgs"].shape and acts.shape == d[f"{tag}_acts"].shape
+    assert relerr(imgs, d[f"{tag}_imgs"]) < 1e-2 and relerr(acts, d[f"{tag}_acts"]) < 1e-2  # north star: final images and activations within 1e-2 relative
