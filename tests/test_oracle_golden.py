@@ -378,3 +378,74 @@ def test_learn_call_replayed_with_the_oracle_and_the_host_stream():
                          1.0, pos, neg, 0.3)
     assert relerr(final["img_post"].reshape(d["short_imgs"].shape), d["short_imgs"]) < 1e-2
     assert relerr(final["acts"], d["short_acts"]) < 1e-2
+
+
+_MATCH_VARIANTS = {
+    "default": dict(),
+    "uniform_noshear": dict(uniform_scale_coordinate_transformation=True, allow_shear_coordinate_transformation=False),
+    "noscale_noclamp": dict(allow_scale_coordinate_transformation=False, coordinate_transform_clamp_boundaries=False),
+    "nosweep_3steps": dict(rotate_angle_and_scale=False, steps_per_epoch=3),
+}
+
+
+@pytest.mark.parametrize("tag", list(_MATCH_VARIANTS))
+def test_match_call_replayed_with_the_oracle_and_the_host_stream(tag):
+    """Whole `match([1, 2], num_epochs=5, ...)` calls of the unmodified reference (tests/golden/match_call_20.npz, match_call_variants_20.npz;
+    oracle/make_golden_match_call.py) replayed from the seed alone: the 60-angle initialisation sweep (:573-650), the product's jittered-grid stream,
+    the oracle's match step and Adam over exactly the scalars the flags leave trainable (:257-278, coordinate_transforms.py:226-262), the final
+    un-jittered snapshot; the CPU generator must end where the call leaves it."""
+    import torch
+    from laminr_b200.utils.training import JitteringGridDatamodule
+    kw = _MATCH_VARIANTS[tag]
+    d = golden("match_call_20" if tag == "default" else "match_call_variants_20")
+    pre = "" if tag == "default" else tag + "_"
+    res, targets, D = (20, 20), [1, 2], 2
+    W, b = [d[f"W{l}"] for l in range(5)], [d[f"b{l}"] for l in range(5)]
+    banks = [O.demo1_banks(list(res))[k] for k in targets]
+    mei_acts = d["mei_acts"][targets]
+    shifts = O.coords_shifts(d["centers"][0].astype(np.float32), d["centers"][targets].astype(np.float32), res)
+    clamp = kw.get("coordinate_transform_clamp_boundaries", True)
+    uniform = kw.get("uniform_scale_coordinate_transformation", False)
+    P = dict(angles=np.zeros(D, np.float32), scalings=np.ones((D, 1 if uniform else 2), np.float32), shears=np.zeros((D, 2), np.float32),
+             translation=np.zeros((D, 2), np.float32))
+    trainable = ["angles", "translation"] + (["scalings"] if kw.get("allow_scale_coordinate_transformation", True) else []) + \
+                (["shears"] if kw.get("allow_shear_coordinate_transformation", True) else [])
+    full = lambda: dict(P, scalings=np.repeat(P["scalings"], 2, axis=1) if uniform else P["scalings"])
+    grid0 = O.latent_grid(20)
+
+    def forward(grid):
+        M, _ = O.affine_matrices(P["angles"], full()["scalings"], P["shears"])
+        cdp = O.match_coords(d["coords"], M, P["translation"], shifts[1], shifts[0], shifts[2], clamp)
+        img = O.inr_forward(W, b, d["B"], d["auxB"], grid, cdp, res)
+        z, _ = O.constrain_norm_fwd(img.reshape((D * 20,) + img.shape[2:]), 1.0, 0.0, -1.0, 1.0)
+        zs = z.reshape(img.shape)
+        return zs, np.stack([O.simresp_fwd(zs[k], banks[k])[0] for k in range(D)])
+
+    torch.manual_seed(5)
+    dm = JitteringGridDatamodule(num_invariances=1, grid_points_per_dim=20, steps_per_epoch=kw.get("steps_per_epoch", 1))
+    if kw.get("rotate_angle_and_scale", True):
+        inv = (1.0 / (d["masks"][targets].sum(axis=(1, 2)) / d["masks"][0].sum())).astype(np.float32)
+        P["scalings"] = np.ones_like(P["scalings"]) * inv[:, None]
+        angles = np.linspace(0, 2 * np.pi, 61)[:-1].astype(np.float32)
+        table = np.zeros((60, D))
+        for i, a in enumerate(angles):
+            P["angles"] = np.full(D, a, np.float32)
+            table[i] = forward(grid0)[1].mean(axis=1)
+        P["angles"] = angles[np.argmax(table, axis=0)]
+    m, v = {k: np.zeros_like(P[k]) for k in trainable}, {k: np.zeros_like(P[k]) for k in trainable}
+    step = 0
+    for _ in range(5):
+        for g in dm.train_dataloader():
+            out = O.match_step(W, b, d["B"], d["auxB"], g[:, 0].numpy(), d["coords"], res, banks, mei_acts, full(), shifts, 1.0, -1.0, 1.0, clamp=clamp)
+            grads = dict(angles=out["d_angles"], shears=out["d_shears"], translation=out["d_translation"],
+                         scalings=out["d_scalings"].sum(axis=1, keepdims=True) if uniform else out["d_scalings"])
+            step += 1
+            for k in trainable:
+                P[k], m[k], v[k] = O.adam_step(P[k], grads[k].astype(np.float32), m[k], v[k], step)
+    assert step == 5 * kw.get("steps_per_epoch", 1)
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(d[pre + "rng_after"]))
+    for k in ("angles", "scalings", "shears", "translation"):
+        assert P[k].shape == d[pre + k].shape, k
+        np.testing.assert_allclose(P[k], d[pre + k], rtol=1e-4, atol=5e-4, err_msg=k)   # the GPU test's tolerances
+    imgs, acts = forward(grid0)
+    assert relerr(imgs.reshape(d[pre + "imgs"].shape), d[pre + "imgs"]) < 1e-2 and relerr(acts, d[pre + "acts"]) < 1e-2
