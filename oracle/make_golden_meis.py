@@ -2,6 +2,8 @@
 of the README quick start), generated in the build container (needs /root/reference; see oracle/ref_harness.py).
 
     python -m oracle.make_golden_meis        ->  tests/golden/mei_dict_100.npz
+                                                 tests/golden/mei_dict_std_40.npz  (std constraint, pixel range [0, 1], neurons [2, 0], 300 iterations,
+                                                                                    zscore 0.5: the non-default arguments of mei.py:74-88)
 
 `create_mask` inside the reference runs with the skimage stubs of oracle/ref_harness.py (`label` via scipy.ndimage, `convex_hull_image` restated):
 the hull step of this fixture is as pinned as tests/golden/create_mask.npz is, everything else is the reference's own code.
@@ -33,6 +35,22 @@ def main():
     )
     np.savez_compressed(os.path.join(OUT, "mei_dict_100.npz"), **out)
     print({k: (v.shape, v.dtype) for k, v in out.items()}, out["activations"], out["centers"])
+
+    torch.manual_seed(3)
+    model = laminr.neuron_models.simulated("demo1", img_res=[40, 40])
+    with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+        meis = laminr.get_mei_dict(model, [1, 40, 40], pixel_value_lower_bound=0.0, pixel_value_upper_bound=1.0, neuron_idxs=[2, 0], required_img_std=0.05,
+                                   zscore=0.5, step_size=5, num_iterations=300)
+    assert sorted(meis) == [0, 1]  # keyed by enumeration index (mei.py:114)
+    out = dict(
+        meis=np.stack([np.asarray(meis[i]["mei"], np.float32) for i in range(2)]),
+        masks=np.stack([np.asarray(meis[i]["mask"], np.float32) for i in range(2)]),
+        activations=np.array([meis[i]["activation"] for i in range(2)], np.float64),
+        centers=np.array([[meis[i]["center_pos"]["x"], meis[i]["center_pos"]["y"]] for i in range(2)], np.float64),
+        rng_after=torch.get_rng_state().numpy(),
+    )
+    np.savez_compressed(os.path.join(OUT, "mei_dict_std_40.npz"), **out)
+    print({k: (v.shape, v.dtype) for k, v in out.items()}, out["activations"], out["centers"], (out["masks"] > 0.5).sum(axis=(1, 2)))
 
 
 if __name__ == "__main__":

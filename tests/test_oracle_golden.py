@@ -449,3 +449,23 @@ def test_match_call_replayed_with_the_oracle_and_the_host_stream(tag):
         np.testing.assert_allclose(P[k], d[pre + k], rtol=1e-4, atol=5e-4, err_msg=k)   # the GPU test's tolerances
     imgs, acts = forward(grid0)
     assert relerr(imgs.reshape(d[pre + "imgs"].shape), d[pre + "imgs"]) < 1e-2 and relerr(acts, d[pre + "acts"]) < 1e-2
+
+
+def test_get_mei_dict_std_call_replayed_with_the_oracle():
+    """The reference's `get_mei_dict(model, [1, 40, 40], 0, 1, neuron_idxs=[2, 0], required_img_std=0.05, zscore=0.5, step_size=5,
+    num_iterations=300)` (tests/golden/mei_dict_std_40.npz, oracle/make_golden_meis.py) replayed from the seed: one CPU draw per listed neuron in list
+    order (mei.py:33), + mean, ChangeStats + ClipRange ascent (featurevis/ops.py:294-307,441-459), create_mask at the given z-score (mask.py:25-64)."""
+    import torch
+    from oracle import mask_oracle as MO
+    d = golden("mei_dict_std_40")
+    banks = O.demo1_banks([40, 40])
+    torch.manual_seed(3)
+    for k, neuron in enumerate([2, 0]):
+        x0 = torch.randn(1, 1, 40, 40, dtype=torch.float32).numpy() + np.float32(0.5)
+        x, fevals = O.mei_ascent(x0, banks[neuron], 5.0, 300, 0.0, 1.0, std=0.05)
+        assert len(fevals) == 301 and abs(fevals[-1] - d["activations"][k]) < 2e-5 * d["activations"][k]
+        assert relerr(x[0], d["meis"][k]) < 1e-4
+        mask, centre = MO.create_mask(d["meis"][k][0], zscore_thresh=0.5)[:2]
+        assert np.abs(np.asarray(mask, np.float32) - d["masks"][k]).max() < 1e-6
+        assert abs(centre["x"] - d["centers"][k, 0]) < 1e-9 and abs(centre["y"] - d["centers"][k, 1]) < 1e-9
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(d["rng_after"]))

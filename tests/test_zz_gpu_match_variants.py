@@ -57,3 +57,22 @@ def test_match_call_variant_vs_reference_call(L, tag):
     np.testing.assert_allclose(aff.translation.detach().cpu().numpy()[:, 0], d[f"{tag}_translation"], rtol=0, atol=5e-4)
     assert imgs.shape == d[f"{tag}_imgs"].shape and acts.shape == d[f"{tag}_acts"].shape
     assert relerr(imgs, d[f"{tag}_imgs"]) < 1e-2 and relerr(acts, d[f"{tag}_acts"]) < 1e-2  # north star: final images and activations within 1e-2 relative
+
+
+def test_get_mei_dict_std_call_vs_reference_call(L):
+    """`get_mei_dict` with the non-default arguments (std constraint, pixel range [0, 1], a reordered neuron subset, z-score 0.5, step size 5, 300
+    iterations) against the unmodified reference's call with the same seed (tests/golden/mei_dict_std_40.npz, oracle/make_golden_meis.py)."""
+    d = golden("mei_dict_std_40")
+    model = L.neuron_models.simulated("demo1", img_res=[40, 40]).cuda()
+    torch.manual_seed(3)
+    meis = L.get_mei_dict(model, [1, 40, 40], pixel_value_lower_bound=0.0, pixel_value_upper_bound=1.0, neuron_idxs=[2, 0], required_img_std=0.05,
+                          zscore=0.5, step_size=5, num_iterations=300)
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(d["rng_after"]))
+    assert sorted(meis) == [0, 1]  # keyed by enumeration index (mei.py:114)
+    for k in range(2):
+        assert abs(float(meis[k]["activation"]) - d["activations"][k]) < 1e-4 * d["activations"][k]
+        assert relerr(np.asarray(meis[k]["mei"], np.float32), d["meis"][k]) < 1e-3
+        m, want = np.asarray(meis[k]["mask"], np.float32), d["masks"][k]
+        assert m.shape == want.shape == (40, 40)
+        assert abs(int((m > 0.5).sum()) - int((want > 0.5).sum())) <= 2 and np.abs(m - want).mean() < 2e-3  # at most a hull-boundary pixel apart
+        assert abs(meis[k]["center_pos"]["x"] - d["centers"][k, 0]) < 0.1 and abs(meis[k]["center_pos"]["y"] - d["centers"][k, 1]) < 0.1
