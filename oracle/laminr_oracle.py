@@ -428,17 +428,20 @@ def simclr_reg_bwd(cache, pos, neg, T):
 # ----------------------------------------------------------------------------------------------------------------
 
 
-def learn_step(weights, biases, B, auxB, grid, coords, img_res, filters, rf_mask, mei_act, reg_scale, norm, pmin, pmax, pos, neg, T, response=None):
+def learn_step(weights, biases, B, auxB, grid, coords, img_res, filters, rf_mask, mei_act, reg_scale, norm, pmin, pmax, pos, neg, T, response=None,
+               std=None):
     """One `learn` hot step up to (and excluding) the optimiser: inv_temp_learn_match.py:187-207.
 
     `response(z, g_act) -> (act[N], g_z)` replaces the simulated filter bank when given (e.g. the conv-core oracle,
-    oracle/convcore_oracle.py:response_and_grad).  Returns dict(loss, acts (normalised), sim, img_pre, img_post, dW, db).
+    oracle/convcore_oracle.py:response_and_grad).  `std` (with norm=None): StandardizeClip instead of FixEnergyNormClip
+    (inv_temp_learn_match.py:52-73).  Returns dict(loss, acts (normalised), sim, img_pre, img_post, dW, db).
     """
+    con_fwd, con_bwd, target = (constrain_std_fwd, constrain_std_bwd, std) if std is not None else (constrain_norm_fwd, constrain_norm_bwd, norm)
     dt = weights[0].dtype
     mean = (pmin + pmax) / 2
     img_pre, cache = inr_forward(weights, biases, B, auxB, grid, coords[None], img_res, keep=True)
     x = img_pre[0]  # [N,C,H,W]
-    z, ccache = constrain_norm_fwd(x, norm, mean, pmin, pmax)
+    z, ccache = con_fwd(x, target, mean, pmin, pmax)
     N = len(x)
     g_act = np.full(N, -1.0 / (N * mei_act), dt)
     if response is not None:
@@ -454,17 +457,19 @@ def learn_step(weights, biases, B, auxB, grid, coords, img_res, filters, rf_mask
     # backward
     g_xm = simclr_reg_bwd(scache, pos, neg, T).reshape(z.shape) * dt.type(-reg_scale)
     g_z = g_z + g_xm * rf_mask.astype(dt)  # d apply_mask / dx = gain_in * mask * gain_out = mask
-    g_x = constrain_norm_bwd(g_z, ccache, norm, pmin, pmax)
+    g_x = con_bwd(g_z, ccache, target, pmin, pmax)
     grads = inr_backward(weights, B, cache, g_x[None], want_weights=True)
     return dict(loss=loss, acts=acts, sim=sim, img_pre=x, img_post=z, dW=grads["dW"], db=grads["db"], g_img_pre=g_x)
 
 
-def match_step(weights, biases, B, auxB, grid, coords, img_res, banks, mei_acts, affine, shifts, norm, pmin, pmax, clamp=True, responses=None):
+def match_step(weights, biases, B, auxB, grid, coords, img_res, banks, mei_acts, affine, shifts, norm, pmin, pmax, clamp=True, responses=None,
+               std=None):
     """One `match` hot step: inv_temp_learn_match.py:352-365.  banks: list of [F,H,W] for the D targets.
 
     affine = dict(angles[D], scalings[D,2], shears[D,2], translation[D,2]); shifts = (shift_to, tc, shift_from).
-    Only neuron d's response to its own images enters the loss (the diagonal, :361).
+    Only neuron d's response to its own images enters the loss (the diagonal, :361).  `std` (with norm=None): StandardizeClip.
     """
+    con_fwd, con_bwd, target = (constrain_std_fwd, constrain_std_bwd, std) if std is not None else (constrain_norm_fwd, constrain_norm_bwd, norm)
     dt = weights[0].dtype
     shift_to, tc, shift_from = shifts
     M, _ = affine_matrices(affine["angles"], affine["scalings"], affine["shears"])
@@ -473,7 +478,7 @@ def match_step(weights, biases, B, auxB, grid, coords, img_res, banks, mei_acts,
     D, N = img_pre.shape[:2]
     mean = (pmin + pmax) / 2
     flat = img_pre.reshape((D * N,) + img_pre.shape[2:])
-    z, ccache = constrain_norm_fwd(flat, norm, mean, pmin, pmax)
+    z, ccache = con_fwd(flat, target, mean, pmin, pmax)
     zs = z.reshape(img_pre.shape)
     acts_dn = np.zeros((D, N), dt)
     g_z = np.zeros_like(zs)
@@ -487,7 +492,7 @@ def match_step(weights, biases, B, auxB, grid, coords, img_res, banks, mei_acts,
         g_z[d] = simresp_bwd(g_act, rc, zs[d].shape, banks[d])
     acts = acts_dn.mean(1) / mei_acts.astype(dt)
     loss = -acts.mean()
-    g_x = constrain_norm_bwd(g_z.reshape(z.shape), ccache, norm, pmin, pmax).reshape(img_pre.shape)
+    g_x = con_bwd(g_z.reshape(z.shape), ccache, target, pmin, pmax).reshape(img_pre.shape)
     G = inr_backward(weights, B, cache, g_x, want_weights=False, want_coords=True)["dcoords"]
     d_ang, d_scal, d_shear, d_t = affine_backward(G, coords, tc, affine["angles"], affine["scalings"], affine["shears"])
     return dict(

@@ -469,3 +469,93 @@ def test_get_mei_dict_std_call_replayed_with_the_oracle():
         assert np.abs(np.asarray(mask, np.float32) - d["masks"][k]).max() < 1e-6
         assert abs(centre["x"] - d["centers"][k, 0]) < 1e-9 and abs(centre["y"] - d["centers"][k, 1]) < 1e-9
     assert torch.equal(torch.get_rng_state(), torch.from_numpy(d["rng_after"]))
+
+
+def test_std_constraint_calls_with_snapshots_replayed_with_the_oracle():
+    """`InvarianceManifold(required_img_std=0.1)`: whole `learn(0, steps_per_epoch=5, num_max_epochs=4, save_results_every_n_epochs=2)` and, continuing
+    on the same generator, `match([1, 2], num_epochs=4, save_results_every_n_epochs=2)` of the unmodified reference (tests/golden/std_calls_20.npz,
+    oracle/make_golden_std_calls.py) replayed from seeds alone: StandardizeClip in both loops, snapshots at epochs 0, 2 and the end."""
+    import torch
+    import laminr_b200 as L
+    from laminr_b200.utils.training import JitteringGridDatamodule
+    d = golden("std_calls_20")
+    res, targets, D = (20, 20), [1, 2], 2
+    meis = {i: dict(mei=np.zeros((1,) + res, np.float32), activation=float(d["mei_acts"][i]), mask=d["masks"][i],
+                    center_pos=dict(x=float(d["centers"][i, 0]), y=float(d["centers"][i, 1]))) for i in range(3)}
+    torch.manual_seed(0)
+    im = L.InvarianceManifold(L.neuron_models.simulated("demo1", img_res=list(res)), meis, device="cpu", required_img_std=0.1,
+                              pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+    sd = {k: v.numpy().copy() for k, v in im.template.state_dict().items()}
+    W, b = [sd[f"func.layer{l}.weight"] for l in range(5)], [sd[f"func.layer{l}.bias"] for l in range(5)]
+    coords, Bm, auxB = sd["coords"].reshape(-1, 2), sd["B"], sd["auxB"]
+    banks = O.demo1_banks(list(res))
+    pos, neg = O.pos_neg_masks(20, 0.1, True)
+    grid0 = O.latent_grid(20)
+    mei_act = float(d["mei_acts"][0])
+
+    # ---- learn
+    def learn_fwd(grid):
+        return O.learn_step(W, b, Bm, auxB, grid, coords, res, banks[0], d["masks"][0], mei_act, 2.0, None, -1.0, 1.0, pos, neg, 0.3, std=0.1)
+
+    mW, vW = [np.zeros_like(w) for w in W], [np.zeros_like(w) for w in W]
+    mb, vb = [np.zeros_like(x) for x in b], [np.zeros_like(x) for x in b]
+    torch.manual_seed(21)
+    dm = JitteringGridDatamodule(num_invariances=1, grid_points_per_dim=20, steps_per_epoch=5)
+    dm.train_dataloader()  # built and discarded by the reference (:137)
+    snaps, step = [], 0
+    for epoch in range(4):
+        if epoch % 2 == 0:
+            snaps.append(learn_fwd(grid0))
+        for g in dm.train_dataloader():
+            out = learn_fwd(g[:, 0].numpy())
+            step += 1
+            for l in range(5):
+                W[l], mW[l], vW[l] = O.adam_step(W[l], out["dW"][l], mW[l], vW[l], step)
+                b[l], mb[l], vb[l] = O.adam_step(b[l], out["db"][l], mb[l], vb[l], step)
+    snaps.append(learn_fwd(grid0))
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(d["rng_after_learn"]))
+    assert d["learn_imgs"].shape == (3, 20, 1, 20, 20) and d["learn_acts"].shape == (3, 20)
+    for k, s in enumerate(snaps):
+        assert relerr(s["img_post"].reshape(20, 1, 20, 20), d["learn_imgs"][k]) < 1e-2, k
+        assert relerr(s["acts"] * mei_act, d["learn_acts"][k]) < 1e-2, k          # the getter returns the raw activations (:399)
+    for l in range(5):
+        assert relerr(W[l], d[f"learned_W{l}"]) < 2e-3, l
+
+    # ---- match, from the learned template, on the same generator
+    mei_acts = d["mei_acts"][targets]
+    shifts = O.coords_shifts(d["centers"][0].astype(np.float32), d["centers"][targets].astype(np.float32), res)
+    P = dict(angles=np.zeros(D, np.float32), scalings=np.ones((D, 2), np.float32), shears=np.zeros((D, 2), np.float32), translation=np.zeros((D, 2), np.float32))
+
+    def match_fwd(grid):
+        M, _ = O.affine_matrices(P["angles"], P["scalings"], P["shears"])
+        img = O.inr_forward(W, b, Bm, auxB, grid, O.match_coords(coords, M, P["translation"], shifts[1], shifts[0], shifts[2], True), res)
+        z, _ = O.constrain_std_fwd(img.reshape((D * 20,) + img.shape[2:]), 0.1, 0.0, -1.0, 1.0)
+        zs = z.reshape(img.shape)
+        return zs, np.stack([O.simresp_fwd(zs[k], banks[targets[k]])[0] for k in range(D)])
+
+    dm = JitteringGridDatamodule(num_invariances=1, grid_points_per_dim=20, steps_per_epoch=1)
+    inv = (1.0 / (d["masks"][targets].sum(axis=(1, 2)) / d["masks"][0].sum())).astype(np.float32)
+    P["scalings"] = np.ones_like(P["scalings"]) * inv[:, None]
+    angles = np.linspace(0, 2 * np.pi, 61)[:-1].astype(np.float32)
+    table = np.zeros((60, D))
+    for i, a in enumerate(angles):
+        P["angles"] = np.full(D, a, np.float32)
+        table[i] = match_fwd(grid0)[1].mean(axis=1)
+    P["angles"] = angles[np.argmax(table, axis=0)]
+    m, v = {k: np.zeros_like(P[k]) for k in P}, {k: np.zeros_like(P[k]) for k in P}
+    msnaps, step = [], 0
+    for epoch in range(4):
+        if epoch % 2 == 0:
+            msnaps.append(match_fwd(grid0))
+        for g in dm.train_dataloader():
+            out = O.match_step(W, b, Bm, auxB, g[:, 0].numpy(), coords, res, [banks[t] for t in targets], mei_acts, P, shifts, None, -1.0, 1.0, std=0.1)
+            step += 1
+            for k in P:
+                P[k], m[k], v[k] = O.adam_step(P[k], out["d_" + k].astype(np.float32), m[k], v[k], step)
+    msnaps.append(match_fwd(grid0))
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(d["rng_after_match"]))
+    assert d["match_imgs"].shape == (3, 2, 20, 1, 20, 20) and d["match_acts"].shape == (3, 2, 20)
+    for k, (zs, acts) in enumerate(msnaps):
+        assert relerr(zs.reshape(2, 20, 1, 20, 20), d["match_imgs"][k]) < 1e-2 and relerr(acts, d["match_acts"][k]) < 1e-2, k
+    for k in P:
+        np.testing.assert_allclose(P[k], d[k], rtol=1e-4, atol=5e-4, err_msg=k)

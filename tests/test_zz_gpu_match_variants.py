@@ -76,3 +76,35 @@ def test_get_mei_dict_std_call_vs_reference_call(L):
         assert m.shape == want.shape == (40, 40)
         assert abs(int((m > 0.5).sum()) - int((want > 0.5).sum())) <= 2 and np.abs(m - want).mean() < 2e-3  # at most a hull-boundary pixel apart
         assert abs(meis[k]["center_pos"]["x"] - d["centers"][k, 0]) < 0.1 and abs(meis[k]["center_pos"]["y"] - d["centers"][k, 1]) < 0.1
+
+
+def test_std_constraint_calls_with_snapshots_vs_reference_calls(L):
+    """`InvarianceManifold(required_img_std=0.1)` (StandardizeClip in the fused learn / match steps): whole `learn` and, continuing on the same
+    generator, `match` calls with `save_results_every_n_epochs=2` against the unmodified reference's calls from seeds alone
+    (tests/golden/std_calls_20.npz, oracle/make_golden_std_calls.py): stacked snapshots (epochs 0, 2, final), generator states, final parameters."""
+    d = golden("std_calls_20")
+    res = 20
+    model = L.neuron_models.simulated("demo1", img_res=[res, res]).cuda()
+    meis = {i: dict(mei=np.zeros((1, res, res), np.float32), activation=float(d["mei_acts"][i]), mask=d["masks"][i],
+                    center_pos=dict(x=float(d["centers"][i, 0]), y=float(d["centers"][i, 1]))) for i in range(3)}
+    torch.manual_seed(0)
+    im = L.InvarianceManifold(model, meis, required_img_std=0.1, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+    torch.manual_seed(21)
+    l_imgs, l_acts = im.learn(0, steps_per_epoch=5, num_max_epochs=4, save_results_every_n_epochs=2)
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(d["rng_after_learn"]))
+    assert l_imgs.shape == d["learn_imgs"].shape == (3, 20, 1, res, res) and l_acts.shape == d["learn_acts"].shape == (3, 20)
+    for k in range(3):
+        assert relerr(l_imgs[k], d["learn_imgs"][k]) < 1e-2 and relerr(l_acts[k], d["learn_acts"][k]) < 1e-2, k
+    sd = im.template.state_dict()
+    for l in range(5):
+        assert relerr(sd[f"func.layer{l}.weight"].cpu().numpy(), d[f"learned_W{l}"]) < 1e-2, l
+    m_imgs, m_acts = im.match([1, 2], num_epochs=4, save_results_every_n_epochs=2)
+    assert torch.equal(torch.get_rng_state(), torch.from_numpy(d["rng_after_match"]))
+    assert m_imgs.shape == d["match_imgs"].shape == (3, 2, 20, 1, res, res) and m_acts.shape == d["match_acts"].shape == (3, 2, 20)
+    for k in range(3):
+        assert relerr(m_imgs[k], d["match_imgs"][k]) < 1e-2 and relerr(m_acts[k], d["match_acts"][k]) < 1e-2, k
+    aff = im.template.coordinate_transform.transforms.Affine
+    np.testing.assert_allclose(aff.angles.detach().cpu().numpy(), d["angles"], rtol=1e-4, atol=5e-4)
+    np.testing.assert_allclose(aff.scalings.detach().cpu().numpy(), d["scalings"], rtol=1e-4, atol=5e-4)
+    np.testing.assert_allclose(aff.shears.detach().cpu().numpy(), d["shears"], rtol=0, atol=5e-4)
+    np.testing.assert_allclose(aff.translation.detach().cpu().numpy()[:, 0], d["translation"], rtol=0, atol=5e-4)
