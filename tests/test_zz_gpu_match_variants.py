@@ -1,7 +1,13 @@
-"""GPU parity of `InvarianceManifold.match` with NON-DEFAULT transform flags against whole calls of the unmodified reference with the same seeds
-(tests/golden/match_call_variants_20.npz, oracle/make_golden_match_call.py::VARIANTS): which of the seven affine scalars are parameters and their
-shapes (uniform scale = one scaling column, no shear / no scale = buffers Adam must not touch), the coordinate clamp switched off, no initialisation
-sweep with several steps per epoch, and the angle x translation sweep (7260 candidates).  (File name: sorted after the other GPU tests.)"""
+"""GPU parity of the public calls with NON-DEFAULT arguments against whole calls of the unmodified reference with the same seeds (each golden is also
+replayed on the CPU through the product's host code and the numpy oracle, tests/test_oracle_golden.py):
+
+  * `InvarianceManifold.match` transform flags (tests/golden/match_call_variants_20.npz, oracle/make_golden_match_call.py::VARIANTS): which of the
+    seven affine scalars are parameters and their shapes (uniform scale = one scaling column, no shear / no scale = buffers Adam must not touch), the
+    coordinate clamp switched off, no initialisation sweep with several steps per epoch, the angle x translation sweep (7260 candidates);
+  * `get_mei_dict` with the std constraint, a [0, 1] pixel range, a reordered neuron subset, z-score / step size / iteration count;
+  * `InvarianceManifold(required_img_std=...)` learn + match with `save_results_every_n_epochs`.
+
+Written after round 1's GPU budget was spent: first run on a B200 at the round-end check.  (File name: sorted after the other GPU tests.)"""
 import numpy as np
 import pytest
 import torch
