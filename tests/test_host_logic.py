@@ -289,3 +289,16 @@ def test_host_only_abi_functions(L):
     assert rc != 0 and b"precision" in lib.lmr_last_error()
     with pytest.raises(_lib.LaminrB200Error, match="precision"):
         _lib.check(rc)
+
+
+def test_conv_model_constructors_consume_rng_like_the_reference(L):
+    """`torch.manual_seed(0)` + `Stacked2dCore(...)`, `FullGaussian2d(...)` of the host mirror give the state_dict (names, shapes, values) and leave
+    the CPU generator where the reference's vendored neuralpredictors constructors do (BASELINE config 4 and a small 2-channel variant;
+    tests/golden/conv_init.npz, oracle/make_golden_conv_init.py)."""
+    from oracle.make_golden_conv_init import digest
+    from laminr_b200.neuron_models.conv_models import FullGaussian2d, Stacked2dCore
+    want = golden("conv_init")
+    got = digest(Stacked2dCore, FullGaussian2d)
+    assert sorted(got) == sorted(want)
+    for k in want:
+        assert np.array_equal(got[k], want[k]), k
