@@ -302,3 +302,14 @@ def test_conv_model_constructors_consume_rng_like_the_reference(L):
     assert sorted(got) == sorted(want)
     for k in want:
         assert np.array_equal(got[k], want[k]), k
+
+
+def test_state_dicts_are_the_references(L):
+    """Checkpoint compatibility: the template's state_dict (INR, coordinate transform of two targets, RF shift buffers) and the demo1 response model's
+    have the reference's keys in the reference's order, shapes, dtypes and -- from the same seed -- values (tests/golden/state_dicts_20.npz,
+    oracle/make_golden_state_dicts.py)."""
+    from oracle.make_golden_state_dicts import digests
+    want = golden("state_dicts_20")
+    got = digests(L, device="cpu")
+    for k in want:
+        assert np.array_equal(got[k], want[k]), (k, got[k] if got[k].ndim == 1 else None)
