@@ -1,4 +1,5 @@
-"""Times lmr_create_mask on a batch of MEI-like images against the scipy restatement on the host (one image at a time, as the reference does)."""
+"""Times lmr_create_mask on a batch of MEI-like images against the scipy restatement on the host (one image at a time, as the reference does).
+Developer tool: `oracle/` appears here only as the CPU baseline being timed beside the kernel (like bench.py's cpu_baseline leg), never on the product path."""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch

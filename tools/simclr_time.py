@@ -3,13 +3,14 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from laminr_b200 import ops
-from oracle import laminr_oracle as O
+from laminr_b200.contrastive_loss import SimCLROnGrid
 
 res = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 N, P = 20, res * res
 z = torch.randn(N, 1, res, res, device="cuda") * 0.01
 mask = torch.rand(P, device="cuda")
-pos, neg = [torch.as_tensor(a).cuda() for a in O.pos_neg_masks(N, 0.1, True)]
+_reg = SimCLROnGrid(1, N, 0.1, 0.3, True)
+pos, neg = _reg.flat_neighbor_mask_pos.cuda(), _reg.flat_neighbor_mask_neg.cuda()
 reg, K = torch.empty(1, device="cuda"), torch.empty(N, N, device="cuda")
 from laminr_b200 import _lib
 ws = torch.empty(_lib.load().lmr_simclr_workspace_bytes(N, 1, P), dtype=torch.uint8, device="cuda")
