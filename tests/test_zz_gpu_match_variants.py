@@ -7,7 +7,8 @@ replayed on the CPU through the product's host code and the numpy oracle, tests/
   * `get_mei_dict` with the std constraint, a [0, 1] pixel range, a reordered neuron subset, z-score / step size / iteration count;
   * `InvarianceManifold(required_img_std=...)` learn + match with `save_results_every_n_epochs`.
 
-Written after round 1's GPU budget was spent: first run on a B200 at the round-end check.  (File name: sorted after the other GPU tests.)"""
+Written as round 1's GPU budget ran out: the std-constraint test passed on a B200 with the last seconds of it, the others first run on a B200 at the
+round-end check.  (File name: sorted after the other GPU tests.)"""
 import numpy as np
 import pytest
 import torch
