@@ -32,6 +32,9 @@ class INRTemplates(nn.Module):
         if batchnorm: unsupported.append("batchnorm=True")
         if jitter_coords: unsupported.append("jitter_coords=True")
         if len(set(widths)) != 1: unsupported.append("non-uniform widths")
+        elif widths[0] != 50: unsupported.append("hidden width %d (the kernels are built for 50)" % widths[0])
+        if not 2 <= len(widths) <= 8: unsupported.append("%d hidden layers (supported: 2..8)" % len(widths))
+        if not 1 <= out_channels <= 4: unsupported.append("%d output channels (supported: 1..4)" % out_channels)
         if unsupported:
             raise NotImplementedError("laminr_b200.INRTemplates: configuration outside the fused kernels (%s); the pipeline "
                                       "(InvarianceManifold) uses widths=[50]*4, tanh, bias, periodic latent, positional encodings" % ", ".join(unsupported))

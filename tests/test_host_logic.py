@@ -313,3 +313,20 @@ def test_state_dicts_are_the_references(L):
     got = digests(L, device="cpu")
     for k in want:
         assert np.array_equal(got[k], want[k]), (k, got[k] if got[k].ndim == 1 else None)
+
+
+def test_unsupported_inr_shapes_fail_at_construction(L):
+    """Shapes the kernels are not built for are refused when the template is constructed (NotImplementedError naming the reason), not at the first
+    launch: hidden width != 50, fewer than 2 / more than 8 hidden layers, more than 4 output channels (csrc/inr_common.cuh: make_net)."""
+    from laminr_b200.inr import INRTemplates
+    from torch import nn
+    kw = dict(periodic_invariance=True, positional_encoding_dim=50, positional_encoding_projection_scale=10, aux_positional_encoding_dim=50,
+              aux_positional_encoding_projection_scale=0.1, final_nonlinearity=nn.Tanh, bias=True, weights_scale=0.1)
+    INRTemplates((8, 8), widths=[50] * 2, **kw), INRTemplates((8, 8), widths=[50] * 8, out_channels=4, **kw)   # the supported corners construct
+    for bad, why in ((dict(widths=[64] * 4), "hidden width 64"), (dict(widths=[50]), "1 hidden layers"), (dict(widths=[50] * 9), "9 hidden layers"),
+                     (dict(widths=[50] * 4, out_channels=5), "5 output channels"), (dict(widths=[50, 40, 50, 50]), "non-uniform")):
+        with pytest.raises(NotImplementedError, match=why):
+            INRTemplates((8, 8), **bad, **kw)
+    m = L.neuron_models.simulated("demo1", img_res=[8, 8])
+    with pytest.raises(NotImplementedError, match="hidden width 32"):
+        L.InvarianceManifold(m, _meis(8), device="cpu", widths=[32] * 4, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
