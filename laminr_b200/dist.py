@@ -41,6 +41,17 @@ def broadcast_module_state(module, src=0):
         dist.broadcast(t.data, src=src)
 
 
+def broadcast_template(template, src=0):
+    """Broadcast of what `learn` produced: the INR network `template.func` and the fixed buffers B / auxB / coords, in a member-independent
+    order.  The coordinate transform and the RF-shift buffers are NOT sent: every rank rebuilds them in `match` (a rank that has already run an
+    unsharded `match` owns members the others lack, and a per-member broadcast of the whole module would then hang on mismatched collectives)."""
+    world, _ = _world()
+    if world == 1:
+        return
+    for t in list(template.func.parameters()) + [template.B, template.auxB, template.coords]:
+        dist.broadcast(t.data, src=src)
+
+
 def broadcast_rng_state(src=0, device=None):
     """Every rank continues with rank `src`'s CPU generator state: the jittered latent grids (laminr/utils/training.py:42-46) and MEI
     starting images (laminr/utils/mei.py:33) are drawn on the CPU generator, so the ranks must agree on it."""
@@ -115,7 +126,9 @@ def gather_ragged(local, n_total, dst=0):
 def match_sharded(im, target_neuron_idxs, **match_kwargs):
     """`InvarianceManifold.match` with the targets sharded over the ranks.  Call on every rank with the same arguments after `learn`
     ran on rank 0 (any rank may hold an untrained copy of the template: it is overwritten by rank 0's).
-    Returns (images [D,N,C,H,W], activations [D,N]) as NumPy arrays on rank 0, (None, None) elsewhere."""
+    Returns (images [D,N,C,H,W], activations [D,N]) as NumPy arrays on rank 0, (None, None) elsewhere.
+    Afterwards every rank's `im` holds the coordinate transforms of ITS block only: `im.target_neuron_idxs` (and with it
+    `get_images_from_matched_template`) is per rank; the full list is kept in `im.all_target_neuron_idxs`."""
     world, rank = _world()
     device = next(im.template.parameters()).device
     targets = list(target_neuron_idxs)
@@ -137,12 +150,13 @@ def match_sharded(im, target_neuron_idxs, **match_kwargs):
     tni = torch.tensor([int(getattr(im, "template_neuron_idx", -1))], dtype=torch.int64, device=device)
     dist.broadcast(tni, src=0)
     im.template_neuron_idx = int(tni.item())
-    broadcast_module_state(im.template, src=0)
+    broadcast_template(im.template, src=0)
     broadcast_rng_state(src=0, device=device)
     lo, hi = shard_bounds(D, world, rank)
     fused = im._fused_ok()
     mark("broadcasts")
     imgs, acts = im.match(targets[lo:hi], _total_targets=D, _stop_reduce=make_stop_reduce(device), _return_device=fused, **match_kwargs)
+    im.all_target_neuron_idxs = targets
     mark("local match")
     if not fused:  # generic autograd path: results come back as host arrays
         imgs, acts = torch.from_numpy(np.ascontiguousarray(imgs)).to(device), torch.from_numpy(np.ascontiguousarray(acts)).to(device)
@@ -181,12 +195,15 @@ def get_mei_dict_sharded(model, input_shape, pixel_value_lower_bound, pixel_valu
     # the reference draws one initial image per neuron, in order, from the CPU generator (mei.py:33): skip the draws of lower ranks
     items = list(model.parameters()) + list(model.buffers())
     broadcast_rng_state(src=0, device=items[0].device if items else None)
-    if lo > 0:
-        torch.randn(lo, *input_shape)
+    # (one draw per neuron, like the unsharded call: the CPU generator's vectorised normal consumes its stream per CALL, so one big draw
+    # is a different stream than `lo` single-image draws unless the image size is a multiple of 16)
+    for _ in range(lo):
+        torch.randn(1, *input_shape)
     # fewer neurons than ranks: the ranks without a neuron only keep the generator in step and take part in the gather
     local = get_mei_dict(model, input_shape, pixel_value_lower_bound, pixel_value_upper_bound, neuron_idxs=neuron_idxs[lo:hi], **kwargs) if hi > lo else {}
     if hi < len(neuron_idxs):  # ... and of the higher ranks: every rank leaves the generator where the unsharded call would (same jitter in `learn`)
-        torch.randn(len(neuron_idxs) - hi, *input_shape)
+        for _ in range(len(neuron_idxs) - hi):
+            torch.randn(1, *input_shape)
     return _allgather_mei_entries(local, lo, len(neuron_idxs), items[0].device if items else torch.device("cpu"))
 
 

@@ -85,8 +85,12 @@ class _SimulatedResponse:
         self.model = model
         self.rmax = torch.empty((D, N), dtype=torch.float32, device=dev)
         self.argmax = torch.empty((D, N), dtype=torch.int32, device=dev)
-        # the partials' chunk size depends on the number of groups of a call: size the workspace for every group count it will be called with
-        self.ws = _ws(max(_lib.load().lmr_simresp_workspace_bytes(g, N, model.packed_filters.shape[1], P) for g in (D,) + tuple(also) if g > 0), dev)
+        # The partials' chunk size depends on the number of groups of a call (fewer groups -> smaller pixel chunks -> MORE partials per group), so
+        # lmr_simresp_workspace_bytes is not monotonic in the group count: size the workspace for EVERY group count 1..D the backend may be called
+        # with (a sweep's smaller tail batch, a block remainder).  Above 2 x 148 groups the chunk no longer changes, so 1..296 and D cover all.
+        lib, Fmax = _lib.load(), model.packed_filters.shape[1]
+        counts = set(range(1, min(int(D), 2 * 148) + 1)) | {int(D)} | {int(g) for g in also if g > 0}
+        self.ws = _ws(max(lib.lmr_simresp_workspace_bytes(g, N, Fmax, P) for g in counts), dev)
 
     def forward(self, z, stride, N, D, Cc, P, nog, act):
         m = self.model

@@ -11,7 +11,8 @@ runs inside a step:
   * any other `nn.Module` response model takes the GENERIC path: the same fused INR / constraint / contrastive
     operators, composed by stock autograd around the user's model.
 
-Out of scope here: GIF export (`save_*_as_gif`, needs matplotlib / lipstick) and the GaussianBlur preconditioner.
+With `gaussian_blur_sigma=` (the GaussianBlur gradient preconditioner, featurevis/ops.py:378-423) the loops run the generic path with the blur as a
+backward hook.  Out of scope here: GIF export (`save_*_as_gif`, needs matplotlib / lipstick).
 """
 import numpy as np
 import torch
@@ -115,6 +116,7 @@ class InvarianceManifold:
         self.learn_steps_taken = 0
         self.template.train()
         pbar = tqdm(range(num_max_epochs), bar_format=_BAR)
+        epoch = -1  # num_max_epochs=0: no epoch runs, the call returns the snapshot of the untrained template like the reference
         for epoch in pbar:
             if save_results_every_n_epochs and epoch % save_results_every_n_epochs == 0:
                 imgs, a = snapshot()
@@ -248,6 +250,7 @@ class InvarianceManifold:
         self.match_steps_taken = 0
         next_grids = None
         pbar = tqdm(range(num_epochs), bar_format=_BAR)
+        epoch = -1  # num_epochs=0: the call returns the snapshot of the initialised transform like the reference
         for epoch in pbar:
             if save_results_every_n_epochs and epoch % save_results_every_n_epochs == 0:
                 imgs, a = snapshot()

@@ -164,17 +164,35 @@ class FiringRateEncoder(nn.Module):
         if shifter is not None or modulator is not None:
             raise NotImplementedError("laminr_b200 FiringRateEncoder: shifter / modulator branches are not mirrored")
         self.core, self.readout, self.shifter, self.modulator, self.offset = core, readout, None, None, elu_offset
+        self._cone, self._cone_sig = None, None
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.refresh_cone())
 
     # ---- B200 path --------------------------------------------------------------------------------------------------
+    def _state_signature(self):
+        # identity + in-place version counter of every tensor the pack is derived from: load_state_dict / optimiser steps / .copy_() bump the
+        # version, .to(device) / .float() replace the tensors
+        return (self.training,) + tuple((id(t), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
     def cone(self):
-        """The lmr_convcore_response weight pack of this (frozen, eval-mode) model; built on first use, rebuilt by `refresh_cone()`."""
-        c = getattr(self, "_cone", None)
-        if c is None:
-            c = self._cone = self._build_cone()
-        return c
+        """The lmr_convcore_response weight pack of this (frozen, eval-mode) model: built on first use and rebuilt whenever the module's
+        parameters / buffers were replaced or modified in place since (load_state_dict, .to(), .train()/.eval(), manual edits), or by
+        `refresh_cone()`."""
+        sig = self._state_signature()
+        if self._cone is None or sig != self._cone_sig:
+            self._cone = self._build_cone()
+            self._cone_sig = self._state_signature()  # (building clamps the readout positions in place)
+        return self._cone
 
     def refresh_cone(self):
         self._cone = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._cone = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def train(self, mode=True):
+        self._cone = None
+        return super().train(mode)
 
     def _build_cone(self):
         from .. import ops

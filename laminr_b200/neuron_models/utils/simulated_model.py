@@ -83,6 +83,8 @@ class ArbitraryMultiNeuronModel(nn.Module):
         self.neuron_models_list = nn.ModuleList(neuron_models_list)
         banks = [m.filters for m in neuron_models_list]
         self.eps = neuron_models_list[0].eps
+        if any(m.eps != self.eps for m in neuron_models_list):  # the kernels take ONE epsilon for the population
+            raise ValueError("ArbitraryMultiNeuronModel: every neuron must use the same eps")
         fmax = max(b.shape[0] for b in banks)
         self.img_res = tuple(banks[0].shape[1:])
         if packed is None:
@@ -92,6 +94,21 @@ class ArbitraryMultiNeuronModel(nn.Module):
         self.register_buffer("packed_filters", packed.reshape(len(banks), fmax, -1).contiguous(), persistent=False)
         self.register_buffer("nfilt", torch.tensor([b.shape[0] for b in banks], dtype=torch.int32), persistent=False)
         self.register_buffer("all_neurons", torch.arange(len(banks), dtype=torch.int32), persistent=False)
+        # `packed_filters` is a derived, non-persistent copy of the per-neuron `filters` buffers (the state_dict keys of the reference): rebuild it
+        # whenever a state_dict is loaded, or the kernels would keep reading the old banks
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.repack())
+
+    def repack(self):
+        """Rebuilds the packed bank the kernels read from the per-neuron `filters` buffers (after they were modified in place)."""
+        fmax = self.packed_filters.shape[1]
+        with torch.no_grad():
+            for i, m in enumerate(self.neuron_models_list):
+                b = m.filters.reshape(m.filters.shape[0], -1).to(self.packed_filters.device)
+                if b.data_ptr() == self.packed_filters[i].data_ptr():
+                    continue  # the buffer is a view of the packed bank: already current
+                self.packed_filters[i, :b.shape[0]].copy_(b)
+                if b.shape[0] < fmax:
+                    self.packed_filters[i, b.shape[0]:].copy_(b[:1].expand(fmax - b.shape[0], -1))
 
     @property
     def n_neurons(self):

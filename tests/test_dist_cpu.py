@@ -29,6 +29,17 @@ def _worker(rank, world, port, n_targets, q):
         mod = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Tanh(), torch.nn.Linear(7, 1))
         mod.register_buffer("B", torch.randn(2, 4))
         D.broadcast_module_state(mod, src=0)
+        # --- template broadcast of match_sharded: only what `learn` produced travels, so a rank that owns extra members (rank 0 after an unsharded
+        #     match(): coordinate transform + RF-shift buffers) does not desynchronise the collectives
+        tmpl = torch.nn.Module()
+        tmpl.func = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.Tanh(), torch.nn.Linear(4, 1))
+        for name, shape in (("B", (2, 5)), ("auxB", (2, 5)), ("coords", (1, 6, 2))):
+            tmpl.register_buffer(name, torch.randn(*shape))
+        if rank == 0:
+            tmpl.coordinate_transform = torch.nn.Linear(2, 2)
+            tmpl.register_buffer("coords_shift_to_center", torch.randn(1, 2))
+        D.broadcast_template(tmpl, src=0)
+        tmpl_state = [p.detach().numpy().copy() for p in tmpl.func.parameters()] + [tmpl.B.numpy().copy(), tmpl.auxB.numpy().copy(), tmpl.coords.numpy().copy()]
         # --- RNG agreement: the jittered grids are drawn on the CPU generator
         D.broadcast_rng_state(src=0)
         dm = JitteringGridDatamodule(1, 20, 3)
@@ -54,7 +65,7 @@ def _worker(rank, world, port, n_targets, q):
         local = torch.arange(lo, hi, dtype=torch.float32)[:, None, None] * torch.ones(1, 3, 2)
         full = D.gather_ragged(local, n_targets, dst=0)
         # numpy payloads are pickled by value; torch tensors would travel as shared-memory handles that die with this process
-        q.put((rank, [p.detach().numpy().copy() for p in mod.parameters()] + [mod.B.numpy().copy()], grids.numpy().copy(), stopped_at, means,
+        q.put((rank, [p.detach().numpy().copy() for p in mod.parameters()] + [mod.B.numpy().copy()] + tmpl_state, grids.numpy().copy(), stopped_at, means,
                None if full is None else full.numpy().copy(), (lo, hi)))
     finally:
         dist.destroy_process_group()
@@ -104,7 +115,7 @@ def test_shard_bounds_cover_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
-def _worker_small(rank, world, port, n_neurons, arrays, q):
+def _worker_small(rank, world, port, n_neurons, arrays, q, shape=(1, 4, 4)):
     """Fewer items than ranks / ragged MEI shards: no rank may be left alone in a collective."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -112,11 +123,11 @@ def _worker_small(rank, world, port, n_neurons, arrays, q):
         from laminr_b200 import dist as D
         import laminr_b200.utils.mei as mei_mod
 
-        shape = [1, 4, 4]
+        shape = list(shape)
 
         def fake_get_mei_dict(model, input_shape, lo_b, hi_b, neuron_idxs=None, **kw):
             # like the real one: one starting image per neuron, in order, from the CPU generator (laminr/utils/mei.py:33); keys = enumeration index
-            x0 = torch.randn(len(neuron_idxs), *input_shape)
+            x0 = torch.cat([torch.randn(1, *input_shape) for _ in neuron_idxs]) if len(neuron_idxs) else torch.empty(0, *input_shape)
             if arrays:  # entries shaped like the real ones: they travel as tensors (images, masks, float64 scalars)
                 return {k: {"mei": x0[k].numpy().copy(), "activation": float(np.float32(i) / 3), "mask": x0[k, 0].numpy().copy() * 2,
                             "center_pos": {"y": i + 0.1, "x": i / 7}} for k, i in enumerate(neuron_idxs)}
@@ -138,7 +149,7 @@ def _worker_small(rank, world, port, n_neurons, arrays, q):
         if arrays:
             for k, v in out.items():
                 i = 10 + k
-                assert tuple(v) == ("mei", "activation", "mask", "center_pos") and v["mei"].dtype == np.float32 and v["mei"].shape == (1, 4, 4)
+                assert tuple(v) == ("mei", "activation", "mask", "center_pos") and v["mei"].dtype == np.float32 and v["mei"].shape == tuple(shape)
                 assert type(v["activation"]) is float and v["activation"] == float(np.float32(i) / 3)
                 assert v["center_pos"] == {"y": i + 0.1, "x": i / 7} and list(v["center_pos"]) == ["y", "x"]
                 assert np.array_equal(v["mask"], v["mei"][0] * 2)
@@ -148,21 +159,24 @@ def _worker_small(rank, world, port, n_neurons, arrays, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_neurons,arrays", [(1, False), (5, False), (1, True), (5, True)])
-def test_sharded_mei_dict_and_too_few_targets_world2(n_neurons, arrays):
+@pytest.mark.parametrize("n_neurons,arrays,shape", [(1, False, (1, 4, 4)), (5, False, (1, 4, 4)), (1, True, (1, 4, 4)), (5, True, (1, 4, 4)),
+                                                     # 15 / 196 pixels: NOT a multiple of 16, where the CPU generator's vectorised normal makes one
+                                                     # [k, ...] draw differ from k single-image draws (the unsharded call draws per neuron)
+                                                     (5, True, (1, 3, 5)), (5, True, (1, 14, 14))])
+def test_sharded_mei_dict_and_too_few_targets_world2(n_neurons, arrays, shape):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker_small, args=(r, world, port, n_neurons, arrays, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker_small, args=(r, world, port, n_neurons, arrays, q, shape)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in procs], key=lambda r: r[0])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    # the unsharded call: rank 0's seed, one draw of all starting images
+    # the unsharded call: rank 0's seed
     torch.manual_seed(50)
-    x0 = torch.randn(n_neurons, 1, 4, 4).numpy()
+    x0 = torch.cat([torch.randn(1, *shape) for _ in range(n_neurons)]).numpy()  # one draw per neuron (laminr/utils/mei.py:33 inside the loop of :98)
     want_after = torch.rand(2).numpy()
     for rank, out, after, err in res:
         assert list(out) == list(range(n_neurons))                                   # the full dict on EVERY rank, enumeration keys
