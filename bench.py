@@ -58,108 +58,131 @@ def synthetic_meis(res):
 
 
 class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU, sampled DURING the timed region by an NVML polling thread (the recipe's clocks line:
+    clocks.sm, clocks.max.sm, clocks_event_reasons.{hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap}).  Round 1 piped
+    `nvidia-smi -lms` and terminated it: its block-buffered pipe never delivered a sample."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
-        self.proc = None
+    def __init__(self, index, period_s=0.02):
+        import threading
+        self.sm, self.smax, self.reasons, self.err = [], None, set(), None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            pass
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            try:  # CUDA_VISIBLE_DEVICES may renumber the devices: address the GPU by its UUID
+                self.h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(index).uuid))
+            except Exception:  # noqa: BLE001
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001
+            self.err = f"NVML unavailable: {e}"
+            return
+
+        def poll():
+            nv = self.nv
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self._stop.is_set():
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                    bits = int(get_reasons(self.h))
+                    for name, bit in self.REASONS:
+                        if bits & bit:
+                            self.reasons.add(name)
+                except Exception as e:  # noqa: BLE001
+                    self.err = str(e)
+                    return
+                self._stop.wait(period_s)
+
+        self._thread = threading.Thread(target=poll, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, smax, reasons = [], None, set()
-        for line in out.strip().splitlines():
-            parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 6:
-                continue
-            try:
-                sm.append(float(parts[0])), (smax := float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[2:6]):
-                if val == "Active":
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+        out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax, "reasons": sorted(self.reasons), "samples": len(self.sm),
+               "source": "NVML polled every 20 ms during the timed steps"}
+        if self.err:
+            out["error"] = self.err
+        return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline
 # ----------------------------------------------------------------------------------------------------------------------
+def workload_config(res):
+    """`config` of the bench line: identical in both arms (the driver compares them)."""
+    return {"workload": f"demo1 learn step, {res}x{res}x1, {N_LATENTS} latents, template neuron 0 (BASELINE configs[0] objects on B200)"}
+
+
 def cpu_learn_steps(res, n_steps, warmup, threads, anomaly=True):
-    """Times the reference's CPU learn step.  Uses the reference itself when it is mounted, else the torch-CPU port."""
+    """Times the reference's CPU learn step on the host cores -> (steps/s, seconds, kind, where).
+
+    kind "reference": the UNMODIFIED reference (the offline pip install under baseline/_ref, else mounted sources) through its own public API and
+    stock code path -- `InvarianceManifold.learn(0, steps_per_epoch=n_steps, num_max_epochs=1)`: one epoch of n_steps jittered steps (forward,
+    loss, anomaly-mode backward, Adam; inv_temp_learn_match.py:185-208) plus the call's fixed tail (one un-jittered snapshot forward, :251), all timed.
+    kind "port" (reference not installed): the torch-CPU port of the same op sequence, oracle/torch_port.py."""
+    import contextlib
+    import io
+
     import torch
 
     torch.set_num_threads(threads)
     from oracle import laminr_oracle as O
 
+    meis = synthetic_meis(res)
+    try:
+        from oracle.ref_harness import import_reference, reference_available, reference_location
+        if not reference_available(prefer_installed=True):
+            raise ImportError("reference not installed")
+        laminr = import_reference(prefer_installed=True)
+        torch.manual_seed(0)
+        np.random.seed(0)
+        model = laminr.neuron_models.simulated("demo1", img_res=[res, res])
+        im = laminr.InvarianceManifold(model, meis, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+        orig_anomaly = torch.autograd.set_detect_anomaly
+        if not anomaly:  # (informational second number: the reference switches anomaly mode on inside its loop, :206)
+            torch.autograd.set_detect_anomaly = lambda *a, **k: None
+        try:
+            with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+                if warmup > 0:
+                    im.learn(0, steps_per_epoch=warmup, num_max_epochs=1)
+                t0 = time.perf_counter()
+                im.learn(0, steps_per_epoch=n_steps, num_max_epochs=1)
+                dt = time.perf_counter() - t0
+        finally:
+            torch.autograd.set_detect_anomaly = orig_anomaly
+            orig_anomaly(False)  # the reference leaves anomaly mode on process-wide
+        return n_steps / dt, dt, "reference", reference_location()
+    except Exception as e:  # noqa: BLE001 -- any import problem -> the port
+        why = f"{type(e).__name__}: {e}"
+    from oracle.torch_port import LearnPort
     rng = np.random.RandomState(0)
     grid0 = O.latent_grid(N_LATENTS)
     sigma = 2 * np.pi / N_LATENTS
     grids = [grid0 + np.float32(rng.rand() * sigma - 0.5 * sigma) for _ in range(n_steps + warmup)]
-    meis = synthetic_meis(res)
-    kind = "port"
-    step_fn = None
-    try:
-        from oracle.ref_harness import import_reference, reference_available
-        if reference_available():
-            laminr = import_reference()
-            from laminr.contrastive_loss import SimCLROnGrid
-            from laminr.utils.general import SingleNeuronModel
-            from laminr.utils.mask import apply_mask
-            torch.manual_seed(0)
-            model = laminr.neuron_models.simulated("demo1", img_res=[res, res])
-            im = laminr.InvarianceManifold(model, meis, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
-            reg = SimCLROnGrid(1, N_LATENTS, 0.1, 0.3, True)
-            opt = torch.optim.Adam(im.template.func.parameters(), lr=1e-3)
-            snm = SingleNeuronModel(model, 0)
-            mask = torch.from_numpy(meis[0]["mask"])
-
-            def step_fn(g):  # inv_temp_learn_match.py:186-208 verbatim in behaviour (anomaly mode on, as shipped)
-                gt = torch.as_tensor(g, dtype=torch.float32).reshape(-1, 1)
-                _, img_post, _acts, _ = im.forward(gt, im.template, im.img_transforms, snm, return_template=True)
-                acts = _acts / meis[0]["activation"]
-                sim = reg.reg_term(apply_mask(img_post, mask, -1.0, 1.0))
-                loss = -acts.mean() - 2 * sim
-                opt.zero_grad()
-                torch.autograd.set_detect_anomaly(anomaly)
-                loss.backward()
-                opt.step()
-
-            kind = "reference"
-    except Exception:  # noqa: BLE001 -- any import problem -> the port
-        step_fn = None
-    if step_fn is None:
-        from oracle.torch_port import LearnPort
-        torch.manual_seed(0)
-        h, pe, ape = 50, 50, 50
-        W = [np.random.RandomState(1).randn(h, 1 + 2 * ape + 2 * pe).astype(np.float32) * 0.1] + \
-            [np.random.RandomState(2 + l).randn(h, h).astype(np.float32) * 0.1 for l in range(3)] + \
-            [np.random.RandomState(9).randn(1, h).astype(np.float32) * 0.1]
-        b = [np.zeros(w.shape[0], np.float32) for w in W]
-        B = np.random.RandomState(10).randn(2, pe).astype(np.float32) * 10
-        auxB = np.random.RandomState(11).randn(2, ape).astype(np.float32) * 0.1
-        pos, neg = O.pos_neg_masks(N_LATENTS, 0.1, True)
-        port = LearnPort(W, b, B, auxB, O.pixel_coords((res, res)), O.demo1_banks([res, res])[0], meis[0]["mask"], meis[0]["activation"], pos, neg,
-                         res=(res, res), anomaly_mode=anomaly)
-        step_fn = port.step
+    torch.manual_seed(0)
+    h, pe, ape = 50, 50, 50
+    W = [np.random.RandomState(1).randn(h, 1 + 2 * ape + 2 * pe).astype(np.float32) * 0.1] + \
+        [np.random.RandomState(2 + l).randn(h, h).astype(np.float32) * 0.1 for l in range(3)] + \
+        [np.random.RandomState(9).randn(1, h).astype(np.float32) * 0.1]
+    b = [np.zeros(w.shape[0], np.float32) for w in W]
+    B = np.random.RandomState(10).randn(2, pe).astype(np.float32) * 10
+    auxB = np.random.RandomState(11).randn(2, ape).astype(np.float32) * 0.1
+    pos, neg = O.pos_neg_masks(N_LATENTS, 0.1, True)
+    port = LearnPort(W, b, B, auxB, O.pixel_coords((res, res)), O.demo1_banks([res, res])[0], meis[0]["mask"], meis[0]["activation"], pos, neg,
+                     res=(res, res), anomaly_mode=anomaly)
     for g in grids[:warmup]:
-        step_fn(g)
+        port.step(g)
     t0 = time.perf_counter()
     for g in grids[warmup:]:
-        step_fn(g)
+        port.step(g)
     dt = time.perf_counter() - t0
-    return n_steps / dt, dt, kind
+    return n_steps / dt, dt, "port", f"oracle/torch_port.py ({why})"
 
 
 def run_reference(args):
@@ -167,15 +190,16 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    steps = max(1, min(args.steps, 60 if args.res <= 100 else 15))  # bounded sample: a reference step is ~0.2 s (100^2) / ~0.9 s (200^2)
-    warm = max(1, min(args.warmup, 3))
-    sps, dt, kind = cpu_learn_steps(args.res, steps, warm, threads)
-    sample = f"{steps} learn steps of demo1 @{args.res}x{args.res} ({N_LATENTS} latents), {'unmodified reference' if kind == 'reference' else 'torch-CPU port of the reference op sequence'}, anomaly mode on as shipped"
+    steps = max(1, min(args.steps, 60 if args.res <= 100 else 15))  # bounded sample: a reference step is ~0.1-0.2 s (100^2) / ~0.9 s (200^2)
+    warm = max(0, min(args.warmup, 10))
+    sps, dt, kind, where = cpu_learn_steps(args.res, steps, warm, threads)
+    what = (f"unmodified reference ({os.path.relpath(where, ROOT) if where.startswith(ROOT) else where}), public call InvarianceManifold.learn(0, "
+            f"steps_per_epoch={steps}, num_max_epochs=1) incl. its final snapshot forward" if kind == "reference" else f"torch-CPU port of the reference op sequence: {where}")
+    sample = f"{steps} learn steps of demo1 @{args.res}x{args.res} ({N_LATENTS} latents) in {dt:.2f} s on {threads} host threads; {what}; anomaly mode on as shipped"
     line = {
         "impl": "reference", "metric": "INR opt steps/sec (learn, 100x100)", "value": sps, "unit": "steps/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 / sps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"demo1 learn step, {args.res}x{args.res}x1, {N_LATENTS} latents, template neuron 0 (BASELINE configs[0] objects on B200)",
-                   "host": f"CPU, {threads} threads"},
+        "config": workload_config(args.res),
         "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": sps, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -352,6 +376,109 @@ def cpu_match_steps(res, n_steps, warmup, threads):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# multi-GPU record: BASELINE configs[2] + configs[4] through the public sharded API (laminr_b200.dist)
+# ----------------------------------------------------------------------------------------------------------------------
+def bench_scale(args, dev, world, rank, barrier, template_state):
+    """ONE shared synthetic population (`--pop` phase-invariant neurons at res x res), the same on every rank:
+      * `get_mei_dict_sharded` of ALL neurons (1000 ascent iterations each, RF masks on the device, full dict gathered on every rank);
+      * `match_sharded` of template 0 -> targets, STRONG (all pop-1 targets split over the ranks) and WEAK (--match-targets per GPU): template
+        broadcast, 60-angle init sweep, a fixed number of epochs with the global 1/D loss scale and the global stop-rule collective every epoch
+        (early stop disabled so that every N runs the same epochs), NCCL gather of the aligned images / activations and their copy to host memory
+        on rank 0 -- all inside the timed region (CUDA events around the call, max over ranks);
+      * sharded == unsharded: rank 0 re-runs `match` unsharded for a fixed subset of targets / `get_mei_dict` for the first neurons from the same
+        generator state and compares with what the sharded calls returned.
+    Returns the compact `scale_summary` (rank 0) -- printed as the LAST key of the JSON line."""
+    import contextlib
+    import io
+
+    import torch
+    import torch.distributed as dist
+
+    import laminr_b200 as L
+    from laminr_b200 import dist as LD
+
+    res, n_pop, epochs = args.res, args.pop, args.match_epochs
+    quiet = lambda: (contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()))
+
+    def timed(fn):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return out, t.item() / 1e3
+
+    t0 = time.perf_counter()
+    pop = LD.simulated_population_sharded(n_pop, (res, res), seed=0, device=dev)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    kw = dict(required_img_norm=1.0)
+    # ---- MEI sweep (BASELINE configs[4])
+    with quiet()[0], quiet()[1]:
+        LD.get_mei_dict_sharded(pop, [1, res, res], -1.0, 1.0, neuron_idxs=list(range(2 * world)), num_iterations=5, **kw)  # warm-up
+        torch.manual_seed(0)
+        meis, mei_s = timed(lambda: LD.get_mei_dict_sharded(pop, [1, res, res], -1.0, 1.0, **kw))
+    # the ascent kernel alone on this rank's shard of the bank (N = 1: all `--pop` neurons, 819 MB at 1024 x 100x100 -> truly HBM-bound)
+    from laminr_b200.utils.mei import batched_simulated_meis
+    lo, hi = LD.shard_bounds(n_pop, world, rank)
+    x0 = torch.randn(hi - lo, 1, res, res, device=dev)
+    batched_simulated_meis(pop, list(range(lo, hi)), x0, -1.0, 1.0, norm=1.0, num_iterations=5)
+    _, kern_s = timed(lambda: batched_simulated_meis(pop, list(range(lo, hi)), x0, -1.0, 1.0, norm=1.0, num_iterations=200))
+    mei_kernel = {"neurons": hi - lo, "us_per_iteration": kern_s / 200 * 1e6,
+                  "gbps": (20 * res * res * 4 + 3 * res * res * 4) * 200 * (hi - lo) / kern_s / 1e9}  # SURVEY 8d: F*P*4 + 3*C*P*4 per neuron-iteration
+    mei_diff = None
+    if rank == 0:  # unsharded call for the first neurons from the same seed: the same initial images, so the same MEIs
+        torch.manual_seed(0)
+        with quiet()[0], quiet()[1]:
+            few = L.get_mei_dict(pop, [1, res, res], -1.0, 1.0, neuron_idxs=[0, 1, 2, 3], **kw)
+        mei_diff = max(float(np.abs(np.asarray(few[k]["mei"]) - np.asarray(meis[k]["mei"])).max()) for k in few)
+    # ---- match (BASELINE configs[2]): template = neuron 0, learnt on rank 0 (the other ranks hold an untrained copy: overwritten by the broadcast)
+    torch.manual_seed(0)
+    im = L.InvarianceManifold(pop, meis, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0, precision=args.precision)
+    if rank == 0:
+        im.template.load_state_dict(template_state, strict=False)
+    im.template_neuron_idx = 0
+
+    def run(targets, ep):
+        state = torch.get_rng_state()
+        with quiet()[0], quiet()[1]:
+            (imgs, acts), secs = timed(lambda: LD.match_sharded(im, targets, num_epochs=ep, patience=10 ** 9))
+        return imgs, acts, secs, state
+
+    run(list(range(1, 1 + 2 * world)), 2)  # warm-up: NCCL channels, allocator, kernel attributes
+    weak_t = list(range(1, 1 + min(args.match_targets * world, n_pop - 1)))
+    _, _, weak_s, _ = run(weak_t, epochs)
+    weak_epochs = int(im.match_epochs_run)
+    strong_t = list(range(1, n_pop))
+    imgs, acts, strong_s, state = run(strong_t, epochs)
+    strong_epochs, steps = int(im.match_epochs_run), int(im.match_steps_taken)
+    match_diff, act_mean = None, None
+    if rank == 0:  # unsharded == sharded on a fixed subset (same generator state -> same jitter; same global 1/D loss scale)
+        subset = sorted({1, 2, 3, n_pop // 3, n_pop // 2, (2 * n_pop) // 3, n_pop - 2, n_pop - 1} & set(strong_t))
+        torch.set_rng_state(state)
+        with quiet()[0], quiet()[1]:
+            want_i, want_a = im.match(subset, num_epochs=epochs, patience=10 ** 9, _total_targets=len(strong_t))
+        idx = [t - 1 for t in subset]
+        match_diff = max(float(np.abs(want_i - imgs[idx]).max()), float(np.abs(want_a - acts[idx]).max()))
+        act_mean = float(np.asarray(acts).mean())
+    barrier()
+    if rank != 0:
+        return None
+    r3 = lambda x: float(f"{x:.4g}")
+    return {"n_gpus": world, "population": n_pop, "res": res, "epochs": epochs, "api": "dist.match_sharded / get_mei_dict_sharded, CUDA events, max over ranks",
+            "match_strong": {"targets": len(strong_t), "neurons_per_s": r3(len(strong_t) / strong_s), "s": r3(strong_s), "epochs_run": strong_epochs,
+                             "target_steps_per_s_incl_sweep_and_gather": r3(len(strong_t) * steps / strong_s)},
+            "match_weak": {"targets_per_gpu": len(weak_t) // world, "neurons_per_s": r3(len(weak_t) / weak_s), "s": r3(weak_s), "epochs_run": weak_epochs},
+            "mei": {"neurons": n_pop, "meis_per_s": r3(n_pop / mei_s), "s": r3(mei_s)},
+            "max_abs_sharded_minus_unsharded": {"match_imgs_acts": match_diff, "meis": mei_diff}, "mean_act_norm": r3(act_mean),
+            "population_build_s": r3(build_s), "mei_kernel": mei_kernel}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -482,6 +609,31 @@ def run_ours(args):
     fwd_ms = time_fn(fwd_only)
     bwd_ms = time_fn(bwd_only)
 
+    # ---- demo1 learn step at the second BASELINE resolution (200x200), back to back from the CUDA graph (rank 0)
+    big = None
+    if rank == 0 and args.res2 > 0:
+        r2 = args.res2
+        model2 = L.neuron_models.simulated("demo1", img_res=[r2, r2]).to(dev)
+        meis2 = synthetic_meis(r2)
+        torch.manual_seed(0)
+        imb = L.InvarianceManifold(model2, meis2, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0, precision=args.precision)
+        stb = LearnStepper(imb.template, imb.img_transforms, model2, 0, meis2[0]["mask"], meis2[0]["activation"], reg, -1.0, 1.0, N_LATENTS, lr=1e-3,
+                           reg_scale=2.0, precision=args.precision, use_graph=True)
+        nb = max(3, min(K, 50))
+        for i in range(4):
+            stb.step(grids[i])
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(nb):
+            stb.step(grids[Wm + (i % K)])
+        b.record()
+        torch.cuda.synchronize()
+        big = {"res": r2, "ms_per_step": a.elapsed_time(b) / nb, "steps": nb, "launches_per_step": stb.kernels_per_step}
+        del stb, imb, model2
+        torch.cuda.empty_cache()
+    barrier()
+
     # ---- match hot step (extra): targets sharded over ranks, weak scaling (fixed targets per GPU)
     match = None
     if args.match_targets > 0:
@@ -523,21 +675,18 @@ def run_ours(args):
                  "algorithmic_gflop_per_target_step": 2 * algorithmic_flops(res)[0] / 1e9}
         # ---- whole match() call (BASELINE metric 2: target neurons aligned/sec): 60-angle init sweep + a FIXED number of epochs (so that the number is
         #      not hostage to the early-stop) + final snapshot and D2H of the aligned images; targets sharded over the ranks, global 1/D and stop rule
-        from laminr_b200.dist import make_stop_reduce
         im2.template_neuron_idx = 0
         epochs = args.match_epochs
         import contextlib, io
-        barrier()
-        t0 = time.perf_counter()
-        with contextlib.redirect_stderr(io.StringIO()):  # tqdm bars
-            imgs, acts_m = im2.match(targets, num_epochs=epochs, patience=10 ** 9, _total_targets=Dloc * world, _stop_reduce=make_stop_reduce(dev))
-        torch.cuda.synchronize()
-        mt2 = torch.tensor([time.perf_counter() - t0], device=dev)
-        if world > 1:
-            dist.all_reduce(mt2, op=dist.ReduceOp.MAX)
-        match["aligned"] = {"metric": "target neurons aligned/sec (whole match(): 60-angle sweep + epochs + result gather to host)", "value": Dloc * world / mt2.item(),
-                            "unit": "neurons/s", "epochs": int(im2.match_epochs_run), "seconds": mt2.item(), "targets_total": Dloc * world,
-                            "result_shape": list(imgs.shape)}
+        if world == 1:  # (N > 1: the whole-call record goes through dist.match_sharded on one shared population, see scale_summary)
+            barrier()
+            t0 = time.perf_counter()
+            with contextlib.redirect_stderr(io.StringIO()):  # tqdm bars
+                imgs, acts_m = im2.match(targets, num_epochs=epochs, patience=10 ** 9)
+            torch.cuda.synchronize()
+            mt2 = time.perf_counter() - t0
+            match["aligned"] = {"metric": "target neurons aligned/sec (whole match(): 60-angle sweep + epochs + result copy to host)", "value": Dloc / mt2,
+                                "unit": "neurons/s", "epochs": int(im2.match_epochs_run), "seconds": mt2, "targets_total": Dloc, "result_shape": list(imgs.shape)}
         # ---- MEI sweep (BASELINE config 5): batched gradient ascent, 1000 iterations, neurons sharded over the ranks
         nmei = args.mei_neurons  # BASELINE configs[4]: 128 neurons per GPU
         if nmei > 0:
@@ -593,6 +742,12 @@ def run_ours(args):
     # ---- BASELINE config 4 (extra): conv-core encoder at 200x200
     conv = bench_conv(args, dev, world, rank, barrier, flush) if args.conv_res > 0 else None
 
+    # ---- the multi-GPU record (every N, N = 1 included: the anchor of the scaling curve): config 3 through the public sharded API
+    del flush
+    torch.cuda.empty_cache()
+    scale_summary = bench_scale(args, dev, world, rank, barrier, {k: v.detach().clone() for k, v in im.template.state_dict().items()
+                                                                  if k.startswith("func.") or k in ("B", "auxB")}) if args.pop > 1 else None
+
     # ---- reduce over ranks (max time), CPU baseline on rank 0 at N == 1
     tt = torch.tensor([step_ms, b2b_ms, e2e_s * 1e3], device=dev)
     if world > 1:
@@ -611,17 +766,41 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n_cpu = 40 if res <= 100 else 12
-            sps, dt, kind = cpu_learn_steps(res, n_cpu, 2, threads)
-            sps_off, _, _ = cpu_learn_steps(res, max(4, n_cpu // 2), 1, threads, anomaly=False)
+            sps, dt, kind, where = cpu_learn_steps(res, n_cpu, 2, threads)
+            sps_off, _, _, _ = cpu_learn_steps(res, max(4, n_cpu // 2), 1, threads, anomaly=False)
             cpu = {"value": sps, "unit": "steps/s", "cores": threads, "kind": kind, "value_anomaly_mode_off": sps_off,
-                   "sample": f"{n_cpu} learn steps of demo1 @{res}x{res} ({dt:.1f} s), {'unmodified reference' if kind == 'reference' else 'torch-CPU port of the reference op sequence'}, anomaly mode on as shipped"}
+                   "sample": f"{n_cpu} learn steps of demo1 @{res}x{res} ({dt:.1f} s), "
+                             f"{'unmodified reference (baseline/_ref) through InvarianceManifold.learn(0, steps_per_epoch=%d, num_max_epochs=1)' % n_cpu if kind == 'reference' else 'torch-CPU port of the reference op sequence'}, anomaly mode on as shipped"}
+        # every throughput as a fraction of its roofline (north star): tensor-bound lines against the SUSTAINED dense bf16 peak (kernels timed
+        # inside long steps), HBM-bound lines against the measured copy bandwidth; algorithmic work per SURVEY 8d (recompute / x3 split / padding
+        # not counted)
+        peak_sus, peak_hbm = peaks.get("bf16_tflops_sustained", 1386.3), peaks.get("hbm_gbs", 6549.4)
+        tf = lambda flop, ms: {"ms": ms, "tflops": flop / (ms * 1e-3) / 1e12, "frac": flop / (ms * 1e-3) / 1e12 / peak_sus}
+        roofline_all = {"peaks": {"bf16_tflops_sustained": peak_sus, "hbm_gbs": peak_hbm, "source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+                        f"learn_step_{res}": dict(tf(fwd_f + bwd_f, b2b_ms / K), bound="tensor")}
+        if big is not None:
+            f2, b2 = algorithmic_flops(big["res"])
+            roofline_all[f"learn_step_{big['res']}"] = dict(tf(f2 + b2, big["ms_per_step"]), bound="tensor", steps_per_s=1e3 / big["ms_per_step"])
+        if match is not None:
+            roofline_all[f"match_target_step_{res}"] = dict(tf(2 * fwd_f, match["ms_per_step"] / match["targets_per_gpu"]), bound="tensor")
+            if "mei" in match:
+                roofline_all[f"mei_{match['mei']['neurons_per_gpu']}_neurons_{res}"] = {
+                    "bound": "hbm (bank mostly L2-resident at this size)", "gbps": match["mei"]["algorithmic_GBps_per_gpu"],
+                    "frac": match["mei"]["algorithmic_GBps_per_gpu"] / peak_hbm}
+        if conv is not None:
+            fc, bc = algorithmic_flops(args.conv_res)
+            roofline_all[f"conv_learn_step_{args.conv_res}"] = dict(tf(fc + bc, conv["learn"]["ms_per_step"]), bound="tensor (INR part; the cone kernel is fp32 CUDA-core)")
+            roofline_all[f"conv_match_target_step_{args.conv_res}"] = dict(tf(2 * fc, conv["match"]["ms_per_step"] / conv["match"]["targets_per_gpu"]), bound="tensor (INR part)")
+        if scale_summary is not None and scale_summary.get("mei_kernel"):
+            mk_ = scale_summary.pop("mei_kernel")
+            roofline_all[f"mei_{mk_['neurons']}_neurons_{res}"] = {"bound": "hbm", "gbps": mk_["gbps"], "frac": mk_["gbps"] / peak_hbm, "us_per_iteration": mk_["us_per_iteration"]}
         line = {
             "metric": "INR opt steps/sec (learn, 100x100)", "value": world * K / (step_ms / 1e3), "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": step_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision in (None, "fp32") else args.precision,
             "data": "synthetic",
-            "config": {"workload": f"demo1 learn step, {res}x{res}x1, {N_LATENTS} latents, template neuron 0 (BASELINE configs[0] objects on B200)",
-                       "precision": args.precision or "fp32", "l2": "flushed (256 MiB write) between timed steps, outside the event pairs",
-                       "multi_gpu": "replicas only (learn has one template; match shards, see 'match')", "cuda_graph": True},
+            "config": workload_config(res),
+            "notes": {"precision": args.precision or "fp32", "l2": "flushed (256 MiB write) between timed steps, outside the event pairs",
+                      "multi_gpu": "value: replicas only (learn has one template); the sharded match / MEI record is scale_summary", "cuda_graph": True},
             "back_to_back": {"value": world * K / (b2b_ms / 1e3), "unit": "steps/s", "ms_per_step": b2b_ms / K, "note": "K graph replays in one event pair, no L2 flush (the loop as it runs)"},
             "e2e": {"value": world * K / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": 4 * N_LATENTS, "d2h_bytes_per_step": 4},
             "gpu_launches": int(stepper.kernels_per_step * K),
@@ -634,7 +813,8 @@ def run_ours(args):
                          "traffic_unit": "bytes per launch (ncu, DRAM)", "kept_activations": keep,
                          "peak_source": "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback",
                          "algorithmic_gflop": bwd_f / 1e9, "ms": bwd_ms, "forward": {"algorithmic_gflop": fwd_f / 1e9, "ms": fwd_ms, "achieved": fwd_f / (fwd_ms * 1e-3) / 1e12}},
-            "cpu_baseline": cpu, "clocks": clocks, "api_learn": api, "match": match, "conv": conv,
+            "cpu_baseline": cpu, "clocks": clocks, "api_learn": api, "roofline_all": roofline_all, "match": match, "conv": conv,
+            "scale_summary": scale_summary,  # LAST key on purpose: it must survive a truncated tail of this line at every N
         }
         print(json.dumps(line))
     if world > 1:
@@ -654,6 +834,8 @@ def main():
     ap.add_argument("--match-steps", type=int, default=20)
     ap.add_argument("--match-epochs", type=int, default=30, help="epochs of the whole-match() measurement (fixed; the early stop is disabled)")
     ap.add_argument("--mei-neurons", type=int, default=128, help="neurons per GPU in the MEI sweep measurement (BASELINE configs[4]: 128 per GPU)")
+    ap.add_argument("--res2", type=int, default=200, help="second resolution of the demo1 learn step (BASELINE: 100x100 and 200x200; 0 = skip)")
+    ap.add_argument("--pop", type=int, default=1024, help="neurons of the shared synthetic population of the multi-GPU record (BASELINE configs[2]; 0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv-res", type=int, default=200, help="resolution of the extra conv-core (BASELINE config 4) measurement (0 = skip)")
     ap.add_argument("--conv-steps", type=int, default=100)

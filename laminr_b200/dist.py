@@ -123,6 +123,28 @@ def gather_ragged(local, n_total, dst=0):
     return torch.cat([host[r][: sizes[r]].to(dev) for r in range(world)], dim=0)
 
 
+def simulated_population_sharded(n_neurons, img_res=(100, 100), seed=0, num_filters=20, device=None):
+    """`neuron_models.simulated_population(n_neurons, ...)` built in parallel: every rank generates the Gabor banks of its contiguous block of
+    neurons on its host cores (same NumPy random stream, so the banks are bit-identical to the serial build), the blocks are all-gathered on the
+    device, and every rank returns the FULL population (match / MEI sharding indexes the same model on every rank).  BASELINE config 3: 1024
+    neurons at 100x100 = 819 MB per GPU; ~5 s of host work on one process, 1/world of it here."""
+    from .neuron_models.simulated_models import simulated_population
+    from .neuron_models.utils.simulated_model import ArbitraryMultiNeuronModel, ArbitraryNeuronModel
+
+    world, rank = _world()
+    if world == 1:
+        pop = simulated_population(n_neurons, img_res=list(img_res), seed=seed, num_filters=num_filters)
+        return pop.to(device) if device is not None else pop
+    lo, hi = shard_bounds(n_neurons, world, rank)
+    local = simulated_population(n_neurons, img_res=list(img_res), seed=seed, num_filters=num_filters, only=range(lo, hi)) if hi > lo else None
+    H, W = int(img_res[1]), int(img_res[0])
+    block = local.packed_filters.reshape(hi - lo, num_filters, H, W) if local is not None else torch.empty(0, num_filters, H, W)
+    if device is not None:
+        block = block.to(device)
+    packed = gather_ragged(block, n_neurons, dst=None)
+    return ArbitraryMultiNeuronModel([ArbitraryNeuronModel.from_tensor(packed[i]) for i in range(n_neurons)], packed=packed)
+
+
 def match_sharded(im, target_neuron_idxs, **match_kwargs):
     """`InvarianceManifold.match` with the targets sharded over the ranks.  Call on every rank with the same arguments after `learn`
     ran on rank 0 (any rank may hold an untrained copy of the template: it is overwritten by rank 0's).

@@ -51,19 +51,22 @@ def simulated(model_type="demo1", img_res=[100, 100]):
     raise ValueError(f"Model type {model_type} does not exist.")
 
 
-def simulated_population(n_neurons, img_res=[100, 100], seed=0, num_filters=20):
+def simulated_population(n_neurons, img_res=[100, 100], seed=0, num_filters=20, only=None):
     """Synthetic population of phase-invariant neurons assembled from the public generators (BASELINE config 3):
     np.random.seed(seed); mats = random_transformation_matrices(n); locs ~ U(-0.35, 0.35)^2 drawn after the matrices;
-    neuron i uses transformation mats[i] (None for i = 0)."""
+    neuron i uses transformation mats[i] (None for i = 0).
+    `only` (optional list of population indices): build just these neurons of the `n_neurons` population -- the same random stream, so neuron k of
+    the result is bit-identical to neuron only[k] of the full population (a sample of config 3 without its 819 MB bank)."""
     np.random.seed(seed)
     mats = random_transformation_matrices(n_neurons)
     locs = np.random.uniform(-0.35, 0.35, size=(n_neurons, 2))
     import torch
-    packed = torch.empty(n_neurons, num_filters, int(img_res[1]), int(img_res[0]))  # meshgrid 'xy': rows = grid_size[1]
+    idxs = list(range(n_neurons)) if only is None else [int(i) for i in only]
+    packed = torch.empty(len(idxs), num_filters, int(img_res[1]), int(img_res[0]))  # meshgrid 'xy': rows = grid_size[1]
     models = []
-    for i in range(n_neurons):
+    for k, i in enumerate(idxs):
         m = phase_invariant_neuron_generator(locs[i], img_res, transformation_matrix=None if i == 0 else mats[i], num_filters=num_filters)[0]
-        packed[i].copy_(m.filters)
-        m.filters = packed[i]  # the per-neuron buffer becomes a view of the packed bank: one copy of the population in host memory
+        packed[k].copy_(m.filters)
+        m.filters = packed[k]  # the per-neuron buffer becomes a view of the packed bank: one copy of the population in host memory
         models.append(m)
     return ArbitraryMultiNeuronModel(models, packed=packed)

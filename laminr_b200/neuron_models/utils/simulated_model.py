@@ -65,6 +65,15 @@ class ArbitraryNeuronModel(nn.Module):
         self.eps = eps
         self._nf = None
 
+    @classmethod
+    def from_tensor(cls, filters, eps=1e-6):
+        """A neuron whose `filters` buffer IS the given [F,H,W] tensor (no copy; e.g. a row of a packed population bank on the device)."""
+        m = cls.__new__(cls)
+        nn.Module.__init__(m)
+        m.register_buffer("filters", filters)
+        m.eps, m._nf = eps, None
+        return m
+
     def forward(self, x):
         F, H, W = self.filters.shape
         if self._nf is None or self._nf.device != x.device:

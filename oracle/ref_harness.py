@@ -17,11 +17,27 @@ import types
 
 import numpy as np
 
-REFERENCE_SRC = os.environ.get("LAMINR_REFERENCE_SRC", "/root/reference/src")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Where the unmodified reference can live: the mounted sources (build container only) or the offline pip install of those sources under
+# baseline/_ref (`pip install --no-index --no-build-isolation --no-deps --target baseline/_ref <copy of /root/reference>`, done by
+# __graft_entry__.build(); git-ignored, but it travels to the GPU box -- that is what `bench.py --impl reference` times there).
+INSTALLED_REF = os.path.join(_REPO, "baseline", "_ref")
+_CANDIDATES = [p for p in (os.environ.get("LAMINR_REFERENCE_SRC"), "/root/reference/src", INSTALLED_REF) if p]
 
 
-def reference_available():
-    return os.path.isdir(os.path.join(REFERENCE_SRC, "laminr"))
+def _find(prefer_installed=False):
+    cands = ([INSTALLED_REF] + _CANDIDATES) if prefer_installed else _CANDIDATES
+    for p in cands:
+        if os.path.isdir(os.path.join(p, "laminr")):
+            return p
+    return None
+
+
+REFERENCE_SRC = _find() or "/root/reference/src"
+
+
+def reference_available(prefer_installed=False):
+    return _find(prefer_installed) is not None
 
 
 def _convex_hull_image(img):
@@ -49,13 +65,22 @@ def install_stubs():
     mor.convex_hull_image = _convex_hull_image
 
 
-def import_reference():
-    """Returns the reference's `laminr` package (plus featurevis / neuralpredictors on sys.path)."""
-    if not reference_available():
-        raise RuntimeError(f"reference sources not found under {REFERENCE_SRC}")
+def import_reference(prefer_installed=False):
+    """Returns the reference's `laminr` package (plus featurevis / neuralpredictors on sys.path).  prefer_installed: take the pip-installed copy
+    under baseline/_ref first (bench.py's reference arm), else the mounted sources first (golden generation)."""
+    src = _find(prefer_installed)
+    if src is None:
+        raise RuntimeError(f"reference not found (looked in {_CANDIDATES})")
     install_stubs()
-    if REFERENCE_SRC not in sys.path:
-        sys.path.insert(0, REFERENCE_SRC)
+    if src not in sys.path:
+        sys.path.insert(0, src)
     import laminr  # noqa: F401  (the reference package, not laminr_b200)
 
     return laminr
+
+
+def reference_location():
+    """Path the imported reference package came from (for the bench line's `sample`)."""
+    import laminr
+
+    return os.path.dirname(os.path.dirname(os.path.abspath(laminr.__file__)))

@@ -40,6 +40,11 @@ def _worker(rank, world, port, n_targets, q):
             tmpl.register_buffer("coords_shift_to_center", torch.randn(1, 2))
         D.broadcast_template(tmpl, src=0)
         tmpl_state = [p.detach().numpy().copy() for p in tmpl.func.parameters()] + [tmpl.B.numpy().copy(), tmpl.auxB.numpy().copy(), tmpl.coords.numpy().copy()]
+        # --- population built in parallel (every rank generates its block of neurons, the banks are all-gathered): the serial build, bit for bit
+        from laminr_b200.neuron_models import simulated_population
+        pop = D.simulated_population_sharded(5, (12, 10), seed=4, num_filters=6)
+        assert torch.equal(pop.packed_filters, simulated_population(5, img_res=[12, 10], seed=4, num_filters=6).packed_filters)
+        assert len(pop.neuron_models_list) == 5 and pop.neuron_models_list[3].filters.data_ptr() == pop.packed_filters[3].data_ptr()
         # --- RNG agreement: the jittered grids are drawn on the CPU generator
         D.broadcast_rng_state(src=0)
         dm = JitteringGridDatamodule(1, 20, 3)
