@@ -515,9 +515,12 @@ __global__ void __launch_bounds__(AFF_THREADS) affine_grad_kernel(Args a) {
     }
     __syncthreads();
     if (t < nq) cxy[t] = transformed_coord(a, cst, p0 + t);
+    // register-blocked items (4 pixels x 4 encoding features each).  A strided loop, not `if (t < items)`: 72 pixels x 100 features are 450 items
+    // for 448 threads -- the two items left out fed uninitialised shared memory into the gradient of every block of 72 pixels (any match call
+    // with D * P > 148 * 68 pixels, e.g. two targets at 100x100; found by tests/golden/match_step_100.npz)
     const int npg = ppb / 4, nkg = nb / 4;
-    if (t < npg * nkg) {
-        const int pg = t / nkg, kg = t % nkg;
+    for (int item = t; item < npg * nkg; item += AFF_THREADS) {
+        const int pg = item / nkg, kg = item % nkg;
         float4 acc[4];
 #pragma unroll
         for (int x = 0; x < 4; ++x) acc[x] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -725,6 +728,8 @@ static int launch_prep(const Args& a, cudaStream_t st) {
     constexpr int HP = (HID + 3) / 4 * 4;
     const int nb = 2 * a.net.pe;
     const int cp_blocks = a.want_cp ? (a.tl.D * a.tl.P + a.ppb_prep - 1) / a.ppb_prep : 0;
+    // the coordinate-part GEMM of a block runs one (4 pixel x 4 output) item per thread; the B table is staged by threads 64 .. 64 + 2 pe
+    LMR_CHECK_ARG(!a.want_cp || ((a.ppb_prep / 4) * (HP / 4) <= 256 && 64 + nb <= 256 && nb <= 128), "inr: pe_dim %d not supported by the preparation kernel", a.net.pe);
     size_t smem = (size_t)2 * a.net.ape * sizeof(float);
     if (a.want_cp) smem = ((size_t)nb * HP + (size_t)nb * a.ppb_prep) * sizeof(float);
     static size_t cache = 0;
@@ -742,6 +747,9 @@ template <int HID>
 static int launch_l0_partial(const Args& a, float* l0part, int grid_l0, cudaStream_t st) {
     constexpr int HP = (HID + 3) / 4 * 4;
     const size_t smem = (size_t)a.ppb * (HP + 2 * a.net.pe) * sizeof(float);
+    // one register-blocked item (4 outputs x 4 encoding features) per thread, accumulated across the block's pixel chunks
+    LMR_CHECK_ARG((HP / 4) * (2 * a.net.pe / 4) <= L0_THREADS && a.net.pe % 2 == 0,
+                  "inr_backward: pe_dim %d needs %d layer-0 weight-gradient items (> %d threads)", a.net.pe, (HP / 4) * (2 * a.net.pe / 4), L0_THREADS);
     static size_t cache = 0;
     if (smem > 40 * 1024 && smem > cache) {
         LMR_CUDA_OK(cudaFuncSetAttribute(l0_partial_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
