@@ -63,7 +63,7 @@ class ClockSampler:
     `nvidia-smi -lms` and terminated it: its block-buffered pipe never delivered a sample."""
     REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index, period_s=0.02):
+    def __init__(self, index, period_s=0.002):
         import threading
         self.sm, self.smax, self.reasons, self.err = [], None, set(), None
         self._stop = threading.Event()
@@ -105,7 +105,7 @@ class ClockSampler:
             self._stop.set()
             self._thread.join(timeout=2)
         out = {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax, "reasons": sorted(self.reasons), "samples": len(self.sm),
-               "source": "NVML polled every 20 ms during the timed steps"}
+               "source": "NVML polled every 2 ms during the timed steps"}
         if self.err:
             out["error"] = self.err
         return out

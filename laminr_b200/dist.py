@@ -142,7 +142,10 @@ def simulated_population_sharded(n_neurons, img_res=(100, 100), seed=0, num_filt
     if device is not None:
         block = block.to(device)
     packed = gather_ragged(block, n_neurons, dst=None)
-    return ArbitraryMultiNeuronModel([ArbitraryNeuronModel.from_tensor(packed[i]) for i in range(n_neurons)], packed=packed)
+    pop = ArbitraryMultiNeuronModel([ArbitraryNeuronModel.from_tensor(packed[i]) for i in range(n_neurons)], packed=packed)
+    # the small index buffers (filter counts, neuron list) are created on the host: move them next to the bank (the bank itself and the per-neuron
+    # views of it are already there: `.to` returns the same tensors)
+    return pop.to(packed.device)
 
 
 def match_sharded(im, target_neuron_idxs, **match_kwargs):

@@ -44,7 +44,13 @@ def _require_cuda(*tensors):
 
 
 def _ptr(t):
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """Device pointer of `t` for the C ABI (every pointer argument of include/laminr_b200.h is device memory): a host tensor here would be an
+    illegal address inside the kernel, so it is refused."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("laminr_b200 operators run on CUDA (sm_100a) only; got a tensor on %s. There is no CPU fallback." % t.device)
+    return C.c_void_p(t.data_ptr())
 
 
 def _stream():
