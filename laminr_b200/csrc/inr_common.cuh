@@ -29,6 +29,12 @@ struct Tiling {
     int N, P, D, NC, TP, tilesP, nChunks, numTiles;
 };
 
+// Kept-activation record of one 128-row tile (tensor-core path, LMR_PREC_KEEP_ACTIVATIONS): the 32 KB split-bf16 operand-tile images of
+// h_1 .. h_{nl-1} as the backward's MMAs read them, then the tile's output values y[c][row] (fp32: the backward needs dy = g (1 - y^2)
+// per row and would otherwise have to rebuild y from all column groups of the row).
+constexpr size_t KEEP_TILE_BYTES = 32768, KEEP_Y_BYTES = 2048;  // 4 channels x 128 rows x 4 bytes
+__host__ __device__ inline size_t keep_record_bytes(int nl) { return (size_t)(nl - 1) * KEEP_TILE_BYTES + KEEP_Y_BYTES; }
+
 static inline Tiling make_tiling(int N, int P, int D, int tp_cap, int rows = TR_MAX) {
     Tiling t;
     t.N = N, t.P = P, t.D = D;
@@ -60,7 +66,7 @@ struct Args {
     float* Cpg;    // [D*P, HP]  layer-0 coordinate part Cp[d,p][o] = sum_k beta[d,p][k] W0c[o][k]   (tensor-core path)
     unsigned char* wtimg;  // (nl-1) x 16 KB: split-bf16 (hi | lo) K-major core-matrix images of the hidden weight tiles (tensor-core path)
     float* betaG;  // [D*P, 2*pe] sin/cos(coords.B) (tensor-core path, D == 1: consumed by the layer-0 weight-gradient kernel), else null
-    unsigned char* hsave;  // [numTiles, nl-1, 32 KB] operand-tile images of h_1..h_{nl-1} kept by the forward for the backward (tensor-core path, opt-in), else null
+    unsigned char* hsave;  // [numTiles] kept-activation records (keep_record_bytes: operand-tile images of h_1..h_{nl-1}, then y) written by the forward for the backward (tensor-core path, opt-in), else null
     int want_cp;
     int ppb;       // pixels per l0 / affine-gradient block
     int ppb_prep;  // pixels per prep block (two blocks per SM: the prep blocks are latency-bound)
@@ -657,7 +663,7 @@ static inline WsLayout ws_layout(const Net& nt, const Tiling& tl, bool bwd, bool
     w.wtimg = want_cp ? take((size_t)(nt.nl - 1) * 16384 / 4) : 0;
     w.Cpg = want_cp ? take((size_t)tl.D * tl.P * HP) : 0;
     w.betaG = (want_cp && tl.D == 1) ? take((size_t)tl.P * 2 * nt.pe) : 0;  // identical prefix in the forward and backward layouts
-    w.hsave = (want_cp && keep_act && !bwd) ? take((size_t)tl.numTiles * (nt.nl - 1) * 32768 / 4) : 0;  // forward layout only (a suffix of it)
+    w.hsave = (want_cp && keep_act && !bwd) ? take((size_t)tl.numTiles * keep_record_bytes(nt.nl) / 4) : 0;  // forward layout only (a suffix of it)
     w.gridMain = tl.numTiles < num_sms() ? tl.numTiles : num_sms();
     const int total = tl.D * tl.P;
     static const int l0_bps = getenv("LMR_L0_BPS") && atoi(getenv("LMR_L0_BPS")) > 0 ? atoi(getenv("LMR_L0_BPS")) : 1;  // l0 / affine-gradient blocks per SM (tuning knob)

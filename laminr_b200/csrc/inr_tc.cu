@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(NT_T, 4) inr_fwd_ts_kernel(Args a) {
             Cj += (active ? j : 0) * SHS;
             const bool as_smem = s.As != nullptr && !multi_chunk;
             const float* An = as_smem ? s.As + (active ? nl : 0) * SHS : a.Avec + (size_t)(ti.n0 + (active ? nl : 0)) * SHP;
-            uint8_t* gimg = a.hsave != nullptr ? a.hsave + (size_t)(blockIdx.x + it * gridDim.x) * (LH - 1) * TILE_BYTES : nullptr;  // h_1 | h_2 | h_3
+            uint8_t* gimg = a.hsave != nullptr ? a.hsave + (size_t)(blockIdx.x + it * gridDim.x) * keep_record_bytes(LH) : nullptr;  // h_1 | h_2 | h_3 | y
             // ---- h_1 = tanh(A[n] + Cp[j]) -> operand (the previous tile's last accumulator was waited for: the operand columns are free)
 #pragma unroll 1
             for (int kc = 0; kc < 4; ++kc) {
@@ -698,10 +698,17 @@ __global__ void __launch_bounds__(NT_T, 4) inr_fwd_ts_kernel(Args a) {
                             y[c] = fmaf(h.x, w.x, fmaf(h.y, w.y, y[c]));
                         }
                     }
+#pragma unroll
+                    for (int c = 0; c < C; ++c) y[c] = act_tanh<FAST>(s.bout[c] + y[c]);
                     if (active) {
                         const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + nl)) * C) * tl.P + ti.p0 + j;
 #pragma unroll
-                        for (int c = 0; c < C; ++c) a.img[base + (size_t)c * tl.P] = act_tanh<FAST>(s.bout[c] + y[c]);
+                        for (int c = 0; c < C; ++c) a.img[base + (size_t)c * tl.P] = y[c];
+                    }
+                    if (gimg != nullptr) {  // the record's y[c][row] (0 for rows without a pixel: their gradient is zero whatever they hold)
+                        float* yrec = reinterpret_cast<float*>(gimg + (size_t)(LH - 1) * TILE_BYTES);
+#pragma unroll
+                        for (int c = 0; c < C; ++c) __stcs(yrec + c * 128 + row, active ? y[c] : 0.f);
                     }
                 }
             }
@@ -760,7 +767,7 @@ __global__ void __launch_bounds__(128 * NG + 64, 1) inr_bwd_tc_kernel(Args a) {
             for (int it = 0; it < myTiles; ++it) {
                 const int rot = (2 * it) % NBUF_BWD;
                 auto buf = [&](int role) { return s.tiles + (size_t)wrap_buf(role + rot) * TILE_BYTES; };
-                const uint8_t* src = a.hsave + (size_t)(blockIdx.x + it * gridDim.x) * (LH - 1) * TILE_BYTES;
+                const uint8_t* src = a.hsave + (size_t)(blockIdx.x + it * gridDim.x) * keep_record_bytes(LH);
                 if (it > 0) mbar_wait(&s.bars[BAR_FREE], (uint32_t)(it - 1) & 1);      // dW_2 of the previous tile done: its dz_2 buffer = this h_3 buffer
                 mbar_arrive_expect_tx(&s.bars[BAR_LAND + 2], TILE_BYTES);
                 bulk_copy_g2s(buf(ROLE_H1 + 2), src + 2 * (size_t)TILE_BYTES, TILE_BYTES, &s.bars[BAR_LAND + 2], pol);
@@ -1687,6 +1694,418 @@ __global__ void __launch_bounds__(b2::NT, 1) inr_bwd2_kernel(Args a) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// backward on kept activations with TWO 128-row tiles in flight per CTA ("ping-pong", round 2).
+//
+// The one-tile kernel above is a serial chain per tile -- epilogue step -> MMAs -> epilogue step ... -- so the tensor pipe idles during every
+// epilogue step and the 16 epilogue warps idle during every MMA phase (tensor pipe active 25 %, 17 % of the executed instructions mbarrier spins).
+// Here the SAME 16 epilogue warps alternate between two tiles A and B (slots 0 / 1): while they turn A's accumulator into A's next operand tile the
+// tensor pipe runs B's products, and vice versa.  What makes two tiles fit:
+//   * shared memory: per slot ONE gradient tile D_s that the epilogue overwrites in place (dz_3 -> dz_2 -> dz_1 -> the fp32 dz_0 panel): legal
+//     because the tcgen05.commit an epilogue step waits for is issued BEHIND the weight-gradient MMAs that read D_s (their ~600 cycles sit on
+//     this slot's critical path, hidden by the other slot's epilogue step).  The kept activation tiles h_3, h_2, h_1 of both slots stream through a
+//     ring of three 32 KB buffers (order h_3(A) h_3(B) h_2(A) h_2(B) h_1(A) h_1(B)): a loader thread refills a buffer as soon as the epilogue step
+//     that was its last reader has finished, one epilogue step (~3 k cycles) ahead of its first use.  3 + 2 tiles + 48 KB of weights = 208 KB;
+//   * tensor memory: one 64-column accumulator per slot (the next product of a slot is issued only after its epilogue step has finished, so no
+//     ping-pong pair per tile) + the three resident 128-column weight-gradient accumulators = 512 columns;
+//   * one operand hand-over (proxy fence + mbarrier arrive) per epilogue step instead of one per 16-feature k-chunk: the k-chunk pipelining of the
+//     one-tile kernel is what the second tile replaces;
+//   * y comes from the kept record (written by the forward) instead of being rebuilt from the four column groups of a row: no partial dot-product
+//     exchange through shared memory, no named barrier, no second tanh in the first epilogue step.
+// Tiles are walked in the REVERSE order of the forward (LMR_BWD_REVERSE=0 switches it off): the records written last are the ones still in L2.
+// ---------------------------------------------------------------------------------------------------------------
+namespace pp {
+constexpr int NG = 4, NE = 128 * NG, NT = NE + 64;  // 16 epilogue warps (4 lane quarters x 4 column groups) + the MMA warp + the loader warp
+constexpr int NCH = 8 / NG;                          // 16-byte chunks (8 features) per epilogue thread
+constexpr int NRING = 3;
+constexpr uint32_t TM_ACC_S = 0;    // + 64 s: accumulator of slot s
+constexpr uint32_t TM_DW_PP = 128;  // + 128 (l - 1): weight-gradient accumulators
+constexpr int B_OP = 0;     // [0..1]  slot s: an epilogue step has finished (D_s written, accumulator and h tile consumed)      16 warp arrivals
+constexpr int B_ACC = 2;    // [2..3]  slot s: accumulator ready                                                                  tcgen05.commit
+constexpr int B_LAND = 4;   // [4..6]  ring buffer r: kept tile landed                                                            1 arrival + 32 KB
+constexpr int B_HFREE = 7;  // [7..9]  ring buffer r: its last reader (an epilogue step) has finished                             16 warp arrivals
+constexpr int B_DONE = 10;  // every MMA of the CTA has completed
+constexpr int NB = 12;
+constexpr int MAX_DA_PP = 4;  // dA[n][o] accumulators per epilogue thread: N * 50 <= 4 * 512
+constexpr int STGP = 53;      // row stride (floats) of the fp32 dz_0 panel (odd: conflict-free both ways); 128 x 53 x 4 = 27 KB <= one tile
+
+struct Smem {
+    uint8_t *ring, *dbuf, *wt;
+    float *Wout, *bout;
+    uint64_t* bars;
+    uint32_t* tmem;
+    size_t bytes;
+    __host__ __device__ Smem(uint8_t* base, int C) {
+        uint8_t* p = base;
+        auto take = [&](size_t n) {
+            uint8_t* r = p;
+            p += (n + 127) / 128 * 128;
+            return r;
+        };
+        ring = take((size_t)NRING * TILE_BYTES);
+        dbuf = take((size_t)2 * TILE_BYTES);
+        wt = take((size_t)(LH - 1) * WT_BYTES);
+        Wout = reinterpret_cast<float*>(take((size_t)C * HPAD * 4));
+        bout = reinterpret_cast<float*>(take(16));
+        bars = reinterpret_cast<uint64_t*>(take(NB * 8));
+        tmem = reinterpret_cast<uint32_t*>(take(16));
+        bytes = p - base;
+    }
+};
+
+// position of the kept tile h_l of (pair j, slot s) in the load sequence of the CTA: 6 tiles per full pair, so every pair starts at ring buffer 0.
+// ns = slots of the pair (2, or 1 for a trailing single tile).  -> ring buffer and how many loads went into that buffer before this one.
+struct RingPos {
+    int r, n;
+};
+__device__ __forceinline__ RingPos ring_pos(int j, int ns, int l, int s) {
+    const int o = (LH - 1 - l) * ns + s;  // 0..5
+    RingPos p;
+    p.r = o >= 3 ? o - 3 : o;
+    p.n = 2 * j + (o >= 3 ? 1 : 0);
+    return p;
+}
+}  // namespace pp
+
+template <bool FAST, int C>
+__global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int reverse) {
+    using namespace pp;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const Net& nt = a.net;
+    const Tiling& tl = a.tl;
+    pp::Smem s(smem_raw, C);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const bool want_w = a.want_weights != 0;
+    load_weight_tiles(a, s);
+    if (warp == NE / 32) tmem_alloc(s.tmem, 512);
+    if (t == 0) {
+        mbar_init(&s.bars[B_OP], NE / 32), mbar_init(&s.bars[B_OP + 1], NE / 32);
+        mbar_init(&s.bars[B_ACC], 1), mbar_init(&s.bars[B_ACC + 1], 1);
+#pragma unroll
+        for (int r = 0; r < NRING; ++r) mbar_init(&s.bars[B_LAND + r], 1), mbar_init(&s.bars[B_HFREE + r], NE / 32);
+        mbar_init(&s.bars[B_DONE], 1);
+        mbar_fence_init();
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tm = *s.tmem;
+    const int G = (int)gridDim.x, b = (int)blockIdx.x;
+    const int myTiles = (tl.numTiles - b + G - 1) / G;
+    const int nPairs = (myTiles + 1) >> 1;
+    auto tile_of = [&](int k) { return reverse ? tl.numTiles - 1 - (b + k * G) : b + k * G; };  // k-th tile of this CTA
+
+    if (warp == NE / 32 + 1) {
+        if (lane == 0) {  // ---- loader: h_3, h_2, h_1 of both slots of every pair, each as soon as its ring buffer has been released
+            const uint64_t pol = l2_policy_evict_first();  // read once
+            for (int j = 0; j < nPairs; ++j) {
+                const int ns = (2 * j + 1 < myTiles) ? 2 : 1;
+#pragma unroll 1
+                for (int l = LH - 1; l >= 1; --l)
+#pragma unroll 1
+                    for (int sl = 0; sl < ns; ++sl) {
+                        const RingPos rp = ring_pos(j, ns, l, sl);
+                        if (rp.n > 0) mbar_wait(&s.bars[B_HFREE + rp.r], (uint32_t)(rp.n - 1) & 1);
+                        const uint8_t* src = a.hsave + (size_t)tile_of(2 * j + sl) * keep_record_bytes(LH) + (size_t)(l - 1) * TILE_BYTES;
+                        mbar_arrive_expect_tx(&s.bars[B_LAND + rp.r], TILE_BYTES);
+                        bulk_copy_g2s(s.ring + (size_t)rp.r * TILE_BYTES, src, TILE_BYTES, &s.bars[B_LAND + rp.r], pol);
+                    }
+            }
+        }
+    } else if (warp == NE / 32) {
+        if (lane == 0) {  // ---- MMA issuer
+            const uint32_t ring_addr = smem_u32(s.ring), d_addr = smem_u32(s.dbuf), w_addr = smem_u32(s.wt);
+            for (int j = 0; j < nPairs; ++j) {
+                const int ns = (2 * j + 1 < myTiles) ? 2 : 1;
+                // z_4 = h_3 W_3^T of both slots (the accumulator of a slot is free once the last epilogue step of its previous tile has read it)
+#pragma unroll 1
+                for (int sl = 0; sl < ns; ++sl) {
+                    const RingPos rp = ring_pos(j, ns, LH - 1, sl);
+                    mbar_wait(&s.bars[B_LAND + rp.r], (uint32_t)rp.n & 1);
+                    if (j > 0) mbar_wait(&s.bars[B_OP + sl], 1);
+                    fence_after_sync();
+                    const StageDesc sd = make_stage(ring_addr + (uint32_t)rp.r * TILE_BYTES, w_addr + (uint32_t)(LH - 2) * WT_BYTES, 0);
+#pragma unroll
+                    for (int kc = 0; kc < 4; ++kc) issue_kstep(tm + TM_ACC_S + 64u * sl, sd, kc);
+                    mma_commit(&s.bars[B_ACC + sl]);
+                }
+                // step p = 1..3: dh_l = dz_l W_l (l = 4 - p), then dW_l += dz_l^T h_l; ONE commit behind both (see the header comment)
+#pragma unroll 1
+                for (int p = 1; p < LH; ++p) {
+                    const int l = LH - p;
+#pragma unroll 1
+                    for (int sl = 0; sl < ns; ++sl) {
+                        mbar_wait(&s.bars[B_OP + sl], (uint32_t)(p - 1) & 1);
+                        fence_after_sync();
+                        const uint32_t dz = d_addr + (uint32_t)sl * TILE_BYTES;
+                        const StageDesc sd = make_stage(dz, w_addr + (uint32_t)(l - 1) * WT_BYTES, 1);
+#pragma unroll
+                        for (int kc = 0; kc < 4; ++kc) issue_kstep(tm + TM_ACC_S + 64u * sl, sd, kc);
+                        if (want_w) {
+                            const RingPos rp = ring_pos(j, ns, l, sl);
+                            if (l < LH - 1) {  // (h_3 landed before z_4)
+                                mbar_wait(&s.bars[B_LAND + rp.r], (uint32_t)rp.n & 1);
+                                fence_after_sync();
+                            }
+                            issue_wgrad(tm + TM_DW_PP + (uint32_t)(l - 1) * 128, dz, ring_addr + (uint32_t)rp.r * TILE_BYTES, j == 0 && sl == 0);
+                        }
+                        mma_commit(&s.bars[B_ACC + sl]);
+                    }
+                }
+            }
+            mma_commit(&s.bars[B_DONE]);
+        }
+    } else {  // ---- epilogue threads
+        const RowCtx rc = row_ctx();
+        const int TP = tl.TP;
+        const int nl = rc.row / TP, jpx = rc.row % TP;
+        const int g0_j = t / SHP, g0_o = t % SHP;
+        float dA[MAX_DA_PP];
+#pragma unroll
+        for (int q = 0; q < MAX_DA_PP; ++q) dA[q] = 0.f;
+        float wacc[C][8 * NCH], bacc[C];  // this row's running sums of dy_c h_4[k] and of dy_c over the CTA's tiles
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            bacc[c] = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8 * NCH; ++k) wacc[c][k] = 0.f;
+        }
+        auto arrive = [&](uint64_t* bar) {  // this warp has finished an epilogue step (call behind a __syncwarp)
+            if (lane == 0) mbar_arrive(bar);
+        };
+
+        for (int j = 0; j < nPairs; ++j) {
+            const int ns = (2 * j + 1 < myTiles) ? 2 : 1;
+            TileIdx tis[2];
+            bool act[2];
+            float dy[2][C];
+            // upstream gradient and output value of this thread's row in both tiles: dy = g (1 - y^2)   (issued first: two global round trips
+            // that would otherwise sit in front of the first epilogue step)
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                act[sl] = false;
+#pragma unroll
+                for (int c = 0; c < C; ++c) dy[sl][c] = 0.f;
+                if (sl < ns) {
+                    const int tile = tile_of(2 * j + sl);
+                    tis[sl] = decode_tile(tl, tile);
+                    act[sl] = nl < tis[sl].nn && jpx < tis[sl].np;
+                    if (act[sl]) {
+                        const size_t base = (((size_t)tis[sl].d * tl.N + (tis[sl].n0 + nl)) * C) * tl.P + tis[sl].p0 + jpx;
+                        const float* yrec = reinterpret_cast<const float*>(a.hsave + (size_t)tile * keep_record_bytes(LH) + (size_t)(LH - 1) * TILE_BYTES);
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const float gg = __ldg(a.g_img + base + (size_t)c * tl.P), yy = __ldcs(yrec + c * 128 + rc.row);
+                            dy[sl][c] = gg * (1.f - yy * yy);
+                        }
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int p = 0; p < LH; ++p) {
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    if (sl >= ns) continue;
+                    uint8_t* Ds = s.dbuf + (size_t)sl * TILE_BYTES;
+                    const uint32_t acc = tm + TM_ACC_S + 64u * sl + rc.lane_taddr;
+                    float2 v[4 * NCH];
+                    float* vf = reinterpret_cast<float*>(v);
+                    if (p == 0) {
+                        // ---- h_4 = tanh(z_4) in registers; dz_3 = (Wout^T dy)(1 - h_4^2) -> D_s; running sums for dWout / dbout
+                        mbar_wait(&s.bars[B_ACC + sl], 0);
+                        fence_after_sync();
+                        load_acc<NG>(acc, rc.g, vf);
+                        if (want_w) {
+#pragma unroll
+                            for (int c = 0; c < C; ++c) bacc[c] += dy[sl][c];
+                        }
+#pragma unroll
+                        for (int i = 0; i < NCH; ++i) {
+                            const int ch = rc.g + NG * i;
+                            if (ch < 7) {
+                                tanh_begin<FAST>(v + 4 * i);
+                                tanh_end<FAST>(v + 4 * i);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    float2 dh = make_float2(0.f, 0.f);
+                                    const float2 h = v[4 * i + q];
+#pragma unroll
+                                    for (int c = 0; c < C; ++c) {
+                                        const float2 d2 = make_float2(dy[sl][c], dy[sl][c]);
+                                        if (want_w) {
+                                            const float2 wa = fma2(h, d2, make_float2(wacc[c][8 * i + 2 * q], wacc[c][8 * i + 2 * q + 1]));
+                                            wacc[c][8 * i + 2 * q] = wa.x, wacc[c][8 * i + 2 * q + 1] = wa.y;
+                                        }
+                                        dh = fma2(*reinterpret_cast<const float2*>(s.Wout + c * HPAD + 8 * ch + 2 * q), d2, dh);
+                                    }
+                                    // dh (1 - h^2); padding columns: Wout == 0; constant-1 column: 1 - 1 == 0
+                                    v[4 * i + q] = fma2(mul2(dh, mul2(h, h)), make_float2(-1.f, -1.f), dh);
+                                }
+                                store_chunk2<4>(Ds, rc.row, ch, v + 4 * i);
+                            } else {
+                                store_chunk_zero(Ds, rc.row, ch);  // chunk 7 (features 56..63): the previous tile's fp32 panel sat here
+                            }
+                        }
+                        fence_proxy_async();
+                        __syncwarp();
+                        arrive(&s.bars[B_OP + sl]);
+                    } else {
+                        // ---- dz_{l-1} = dh_l (1 - h_l^2), l = 4 - p   (h_l[50] == 1 zeroes the bias column)
+                        const int l = LH - p;
+                        const RingPos rp = ring_pos(j, ns, l, sl);
+                        const uint8_t* Hl = s.ring + (size_t)rp.r * TILE_BYTES;
+                        mbar_wait(&s.bars[B_LAND + rp.r], (uint32_t)rp.n & 1);
+                        float2 hv[4 * NCH];
+#pragma unroll
+                        for (int i = 0; i < NCH; ++i)
+                            if (rc.g + NG * i < 7) load_chunk2<4>(Hl, rc.row, rc.g + NG * i, hv + 4 * i);
+                        mbar_wait(&s.bars[B_ACC + sl], (uint32_t)p & 1);
+                        fence_after_sync();
+                        load_acc<NG>(acc, rc.g, vf);
+#pragma unroll
+                        for (int i = 0; i < NCH; ++i)
+                            if (rc.g + NG * i < 7) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) v[4 * i + q] = fma2(mul2(v[4 * i + q], mul2(hv[4 * i + q], hv[4 * i + q])), make_float2(-1.f, -1.f), v[4 * i + q]);
+                            }
+                        if (p < LH - 1) {
+#pragma unroll
+                            for (int i = 0; i < NCH; ++i)
+                                if (rc.g + NG * i < 7) store_chunk2<4>(Ds, rc.row, rc.g + NG * i, v + 4 * i);
+                            fence_proxy_async();
+                            __syncwarp();
+                            arrive(&s.bars[B_OP + sl]);
+                            arrive(&s.bars[B_HFREE + rp.r]);
+                        } else {
+                            // dz_0 feeds only CUDA-core reductions: fp32 panel stage[row][o] in D_s (its last readers, the dh_1 / dW_1 products, have
+                            // completed: this step waited for their commit), then  G0[j][o] = sum_n dz0 -> global memory (layer-0 weight-gradient
+                            // kernel / coordinate-gradient kernel),  dA[n][o] += sum_j dz0 in registers
+                            float* stage = reinterpret_cast<float*>(Ds);
+#pragma unroll
+                            for (int i = 0; i < NCH; ++i) {
+                                const int ch = rc.g + NG * i;
+                                if (ch < 7) {
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const int o = 8 * ch + 2 * q;
+                                        if (o < STGP - 1) stage[rc.row * STGP + o] = v[4 * i + q].x, stage[rc.row * STGP + o + 1] = v[4 * i + q].y;
+                                    }
+                                }
+                            }
+                            named_bar_sync(1, NE);
+                            const TileIdx& tp = tis[sl];
+                            if (t < TP * SHP && g0_j < tp.np) {
+                                float sum = 0.f;
+                                if (g0_o < HID) {
+                                    const float* zr = stage + g0_j * STGP + g0_o;
+                                    float s0 = 0.f, s1 = 0.f;
+                                    int n = 0;
+                                    for (; n + 1 < tp.nn; n += 2) s0 += zr[n * TP * STGP], s1 += zr[(n + 1) * TP * STGP];
+                                    if (n < tp.nn) s0 += zr[n * TP * STGP];
+                                    sum = s0 + s1;
+                                }
+                                a.G0[((size_t)tp.d * tl.P + tp.p0 + g0_j) * SHP + g0_o] = sum;
+                            }
+                            if (want_w) {
+#pragma unroll
+                                for (int q = 0; q < MAX_DA_PP; ++q) {
+                                    const int e = t + NE * q, n = e / HID, o = e % HID;
+                                    if (n < tp.nn) {
+                                        const float* zr = stage + n * TP * STGP + o;
+                                        float sum = 0.f;
+#pragma unroll
+                                        for (int jj = 0; jj < TP_CAP_TC; ++jj)
+                                            if (jj < tp.np) sum += zr[jj * STGP];
+                                        dA[q] += sum;
+                                    }
+                                }
+                            }
+                            // (the arrivals below order these panel reads before the next tile's dz_3 stores into D_s: its z_4 product, and with it
+                            //  the accumulator its first epilogue step waits for, is only issued once all 16 warps have arrived)
+                            __syncwarp();
+                            arrive(&s.bars[B_OP + sl]);
+                            arrive(&s.bars[B_HFREE + rp.r]);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- drain: wait for every MMA, then read the weight-gradient accumulators out of TMEM and write this CTA's partial
+        mbar_wait(&s.bars[B_DONE], 0);
+        fence_after_sync();
+        named_bar_sync(1, NE);
+        if (want_w) {
+            float* part = a.partials + (size_t)blockIdx.x * partial_size(nt, tl, SHP);
+            float* p_dW = part;
+            float* p_db = part + (size_t)(LH - 1) * HID * HID;
+            float* p_dWout = p_db + (size_t)(LH - 1) * SHP;
+            float* p_dA = p_dWout + (size_t)C * SHP + 4;
+            float* red = reinterpret_cast<float*>(s.ring);  // [128][57] fp32 / [57][129] (66 KB of the 96 KB ring: every load has been consumed)
+            constexpr int RS = 57;
+#pragma unroll 1
+            for (int l = 1; l < LH; ++l) {
+                // D[m][n]: m = dz feature (hi 0..63 | lo 64..127), n = h feature (hi 0..63 | lo 64..127); dW = D_hh + D_hl + D_lh
+                const uint32_t dw = tm + TM_DW_PP + (uint32_t)(l - 1) * 128 + rc.lane_taddr;
+                float x[8 * NCH], y2[8 * NCH];
+                if (myTiles > 0) {
+                    load_acc<NG>(dw, rc.g, x);
+                    load_acc<NG>(dw + 64, rc.g, y2);
+                } else {  // never written
+#pragma unroll
+                    for (int k = 0; k < 8 * NCH; ++k) x[k] = 0.f, y2[k] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int ch = rc.g + NG * i;
+                    if (ch < 7) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) red[rc.row * RS + 8 * ch + k] = rc.row < 64 ? x[8 * i + k] + y2[8 * i + k] : x[8 * i + k];
+                    }
+                }
+                named_bar_sync(1, NE);
+                for (int i = t; i < HID * (HID + 1); i += NE) {
+                    const int o = i / (HID + 1), k = i % (HID + 1);
+                    const float val = red[o * RS + k] + red[(64 + o) * RS + k];
+                    if (k < HID) p_dW[(size_t)(l - 1) * HID * HID + o * HID + k] = val;
+                    else p_db[(l - 1) * SHP + o] = val;  // column ONE_COL: sum_r dz_l[r][o] * 1
+                }
+                named_bar_sync(1, NE);
+            }
+            // output layer: column sums over the 128 rows of this thread's running products   (red as [57][129]; row 56 = sum of dy)
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int ch = rc.g + NG * i;
+                    if (ch < 7) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) red[(8 * ch + k) * 129 + rc.row] = wacc[c][8 * i + k];
+                    }
+                }
+                if (rc.g == 0) red[56 * 129 + rc.row] = bacc[c];
+                named_bar_sync(1, NE);
+                if (t < 53) {
+                    const float* src = red + (t == 52 ? 56 : t) * 129;
+                    float s0 = 0.f, s1 = 0.f;
+                    for (int r = 0; r < 128; r += 2) s0 += src[r], s1 += src[r + 1];
+                    if (t < HID) p_dWout[c * SHP + t] = s0 + s1;
+                    else if (t == 52) p_dWout[C * SHP + c] = s0 + s1;
+                }
+                named_bar_sync(1, NE);
+            }
+#pragma unroll
+            for (int q = 0; q < MAX_DA_PP; ++q) {
+                const int e = t + NE * q, n = e / HID, o = e % HID;
+                if (n < tl.NC) p_dA[n * SHP + o] = dA[q];
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == NE / 32) tmem_dealloc(tm, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static int check_tc(const Net& nt) {
@@ -1816,7 +2235,24 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     const bool loadh = keep_act && a.hsave != nullptr;
     const bool single_stream = mode != 2 || loadh;
     int n_partials = wl.gridMain;
-    if (!single_stream) {
+    // kept activations: two tiles in flight per CTA (LMR_BWD_PP=0: the one-tile kernel of round 1)
+    static const bool use_pp = !(getenv("LMR_BWD_PP") && atoi(getenv("LMR_BWD_PP")) == 0);
+    static const int pp_reverse = getenv("LMR_BWD_REVERSE") ? atoi(getenv("LMR_BWD_REVERSE")) : 1;
+    if (loadh && use_pp) {
+        pp::Smem sp(nullptr, nt.C);
+        const size_t smem = sp.bytes + 1024;
+        LMR_CHECK_ARG(smem <= 227 * 1024, "inr_backward (tensor-core path): needs %zu bytes of shared memory (> 227 KB)", smem);
+        static size_t cachep[2][5] = {};
+#define LMR_BWD_PP_CASE(FASTV, CV)                                                                       \
+    if (fast == FASTV && nt.C == CV) {                                                                   \
+        if (int rc = set_smem(inr_bwd_pp_kernel<FASTV, CV>, smem, &cachep[FASTV][CV])) return rc;       \
+        inr_bwd_pp_kernel<FASTV, CV><<<wl.gridMain, pp::NT, smem, st>>>(a, pp_reverse);                  \
+    }
+        LMR_BWD_PP_CASE(false, 1) LMR_BWD_PP_CASE(false, 2) LMR_BWD_PP_CASE(false, 3) LMR_BWD_PP_CASE(false, 4)
+        LMR_BWD_PP_CASE(true, 1) LMR_BWD_PP_CASE(true, 2) LMR_BWD_PP_CASE(true, 3) LMR_BWD_PP_CASE(true, 4)
+#undef LMR_BWD_PP_CASE
+        LMR_LAUNCH_OK();
+    } else if (!single_stream) {
         const Tiling tl2 = make_tiling(N, P, D, TP_CAP_TC, b2::R);
         a.tl = tl2;  // the kernels behind this one only read N, P, D and NC (== the 128-row tiling's for N <= 40)
         static const int stagger = getenv("LMR_B2_STAGGER") ? atoi(getenv("LMR_B2_STAGGER")) : 0;

@@ -199,7 +199,7 @@ def match_sharded(im, target_neuron_idxs, **match_kwargs):
     out = to_host_numpy(g_img), g_act.cpu().numpy()
     mark("copy to host")
     if timing:
-        print("[match_sharded] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.1f} ms" for a, b in zip(marks, marks[1:])), file=sys.stderr)
+        print("[match_sharded] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.1f} ms" for a, b in zip(marks, marks[1:])), file=sys.__stderr__)
     return out
 
 

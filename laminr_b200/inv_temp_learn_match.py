@@ -309,7 +309,7 @@ class InvarianceManifold:
         imgs, a = snapshot()
         mark("snapshot")
         if timing:
-            print("[match] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a_[1]):.1f} ms" for a_, b in zip(marks, marks[1:])), file=sys.stderr)
+            print("[match] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a_[1]):.1f} ms" for a_, b in zip(marks, marks[1:])), file=sys.__stderr__)
         if save_results_every_n_epochs is not None:
             images_list.append(imgs), acts_list.append(a)
             if torch.is_tensor(imgs):
