@@ -42,8 +42,8 @@ typedef enum {
 } lmr_precision;
 
 /* Flag, OR-ed into `precision` of lmr_inr_forward AND of the matching lmr_inr_backward_after_forward (tensor-core modes only): the forward
- * keeps the split-bf16 operand tiles of the hidden activations h_1..h_3 in its workspace (numTiles x 3 x 32 KB: 160 MB for one 20 x 100 x 100
- * image set) and the backward loads them with bulk async copies instead of recomputing the forward per tile.  The forward workspace must
+ * keeps the split-bf16 operand tiles of the hidden activations h_1..h_3 and the output values y in its workspace (numTiles x (3 x 32 KB + 2 KB):
+ * 163 MB for one 20 x 100 x 100 image set) and the backward loads them with bulk async copies instead of recomputing the forward per tile.  The forward workspace must
  * then have lmr_inr_forward_workspace_bytes_keep(...) bytes. */
 #define LMR_PREC_KEEP_ACTIVATIONS 0x100
 
@@ -119,6 +119,18 @@ int lmr_inr_backward_after_forward(const lmr_inr_desc* desc, const float* params
                                    float* g_params, float* g_angles, float* g_scalings, float* g_shears, float* g_translation,
                                    void* workspace, size_t workspace_bytes, const void* forward_workspace,
                                    size_t forward_workspace_bytes, int precision, void* stream);
+
+/* The learn step's lmr_inr_backward_after_forward (parameter gradients of ONE image set, no affine transform) and the lmr_adam_step over the INR
+ * parameters behind it -- `loss.backward(); optimizer.step()` of laminr/inv_temp_learn_match.py:206-207 with torch.optim.Adam over
+ * template.func.parameters() (:162) -- as one call.  On the tensor-core precisions everything behind the tile kernel (layer-0 weight-gradient
+ * partials, the cross-CTA reductions, the latent block of W0, Adam) is ONE cooperative launch instead of four; same summation orders and Adam
+ * arithmetic as the two separate calls, so gradients and parameters are bit-identical to them.  params is updated in place; g_params [count]
+ * still receives the gradient; adam_step: int32[2] = {steps taken, 0} as in lmr_adam_step.  LMR_PREC_FP32: runs the two calls. */
+int lmr_inr_backward_adam(const lmr_inr_desc* desc, float* params, const float* B, const float* auxB, const float* grid, int N,
+                          const float* coords, int P, const float* coord_shift, const float* g_img, float* g_params, float* adam_m,
+                          float* adam_v, int* adam_step, float lr, float beta1, float beta2, float eps, void* workspace,
+                          size_t workspace_bytes, const void* forward_workspace, size_t forward_workspace_bytes, int precision,
+                          void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Image-constraint projection -- replaces FixEnergyNormClip / StandardizeClip (laminr/utils/img_transforms.py:5-65)

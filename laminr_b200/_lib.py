@@ -48,6 +48,7 @@ SIGNATURES = {
     "lmr_inr_backward": (_i, [C.POINTER(InrDesc), _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, C.POINTER(Affine), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _vp]),
     "lmr_inr_backward_after_forward": (_i, [C.POINTER(InrDesc), _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, C.POINTER(Affine), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                             _vp, _sz, _i, _vp]),
+    "lmr_inr_backward_adam": (_i, [C.POINTER(InrDesc), _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _sz, _vp, _sz, _i, _vp]),
     "lmr_constrain_workspace_bytes": (_sz, [_i, _i]),
     "lmr_constrain_fwd": (_i, [_i, _vp, _i, _i, _f, _f, _i, _f, _i, _f, _f, _vp, _vp, _vp, _sz, _vp]),
     "lmr_constrain_bwd": (_i, [_i, _vp, _vp, _vp, _i, _i, _f, _f, _i, _f, _i, _f, _f, _vp, _vp, _sz, _vp]),

@@ -38,7 +38,7 @@ namespace tc {
 int forward(const lmr_inr_desc*, const float*, const float*, const float*, const float*, int, const float*, int, const float*, const lmr_affine*, int,
             float*, void*, size_t, int, cudaStream_t);
 int backward(const lmr_inr_desc*, const float*, const float*, const float*, const float*, int, const float*, int, const float*, const lmr_affine*, int,
-             const float*, float*, float*, float*, float*, float*, void*, size_t, int, cudaStream_t, const void*, size_t);
+             const float*, float*, float*, float*, float*, float*, void*, size_t, int, cudaStream_t, const void*, size_t, const AdamArgs*);
 size_t workspace_bytes(const lmr_inr_desc*, int, int, int, bool, bool keep_act = false);
 }  // namespace tc
 
@@ -99,7 +99,7 @@ extern "C" int lmr_inr_backward(const lmr_inr_desc* desc, const float* params, c
                               g_translation, ws, ws_bytes, st);
     if (precision == LMR_PREC_BF16X3_FAST || precision == LMR_PREC_BF16X3)
         return tc::backward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, g_img, g_params, g_angles, g_scalings, g_shears,
-                            g_translation, ws, ws_bytes, precision, st, nullptr, 0);
+                            g_translation, ws, ws_bytes, precision, st, nullptr, 0, nullptr);
     set_error("inr_backward: unknown precision %d", precision);
     return LMR_ERR_INVALID;
 }
@@ -113,7 +113,27 @@ extern "C" int lmr_inr_backward_after_forward(const lmr_inr_desc* desc, const fl
     const int mode = precision & ~LMR_PREC_KEEP_ACTIVATIONS;
     if (mode == LMR_PREC_BF16X3_FAST || mode == LMR_PREC_BF16X3)
         return tc::backward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, g_img, g_params, g_angles, g_scalings, g_shears,
-                            g_translation, ws, ws_bytes, precision, st, forward_workspace, forward_workspace_bytes);
+                            g_translation, ws, ws_bytes, precision, st, forward_workspace, forward_workspace_bytes, nullptr);
     return lmr_inr_backward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, g_img, g_params, g_angles, g_scalings, g_shears,
                             g_translation, ws, ws_bytes, mode, stream);  // the fp32 path recomputes its tables
+}
+
+extern "C" int lmr_inr_backward_adam(const lmr_inr_desc* desc, float* params, const float* B, const float* auxB, const float* grid, int N,
+                                     const float* coords, int P, const float* coord_shift, const float* g_img, float* g_params, float* adam_m,
+                                     float* adam_v, int* adam_step, float lr, float beta1, float beta2, float eps, void* ws, size_t ws_bytes,
+                                     const void* forward_workspace, size_t forward_workspace_bytes, int precision, void* stream) {
+    LMR_CHECK_ARG(params && g_params && adam_m && adam_v && adam_step, "inr_backward_adam: null pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int mode = precision & ~LMR_PREC_KEEP_ACTIVATIONS;
+    if ((mode == LMR_PREC_BF16X3_FAST || mode == LMR_PREC_BF16X3) && forward_workspace != nullptr) {
+        const AdamArgs ad{params, adam_m, adam_v, adam_step, lr, beta1, beta2, eps};
+        return tc::backward(desc, params, B, auxB, grid, N, coords, P, coord_shift, nullptr, 1, g_img, g_params, nullptr, nullptr, nullptr, nullptr, ws,
+                            ws_bytes, precision, st, forward_workspace, forward_workspace_bytes, &ad);
+    }
+    // fp32 path (or no forward workspace): the two calls it stands for
+    if (int rc = lmr_inr_backward_after_forward(desc, params, B, auxB, grid, N, coords, P, coord_shift, nullptr, 1, g_img, g_params, nullptr, nullptr,
+                                                nullptr, nullptr, ws, ws_bytes, forward_workspace, forward_workspace_bytes, precision, stream))
+        return rc;
+    const size_t n = lmr_inr_params_count(desc);
+    return lmr_adam_step(params, g_params, adam_m, adam_v, (int)n, lr, beta1, beta2, eps, adam_step, stream);
 }

@@ -32,6 +32,32 @@ int num_sms();
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// state of a torch.optim.Adam step fused into another launch (lmr_inr_backward_adam): parameters, both moments, the int32[2] step word of lmr_adam_step
+struct AdamArgs {
+    float *p, *m, *v;
+    int* step;
+    float lr, b1, b2, eps;
+};
+
+// One element of torch.optim.Adam's single-tensor update (exp_avg.lerp_(grad, 1 - beta1); exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value =
+// 1 - beta2); param.addcdiv_(exp_avg, sqrt(exp_avg_sq) / sqrt(bias_correction2) + eps, value = -lr / bias_correction1)).  Every rounding is spelled
+// out with intrinsics: the expression is compiled into several kernels (lmr_adam_step, the fused learn tail), and left to the compiler each copy
+// may contract its multiply-adds differently -- equal to the last bit only as long as the second moment is still zero.
+__device__ __forceinline__ void adam_element(float g, float m0, float v0, float p0, float b1, float b2, float eps, float step_size, float bc2_sqrt,
+                                             float* m_out, float* v_out, float* p_out) {
+    const float mi = __fmaf_rn(__fsub_rn(g, m0), __fsub_rn(1.f, b1), m0);
+    const float vi = __fmaf_rn(__fmul_rn(__fsub_rn(1.f, b2), g), g, __fmul_rn(v0, b2));
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vi), bc2_sqrt), eps);
+    *m_out = mi, *v_out = vi;
+    *p_out = __fmaf_rn(-step_size, __fdiv_rn(mi, denom), p0);
+}
+// bias corrections of step t (1-based): step_size = lr / (1 - beta1^t), sqrt(1 - beta2^t)
+__device__ __forceinline__ void adam_step_consts(int t, float lr, float b1, float b2, float* step_size, float* bc2_sqrt) {
+    const float bc1 = __fsub_rn(1.f, powf(b1, (float)t)), bc2 = __fsub_rn(1.f, powf(b2, (float)t));
+    *step_size = __fdiv_rn(lr, bc1);
+    *bc2_sqrt = __fsqrt_rn(bc2);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

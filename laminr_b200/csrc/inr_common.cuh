@@ -411,6 +411,18 @@ __device__ __forceinline__ float strided_sum8(const float* src, int count, size_
     return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 
+// the same for values written by OTHER blocks of the running launch (behind a grid barrier): the loads bypass L1
+__device__ __forceinline__ float strided_sum8_cg(const float* src, int count, size_t stride) {
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int b = 0;
+    for (; b + 8 <= count; b += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] += __ldcg(src + (size_t)(b + u) * stride);
+    }
+    for (int u = 0; b < count; ++b, ++u) s[u] += __ldcg(src + (size_t)b * stride);
+    return ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+}
+
 __device__ __forceinline__ float quad_sum(float v) {  // lanes 4k..4k+3 -> (v0 + v1) + (v2 + v3) on every lane of the quad
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
@@ -483,6 +495,218 @@ __global__ void __launch_bounds__(128) finish_w0a_kernel(Args a, float* g_params
         for (int n = 0; n < N; ++n) sum += a.dAred[(size_t)n * HP + o];
         g_params[nt.offb(0) + o] = sum;
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// learn: everything behind the tile kernel of the backward AND the Adam step in ONE cooperative launch (round 2; the four launches
+// l0_partial -> reduce_partials -> finish_w0a -> adam_ticket were 21 us of a 200 us step, each near the launch-latency floor):
+//   phase A  (a) this block's pixel chunks of the layer-0 coordinate block  dW0c = G0^T beta  -> l0part[block]      (= l0_partial_kernel)
+//            (b) this block's slice of the hidden / output layer gradients and of dA[n][o], summed over the tile kernel's per-CTA partials in
+//                the fixed order of reduce_partials_kernel; Adam applied to the hidden / output layers right away
+//   grid barrier (all blocks co-resident: cooperative launch)
+//   phase B  (c) a slice of the coordinate block summed over the l0 partials, (d) a slice of the latent block of W0 and of b0 from dAred and alpha
+//            (= finish_w0a_kernel); Adam on them
+// Same summation orders and the same Adam arithmetic as the separate launches: bit-identical gradients and parameters.
+// step: int32[2] = {steps taken, scratch (0 between launches)} as in lmr_adam_step; the scratch word is the arrival counter of the barrier and of
+// the exit count (the last block out publishes the incremented step count and re-arms the word).
+// ---------------------------------------------------------------------------------------------------------------
+// (m0, v0, p0 = the element's state, loaded by the caller BEFORE the reduction that produces gi: three more round trips off the serial path)
+__device__ __forceinline__ void adam_update(const AdamArgs& ad, size_t i, float gi, float m0, float v0, float p0, float step_size, float bc2_sqrt) {
+    adam_element(gi, m0, v0, p0, ad.b1, ad.b2, ad.eps, step_size, bc2_sqrt, &ad.m[i], &ad.v[i], &ad.p[i]);
+}
+
+template <int HID>
+__global__ void __launch_bounds__(L0_THREADS, 2) learn_tail_kernel(Args a, float* l0part, int nL0, int nPartMain, float* g_params, AdamArgs ad) {
+    constexpr int HP = (HID + 3) / 4 * 4;
+    extern __shared__ __align__(16) float sm[];
+    const Net& nt = a.net;
+    const Tiling& tl = a.tl;
+    const int pe = nt.pe, nb = 2 * pe, na = 2 * nt.ape, ppb = a.ppb, L = nt.nl;
+    const int t = threadIdx.x, G = (int)gridDim.x, blk = (int)blockIdx.x;
+    // Two roles in phase A, side by side on every SM (the grid is 2 blocks per l0 block, all co-resident): blocks [0, nL0) compute the layer-0
+    // partials, blocks [nL0, G) sum the tile kernel's partials -- both are latency-bound chains, so running them concurrently costs no more
+    // than the longer one.  Phase B is spread over all G blocks.
+    // Adam constants of this step (every block reads the counter before anybody can publish the new one: that happens after the last exit count)
+    const int tstep = *reinterpret_cast<volatile int*>(ad.step) + 1;
+    float step_size, bc2_sqrt;
+    adam_step_consts(tstep, ad.lr, ad.b1, ad.b2, &step_size, &bc2_sqrt);
+    const size_t psz = partial_size(nt, tl, HP);
+    const size_t nHid = nt.count() - nt.size0(), nA = nHid + (size_t)tl.N * HP;
+    const size_t offA = (size_t)(L - 1) * HID * HID + (size_t)(L - 1) * HP + (size_t)nt.C * HP + 4;
+    const int QB = blockDim.x / 4;  // element quads per block and pass
+
+    if (blk < nL0) {
+        // ---- phase A (a): layer-0 coordinate block partial of this block's pixel chunks
+        float* Gs = sm;             // [ppb][HP]
+        float* Bs = Gs + ppb * HP;  // [ppb][nb]
+        const int total = tl.D * tl.P;
+        const int nchunks = (total + ppb - 1) / ppb;
+        const int nOG = HP / 4, nKG = nb / 4;
+        const bool owner = t < nOG * nKG;
+        const int og = t % nOG, kg = t / nOG;
+        float4 acc[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) acc[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int ch = blk; ch < nchunks; ch += nL0) {
+            const int q0 = ch * ppb, nq = min(ppb, total - q0);
+            __syncthreads();
+            for (int i = t; i < nq * HP / 4; i += blockDim.x) reinterpret_cast<float4*>(Gs)[i] = reinterpret_cast<const float4*>(a.G0 + (size_t)q0 * HP)[i];
+            for (int i = t; i < nq * nb / 4; i += blockDim.x) reinterpret_cast<float4*>(Bs)[i] = reinterpret_cast<const float4*>(a.betaG + (size_t)q0 * nb)[i];
+            __syncthreads();
+            if (owner) {
+                const float4* gp = reinterpret_cast<const float4*>(Gs) + og;
+                const float4* bp = reinterpret_cast<const float4*>(Bs) + kg;
+#pragma unroll 4
+                for (int jj = 0; jj < nq; ++jj) {
+                    const float4 g = gp[jj * nOG], b = bp[jj * nKG];
+                    acc[0].x = fmaf(g.x, b.x, acc[0].x), acc[0].y = fmaf(g.x, b.y, acc[0].y), acc[0].z = fmaf(g.x, b.z, acc[0].z), acc[0].w = fmaf(g.x, b.w, acc[0].w);
+                    acc[1].x = fmaf(g.y, b.x, acc[1].x), acc[1].y = fmaf(g.y, b.y, acc[1].y), acc[1].z = fmaf(g.y, b.z, acc[1].z), acc[1].w = fmaf(g.y, b.w, acc[1].w);
+                    acc[2].x = fmaf(g.z, b.x, acc[2].x), acc[2].y = fmaf(g.z, b.y, acc[2].y), acc[2].z = fmaf(g.z, b.z, acc[2].z), acc[2].w = fmaf(g.z, b.w, acc[2].w);
+                    acc[3].x = fmaf(g.w, b.x, acc[3].x), acc[3].y = fmaf(g.w, b.y, acc[3].y), acc[3].z = fmaf(g.w, b.z, acc[3].z), acc[3].w = fmaf(g.w, b.w, acc[3].w);
+                }
+            }
+        }
+        if (owner) {
+            float* dst = l0part + (size_t)blk * HID * nb;
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+                if (4 * og + x < HID) reinterpret_cast<float4*>(dst + (size_t)(4 * og + x) * nb)[kg] = acc[x];
+        }
+    } else {
+        // ---- phase A (b): hidden / output layers and dA[n][o] over the tile kernel's partials (4 lanes per element, fixed-order quad combine).
+        //      Element list: the parameters from size0() on, then dAred.
+        const int nR = G - nL0, rb = blk - nL0;
+        const size_t per = (nA + nR - 1) / nR;
+        const size_t e0 = (size_t)rb * per, e1 = e0 + per < nA ? e0 + per : nA;
+        const int sub = t & 3;
+        const size_t passes = (per + QB - 1) / QB;
+        for (size_t ps = 0; ps < passes; ++ps) {
+            const size_t e = e0 + ps * QB + (t >> 2);
+            const bool live = e < e1;  // (whole warps run the shuffles together)
+            size_t off = 0;
+            if (live) {
+                if (e >= nHid) {
+                    off = offA + (e - nHid);
+                } else {
+                    const size_t i = nt.size0() + e;
+                    if (i < nt.offWout()) {
+                        const size_t r = i - nt.size0();
+                        const int l = r / nt.sizeh();
+                        const size_t w = r % nt.sizeh();
+                        off = w < (size_t)HID * HID ? (size_t)l * HID * HID + w : (size_t)(L - 1) * HID * HID + (size_t)l * HP + (w - (size_t)HID * HID);
+                    } else {
+                        const size_t r = i - nt.offWout();
+                        const size_t base = (size_t)(L - 1) * HID * HID + (size_t)(L - 1) * HP;
+                        off = r < (size_t)nt.C * HID ? base + (r / HID) * HP + (r % HID) : base + (size_t)nt.C * HP + (r - (size_t)nt.C * HID);
+                    }
+                }
+            }
+            const bool upd = live && sub == 0 && e < nHid;
+            const size_t pi = nt.size0() + e;
+            const float m0 = upd ? ad.m[pi] : 0.f, v0 = upd ? ad.v[pi] : 0.f, p0 = upd ? ad.p[pi] : 0.f;
+            const float part = live ? strided_sum8(a.partials + off + (size_t)sub * psz, (nPartMain - sub + 3) / 4, 4 * psz) : 0.f;
+            const float tot = quad_sum(part);
+            if (live && sub == 0) {
+                if (e >= nHid) {
+                    a.dAred[e - nHid] = tot;
+                } else {
+                    g_params[pi] = tot;
+                    adam_update(ad, pi, tot, m0, v0, p0, step_size, bc2_sqrt);
+                }
+            }
+        }
+    }
+    // ---- grid barrier
+    __syncthreads();
+    if (t == 0) {
+        __threadfence();
+        atomicAdd(ad.step + 1, 1);
+        while (*reinterpret_cast<volatile int*>(ad.step + 1) < G) __nanosleep(32);
+        __threadfence();
+    }
+    __syncthreads();
+    // ---- phase B, again two roles side by side: (c) on blocks [0, nL0), (d) on blocks [nL0, G)
+    if (blk < nL0) {
+        // (c) coordinate block of W0 over the nL0 layer-0 partials, 4 lanes per element
+        const size_t nC = (size_t)HID * nb;
+        const size_t per = (nC + nL0 - 1) / nL0;
+        const size_t e0 = (size_t)blk * per, e1 = e0 + per < nC ? e0 + per : nC;
+        const int sub = t & 3;
+        const size_t passes = (per + QB - 1) / QB;
+        for (size_t ps = 0; ps < passes; ++ps) {
+            const size_t e = e0 + ps * QB + (t >> 2);
+            const bool live = e < e1, upd = live && sub == 0;
+            const int o = (int)(e / nb), k = (int)(e % nb);
+            const size_t i = (size_t)o * nt.in_dim + 1 + na + k;
+            const float m0 = upd ? ad.m[i] : 0.f, v0 = upd ? ad.v[i] : 0.f, p0 = upd ? ad.p[i] : 0.f;
+            const float part = live ? strided_sum8_cg(l0part + e + (size_t)sub * nC, (nL0 - sub + 3) / 4, 4 * nC) : 0.f;
+            const float tot = quad_sum(part);
+            if (upd) {
+                g_params[i] = tot;
+                adam_update(ad, i, tot, m0, v0, p0, step_size, bc2_sqrt);
+            }
+        }
+    } else {
+        // (d) latent block of W0 (and the template column, whose input is the constant 0) and b0 from dAred and alpha; the N terms of an element
+        //     are fetched together (a dependent chain of N L2 round trips otherwise), summed in the order of finish_w0a_kernel
+        const int nR = G - nL0, rb = blk - nL0;
+        const int nW = HID * (1 + na), nD = nW + HID;
+        const int per = (nD + nR - 1) / nR;
+        constexpr int NB8 = 8;  // terms fetched together
+        for (int i = rb * per + t; i < min(nD, (rb + 1) * per); i += blockDim.x) {
+            const int o = i < nW ? i / (1 + na) : i - nW, col = i < nW ? i % (1 + na) : -1;
+            const size_t idx = i < nW ? (size_t)o * nt.in_dim + col : nt.offb(0) + o;
+            const float m0 = ad.m[idx], v0 = ad.v[idx], p0 = ad.p[idx];
+            float sum = 0.f;
+            if (col != 0) {
+                for (int n0 = 0; n0 < tl.N; n0 += NB8) {
+                    float dv[NB8], av[NB8];
+#pragma unroll
+                    for (int u = 0; u < NB8; ++u) {
+                        const int n = n0 + u;
+                        dv[u] = n < tl.N ? __ldcg(a.dAred + (size_t)n * HP + o) : 0.f;
+                        av[u] = (n < tl.N && col > 0) ? a.alpha[(size_t)n * na + col - 1] : 1.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < NB8; ++u)
+                        if (n0 + u < tl.N) sum = col > 0 ? fmaf(dv[u], av[u], sum) : sum + dv[u];
+                }
+            }
+            g_params[idx] = sum;
+            adam_update(ad, idx, sum, m0, v0, p0, step_size, bc2_sqrt);
+        }
+    }
+    // ---- exit count: the last block out publishes the step count and re-arms the scratch word
+    __syncthreads();
+    if (t == 0) {
+        __threadfence();
+        if (atomicAdd(ad.step + 1, 1) == 2 * G - 1) {
+            ad.step[1] = 0;
+            ad.step[0] = tstep;
+        }
+    }
+}
+
+template <int HID>
+static int launch_learn_tail(const Args& a, float* l0part, int grid_l0, int nPartMain, float* g_params, const AdamArgs& ad, cudaStream_t st) {
+    constexpr int HP = (HID + 3) / 4 * 4;
+    LMR_CHECK_ARG(a.betaG != nullptr, "learn tail: needs the kept sin/cos table of the forward workspace (D == 1)");
+    LMR_CHECK_ARG((HP / 4) * (2 * a.net.pe / 4) <= L0_THREADS, "learn tail: pe_dim %d not supported", a.net.pe);
+    LMR_CHECK_ARG(grid_l0 <= num_sms(), "learn tail: %d blocks cannot be co-resident", grid_l0);
+    const size_t smem = (size_t)a.ppb * (HP + 2 * a.net.pe) * sizeof(float);
+    static size_t cache = 0;
+    if (smem > 40 * 1024 && smem > cache) {
+        LMR_CUDA_OK(cudaFuncSetAttribute(learn_tail_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cache = smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * grid_l0), cfg.blockDim = dim3(L0_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = st;  // two roles per SM
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;  // all blocks co-resident: the software grid barrier needs it
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    LMR_CUDA_OK(cudaLaunchKernelEx(&cfg, learn_tail_kernel<HID>, a, l0part, grid_l0, nPartMain, g_params, ad));
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -1719,8 +1719,10 @@ constexpr int NCH = 8 / NG;                          // 16-byte chunks (8 featur
 constexpr int NRING = 3;
 constexpr uint32_t TM_ACC_S = 0;    // + 64 s: accumulator of slot s
 constexpr uint32_t TM_DW_PP = 128;  // + 128 (l - 1): weight-gradient accumulators
+// mbarriers; "slot" = one of the two tiles in flight.  As few as possible: every wait / arrive is ~100 cycles on the serial path of an epilogue step
+// (measured: per-k-chunk hand-over + a separate accumulator-consumed barrier + a separate weight-gradient commit cost 11 us of a 70 us kernel)
 constexpr int B_OP = 0;     // [0..1]  slot s: an epilogue step has finished (D_s written, accumulator and h tile consumed)      16 warp arrivals
-constexpr int B_ACC = 2;    // [2..3]  slot s: accumulator ready                                                                  tcgen05.commit
+constexpr int B_ACC = 2;    // [2..3]  slot s: accumulator ready, D_s and the h tile no longer read by the tensor pipe             tcgen05.commit
 constexpr int B_LAND = 4;   // [4..6]  ring buffer r: kept tile landed                                                            1 arrival + 32 KB
 constexpr int B_HFREE = 7;  // [7..9]  ring buffer r: its last reader (an epilogue step) has finished                             16 warp arrivals
 constexpr int B_DONE = 10;  // every MMA of the CTA has completed
@@ -1767,7 +1769,7 @@ __device__ __forceinline__ RingPos ring_pos(int j, int ns, int l, int s) {
 }  // namespace pp
 
 template <bool FAST, int C>
-__global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int reverse) {
+__global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int reverse) {  // (18 warps are allocated as 20: at most 96 registers per thread)
     using namespace pp;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const Net& nt = a.net;
@@ -1794,6 +1796,7 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
     const int myTiles = (tl.numTiles - b + G - 1) / G;
     const int nPairs = (myTiles + 1) >> 1;
     auto tile_of = [&](int k) { return reverse ? tl.numTiles - 1 - (b + k * G) : b + k * G; };  // k-th tile of this CTA
+    if (t == 0) LMR_TRACE(0, 500);
 
     if (warp == NE / 32 + 1) {
         if (lane == 0) {  // ---- loader: h_3, h_2, h_1 of both slots of every pair, each as soon as its ring buffer has been released
@@ -1829,7 +1832,10 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                     for (int kc = 0; kc < 4; ++kc) issue_kstep(tm + TM_ACC_S + 64u * sl, sd, kc);
                     mma_commit(&s.bars[B_ACC + sl]);
                 }
-                // step p = 1..3: dh_l = dz_l W_l (l = 4 - p), then dW_l += dz_l^T h_l; ONE commit behind both (see the header comment)
+                // step p = 1..3: dh_l = dz_l W_l (l = 4 - p), then dW_l += dz_l^T h_l; ONE commit behind both: the weight-gradient MMAs (~600
+                // cycles) sit on this slot's critical path but finish long before the epilogue warps come back from the other slot's step
+                // (measured: the accumulator is ready ~1 k cycles before it is asked for), and one barrier then covers the accumulator, the
+                // in-place overwrite of D_s and the release of the h tile
 #pragma unroll 1
                 for (int p = 1; p < LH; ++p) {
                     const int l = LH - p;
@@ -1850,6 +1856,7 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                             issue_wgrad(tm + TM_DW_PP + (uint32_t)(l - 1) * 128, dz, ring_addr + (uint32_t)rp.r * TILE_BYTES, j == 0 && sl == 0);
                         }
                         mma_commit(&s.bars[B_ACC + sl]);
+                        LMR_TRACE(1, (j * 4 + p) * 2 + sl);
                     }
                 }
             }
@@ -1859,7 +1866,6 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
         const RowCtx rc = row_ctx();
         const int TP = tl.TP;
         const int nl = rc.row / TP, jpx = rc.row % TP;
-        const int g0_j = t / SHP, g0_o = t % SHP;
         float dA[MAX_DA_PP];
 #pragma unroll
         for (int q = 0; q < MAX_DA_PP; ++q) dA[q] = 0.f;
@@ -1870,39 +1876,43 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
 #pragma unroll
             for (int k = 0; k < 8 * NCH; ++k) wacc[c][k] = 0.f;
         }
-        auto arrive = [&](uint64_t* bar) {  // this warp has finished an epilogue step (call behind a __syncwarp)
+        auto arrive = [&](uint64_t* bar) {  // (call behind a __syncwarp)
             if (lane == 0) mbar_arrive(bar);
         };
-
-        for (int j = 0; j < nPairs; ++j) {
-            const int ns = (2 * j + 1 < myTiles) ? 2 : 1;
-            TileIdx tis[2];
-            bool act[2];
-            float dy[2][C];
-            // upstream gradient and output value of this thread's row in both tiles: dy = g (1 - y^2)   (issued first: two global round trips
-            // that would otherwise sit in front of the first epilogue step)
+        // upstream gradient and output value of this thread's row in the two tiles of pair j: dy = g (1 - y^2).  Two global round trips (y comes
+        // from HBM): fetched one pair ahead, during the previous pair's last step
+        TileIdx tis[2];
+        float dy[2][C], g_next[2][C], y_next[2][C];
+        auto fetch_gy = [&](int j) {  // loads only: nothing here depends on the loaded values, so the round trips overlap the following work
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
-                act[sl] = false;
 #pragma unroll
-                for (int c = 0; c < C; ++c) dy[sl][c] = 0.f;
-                if (sl < ns) {
+                for (int c = 0; c < C; ++c) g_next[sl][c] = 0.f, y_next[sl][c] = 0.f;
+                if (2 * j + sl < myTiles) {
                     const int tile = tile_of(2 * j + sl);
-                    tis[sl] = decode_tile(tl, tile);
-                    act[sl] = nl < tis[sl].nn && jpx < tis[sl].np;
-                    if (act[sl]) {
-                        const size_t base = (((size_t)tis[sl].d * tl.N + (tis[sl].n0 + nl)) * C) * tl.P + tis[sl].p0 + jpx;
+                    const TileIdx ti = decode_tile(tl, tile);
+                    if (nl < ti.nn && jpx < ti.np) {
+                        const size_t base = (((size_t)ti.d * tl.N + (ti.n0 + nl)) * C) * tl.P + ti.p0 + jpx;
                         const float* yrec = reinterpret_cast<const float*>(a.hsave + (size_t)tile * keep_record_bytes(LH) + (size_t)(LH - 1) * TILE_BYTES);
 #pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const float gg = __ldg(a.g_img + base + (size_t)c * tl.P), yy = __ldcs(yrec + c * 128 + rc.row);
-                            dy[sl][c] = gg * (1.f - yy * yy);
-                        }
+                        for (int c = 0; c < C; ++c) g_next[sl][c] = __ldg(a.g_img + base + (size_t)c * tl.P), y_next[sl][c] = __ldcs(yrec + c * 128 + rc.row);
                     }
                 }
             }
+        };
+        fetch_gy(0);
+
+        for (int j = 0; j < nPairs; ++j) {
+            const int ns = (2 * j + 1 < myTiles) ? 2 : 1;
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                tis[sl] = sl < ns ? decode_tile(tl, tile_of(2 * j + sl)) : TileIdx{0, 0, 0, 0, 0};
+#pragma unroll
+                for (int c = 0; c < C; ++c) dy[sl][c] = g_next[sl][c] * (1.f - y_next[sl][c] * y_next[sl][c]);
+            }
 #pragma unroll 1
             for (int p = 0; p < LH; ++p) {
+                if (p == LH - 1 && j + 1 < nPairs) fetch_gy(j + 1);  // in flight across the two longest steps of the pair
 #pragma unroll
                 for (int sl = 0; sl < 2; ++sl) {
                     if (sl >= ns) continue;
@@ -1910,10 +1920,12 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                     const uint32_t acc = tm + TM_ACC_S + 64u * sl + rc.lane_taddr;
                     float2 v[4 * NCH];
                     float* vf = reinterpret_cast<float*>(v);
+                    if (t == 0) LMR_TRACE(0, ((j * 4 + p) * 2 + sl) * 3);
                     if (p == 0) {
                         // ---- h_4 = tanh(z_4) in registers; dz_3 = (Wout^T dy)(1 - h_4^2) -> D_s; running sums for dWout / dbout
                         mbar_wait(&s.bars[B_ACC + sl], 0);
                         fence_after_sync();
+                        if (t == 0) LMR_TRACE(0, ((j * 4 + p) * 2 + sl) * 3 + 1);
                         load_acc<NG>(acc, rc.g, vf);
                         if (want_w) {
 #pragma unroll
@@ -1954,14 +1966,21 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                         const int l = LH - p;
                         const RingPos rp = ring_pos(j, ns, l, sl);
                         const uint8_t* Hl = s.ring + (size_t)rp.r * TILE_BYTES;
+                        // the accumulator first (ready ~1 k cycles early: the other slot's step was in between), its TMEM load in flight while the
+                        // h tile is read and unpacked
+                        mbar_wait(&s.bars[B_ACC + sl], (uint32_t)p & 1);
+                        fence_after_sync();
+                        if (t == 0) LMR_TRACE(0, ((j * 4 + p) * 2 + sl) * 3 + 1);
+#pragma unroll
+                        for (int i = 0; i < NCH; ++i)
+                            if (rc.g + NG * i < 7) tmem_ld8(acc + 8 * (rc.g + NG * i), vf + 8 * i);
                         mbar_wait(&s.bars[B_LAND + rp.r], (uint32_t)rp.n & 1);
                         float2 hv[4 * NCH];
 #pragma unroll
                         for (int i = 0; i < NCH; ++i)
                             if (rc.g + NG * i < 7) load_chunk2<4>(Hl, rc.row, rc.g + NG * i, hv + 4 * i);
-                        mbar_wait(&s.bars[B_ACC + sl], (uint32_t)p & 1);
-                        fence_after_sync();
-                        load_acc<NG>(acc, rc.g, vf);
+                        tmem_ld_wait();
+                        fence_before_sync();  // orders these loads before the MMAs that overwrite the accumulator after the arrival below
 #pragma unroll
                         for (int i = 0; i < NCH; ++i)
                             if (rc.g + NG * i < 7) {
@@ -1971,7 +1990,7 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                         if (p < LH - 1) {
 #pragma unroll
                             for (int i = 0; i < NCH; ++i)
-                                if (rc.g + NG * i < 7) store_chunk2<4>(Ds, rc.row, rc.g + NG * i, v + 4 * i);
+                                if (rc.g + NG * i < 7) store_chunk2<4>(Ds, rc.row, rc.g + NG * i, v + 4 * i);  // (chunk 7 keeps the zeros of the tile's first step)
                             fence_proxy_async();
                             __syncwarp();
                             arrive(&s.bars[B_OP + sl]);
@@ -1979,7 +1998,7 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                         } else {
                             // dz_0 feeds only CUDA-core reductions: fp32 panel stage[row][o] in D_s (its last readers, the dh_1 / dW_1 products, have
                             // completed: this step waited for their commit), then  G0[j][o] = sum_n dz0 -> global memory (layer-0 weight-gradient
-                            // kernel / coordinate-gradient kernel),  dA[n][o] += sum_j dz0 in registers
+                            // kernel / coordinate-gradient kernel)  and  dA[n][o] += sum_j dz0 in registers
                             float* stage = reinterpret_cast<float*>(Ds);
 #pragma unroll
                             for (int i = 0; i < NCH; ++i) {
@@ -1992,24 +2011,30 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                                     }
                                 }
                             }
+                            __syncwarp();
+                            arrive(&s.bars[B_OP + sl]);       // accumulator read: the next tile's z_4 may be issued
+                            arrive(&s.bars[B_HFREE + rp.r]);
                             named_bar_sync(1, NE);
                             const TileIdx& tp = tis[sl];
-                            if (t < TP * SHP && g0_j < tp.np) {
-                                float sum = 0.f;
-                                if (g0_o < HID) {
-                                    const float* zr = stage + g0_j * STGP + g0_o;
-                                    float s0 = 0.f, s1 = 0.f;
-                                    int n = 0;
-                                    for (; n + 1 < tp.nn; n += 2) s0 += zr[n * TP * STGP], s1 += zr[(n + 1) * TP * STGP];
-                                    if (n < tp.nn) s0 += zr[n * TP * STGP];
-                                    sum = s0 + s1;
+                            if (t < TP * SHP) {
+                                const int g0_j = t / SHP, g0_o = t - g0_j * SHP;
+                                if (g0_j < tp.np) {
+                                    float sum = 0.f;
+                                    if (g0_o < HID) {
+                                        const float* zr = stage + g0_j * STGP + g0_o;
+                                        float s0 = 0.f, s1 = 0.f;
+                                        int n = 0;
+                                        for (; n + 1 < tp.nn; n += 2) s0 += zr[n * TP * STGP], s1 += zr[(n + 1) * TP * STGP];
+                                        if (n < tp.nn) s0 += zr[n * TP * STGP];
+                                        sum = s0 + s1;
+                                    }
+                                    a.G0[((size_t)tp.d * tl.P + tp.p0 + g0_j) * SHP + g0_o] = sum;
                                 }
-                                a.G0[((size_t)tp.d * tl.P + tp.p0 + g0_j) * SHP + g0_o] = sum;
                             }
                             if (want_w) {
 #pragma unroll
                                 for (int q = 0; q < MAX_DA_PP; ++q) {
-                                    const int e = t + NE * q, n = e / HID, o = e % HID;
+                                    const int e = t + NE * q, n = e / HID, o = e - n * HID;
                                     if (n < tp.nn) {
                                         const float* zr = stage + n * TP * STGP + o;
                                         float sum = 0.f;
@@ -2020,17 +2045,17 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                                     }
                                 }
                             }
-                            // (the arrivals below order these panel reads before the next tile's dz_3 stores into D_s: its z_4 product, and with it
-                            //  the accumulator its first epilogue step waits for, is only issued once all 16 warps have arrived)
-                            __syncwarp();
-                            arrive(&s.bars[B_OP + sl]);
-                            arrive(&s.bars[B_HFREE + rp.r]);
+                            // every panel read must be done before a fast warp stores the next tile's dz_3 into D_s: for slot 0 the other slot's
+                            // step (its named barrier above) lies in between; for the last slot of the pair nothing does
+                            if (sl == ns - 1) named_bar_sync(1, NE);
                         }
                     }
+                    if (t == 0) LMR_TRACE(0, ((j * 4 + p) * 2 + sl) * 3 + 2);
                 }
             }
         }
         // ---- drain: wait for every MMA, then read the weight-gradient accumulators out of TMEM and write this CTA's partial
+        if (t == 0) LMR_TRACE(0, 501);
         mbar_wait(&s.bars[B_DONE], 0);
         fence_after_sync();
         named_bar_sync(1, NE);
@@ -2047,13 +2072,8 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                 // D[m][n]: m = dz feature (hi 0..63 | lo 64..127), n = h feature (hi 0..63 | lo 64..127); dW = D_hh + D_hl + D_lh
                 const uint32_t dw = tm + TM_DW_PP + (uint32_t)(l - 1) * 128 + rc.lane_taddr;
                 float x[8 * NCH], y2[8 * NCH];
-                if (myTiles > 0) {
-                    load_acc<NG>(dw, rc.g, x);
-                    load_acc<NG>(dw + 64, rc.g, y2);
-                } else {  // never written
-#pragma unroll
-                    for (int k = 0; k < 8 * NCH; ++k) x[k] = 0.f, y2[k] = 0.f;
-                }
+                load_acc<NG>(dw, rc.g, x);
+                load_acc<NG>(dw + 64, rc.g, y2);
 #pragma unroll
                 for (int i = 0; i < NCH; ++i) {
                     const int ch = rc.g + NG * i;
@@ -2095,11 +2115,12 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
             }
 #pragma unroll
             for (int q = 0; q < MAX_DA_PP; ++q) {
-                const int e = t + NE * q, n = e / HID, o = e % HID;
+                const int e = t + NE * q, n = e / HID, o = e - n * HID;
                 if (n < tl.NC) p_dA[n * SHP + o] = dA[q];
             }
         }
     }
+    if (t == 0) LMR_TRACE(0, 502);
     fence_before_sync();
     __syncthreads();
     if (warp == NE / 32) tmem_dealloc(tm, 512);
@@ -2182,11 +2203,13 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
 int backward(const lmr_inr_desc* desc, const float* params, const float* B, const float* auxB, const float* grid, int N, const float* coords,
              int P, const float* coord_shift, const lmr_affine* affine, int D, const float* g_img, float* g_params, float* g_angles,
              float* g_scalings, float* g_shears, float* g_translation, void* ws, size_t ws_bytes, int precision, cudaStream_t st,
-             const void* fwd_ws, size_t fwd_ws_bytes) {
+             const void* fwd_ws, size_t fwd_ws_bytes, const AdamArgs* adam) {
     Net nt;
     if (int rc = make_net(desc, &nt)) return rc;
     if (int rc = check_tc(nt)) return rc;
     LMR_CHECK_ARG(N >= 1 && P >= 1 && D >= 1, "inr_backward: bad sizes N=%d P=%d D=%d", N, P, D);
+    LMR_CHECK_ARG(adam == nullptr || (g_params != nullptr && g_angles == nullptr && D == 1 && fwd_ws != nullptr),
+                  "inr_backward_adam: the fused Adam step serves the learn backward (parameter gradients, one target, after a forward)");
     LMR_CHECK_ARG(N <= 40, "inr_backward (tensor-core path): N=%d latents per step not supported (max 40); use the fp32 path", N);
     const bool want_aff = g_angles != nullptr;
     LMR_CHECK_ARG(g_params != nullptr || want_aff, "inr_backward: nothing to compute");
@@ -2252,6 +2275,21 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
         LMR_BWD_PP_CASE(true, 1) LMR_BWD_PP_CASE(true, 2) LMR_BWD_PP_CASE(true, 3) LMR_BWD_PP_CASE(true, 4)
 #undef LMR_BWD_PP_CASE
         LMR_LAUNCH_OK();
+        if (tracing) {  // debug only: synchronises and prints CTA 0's time line -- per (pair, step, slot): epilogue thread 0 enters / has the accumulator / is
+            static long long h[1024];  // done; MMA thread: the step's MMAs issued and committed
+            cudaStreamSynchronize(st);
+            cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+            const long long t0 = h[500];
+            fprintf(stderr, "[trace pp] CTA 0: tiles done %lld  drain done %lld (cycles after the prologue)\n", h[501] - t0, h[502] - t0);
+            for (int j = 0; j < 3; ++j)
+                for (int p = 0; p < 4; ++p)
+                    for (int sl = 0; sl < 2; ++sl) {
+                        const int e = ((j * 4 + p) * 2 + sl) * 3, m = 512 + (j * 4 + p) * 2 + sl;
+                        fprintf(stderr, "[trace pp] pair %d step %d slot %d  E: enter %6lld acc %6lld done %6lld | M: MMAs issued %6lld\n", j, p, sl, h[e] - t0, h[e + 1] - t0,
+                                h[e + 2] - t0, h[m] ? h[m] - t0 : -1);
+                    }
+            return 0;  // (skips the small follow-up launches: timing runs only)
+        }
     } else if (!single_stream) {
         const Tiling tl2 = make_tiling(N, P, D, TP_CAP_TC, b2::R);
         a.tl = tl2;  // the kernels behind this one only read N, P, D and NC (== the 128-row tiling's for N <= 40)
@@ -2325,8 +2363,15 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     }
     if (a.want_weights) {
         float* l0part = reinterpret_cast<float*>(static_cast<char*>(ws) + wl.l0part);
-        if (int rc = launch_l0_partial<50>(a, l0part, wl.gridL0, st)) return rc;
-        if (int rc = launch_finish_weights<50>(a, l0part, n_partials, wl.gridL0, g_params, st)) return rc;
+        static const bool fused_tail = !(getenv("LMR_FUSED_TAIL") && atoi(getenv("LMR_FUSED_TAIL")) == 0);
+        if (adam != nullptr && fused_tail && a.betaG != nullptr && wl.gridL0 <= num_sms()) {
+            // one cooperative launch: layer-0 weight-gradient partials, every cross-CTA reduction and the Adam step
+            if (int rc = launch_learn_tail<50>(a, l0part, wl.gridL0, n_partials, g_params, *adam, st)) return rc;
+        } else {
+            if (int rc = launch_l0_partial<50>(a, l0part, wl.gridL0, st)) return rc;
+            if (int rc = launch_finish_weights<50>(a, l0part, n_partials, wl.gridL0, g_params, st)) return rc;
+            if (adam != nullptr) return lmr_adam_step(adam->p, g_params, adam->m, adam->v, (int)nt.count(), adam->lr, adam->b1, adam->b2, adam->eps, adam->step, st);
+        }
     }
     if (want_aff) {  // the tile kernel wrote G0[d,p][o] = sum_n dz0: coordinate gradient and its moments pixel-parallel, then the 7 scalars per target
         int nblk = 0;

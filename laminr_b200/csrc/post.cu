@@ -433,18 +433,9 @@ __global__ void __launch_bounds__(128) simclr_bwd_kernel(const float* __restrict
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int n, float lr,
                             float b1, float b2, float eps, const int* __restrict__ step) {
     const int t = step[0] + 1;
-    const float bc1 = 1.f - powf(b1, (float)t);
-    const float bc2 = 1.f - powf(b2, (float)t);
-    const float step_size = lr / bc1;
-    const float bc2_sqrt = sqrtf(bc2);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float gi = g[i];
-        const float mi = m[i] + (gi - m[i]) * (1.f - b1);  // lerp_
-        const float vi = v[i] * b2 + (1.f - b2) * gi * gi;  // mul_ + addcmul_
-        m[i] = mi, v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = p[i] - step_size * (mi / denom);  // addcdiv_
-    }
+    float step_size, bc2_sqrt;
+    adam_step_consts(t, lr, b1, b2, &step_size, &bc2_sqrt);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) adam_element(g[i], m[i], v[i], p[i], b1, b2, eps, step_size, bc2_sqrt, &m[i], &v[i], &p[i]);
 }
 __global__ void counter_inc_kernel(int* c) { c[0] += 1; }
 
@@ -453,19 +444,10 @@ __global__ void counter_inc_kernel(int* c) { c[0] += 1; }
 __global__ void __launch_bounds__(256) adam_ticket_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                           int n, float lr, float b1, float b2, float eps, int* __restrict__ step) {
     const int t = *reinterpret_cast<volatile int*>(step) + 1;
-    const float bc1 = 1.f - powf(b1, (float)t);
-    const float bc2 = 1.f - powf(b2, (float)t);
-    const float step_size = lr / bc1;
-    const float bc2_sqrt = sqrtf(bc2);
+    float step_size, bc2_sqrt;
+    adam_step_consts(t, lr, b1, b2, &step_size, &bc2_sqrt);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        const float gi = g[i];
-        const float mi = m[i] + (gi - m[i]) * (1.f - b1);  // lerp_
-        const float vi = v[i] * b2 + (1.f - b2) * gi * gi;  // mul_ + addcmul_
-        m[i] = mi, v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = p[i] - step_size * (mi / denom);  // addcdiv_
-    }
+    if (i < n) adam_element(g[i], m[i], v[i], p[i], b1, b2, eps, step_size, bc2_sqrt, &m[i], &v[i], &p[i]);
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();

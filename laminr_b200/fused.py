@@ -180,7 +180,8 @@ class LearnStepper:
             self.bank = model.packed_filters[int(neuron_idx), :int(model.nfilt[int(neuron_idx)].item())].contiguous()
             self.ws_obj = ops.learn_objective_workspace(N, Cc, P, self.bank.shape[0], dev)
         # inr fwd (2) + [objective (1) | constrain fwd (2) + simclr fwd (2) + simclr bwd (1) + response + constrain bwd (2)] + inr bwd (4) + adam (1)
-        self.kernels_per_step = 8 if self.ws_obj is not None else 14 + self.resp.launches_fwd_bwd
+        # prep + forward + objective + backward tile kernel + fused tail (fp32 path: the four separate tail launches)
+        self.kernels_per_step = (5 if ops.precision_code(precision) != _lib.PREC_FP32 else 8) if self.ws_obj is not None else 14 + self.resp.launches_fwd_bwd
 
     def set_reg_scale(self, reg_scale):
         self.g_reg.fill_(-float(reg_scale))
@@ -203,9 +204,10 @@ class LearnStepper:
                                     r.flat_neighbor_mask_pos, r.flat_neighbor_mask_neg, r.temperature, r.eps, self.g_reg, self.z, self.act.view(-1),
                                     self.reg, self.loss_buf, self.g_x, self.ws_obj, stats=self.stats, rmax=self.resp.rmax.view(-1),
                                     argmax=self.resp.argmax.view(-1), K=self.K)
-            ops.raw_inr_backward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, self.g_x.view(1, N, Cc, P), want_params=True,
-                                 precision=self.precision, workspace=self.ws_bwd, g_params=self.g_flat, forward_workspace=self.ws_fwd, keep_activations=self.keep)
-            ops.raw_adam_step(self.flat, self.g_flat, self.m, self.v, self.step_count, lr=self.lr)
+            # backward + Adam as one C-ABI call: one cooperative launch behind the tile kernel instead of four small ones
+            ops.raw_inr_backward_adam(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, self.g_x.view(1, N, Cc, P), self.g_flat, self.m, self.v,
+                                      self.step_count, lr=self.lr, precision=self.precision, workspace=self.ws_bwd, forward_workspace=self.ws_fwd,
+                                      keep_activations=self.keep)
             return
         ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, out=self.img_pre.view(1, N, Cc, P),
                             precision=self.precision, workspace=self.ws_fwd, keep_activations=self.keep)

@@ -202,6 +202,27 @@ def raw_inr_backward(desc, params, B, auxB, grid, coords, coord_shift, affine, g
     return (g_params if want_params else None), (g_affine if want_affine else None)
 
 
+def raw_inr_backward_adam(desc, params, B, auxB, grid, coords, coord_shift, g_img, g_params, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8,
+                          precision=None, workspace=None, forward_workspace=None, keep_activations=False):
+    """The learn step's raw_inr_backward(..., forward_workspace=...) + raw_adam_step(params, g_params, m, v, step) as ONE C-ABI call
+    (lmr_inr_backward_adam): on the tensor-core precisions the reductions behind the tile kernel and the Adam update share one launch.
+    `params` is updated in place, `g_params` receives the gradient."""
+    lib = _lib.load()
+    _require_cuda(params, g_img, g_params, m, v, step)
+    if step.numel() < 2 or step.dtype != torch.int32:
+        raise ValueError("raw_inr_backward_adam: `step` must be an int32 tensor with 2 elements ([steps taken, zero-initialised scratch])")
+    N, P = grid.numel(), coords.shape[0]
+    if workspace is None:
+        workspace = _workspace(lib.lmr_inr_backward_workspace_bytes(C.byref(desc), N, P, 1), params.device)
+    prec = precision_code(precision)
+    keep = bool(keep_activations) and prec != _lib.PREC_FP32
+    check(lib.lmr_inr_backward_adam(C.byref(desc), _ptr(params), _ptr(B), _ptr(auxB), _ptr(grid), N, _ptr(coords), P, _ptr(coord_shift), _ptr(_f32c(g_img)),
+                                    _ptr(g_params), _ptr(m), _ptr(v), _ptr(step), float(lr), float(b1), float(b2), float(eps), _ptr(workspace),
+                                    workspace.numel(), _ptr(forward_workspace), 0 if forward_workspace is None else forward_workspace.numel(),
+                                    prec | (_lib.PREC_KEEP_ACTIVATIONS if keep else 0), _stream()))
+    return g_params
+
+
 class _InrImages(torch.autograd.Function):
     """img[D,N,C,P] = INR(...).  Differentiable wrt the MLP parameters (learn) and the affine scalars (match)."""
 

@@ -194,9 +194,10 @@ def test_match_block_selection(L, monkeypatch):
     N, P = 20, 100 * 100
     for k in ("LMR_KEEP_ACT", "LMR_KEEP_ACT_MAX_GIB", "LMR_MATCH_BLOCK"):
         monkeypatch.delenv(k, raising=False)
-    # the kept operand tiles: 3 layers x 32 KB per 128-row tile, 6 pixels x 20 latents per tile (include/laminr_b200.h, LMR_PREC_KEEP_ACTIVATIONS)
+    # the kept record of a 128-row tile (6 pixels x 20 latents): 3 layers x 32 KB of operand tiles + 2 KB of output values y
+    # (include/laminr_b200.h, LMR_PREC_KEEP_ACTIVATIONS)
     per_target = ops.forward_workspace_bytes(d, N, P, 1, True) - ops.forward_workspace_bytes(d, N, P, 1, False)
-    assert per_target == -(-P // 6) * 3 * 32768
+    assert per_target == -(-P // 6) * (3 * 32768 + 2048)
     assert match_block("bf16x3", d, N, P, 32) == (32, True)          # 4.9 GiB of tiles: one pass
     blk, keep = match_block("bf16x3", d, N, P, 1024)                  # BASELINE config 3 on one GPU: 157 GiB of tiles > 32 GiB budget
     assert keep and 190 <= blk <= 210
