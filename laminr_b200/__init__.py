@@ -13,5 +13,6 @@ from . import neuron_models  # noqa: E402,F401
 from .inv_temp_learn_match import InvarianceManifold  # noqa: E402,F401
 from .utils import get_mei_dict  # noqa: E402,F401
 from .ops import set_default_precision  # noqa: E402,F401
+from . import torch_ops  # noqa: E402,F401  (registers torch.ops.laminr_b200.*)
 
 __version__ = "0.1.0"

@@ -65,10 +65,17 @@ def broadcast_rng_state(src=0, device=None):
 
 
 def make_stop_reduce(device=None):
-    """-> f(sum, min, max) all-reducing the three floats over the ranks (SUM, MIN, MAX): the global stop rule of `match` (:368-375)."""
+    """-> f(sum, min, max) all-reducing the three floats over the ranks (SUM, MIN, MAX): the global stop rule of `match` (:368-375).
+    f.begin(t3) / f.end(handle) split the call for a device-resident 3-element tensor: `begin` queues the collective and the copy to pinned host
+    memory behind the work queued so far and returns at once; `end` waits for that copy and combines -- the match loop calls `end` one epoch
+    later, so neither the collective nor the copy ever stalls the GPU."""
     world, _ = _world()
     if world == 1:
         return None
+
+    def combine(allr):
+        allr = allr.double()
+        return float(allr[:, 0].sum()), float(allr[:, 1].min()), float(allr[:, 2].max())
 
     def reduce(a_sum, a_min=None, a_max=None):
         # ONE collective per epoch: every rank gets every rank's (sum, min, max) and combines them in rank order (deterministic).
@@ -80,9 +87,28 @@ def make_stop_reduce(device=None):
             t = torch.tensor([a_sum, a_min, a_max], dtype=torch.float64, device=device)
         parts = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(parts, t)
-        allr = torch.stack(parts).cpu().double()
-        return float(allr[:, 0].sum()), float(allr[:, 1].min()), float(allr[:, 2].max())
+        return combine(torch.stack(parts).cpu())
 
+    def begin(t3):
+        t = t3.detach().reshape(3)
+        if dist.get_backend() != "nccl":  # gloo (CPU tests of the plumbing; GPU tests on a one-GPU box): host tensors, blocking
+            parts = [torch.empty(3, dtype=t.dtype) for _ in range(world)]
+            dist.all_gather(parts, t.cpu())
+            return torch.stack(parts), None
+        full = torch.empty((world, 3), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(full, t.contiguous())
+        host = torch.empty((world, 3), dtype=t.dtype).pin_memory()
+        host.copy_(full, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return host, ev, full  # (`full` is kept alive until the copy has run)
+
+    def end(handle):
+        if handle[1] is not None:
+            handle[1].synchronize()
+        return combine(handle[0])
+
+    reduce.begin, reduce.end = begin, end
     return reduce
 
 

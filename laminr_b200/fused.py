@@ -302,11 +302,17 @@ class MatchStepper:
         self.ws_fwd = _ws(max(ops.forward_workspace_bytes(d, N, P, D, False), ops.forward_workspace_bytes(d, N, P, Bk, self.keep)), dev)
         self.ws_bwd = _ws(lib.lmr_inr_backward_workspace_bytes(C.byref(d), N, P, Bk), dev)
         self.ws_con = _ws(lib.lmr_constrain_workspace_bytes(D * N, Cc * P), dev)
-        self.use_graph, self.graph = use_graph, None
-        # (sum, min, max) over the local targets of acts_d = mean_n act[d,n] / a*_d, written by the last launch of every step; the stop rule of the
-        # match loop reads these 12 bytes through a pinned buffer (one small copy + one stream synchronisation per epoch)
-        self.epoch = torch.zeros(3, **f32)
-        self.epoch_host = torch.zeros(3, dtype=torch.float32).pin_memory()
+        self.use_graph = use_graph
+        # (sum, min, max) over the local targets of acts_d = mean_n act[d,n] / a*_d, written by the last launch of every step into one of TWO slots
+        # (epoch parity): the match loop queues epoch e + 1 before it reads epoch e's statistics (12 bytes through a pinned buffer, waited for on
+        # an event), so the GPU never idles for the host's round trip; `backup` holds the state (parameters, Adam moments, step counters) from
+        # before the running epoch, which is what `restore_state` brings back when the stop rule turns out to have fired one epoch earlier
+        self.epoch2 = torch.zeros((2, 3), **f32)
+        self.epoch = self.epoch2[0]
+        self.epoch_host = torch.zeros((2, 3), dtype=torch.float32).pin_memory()
+        self.stats_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.backup = [[x.detach().clone() for x in grp] for grp in (self.params, self.m, self.v, self.steps)]
+        self.graphs = {}
 
     def _affine(self):
         return self.t.affine_args()
@@ -333,8 +339,22 @@ class MatchStepper:
         return ops.AffineArgs(a.angles.detach()[b0:b1], a.scalings.detach()[b0:b1], a.shears.detach()[b0:b1], a.translation.detach().reshape(D, 2)[b0:b1],
                               tc=const["tc"], shift_to=const["shift_to"], shift_from=None if sf is None else sf.reshape(D, 2)[b0:b1], clamp=const["clamp"])
 
-    def _train(self):
+    def _save_state(self):
+        for grp, bak in zip((self.params, self.m, self.v, self.steps), self.backup):
+            for x, y in zip(grp, bak):
+                y.copy_(x.detach(), non_blocking=True)
+
+    def restore_state(self):
+        """Back to the state saved by the last step(..., save=True): undoes the (speculatively queued) epoch that followed it."""
+        with torch.no_grad():
+            for grp, bak in zip((self.params, self.m, self.v, self.steps), self.backup):
+                for x, y in zip(grp, bak):
+                    x.detach().copy_(y, non_blocking=True)
+
+    def _train(self, slot=0, save=False):
         t, c, N, D, Cc, P = self.t, self.con, self.N, self.D, self.C, self.P
+        if save:
+            self._save_state()
         for b0 in range(0, D, self.block):
             b1 = min(D, b0 + self.block)
             Db = b1 - b0
@@ -354,23 +374,35 @@ class MatchStepper:
         for p, g, m, v, s, tr in zip(self.params, self.grads, self.m, self.v, self.steps, self.trainable):
             if tr:
                 ops.raw_adam_step(p.data, g, m, v, s, lr=self.lr)
-        ops.raw_match_epoch_stats(self.act, self.mei_acts, self.epoch)
+        ops.raw_match_epoch_stats(self.act, self.mei_acts, self.epoch2[slot])
 
-    def epoch_stats(self):
+    def epoch_stats(self, slot=0):
         """(sum_d, min_d, max_d) of the last step's normalised activations acts_d (inv_temp_learn_match.py:362,368-371) as host floats."""
-        self.epoch_host.copy_(self.epoch, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return tuple(self.epoch_host.tolist())
+        self.queue_stats(slot)
+        return self.wait_stats(slot)
 
-    def step(self, grid_row):
+    def queue_stats(self, slot):
+        """Queues the copy of slot `slot` of the epoch statistics to pinned host memory behind the launches queued so far."""
+        self.epoch_host[slot].copy_(self.epoch2[slot], non_blocking=True)
+        self.stats_ready[slot].record()
+
+    def wait_stats(self, slot):
+        self.stats_ready[slot].synchronize()
+        return tuple(self.epoch_host[slot].tolist())
+
+    def step(self, grid_row, slot=0, save=False):
+        """One Adam step of every target on the jittered latents `grid_row`.  slot: which of the two statistics slots the step writes;
+        save: keep a copy of the state from before the step (first step of an epoch: what `restore_state` goes back to)."""
         self.grid.copy_(grid_row.reshape(-1), non_blocking=True)
+        key = (int(slot), bool(save))
         if not self.use_graph:
-            self._train()
-        elif self.graph is None:
-            self._train()
-            self.graph = capture_graph(self._train)  # records the launches without executing them
+            self._train(*key)
+        elif key not in self.graphs:
+            # the first step of a kind runs eagerly (it is also the warm-up that sets kernel attributes); captured afterwards
+            self._train(*key)
+            self.graphs[key] = capture_graph(lambda: self._train(*key))  # records the launches without executing them
         else:
-            self.graph.replay()
+            self.graphs[key].replay()
 
     def evaluate(self, grid_row):
         """No-grad forward on `grid_row`: act [D,N] of every target neuron on its own images."""

@@ -248,28 +248,71 @@ class InvarianceManifold:
 
         images_list, acts_list = [], []
         self.match_steps_taken = 0
-        next_grids = None
         pbar = tqdm(range(num_epochs), bar_format=_BAR)
         epoch = -1  # num_epochs=0: the call returns the snapshot of the initialised transform like the reference
-        for epoch in pbar:
-            if save_results_every_n_epochs and epoch % save_results_every_n_epochs == 0:
-                imgs, a = snapshot()
-                images_list.append(imgs), acts_list.append(a)
-            if not template.training:  # (the reference calls .train() every epoch, :350: a walk over the module tree; only the first one changes anything)
+        epochs_run = 0
+
+        def judge(a_sum, a_min, a_max):
+            """The stop rule of :368-375 on one epoch's statistics -> (keep going?, progress-bar text)."""
+            a_mean = a_sum / d_total
+            going = improvement_checker.is_increasing(a_mean)
+            return going, f"Activation mean = {a_mean:.2f} (min = {a_min:.2f} max = {a_max:.2f})"
+
+        if fused:
+            # Fused path: the statistics of epoch e are read while epoch e + 1 already runs -- the host's round trip (copy of 12 bytes, in the
+            # sharded case a 3-float collective before it, the stop rule, the next launch) never leaves the GPU idle.  Epoch e + 1 is therefore
+            # SPECULATIVE: its first step saves the state it starts from, and if the stop rule turns out to have fired at epoch e, that state is
+            # restored, the CPU generator is rewound to before e + 1's jitter draw and a snapshot taken for e + 1 is dropped -- parameters,
+            # results, epoch / step counts and generator state are those of the reference's sequential loop.
+            pending = None  # (statistics handle of the previous epoch, its slot)
+            stopped = False
+            for epoch in pbar:
+                took_snapshot = False
+                if save_results_every_n_epochs and epoch % save_results_every_n_epochs == 0:
+                    imgs, a = snapshot()
+                    images_list.append(imgs), acts_list.append(a)
+                    took_snapshot = True
+                if not template.training:  # (the reference calls .train() every epoch, :350: a walk over the module tree; only the first one changes anything)
+                    template.train()
+                rng_before = torch.get_rng_state()
+                epoch_grids = [g.to(device) for g in grid_dataloader.train_dataloader()]  # same generator, same order as the reference (:351)
+                slot = epoch & 1
+                for i, input_grid in enumerate(epoch_grids):
+                    stepper.step(input_grid, slot=slot, save=(i == 0))
+                handle = _stop_reduce.begin(stepper.epoch2[slot]) if _stop_reduce is not None else stepper.queue_stats(slot)
+                if pending is not None:
+                    stats = _stop_reduce.end(pending[0]) if _stop_reduce is not None else stepper.wait_stats(pending[1])
+                    going, act_desc = judge(*stats)
+                    if not going:  # the PREVIOUS epoch was the last one: undo this one
+                        stepper.restore_state()
+                        torch.set_rng_state(rng_before)
+                        if took_snapshot:
+                            images_list.pop(), acts_list.pop()
+                        if _stop_reduce is not None:
+                            _stop_reduce.end(handle)  # (every rank leaves its last collective completed)
+                        stopped = True
+                        pbar.set_description("✅ Invariance matching is finished!" + " " + act_desc)
+                        pbar.close()
+                        break
+                    desc = act_desc
+                    if verbose:
+                        desc += f" | Epochs w/o improving = {improvement_checker.has_not_improved_counter} (patience: {improvement_checker.patience})"
+                    pbar.set_description(desc, refresh=False)
+                self.match_steps_taken += len(epoch_grids)
+                epochs_run = epoch + 1
+                pending = (handle, slot)
+            if not stopped and pending is not None:  # the last epoch's statistics: nothing left to undo, but the checker and the bar see them
+                stats = _stop_reduce.end(pending[0]) if _stop_reduce is not None else stepper.wait_stats(pending[1])
+                going, act_desc = judge(*stats)
+                if not going:
+                    pbar.set_description("✅ Invariance matching is finished!" + " " + act_desc)
+                pbar.close()
+        else:
+            for epoch in pbar:
+                if save_results_every_n_epochs and epoch % save_results_every_n_epochs == 0:
+                    imgs, a = snapshot()
+                    images_list.append(imgs), acts_list.append(a)
                 template.train()
-            if fused:
-                # The epoch's launches are queued first; the host then draws the NEXT epoch's jittered grids (same generator, same order as the
-                # reference: train_dataloader() then the iterator's base-seed draw) while the GPU works, and only then waits for this epoch's
-                # statistics.  If the stop rule fires, the generator is rewound to where the reference would have left it.
-                epoch_grids = next_grids if next_grids is not None else [g.to(device) for g in grid_dataloader.train_dataloader()]
-                for input_grid in epoch_grids:
-                    stepper.step(input_grid)
-                    self.match_steps_taken += 1
-                rng_before_next, next_grids = None, None
-                if epoch + 1 < num_epochs:
-                    rng_before_next = torch.get_rng_state()
-                    next_grids = [g.to(device) for g in grid_dataloader.train_dataloader()]
-            else:
                 for input_grid in grid_dataloader.train_dataloader():
                     input_grid = input_grid.to(device)
                     _, _, _acts, _ = self.forward(input_grid, template, self.img_transforms, self.response_predicting_model, return_template=False,
@@ -281,29 +324,21 @@ class InvarianceManifold:
                     loss.backward()
                     optimizer.step()
                     self.match_steps_taken += 1
-
-            if fused and _stop_reduce is not None:  # sharded: the ranks exchange the device-resident statistics, one copy to the host
-                a_sum, a_min, a_max = _stop_reduce(stepper.epoch)
-            elif fused:  # written by the step's last launch (lmr_match_epoch_stats): 12 bytes, one synchronisation per epoch
-                a_sum, a_min, a_max = stepper.epoch_stats()
-            else:
                 a_sum, a_min, a_max = torch.stack([acts.sum(), acts.min(), acts.max()]).tolist()
                 if _stop_reduce is not None:
                     a_sum, a_min, a_max = _stop_reduce(a_sum, a_min, a_max)
-            a_mean = a_sum / d_total
-            is_increasing = improvement_checker.is_increasing(a_mean)
-            desc = act_desc = f"Activation mean = {a_mean:.2f} (min = {a_min:.2f} max = {a_max:.2f})"
-            if not is_increasing and fused and rng_before_next is not None:
-                torch.set_rng_state(rng_before_next)  # the next epoch's draws were speculative
-            if not is_increasing:
-                pbar.set_description("✅ Invariance matching is finished!" + " " + act_desc)
-                pbar.close()
-                break
-            if verbose:
-                desc += f" | Epochs w/o improving = {improvement_checker.has_not_improved_counter} (patience: {improvement_checker.patience})"
-            pbar.set_description(desc, refresh=False)
-        self.match_epochs_run = epoch + 1
-        mark(f"{epoch + 1} epochs")
+                epochs_run = epoch + 1
+                going, act_desc = judge(a_sum, a_min, a_max)
+                if not going:
+                    pbar.set_description("✅ Invariance matching is finished!" + " " + act_desc)
+                    pbar.close()
+                    break
+                desc = act_desc
+                if verbose:
+                    desc += f" | Epochs w/o improving = {improvement_checker.has_not_improved_counter} (patience: {improvement_checker.patience})"
+                pbar.set_description(desc, refresh=False)
+        self.match_epochs_run = epochs_run
+        mark(f"{epochs_run} epochs")
 
         template.eval()
         imgs, a = snapshot()

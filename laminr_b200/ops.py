@@ -223,50 +223,18 @@ def raw_inr_backward_adam(desc, params, B, auxB, grid, coords, coord_shift, g_im
     return g_params
 
 
-class _InrImages(torch.autograd.Function):
-    """img[D,N,C,P] = INR(...).  Differentiable wrt the MLP parameters (learn) and the affine scalars (match)."""
-
-    @staticmethod
-    def forward(ctx, meta, flat_params, B, auxB, grid, coords, coord_shift, angles, scalings, shears, translation, *param_views):
-        desc, aff_const, precision = meta["desc"], meta["affine_const"], meta["precision"]
-        affine = None
-        if angles is not None:
-            affine = AffineArgs(angles.detach(), scalings.detach(), shears.detach(), translation.detach(), **aff_const)
-        grid = _f32c(grid.detach().reshape(-1))
-        out = raw_inr_forward(desc, flat_params, B, auxB, grid, coords, coord_shift, affine, precision=precision)
-        ctx.meta, ctx.affine = meta, affine
-        ctx.save_for_backward(flat_params, B, auxB, grid, coords, coord_shift)
-        ctx.param_shapes = [p.shape for p in param_views]
-        ctx.translation_shape = None if translation is None else translation.shape
-        return out
-
-    @staticmethod
-    def backward(ctx, g_img):
-        flat_params, B, auxB, grid, coords, coord_shift = ctx.saved_tensors
-        meta = ctx.meta
-        n_fixed = 11
-        want_params = any(ctx.needs_input_grad[n_fixed:])
-        want_affine = ctx.affine is not None and any(ctx.needs_input_grad[7:11])
-        grads = [None] * (n_fixed + len(ctx.param_shapes))
-        if not (want_params or want_affine):
-            return tuple(grads)
-        g_params, g_aff = raw_inr_backward(meta["desc"], flat_params, B, auxB, grid, coords, coord_shift, ctx.affine, g_img,
-                                           want_params=want_params, want_affine=want_affine, precision=meta["precision"])
-        if want_affine:
-            grads[7], grads[8], grads[9] = g_aff[0], g_aff[1], g_aff[2]
-            grads[10] = g_aff[3].reshape(ctx.translation_shape)
-        if want_params:
-            off = 0
-            for i, shp in enumerate(ctx.param_shapes):
-                n = int(torch.Size(shp).numel())
-                grads[n_fixed + i] = g_params[off:off + n].view(shp)
-                off += n
-        return tuple(grads)
-
-
 def inr_images(meta, flat_params, B, auxB, grid, coords, coord_shift, affine_params, param_views):
+    """img[D,N,C,P] = INR(...), differentiable wrt the MLP parameters (learn) and the affine scalars (match): the registered operator
+    torch.ops.laminr_b200.inr_images (laminr_b200/torch_ops.py), whose backward is torch.ops.laminr_b200.inr_backward."""
+    from . import torch_ops  # noqa: F401  (registers the operators)
+    desc, const = meta["desc"], meta["affine_const"]
     a = affine_params if affine_params is not None else (None, None, None, None)
-    return _InrImages.apply(meta, flat_params, B, auxB, grid, coords, coord_shift, a[0], a[1], a[2], a[3], *param_views)
+    has_aff = a[0] is not None
+    return torch.ops.laminr_b200.inr_images(
+        flat_params, list(param_views), B, auxB, grid, coords, coord_shift, a[0], a[1], a[2], a[3],
+        const.get("tc") if has_aff else None, const.get("shift_to") if has_aff else None, const.get("shift_from") if has_aff else None,
+        bool(const.get("clamp", True)), int(desc.hidden), int(desc.n_hidden), int(desc.pe_dim), int(desc.aux_pe_dim), int(desc.channels),
+        str(meta["precision"] or default_precision()))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -301,24 +269,12 @@ def raw_constrain_bwd(mode, x, g_z, stats, target, mean, pmin, pmax, eps, out=No
     return out
 
 
-class _Constrain(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, mode, target, mean, pmin, pmax, eps):
-        x = _f32c(x)
-        z, stats = raw_constrain_fwd(mode, x, target, mean, pmin, pmax, eps)
-        ctx.save_for_backward(x, stats)
-        ctx.cfg = (mode, target, mean, pmin, pmax, eps)
-        return z
-
-    @staticmethod
-    def backward(ctx, g_z):
-        x, stats = ctx.saved_tensors
-        mode, target, mean, pmin, pmax, eps = ctx.cfg
-        return raw_constrain_bwd(mode, x, _f32c(g_z), stats, target, mean, pmin, pmax, eps), None, None, None, None, None, None
-
-
 def constrain(x, mode, target, mean, pmin, pmax, eps=1e-12):
-    return _Constrain.apply(x, mode, target, mean, pmin, pmax, eps)
+    """Differentiable constraint projection: torch.ops.laminr_b200.constrain (backward: constrain_backward)."""
+    from . import torch_ops  # noqa: F401
+    z, _stats = torch.ops.laminr_b200.constrain(x, int(mode), float(target), float(mean), pmin is not None, float(pmin or 0.0), pmax is not None,
+                                                float(pmax or 0.0), float(eps))
+    return z
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -347,31 +303,12 @@ def raw_simresp_bwd(g_act, rmax, argmax, group_stride, NB, G, Cc, HW, filters, n
     return g_img
 
 
-class _SimResp(torch.autograd.Function):
-    """x [B,C,H,W] -> act [G,B] for the neurons in `neuron_of_group` (every neuron sees every image)."""
-
-    @staticmethod
-    def forward(ctx, x, filters, nfilt, neuron_of_group, eps):
-        x = _f32c(x)
-        Bn, Cc = x.shape[0], x.shape[1]
-        HW = x.shape[2] * x.shape[3]
-        G = neuron_of_group.numel()
-        act, rmax, argmax = raw_simresp_fwd(x, 0, Bn, G, Cc, HW, filters, nfilt, neuron_of_group, eps)
-        ctx.save_for_backward(rmax, argmax, filters, neuron_of_group)
-        ctx.shape = x.shape
-        return act
-
-    @staticmethod
-    def backward(ctx, g_act):
-        rmax, argmax, filters, neuron_of_group = ctx.saved_tensors
-        Bn, Cc, H, W = ctx.shape
-        g_img = torch.empty(ctx.shape, dtype=torch.float32, device=g_act.device)
-        raw_simresp_bwd(_f32c(g_act), rmax, argmax, 0, Bn, neuron_of_group.numel(), Cc, H * W, filters, neuron_of_group, g_img)
-        return g_img, None, None, None, None
-
-
 def simresp(x, filters, nfilt, neuron_of_group, eps=1e-6):
-    return _SimResp.apply(x, filters, nfilt, neuron_of_group, eps)
+    """x [B,C,H,W] -> act [G,B] for the neurons in `neuron_of_group` (every neuron sees every image), differentiable wrt x:
+    torch.ops.laminr_b200.simresp (backward: simresp_backward)."""
+    from . import torch_ops  # noqa: F401
+    act, _rmax, _argmax = torch.ops.laminr_b200.simresp(x, filters, nfilt, neuron_of_group, float(eps))
+    return act
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -502,29 +439,12 @@ def raw_simclr_bwd(img, mask, K, g_reg, scale, N, Cc, HW, pmin, pmax, g_img, acc
     return g_img
 
 
-class _SimclrReg(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, img, mask, pmin, pmax, pos, neg, T, eps):
-        img = _f32c(img)
-        N, Cc = img.shape[0], img.shape[1]
-        HW = img[0, 0].numel()
-        reg, K = raw_simclr_fwd(img, mask, N, Cc, HW, pmin, pmax, pos, neg, T, eps)
-        ctx.save_for_backward(img, mask, K)
-        ctx.cfg = (N, Cc, HW, pmin, pmax)
-        return reg.reshape(())
-
-    @staticmethod
-    def backward(ctx, g_reg):
-        img, mask, K = ctx.saved_tensors
-        N, Cc, HW, pmin, pmax = ctx.cfg
-        g_img = torch.empty_like(img)
-        raw_simclr_bwd(img, mask, K, _f32c(g_reg.reshape(1)), 1.0, N, Cc, HW, pmin, pmax, g_img)
-        return g_img, None, None, None, None, None, None, None
-
-
 def simclr_reg(img, mask, pmin, pmax, pos, neg, T, eps=1e-6):
-    """apply_mask + SimCLROnGrid.reg_term fused.  img [N,C,H,W]; mask [H,W]."""
-    return _SimclrReg.apply(img, _f32c(mask), pmin, pmax, pos, neg, T, eps)
+    """apply_mask + SimCLROnGrid.reg_term fused, differentiable wrt img.  img [N,C,H,W]; mask [H,W]: torch.ops.laminr_b200.simclr_reg
+    (backward: simclr_reg_backward)."""
+    from . import torch_ops  # noqa: F401
+    reg, _K = torch.ops.laminr_b200.simclr_reg(img, _f32c(mask), float(pmin), float(pmax), pos, neg, float(T), float(eps))
+    return reg.reshape(())
 
 
 # ------------------------------------------------------------------------------------------------------------------

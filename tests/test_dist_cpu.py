@@ -61,6 +61,8 @@ def _worker(rank, world, port, n_targets, q):
             # the tensor form (the fused stepper's 3-float epoch statistics) must give the same decision inputs
             s2, mn2, mx2 = reduce(torch.tensor([a.sum(), a.min(), a.max()], dtype=torch.float64))
             assert (s2, mn2, mx2) == (s, mn, mx)
+            # ... and so must the split form (collective queued now, result read an epoch later)
+            assert reduce.end(reduce.begin(torch.tensor([a.sum(), a.min(), a.max()], dtype=torch.float64))) == (s, mn, mx)
             means.append(s / n_targets)
             assert abs(mn - curves[epoch].min()) < 1e-12 and abs(mx - curves[epoch].max()) < 1e-12
             if not chk.is_increasing(s / n_targets):

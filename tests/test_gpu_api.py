@@ -161,17 +161,25 @@ def test_match_leaves_cpu_generator_like_the_reference_loop(L, kw, epochs):
     """The fused match loop draws the next epoch's jitter while the GPU still runs the current one; whether the loop ends by exhausting num_epochs
     or by the stop rule (:368-375), the CPU generator must end where the reference's loop (= the generic path) leaves it."""
     d = golden("match_step_20")
-    states = []
+    states, finals = [], []
     for fused in (True, False):
         model, im = _manifold(L, 20, d)
         if not fused:
             im._fused_ok = lambda gaussian_blur=None: False
         im.template_neuron_idx = 0
         torch.manual_seed(11)
-        im.match([1, 2], **kw)
+        imgs, acts = im.match([1, 2], save_results_every_n_epochs=1, **kw)
         assert im.match_epochs_run == epochs and im.match_steps_taken == epochs
+        assert imgs.shape[0] == epochs + 1  # one snapshot per epoch that ran + the final one (a snapshot taken for an undone epoch is dropped)
         states.append(torch.get_rng_state().clone())
+        aff = im.template.coordinate_transform.transforms.Affine
+        finals.append([p.detach().cpu().numpy().copy() for p in (aff.angles, aff.scalings, aff.shears, aff.translation)] + [np.asarray(acts)])
     assert torch.equal(states[0], states[1])
+    # the fused loop runs one epoch ahead of its stop rule and rolls it back: the final transform must be the sequential loop's, not one Adam step
+    # (1e-3 per scalar) further
+    for a, b in zip(finals[0][:4], finals[1][:4]):
+        np.testing.assert_allclose(a, b, rtol=2e-4, atol=5e-5)
+    np.testing.assert_allclose(finals[0][4], finals[1][4], rtol=2e-4, atol=2e-5)
 
 
 def test_match_step_in_target_blocks_equals_one_pass(L, monkeypatch):

@@ -337,3 +337,22 @@ def test_config3_sample_meis_and_match_vs_reference(L):
     np.testing.assert_allclose(aff.translation.detach().cpu().numpy()[:, 0], d["translation"], rtol=0, atol=5e-4)
     sub = int(d["sub"])
     assert relerr(imgs.reshape(n - 1, 20, -1)[:, :, ::sub], d["imgs"].astype(np.float32)) < 1e-2 and relerr(acts, d["acts"]) < 1e-2
+
+
+def test_torch_library_operators_opcheck(L):
+    """torch.library.opcheck of the registered operators on small inputs: schema, fake kernel vs real kernel, autograd registration."""
+    from torch.library import opcheck
+    torch.manual_seed(0)
+    x = torch.randn(3, 1, 6, 5, device="cuda", requires_grad=True)
+    opcheck(torch.ops.laminr_b200.constrain, (x, 0, 1.0, 0.0, True, -1.0, True, 1.0, 1e-12), test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    pop = L.neuron_models.simulated_population(4, img_res=[5, 6], seed=1, num_filters=3).cuda()
+    idx = torch.tensor([2, 0], dtype=torch.int32, device="cuda")
+    opcheck(torch.ops.laminr_b200.simresp, (x, pop.packed_filters, pop.nfilt, idx, 1e-6), test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+    # gradients through the operators == the raw C-ABI calls
+    act, rmax, argmax = torch.ops.laminr_b200.simresp(x, pop.packed_filters, pop.nfilt, idx, 1e-6)
+    g = torch.randn_like(act)
+    (gx,) = torch.autograd.grad(act, x, g)
+    from laminr_b200 import ops
+    want = torch.empty_like(x)
+    ops.raw_simresp_bwd(g.contiguous(), rmax, argmax, 0, 3, 2, 1, 30, pop.packed_filters, idx, want)
+    assert torch.equal(gx, want)

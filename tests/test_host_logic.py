@@ -331,3 +331,29 @@ def test_unsupported_inr_shapes_fail_at_construction(L):
     m = L.neuron_models.simulated("demo1", img_res=[8, 8])
     with pytest.raises(NotImplementedError, match="hidden width 32"):
         L.InvarianceManifold(m, _meis(8), device="cpu", widths=[32] * 4, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+
+
+def test_torch_library_operators_are_registered(L):
+    """The C-ABI entry points of the generic path are PyTorch custom operators (torch.ops.laminr_b200.*) with CUDA-only kernels: a CPU tensor
+    finds no kernel instead of a fallback; the fake kernels give the output shapes without running anything."""
+    from laminr_b200 import torch_ops
+    for name in torch_ops.OPERATORS:
+        assert hasattr(torch.ops.laminr_b200, name), name
+    schema = str(torch.ops.laminr_b200.inr_images.default._schema)
+    assert "Tensor[] param_views" in schema and "Tensor? angles" in schema and schema.endswith("-> Tensor")
+    with pytest.raises(NotImplementedError):
+        torch.ops.laminr_b200.constrain(torch.zeros(2, 1, 4, 4), 0, 1.0, 0.0, True, -1.0, True, 1.0, 1e-12)
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        x = torch.empty(3, 1, 5, 6, device="cuda")
+        z, stats = torch.ops.laminr_b200.constrain(x, 0, 1.0, 0.0, True, -1.0, True, 1.0, 1e-12)
+        assert z.shape == x.shape and stats.shape == (3, 2)
+        act, rmax, am = torch.ops.laminr_b200.simresp(x, torch.empty(4, 7, 30, device="cuda"), torch.empty(4, dtype=torch.int32, device="cuda"),
+                                                      torch.empty(2, dtype=torch.int32, device="cuda"), 1e-6)
+        assert act.shape == (2, 3) and am.dtype == torch.int32
+        flat = torch.empty(17801, device="cuda")
+        img = torch.ops.laminr_b200.inr_forward(flat, torch.empty(2, 50, device="cuda"), torch.empty(2, 50, device="cuda"), torch.empty(20, device="cuda"),
+                                                torch.empty(100, 2, device="cuda"), None, torch.empty(3, device="cuda"), torch.empty(3, 2, device="cuda"),
+                                                torch.empty(3, 2, device="cuda"), torch.empty(3, 1, 2, device="cuda"), None, None, None, True, 50, 4, 50, 50, 1,
+                                                "fp32")
+        assert img.shape == (3, 20, 1, 100)
