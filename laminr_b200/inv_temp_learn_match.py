@@ -238,12 +238,19 @@ class InvarianceManifold:
         grid = grid_dataloader.grid.to(device)
         d_total = _total_targets if _total_targets is not None else num_targets
 
-        def snapshot():
+        # the final image block is large (0.8 GB for 1023 targets at 100x100): its host array is allocated NOW and made resident by a background
+        # thread while the GPU works, so that the copy at the end runs at PCIe speed instead of at first-touch page-fault speed
+        host_buf = None
+        if fused and not _return_device and save_results_every_n_epochs is None and stepper.z.numel() * 4 >= (64 << 20):
+            host_buf = ops.HostBuffer(stepper.z.numel(), np.float32)
+
+        def snapshot(final=False):
             if fused:
                 act = stepper.evaluate(grid)
-                if _return_device:  # laminr_b200.dist gathers the blocks over NCCL before the one copy to the host
+                if _return_device:  # laminr_b200.dist collects the blocks of all ranks on the host itself
                     return stepper.z.clone(), act.clone()
-                return ops.to_host_numpy(stepper.z), act.cpu().numpy()
+                out = host_buf.wait() if (final and host_buf is not None) else None
+                return ops.to_host_numpy(stepper.z, out=out), act.cpu().numpy()
             return self.get_matched_images_and_activations(grid, template, loc_in_list, loc_in_model)
 
         images_list, acts_list = [], []
@@ -341,7 +348,7 @@ class InvarianceManifold:
         mark(f"{epochs_run} epochs")
 
         template.eval()
-        imgs, a = snapshot()
+        imgs, a = snapshot(final=True)
         mark("snapshot")
         if timing:
             print("[match] " + ", ".join(f"{b[0]} {1e3 * (b[1] - a_[1]):.1f} ms" for a_, b in zip(marks, marks[1:])), file=sys.__stderr__)

@@ -71,26 +71,39 @@ def _workspace(nbytes, device):
 # results -> host (result getters, inv_temp_learn_match.py:394-422: `.cpu().data.numpy()`)
 # ------------------------------------------------------------------------------------------------------------------
 _HOST_RING = {}
+_HOST_RING_LOCK = __import__("threading").Lock()
 
 
-def to_host_numpy(t, chunk_bytes=32 << 20, nbuf=4):
+def _host_ring(dtype, step, nbuf):
+    """The persistent ring of pinned staging buffers (+ its worker pool) for `to_host_numpy`; allocating it (cudaHostAlloc of nbuf x 32 MB) takes
+    ~100 ms, once per process: HostBuffer does it from its background thread, off the caller's path."""
+    import concurrent.futures as cf
+    key = (dtype, step, nbuf)
+    with _HOST_RING_LOCK:
+        if key not in _HOST_RING:
+            _HOST_RING[key] = ([torch.empty(step, dtype=dtype, pin_memory=True) for _ in range(nbuf)], cf.ThreadPoolExecutor(nbuf))
+        return _HOST_RING[key]
+
+
+def to_host_numpy(t, chunk_bytes=32 << 20, nbuf=4, out=None):
     """`t.cpu().numpy()` for large device tensors (the [D,N,C,H,W] image blocks of match: 0.8 GB for 1023 targets at 100x100): the device-to-host
     copies run asynchronously through a small ring of persistent pinned buffers while worker threads move finished chunks into the destination
-    array (a pageable `.cpu()` of that block takes 0.36 s on the B200 box, the first-touch host copy being the bottleneck; this takes about half)."""
-    nbytes = t.numel() * t.element_size()
-    if not t.is_cuda or nbytes < 4 * chunk_bytes:
-        return t.detach().cpu().numpy()
-    import concurrent.futures as cf
-
+    array (a pageable `.cpu()` of that block takes 0.36 s on the B200 box, the first-touch host copy being the bottleneck; this takes about half).
+    out: optional flat, writable numpy array of t.numel() elements to fill instead of a new one (e.g. a slice of a shared-memory segment)."""
     import numpy as np
 
+    nbytes = t.numel() * t.element_size()
+    if not t.is_cuda or nbytes < (chunk_bytes // 4 if out is not None else 4 * chunk_bytes):
+        host = t.detach().cpu().numpy()
+        if out is None:
+            return host
+        out[...] = host.reshape(-1)
+        return out.reshape(tuple(t.shape))
     flat = t.detach().contiguous().reshape(-1)
     step = chunk_bytes // flat.element_size()
-    key = (flat.dtype, step, nbuf)
-    if key not in _HOST_RING:
-        _HOST_RING[key] = ([torch.empty(step, dtype=flat.dtype, pin_memory=True) for _ in range(nbuf)], cf.ThreadPoolExecutor(nbuf))
-    bufs, pool = _HOST_RING[key]
-    out = np.empty(flat.numel(), dtype=bufs[0].numpy().dtype)
+    bufs, pool = _host_ring(flat.dtype, step, nbuf)
+    if out is None:
+        out = np.empty(flat.numel(), dtype=bufs[0].numpy().dtype)
     side = torch.cuda.Stream(device=t.device)
     side.wait_stream(torch.cuda.current_stream(t.device))
 
@@ -112,6 +125,39 @@ def to_host_numpy(t, chunk_bytes=32 << 20, nbuf=4):
         if f is not None:
             f.result()
     return out.reshape(tuple(t.shape))
+
+
+class HostBuffer:
+    """A host destination for a large result, made resident BEFORE the result exists: a background thread touches (zeroes) every page while the
+    GPU still computes, so the final device-to-host copy runs at PCIe speed instead of at page-fault speed (first touch of 0.8 GB: 56-170 ms on
+    the B200 box, as long as a whole 32-target match call).  `flat`: writable flat NumPy array (a new anonymous array, or a slice of a
+    shared-memory segment handed in by laminr_b200.dist)."""
+
+    def __init__(self, numel, dtype, flat=None, device=None):
+        import ctypes
+        import threading
+
+        import numpy as np
+
+        self.flat = np.empty(int(numel), dtype=dtype) if flat is None else flat
+        addr, nbytes = self.flat.ctypes.data, self.flat.nbytes
+        tdtype = torch.from_numpy(np.empty(0, dtype=self.flat.dtype)).dtype
+        dev = torch.cuda.current_device() if device is None and torch.cuda.is_available() else device
+
+        def touch():
+            if dev is not None and torch.cuda.is_available():
+                torch.cuda.set_device(dev)
+                _host_ring(tdtype, (32 << 20) // self.flat.dtype.itemsize, 4)  # the pinned staging ring of to_host_numpy, if this process has none yet
+            step = 64 << 20
+            for o in range(0, nbytes, step):  # (ctypes releases the GIL for the duration of each call)
+                ctypes.memset(addr + o, 0, min(step, nbytes - o))
+
+        self._thread = threading.Thread(target=touch, daemon=True)
+        self._thread.start()
+
+    def wait(self):
+        self._thread.join()
+        return self.flat
 
 
 # ------------------------------------------------------------------------------------------------------------------

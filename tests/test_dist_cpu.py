@@ -71,6 +71,13 @@ def _worker(rank, world, port, n_targets, q):
         # --- ragged gather of per-target results
         local = torch.arange(lo, hi, dtype=torch.float32)[:, None, None] * torch.ones(1, 3, 2)
         full = D.gather_ragged(local, n_targets, dst=0)
+        # --- the same blocks collected on rank 0's HOST through one shared-memory segment that every rank fills itself
+        host = D.gather_to_host(local, n_targets)
+        assert (host is None) == (rank != 0)
+        if rank == 0:
+            assert isinstance(host, np.ndarray) and host.shape == (n_targets, 3, 2) and np.array_equal(host, full.numpy())
+            host[0, 0, 0] = 5.0  # writable, and alive after the segment's name is gone
+            assert not any(f.startswith("laminr_b200_") for f in os.listdir("/dev/shm"))
         # numpy payloads are pickled by value; torch tensors would travel as shared-memory handles that die with this process
         q.put((rank, [p.detach().numpy().copy() for p in mod.parameters()] + [mod.B.numpy().copy()] + tmpl_state, grids.numpy().copy(), stopped_at, means,
                None if full is None else full.numpy().copy(), (lo, hi)))
