@@ -108,6 +108,9 @@ class InvarianceManifold:
             mask_dev = torch.as_tensor(template_rf_mask, dtype=torch.float32).to(device)
 
         def snapshot():
+            if fused:  # images / activations of the un-jittered grid straight from the stepper's launches (what :394-405 computes through `forward`)
+                stepper.evaluate(grid)
+                return stepper.z.cpu().numpy(), stepper.act[0].cpu().numpy()
             return self.get_template_images_and_activations(grid, template_neuron_model, gaussian_blur)
 
         images_list, acts_list = [], []
