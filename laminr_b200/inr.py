@@ -17,6 +17,13 @@ from .coordinate_transforms import CoordinateTransform
 
 
 class INRTemplates(nn.Module):
+    # Hidden width the kernels are built for.  Any list of widths up to it (uniform or not, the reference's `widths=` argument, inr.py:156-174) runs
+    # on the same kernels ZERO-PADDED: the parameters are strided views ([w_out, w_in] corners) of 50-wide blocks of the flat vector; a padded unit
+    # has zero weights and bias, so it outputs tanh(0) = 0, feeds nothing forward, receives a zero gradient (its outgoing weights are zero) and
+    # passes a zero gradient to its incoming weights (its activation is zero) -- the padding stays exactly zero under SGD / Adam, and the
+    # function and every gradient are those of the narrow network.
+    KERNEL_WIDTH = 50
+
     def __init__(self, img_res, num_neurons=0, num_templates=1, out_channels=1, aux_dim=1, widths=[15] * 8, periodic_invariance=False,
                  positional_encoding_dim=None, positional_encoding_projection_scale=1.0, aux_positional_encoding_dim=None,
                  aux_positional_encoding_projection_scale=1.0, nonlinearity=nn.Tanh, final_nonlinearity=nn.Sigmoid, bias=False,
@@ -31,8 +38,8 @@ class INRTemplates(nn.Module):
         if not bias: unsupported.append("bias=False")
         if batchnorm: unsupported.append("batchnorm=True")
         if jitter_coords: unsupported.append("jitter_coords=True")
-        if len(set(widths)) != 1: unsupported.append("non-uniform widths")
-        elif widths[0] != 50: unsupported.append("hidden width %d (the kernels are built for 50)" % widths[0])
+        if max(widths) > self.KERNEL_WIDTH or min(widths) < 1:
+            unsupported.append("hidden widths %s (the kernels serve widths up to %d: narrower layers run zero-padded)" % (list(widths), self.KERNEL_WIDTH))
         if not 2 <= len(widths) <= 8: unsupported.append("%d hidden layers (supported: 2..8)" % len(widths))
         if not 1 <= out_channels <= 4: unsupported.append("%d output channels (supported: 1..4)" % out_channels)
         if unsupported:
@@ -69,27 +76,46 @@ class INRTemplates(nn.Module):
                 m.weight.data.normal_(0.0, weights_scale)
                 m.bias.data.fill_(0)
         self._flat = None
-        self._desc = ops.make_desc(self.widths[0], len(self.widths), positional_encoding_dim, aux_positional_encoding_dim, out_channels)
+        self._desc = ops.make_desc(self.KERNEL_WIDTH, len(self.widths), positional_encoding_dim, aux_positional_encoding_dim, out_channels)
 
     # ---- flat parameter vector shared with the kernels -------------------------------------------------------
+    def _blocks(self):
+        """(offset, padded shape) in the flat vector of every parameter of `func`, in module order: W0 [50, in_dim], b0 [50], W_l [50, 50],
+        b_l [50], ..., W_out [C, 50], b_out [C] -- the layout include/laminr_b200.h gives lmr_inr_forward for hidden width 50."""
+        K, out, off = self.KERNEL_WIDTH, [], 0
+        k_in = self.in_dim
+        for _ in self.widths:
+            out.append((off, (K, k_in))); off += K * k_in
+            out.append((off, (K,))); off += K
+            k_in = K
+        out.append((off, (self.out_channels, K))); off += self.out_channels * K
+        out.append((off, (self.out_channels,))); off += self.out_channels
+        return out, off
+
     def flat_params(self):
-        """The parameters of `func` as ONE contiguous vector (the layout lmr_inr_forward takes); every nn.Parameter is a view of it."""
+        """The parameters of `func` as ONE contiguous vector (the layout lmr_inr_forward takes); every nn.Parameter is a view of it (the
+        [w_out, w_in] corner of its zero-padded block when a layer is narrower than the kernels' width)."""
         ps = list(self.func.parameters())
+        blocks, total = self._blocks()
         flat = self._flat
-        ok = flat is not None and flat.device == ps[0].device
+
+        def view_of(fl, off, shape, p):
+            blk = fl[off:off + int(torch.Size(shape).numel())].view(shape)
+            return blk[tuple(slice(0, n) for n in p.shape)]
+
+        ok = flat is not None and flat.device == ps[0].device and flat.numel() == total
         if ok:
-            off = 0
-            for p in ps:
-                if p.data_ptr() != flat.data_ptr() + 4 * off or not p.is_contiguous():
+            for p, (off, shape) in zip(ps, blocks):
+                want = view_of(flat, off, shape, p)
+                if p.data_ptr() != want.data_ptr() or p.stride() != want.stride():
                     ok = False
                     break
-                off += p.numel()
         if not ok:
-            flat = torch.cat([p.detach().reshape(-1) for p in ps]).contiguous()
-            off = 0
-            for p in ps:
-                p.data = flat[off:off + p.numel()].view(p.shape)
-                off += p.numel()
+            flat = torch.zeros(total, dtype=torch.float32, device=ps[0].device)
+            for p, (off, shape) in zip(ps, blocks):
+                v = view_of(flat, off, shape, p)
+                v.copy_(p.detach())
+                p.data = v
             self._flat = flat
         return flat
 

@@ -48,7 +48,7 @@ class InvarianceManifold:
         if precision is None:
             # the tcgen05 path (split-bf16 x3 operands, fp32 accumulate: fp32-class results) serves the pipeline default network
             # (4 hidden layers of width 50); any other shape runs on the fp32 CUDA-core path
-            precision = "bf16x3" if (list(widths) == [50] * 4 and positional_encoding_dim <= 64) else "fp32"
+            precision = "bf16x3" if (len(widths) == 4 and max(widths) <= INRTemplates.KERNEL_WIDTH and positional_encoding_dim <= 64) else "fp32"
         self.precision, self.use_cuda_graph = precision, use_cuda_graph
         self.template = INRTemplates(
             img_res=(height, width), num_templates=1, out_channels=channels, widths=widths,

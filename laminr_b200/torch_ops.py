@@ -99,6 +99,11 @@ def _inr_setup(ctx, inputs, output):
      pe_dim, aux_pe_dim, channels, precision) = inputs
     ctx.save_for_backward(flat, B, auxB, grid, coords, coord_shift, angles, scalings, shears, translation, tc, shift_to, shift_from)
     ctx.cfg = (clamp, hidden, n_hidden, pe_dim, aux_pe_dim, channels, precision)
+    # every view is a strided window of `flat` (contiguous for 50-wide layers, the corner of a zero-padded block for narrower ones): its
+    # gradient is the same window of the flat gradient
+    base = flat.storage_offset()
+    ctx.view_geom = [(tuple(v.shape), tuple(v.stride()), v.storage_offset() - base) if v.untyped_storage().data_ptr() == flat.untyped_storage().data_ptr()
+                     else None for v in param_views]
     ctx.view_shapes = [tuple(v.shape) for v in param_views]
     ctx.want_params = any(v.requires_grad for v in param_views)
     ctx.want_affine = angles is not None and any(t is not None and t.requires_grad for t in (angles, scalings, shears, translation))
@@ -117,11 +122,11 @@ def _inr_backward(ctx, g_img):
         hidden, n_hidden, pe_dim, aux_pe_dim, channels, precision, g_img.contiguous(), ctx.want_params, ctx.want_affine)
     if ctx.want_params:
         grads, off = [], 0
-        for shp in ctx.view_shapes:
+        for shp, geom in zip(ctx.view_shapes, ctx.view_geom):
             n = 1
             for s_ in shp:
                 n *= s_
-            grads.append(g_flat[off:off + n].view(shp))
+            grads.append(g_flat.as_strided(*geom) if geom is not None else g_flat[off:off + n].view(shp))
             off += n
         out[1] = grads
     if ctx.want_affine:

@@ -356,3 +356,52 @@ def test_torch_library_operators_opcheck(L):
     want = torch.empty_like(x)
     ops.raw_simresp_bwd(g.contiguous(), rmax, argmax, 0, 3, 2, 1, 30, pop.packed_filters, idx, want)
     assert torch.equal(gx, want)
+
+
+@pytest.mark.parametrize("widths,precision", [([32, 20, 50], "fp32"), ([24] * 4, "fp32"), ([40, 16, 50, 33], "bf16x3"), ([50, 50, 8], "fp32")])
+def test_narrow_widths_forward_backward_vs_oracle(L, widths, precision):
+    """INR networks narrower than the kernels' 50 (the reference's `widths=` argument) run zero-padded on the same kernels: images and parameter
+    gradients against the numpy oracle evaluated on the TRUE shapes (fp32: 1e-5 / 2e-3; split-bf16: 1e-4 / 5e-3), gradients arrive in the
+    parameters' own shapes, and three fused Adam steps leave the padding exactly zero."""
+    from torch import nn
+    from laminr_b200.inr import INRTemplates
+    from oracle import laminr_oracle as O
+    H, W, N = 9, 11, 20
+    torch.manual_seed(1)
+    t = INRTemplates((H, W), widths=widths, periodic_invariance=True, positional_encoding_dim=50, positional_encoding_projection_scale=10,
+                     aux_positional_encoding_dim=50, aux_positional_encoding_projection_scale=0.1, final_nonlinearity=nn.Tanh, bias=True, weights_scale=0.1,
+                     precision=precision).cuda()
+    with torch.no_grad():
+        for p in t.func.parameters():
+            p.add_(torch.randn_like(p) * 0.1)
+    grid = (torch.linspace(0, 2 * np.pi, N + 1)[:-1] + 0.3).reshape(N, 1).cuda()
+    img = t(aux=grid, return_template=True)
+    g = torch.randn_like(img)
+    (img * g).sum().backward()
+    Ws = [getattr(t.func, f"layer{i}").weight.detach().cpu().numpy() for i in range(len(widths) + 1)]
+    bs = [getattr(t.func, f"layer{i}").bias.detach().cpu().numpy() for i in range(len(widths) + 1)]
+    coords = t.coords.reshape(-1, 2).cpu().numpy()
+    want, cache = O.inr_forward(Ws, bs, t.B.cpu().numpy(), t.auxB.cpu().numpy(), grid[:, 0].cpu().numpy(), coords[None], (H, W), keep=True)
+    tol_i, tol_g = (1e-5, 2e-3) if precision == "fp32" else (1e-4, 5e-3)
+    assert relerr(img.detach().cpu().numpy().reshape(want.shape), want) < tol_i
+    grads = O.inr_backward(Ws, t.B.cpu().numpy(), cache, g.detach().cpu().numpy().reshape(want.shape), want_weights=True)
+    dW, db = grads["dW"], grads["db"]
+    for i in range(len(widths) + 1):
+        lay = getattr(t.func, f"layer{i}")
+        assert lay.weight.grad.shape == lay.weight.shape and relerr(lay.weight.grad.cpu().numpy(), dW[i]) < tol_g, i
+        assert relerr(lay.bias.grad.cpu().numpy(), db[i]) < tol_g, i
+    # the padding of the flat vector stays zero under the fused Adam step
+    flat = t.flat_params()
+    live = torch.zeros_like(flat, dtype=torch.bool)
+    for p in t.func.parameters():
+        live.as_strided(p.shape, p.stride(), p.storage_offset() - flat.storage_offset()).fill_(True)
+    assert float(flat[~live].abs().max()) == 0.0
+    from laminr_b200 import ops
+    m, v, step, gp = torch.zeros_like(flat), torch.zeros_like(flat), torch.zeros(2, dtype=torch.int32, device="cuda"), torch.empty_like(flat)
+    cflat = t.coords.reshape(-1, 2).contiguous()
+    for _ in range(3):
+        ws = torch.empty(ops.forward_workspace_bytes(t._desc, N, H * W, 1, precision != "fp32"), dtype=torch.uint8, device="cuda")
+        ops.raw_inr_forward(t._desc, flat, t.B, t.auxB, grid.reshape(-1), cflat, None, None, precision=precision, workspace=ws, keep_activations=True)
+        ops.raw_inr_backward_adam(t._desc, flat, t.B, t.auxB, grid.reshape(-1), cflat, None, g.reshape(1, N, 1, H * W).contiguous(), gp, m, v, step,
+                                  precision=precision, forward_workspace=ws, keep_activations=True)
+    assert float(flat[~live].abs().max()) == 0.0 and float(gp[~live].abs().max()) == 0.0 and float(m[~live].abs().max()) == 0.0

@@ -318,19 +318,55 @@ def test_state_dicts_are_the_references(L):
 
 def test_unsupported_inr_shapes_fail_at_construction(L):
     """Shapes the kernels are not built for are refused when the template is constructed (NotImplementedError naming the reason), not at the first
-    launch: hidden width != 50, fewer than 2 / more than 8 hidden layers, more than 4 output channels (csrc/inr_common.cuh: make_net)."""
+    launch: a hidden width above 50, fewer than 2 / more than 8 hidden layers, more than 4 output channels (csrc/inr_common.cuh: make_net)."""
     from laminr_b200.inr import INRTemplates
     from torch import nn
     kw = dict(periodic_invariance=True, positional_encoding_dim=50, positional_encoding_projection_scale=10, aux_positional_encoding_dim=50,
               aux_positional_encoding_projection_scale=0.1, final_nonlinearity=nn.Tanh, bias=True, weights_scale=0.1)
     INRTemplates((8, 8), widths=[50] * 2, **kw), INRTemplates((8, 8), widths=[50] * 8, out_channels=4, **kw)   # the supported corners construct
-    for bad, why in ((dict(widths=[64] * 4), "hidden width 64"), (dict(widths=[50]), "1 hidden layers"), (dict(widths=[50] * 9), "9 hidden layers"),
-                     (dict(widths=[50] * 4, out_channels=5), "5 output channels"), (dict(widths=[50, 40, 50, 50]), "non-uniform")):
+    for bad, why in ((dict(widths=[64] * 4), "hidden widths"), (dict(widths=[50]), "1 hidden layers"), (dict(widths=[50] * 9), "9 hidden layers"),
+                     (dict(widths=[50] * 4, out_channels=5), "5 output channels"), (dict(widths=[50, 51, 50, 50]), "hidden widths")):
         with pytest.raises(NotImplementedError, match=why):
             INRTemplates((8, 8), **bad, **kw)
     m = L.neuron_models.simulated("demo1", img_res=[8, 8])
-    with pytest.raises(NotImplementedError, match="hidden width 32"):
-        L.InvarianceManifold(m, _meis(8), device="cpu", widths=[32] * 4, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+    with pytest.raises(NotImplementedError, match="hidden widths"):
+        L.InvarianceManifold(m, _meis(8), device="cpu", widths=[64] * 4, required_img_norm=1.0, pixel_value_lower_bound=-1.0, pixel_value_upper_bound=1.0)
+
+
+def test_narrow_and_non_uniform_widths_are_zero_padded_views(L):
+    """`widths=` below the kernels' 50 (uniform or not; reference inr.py:156-174): the parameters keep the reference's shapes, names and seeded
+    values (same CPU draws, in the same order: nn.Linear constructions, B, auxB, then normal_ per layer, inr.py:49-51,207-211) and are strided
+    views of zero-padded 50-wide blocks of the flat vector the kernels read; state_dict round-trips."""
+    from laminr_b200.inr import INRTemplates
+    from torch import nn
+    widths, C, pe = [32, 20, 50], 2, 50
+    kw = dict(out_channels=C, periodic_invariance=True, positional_encoding_dim=pe, positional_encoding_projection_scale=10, aux_positional_encoding_dim=pe,
+              aux_positional_encoding_projection_scale=0.1, final_nonlinearity=nn.Tanh, bias=True, weights_scale=0.1)
+    torch.manual_seed(3)
+    t = INRTemplates((8, 8), widths=widths, **kw)
+    # the reference's draw order restated with plain torch
+    torch.manual_seed(3)
+    dims = [1 + 4 * pe] + widths + [C]
+    lin = [nn.Linear(dims[i], dims[i + 1], bias=True) for i in range(len(dims) - 1)]
+    B, auxB = torch.randn(2, pe) * 10, torch.randn(2, pe) * 0.1
+    for m_ in lin:
+        m_.weight.data.normal_(0.0, 0.1), m_.bias.data.fill_(0)
+    assert torch.equal(t.B, B) and torch.equal(t.auxB, auxB)
+    for i, m_ in enumerate(lin):
+        assert torch.equal(getattr(t.func, f"layer{i}").weight, m_.weight) and tuple(getattr(t.func, f"layer{i}").bias.shape) == (dims[i + 1],)
+    flat = t.flat_params()
+    assert flat.numel() == 50 * 201 + 50 + 2 * (2500 + 50) + C * 50 + C and t._desc.hidden == 50 and t._desc.n_hidden == 3
+    assert sum(p.numel() for p in t.func.parameters()) == sum(dims[i] * dims[i + 1] + dims[i + 1] for i in range(len(dims) - 1))
+    blk = flat[50 * 201 + 50: 50 * 201 + 50 + 2500].view(50, 50)            # layer 1: [20, 32] in the corner of a zero [50, 50] block
+    assert torch.equal(blk[:20, :32], lin[1].weight) and float(blk[20:].abs().sum()) == 0 and float(blk[:, 32:].abs().sum()) == 0
+    assert float(flat.abs().sum()) == pytest.approx(float(sum(m_.weight.abs().sum() for m_ in lin)), rel=1e-5)
+    flat[50 * 201 + 50] = 7.0                                                 # the parameters ARE views of the flat vector
+    assert t.func.layer1.weight[0, 0].item() == 7.0 and t.flat_params().data_ptr() == flat.data_ptr()
+    torch.manual_seed(4)
+    t2 = INRTemplates((8, 8), widths=widths, **kw)
+    t2.flat_params()
+    t2.load_state_dict(t.state_dict())
+    assert torch.equal(t2.flat_params(), flat) and [k for k in t.state_dict()] == [k for k in t2.state_dict()]
 
 
 def test_torch_library_operators_are_registered(L):
