@@ -302,6 +302,68 @@ int lmr_create_mask(const float* mei, int G, int H, int W, float zscore_thresh, 
 int lmr_gaussian_blur(const float* x, int B, int H, int W, const float* wy, int hy, const float* wx, int hx,
                       int pad_mode, float inv_norm, float* out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Full-frame conv response model -- every neuron's response to every image, and the gradient of sum(g_act * act) back to the
+ * images.  Replaces, in eval mode, the reference's per-call module chains
+ *   SE2dCore.forward (laminr/neuron_models/utils/monkey_model.py:114-317: first convolution, DepthSeparableConv2d hidden layers
+ *   neuralpredictors/layers/conv.py:4-30 with dilation, BatchNorm, ELU, SQ_EX_Block :95-108) or Stacked2dCore.forward
+ *   (neuralpredictors/layers/cores/conv2d.py:246-253)
+ *   -> PointPooled2d.forward (neuralpredictors/layers/readouts/point_pooled.py:121-169) or eval-mode FullGaussian2d.forward
+ *   (readouts/gaussian.py:532-581; = one scale)
+ *   -> elu(. + offset) + 1 (laminr/neuron_models/monkey_models.py:292-294, neuralpredictors/layers/encoders/firing_rate.py:36-52)
+ * and torch autograd's gradient with respect to the images (parameters frozen).  This is the path for models whose layers pool over
+ * the whole frame (squeeze-excitation) and for `model(x)` of all neurons; lmr_convcore_response stays the single-neuron cone path.
+ *
+ * Layers (stride 1 everywhere); after every convolution optionally  v*scale[c] + shift[c]  (eval-mode batch norm + conv bias folded)
+ * and  elu(v - elu_xshift) + elu_yshift:
+ *   LMR_FF_DENSE      conv2d, dilation 1, zero padding `pad`.  Weights packed for the kernel: CO = (c_out % 4 == 0 ? 4 : 1),
+ *                     kp = k rounded up to 8,  w_fwd [c_in][c_out / CO][k][kp][CO] = conv.weight[co][ci][ky][kx] (0 for kx >= k);
+ *                     w_bwd = the same packing of the transposed, flipped kernel  w'[ci][co][ky][kx] = w[co][ci][k-1-ky][k-1-kx]
+ *                     (roles of c_in / c_out swapped).
+ *   LMR_FF_DEPTHWISE  groups = channels, dilation 1 or 2, k in {3,5,7,9}; w_fwd [c][k][k], w_bwd = flipped.
+ *   LMR_FF_POINTWISE  1 x 1 convolution; w_fwd [c_in][c_out] (= weight^T), w_bwd [c_out][c_in] (= weight).
+ *   LMR_FF_SE         x * sigmoid(W2 relu(W1 mean_hw(x) + b1) + b2); se_w1 [se_hidden][c], se_w2 [c][se_hidden].
+ * w_bwd may be NULL for forward-only use.
+ * Readout: n_scales feature maps (the last layer's output and n_scales - 1 average poolings k = stride = pool_kern of it); neuron n
+ * reads every map bilinearly at grid[n] (x -> width, y -> height, clamped to [-1,1]) and dots the n_scales * C values with
+ * features[n][:] (scale-major), + bias[n];  act [B, n_neurons] = elu(. + elu_offset) + 1.
+ * lmr_ff_forward leaves the layer outputs in the workspace; lmr_ff_backward must follow it with the same net, B and workspace:
+ *   g_img [B, c_in, H, W] = d sum(g_act * act) / d img   (overwritten).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define LMR_FF_MAX_LAYERS 16
+enum { LMR_FF_DENSE = 0, LMR_FF_DEPTHWISE = 1, LMR_FF_POINTWISE = 2, LMR_FF_SE = 3 };
+typedef struct {
+    int kind;
+    int c_in, c_out;
+    int k, dilation, pad;
+    int affine, elu;
+    float elu_xshift, elu_yshift;
+    int se_hidden;
+    const float* w_fwd;
+    const float* w_bwd;
+    const float* scale;
+    const float* shift;
+    const float* se_w1;
+    const float* se_b1;
+    const float* se_w2;
+    const float* se_b2;
+} lmr_ff_layer;
+
+typedef struct {
+    int n_layers;
+    int c_in, height, width;
+    int n_neurons, n_scales, pool_kern, align_corners;
+    float elu_offset;
+    const float* grid;     /* [n_neurons, 2] */
+    const float* features; /* [n_neurons, n_scales * C] */
+    const float* bias;     /* [n_neurons] or NULL */
+    lmr_ff_layer layers[LMR_FF_MAX_LAYERS];
+} lmr_ff_net;
+
+size_t lmr_ff_workspace_bytes(const lmr_ff_net* net, int B);
+int lmr_ff_forward(const lmr_ff_net* net, const float* img, int B, float* act, void* workspace, size_t workspace_bytes, void* stream);
+int lmr_ff_backward(const lmr_ff_net* net, const float* g_act, int B, float* g_img, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

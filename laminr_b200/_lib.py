@@ -33,6 +33,22 @@ class ConvcoreWeights(C.Structure):
                 ("shift", C.c_void_p * CONV_MAX_LAYERS), ("mu", C.c_void_p), ("features", C.c_void_p), ("bias", C.c_void_p)]
 
 
+FF_MAX_LAYERS = 16
+FF_DENSE, FF_DEPTHWISE, FF_POINTWISE, FF_SE = 0, 1, 2, 3
+
+
+class FFLayer(C.Structure):
+    _fields_ = [("kind", C.c_int), ("c_in", C.c_int), ("c_out", C.c_int), ("k", C.c_int), ("dilation", C.c_int), ("pad", C.c_int), ("affine", C.c_int),
+                ("elu", C.c_int), ("elu_xshift", C.c_float), ("elu_yshift", C.c_float), ("se_hidden", C.c_int), ("w_fwd", C.c_void_p), ("w_bwd", C.c_void_p),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("se_w1", C.c_void_p), ("se_b1", C.c_void_p), ("se_w2", C.c_void_p), ("se_b2", C.c_void_p)]
+
+
+class FFNet(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("c_in", C.c_int), ("height", C.c_int), ("width", C.c_int), ("n_neurons", C.c_int), ("n_scales", C.c_int),
+                ("pool_kern", C.c_int), ("align_corners", C.c_int), ("elu_offset", C.c_float), ("grid", C.c_void_p), ("features", C.c_void_p),
+                ("bias", C.c_void_p), ("layers", FFLayer * FF_MAX_LAYERS)]
+
+
 _vp, _i, _f, _sz, _ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 
 # name -> (restype, argtypes): one entry per symbol declared in include/laminr_b200.h
@@ -54,6 +70,9 @@ SIGNATURES = {
     "lmr_constrain_bwd": (_i, [_i, _vp, _vp, _vp, _i, _i, _f, _f, _i, _f, _i, _f, _f, _vp, _vp, _sz, _vp]),
     "lmr_ascent_update": (_i, [_i, _vp, _vp, _f, _i, _i, _f, _f, _i, _f, _i, _f, _f, _vp, _sz, _vp]),
     "lmr_convcore_response": (_i, [C.POINTER(ConvcoreDesc), C.POINTER(ConvcoreWeights), _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _i, _vp]),
+    "lmr_ff_workspace_bytes": (_sz, [C.POINTER(FFNet), _i]),
+    "lmr_ff_forward": (_i, [C.POINTER(FFNet), _vp, _i, _vp, _vp, _sz, _vp]),
+    "lmr_ff_backward": (_i, [C.POINTER(FFNet), _vp, _i, _vp, _vp, _sz, _vp]),
     "lmr_simresp_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "lmr_simresp_fwd": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
     "lmr_simresp_bwd": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _i, _vp, _i, _vp, _vp, _i, _vp]),

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-SOURCES = ["api.cu", "inr_simt.cu", "inr_tc.cu", "post.cu", "learn_obj.cu", "convcone.cu", "mask.cu"]
+SOURCES = ["api.cu", "inr_simt.cu", "inr_tc.cu", "post.cu", "learn_obj.cu", "convcone.cu", "fullframe.cu", "mask.cu"]
 OBJ_DIR = os.path.join(HERE, "_obj")  # git-ignored object cache: only changed translation units are recompiled
 OUT = os.path.join(os.path.dirname(HERE), "liblaminr_b200.so")
 

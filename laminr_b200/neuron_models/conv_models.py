@@ -12,8 +12,8 @@ configuration (depth-separable / attention convolutions, skip > 1, grid predicto
 
 On a CUDA device `FiringRateEncoder` evaluates responses with lmr_convcore_response (csrc/convcone.cu): one CTA per (image, neuron) pair
 runs the receptive-field cone of the selected neuron through all layers in shared memory and returns the response and its image gradient
-in one launch.  `forward_neurons(x, idxs)` (what SingleNeuronModel / the fused steppers / the batched MEI ascent use) and `forward(x)`
-(all neurons) both go through that kernel.  There is NO stock-PyTorch / CPU evaluation path: the classes below only build and hold the
+in one launch: `forward_neurons(x, idxs)`, what SingleNeuronModel / the fused steppers / the batched MEI ascent use.  `forward(x)` (all neurons)
+runs the whole frame through the core once with lmr_ff_forward / lmr_ff_backward (csrc/fullframe.cu) and reads every neuron out of that.  There is NO stock-PyTorch / CPU evaluation path: the classes below only build and hold the
 parameters (same names, shapes and RNG draw order as the reference, so a reference state_dict loads unchanged); CPU tensors raise, and
 configurations the kernel does not cover (non-"same" padding, stride/dilation != 1, more than the last layer stacked, training mode) raise
 NotImplementedError instead of silently falling back.
@@ -164,7 +164,7 @@ class FiringRateEncoder(nn.Module):
         if shifter is not None or modulator is not None:
             raise NotImplementedError("laminr_b200 FiringRateEncoder: shifter / modulator branches are not mirrored")
         self.core, self.readout, self.shifter, self.modulator, self.offset = core, readout, None, None, elu_offset
-        self._cone, self._cone_sig = None, None
+        self._cone, self._cone_sig, self._ff, self._ff_sig = None, None, None, None
         self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.refresh_cone())
 
     # ---- B200 path --------------------------------------------------------------------------------------------------
@@ -184,14 +184,14 @@ class FiringRateEncoder(nn.Module):
         return self._cone
 
     def refresh_cone(self):
-        self._cone = None
+        self._cone = self._ff = None
 
     def _apply(self, fn, *args, **kwargs):
-        self._cone = None
+        self._cone = self._ff = None
         return super()._apply(fn, *args, **kwargs)
 
     def train(self, mode=True):
-        self._cone = None
+        self._cone = self._ff = None
         return super().train(mode)
 
     def _build_cone(self):
@@ -230,11 +230,40 @@ class FiringRateEncoder(nn.Module):
         nog = torch.as_tensor(list(idxs), dtype=torch.int32, device=x.device)
         return ops.convresp(x, cone, nog).t()  # raises on CPU tensors: no fallback
 
+    def full_frame(self):
+        """The lmr_ff_forward weight pack (csrc/fullframe.cu): the whole frame through the core once, every neuron read out in one launch.  Cached and
+        invalidated like `cone()`."""
+        from .. import ops
+        sig = self._state_signature()
+        if self._ff is None or sig != self._ff_sig:
+            if self.training:
+                raise NotImplementedError("laminr_b200: the full-frame kernels implement EVAL mode; call model.eval() first")
+            core, ro = self.core, self.readout
+            if list(core.stack) != [len(core.features) - 1]:
+                raise NotImplementedError("laminr_b200: only stack=-1 (last layer read out) is covered by the full-frame kernels")
+            specs = []
+            for feat in core.features:
+                conv = feat.conv
+                if tuple(conv.stride) != (1, 1) or tuple(conv.dilation) != (1, 1) or conv.groups != 1 or conv.kernel_size[0] != conv.kernel_size[1] \
+                        or conv.padding[0] != conv.padding[1]:
+                    raise NotImplementedError("laminr_b200: the full-frame kernels cover stride-1, dilation-1 square convolutions for this core")
+                n = getattr(feat, "norm", None)
+                specs.append(dict(kind="dense", weight=conv.weight, pad=conv.padding[0], conv_bias=conv.bias,
+                                  bn=None if n is None else (n.running_mean, n.running_var, n.weight, n.bias, n.eps),
+                                  elu=(core.elu_xshift, core.elu_yshift) if hasattr(feat, "nonlin") else None))
+            with torch.no_grad():
+                ro._mu.clamp_(min=-1, max=1)
+            c, h, w = ro.in_shape
+            self._ff = ops.FullFrameNet(specs, (core.input_channels, h, w), ro._mu, ro._features, ro.bias, offset=self.offset, align_corners=ro.align_corners)
+            self._ff_sig = self._state_signature()
+        return self._ff
+
     def forward(self, inputs, *args, shift=None, detach_core=False, **kwargs):
-        """firing_rate.py:36-52: elu(readout(core(x)) + offset) + 1 for all neurons -> [B, n]."""
+        """firing_rate.py:36-52: elu(readout(core(x)) + offset) + 1 for all neurons -> [B, n]; one full-frame evaluation of the core."""
+        from .. import ops
         if shift is not None or detach_core:
             raise NotImplementedError("laminr_b200: shift / detach_core are not covered by the conv-core kernel")
-        return self.forward_neurons(inputs, range(self.readout.outdims))
+        return ops.fullframe_response(inputs, self.full_frame())
 
 
 def export_arrays(model):

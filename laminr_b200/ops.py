@@ -446,6 +446,178 @@ def convresp(x, cone, neuron_of_group):
     return _ConvResp.apply(x, cone, neuron_of_group)
 
 
+def fold_affine(c_out, conv_bias=None, bn=None, device=None):
+    """Eval-mode batch norm (running_mean, running_var, gamma|None, beta|None, eps) + convolution bias folded into v*scale + shift (float64 on
+    the way, like the oracle).  Returns (None, None) when there is neither."""
+    if conv_bias is None and bn is None:
+        return None, None
+    scale, shift = torch.ones(c_out, dtype=torch.float64, device=device), torch.zeros(c_out, dtype=torch.float64, device=device)
+    if conv_bias is not None:
+        shift = shift + conv_bias.detach().double()
+    if bn is not None:
+        rm, rv, gamma, beta, eps = bn
+        scale = 1.0 / torch.sqrt(rv.detach().double() + eps)
+        if gamma is not None:
+            scale = scale * gamma.detach().double()
+        shift = (shift - rm.detach().double()) * scale
+        if beta is not None:
+            shift = shift + beta.detach().double()
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+def _pack_dense(W):
+    """[co, ci, k, k] -> the [ci][co / CO][k][kp][CO] layout of LMR_FF_DENSE (include/laminr_b200.h)."""
+    co, ci, k, _ = W.shape
+    CO, kp = (4 if co % 4 == 0 else 1), (k + 7) // 8 * 8
+    Wp = torch.zeros(co, ci, k, kp, dtype=torch.float32, device=W.device)
+    Wp[..., :k] = W
+    return Wp.reshape(co // CO, CO, ci, k, kp).permute(2, 0, 3, 4, 1).contiguous()
+
+
+class FullFrameNet:
+    """Device-side weight pack + lmr_ff_net descriptor of a frozen, eval-mode conv response model, in the layouts lmr_ff_forward / lmr_ff_backward
+    read (include/laminr_b200.h).  `layers`: list of dicts
+        dict(kind="dense"|"depthwise"|"pointwise", weight=conv.weight, pad=, dilation=, conv_bias=|None, bn=(mean, var, gamma, beta, eps)|None,
+             elu=(xshift, yshift)|None)
+        dict(kind="se", w1=[r,c], b1=[r], w2=[c,r], b2=[c])
+    readout: grid [n,2] (or any shape with n*2 elements), features [n_scales*C, n] (scale-major rows, the reference's layout), bias [n]|None."""
+
+    def __init__(self, layers, in_shape, grid, features, bias, n_scales=1, pool_kern=1, offset=0.0, align_corners=True, need_grad=True):
+        _require_cuda(grid, features)
+        if not 1 <= len(layers) <= _lib.FF_MAX_LAYERS:
+            raise ValueError(f"FullFrameNet: 1..{_lib.FF_MAX_LAYERS} layers supported")
+        net = _lib.FFNet()
+        self.keep = []
+        dev = grid.device
+        hold = lambda t: (self.keep.append(t), t.data_ptr())[1]
+        f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        net.n_layers = len(layers)
+        net.c_in, net.height, net.width = (int(v) for v in in_shape)
+        c = net.c_in
+        for l, L in enumerate(layers):
+            d = net.layers[l]
+            kind = L["kind"]
+            d.c_in, d.dilation, d.k = c, 1, 1
+            if kind == "se":
+                w1, b1, w2, b2 = f32(L["w1"]), f32(L["b1"]), f32(L["w2"]), f32(L["b2"])
+                if w1.shape[1] != c or tuple(w2.shape) != (c, w1.shape[0]):
+                    raise ValueError(f"FullFrameNet layer {l}: squeeze-excitation weights do not match {c} channels")
+                d.kind, d.c_out, d.se_hidden = _lib.FF_SE, c, w1.shape[0]
+                d.se_w1, d.se_b1, d.se_w2, d.se_b2 = hold(w1), hold(b1), hold(w2), hold(b2)
+                continue
+            W = f32(L["weight"])
+            co, cig, k, k2 = W.shape
+            if k != k2:
+                raise ValueError(f"FullFrameNet layer {l}: square kernels only")
+            d.c_out, d.k, d.pad, d.dilation = co, k, int(L.get("pad", 0)), int(L.get("dilation", 1))
+            if kind == "dense":
+                if cig != c:
+                    raise ValueError(f"FullFrameNet layer {l}: {cig} input channels, {c} expected")
+                d.kind = _lib.FF_DENSE
+                d.w_fwd = hold(_pack_dense(W))
+                if need_grad:
+                    d.w_bwd = hold(_pack_dense(W.flip(2, 3).transpose(0, 1).contiguous()))
+            elif kind == "depthwise":
+                if cig != 1 or co != c:
+                    raise ValueError(f"FullFrameNet layer {l}: depthwise convolution needs groups == channels")
+                d.kind = _lib.FF_DEPTHWISE
+                d.w_fwd = hold(W.reshape(co, k, k).contiguous())
+                if need_grad:
+                    d.w_bwd = hold(W.flip(2, 3).reshape(co, k, k).contiguous())
+            elif kind == "pointwise":
+                if cig != c or k != 1:
+                    raise ValueError(f"FullFrameNet layer {l}: pointwise convolution needs a 1 x 1 kernel over {c} channels")
+                d.kind = _lib.FF_POINTWISE
+                d.w_fwd = hold(W.reshape(co, cig).t().contiguous())
+                if need_grad:
+                    d.w_bwd = hold(W.reshape(co, cig).contiguous())
+            else:
+                raise ValueError(f"FullFrameNet layer {l}: unknown kind {kind!r}")
+            scale, shift = fold_affine(co, L.get("conv_bias"), L.get("bn"), device=dev)
+            if scale is not None:
+                d.affine, d.scale, d.shift = 1, hold(scale), hold(shift)
+            if L.get("elu") is not None:
+                d.elu, d.elu_xshift, d.elu_yshift = 1, float(L["elu"][0]), float(L["elu"][1])
+            c = co
+        self.grid = f32(grid).reshape(-1, 2).clamp(-1, 1).contiguous()
+        n = self.grid.shape[0]
+        feats = f32(features).reshape(-1, n)
+        if feats.shape[0] != n_scales * c:
+            raise ValueError(f"FullFrameNet: features have {feats.shape[0]} rows, {n_scales} scales x {c} channels expected")
+        self.features = feats.t().contiguous()
+        self.bias = None if bias is None else f32(bias)
+        net.n_neurons, net.n_scales, net.pool_kern, net.align_corners = n, int(n_scales), int(pool_kern), int(bool(align_corners))
+        net.elu_offset = float(offset)
+        net.grid, net.features, net.bias = self.grid.data_ptr(), self.features.data_ptr(), (self.bias.data_ptr() if self.bias is not None else None)
+        self.net, self.device, self.n_neurons, self.need_grad = net, dev, n, need_grad
+        self.in_shape = (net.c_in, net.height, net.width)
+        self._ws = {}
+
+    def workspace(self, B):
+        ws = self._ws.get(B)
+        if ws is None:
+            nbytes = _lib.load().lmr_ff_workspace_bytes(C.byref(self.net), int(B))
+            if nbytes == 0:
+                raise _lib.LaminrB200Error("laminr_b200: " + _lib.load().lmr_last_error().decode())
+            self._ws = {B: _workspace(nbytes, self.device)}  # one batch size at a time
+            ws = self._ws[B]
+        return ws
+
+
+def raw_ff_forward(net, img, act=None):
+    """act [B, n_neurons] of every neuron on every image; the layer outputs stay in net.workspace(B) for raw_ff_backward."""
+    lib = _lib.load()
+    _require_cuda(img)
+    if tuple(img.shape[1:]) != net.in_shape:
+        raise ValueError(f"expected images [B,{net.in_shape[0]},{net.in_shape[1]},{net.in_shape[2]}], got {tuple(img.shape)}")
+    B = img.shape[0]
+    ws = net.workspace(B)
+    if act is None:
+        act = torch.empty((B, net.n_neurons), dtype=torch.float32, device=img.device)
+    check(lib.lmr_ff_forward(C.byref(net.net), _ptr(img), B, _ptr(act), _ptr(ws), ws.numel(), _stream()))
+    return act
+
+
+def raw_ff_backward(net, g_act, g_img):
+    """g_img [B, C, H, W] = d sum(g_act * act) / d img of the forward that last used net.workspace(B)."""
+    lib = _lib.load()
+    _require_cuda(g_act, g_img)
+    B = g_act.shape[0]
+    ws = net.workspace(B)
+    check(lib.lmr_ff_backward(C.byref(net.net), _ptr(g_act), B, _ptr(g_img), _ptr(ws), ws.numel(), _stream()))
+    return g_img
+
+
+class _FullFrameResp(torch.autograd.Function):
+    """x [B,C,H,W] -> act [B, n_neurons]; gradient wrt x only (the response model is frozen)."""
+
+    @staticmethod
+    def forward(ctx, x, net):
+        x = _f32c(x)
+        ctx.net, ctx.shape = net, x.shape
+        net._fwd_serial = getattr(net, "_fwd_serial", 0) + 1
+        ctx.serial = net._fwd_serial
+        ctx.save_for_backward(x)
+        return raw_ff_forward(net, x)
+
+    @staticmethod
+    def backward(ctx, g_act):
+        net = ctx.net
+        (x,) = ctx.saved_tensors
+        if not net.need_grad:
+            raise RuntimeError("laminr_b200: this FullFrameNet was packed without gradient weights")
+        if ctx.serial != net._fwd_serial:  # another forward overwrote the kept layer outputs: run this one again
+            raw_ff_forward(net, x)
+            net._fwd_serial += 1
+        g_img = torch.empty(ctx.shape, dtype=torch.float32, device=g_act.device)
+        raw_ff_backward(net, _f32c(g_act), g_img)
+        return g_img, None
+
+
+def fullframe_response(x, net):
+    return _FullFrameResp.apply(x, net)
+
+
 def raw_ascent_update(mode, x, g, step_size, target, mean, pmin, pmax, eps=1e-9, workspace=None):
     """x <- clip(renorm(x + step_size*g)) in place; x, g: [B, ...]."""
     lib = _lib.load()

@@ -243,7 +243,7 @@ def _ctype_of(decl):
     from laminr_b200 import _lib
     if "*" in decl:
         for struct, ct in (("lmr_inr_desc", _lib.InrDesc), ("lmr_affine", _lib.Affine), ("lmr_convcore_desc", _lib.ConvcoreDesc),
-                           ("lmr_convcore_weights", _lib.ConvcoreWeights)):
+                           ("lmr_convcore_weights", _lib.ConvcoreWeights), ("lmr_ff_net", _lib.FFNet)):
             if re.search(rf"\b{struct}\b", decl):
                 return ctypes.POINTER(ct)
         return ctypes.c_char_p if re.match(r"const char\s*\*$", decl) else ctypes.c_void_p
@@ -393,3 +393,27 @@ def test_torch_library_operators_are_registered(L):
                                                 torch.empty(3, 2, device="cuda"), torch.empty(3, 1, 2, device="cuda"), None, None, None, True, 50, 4, 50, 50, 1,
                                                 "fp32")
         assert img.shape == (3, 20, 1, 100)
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """sizeof / field offsets of every struct passed by pointer through the C ABI, as gcc lays out include/laminr_b200.h, against the ctypes mirrors."""
+    import subprocess
+    from laminr_b200 import _lib
+    pairs = [("lmr_inr_desc", _lib.InrDesc), ("lmr_affine", _lib.Affine), ("lmr_convcore_desc", _lib.ConvcoreDesc), ("lmr_convcore_weights", _lib.ConvcoreWeights),
+             ("lmr_ff_layer", _lib.FFLayer), ("lmr_ff_net", _lib.FFNet)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "laminr_b200.h"', "int main(void) {"]
+    for cname, ct in pairs:
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for (cname, ct), line in zip(pairs, got):
+        nums = [int(v) for v in line.split()[1:]]
+        assert nums[0] == ctypes.sizeof(ct), (cname, nums[0], ctypes.sizeof(ct))
+        assert nums[1:] == [getattr(ct, f).offset for f, _ in ct._fields_], cname
