@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_LATENTS = 20
-TRAFFIC_BWD_KEEP = 164783360 + 4096768  # dram read + write of inr_bwd_tc_kernel with kept activations (profiles/r1e_ncu_inr_keep.md)
+TRAFFIC_BWD_KEEP = 165600000 + 3900000  # dram read + write of inr_bwd_pp_kernel (kept activations; profiles/r2a_ncu_bwd_pp.md)
 
 
 def algorithmic_flops(res, N=N_LATENTS, h=50, pe=50, C=1):
@@ -579,10 +579,16 @@ def run_ours(args):
     t = im.template
     gx = stepper.g_x.view(1, N_LATENTS, 1, res * res)
     keep = bool(getattr(stepper, "keep", False))  # as in the step: the forward keeps the hidden activations' operand tiles, the backward loads them
+    fused_tail = keep and hasattr(stepper, "step_count")  # the step's own call: tile kernel + ONE cooperative tail launch (reductions + Adam)
     def bwd_only():
-        ops.raw_inr_backward(t._desc, stepper.flat, t.B, t.auxB, stepper.grid, stepper.coords, None, None, gx, want_params=True,
-                             precision=args.precision, workspace=stepper.ws_bwd, g_params=stepper.g_flat,
-                             forward_workspace=stepper.ws_fwd if keep else None, keep_activations=keep)
+        if fused_tail:
+            ops.raw_inr_backward_adam(t._desc, stepper.flat, t.B, t.auxB, stepper.grid, stepper.coords, None, gx, stepper.g_flat, stepper.m, stepper.v,
+                                      stepper.step_count, lr=stepper.lr, precision=args.precision, workspace=stepper.ws_bwd, forward_workspace=stepper.ws_fwd,
+                                      keep_activations=keep)
+        else:
+            ops.raw_inr_backward(t._desc, stepper.flat, t.B, t.auxB, stepper.grid, stepper.coords, None, None, gx, want_params=True,
+                                 precision=args.precision, workspace=stepper.ws_bwd, g_params=stepper.g_flat,
+                                 forward_workspace=stepper.ws_fwd if keep else None, keep_activations=keep)
     def fwd_only():
         ops.raw_inr_forward(t._desc, stepper.flat, t.B, t.auxB, stepper.grid, stepper.coords, None, None, out=stepper.img_pre.view(1, N_LATENTS, 1, res * res),
                             precision=args.precision, workspace=stepper.ws_fwd, keep_activations=keep)
@@ -607,7 +613,11 @@ def run_ours(args):
             tot += a.elapsed_time(b)
         return tot / reps
     fwd_ms = time_fn(fwd_only)
-    bwd_ms = time_fn(bwd_only)
+    saved = [x.clone() for x in (stepper.flat, stepper.m, stepper.v, stepper.step_count)] if fused_tail else None  # the fused tail applies Adam: put the
+    bwd_ms = time_fn(bwd_only)                                                                                    # template back afterwards
+    if saved is not None:
+        for dst, src in zip((stepper.flat, stepper.m, stepper.v, stepper.step_count), saved):
+            dst.copy_(src)
 
     # ---- demo1 learn step at the second BASELINE resolution (200x200), back to back from the CUDA graph (rank 0)
     big = None
@@ -804,11 +814,12 @@ def run_ours(args):
             "back_to_back": {"value": world * K / (b2b_ms / 1e3), "unit": "steps/s", "ms_per_step": b2b_ms / K, "note": "K graph replays in one event pair, no L2 flush (the loop as it runs)"},
             "e2e": {"value": world * K / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": 4 * N_LATENTS, "d2h_bytes_per_step": 4},
             "gpu_launches": int(stepper.kernels_per_step * K),
-            "roofline": {"bound": "tensor", "kernel": "lmr_inr_backward launch group (inr_bwd_tc_kernel dominant; + layer-0 weight gradient and partial reduction launches)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "kernel": ("lmr_inr_backward_adam launch group: inr_bwd_pp_kernel (dominant) + learn_tail_kernel (layer-0 weight gradient, partial reductions, Adam)"
+                                                       if fused_tail else "lmr_inr_backward launch group (tile kernel + layer-0 weight gradient and partial reduction launches)"), "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved / peak_tf,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of inr_bwd_tc_kernel, one `ncu --set full` capture of this workload:
+                         # dram__bytes_read.sum + dram__bytes_write.sum of the tile kernel, one `ncu --set full` capture of this workload:
                          # recompute variant 2.995 MB (profiles/r1b_ncu_inr_bwd_tc.md); kept-activation variant: the 160 MB of operand tiles it loads
-                         # (profiles/r1e_ncu_inr_keep.md)
+                         # (profiles/r2a_ncu_bwd_pp.md)
                          "traffic": (TRAFFIC_BWD_KEEP if keep else 2995456) if (res == 100 and args.precision != "fp32") else None,
                          "traffic_unit": "bytes per launch (ncu, DRAM)", "kept_activations": keep,
                          "peak_source": "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback",
