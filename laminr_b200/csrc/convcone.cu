@@ -37,17 +37,19 @@ __host__ __device__ inline int flat_items(int So, int Co) {
     return So * ((So + xb - 1) / xb) * (Co / cb);
 }
 
-struct Plan {
-    int S[MAXL];  // output window edge of layer l
-    int Sin;      // input window edge
+struct Plan {  // built on the host, handed to the kernel inside Args (parameter space: indexed without a local-memory copy)
+    int S[MAXL];     // output window edge of layer l
+    int halo[MAXL];  // window origin of layer l's output = top-left readout tap - halo[l]  (sum of k/2 of the layers above)
+    int halo_in;     // the same for the input window
+    int Sin;         // input window edge
     int off_in, off_a[MAXL], off_g[MAXL], off_gin, off_scratch, total;  // float offsets into dynamic shared memory
 };
 
 __host__ __device__ inline void make_plan(const lmr_convcore_desc& d, bool with_grad, Plan& p) {
     const int L = d.n_layers;
-    p.S[L - 1] = 2;
-    for (int l = L - 2; l >= 0; --l) p.S[l] = p.S[l + 1] + d.kernel[l + 1] - 1;
-    p.Sin = p.S[0] + d.kernel[0] - 1;
+    p.S[L - 1] = 2, p.halo[L - 1] = 0;
+    for (int l = L - 2; l >= 0; --l) p.S[l] = p.S[l + 1] + d.kernel[l + 1] - 1, p.halo[l] = p.halo[l + 1] + d.kernel[l + 1] / 2;
+    p.Sin = p.S[0] + d.kernel[0] - 1, p.halo_in = p.halo[0] + d.kernel[0] / 2;
     int off = 0;
     auto take = [&](int n) { int o = off; off += (n + 3) & ~3; return o; };
     p.off_in = take(d.c_in * p.Sin * p.Sin);
@@ -83,6 +85,7 @@ struct Args {
     float* act;
     float* g_img;  // nullable
     int accumulate;
+    Plan pl;
 };
 
 // Partial sums of a stride-1 correlation: out[co, y, x] = sum_{ci in split, ky, kx} in[ci, y + ky - vp, x + kx - vp] * Wt[ci, ky, kx, co], input taken
@@ -271,8 +274,7 @@ __global__ void __launch_bounds__(NT, 1) convcone_kernel(const Args a) {
     const lmr_convcore_desc& d = a.d;
     const int L = d.n_layers, H = d.height, W = d.width, P = H * W, Hc = d.hidden, Cin = d.c_in;
     const bool with_grad = a.g_img != nullptr;
-    Plan pl;
-    make_plan(d, with_grad, pl);
+    const Plan& pl = a.pl;
     const int pair = blockIdx.x / CS;  // (group, image) pair of this cluster
     const int g = pair / a.NB, b = pair - g * a.NB;
     const int neuron = a.neuron_of_group[g];
@@ -295,11 +297,8 @@ __global__ void __launch_bounds__(NT, 1) convcone_kernel(const Args a) {
     const float wx1 = fx - flx, wy1 = fy - fly, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
     if (tid == 0) s_tap[0] = wy0 * wx0, s_tap[1] = wy0 * wx1, s_tap[2] = wy1 * wx0, s_tap[3] = wy1 * wx1;
 
-    // window origins (frame coordinates) of every layer's output and of the input
-    int oy[MAXL], ox[MAXL];
-    oy[L - 1] = Y0, ox[L - 1] = X0;
-    for (int l = L - 2; l >= 0; --l) oy[l] = oy[l + 1] - d.kernel[l + 1] / 2, ox[l] = ox[l + 1] - d.kernel[l + 1] / 2;
-    const int iy0 = oy[0] - d.kernel[0] / 2, ix0 = ox[0] - d.kernel[0] / 2;
+    // window origins (frame coordinates): layer l's output starts at (Y0 - halo[l], X0 - halo[l]), the input window at (iy0, ix0)
+    const int iy0 = Y0 - pl.halo_in, ix0 = X0 - pl.halo_in;
     const int Sin = pl.Sin;
 
     // ---- input window (every CTA of the cluster keeps its own copy)
@@ -322,7 +321,7 @@ __global__ void __launch_bounds__(NT, 1) convcone_kernel(const Args a) {
         conv_dispatch(in, cin, Si, 0, So, Hc, k, a.w.w_fwd[l], scratch, lo, hi, ks);
         __syncthreads();
         reduce_store(cl, CS, scratch, lo, hi, ks, So, Hc, sm + pl.off_a[l], EPI_FWD, a.w.scale[l], a.w.shift[l], d.nonlin[l], d.elu_xshift, d.elu_yshift, nullptr,
-                     oy[l], ox[l], H, W);
+                     Y0 - pl.halo[l], X0 - pl.halo[l], H, W);
         cl.sync();
     }
 
@@ -357,7 +356,7 @@ __global__ void __launch_bounds__(NT, 1) convcone_kernel(const Args a) {
         __syncthreads();
         if (l > 0)
             reduce_store(cl, CS, scratch, lo, hi, ks, So, cout, sm + pl.off_g[l - 1], EPI_BWD, a.w.scale[l - 1], nullptr, d.nonlin[l - 1], d.elu_xshift,
-                         d.elu_yshift, sm + pl.off_a[l - 1], oy[l - 1], ox[l - 1], H, W);
+                         d.elu_yshift, sm + pl.off_a[l - 1], Y0 - pl.halo[l - 1], X0 - pl.halo[l - 1], H, W);
         else
             reduce_store(cl, CS, scratch, lo, hi, ks, So, cout, sm + pl.off_gin, EPI_PLAIN, nullptr, nullptr, 0, 0.f, 0.f, nullptr, 0, 0, H, W);
         cl.sync();
@@ -431,7 +430,7 @@ extern "C" int lmr_convcore_response(const lmr_convcore_desc* desc, const lmr_co
         }
     cone::Args a;
     a.d = d, a.w = *weights, a.img = img, a.group_stride = img_group_stride, a.NB = NB, a.G = G, a.neuron_of_group = neuron_of_group;
-    a.g_act = g_act, a.act = act, a.g_img = g_img, a.accumulate = accumulate;
+    a.g_act = g_act, a.act = act, a.g_img = g_img, a.accumulate = accumulate, a.pl = pl;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(pairs * cs)), cfg.blockDim = dim3(cone::NT), cfg.dynamicSmemBytes = smem, cfg.stream = st;
     cudaLaunchAttribute attr[1];

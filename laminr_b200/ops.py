@@ -71,12 +71,13 @@ def _workspace(nbytes, device):
 # results -> host (result getters, inv_temp_learn_match.py:394-422: `.cpu().data.numpy()`)
 # ------------------------------------------------------------------------------------------------------------------
 _HOST_RING = {}
+HOST_CHUNK_BYTES = 8 << 20
 _HOST_RING_LOCK = __import__("threading").Lock()
 
 
 def _host_ring(dtype, step, nbuf):
-    """The persistent ring of pinned staging buffers (+ its worker pool) for `to_host_numpy`; allocating it (cudaHostAlloc of nbuf x 32 MB) takes
-    ~100 ms, once per process: HostBuffer does it from its background thread, off the caller's path."""
+    """The persistent ring of pinned staging buffers (+ its worker pool) for `to_host_numpy`.  Allocating it is a cudaHostAlloc (~1 ms per MB, once per
+    process) that also stalls kernel launches from other threads while it runs, so the ring is kept small: nbuf x 8 MB chunks still move at PCIe speed."""
     import concurrent.futures as cf
     key = (dtype, step, nbuf)
     with _HOST_RING_LOCK:
@@ -85,7 +86,7 @@ def _host_ring(dtype, step, nbuf):
         return _HOST_RING[key]
 
 
-def to_host_numpy(t, chunk_bytes=32 << 20, nbuf=4, out=None):
+def to_host_numpy(t, chunk_bytes=HOST_CHUNK_BYTES, nbuf=4, out=None):
     """`t.cpu().numpy()` for large device tensors (the [D,N,C,H,W] image blocks of match: 0.8 GB for 1023 targets at 100x100): the device-to-host
     copies run asynchronously through a small ring of persistent pinned buffers while worker threads move finished chunks into the destination
     array (a pageable `.cpu()` of that block takes 0.36 s on the B200 box, the first-touch host copy being the bottleneck; this takes about half).
@@ -93,7 +94,7 @@ def to_host_numpy(t, chunk_bytes=32 << 20, nbuf=4, out=None):
     import numpy as np
 
     nbytes = t.numel() * t.element_size()
-    if not t.is_cuda or nbytes < (chunk_bytes // 4 if out is not None else 4 * chunk_bytes):
+    if not t.is_cuda or nbytes < (chunk_bytes if out is not None else 16 * chunk_bytes):
         host = t.detach().cpu().numpy()
         if out is None:
             return host
@@ -147,7 +148,7 @@ class HostBuffer:
         def touch():
             if dev is not None and torch.cuda.is_available():
                 torch.cuda.set_device(dev)
-                _host_ring(tdtype, (32 << 20) // self.flat.dtype.itemsize, 4)  # the pinned staging ring of to_host_numpy, if this process has none yet
+                _host_ring(tdtype, HOST_CHUNK_BYTES // self.flat.dtype.itemsize, 4)  # the pinned staging ring of to_host_numpy, if this process has none yet
             step = 64 << 20
             for o in range(0, nbytes, step):  # (ctypes releases the GIL for the duration of each call)
                 ctypes.memset(addr + o, 0, min(step, nbytes - o))

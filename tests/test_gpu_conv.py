@@ -265,3 +265,46 @@ def test_conv_batched_mei_ascent_vs_oracle():
         assert fev.shape == (n, iters + 1)
         assert relerr(fev.cpu().numpy(), np.stack(want_f, 1)) < 1e-4
         assert relerr(meis.cpu().numpy(), x) < 1e-4
+
+
+def test_all_neuron_forward_at_config4_size_equals_cone_path():
+    """`model(x)` (all 128 neurons, one full-frame evaluation of the core: csrc/fullframe.cu) against the single-neuron cone kernel
+    (csrc/convcone.cu, pinned by the reference goldens up to 200x200) on BASELINE config 4 shapes, responses and image gradients."""
+    from laminr_b200.neuron_models import conv_core_gaussian_model
+    model = conv_core_gaussian_model((1, 200, 200), n_neurons=128, seed=1)
+    g = torch.Generator().manual_seed(4)
+    with torch.no_grad():
+        model.readout._mu.copy_(torch.rand(1, 128, 1, 2, generator=g) * 2 - 1)
+        model.readout._features.copy_(torch.randn(1, 32, 1, 128, generator=g) * 0.2)
+        model.readout.bias.copy_(torch.randn(128, generator=g) * 0.1)
+        for feat in model.core.features:
+            feat.norm.running_mean.copy_(torch.randn(32, generator=g) * 0.1)
+            feat.norm.running_var.copy_(torch.rand(32, generator=g) + 0.5)
+    model = model.cuda().eval()
+    x = (torch.randn(3, 1, 200, 200, generator=g) * 0.2).cuda().requires_grad_(True)
+    idx = [0, 17, 64, 127]
+    full = model(x)
+    assert full.shape == (3, 128)
+    cone = model.forward_neurons(x, idx)
+    assert relerr(full[:, idx].detach().cpu().numpy(), cone.detach().cpu().numpy()) < TOL_ACT
+    w = torch.randn(3, 4, generator=g).cuda()
+    (g_full,) = torch.autograd.grad((full[:, idx] * w).sum(), x)
+    (g_cone,) = torch.autograd.grad((cone * w).sum(), x)
+    assert relerr(g_full.cpu().numpy(), g_cone.cpu().numpy()) < TOL_GRAD
+    # dense upstream gradient over all neurons: against float64 stock ops on the host
+    import torch.nn.functional as F
+    gw = torch.randn(3, 128, generator=g)
+    (g_all,) = torch.autograd.grad((full * gw.cuda()).sum(), x)
+    xd = x.detach().cpu().double().requires_grad_(True)
+    h = xd
+    for feat in model.core.features:
+        n = feat.norm
+        h = F.conv2d(h, feat.conv.weight.detach().cpu().double(), padding=feat.conv.padding)
+        h = F.elu(F.batch_norm(h, n.running_mean.cpu().double(), n.running_var.cpu().double(), n.weight.detach().cpu().double(), n.bias.detach().cpu().double(),
+                               False, 0.0, n.eps))
+    ro = model.readout
+    y = F.grid_sample(h, ro._mu.detach().cpu().double().expand(3, -1, 1, 2), align_corners=True).squeeze(-1)
+    y = F.elu((y * ro._features.detach().cpu().double().view(1, 32, 128)).sum(1) + ro.bias.detach().cpu().double()) + 1
+    (g_want,) = torch.autograd.grad((y * gw.double()).sum(), xd)
+    assert relerr(full.detach().cpu().numpy(), y.detach().numpy()) < TOL_ACT
+    assert relerr(g_all.cpu().numpy(), g_want.numpy()) < TOL_GRAD
