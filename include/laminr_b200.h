@@ -46,6 +46,11 @@ typedef enum {
  * 163 MB for one 20 x 100 x 100 image set) and the backward loads them with bulk async copies instead of recomputing the forward per tile.  The forward workspace must
  * then have lmr_inr_forward_workspace_bytes_keep(...) bytes. */
 #define LMR_PREC_KEEP_ACTIVATIONS 0x100
+/* Flag, OR-ed into `precision` of lmr_inr_forward (tensor-core modes, learn stage: D == 1 and no affine transform; ignored otherwise): the sin/cos
+ * table of the pixel coordinates that the previous lmr_inr_forward on this workspace left there is reused instead of recomputed.  The caller
+ * guarantees the same desc / B / coords / coord_shift / P as that call (the pixel grid of a learn loop never changes; only the latents and the
+ * parameters do).  Same table, same products: results are bit-identical to a call without the flag. */
+#define LMR_PREC_REUSE_COORD_TABLE 0x200
 
 typedef enum { LMR_CONSTRAIN_NORM = 0, LMR_CONSTRAIN_STD = 1 } lmr_constrain_mode;
 

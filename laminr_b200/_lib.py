@@ -6,6 +6,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblaminr_b200.so")
 
 PREC_FP32, PREC_BF16X3_FAST, PREC_BF16X3 = 0, 1, 2
+PREC_REUSE_COORD_TABLE = 0x200  # flag: the forward reuses the coordinate sin/cos table its previous call left in the workspace (learn stage)
 PREC_KEEP_ACTIVATIONS = 0x100  # flag: the forward keeps the hidden activations' operand tiles for the backward (include/laminr_b200.h)
 MODE_NORM, MODE_STD = 0, 1
 

@@ -81,7 +81,7 @@ extern "C" int lmr_inr_forward(const lmr_inr_desc* desc, const float* params, co
                                const float* coords, int P, const float* coord_shift, const lmr_affine* affine, int D, float* img, void* ws,
                                size_t ws_bytes, int precision, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int mode = precision & ~LMR_PREC_KEEP_ACTIVATIONS;  // the flag is passed on to the tensor-core path, ignored by the fp32 path
+    const int mode = precision & ~(LMR_PREC_KEEP_ACTIVATIONS | LMR_PREC_REUSE_COORD_TABLE);  // the flags are passed on to the tensor-core path, ignored by the fp32 path
     if (mode == LMR_PREC_FP32) return simt::forward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, img, ws, ws_bytes, st);
     if (mode == LMR_PREC_BF16X3_FAST || mode == LMR_PREC_BF16X3)
         return tc::forward(desc, params, B, auxB, grid, N, coords, P, coord_shift, affine, D, img, ws, ws_bytes, precision, st);

@@ -68,6 +68,7 @@ struct Args {
     float* betaG;  // [D*P, 2*pe] sin/cos(coords.B) (tensor-core path, D == 1: consumed by the layer-0 weight-gradient kernel), else null
     unsigned char* hsave;  // [numTiles] kept-activation records (keep_record_bytes: operand-tile images of h_1..h_{nl-1}, then y) written by the forward for the backward (tensor-core path, opt-in), else null
     int want_cp;
+    int reuse_beta;  // betaG already holds this call's table (LMR_PREC_REUSE_COORD_TABLE): the prep blocks load it instead of evaluating sin/cos
     int ppb;       // pixels per l0 / affine-gradient block
     int ppb_prep;  // pixels per prep block (two blocks per SM: the prep blocks are latency-bound)
     // forward
@@ -243,7 +244,17 @@ __global__ void __launch_bounds__(256) prep_all_kernel(Args a) {
         const int total = a.tl.D * a.tl.P;
         const int q0 = (bid - N - 1) * ppb, nq = min(ppb, total - q0);
         const int d0 = q0 / a.tl.P;
-        if (a.has_aff && t < 2 && d0 + t < a.tl.D) affine_consts(a.aff, d0 + t, cst[t]);  // a block usually spans at most two targets
+        const bool reuse = a.reuse_beta != 0;  // the table of this call is already in betaG (same pixel grid as the previous call): load it
+        if (!reuse && a.has_aff && t < 2 && d0 + t < a.tl.D) affine_consts(a.aff, d0 + t, cst[t]);  // a block usually spans at most two targets
+        constexpr int UB = 16;  // the first 4096 table entries of the slice (36 pixels x 100 features at 100x100) are fetched together with W0's block below
+        float bv[UB];
+        if (reuse) {
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int i = t + u * 256;
+                bv[u] = i < nq * nb ? a.betaG[(size_t)q0 * nb + i] : 0.f;
+            }
+        }
         if (t >= 64 && t < 64 + nb) Bsm[t - 64] = a.B[t - 64];
         {
             constexpr int U = 10;
@@ -262,10 +273,18 @@ __global__ void __launch_bounds__(256) prep_all_kernel(Args a) {
             }
         }
         for (int i = t; i < nb * (HP - HID); i += blockDim.x) Wc[(i / (HP - HID)) * HP + HID + i % (HP - HID)] = 0.f;
+        if (reuse) {
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int i = t + u * 256;
+                if (i < ppb * nb) bet[(i % nb) * ppb + i / nb] = bv[u];  // pixel-major -> k-major (pixels past nq: zeros)
+            }
+            for (int i = t + UB * 256; i < ppb * nb; i += 256) bet[(i % nb) * ppb + i / nb] = i < nq * nb ? a.betaG[(size_t)q0 * nb + i] : 0.f;
+        }
         __syncthreads();
         if (bid == N + 1)  // packed transpose W0cT[k][o] of W0's coordinate block (consumed by the match backward)
             for (int i = t; i < nb * HP; i += blockDim.x) a.W0cT[i] = Wc[i];
-        if (t < nq) {  // transformed coordinates of the block's pixels, once per pixel
+        if (!reuse && t < nq) {  // transformed coordinates of the block's pixels, once per pixel
             const int q = q0 + t;
             float loc[10];
             const float* cc = cst[0];
@@ -277,17 +296,18 @@ __global__ void __launch_bounds__(256) prep_all_kernel(Args a) {
             cxy[t] = transformed_coord(a, cc, q % a.tl.P);
         }
         __syncthreads();
-        for (int i = t; i < pe * ppb; i += blockDim.x) {
-            const int m = i / ppb, jj = i % ppb;
-            float sn = 0.f, cs = 0.f;
-            if (jj < nq) {
-                const float2 c = cxy[jj];
-                sincosf(c.x * Bsm[m] + c.y * Bsm[pe + m], &sn, &cs);
+        if (!reuse)
+            for (int i = t; i < pe * ppb; i += blockDim.x) {
+                const int m = i / ppb, jj = i % ppb;
+                float sn = 0.f, cs = 0.f;
+                if (jj < nq) {
+                    const float2 c = cxy[jj];
+                    sincosf(c.x * Bsm[m] + c.y * Bsm[pe + m], &sn, &cs);
+                }
+                bet[m * ppb + jj] = sn, bet[(pe + m) * ppb + jj] = cs;
             }
-            bet[m * ppb + jj] = sn, bet[(pe + m) * ppb + jj] = cs;
-        }
         __syncthreads();
-        if (a.betaG != nullptr) {  // pixel-major copy for the layer-0 weight-gradient kernel (coalesced over k)
+        if (!reuse && a.betaG != nullptr) {  // pixel-major copy for the layer-0 weight-gradient kernel (coalesced over k)
             for (int i = t; i < nq * nb; i += blockDim.x) {
                 const int jj = i / nb, k = i % nb;
                 a.betaG[(size_t)(q0 + jj) * nb + k] = bet[k * ppb + jj];
@@ -939,6 +959,7 @@ static inline int fill_args(Args& a, const Net& nt, const Tiling& tl, const floa
     a.Cpg = reinterpret_cast<float*>(base + wl.Cpg);
     a.betaG = wl.betaG ? reinterpret_cast<float*>(base + wl.betaG) : nullptr;
     a.want_cp = 0;
+    a.reuse_beta = 0;
     a.ppb = wl.ppb;
     static const int prep_bps = getenv("LMR_PREP_BPS") ? atoi(getenv("LMR_PREP_BPS")) : 2;  // prep blocks per SM (tuning knob; measured: 1 -> 22 us, 2 -> 16 us at 100x100)
     a.ppb_prep = choose_ppb(tl.D * tl.P, prep_bps > 0 ? prep_bps : 2);

@@ -2154,7 +2154,8 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
     LMR_CHECK_ARG(N >= 1 && P >= 1 && D >= 1, "inr_forward: bad sizes N=%d P=%d D=%d", N, P, D);
     const Tiling tl = make_tiling(N, P, D, TP_CAP_TC);
     const bool keep_act = (precision & LMR_PREC_KEEP_ACTIVATIONS) != 0;
-    precision &= ~LMR_PREC_KEEP_ACTIVATIONS;
+    const bool reuse_table = (precision & LMR_PREC_REUSE_COORD_TABLE) != 0;
+    precision &= ~(LMR_PREC_KEEP_ACTIVATIONS | LMR_PREC_REUSE_COORD_TABLE);
     const WsLayout wl = ws_layout(nt, tl, false, true, keep_act);
     if (ws_bytes < wl.total) {
         set_error("inr_forward: workspace %zu < %zu bytes%s", ws_bytes, wl.total, keep_act ? " (LMR_PREC_KEEP_ACTIVATIONS: lmr_inr_forward_workspace_bytes_keep)" : "");
@@ -2164,6 +2165,7 @@ int forward(const lmr_inr_desc* desc, const float* params, const float* B, const
     if (int rc = fill_args(a, nt, tl, params, B, auxB, grid, coords, coord_shift, affine, ws, wl)) return rc;
     a.img = img;
     a.want_cp = 1;
+    a.reuse_beta = reuse_table && a.betaG != nullptr && !a.has_aff;  // learn stage: the coordinate sin/cos table of the previous call is still valid
     if (int rc = launch_prep<50>(a, st)) return rc;
     static const bool smem_operands_env = getenv("LMR_FWD_SMEM") != nullptr;  // development switch: operand tiles in shared memory
     const bool smem_operands = smem_operands_env && !keep_act;

@@ -5,6 +5,8 @@ objective, backward, Adam) without autograd, without per-step allocation or host
 from a CUDA graph.  `MatchStepper.step()` is the body of :351-366 for D targets, each neuron evaluated on its own
 images only (the reference evaluates all neurons on all D*N images and keeps the diagonal, :551,:361).
 """
+import os
+
 import torch
 
 from . import _lib
@@ -15,8 +17,6 @@ def _keep_activations(precision, workspace_bytes):
     """Keep the hidden activations' operand tiles between the INR forward and backward of a training step (LMR_PREC_KEEP_ACTIVATIONS)?  Yes on
     the tensor-core precisions when the enlarged forward workspace stays under LMR_KEEP_ACT_MAX_GIB (default 32 GiB of the 180 GB); the backward then
     loads the tiles instead of recomputing the forward.  LMR_KEEP_ACT=0 switches it off."""
-    import os
-
     if os.environ.get("LMR_KEEP_ACT", "1") == "0" or ops.precision_code(precision) == _lib.PREC_FP32:
         return False
     return workspace_bytes <= float(os.environ.get("LMR_KEEP_ACT_MAX_GIB", "32")) * 2 ** 30
@@ -172,6 +172,7 @@ class LearnStepper:
         self.ws_con = _ws(lib.lmr_constrain_workspace_bytes(N, Cc * P), dev)
         self.ws_clr = _ws(lib.lmr_simclr_workspace_bytes(N, Cc, P), dev)
         self.use_graph, self.graph, self.eval_graph = use_graph, None, None
+        self._table_written = False
         self.side = torch.cuda.Stream(device=dev)
         # fused objective (one persistent launch for constraint + response + contrastive, forward and backward) for simulated neurons when it fits
         self.loss_buf = torch.zeros(1, **f32)
@@ -186,11 +187,18 @@ class LearnStepper:
     def set_reg_scale(self, reg_scale):
         self.g_reg.fill_(-float(reg_scale))
 
+    def _table_valid(self):
+        """Has a forward of this stepper already left the coordinate sin/cos table in `ws_fwd`?  The pixel grid, B and the (absent) coordinate shift
+        never change during a learn loop, so every forward after the first one reuses the table (LMR_PREC_REUSE_COORD_TABLE).  The first call
+        of a stepper always runs eagerly (graph capture comes after it), so a captured launch never carries the first-call flag value."""
+        valid, self._table_written = self._table_written, True
+        return valid and os.environ.get("LMR_REUSE_COORD_TABLE", "1") != "0"
+
     # ---- launches -------------------------------------------------------------------------------------------------
     def _forward(self):
         t, c, N, Cc, P = self.t, self.con, self.N, self.C, self.P
         ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, out=self.img_pre.view(1, N, Cc, P),
-                            precision=self.precision, workspace=self.ws_fwd)
+                            precision=self.precision, workspace=self.ws_fwd, reuse_coord_table=self._table_valid())
         ops.raw_constrain_fwd(c.mode, self.img_pre, c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.z, stats=self.stats, workspace=self.ws_con)
         self.resp.forward(self.z, 0, N, 1, Cc, P, self.nog, self.act)
 
@@ -199,7 +207,7 @@ class LearnStepper:
         r = self.reg_mod
         if self.ws_obj is not None:
             ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, out=self.img_pre.view(1, N, Cc, P),
-                                precision=self.precision, workspace=self.ws_fwd, keep_activations=self.keep)
+                                precision=self.precision, workspace=self.ws_fwd, keep_activations=self.keep, reuse_coord_table=self._table_valid())
             ops.raw_learn_objective(c.mode, self.img_pre, c.target, c.mean, c.pmin, c.pmax, c.eps, self.bank, self.model.eps, self.mei_act, self.mask,
                                     r.flat_neighbor_mask_pos, r.flat_neighbor_mask_neg, r.temperature, r.eps, self.g_reg, self.z, self.act.view(-1),
                                     self.reg, self.loss_buf, self.g_x, self.ws_obj, stats=self.stats, rmax=self.resp.rmax.view(-1),
@@ -210,7 +218,7 @@ class LearnStepper:
                                       keep_activations=self.keep)
             return
         ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, out=self.img_pre.view(1, N, Cc, P),
-                            precision=self.precision, workspace=self.ws_fwd, keep_activations=self.keep)
+                            precision=self.precision, workspace=self.ws_fwd, keep_activations=self.keep, reuse_coord_table=self._table_valid())
         ops.raw_constrain_fwd(c.mode, self.img_pre, c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.z, stats=self.stats, workspace=self.ws_con)
         # the response (+ its image gradient -> g_z) and the contrastive forward are independent: run them side by side (the response of a
         # 20-image batch occupies a fraction of the SMs), then add the contrastive gradient on top

@@ -195,10 +195,13 @@ def forward_workspace_bytes(desc, N, P, D, keep_activations=False):
     return int(fn(C.byref(desc), N, P, D))
 
 
-def raw_inr_forward(desc, params, B, auxB, grid, coords, coord_shift, affine, out=None, precision=None, workspace=None, keep_activations=False):
+def raw_inr_forward(desc, params, B, auxB, grid, coords, coord_shift, affine, out=None, precision=None, workspace=None, keep_activations=False,
+                    reuse_coord_table=False):
     """-> img [D, N, C, P] (float32).  params: flat parameter vector (see header); grid [N]; coords [P,2].
     keep_activations (tensor-core precisions): the forward keeps the operand tiles of the hidden activations in `workspace` (size:
-    forward_workspace_bytes(..., keep_activations=True)) for a raw_inr_backward(..., forward_workspace=workspace, keep_activations=True)."""
+    forward_workspace_bytes(..., keep_activations=True)) for a raw_inr_backward(..., forward_workspace=workspace, keep_activations=True).
+    reuse_coord_table (tensor-core precisions, no affine): `workspace` still holds the coordinate sin/cos table of the previous call with the same
+    B / coords / coord_shift (LMR_PREC_REUSE_COORD_TABLE); bit-identical results, no sin/cos evaluation."""
     lib = _lib.load()
     _require_cuda(params, B, auxB, grid, coords)
     N, P = grid.numel(), coords.shape[0]
@@ -210,9 +213,10 @@ def raw_inr_forward(desc, params, B, auxB, grid, coords, coord_shift, affine, ou
     if workspace is None:
         workspace = _workspace(forward_workspace_bytes(desc, N, P, D, keep), params.device)
     aff = affine.struct() if affine is not None else None
+    flags = (_lib.PREC_KEEP_ACTIVATIONS if keep else 0) | (_lib.PREC_REUSE_COORD_TABLE if reuse_coord_table and aff is None and prec != _lib.PREC_FP32 else 0)
     check(lib.lmr_inr_forward(
         C.byref(desc), _ptr(params), _ptr(B), _ptr(auxB), _ptr(grid), N, _ptr(coords), P, _ptr(coord_shift),
-        C.byref(aff) if aff is not None else None, D, _ptr(out), _ptr(workspace), workspace.numel(), prec | (_lib.PREC_KEEP_ACTIVATIONS if keep else 0), _stream(),
+        C.byref(aff) if aff is not None else None, D, _ptr(out), _ptr(workspace), workspace.numel(), prec | flags, _stream(),
     ))
     return out
 

@@ -288,7 +288,7 @@ def test_all_neuron_forward_at_config4_size_equals_cone_path():
     cone = model.forward_neurons(x, idx)
     assert relerr(full[:, idx].detach().cpu().numpy(), cone.detach().cpu().numpy()) < TOL_ACT
     w = torch.randn(3, 4, generator=g).cuda()
-    (g_full,) = torch.autograd.grad((full[:, idx] * w).sum(), x)
+    (g_full,) = torch.autograd.grad((full[:, idx] * w).sum(), x, retain_graph=True)  # `full` is differentiated again below
     (g_cone,) = torch.autograd.grad((cone * w).sum(), x)
     assert relerr(g_full.cpu().numpy(), g_cone.cpu().numpy()) < TOL_GRAD
     # dense upstream gradient over all neurons: against float64 stock ops on the host

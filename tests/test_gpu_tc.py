@@ -186,3 +186,26 @@ def test_two_stream_backward_variant_parity():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"], env=env, cwd=root,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("res", [(12, 10), (100, 100)])
+def test_reused_coordinate_table_is_bit_identical(ops, mode, res):
+    """LMR_PREC_REUSE_COORD_TABLE: the learn loop's second and later forwards take the pixel grid's sin/cos table from the workspace of the previous
+    call instead of evaluating it again (the grid never changes; parameters and latents do): same images, bit for bit, after a parameter change."""
+    d = golden("inr_12x10")
+    desc = desc_for(ops, d, 1)
+    P = res[0] * res[1]
+    coords = dev(O.pixel_coords(res))
+    ws = torch.empty(ops.forward_workspace_bytes(desc, len(d["grid"]), P, 1, True), dtype=torch.uint8, device="cuda")
+    p0 = dev(flat_params(d))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    p1 = p0 + 0.01 * torch.randn(p0.shape, device="cuda", generator=g)
+    grid1 = dev(d["grid"]) + 0.05
+    fwd = lambda p, gr, **kw: ops.raw_inr_forward(desc, p, dev(d["B"]), dev(d["auxB"]), gr, coords, None, None, precision=mode, **kw)
+    want = fwd(p1, grid1).clone()                                  # fresh workspace: evaluates the table
+    fwd(p0, dev(d["grid"]), workspace=ws, keep_activations=True)   # first call on `ws` writes the table
+    got = fwd(p1, grid1, workspace=ws, keep_activations=True, reuse_coord_table=True)
+    assert torch.equal(got, want)
+    got2 = fwd(p1, grid1, workspace=ws, reuse_coord_table=True)    # the evaluation forward (no kept tiles) shares the table
+    assert torch.equal(got2, want)

@@ -417,3 +417,30 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
         nums = [int(v) for v in line.split()[1:]]
         assert nums[0] == ctypes.sizeof(ct), (cname, nums[0], ctypes.sizeof(ct))
         assert nums[1:] == [getattr(ct, f).offset for f, _ in ct._fields_], cname
+
+
+def test_package_modules_have_no_undefined_global_names():
+    """The GPU-only code paths (steppers, sharded drivers) cannot run in the CPU tier: at least every name they load must be bound somewhere in its
+    module (an `os.environ` without `import os` would otherwise surface on the GPU box only)."""
+    import ast
+    import builtins
+    import pathlib
+
+    root = pathlib.Path(__file__).resolve().parent.parent
+    bad = []
+    for f in list((root / "laminr_b200").rglob("*.py")) + [root / "bench.py", root / "__graft_entry__.py"]:
+        tree = ast.parse(f.read_text())
+        bound = set(dir(builtins)) | {"__file__"}
+        for n in ast.walk(tree):
+            if isinstance(n, (ast.Import, ast.ImportFrom)):
+                bound.update((a.asname or a.name).split(".")[0] for a in n.names)
+            elif isinstance(n, (ast.FunctionDef, ast.AsyncFunctionDef, ast.ClassDef)):
+                bound.add(n.name)
+            elif isinstance(n, ast.Name) and isinstance(n.ctx, (ast.Store, ast.Del)):
+                bound.add(n.id)
+            elif isinstance(n, ast.arg):
+                bound.add(n.arg)
+            elif isinstance(n, ast.ExceptHandler) and n.name:
+                bound.add(n.name)
+        bad += [f"{f.relative_to(root)}:{n.lineno} {n.id}" for n in ast.walk(tree) if isinstance(n, ast.Name) and isinstance(n.ctx, ast.Load) and n.id not in bound]
+    assert not bad, bad
