@@ -71,6 +71,7 @@ struct Args {
     int reuse_beta;  // betaG already holds this call's table (LMR_PREC_REUSE_COORD_TABLE): the prep blocks load it instead of evaluating sin/cos
     int ppb;       // pixels per l0 / affine-gradient block
     int ppb_prep;  // pixels per prep block (two blocks per SM: the prep blocks are latency-bound)
+    FastDiv fd_nb, fd_ppb_prep;  // divisions by 2*pe and by ppb_prep in the prep blocks' flattened copy loops
     // forward
     float* img;  // [D,N,C,P]
     // backward
@@ -263,12 +264,16 @@ __global__ void __launch_bounds__(256) prep_all_kernel(Args a) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int i = i0 + u * 256;
-                    w[u] = i < HID * nb ? W0[(size_t)(i / nb) * nt.in_dim + 1 + na + i % nb] : 0.f;
+                    int o, k;
+                    fd_divmod(i, a.fd_nb, &o, &k);
+                    w[u] = i < HID * nb ? W0[(size_t)o * nt.in_dim + 1 + na + k] : 0.f;
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int i = i0 + u * 256;
-                    if (i < HID * nb) Wc[(i % nb) * HP + i / nb] = w[u];
+                    int o, k;
+                    fd_divmod(i, a.fd_nb, &o, &k);
+                    if (i < HID * nb) Wc[k * HP + o] = w[u];
                 }
             }
         }
@@ -277,9 +282,15 @@ __global__ void __launch_bounds__(256) prep_all_kernel(Args a) {
 #pragma unroll
             for (int u = 0; u < UB; ++u) {
                 const int i = t + u * 256;
-                if (i < ppb * nb) bet[(i % nb) * ppb + i / nb] = bv[u];  // pixel-major -> k-major (pixels past nq: zeros)
+                int jj, k;
+                fd_divmod(i, a.fd_nb, &jj, &k);
+                if (i < ppb * nb) bet[k * ppb + jj] = bv[u];  // pixel-major -> k-major (pixels past nq: zeros)
             }
-            for (int i = t + UB * 256; i < ppb * nb; i += 256) bet[(i % nb) * ppb + i / nb] = i < nq * nb ? a.betaG[(size_t)q0 * nb + i] : 0.f;
+            for (int i = t + UB * 256; i < ppb * nb; i += 256) {
+                int jj, k;
+                fd_divmod(i, a.fd_nb, &jj, &k);
+                bet[k * ppb + jj] = i < nq * nb ? a.betaG[(size_t)q0 * nb + i] : 0.f;
+            }
         }
         __syncthreads();
         if (bid == N + 1)  // packed transpose W0cT[k][o] of W0's coordinate block (consumed by the match backward)
@@ -298,7 +309,8 @@ __global__ void __launch_bounds__(256) prep_all_kernel(Args a) {
         __syncthreads();
         if (!reuse)
             for (int i = t; i < pe * ppb; i += blockDim.x) {
-                const int m = i / ppb, jj = i % ppb;
+                int m, jj;
+                fd_divmod(i, a.fd_ppb_prep, &m, &jj);
                 float sn = 0.f, cs = 0.f;
                 if (jj < nq) {
                     const float2 c = cxy[jj];
@@ -309,7 +321,8 @@ __global__ void __launch_bounds__(256) prep_all_kernel(Args a) {
         __syncthreads();
         if (!reuse && a.betaG != nullptr) {  // pixel-major copy for the layer-0 weight-gradient kernel (coalesced over k)
             for (int i = t; i < nq * nb; i += blockDim.x) {
-                const int jj = i / nb, k = i % nb;
+                int jj, k;
+                fd_divmod(i, a.fd_nb, &jj, &k);
                 a.betaG[(size_t)(q0 + jj) * nb + k] = bet[k * ppb + jj];
             }
         }
@@ -963,6 +976,7 @@ static inline int fill_args(Args& a, const Net& nt, const Tiling& tl, const floa
     a.ppb = wl.ppb;
     static const int prep_bps = getenv("LMR_PREP_BPS") ? atoi(getenv("LMR_PREP_BPS")) : 2;  // prep blocks per SM (tuning knob; measured: 1 -> 22 us, 2 -> 16 us at 100x100)
     a.ppb_prep = choose_ppb(tl.D * tl.P, prep_bps > 0 ? prep_bps : 2);
+    a.fd_nb = make_fastdiv(2 * nt.pe), a.fd_ppb_prep = make_fastdiv(a.ppb_prep);
     a.dAred = reinterpret_cast<float*>(base + wl.dAred);
     a.G0 = reinterpret_cast<float*>(base + wl.G0);
     a.partials = reinterpret_cast<float*>(base + wl.partials);

@@ -630,30 +630,51 @@ __global__ void __launch_bounds__(NT_T, 4) inr_fwd_ts_kernel(Args a) {
         if (myTiles > 0) stage_tile_inputs(a, decode_tile(tl, blockIdx.x), s.Cps, NE_T);
         cp_async_commit();
         const int nl = row / tl.TP, j = row % tl.TP;
+        // Layer-0 latent part A[n][:] of this thread's row: read from global memory (L1 / L2 hits; a shared-memory copy would cost the fourth CTA per
+        // SM) as 16-byte loads issued ONE CHUNK AHEAD of their use.  With a single latent chunk the row does not depend on the tile, so the
+        // prefetch of chunk 0 at the end of a tile serves the next tile.  (Scalar loads at the point of use were the top stall site of this
+        // kernel: 18.6 % of the samples, profiles/r2c_ncu_source_hotspots.md.)
+        const bool a_fixed = !multi_chunk;
+        const float* An_fixed = a.Avec + (size_t)(nl < tl.N ? nl : 0) * SHP;
+        auto load_a = [&](const float* An, int kc, float4* o) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                const int col = 16 * kc + 4 * k4;
+                o[k4] = col + 4 <= SHP ? __ldg(reinterpret_cast<const float4*>(An + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 an[4];
+        if (a_fixed) load_a(An_fixed, 0, an);
         for (int it = 0; it < myTiles; ++it) {
             const TileIdx ti = decode_tile(tl, blockIdx.x + it * gridDim.x);
             cp_async_wait<0>();
             named_bar_sync(1, NE_T);
             if (it + 1 < myTiles) stage_tile_inputs(a, decode_tile(tl, blockIdx.x + (it + 1) * gridDim.x), s.Cps + ((it + 1) & 1) * tl.TP * SHS, NE_T);
             cp_async_commit();
-            const float* Cj = s.Cps + (it & 1) * tl.TP * SHS;
             const bool active = nl < ti.nn && j < ti.np;
-            Cj += (active ? j : 0) * SHS;
-            const bool as_smem = s.As != nullptr && !multi_chunk;
-            const float* An = as_smem ? s.As + (active ? nl : 0) * SHS : a.Avec + (size_t)(ti.n0 + (active ? nl : 0)) * SHP;
+            const uint32_t Cj_s = smem_u32(s.Cps + (it & 1) * tl.TP * SHS + (active ? j : 0) * SHS);
+            const float* An = a_fixed ? An_fixed : a.Avec + (size_t)(ti.n0 + (active ? nl : 0)) * SHP;
+            if (!a_fixed) load_a(An, 0, an);
             uint8_t* gimg = a.hsave != nullptr ? a.hsave + (size_t)(blockIdx.x + it * gridDim.x) * keep_record_bytes(LH) : nullptr;  // h_1 | h_2 | h_3 | y
             // ---- h_1 = tanh(A[n] + Cp[j]) -> operand (the previous tile's last accumulator was waited for: the operand columns are free)
 #pragma unroll 1
             for (int kc = 0; kc < 4; ++kc) {
                 float2 v[8];
-                float* vf = reinterpret_cast<float*>(v);
                 const int ncol = kc < 3 ? 16 : 8;  // chunk 6 (features 48..55: 4 live + 4 zero) only; chunk 7 stays zero
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    const int col = 16 * kc + k;
-                    float z0 = 0.f;
-                    if (k < ncol) z0 = (as_smem ? An[col] : (col < SHP ? An[col] : 0.f)) + Cj[col];
-                    vf[k] = z0;
+                const float4 a0 = an[0], a1 = an[1], a2 = an[2], a3 = an[3];
+                load_a(An, (kc + 1) & 3, an);  // next chunk (kc == 3: chunk 0 again -- of the next tile when the row is tile-independent)
+                {
+                    const uint32_t cj = Cj_s + (uint32_t)(16 * kc) * 4u;
+                    const float4 c0 = lds128(cj), c1 = lds128(cj + 16);
+                    v[0] = add2(make_float2(a0.x, a0.y), make_float2(c0.x, c0.y)), v[1] = add2(make_float2(a0.z, a0.w), make_float2(c0.z, c0.w));
+                    v[2] = add2(make_float2(a1.x, a1.y), make_float2(c1.x, c1.y)), v[3] = add2(make_float2(a1.z, a1.w), make_float2(c1.z, c1.w));
+                    if (kc < 3) {
+                        const float4 c2 = lds128(cj + 32), c3 = lds128(cj + 48);
+                        v[4] = add2(make_float2(a2.x, a2.y), make_float2(c2.x, c2.y)), v[5] = add2(make_float2(a2.z, a2.w), make_float2(c2.z, c2.w));
+                        v[6] = add2(make_float2(a3.x, a3.y), make_float2(c3.x, c3.y)), v[7] = add2(make_float2(a3.z, a3.w), make_float2(c3.z, c3.w));
+                    } else {
+                        v[4] = v[5] = v[6] = v[7] = make_float2(0.f, 0.f);
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {

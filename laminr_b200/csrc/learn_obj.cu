@@ -39,6 +39,7 @@ struct Params {
     unsigned int* sync;    // [0] arrival counter (monotonic), [1] launch epoch
     float *part_a, *part_b, *fin, *part_c;
     int PS;                // pixels per slice
+    FastDiv fdPS, fdF, fdN, fdC;  // the flattened loops divide by these
     long long* trace;      // debug (LMR_OBJ_TRACE=1): CTA 0's phase time stamps (globaltimer ns), else null
 };
 
@@ -127,6 +128,8 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     float* Ks = rowc + 4 * N;          // [N][N]
     float* posS = Ks + N * N;          // [N][N]
     float* negS = posS + N * N;        // [N][N]
+    float* actv = negS + N * N;        // [N]  activations (summed into the loss)
+    float* scal = actv + N;            // [4]
     stamp(p, 0);
     const unsigned int epoch = ld_acquire(p.sync + 1);
     const float g_reg = __ldg(p.g_reg);  // issued up front: an L2 round trip that would otherwise sit on the critical path after barrier 3
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     // ---- phase 1: z (written out), sum_c z, masked z; partial responses and partial gram  (work items flattened over all threads)
 #pragma unroll 1
     for (int i = t; i < NC * PS; i += NT) {
-        const int r = i / PS, e = i - r * PS, n = r / C;
+        const int r = fd_div(i, p.fdPS), e = i - r * PS, n = fd_div(r, p.fdC);
         const float sdn = sd[n] + p.eps_con;
         float y;
         if (p.mode == LMR_CONSTRAIN_NORM) y = (xs[r * PSP + e] - p.mean) / sdn * p.target + p.mean;
@@ -234,7 +237,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     __syncthreads();
 #pragma unroll 1
     for (int i = t; i < N * PS; i += NT) {
-        const int n = i / PS, e = i - n * PS;
+        const int n = fd_div(i, p.fdPS), e = i - n * PS;
         float v = 0.f;
         for (int c = 0; c < C; ++c) v += gy[(n * C + c) * PSP + e];
         zs[n * PSP + e] = v;
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
 #pragma unroll 1
         for (int it = t; it < N * F + N * N; it += NT) {
             if (it < N * F) {
-                const int n = it / F, f = it - n * F;
+                const int n = fd_div(it, p.fdF), f = it - n * F;
                 const float* a = zs + n * PSP;
                 const float* w = ws + f * PSP;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
                 for (; e < PS; ++e) s0 = fmaf(a[e], w[e], s0);
                 outR[it] = (s0 + s1) + (s2 + s3);
             } else {
-                const int pr = it - N * F, i = pr / N, j = pr - i * N;
+                const int pr = it - N * F, i = fd_div(pr, p.fdN), j = pr - i * N;
                 if (j < i) continue;
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
                 for (int c = 0; c < C; ++c) {
@@ -297,15 +300,17 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     __syncthreads();
     // responses: first maximum wins (torch.max), act = (elu(m)+1)/2 + eps.  8 lanes per image scan the filters f = sub, sub + 8, ..; ties go to the
     // lower filter index in the lane-local scan and in the shuffle combine
+    const int sub = lane & (GRP - 1);
+    const unsigned gmask = 0xffu << (lane & ~(GRP - 1));
+#pragma unroll 1
     for (int n = t / GRP; n < N; n += NT / GRP) {
-        const int sub = lane & (GRP - 1);
         float best = -INFINITY;
         int bi = 0x7fffffff;
+#pragma unroll 1
         for (int f = sub; f < F; f += GRP) {
             const float r = fin[n * F + f];
             if (r > best) best = r, bi = f;
         }
-        const unsigned gmask = 0xffu << (lane & ~(GRP - 1));
 #pragma unroll
         for (int o = 1; o < GRP; o <<= 1) {
             const float ob = __shfl_xor_sync(gmask, best, o);
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
             const float act = (e + 1.f) / 2.f + p.act_eps;
             amax[n] = bi;
             coef[n] = (-p.inv_mei_act / (float)N) * 0.5f * (best > 0.f ? 1.f : expf(best));
-            rho[n] = act;  // parked until the loss is formed below
+            actv[n] = act;
             if (b == 0) {
                 p.act[n] = act;
                 if (p.rmax) p.rmax[n] = best;
@@ -328,27 +333,30 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     }
     // contrastive term and its backward coefficient matrix K (same maths as post.cu simclr_finalize_kernel)
     const float* gram = fin + N * F;
+#pragma unroll 1
     for (int pr = t; pr < N * N; pr += NT) {
-        const int i = pr / N, j = pr - i * N;
+        const int i = fd_div(pr, p.fdN), j = pr - i * N;
         const float c = gram[pr] / (sqrtf(gram[i * N + i]) * sqrtf(gram[j * N + j]));
         cosm[pr] = c;
         Sm[pr] = expf(c / p.T);
+        if (i == j) rho[i] = sqrtf(gram[pr]);
     }
     __syncthreads();
-    float act_sum = 0.f;
-    if (t == 0)
-        for (int n = 0; n < N; ++n) act_sum += rho[n];
-    __syncthreads();
-    for (int i = t; i < N; i += NT) rho[i] = sqrtf(gram[i * N + i]);
-    // one warp per row: masked row sums of S over the lanes (fixed shuffle tree: deterministic)
-    for (int i = warp; i < N; i += NW) {
+    // 8 lanes per row: masked row sums of S (fixed shuffle tree: deterministic); the last warp adds up the activations meanwhile
+#pragma unroll 1
+    for (int i = t / GRP; i < N; i += NT / GRP) {
         float ps = 0.f, np_ = 0.f, ns = 0.f, nn = 0.f;
-        for (int j = lane; j < N; j += 32) {
+#pragma unroll 1
+        for (int j = sub; j < N; j += GRP) {
             ps = fmaf(Sm[i * N + j], posS[i * N + j], ps), np_ += posS[i * N + j];
             ns = fmaf(Sm[i * N + j], negS[i * N + j], ns), nn += negS[i * N + j];
         }
-        ps = warp_sum(ps), np_ = warp_sum(np_), ns = warp_sum(ns), nn = warp_sum(nn);
-        if (lane == 0) {
+#pragma unroll
+        for (int o = 1; o < GRP; o <<= 1) {
+            ps += __shfl_xor_sync(gmask, ps, o), np_ += __shfl_xor_sync(gmask, np_, o);
+            ns += __shfl_xor_sync(gmask, ns, o), nn += __shfl_xor_sync(gmask, nn, o);
+        }
+        if (sub == 0) {
             const float num = (ps == 0.f ? 0.f : ps / np_) + p.eps_clr;
             const float den = (ns == 0.f ? 0.f : ns / nn) + p.eps_clr;
             rowc[i * 4 + 0] = ps == 0.f ? 0.f : (p.T / (2.f * N)) / (np_ * num);
@@ -356,28 +364,40 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
             rowc[i * 4 + 2] = logf(num / den);
         }
     }
-    __syncthreads();
-    if (b == 0 && t == 0) {
-        float logsum = 0.f;
-        for (int i = 0; i < N; ++i) logsum += rowc[i * 4 + 2];
-        const float reg = logsum / (float)N * p.T / 2.f;
-        p.reg[0] = reg;
-        p.loss[0] = -(act_sum * p.inv_mei_act) / (float)N + g_reg * reg;
+    if (b == 0 && warp == NW - 1) {  // (N <= 64: two terms per lane)
+        float a0 = (lane < N ? actv[lane] : 0.f) + (lane + 32 < N ? actv[lane + 32] : 0.f);
+        a0 = warp_sum(a0);
+        if (lane == 0) scal[0] = a0;
     }
+    __syncthreads();
+    if (b == 0 && warp == 0) {
+        float ls = (lane < N ? rowc[lane * 4 + 2] : 0.f) + (lane + 32 < N ? rowc[(lane + 32) * 4 + 2] : 0.f);
+        ls = warp_sum(ls);
+        if (lane == 0) {
+            const float reg = ls / (float)N * p.T / 2.f;
+            p.reg[0] = reg;
+            p.loss[0] = -(scal[0] * p.inv_mei_act) / (float)N + g_reg * reg;
+        }
+    }
+#pragma unroll 1
     for (int pr = t; pr < N * N; pr += NT) {
-        const int i = pr / N;
+        const int i = fd_div(pr, p.fdN);
         Sm[pr] = (posS[pr] * rowc[i * 4] - negS[pr] * rowc[i * 4 + 1]) * Sm[pr] / p.T;  // Gamma_ij = A_ij S_ij / T
     }
     __syncthreads();
-    for (int i = warp; i < N; i += NW) {
+#pragma unroll 1
+    for (int i = t / GRP; i < N; i += NT / GRP) {
         float kap = 0.f;
-        for (int j = lane; j < N; j += 32) kap = fmaf(Sm[i * N + j] + Sm[j * N + i], cosm[i * N + j], kap);
-        kap = warp_sum(kap);
-        if (lane == 0) rowc[i * 4 + 3] = kap;
+#pragma unroll 1
+        for (int j = sub; j < N; j += GRP) kap = fmaf(Sm[i * N + j] + Sm[j * N + i], cosm[i * N + j], kap);
+#pragma unroll
+        for (int o = 1; o < GRP; o <<= 1) kap += __shfl_xor_sync(gmask, kap, o);
+        if (sub == 0) rowc[i * 4 + 3] = kap;
     }
     __syncthreads();
+#pragma unroll 1
     for (int pr = t; pr < N * N; pr += NT) {
-        const int i = pr / N, j = pr - i * N;
+        const int i = fd_div(pr, p.fdN), j = pr - i * N;
         float k = (Sm[i * N + j] + Sm[j * N + i]) / (rho[i] * rho[j]);
         if (i == j) k -= rowc[i * 4 + 3] / (rho[i] * rho[i]);
         Ks[pr] = k;
@@ -389,7 +409,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     // ---- phase 3: g_z = response backward + contrastive backward; gradient wrt the pre-clamp image; per-image sums for the projection
 #pragma unroll 1
     for (int i = t; i < NC * PS; i += NT) {
-        const int r = i / PS, e = i - r * PS, n = r / C, c = r - n * C;
+        const int r = fd_div(i, p.fdPS), e = i - r * PS, n = fd_div(r, p.fdC), c = r - n * C;
         float v = 0.f;
         if (e < np) {
             const float sdn = sd[n] + p.eps_con, mun = p.mode == LMR_CONSTRAIN_NORM ? p.mean : mu[n];
@@ -441,7 +461,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     // ---- phase 4: g_x   NORM: k gy - target dot / ((s+eps)^2 s) u ;  STD: k (gy - mean(gy)) - target dot / ((sd+eps)^2 (n-1) sd) (x-mu)
 #pragma unroll 1
     for (int i = t; i < NC * PS; i += NT) {
-        const int r = i / PS, e = i - r * PS, n = r / C;
+        const int r = fd_div(i, p.fdPS), e = i - r * PS, n = fd_div(r, p.fdC);
         if (e >= np) continue;
         const float s_ = sd[n];
         const float k = p.target / (s_ + p.eps_con);
@@ -461,7 +481,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
 
 static size_t smem_floats(int N, int C, int F, int PS) {
     const int PSP = PS | 1, NC = N * C;
-    return (size_t)3 * NC * PSP + (size_t)F * PSP + (size_t)N * PSP + PSP + 6 * (size_t)N + 2 * (size_t)NC + (size_t)N /*amax*/ + (size_t)N * F + N * N + 5 * (size_t)N * N + 5 * (size_t)N + 16;
+    return (size_t)3 * NC * PSP + (size_t)F * PSP + (size_t)N * PSP + PSP + 6 * (size_t)N + 2 * (size_t)NC + (size_t)N /*amax*/ + (size_t)N * F + N * N + 5 * (size_t)N * N + 6 * (size_t)N + 20;
 }
 
 struct Plan {
@@ -532,6 +552,7 @@ extern "C" int lmr_learn_objective(int mode, const float* x, int N, int C, int H
     p.part_a = reinterpret_cast<float*>(base + pl.off_a), p.part_b = reinterpret_cast<float*>(base + pl.off_b);
     p.fin = reinterpret_cast<float*>(base + pl.off_fin), p.part_c = reinterpret_cast<float*>(base + pl.off_c);
     p.PS = pl.PS;
+    p.fdPS = make_fastdiv(pl.PS), p.fdF = make_fastdiv(F), p.fdN = make_fastdiv(N), p.fdC = make_fastdiv(C);
     static const bool tracing = getenv("LMR_OBJ_TRACE") != nullptr;
     static long long* trace_dev = nullptr;
     p.trace = nullptr;
