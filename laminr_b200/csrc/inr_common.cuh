@@ -432,10 +432,23 @@ __global__ void __launch_bounds__(L0_THREADS) l0_partial_kernel(Args a, float* l
     }
 }
 
+__device__ __forceinline__ void cp_async16_g(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+
 // sum of `count` values spaced `stride` apart: 8 independent chains (the loads are L2 round trips), combined in a fixed order
 __device__ __forceinline__ float strided_sum8(const float* src, int count, size_t stride) {
     float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int b = 0;
+    for (; b + 16 <= count; b += 16) {  // 16 round trips in flight, added in the order of the 8-wide loop below (same bits)
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = src[(size_t)(b + u) * stride];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] += v[u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] += v[8 + u];
+    }
     for (; b + 8 <= count; b += 8) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) s[u] += src[(size_t)(b + u) * stride];
@@ -448,6 +461,15 @@ __device__ __forceinline__ float strided_sum8(const float* src, int count, size_
 __device__ __forceinline__ float strided_sum8_cg(const float* src, int count, size_t stride) {
     float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int b = 0;
+    for (; b + 16 <= count; b += 16) {  // 16 round trips in flight, added in the order of the 8-wide loop below (same bits)
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (size_t)(b + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] += v[u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] += v[8 + u];
+    }
     for (; b + 8 <= count; b += 8) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) s[u] += __ldcg(src + (size_t)(b + u) * stride);
@@ -561,12 +583,23 @@ __global__ void __launch_bounds__(L0_THREADS, 2) learn_tail_kernel(Args a, float
     // than the longer one.  Phase B is spread over all G blocks.
     // Adam constants of this step (every block reads the counter before anybody can publish the new one: that happens after the last exit count)
     const int tstep = *reinterpret_cast<volatile int*>(ad.step) + 1;
-    float step_size, bc2_sqrt;
-    adam_step_consts(tstep, ad.lr, ad.b1, ad.b2, &step_size, &bc2_sqrt);
+    // (two powf: ~200 instructions behind an L2 round trip.  The reduction blocks need them in phase A and evaluate them here; the layer-0 blocks --
+    //  the long pole of phase A, tools/trace_tail.py -- only in phase B: they start their loads first and evaluate them behind the product)
+    float step_size = 0.f, bc2_sqrt = 1.f;
+    if (blk >= nL0) adam_step_consts(tstep, ad.lr, ad.b1, ad.b2, &step_size, &bc2_sqrt);
     const size_t psz = partial_size(nt, tl, HP);
     const size_t nHid = nt.count() - nt.size0(), nA = nHid + (size_t)tl.N * HP;
     const size_t offA = (size_t)(L - 1) * HID * HID + (size_t)(L - 1) * HP + (size_t)nt.C * HP + 4;
     const int QB = blockDim.x / 4;  // element quads per block and pass
+    // debug (LMR_TAIL_TRACE=1): globaltimer stamps of thread 0 of block 0 (layer-0 role, slots 0..7) and of block nL0 (reduction role, slots 8..15)
+    auto stamp = [&](int idx) {
+        if (a.trace != nullptr && t == 0 && (blk == 0 || blk == nL0)) {
+            long long tns;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+            a.trace[(blk == 0 ? 0 : 8) + idx] = tns;
+        }
+    };
+    stamp(0);
 
     if (blk < nL0) {
         // ---- phase A (a): layer-0 coordinate block partial of this block's pixel chunks
@@ -583,9 +616,15 @@ __global__ void __launch_bounds__(L0_THREADS, 2) learn_tail_kernel(Args a, float
         for (int ch = blk; ch < nchunks; ch += nL0) {
             const int q0 = ch * ppb, nq = min(ppb, total - q0);
             __syncthreads();
-            for (int i = t; i < nq * HP / 4; i += blockDim.x) reinterpret_cast<float4*>(Gs)[i] = reinterpret_cast<const float4*>(a.G0 + (size_t)q0 * HP)[i];
-            for (int i = t; i < nq * nb / 4; i += blockDim.x) reinterpret_cast<float4*>(Bs)[i] = reinterpret_cast<const float4*>(a.betaG + (size_t)q0 * nb)[i];
+            // every 16-byte piece of the two slices in flight at once (cp.async: no register staging, no dependence on the unrolling of these loops)
+            for (int i = t; i < nq * HP / 4; i += blockDim.x) cp_async16_g(reinterpret_cast<float4*>(Gs) + i, reinterpret_cast<const float4*>(a.G0 + (size_t)q0 * HP) + i);
+            for (int i = t; i < nq * nb / 4; i += blockDim.x) cp_async16_g(reinterpret_cast<float4*>(Bs) + i, reinterpret_cast<const float4*>(a.betaG + (size_t)q0 * nb) + i);
+            asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
             __syncthreads();
+            stamp(4);
+            // (measured, round 2: this 4 x 4 register block runs at the shared-memory pipe's rate -- 2 broadcast 16-byte loads per 16 multiply-adds,
+            //  ~185 cycles per pixel for the block's 11 warps: 6.4 of the kernel's 18 us.  8 x 8 blocks on packed fma.rn.f32x2 (4 loads per 64) need
+            //  91 threads, whose 3 warps expose every load latency under the 88-register cap of two co-resident blocks: 8.2 us.  tools/trace_tail.py)
             if (owner) {
                 const float4* gp = reinterpret_cast<const float4*>(Gs) + og;
                 const float4* bp = reinterpret_cast<const float4*>(Bs) + kg;
@@ -599,6 +638,8 @@ __global__ void __launch_bounds__(L0_THREADS, 2) learn_tail_kernel(Args a, float
                 }
             }
         }
+        stamp(5);
+        adam_step_consts(tstep, ad.lr, ad.b1, ad.b2, &step_size, &bc2_sqrt);  // (used in phase B)
         if (owner) {
             float* dst = l0part + (size_t)blk * HID * nb;
 #pragma unroll
@@ -651,6 +692,7 @@ __global__ void __launch_bounds__(L0_THREADS, 2) learn_tail_kernel(Args a, float
     }
     // ---- grid barrier
     __syncthreads();
+    stamp(1);
     if (t == 0) {
         __threadfence();
         atomicAdd(ad.step + 1, 1);
@@ -658,6 +700,7 @@ __global__ void __launch_bounds__(L0_THREADS, 2) learn_tail_kernel(Args a, float
         __threadfence();
     }
     __syncthreads();
+    stamp(2);
     // ---- phase B, again two roles side by side: (c) on blocks [0, nL0), (d) on blocks [nL0, G)
     if (blk < nL0) {
         // (c) coordinate block of W0 over the nL0 layer-0 partials, 4 lanes per element
@@ -711,6 +754,7 @@ __global__ void __launch_bounds__(L0_THREADS, 2) learn_tail_kernel(Args a, float
     }
     // ---- exit count: the last block out publishes the step count and re-arms the scratch word
     __syncthreads();
+    stamp(3);
     if (t == 0) {
         __threadfence();
         if (atomicAdd(ad.step + 1, 1) == 2 * G - 1) {
@@ -724,7 +768,7 @@ template <int HID>
 static int launch_learn_tail(const Args& a, float* l0part, int grid_l0, int nPartMain, float* g_params, const AdamArgs& ad, cudaStream_t st) {
     constexpr int HP = (HID + 3) / 4 * 4;
     LMR_CHECK_ARG(a.betaG != nullptr, "learn tail: needs the kept sin/cos table of the forward workspace (D == 1)");
-    LMR_CHECK_ARG((HP / 4) * (2 * a.net.pe / 4) <= L0_THREADS, "learn tail: pe_dim %d not supported", a.net.pe);
+    LMR_CHECK_ARG((HP / 4) * (2 * a.net.pe / 4) <= L0_THREADS && a.net.pe % 2 == 0, "learn tail: pe_dim %d not supported", a.net.pe);
     LMR_CHECK_ARG(grid_l0 <= num_sms(), "learn tail: %d blocks cannot be co-resident", grid_l0);
     const size_t smem = (size_t)a.ppb * (HP + 2 * a.net.pe) * sizeof(float);
     static size_t cache = 0;
@@ -738,7 +782,23 @@ static int launch_learn_tail(const Args& a, float* l0part, int grid_l0, int nPar
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;  // all blocks co-resident: the software grid barrier needs it
     cfg.attrs = attr, cfg.numAttrs = 1;
-    LMR_CUDA_OK(cudaLaunchKernelEx(&cfg, learn_tail_kernel<HID>, a, l0part, grid_l0, nPartMain, g_params, ad));
+    static const bool tracing = getenv("LMR_TAIL_TRACE") != nullptr;
+    if (tracing) {  // debug only: synchronises and prints the phase time line of one block of each role
+        static long long* trace_dev = nullptr;
+        if (trace_dev == nullptr) cudaMalloc(&trace_dev, 16 * sizeof(long long));
+        Args at = a;
+        at.trace = trace_dev;
+        LMR_CUDA_OK(cudaLaunchKernelEx(&cfg, learn_tail_kernel<HID>, at, l0part, grid_l0, nPartMain, g_params, ad));
+        long long h[16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[tail trace] ns since block 0's entry: layer-0 role: slices loaded %lld | product %lld | phase A %lld | barrier %lld | phase B %lld ;  reduction role: entry %lld | phase A %lld | barrier %lld | phase B %lld\n",
+                h[4] - h[0], h[5] - h[0], h[1] - h[0], h[2] - h[0], h[3] - h[0], h[8] - h[0], h[9] - h[0], h[10] - h[0], h[11] - h[0]);
+        return 0;
+    }
+    Args an = a;
+    an.trace = nullptr;  // (the tile kernel's LMR_TC_TRACE buffer is not this kernel's)
+    LMR_CUDA_OK(cudaLaunchKernelEx(&cfg, learn_tail_kernel<HID>, an, l0part, grid_l0, nPartMain, g_params, ad));
     return 0;
 }
 
@@ -768,7 +828,8 @@ __global__ void __launch_bounds__(AFF_THREADS) affine_grad_kernel(Args a) {
     if (t == 0) affine_consts(a.aff, d, cst);
     if (t >= 64 && t < 64 + nb) Bsm[t - 64] = a.B[t - 64];
     for (int i = t; i < HP * nb; i += AFF_THREADS) {
-        const int o = i / nb, k = i % nb;
+        int o, k;
+        fd_divmod(i, a.fd_nb, &o, &k);
         Wt[i] = o < HID ? a.params[(size_t)o * nt.in_dim + 1 + na + k] : 0.f;
     }
     const float* gsrc = a.G0 + ((size_t)d * a.tl.P + p0) * HP;

@@ -72,7 +72,9 @@ __device__ __forceinline__ float clamp_pass(float y, int has_min, float pmin, in
 // 8 consecutive lanes sum `count` values spaced `stride` apart in a fixed order (all loads of a lane in flight together, then a shuffle
 // tree): deterministic.  The values were written by other CTAs of this launch: the loads bypass L1.
 constexpr int GRP = 8, MAXLD = 20;  // up to GRP * MAXLD = 160 partials (grid <= 148 CTAs)
-__device__ __forceinline__ float group_strided_sum(const float* src, int count, size_t stride, int lane) {
+// (not inlined: five call sites x 20 predicated loads were a tenth of the kernel's code, and the kernel runs through its ~100 KB of code once per
+// launch with a cold instruction cache -- `no_inst` was the top stall reason of its one-shot sections)
+__device__ __noinline__ float group_strided_sum(const float* src, int count, size_t stride, int lane) {
     const int sub = lane & (GRP - 1);
     float v[MAXLD];
 #pragma unroll
@@ -157,15 +159,18 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
             else ws[f * PSP + e] = 0.f;
         }
     }
+#pragma unroll 1
     for (int e = t; e < PS; e += NT) {
         if (e < np) cp_async4(mk + e, p.mask + p0 + e);
         else mk[e] = 0.f;
     }
+#pragma unroll 1
     for (int i = t; i < N * N; i += NT) cp_async4(posS + i, p.pos + i), cp_async4(negS + i, p.neg + i);
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     stamp(p, 1);
     if (p.mode == LMR_CONSTRAIN_NORM) {
+#pragma unroll 1
         for (int n = warp; n < N; n += NW) {
             float acc = 0.f;
             for (int c = 0; c < C; ++c)
@@ -177,11 +182,13 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
             if (lane == 0) p.part_a[(size_t)b * N + n] = acc;
         }
         barrier();
+#pragma unroll 1
         for (int n = t / GRP; n < N; n += NT / GRP) {
             const float tot = group_strided_sum(p.part_a + n, G, N, lane);
             if ((lane & (GRP - 1)) == 0) sd[n] = sqrtf(tot), mu[n] = 0.f;
         }
     } else {
+#pragma unroll 1
         for (int n = warp; n < N; n += NW) {
             float acc = 0.f;
             for (int c = 0; c < C; ++c)
@@ -190,11 +197,13 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
             if (lane == 0) p.part_a[(size_t)b * N + n] = acc;
         }
         barrier();
+#pragma unroll 1
         for (int n = t / GRP; n < N; n += NT / GRP) {
             const float tot = group_strided_sum(p.part_a + n, G, N, lane);
             if ((lane & (GRP - 1)) == 0) mu[n] = tot / (float)(C * HW);
         }
         __syncthreads();
+#pragma unroll 1
         for (int n = warp; n < N; n += NW) {
             float acc = 0.f;
             for (int c = 0; c < C; ++c)
@@ -206,14 +215,17 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
             if (lane == 0) p.part_c[(size_t)b * 2 * N + n] = acc;
         }
         barrier();
+#pragma unroll 1
         for (int n = t / GRP; n < N; n += NT / GRP) {
             const float tot = group_strided_sum(p.part_c + n, G, 2 * N, lane);
             if ((lane & (GRP - 1)) == 0) sd[n] = sqrtf(tot / (float)(C * HW - 1));  // unbiased (Tensor.std default)
         }
     }
     __syncthreads();
-    if (b == 0 && p.stats != nullptr)
+    if (b == 0 && p.stats != nullptr) {
+#pragma unroll 1
         for (int n = t; n < N; n += NT) p.stats[2 * n] = sd[n], p.stats[2 * n + 1] = mu[n];
+    }
 
     stamp(p, 2);
     // ---- phase 1: z (written out), sum_c z, masked z; partial responses and partial gram  (work items flattened over all threads)
@@ -285,6 +297,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     // ---- phase 2: two-level combine of the partials (value v is summed by CTA v % G), then everybody reads the totals
     {
         const int nval = N * F + N * N;
+#pragma unroll 1
         for (int v = b + G * (t / GRP); v < nval; v += G * (NT / GRP)) {
             const float tot = group_strided_sum(p.part_b + v, G, (size_t)nval, lane);
             if ((lane & (GRP - 1)) == 0) p.fin[v] = tot;
@@ -295,6 +308,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     stamp(p, 6);
     {
         const int nval = N * F + N * N;
+#pragma unroll 1
         for (int v = t; v < nval; v += NT) fin[v] = __ldcg(p.fin + v);
     }
     __syncthreads();
@@ -417,10 +431,12 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
             const float* xc = xm + c * PSP + e;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
             int jn = 0;
+#pragma unroll 1
             for (; jn + 3 < N; jn += 4) {
                 a0 = fmaf(kr[jn], xc[(jn * C) * PSP], a0), a1 = fmaf(kr[jn + 1], xc[((jn + 1) * C) * PSP], a1);
                 a2 = fmaf(kr[jn + 2], xc[((jn + 2) * C) * PSP], a2), a3 = fmaf(kr[jn + 3], xc[((jn + 3) * C) * PSP], a3);
             }
+#pragma unroll 1
             for (; jn < N; ++jn) a0 = fmaf(kr[jn], xc[(jn * C) * PSP], a0);
             const float acc = (a0 + a1) + (a2 + a3);
             const float gz = coef[n] * ws[amax[n] * PSP + e] + g_reg * (p.g1 * mk[e] * p.g2) * acc;
@@ -433,6 +449,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
         gy[r * PSP + e] = v;
     }
     __syncthreads();
+#pragma unroll 1
     for (int r = warp; r < NC; r += NW) {
         const float mun = p.mode == LMR_CONSTRAIN_NORM ? p.mean : mu[r / C];
         float a0 = 0.f, a1 = 0.f;
@@ -445,6 +462,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
         if (lane == 0) dotu[2 * r] = a0, dotu[2 * r + 1] = a1;  // per (image, channel) row; combined over channels below
     }
     __syncthreads();
+#pragma unroll 1
     for (int n = t; n < N; n += NT) {
         float a0 = 0.f, a1 = 0.f;
         for (int c = 0; c < C; ++c) a0 += dotu[2 * (n * C + c)], a1 += dotu[2 * (n * C + c) + 1];
@@ -453,6 +471,7 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     stamp(p, 8);
     barrier();
     stamp(p, 9);
+#pragma unroll 1
     for (int n = t / GRP; n < 2 * N; n += NT / GRP) {  // part_c rows are [a0[0..N) | a1[0..N)]
         const float tot = group_strided_sum(p.part_c + n, G, 2 * N, lane);
         if ((lane & (GRP - 1)) == 0) dotn[n < N ? 2 * n : 2 * (n - N) + 1] = tot;
