@@ -478,15 +478,21 @@ __global__ void __launch_bounds__(NT, 1) learn_objective_kernel(Params p) {
     }
     __syncthreads();
     // ---- phase 4: g_x   NORM: k gy - target dot / ((s+eps)^2 s) u ;  STD: k (gy - mean(gy)) - target dot / ((sd+eps)^2 (n-1) sd) (x-mu)
+    // (the three per-image coefficients once per image -- three divisions per ELEMENT before -- in the finalize scratch rowc[n][0..2])
+#pragma unroll 1
+    for (int n = t; n < N; n += NT) {
+        const float s_ = sd[n];
+        const float denom = (s_ + p.eps_con) * (s_ + p.eps_con) * s_ * (p.mode == LMR_CONSTRAIN_NORM ? 1.f : (float)(C * HW - 1));
+        rowc[4 * n + 0] = p.target / (s_ + p.eps_con);
+        rowc[4 * n + 1] = p.target * dotn[2 * n + 1] / denom;
+        rowc[4 * n + 2] = p.mode == LMR_CONSTRAIN_NORM ? 0.f : dotn[2 * n] / (float)(C * HW);
+    }
+    __syncthreads();
 #pragma unroll 1
     for (int i = t; i < NC * PS; i += NT) {
         const int r = fd_div(i, p.fdPS), e = i - r * PS, n = fd_div(r, p.fdC);
         if (e >= np) continue;
-        const float s_ = sd[n];
-        const float k = p.target / (s_ + p.eps_con);
-        const float denom = (s_ + p.eps_con) * (s_ + p.eps_con) * s_ * (p.mode == LMR_CONSTRAIN_NORM ? 1.f : (float)(C * HW - 1));
-        const float c2 = p.target * dotn[2 * n + 1] / denom;
-        const float gmean = p.mode == LMR_CONSTRAIN_NORM ? 0.f : dotn[2 * n] / (float)(C * HW);
+        const float k = rowc[4 * n + 0], c2 = rowc[4 * n + 1], gmean = rowc[4 * n + 2];
         const float mun = p.mode == LMR_CONSTRAIN_NORM ? p.mean : mu[n];
         p.g_x[(size_t)r * HW + p0 + e] = k * (gy[r * PSP + e] - gmean) - c2 * (xs[r * PSP + e] - mun);
     }
