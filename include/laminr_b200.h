@@ -259,6 +259,21 @@ int lmr_learn_objective(int mode, const float* x, int N, int C, int HW, float ta
 int lmr_adam_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, int n, float lr, float beta1,
                   float beta2, float eps, int* step, void* stream);
 
+/* The same step over up to LMR_ADAM_MAX_GROUPS parameter tensors in ONE launch -- torch.optim.Adam over
+ * coordinate_transform.parameters() (inv_temp_learn_match.py:335,366: angles, scalings, shears, translation): four launches per match step
+ * otherwise, a tenth of the step's kernel time for two targets.  Every group keeps its own moments and its own int32[2] step word; element
+ * arithmetic and step semantics are those of lmr_adam_step (bit-identical results).  n <= 262144 per group. */
+#define LMR_ADAM_MAX_GROUPS 8
+typedef struct {
+    float* p;
+    const float* g;
+    float* exp_avg;
+    float* exp_avg_sq;
+    int* step;
+    int n;
+} lmr_adam_group;
+int lmr_adam_step_multi(const lmr_adam_group* groups, int count, float lr, float beta1, float beta2, float eps, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Match epoch statistics -- replaces the host-driven reductions of the match loop (inv_temp_learn_match.py:361-362:
  * acts_d = mean_n act[d,n,d] / mei_act_d; :368-371: their mean / min / max for the stop rule and the progress bar).

@@ -84,6 +84,7 @@ SIGNATURES = {
     "lmr_learn_objective": (_i, [_i, _vp, _i, _i, _i, _f, _f, _i, _f, _i, _f, _f, _vp, _i, _f, _f, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _vp, _vp, _sz, _vp]),
     "lmr_adam_step": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _f, _vp, _vp]),
+    "lmr_adam_step_multi": (_i, [_vp, _i, _f, _f, _f, _f, _vp]),
     "lmr_match_epoch_stats": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "lmr_create_mask_workspace_bytes": (_sz, [_i, _i, _i]),
     "lmr_create_mask": (_i, [_vp, _i, _i, _i, _f, _i, _vp, _i, _vp, _vp, _vp, _sz, _vp]),

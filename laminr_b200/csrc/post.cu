@@ -235,6 +235,13 @@ __global__ void __launch_bounds__(128) simresp_finalize_kernel(const float* __re
         const float* src = Rpart + (((size_t)g * S) * NB + b) * Fmax + f;
         float r4[4] = {0.f, 0.f, 0.f, 0.f};  // four independent chains (the loads are L2 round trips), combined in a fixed order
         int sidx = 0;
+        for (; sidx + 16 <= S; sidx += 16) {  // 16 round trips in flight, added in the order of the 4-wide loop below (same bits); few groups
+            float v[16];                      // mean many chunks: 79 per response for two targets at 100x100, a 20 us kernel with 4 in flight
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = src[(size_t)(sidx + u) * NB * Fmax];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) r4[u & 3] += v[u];
+        }
         for (; sidx + 4 <= S; sidx += 4) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) r4[u] += src[(size_t)(sidx + u) * NB * Fmax];
@@ -454,6 +461,33 @@ __global__ void __launch_bounds__(256) adam_ticket_kernel(float* __restrict__ p,
         if (atomicAdd(step + 1, 1) == (int)gridDim.x - 1) {
             step[1] = 0;
             step[0] = t;
+        }
+    }
+}
+
+// several tensors in one launch: block b belongs to the group g with first[g] <= b < first[g + 1]; per-group step word and ticket
+struct AdamGroups {
+    lmr_adam_group g[LMR_ADAM_MAX_GROUPS];
+    int first[LMR_ADAM_MAX_GROUPS + 1];
+    int count;
+};
+__global__ void __launch_bounds__(256) adam_multi_kernel(AdamGroups a, float lr, float b1, float b2, float eps) {
+    int gi = 0;
+#pragma unroll
+    for (int k = 1; k < LMR_ADAM_MAX_GROUPS; ++k)
+        if (k < a.count && (int)blockIdx.x >= a.first[k]) gi = k;
+    const lmr_adam_group& G = a.g[gi];
+    const int t = *reinterpret_cast<volatile int*>(G.step) + 1;
+    float step_size, bc2_sqrt;
+    adam_step_consts(t, lr, b1, b2, &step_size, &bc2_sqrt);
+    const int i = ((int)blockIdx.x - a.first[gi]) * blockDim.x + threadIdx.x;
+    if (i < G.n) adam_element(G.g[i], G.exp_avg[i], G.exp_avg_sq[i], G.p[i], b1, b2, eps, step_size, bc2_sqrt, &G.exp_avg[i], &G.exp_avg_sq[i], &G.p[i]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(G.step + 1, 1) == a.first[gi + 1] - a.first[gi] - 1) {
+            G.step[1] = 0;
+            G.step[0] = t;
         }
     }
 }
@@ -813,6 +847,22 @@ extern "C" int lmr_adam_step(float* p, const float* g, float* m, float* v, int n
     adam_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, step);
     LMR_LAUNCH_OK();
     counter_inc_kernel<<<1, 1, 0, st>>>(step);
+    LMR_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int lmr_adam_step_multi(const lmr_adam_group* groups, int count, float lr, float b1, float b2, float eps, void* stream) {
+    LMR_CHECK_ARG(groups != nullptr && count >= 1 && count <= LMR_ADAM_MAX_GROUPS, "adam_multi: 1..%d groups", LMR_ADAM_MAX_GROUPS);
+    post::AdamGroups a;
+    a.count = count, a.first[0] = 0;
+    for (int k = 0; k < count; ++k) {
+        const lmr_adam_group& g = groups[k];
+        LMR_CHECK_ARG(g.p && g.g && g.exp_avg && g.exp_avg_sq && g.step && g.n >= 1 && g.n <= 256 * 1024, "adam_multi: bad group %d", k);
+        a.g[k] = g;
+        a.first[k + 1] = a.first[k] + (g.n + 255) / 256;
+    }
+    for (int k = count; k < LMR_ADAM_MAX_GROUPS; ++k) a.g[k] = groups[0], a.first[k + 1] = a.first[count];
+    post::adam_multi_kernel<<<a.first[count], 256, 0, static_cast<cudaStream_t>(stream)>>>(a, lr, b1, b2, eps);
     LMR_LAUNCH_OK();
     return 0;
 }

@@ -379,9 +379,9 @@ class MatchStepper:
                                  want_affine=True, precision=self.precision, workspace=self.ws_bwd,
                                  g_affine=(self.grads[0][b0:b1], self.grads[1][b0:b1], self.grads[2][b0:b1], self.grads[3].view(D, 2)[b0:b1]),
                                  forward_workspace=self.ws_fwd, keep_activations=self.keep)
-        for p, g, m, v, s, tr in zip(self.params, self.grads, self.m, self.v, self.steps, self.trainable):
-            if tr:
-                ops.raw_adam_step(p.data, g, m, v, s, lr=self.lr)
+        groups = [(p.data, g, m, v, s) for p, g, m, v, s, tr in zip(self.params, self.grads, self.m, self.v, self.steps, self.trainable) if tr]
+        if groups:  # torch.optim.Adam over the trainable scalars of all targets (:335,366): one launch for the (up to) four tensors
+            ops.raw_adam_step_multi(groups, lr=self.lr)
         ops.raw_match_epoch_stats(self.act, self.mei_acts, self.epoch2[slot])
 
     def epoch_stats(self, slot=0):

@@ -705,6 +705,25 @@ def raw_adam_step(p, g, m, v, step, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
     check(lib.lmr_adam_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(b1), float(b2), float(eps), _ptr(step), _stream()))
 
 
+class _AdamGroup(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("step", C.c_void_p), ("n", C.c_int)]
+
+
+def raw_adam_step_multi(groups, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+    """One launch for up to 8 parameter tensors: `groups` = [(p, g, m, v, step), ...] with the arguments of raw_adam_step (lmr_adam_step_multi:
+    same element arithmetic, every group its own moments and step word)."""
+    lib = _lib.load()
+    if not 1 <= len(groups) <= 8:
+        raise ValueError("raw_adam_step_multi: 1..8 groups")
+    arr = (_AdamGroup * len(groups))()
+    for k, (p, g, m, v, step) in enumerate(groups):
+        _require_cuda(p, g, m, v, step)
+        if step.numel() < 2 or step.dtype != torch.int32:
+            raise ValueError("raw_adam_step_multi: `step` must be an int32 tensor with 2 elements ([steps taken, zero-initialised scratch])")
+        arr[k] = _AdamGroup(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(step), p.numel())
+    check(lib.lmr_adam_step_multi(arr, len(groups), float(lr), float(b1), float(b2), float(eps), _stream()))
+
+
 def raw_match_epoch_stats(act, mei_act, out3):
     """act [D,N], mei_act [D] -> out3 = (sum_d, min_d, max_d) of acts_d = mean_n act[d,n] / mei_act[d] (inv_temp_learn_match.py:361-371)."""
     lib = _lib.load()

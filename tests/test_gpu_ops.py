@@ -179,6 +179,29 @@ def test_adam_golden(ops):
     assert step.tolist() == [5, 0]
 
 
+def test_adam_multi_equals_separate_steps(ops):
+    """lmr_adam_step_multi (the match step's one launch over angles / scalings / shears / translation) == lmr_adam_step per tensor, bit for bit:
+    parameters, both moments and every group's own step word, over several steps and ragged sizes (one group spans several blocks)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    sizes = [2, 4, 4, 4, 1023, 700]
+    mk = lambda: [torch.randn(n, device="cuda", generator=g) for n in sizes]
+    p_a = mk()
+    p_b = [x.clone() for x in p_a]
+    st_a = [dict(m=torch.zeros_like(x), v=torch.zeros_like(x), s=torch.zeros(2, dtype=torch.int32, device="cuda")) for x in p_a]
+    st_b = [dict(m=torch.zeros_like(x), v=torch.zeros_like(x), s=torch.zeros(2, dtype=torch.int32, device="cuda")) for x in p_b]
+    st_b[2]["s"][0] = 7  # groups keep their own step counts
+    st_a[2]["s"][0] = 7
+    for it in range(4):
+        grads = mk()
+        for x, gr, st in zip(p_a, grads, st_a):
+            ops.raw_adam_step(x, gr, st["m"], st["v"], st["s"], lr=1e-2)
+        ops.raw_adam_step_multi([(x, gr, st["m"], st["v"], st["s"]) for x, gr, st in zip(p_b, grads, st_b)], lr=1e-2)
+    for x, y, sa, sb in zip(p_a, p_b, st_a, st_b):
+        assert torch.equal(x, y) and torch.equal(sa["m"], sb["m"]) and torch.equal(sa["v"], sb["v"])
+        assert sa["s"].tolist() == sb["s"].tolist() and sb["s"][1].item() == 0
+    assert st_b[2]["s"][0].item() == 11 and st_b[0]["s"][0].item() == 4
+
+
 @pytest.mark.parametrize("shape", [(3, 20, 1, 10, 10), (40, 20, 1, 100, 101), (7, 5, 3, 333, 77)])
 def test_to_host_numpy_equals_cpu_copy(ops, shape):
     """The pipelined device-to-host copy of result blocks (pinned ring + worker threads) returns exactly `t.cpu().numpy()`; small tensors take the
