@@ -694,10 +694,12 @@ __global__ void __launch_bounds__(L0_THREADS, 2) learn_tail_kernel(Args a, float
     __syncthreads();
     stamp(1);
     if (t == 0) {
-        __threadfence();
-        atomicAdd(ad.step + 1, 1);
-        while (*reinterpret_cast<volatile int*>(ad.step + 1) < G) __nanosleep(32);
-        __threadfence();
+        // release (cumulative over the block's writes ordered before it by the bar.sync above) / acquire at gpu scope: no separate fences
+        asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ad.step + 1) : "memory");
+        int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(ad.step + 1) : "memory");
+        } while (seen < G);
     }
     __syncthreads();
     stamp(2);

@@ -52,10 +52,10 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
 __device__ __forceinline__ void grid_sync(unsigned int* counter, unsigned int target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        // release (cumulative over the CTA's writes ordered before it by the bar.sync above) / acquire at gpu scope: no separate fences
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-        while ((int)(ld_acquire(counter) - target) < 0) __nanosleep(32);
-        __threadfence();
+        while ((int)(ld_acquire(counter) - target) < 0) {
+        }
     }
     __syncthreads();
 }
