@@ -204,20 +204,28 @@ struct TcSmem {
 // (role + rot) mod NBUF_BWD for role, rot in [0, NBUF_BWD): one compare + subtract instead of a division by a runtime-looking constant chain
 __device__ __forceinline__ int wrap_buf(int x) { return x >= NBUF_BWD ? x - NBUF_BWD : x; }
 
+// The hidden layers' weight tiles (split-bf16 images built once per step by the prep kernel: 3 x 16 KB, contiguous) are staged by the TMA engine:
+// ONE bulk async copy issued by thread 0, completion counted in bytes on `wbar` (a barrier slot the kernel does not use otherwise); every thread
+// waits on it at the end of its prologue, wait_weight_tiles (before: 3072 16-byte cp.async pieces spread over the CTA's threads).
 template <class SmemT>
-__device__ inline void load_weight_tiles(const Args& a, SmemT& s) {
+__device__ inline void load_weight_tiles(const Args& a, SmemT& s, uint64_t* wbar) {
     const Net& nt = a.net;
-    // the split-bf16 tile images were built once by the prep kernel: a straight 16-byte copy, every chunk in flight at once
-    for (int i = threadIdx.x; i < (LH - 1) * WT_BYTES / 16; i += blockDim.x) cp_async16(s.wt + 16 * i, a.wtimg + 16 * i);
-    cp_async_commit();
+    constexpr uint32_t kBytes = (LH - 1) * WT_BYTES;
+    if (threadIdx.x == 0) {
+        mbar_init(wbar, 1);
+        mbar_fence_init();
+        mbar_arrive_expect_tx(wbar, kBytes);
+        bulk_copy_g2s_plain(s.wt, a.wtimg, kBytes, wbar);
+    }
     const float* Wo = a.params + nt.offWout();
     for (int i = threadIdx.x; i < nt.C * HPAD; i += blockDim.x) {
         const int c = i / HPAD, k = i % HPAD;
         s.Wout[i] = k < HID ? Wo[c * HID + k] : 0.f;
     }
     if (threadIdx.x < 4) s.bout[threadIdx.x] = threadIdx.x < nt.C ? a.params[nt.offbout() + threadIdx.x] : 0.f;
-    cp_async_wait<0>();
 }
+// behind the prologue's __syncthreads (which also publishes the barrier's initialisation): the tiles have landed
+__device__ __forceinline__ void wait_weight_tiles(uint64_t* wbar) { mbar_wait(wbar, 0); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // MMA issue (ONE thread)
@@ -419,7 +427,7 @@ __global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
     TcSmem s(smem_raw, nt, tl, 1, false, NG);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const bool multi_chunk = tl.nChunks > 1;
-    load_weight_tiles(a, s);
+    load_weight_tiles(a, s, &s.bars[7]);
     init_layer0_tables(a, s, !multi_chunk, NT_F);
     if (warp == NE / 32) tmem_alloc(s.tmem, TM_COLS_FWD);
     if (t == 0) init_barriers(s.bars, 8);
@@ -427,6 +435,7 @@ __global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    wait_weight_tiles(&s.bars[7]);
     const uint32_t tm = *s.tmem;
     const int myTiles = (tl.numTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     uint8_t* T = s.tiles;
@@ -590,7 +599,7 @@ __global__ void __launch_bounds__(NT_T, 4) inr_fwd_ts_kernel(Args a) {
     TcSmem s(smem_raw, nt, tl, 0, false, 1);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const bool multi_chunk = tl.nChunks > 1;
-    load_weight_tiles(a, s);
+    load_weight_tiles(a, s, &s.bars[7]);
     init_layer0_tables(a, s, !multi_chunk, NT_T);
     if (warp == NE_T / 32) tmem_alloc(s.tmem, TM_T_COLS);
     if (t == 0) init_barriers(s.bars, 4);
@@ -603,6 +612,7 @@ __global__ void __launch_bounds__(NT_T, 4) inr_fwd_ts_kernel(Args a) {
 
     if (warp == NE_T / 32) {
         if (lane == 0) {  // ---- MMA issuer
+            wait_weight_tiles(&s.bars[7]);  // only this thread needs the weight tiles: the epilogue warps start the first tile's h_1 at once
             const uint32_t w_addr = smem_u32(s.wt);
             const uint32_t idesc = instr_desc(FMT_BF16, 128, HPAD, 0, 0);
             uint32_t pk = 0;
@@ -772,7 +782,7 @@ __global__ void __launch_bounds__(128 * NG + 64, 1) inr_bwd_tc_kernel(Args a) {
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const bool want_w = a.want_weights != 0;
     if (t == 0) LMR_TRACE(0, 500);
-    load_weight_tiles(a, s);
+    load_weight_tiles(a, s, &s.bars[7]);
     init_layer0_tables(a, s, true, NT_B);
     if (warp == NE / 32) tmem_alloc(s.tmem, TM_COLS_BWD);
     if (t == 0) {
@@ -786,6 +796,7 @@ __global__ void __launch_bounds__(128 * NG + 64, 1) inr_bwd_tc_kernel(Args a) {
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    wait_weight_tiles(&s.bars[7]);
     const uint32_t tm = *s.tmem;
     const int myTiles = (tl.numTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     if (t == 0) LMR_TRACE(0, 501);
@@ -1340,7 +1351,7 @@ __global__ void __launch_bounds__(b2::NT, 1) inr_bwd2_kernel(Args a) {
     const bool want_w = a.want_weights != 0;
     const int TP = tl.TP;
     if (t == 0) LMR_TRACE(0, 500);
-    load_weight_tiles(a, s);
+    load_weight_tiles(a, s, &s.bars[7]);
     for (int i = t; i < NS * 2 * TP * SHS; i += NT) s.Cps[i] = 0.f;
     for (int i = t; i < tl.NC * SHS; i += NT) {
         const int n = i / SHS, k = i % SHS;
@@ -1359,6 +1370,7 @@ __global__ void __launch_bounds__(b2::NT, 1) inr_bwd2_kernel(Args a) {
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    wait_weight_tiles(&s.bars[7]);
     const uint32_t tm = *s.tmem;
     const int sidx = warp >= NS * NE / 32 ? warp - NS * NE / 32 : warp / (NE / 32);  // stream of this warp
     uint64_t* bars = s.bars + sidx * BPS;
@@ -1806,7 +1818,7 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
     pp::Smem s(smem_raw, C);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const bool want_w = a.want_weights != 0;
-    load_weight_tiles(a, s);
+    load_weight_tiles(a, s, &s.bars[11]);
     if (warp == NE / 32) tmem_alloc(s.tmem, 512);
     if (t == 0) {
         mbar_init(&s.bars[B_OP], NE / 32), mbar_init(&s.bars[B_OP + 1], NE / 32);
@@ -1846,6 +1858,7 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
         }
     } else if (warp == NE / 32) {
         if (lane == 0) {  // ---- MMA issuer
+            wait_weight_tiles(&s.bars[11]);  // (the only reader of the weight tiles)
             const uint32_t ring_addr = smem_u32(s.ring), d_addr = smem_u32(s.dbuf), w_addr = smem_u32(s.wt);
             for (int j = 0; j < nPairs; ++j) {
                 const int ns = (2 * j + 1 < myTiles) ? 2 : 1;

@@ -77,6 +77,11 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src, u
                  "r"(bytes), "r"(smem_u32(bar)), "l"(l2_policy)
                  : "memory");
 }
+__device__ __forceinline__ void bulk_copy_g2s_plain(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
 // named barrier among `nthreads` threads (a multiple of 32) of the CTA; id 1..15 (0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
