@@ -4,7 +4,8 @@ Mirror of the reference interface laminr/coordinate_transforms.py:226-354 for th
 (`CoordinateTransform(only_affine=True)` -> `AffineTransform`): same constructor arguments, same parameter names
 (`transforms.Affine.{angles,scalings,shears,translation}`) and initial values, so `state_dict()` round-trips with the
 reference.  The arithmetic (M_d = R.S.Hs, coordinate map, clamp, gradients of the 7 scalars) runs inside the INR
-kernels (lmr_inr_forward / lmr_inr_backward); these modules only own the parameters.
+kernels (lmr_inr_forward / lmr_inr_backward); these modules own the parameters, and `forward` is a plain tensor-op mirror
+of the reference's for callers that map coordinates themselves.
 
 Out of scope: the RealNVP warp (`only_affine=False`) and the stochastic transform.
 """
@@ -44,8 +45,13 @@ class AffineTransform(nn.Module):
         Hs = torch.stack([torch.stack([one, self.shears[:, 0]], -1), torch.stack([self.shears[:, 1], one], -1)], -2)
         return R @ S @ Hs
 
-    def forward(self, x):
-        raise RuntimeError("laminr_b200: the affine transform is evaluated inside the fused INR kernels; call INRTemplates.forward")
+    def forward(self, x, stochastic=None):
+        """x [D, P, 2] -> M_d x + t_d (coordinate_transforms.py:299-309).  Host-side mirror for callers that map coordinates themselves (plots,
+        inspection of a matched transform): plain differentiable tensor ops on whatever device the parameters live on.  The optimisation loops
+        never call it -- learn / match evaluate the transform inside the fused INR kernels (lmr_inr_forward / lmr_inr_backward)."""
+        if stochastic:
+            raise NotImplementedError("laminr_b200: stochastic coordinate transforms are not supported (reference default is False)")
+        return torch.matmul(x, self.As.transpose(-1, -2)) + self.translation
 
 
 class CoordinateTransform(nn.Module):
