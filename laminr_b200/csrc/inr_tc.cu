@@ -2056,7 +2056,9 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                             __syncwarp();
                             arrive(&s.bars[B_OP + sl]);       // accumulator read: the next tile's z_4 may be issued
                             arrive(&s.bars[B_HFREE + rp.r]);
+                            if (t == 0 && j < 3) LMR_TRACE(0, 200 + (j * 2 + sl) * 4);
                             named_bar_sync(1, NE);
+                            if (t == 0 && j < 3) LMR_TRACE(0, 201 + (j * 2 + sl) * 4);
                             const TileIdx& tp = tis[sl];
                             if (t < TP * SHP) {
                                 const int g0_j = t / SHP, g0_o = t - g0_j * SHP;
@@ -2073,6 +2075,7 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                                     a.G0[((size_t)tp.d * tl.P + tp.p0 + g0_j) * SHP + g0_o] = sum;
                                 }
                             }
+                            if (t == 0 && j < 3) LMR_TRACE(0, 202 + (j * 2 + sl) * 4);
                             if (want_w) {
 #pragma unroll
                                 for (int q = 0; q < MAX_DA_PP; ++q) {
@@ -2089,6 +2092,7 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                             }
                             // every panel read must be done before a fast warp stores the next tile's dz_3 into D_s: for slot 0 the other slot's
                             // step (its named barrier above) lies in between; for the last slot of the pair nothing does
+                            if (t == 0 && j < 3) LMR_TRACE(0, 203 + (j * 2 + sl) * 4);
                             if (sl == ns - 1) named_bar_sync(1, NE);
                         }
                     }
@@ -2325,6 +2329,11 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
             cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
             const long long t0 = h[500];
             fprintf(stderr, "[trace pp] CTA 0: tiles done %lld  drain done %lld (cycles after the prologue)\n", h[501] - t0, h[502] - t0);
+            for (int j = 0; j < 3; ++j)
+                for (int sl = 0; sl < 2; ++sl) {
+                    const long long* f = h + 200 + (j * 2 + sl) * 4;
+                    fprintf(stderr, "[trace pp] pair %d slot %d last step: panel staged %6lld | barrier %6lld | G0 %6lld | dA %6lld\n", j, sl, f[0] - t0, f[1] - t0, f[2] - t0, f[3] - t0);
+                }
             for (int j = 0; j < 3; ++j)
                 for (int p = 0; p < 4; ++p)
                     for (int sl = 0; sl < 2; ++sl) {
