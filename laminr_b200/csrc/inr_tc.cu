@@ -264,6 +264,29 @@ __device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t x_addr, ui
     }
 }
 
+// the same into a 64-column accumulator: D[128 x 64] (+)= [X_hi | X_lo]^T . (Y_hi + Y_lo): two N = 64 products per 16 rows (adds the lo x lo term)
+__device__ __forceinline__ void issue_wgrad64(uint32_t tmem_d, uint32_t x_addr, uint32_t y_addr, bool zero_first) {
+    const uint32_t idesc = instr_desc(FMT_BF16, 128, 64, 1, 1);
+    uint64_t xd = smem_desc(x_addr, 128, 128 * 16), yd = smem_desc(y_addr, 128, 128 * 16);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        mma_f16(tmem_d, xd, yd, idesc, (ks > 0 || !zero_first) ? 1u : 0u);
+        mma_f16(tmem_d, xd, yd + (TILE_HALF >> 4), idesc, 1u);
+        xd += 256 >> 4, yd += 256 >> 4;
+    }
+}
+// layer-0 reductions of one tile: pixel columns -> tmem_g0[128 x 16] (overwritten), latent columns -> tmem_da[128 x 64] (accumulated)
+__device__ __forceinline__ void issue_l0(uint32_t tmem_g0, uint32_t tmem_da, uint32_t x_addr, uint32_t sel_addr, bool want_da, bool da_zero_first) {
+    const uint32_t idesc16 = instr_desc(FMT_BF16, 128, 16, 1, 1), idesc64 = instr_desc(FMT_BF16, 128, 64, 1, 1);
+    uint64_t xd = smem_desc(x_addr, 128, 128 * 16), yd = smem_desc(sel_addr, 128, 128 * 16);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+        mma_f16(tmem_g0, xd, yd, idesc16, ks > 0 ? 1u : 0u);
+        if (want_da) mma_f16(tmem_da, xd, yd, idesc64, (ks > 0 || !da_zero_first) ? 1u : 0u);
+        xd += 256 >> 4, yd += 256 >> 4;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // epilogue building blocks.  Epilogue thread = (row, column group g of NG): warps q, q+4, q+8, .. own TMEM lanes 32q..32q+31; group g
 // owns the 16-byte chunks (8 features) {g, g+NG, g+2NG, ..} < 8 of the row, so that the MMA k-chunks (16 features = chunks 2kc, 2kc+1)
@@ -1758,6 +1781,7 @@ namespace pp {
 constexpr int NG = 4, NE = 128 * NG, NT = NE + 64;  // 16 epilogue warps (4 lane quarters x 4 column groups) + the MMA warp + the loader warp
 constexpr int NCH = 8 / NG;                          // 16-byte chunks (8 features) per epilogue thread
 constexpr int NRING = 3;
+constexpr int SHP_PP = 52;           // live feature columns (SHP)
 constexpr uint32_t TM_ACC_S = 0;    // + 64 s: accumulator of slot s
 constexpr uint32_t TM_DW_PP = 128;  // + 128 (l - 1): weight-gradient accumulators
 // mbarriers; "slot" = one of the two tiles in flight.  As few as possible: every wait / arrive is ~100 cycles on the serial path of an epilogue step
@@ -1768,16 +1792,24 @@ constexpr int B_LAND = 4;   // [4..6]  ring buffer r: kept tile landed          
 constexpr int B_HFREE = 7;  // [7..9]  ring buffer r: its last reader (an epilogue step) has finished                             16 warp arrivals
 constexpr int B_DONE = 10;  // every MMA of the CTA has completed
 constexpr int NB = 12;
+// L0M variant (layer-0 reductions on the tensor core): G0[j][o] = sum_n dz_0 and dA[n][o] = sum_j dz_0 are both Sel^T dz_0 with a constant 0/1
+// selection tile Sel[row][col] (col j < 8: the row's pixel, col 8 + n: the row's latent).  TMEM: the dW accumulators in the 64-column form
+// ([dz_hi; dz_lo]^T (h_hi + h_lo): two N = 64 products per 16 rows into one accumulator, dW = lanes 0..63 + lanes 64..127) free 192 columns.
+constexpr uint32_t TM_DW64 = 128;   // + 64 (l - 1)
+constexpr uint32_t TM_DA = 320;     // [128 x 64]: latent columns 8.. accumulated over the CTA's tiles (columns 0..7: ignored)
+constexpr uint32_t TM_G0 = 384;     // + 16 s: [128 x 16] pixel columns 0..7 of slot s's last finished tile (columns 8..15: ignored)
+constexpr int SEL_LAT = 8;          // first latent column of Sel
+constexpr int G0X_STRIDE = 8;       // floats per feature of the hi / lo exchange buffer
 constexpr int MAX_DA_PP = 4;  // dA[n][o] accumulators per epilogue thread: N * 50 <= 4 * 512
 constexpr int STGP = 53;      // row stride (floats) of the fp32 dz_0 panel (odd: conflict-free both ways); 128 x 53 x 4 = 27 KB <= one tile
 
 struct Smem {
-    uint8_t *ring, *dbuf, *wt;
-    float *Wout, *bout;
+    uint8_t *ring, *dbuf, *wt, *sel;
+    float *Wout, *bout, *g0x;
     uint64_t* bars;
     uint32_t* tmem;
     size_t bytes;
-    __host__ __device__ Smem(uint8_t* base, int C) {
+    __host__ __device__ Smem(uint8_t* base, int C, bool l0m = false) {
         uint8_t* p = base;
         auto take = [&](size_t n) {
             uint8_t* r = p;
@@ -1787,10 +1819,12 @@ struct Smem {
         ring = take((size_t)NRING * TILE_BYTES);
         dbuf = take((size_t)2 * TILE_BYTES);
         wt = take((size_t)(LH - 1) * WT_BYTES);
+        sel = l0m ? take(TILE_HALF) : nullptr;  // hi half of an operand tile: 128 rows x 64 columns of bf16 zeros and ones
         Wout = reinterpret_cast<float*>(take((size_t)C * HPAD * 4));
         bout = reinterpret_cast<float*>(take(16));
         bars = reinterpret_cast<uint64_t*>(take(NB * 8));
         tmem = reinterpret_cast<uint32_t*>(take(16));
+        g0x = l0m ? reinterpret_cast<float*>(take((size_t)SHP_PP * G0X_STRIDE * 4)) : nullptr;
         bytes = p - base;
     }
 };
@@ -1809,16 +1843,29 @@ __device__ __forceinline__ RingPos ring_pos(int j, int ns, int l, int s) {
 }
 }  // namespace pp
 
-template <bool FAST, int C>
+template <bool FAST, int C, bool L0M>
 __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int reverse) {  // (18 warps are allocated as 20: at most 96 registers per thread)
     using namespace pp;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const Net& nt = a.net;
     const Tiling& tl = a.tl;
-    pp::Smem s(smem_raw, C);
+    pp::Smem s(smem_raw, C, L0M);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const bool want_w = a.want_weights != 0;
     load_weight_tiles(a, s, &s.bars[11]);
+    if (L0M) {  // the selection tile (constant for the kernel): row r = (latent nl, pixel j) of a tile -> ones in columns j and SEL_LAT + nl
+        for (int i = t; i < TILE_HALF / 16; i += NT) reinterpret_cast<uint4*>(s.sel)[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        if (t < 128) {
+            const int nl = t / tl.TP, jp = t - nl * tl.TP;
+            if (nl < tl.NC) {
+                const __nv_bfloat16 one = __float2bfloat16(1.f);
+                *reinterpret_cast<__nv_bfloat16*>(s.sel + tile_off(t, jp >> 3, 128) + (jp & 7) * 2) = one;
+                const int cl = SEL_LAT + nl;
+                *reinterpret_cast<__nv_bfloat16*>(s.sel + tile_off(t, cl >> 3, 128) + (cl & 7) * 2) = one;
+            }
+        }
+    }
     if (warp == NE / 32) tmem_alloc(s.tmem, 512);
     if (t == 0) {
         mbar_init(&s.bars[B_OP], NE / 32), mbar_init(&s.bars[B_OP + 1], NE / 32);
@@ -1860,6 +1907,13 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
         if (lane == 0) {  // ---- MMA issuer
             wait_weight_tiles(&s.bars[11]);  // (the only reader of the weight tiles)
             const uint32_t ring_addr = smem_u32(s.ring), d_addr = smem_u32(s.dbuf), w_addr = smem_u32(s.wt);
+            const uint32_t sel_addr = L0M ? smem_u32(s.sel) : 0u;
+            bool l0_pending[2] = {false, false};  // L0M: the slot's last tile has its dz_0 in D_s and its layer-0 products not issued yet
+            bool da_first = true;
+            auto flush_l0 = [&](int sl) {  // (behind a wait for the slot's last epilogue step)
+                issue_l0(tm + TM_G0 + 16u * sl, tm + TM_DA, d_addr + (uint32_t)sl * TILE_BYTES, sel_addr, want_w, da_first);
+                da_first = false, l0_pending[sl] = false;
+            };
             for (int j = 0; j < nPairs; ++j) {
                 const int ns = (2 * j + 1 < myTiles) ? 2 : 1;
                 // z_4 = h_3 W_3^T of both slots (the accumulator of a slot is free once the last epilogue step of its previous tile has read it)
@@ -1869,6 +1923,9 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                     mbar_wait(&s.bars[B_LAND + rp.r], (uint32_t)rp.n & 1);
                     if (j > 0) mbar_wait(&s.bars[B_OP + sl], 1);
                     fence_after_sync();
+                    // L0M: the previous tile of this slot left dz_0 in D_s (its last step is what the wait above was for): its layer-0 products
+                    // go in front of this tile's z_4, whose commit then also tells the epilogue that they are done and D_s is free
+                    if (L0M && l0_pending[sl]) flush_l0(sl);
                     const StageDesc sd = make_stage(ring_addr + (uint32_t)rp.r * TILE_BYTES, w_addr + (uint32_t)(LH - 2) * WT_BYTES, 0);
 #pragma unroll
                     for (int kc = 0; kc < 4; ++kc) issue_kstep(tm + TM_ACC_S + 64u * sl, sd, kc);
@@ -1895,12 +1952,23 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                                 mbar_wait(&s.bars[B_LAND + rp.r], (uint32_t)rp.n & 1);
                                 fence_after_sync();
                             }
-                            issue_wgrad(tm + TM_DW_PP + (uint32_t)(l - 1) * 128, dz, ring_addr + (uint32_t)rp.r * TILE_BYTES, j == 0 && sl == 0);
+                            if (L0M) issue_wgrad64(tm + TM_DW64 + (uint32_t)(l - 1) * 64, dz, ring_addr + (uint32_t)rp.r * TILE_BYTES, j == 0 && sl == 0);
+                            else issue_wgrad(tm + TM_DW_PP + (uint32_t)(l - 1) * 128, dz, ring_addr + (uint32_t)rp.r * TILE_BYTES, j == 0 && sl == 0);
                         }
                         mma_commit(&s.bars[B_ACC + sl]);
                         LMR_TRACE(1, (j * 4 + p) * 2 + sl);
+                        if (L0M && p == LH - 1) l0_pending[sl] = true;
                     }
                 }
+            }
+            if (L0M) {  // the last tile of each slot
+#pragma unroll 1
+                for (int sl = 0; sl < 2; ++sl)
+                    if (l0_pending[sl]) {
+                        mbar_wait(&s.bars[B_OP + sl], 1);
+                        fence_after_sync();
+                        flush_l0(sl);
+                    }
             }
             mma_commit(&s.bars[B_DONE]);
         }
@@ -1943,6 +2011,31 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
             }
         };
         fetch_gy(0);
+        // L0M: G0 of a finished tile sits in the slot's [128 x 16] accumulator (lanes 0..63: from dz_0's hi half, 64..127: lo half).  The four warps
+        // of column group 0 read it out -- lo lanes hand their values to the hi lanes through `g0x`, those write G0[pixel][feature] -- in front of
+        // an accumulator wait of the slot's NEXT tile (or behind the last MMA), where these warps would otherwise idle.
+        int g0_base[2] = {0, 0}, g0_np[2] = {0, 0};  // first pixel row (d * P + p0) and pixel count of the tile whose G0 is pending
+        bool g0_pend[2] = {false, false};
+        auto read_g0 = [&](int sl) {
+            if (rc.g == 0) {
+                float gv[8];
+                tmem_ld8(tm + TM_G0 + 16u * sl + rc.lane_taddr, gv);
+                tmem_ld_wait();
+                fence_before_sync();
+                named_bar_sync(2, 128);  // (the previous exchange has been consumed)
+                if (rc.row >= 64 && rc.row - 64 < SHP) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) s.g0x[(rc.row - 64) * G0X_STRIDE + jj] = gv[jj];
+                }
+                named_bar_sync(2, 128);
+                if (rc.row < SHP) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj)
+                        if (jj < g0_np[sl]) a.G0[((size_t)g0_base[sl] + jj) * SHP + rc.row] = gv[jj] + s.g0x[rc.row * G0X_STRIDE + jj];
+                }
+            }
+            g0_pend[sl] = false;
+        };
 
         for (int j = 0; j < nPairs; ++j) {
             const int ns = (2 * j + 1 < myTiles) ? 2 : 1;
@@ -2008,6 +2101,7 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                         const int l = LH - p;
                         const RingPos rp = ring_pos(j, ns, l, sl);
                         const uint8_t* Hl = s.ring + (size_t)rp.r * TILE_BYTES;
+                        if (L0M && p == 1 && g0_pend[sl]) read_g0(sl);  // (the slot's previous tile: its products completed before this tile's z_4)
                         // the accumulator first (ready ~1 k cycles early: the other slot's step was in between), its TMEM load in flight while the
                         // h tile is read and unpacked
                         mbar_wait(&s.bars[B_ACC + sl], (uint32_t)p & 1);
@@ -2029,7 +2123,8 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) v[4 * i + q] = fma2(mul2(v[4 * i + q], mul2(hv[4 * i + q], hv[4 * i + q])), make_float2(-1.f, -1.f), v[4 * i + q]);
                             }
-                        if (p < LH - 1) {
+                        if (p < LH - 1 || L0M) {
+                            // (L0M, last step: dz_0 is one more split-bf16 operand tile -- the MMA thread multiplies it by the selection tile)
 #pragma unroll
                             for (int i = 0; i < NCH; ++i)
                                 if (rc.g + NG * i < 7) store_chunk2<4>(Ds, rc.row, rc.g + NG * i, v + 4 * i);  // (chunk 7 keeps the zeros of the tile's first step)
@@ -2037,6 +2132,10 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                             __syncwarp();
                             arrive(&s.bars[B_OP + sl]);
                             arrive(&s.bars[B_HFREE + rp.r]);
+                            if (L0M && p == LH - 1) {
+                                g0_base[sl] = tis[sl].d * tl.P + tis[sl].p0, g0_np[sl] = tis[sl].np;
+                                g0_pend[sl] = true;
+                            }
                         } else {
                             // dz_0 feeds only CUDA-core reductions: fp32 panel stage[row][o] in D_s (its last readers, the dh_1 / dW_1 products, have
                             // completed: this step waited for their commit), then  G0[j][o] = sum_n dz0 -> global memory (layer-0 weight-gradient
@@ -2104,6 +2203,11 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
         if (t == 0) LMR_TRACE(0, 501);
         mbar_wait(&s.bars[B_DONE], 0);
         fence_after_sync();
+        if (L0M) {  // G0 of the last tile of each slot
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+                if (g0_pend[sl]) read_g0(sl);
+        }
         named_bar_sync(1, NE);
         if (want_w) {
             float* part = a.partials + (size_t)blockIdx.x * partial_size(nt, tl, SHP);
@@ -2116,16 +2220,17 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
 #pragma unroll 1
             for (int l = 1; l < LH; ++l) {
                 // D[m][n]: m = dz feature (hi 0..63 | lo 64..127), n = h feature (hi 0..63 | lo 64..127); dW = D_hh + D_hl + D_lh
-                const uint32_t dw = tm + TM_DW_PP + (uint32_t)(l - 1) * 128 + rc.lane_taddr;
+                // (L0M: one 64-column accumulator, n = h feature with hi + lo already summed by the two products per 16 rows)
+                const uint32_t dw = tm + (L0M ? TM_DW64 + (uint32_t)(l - 1) * 64 : TM_DW_PP + (uint32_t)(l - 1) * 128) + rc.lane_taddr;
                 float x[8 * NCH], y2[8 * NCH];
                 load_acc<NG>(dw, rc.g, x);
-                load_acc<NG>(dw + 64, rc.g, y2);
+                if (!L0M) load_acc<NG>(dw + 64, rc.g, y2);
 #pragma unroll
                 for (int i = 0; i < NCH; ++i) {
                     const int ch = rc.g + NG * i;
                     if (ch < 7) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) red[rc.row * RS + 8 * ch + k] = rc.row < 64 ? x[8 * i + k] + y2[8 * i + k] : x[8 * i + k];
+                        for (int k = 0; k < 8; ++k) red[rc.row * RS + 8 * ch + k] = (!L0M && rc.row < 64) ? x[8 * i + k] + y2[8 * i + k] : x[8 * i + k];
                     }
                 }
                 named_bar_sync(1, NE);
@@ -2159,10 +2264,28 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                 }
                 named_bar_sync(1, NE);
             }
+            if (L0M) {  // dA[n][o] = column SEL_LAT + n of the accumulated latent product, lanes o (hi) + 64 + o (lo)
+                float x[8 * NCH];
+                load_acc<NG>(tm + TM_DA + rc.lane_taddr, rc.g, x);
 #pragma unroll
-            for (int q = 0; q < MAX_DA_PP; ++q) {
-                const int e = t + NE * q, n = e / HID, o = e - n * HID;
-                if (n < tl.NC) p_dA[n * SHP + o] = dA[q];
+                for (int i = 0; i < NCH; ++i) {
+                    const int ch = rc.g + NG * i;
+                    if (ch < 7) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) red[rc.row * RS + 8 * ch + k] = x[8 * i + k];
+                    }
+                }
+                named_bar_sync(1, NE);
+                for (int i = t; i < tl.NC * HID; i += NE) {
+                    const int n = i / HID, o = i - n * HID;
+                    p_dA[n * SHP + o] = red[o * RS + SEL_LAT + n] + red[(64 + o) * RS + SEL_LAT + n];
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < MAX_DA_PP; ++q) {
+                    const int e = t + NE * q, n = e / HID, o = e - n * HID;
+                    if (n < tl.NC) p_dA[n * SHP + o] = dA[q];
+                }
             }
         }
     }
@@ -2310,17 +2433,22 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
     static const bool use_pp = !(getenv("LMR_BWD_PP") && atoi(getenv("LMR_BWD_PP")) == 0);
     static const int pp_reverse = getenv("LMR_BWD_REVERSE") ? atoi(getenv("LMR_BWD_REVERSE")) : 1;
     if (loadh && use_pp) {
-        pp::Smem sp(nullptr, nt.C);
-        const size_t smem = sp.bytes + 1024;
+        // layer-0 reductions on the tensor core (LMR_BWD_L0M=0: the fp32 panel on CUDA cores of round 2 a); needs N <= 40 latents per tile (selection
+        // columns 8 .. 8 + N) -- guaranteed by the check above
+        static const bool l0m = !(getenv("LMR_BWD_L0M") && atoi(getenv("LMR_BWD_L0M")) == 0);
+        pp::Smem sp(nullptr, nt.C, l0m);
+        const size_t smem = sp.bytes + (l0m ? 0 : 1024);
         LMR_CHECK_ARG(smem <= 227 * 1024, "inr_backward (tensor-core path): needs %zu bytes of shared memory (> 227 KB)", smem);
-        static size_t cachep[2][5] = {};
-#define LMR_BWD_PP_CASE(FASTV, CV)                                                                       \
-    if (fast == FASTV && nt.C == CV) {                                                                   \
-        if (int rc = set_smem(inr_bwd_pp_kernel<FASTV, CV>, smem, &cachep[FASTV][CV])) return rc;       \
-        inr_bwd_pp_kernel<FASTV, CV><<<wl.gridMain, pp::NT, smem, st>>>(a, pp_reverse);                  \
+        static size_t cachep[2][2][5] = {};
+#define LMR_BWD_PP_CASE(FASTV, CV, L0V)                                                                          \
+    if (fast == FASTV && nt.C == CV && l0m == L0V) {                                                             \
+        if (int rc = set_smem(inr_bwd_pp_kernel<FASTV, CV, L0V>, smem, &cachep[L0V][FASTV][CV])) return rc;     \
+        inr_bwd_pp_kernel<FASTV, CV, L0V><<<wl.gridMain, pp::NT, smem, st>>>(a, pp_reverse);                     \
     }
-        LMR_BWD_PP_CASE(false, 1) LMR_BWD_PP_CASE(false, 2) LMR_BWD_PP_CASE(false, 3) LMR_BWD_PP_CASE(false, 4)
-        LMR_BWD_PP_CASE(true, 1) LMR_BWD_PP_CASE(true, 2) LMR_BWD_PP_CASE(true, 3) LMR_BWD_PP_CASE(true, 4)
+        LMR_BWD_PP_CASE(false, 1, false) LMR_BWD_PP_CASE(false, 2, false) LMR_BWD_PP_CASE(false, 3, false) LMR_BWD_PP_CASE(false, 4, false)
+        LMR_BWD_PP_CASE(true, 1, false) LMR_BWD_PP_CASE(true, 2, false) LMR_BWD_PP_CASE(true, 3, false) LMR_BWD_PP_CASE(true, 4, false)
+        LMR_BWD_PP_CASE(false, 1, true) LMR_BWD_PP_CASE(false, 2, true) LMR_BWD_PP_CASE(false, 3, true) LMR_BWD_PP_CASE(false, 4, true)
+        LMR_BWD_PP_CASE(true, 1, true) LMR_BWD_PP_CASE(true, 2, true) LMR_BWD_PP_CASE(true, 3, true) LMR_BWD_PP_CASE(true, 4, true)
 #undef LMR_BWD_PP_CASE
         LMR_LAUNCH_OK();
         if (tracing) {  // debug only: synchronises and prints CTA 0's time line -- per (pair, step, slot): epilogue thread 0 enters / has the accumulator / is
