@@ -2460,7 +2460,8 @@ int backward(const lmr_inr_desc* desc, const float* params, const float* B, cons
             for (int j = 0; j < 3; ++j)
                 for (int sl = 0; sl < 2; ++sl) {
                     const long long* f = h + 200 + (j * 2 + sl) * 4;
-                    fprintf(stderr, "[trace pp] pair %d slot %d last step: panel staged %6lld | barrier %6lld | G0 %6lld | dA %6lld\n", j, sl, f[0] - t0, f[1] - t0, f[2] - t0, f[3] - t0);
+                    if (f[0] != 0)  // (fp32-panel variant only, LMR_BWD_L0M=0)
+                        fprintf(stderr, "[trace pp] pair %d slot %d last step: panel staged %6lld | barrier %6lld | G0 %6lld | dA %6lld\n", j, sl, f[0] - t0, f[1] - t0, f[2] - t0, f[3] - t0);
                 }
             for (int j = 0; j < 3; ++j)
                 for (int p = 0; p < 4; ++p)
