@@ -275,14 +275,14 @@ __device__ __forceinline__ void issue_wgrad64(uint32_t tmem_d, uint32_t x_addr, 
         xd += 256 >> 4, yd += 256 >> 4;
     }
 }
-// layer-0 reductions of one tile: pixel columns -> tmem_g0[128 x 16] (overwritten), latent columns -> tmem_da[128 x 64] (accumulated)
-__device__ __forceinline__ void issue_l0(uint32_t tmem_g0, uint32_t tmem_da, uint32_t x_addr, uint32_t sel_addr, bool want_da, bool da_zero_first) {
-    const uint32_t idesc16 = instr_desc(FMT_BF16, 128, 16, 1, 1), idesc64 = instr_desc(FMT_BF16, 128, 64, 1, 1);
+// layer-0 reductions of one tile: tmem_l0[128 x n_cols] += [X_hi | X_lo]^T . Sel[:, 0 .. n_cols): ONE accumulating product per 16 rows.  The
+// latent columns are meant to accumulate over the slot's tiles; the pixel columns are zeroed by the epilogue warps that read them out.
+__device__ __forceinline__ void issue_l0(uint32_t tmem_l0, uint32_t x_addr, uint32_t sel_addr, int n_cols) {
+    const uint32_t idesc = n_cols == 32 ? instr_desc(FMT_BF16, 128, 32, 1, 1) : instr_desc(FMT_BF16, 128, 64, 1, 1);
     uint64_t xd = smem_desc(x_addr, 128, 128 * 16), yd = smem_desc(sel_addr, 128, 128 * 16);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
-        mma_f16(tmem_g0, xd, yd, idesc16, ks > 0 ? 1u : 0u);
-        if (want_da) mma_f16(tmem_da, xd, yd, idesc64, (ks > 0 || !da_zero_first) ? 1u : 0u);
+        mma_f16(tmem_l0, xd, yd, idesc, 1u);
         xd += 256 >> 4, yd += 256 >> 4;
     }
 }
@@ -1795,9 +1795,25 @@ constexpr int NB = 12;
 // L0M variant (layer-0 reductions on the tensor core): G0[j][o] = sum_n dz_0 and dA[n][o] = sum_j dz_0 are both Sel^T dz_0 with a constant 0/1
 // selection tile Sel[row][col] (col j < 8: the row's pixel, col 8 + n: the row's latent).  TMEM: the dW accumulators in the 64-column form
 // ([dz_hi; dz_lo]^T (h_hi + h_lo): two N = 64 products per 16 rows into one accumulator, dW = lanes 0..63 + lanes 64..127) free 192 columns.
-constexpr uint32_t TM_DW64 = 128;   // + 64 (l - 1)
-constexpr uint32_t TM_DA = 320;     // [128 x 64]: latent columns 8.. accumulated over the CTA's tiles (columns 0..7: ignored)
-constexpr uint32_t TM_G0 = 384;     // + 16 s: [128 x 16] pixel columns 0..7 of slot s's last finished tile (columns 8..15: ignored)
+// Column map behind the two slot accumulators [0, 128), by the number of latents NC that share a tile:
+//   NC <= 24 ("narrow": selection columns 0 .. 8 + NC fit N = 32):  dW_3 [128, 256) and dW_2 [256, 384) in the 128-column form (one N = 128 product
+//            per 16 rows streams 8 KB of operands instead of 12), dW_1 [384, 448) in the 64-column form, layer-0 accumulators [448 + 32 s, +32)
+//   NC <= 40 ("wide", N = 64):  dW_l [128 + 64 (l - 1), +64), layer-0 accumulators [320 + 64 s, +64)
+struct TmMap {
+    bool narrow;
+    uint32_t l0;  // first column of slot 0's layer-0 accumulator
+    int nl0;      // its columns (= the product's N)
+    __device__ __forceinline__ bool dw128(int l) const { return narrow && l > 1; }  // dW_l in the 128-column form?
+    __device__ __forceinline__ uint32_t dw(int l) const {                            // first column of dW_l, l = 1 .. LH - 1
+        return narrow ? (l == 1 ? 384u : 128u + 128u * (uint32_t)(LH - 1 - l)) : 128u + 64u * (uint32_t)(l - 1);
+    }
+};
+__device__ __forceinline__ TmMap tm_map(int NC) {
+    TmMap m;
+    m.narrow = NC <= 24;
+    m.l0 = m.narrow ? 448u : 320u, m.nl0 = m.narrow ? 32 : 64;
+    return m;
+}
 constexpr int SEL_LAT = 8;          // first latent column of Sel
 constexpr int G0X_STRIDE = 8;       // floats per feature of the hi / lo exchange buffer
 constexpr int MAX_DA_PP = 4;  // dA[n][o] accumulators per epilogue thread: N * 50 <= 4 * 512
@@ -1909,10 +1925,10 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
             const uint32_t ring_addr = smem_u32(s.ring), d_addr = smem_u32(s.dbuf), w_addr = smem_u32(s.wt);
             const uint32_t sel_addr = L0M ? smem_u32(s.sel) : 0u;
             bool l0_pending[2] = {false, false};  // L0M: the slot's last tile has its dz_0 in D_s and its layer-0 products not issued yet
-            bool da_first = true;
+            const TmMap tmm = tm_map(tl.NC);
             auto flush_l0 = [&](int sl) {  // (behind a wait for the slot's last epilogue step)
-                issue_l0(tm + TM_G0 + 16u * sl, tm + TM_DA, d_addr + (uint32_t)sl * TILE_BYTES, sel_addr, want_w, da_first);
-                da_first = false, l0_pending[sl] = false;
+                issue_l0(tm + tmm.l0 + (uint32_t)(tmm.nl0 * sl), d_addr + (uint32_t)sl * TILE_BYTES, sel_addr, tmm.nl0);
+                l0_pending[sl] = false;
             };
             for (int j = 0; j < nPairs; ++j) {
                 const int ns = (2 * j + 1 < myTiles) ? 2 : 1;
@@ -1952,8 +1968,8 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                                 mbar_wait(&s.bars[B_LAND + rp.r], (uint32_t)rp.n & 1);
                                 fence_after_sync();
                             }
-                            if (L0M) issue_wgrad64(tm + TM_DW64 + (uint32_t)(l - 1) * 64, dz, ring_addr + (uint32_t)rp.r * TILE_BYTES, j == 0 && sl == 0);
-                            else issue_wgrad(tm + TM_DW_PP + (uint32_t)(l - 1) * 128, dz, ring_addr + (uint32_t)rp.r * TILE_BYTES, j == 0 && sl == 0);
+                            if (L0M && !tmm.dw128(l)) issue_wgrad64(tm + tmm.dw(l), dz, ring_addr + (uint32_t)rp.r * TILE_BYTES, j == 0 && sl == 0);
+                            else issue_wgrad(tm + (L0M ? tmm.dw(l) : TM_DW_PP + (uint32_t)(l - 1) * 128), dz, ring_addr + (uint32_t)rp.r * TILE_BYTES, j == 0 && sl == 0);
                         }
                         mma_commit(&s.bars[B_ACC + sl]);
                         LMR_TRACE(1, (j * 4 + p) * 2 + sl);
@@ -2011,16 +2027,30 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
             }
         };
         fetch_gy(0);
-        // L0M: G0 of a finished tile sits in the slot's [128 x 16] accumulator (lanes 0..63: from dz_0's hi half, 64..127: lo half).  The four warps
-        // of column group 0 read it out -- lo lanes hand their values to the hi lanes through `g0x`, those write G0[pixel][feature] -- in front of
-        // an accumulator wait of the slot's NEXT tile (or behind the last MMA), where these warps would otherwise idle.
+        // L0M: G0 of a finished tile sits in the pixel columns 0..7 of the slot's layer-0 accumulator (lanes 0..63: from dz_0's hi half, 64..127: lo
+        // half).  The four warps of column group 0 read it out -- lo lanes hand their values to the hi lanes through `g0x`, those write
+        // G0[pixel][feature] -- in front of an accumulator wait of the slot's NEXT tile (or behind the last MMA), where these warps would otherwise
+        // idle, and ZERO the columns again: the slot's products accumulate (the latent columns are sums over the slot's tiles).
+        const TmMap tmm = tm_map(tl.NC);
         int g0_base[2] = {0, 0}, g0_np[2] = {0, 0};  // first pixel row (d * P + p0) and pixel count of the tile whose G0 is pending
         bool g0_pend[2] = {false, false};
+        if (L0M && rc.g == 0) {  // both accumulators start from zero (ordered before the first product by the arrivals of the first tile's steps)
+            const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            for (int c = 0; c < 2 * tmm.nl0; c += 8) tmem_st8(tm + tmm.l0 + (uint32_t)c + rc.lane_taddr, z);
+            tmem_st_wait();
+            fence_before_sync();
+        }
         auto read_g0 = [&](int sl) {
             if (rc.g == 0) {
                 float gv[8];
-                tmem_ld8(tm + TM_G0 + 16u * sl + rc.lane_taddr, gv);
+                const uint32_t gaddr = tm + tmm.l0 + (uint32_t)(tmm.nl0 * sl) + rc.lane_taddr;
+                tmem_ld8(gaddr, gv);
                 tmem_ld_wait();
+                {
+                    const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                    tmem_st8(gaddr, z);
+                    tmem_st_wait();
+                }
                 fence_before_sync();
                 named_bar_sync(2, 128);  // (the previous exchange has been consumed)
                 if (rc.row >= 64 && rc.row - 64 < SHP) {
@@ -2220,17 +2250,18 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
 #pragma unroll 1
             for (int l = 1; l < LH; ++l) {
                 // D[m][n]: m = dz feature (hi 0..63 | lo 64..127), n = h feature (hi 0..63 | lo 64..127); dW = D_hh + D_hl + D_lh
-                // (L0M: one 64-column accumulator, n = h feature with hi + lo already summed by the two products per 16 rows)
-                const uint32_t dw = tm + (L0M ? TM_DW64 + (uint32_t)(l - 1) * 64 : TM_DW_PP + (uint32_t)(l - 1) * 128) + rc.lane_taddr;
+                // (64-column form: ONE accumulator, n = h feature with hi + lo already summed by the two products per 16 rows)
+                const bool form128 = !L0M || tmm.dw128(l);
+                const uint32_t dw = tm + (L0M ? tmm.dw(l) : TM_DW_PP + (uint32_t)(l - 1) * 128) + rc.lane_taddr;
                 float x[8 * NCH], y2[8 * NCH];
                 load_acc<NG>(dw, rc.g, x);
-                if (!L0M) load_acc<NG>(dw + 64, rc.g, y2);
+                if (form128) load_acc<NG>(dw + 64, rc.g, y2);
 #pragma unroll
                 for (int i = 0; i < NCH; ++i) {
                     const int ch = rc.g + NG * i;
                     if (ch < 7) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) red[rc.row * RS + 8 * ch + k] = (!L0M && rc.row < 64) ? x[8 * i + k] + y2[8 * i + k] : x[8 * i + k];
+                        for (int k = 0; k < 8; ++k) red[rc.row * RS + 8 * ch + k] = (form128 && rc.row < 64) ? x[8 * i + k] + y2[8 * i + k] : x[8 * i + k];
                     }
                 }
                 named_bar_sync(1, NE);
@@ -2264,15 +2295,25 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
                 }
                 named_bar_sync(1, NE);
             }
-            if (L0M) {  // dA[n][o] = column SEL_LAT + n of the accumulated latent product, lanes o (hi) + 64 + o (lo)
-                float x[8 * NCH];
-                load_acc<NG>(tm + TM_DA + rc.lane_taddr, rc.g, x);
+            if (L0M) {  // dA[n][o] = column SEL_LAT + n of the two slots' accumulated latent products, lanes o (hi) + 64 + o (lo)
+                float x[8 * NCH], y2[8 * NCH];
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int ch = rc.g + NG * i;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) x[8 * i + k] = 0.f, y2[8 * i + k] = 0.f;
+                    if (8 * ch < tmm.nl0) {
+                        tmem_ld8(tm + tmm.l0 + (uint32_t)(8 * ch) + rc.lane_taddr, x + 8 * i);
+                        tmem_ld8(tm + tmm.l0 + (uint32_t)(tmm.nl0 + 8 * ch) + rc.lane_taddr, y2 + 8 * i);
+                    }
+                }
+                tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < NCH; ++i) {
                     const int ch = rc.g + NG * i;
                     if (ch < 7) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) red[rc.row * RS + 8 * ch + k] = x[8 * i + k];
+                        for (int k = 0; k < 8; ++k) red[rc.row * RS + 8 * ch + k] = x[8 * i + k] + y2[8 * i + k];
                     }
                 }
                 named_bar_sync(1, NE);
