@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(NT_F, 2) inr_fwd_tc_kernel(Args a) {
     uint8_t* T = s.tiles;
 
     if (warp == NE / 32) {
-        if (lane == 0) {  // ---- MMA issuer: stage st computes z_{st+1} = h_{st+1} W^T into accumulator st&1 as the chunks of h_{st+1} arrive
+        if (elect_one()) {  // ---- MMA issuer: stage st computes z_{st+1} = h_{st+1} W^T into accumulator st&1 as the chunks of h_{st+1} arrive
             const uint32_t t_addr = smem_u32(T), w_addr = smem_u32(s.wt);
             uint32_t pk = 0;
             for (int it = 0; it < myTiles; ++it) {
@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(NT_T, 4) inr_fwd_ts_kernel(Args a) {
     const int myTiles = (tl.numTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp == NE_T / 32) {
-        if (lane == 0) {  // ---- MMA issuer
+        if (elect_one()) {  // ---- MMA issuer
             wait_weight_tiles(&s.bars[7]);  // only this thread needs the weight tiles: the epilogue warps start the first tile's h_1 at once
             const uint32_t w_addr = smem_u32(s.wt);
             const uint32_t idesc = instr_desc(FMT_BF16, 128, HPAD, 0, 0);
@@ -847,7 +847,7 @@ __global__ void __launch_bounds__(128 * NG + 64, 1) inr_bwd_tc_kernel(Args a) {
     } else
 
     if (warp == NE / 32) {
-        if (lane == 0) {  // ---- MMA issuer
+        if (elect_one()) {  // ---- MMA issuer
             const uint32_t tiles_addr = smem_u32(s.tiles), w_addr = smem_u32(s.wt);
             uint32_t pk = 0;
             for (int it = 0; it < myTiles; ++it) {
@@ -1404,7 +1404,7 @@ __global__ void __launch_bounds__(b2::NT, 1) inr_bwd2_kernel(Args a) {
     const uint32_t dw_base = tm + TM_DW2 + (uint32_t)sidx * 192;
 
     if (warp >= NS * NE / 32) {
-        if (lane == 0) {  // ---- MMA issuer of stream sidx
+        if (elect_one()) {  // ---- MMA issuer of stream sidx
             const uint32_t tiles_addr = smem_u32(tiles), w_addr = smem_u32(s.wt);
             uint32_t pk = 0;
             for (int it = 0; it < myTiles; ++it) {
@@ -1903,7 +1903,7 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
     if (t == 0) LMR_TRACE(0, 500);
 
     if (warp == NE / 32 + 1) {
-        if (lane == 0) {  // ---- loader: h_3, h_2, h_1 of both slots of every pair, each as soon as its ring buffer has been released
+        if (elect_one()) {  // ---- loader: h_3, h_2, h_1 of both slots of every pair, each as soon as its ring buffer has been released
             const uint64_t pol = l2_policy_evict_first();  // read once
             for (int j = 0; j < nPairs; ++j) {
                 const int ns = (2 * j + 1 < myTiles) ? 2 : 1;
@@ -1920,7 +1920,7 @@ __global__ void __launch_bounds__(pp::NT, 1) inr_bwd_pp_kernel(Args a, int rever
             }
         }
     } else if (warp == NE / 32) {
-        if (lane == 0) {  // ---- MMA issuer
+        if (elect_one()) {  // ---- MMA issuer
             wait_weight_tiles(&s.bars[11]);  // (the only reader of the weight tiles)
             const uint32_t ring_addr = smem_u32(s.ring), d_addr = smem_u32(s.dbuf), w_addr = smem_u32(s.wt);
             const uint32_t sel_addr = L0M ? smem_u32(s.sel) : 0u;

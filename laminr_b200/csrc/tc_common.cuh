@@ -117,6 +117,20 @@ __host__ __device__ constexpr uint32_t instr_desc(uint32_t fmt, int M, int N, in
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// one lane of a converged warp (elect.sync): code dominated by this predicate is known to the compiler to run on a single thread -- under a plain
+// `if (lane == 0)` every tcgen05.mma was wrapped in a lane-election loop (ELECT / R2UR / BRA.U.ANY: 7-15 instructions per MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- MMA (single thread issues) -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
