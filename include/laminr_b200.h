@@ -205,8 +205,10 @@ typedef struct {
 } lmr_convcore_desc;
 
 typedef struct {
-    const float* w_fwd[LMR_CONV_MAX_LAYERS];  /* [c_in_l, k, k, hidden]: conv.weight.permute(1,2,3,0) */
-    const float* w_bwd[LMR_CONV_MAX_LAYERS];  /* [hidden, k, k, c_in_l]: conv.weight.flip(2,3).permute(0,2,3,1); may be NULL for forward-only calls */
+    /* channel-blocked: CB(n) = 4 if n % 4 == 0, else 2 if n is even, else 1 */
+    const float* w_fwd[LMR_CONV_MAX_LAYERS];  /* [c_in_l][k][hidden / CB][k][CB], CB = CB(hidden): element [ci][ky][co / CB][kx][co % CB] = conv.weight[co][ci][ky][kx] */
+    const float* w_bwd[LMR_CONV_MAX_LAYERS];  /* [hidden][k][c_in_l / CB][k][CB], CB = CB(c_in_l): element [co][ky][ci / CB][kx][ci % CB] = conv.weight[co][ci][k-1-ky][k-1-kx];
+                                                 may be NULL for forward-only calls */
     const float* scale[LMR_CONV_MAX_LAYERS];  /* [hidden] gamma / sqrt(running_var + eps)  (1 without batch norm) */
     const float* shift[LMR_CONV_MAX_LAYERS];  /* [hidden] beta + (conv_bias - running_mean) * scale */
     const float* mu;                          /* [n_neurons, 2] readout positions (x -> width, y -> height); clamped to [-1,1] by the kernel */

@@ -29,6 +29,13 @@ namespace cone {
 constexpr int NT = 512;
 constexpr int MAXL = LMR_CONV_MAX_LAYERS;
 constexpr int TILE = 16;  // outputs per item: CB channels x XB pixels
+#ifndef LMR_CONE_UNROLL
+#define LMR_CONE_UNROLL 1
+#endif
+constexpr int ROW_UNROLL = LMR_CONE_UNROLL;
+#ifndef LMR_CONE_ITEMS_INLINE
+#define LMR_CONE_ITEMS_INLINE __device__ __forceinline__
+#endif
 
 __host__ __device__ inline int pick_cb(int co) { return (co % 4 == 0) ? 4 : (co % 2 == 0) ? 2 : 1; }
 // number of (pixel block, channel block) items of a convolution with So x So outputs and Co channels
@@ -42,6 +49,8 @@ struct Plan {  // built on the host, handed to the kernel inside Args (parameter
     int halo[MAXL];  // window origin of layer l's output = top-left readout tap - halo[l]  (sum of k/2 of the layers above)
     int halo_in;     // the same for the input window
     int Sin;         // input window edge
+    int GS[MAXL];    // row stride of layer l's gradient map: S[l] + 2 (k_l - 1) -- k_l - 1 zeros on either side of every row, so that the
+                     // data-gradient ("full") correlation reads its rows without bounds checks -- or S[l] (unpadded, see make_plan)
     int off_in, off_a[MAXL], off_g[MAXL], off_gin, off_scratch, total;  // float offsets into dynamic shared memory
 };
 
@@ -60,14 +69,19 @@ __host__ __device__ inline void make_plan(const lmr_convcore_desc& d, bool with_
         items = n > items ? n : items;
     }
     if (with_grad) {
-        for (int l = 0; l < L; ++l) p.off_g[l] = take(d.hidden * p.S[l] * p.S[l]);
+        for (int l = 0; l < L; ++l) {
+            // padded rows where the data-gradient convolution that reads the map runs 4-channel blocks (the bulk of the work); the others keep
+            // plain rows and check their bounds: shared memory left over is L1 cache, and the weight rows are shared between warps through L1
+            const bool pad = pick_cb(l == 0 ? d.c_in : d.hidden) == 4;
+            p.GS[l] = p.S[l] + (pad ? 2 * (d.kernel[l] - 1) : 0), p.off_g[l] = take(d.hidden * p.S[l] * p.GS[l]);
+        }
         p.off_gin = take(d.c_in * p.Sin * p.Sin);
         for (int l = 0; l < L; ++l) {
             const int n = flat_items(l == 0 ? p.Sin : p.S[l - 1], l == 0 ? d.c_in : d.hidden);
             items = n > items ? n : items;
         }
     } else {
-        for (int l = 0; l < L; ++l) p.off_g[l] = 0;
+        for (int l = 0; l < L; ++l) p.off_g[l] = 0, p.GS[l] = 0;
         p.off_gin = 0;
     }
     p.off_scratch = take(items * TILE);
@@ -88,18 +102,58 @@ struct Args {
     Plan pl;
 };
 
-// Partial sums of a stride-1 correlation: out[co, y, x] = sum_{ci in split, ky, kx} in[ci, y + ky - vp, x + kx - vp] * Wt[ci, ky, kx, co], input taken
-// as 0 outside [0,Sin)^2 (vp = 0: "valid" forward convolution of the window; vp = k-1: "full" data-gradient convolution).
+// Partial sums of a stride-1 correlation: out[co, y, x] = sum_{ci in split, ky, kx} in[ci][y + ky - vp][x + kx] * W[ci, ky, kx, co] over an input of
+// `rows` rows with row stride RS and plane stride PS; rows outside [0, rows) count as 0 (vp = 0: "valid" forward convolution of the window;
+// vp = k-1: "full" data-gradient convolution; its input rows either carry k-1 zeros on both sides (xlim = 0: no bounds in x at all) or are
+// unpadded rows of xlim values, bounds-checked per load).
 // This CTA computes the items [lo, hi) of the flat (pixel block, channel block) space (channel block fastest), each split over `ksplit`
 // input-channel ranges; scratch[(ks*(hi-lo) + item-lo)*TILE + c*XB + j] receives the partial sums.
-// K > 0: kernel size known at compile time (rows preloaded into registers); K == 0: any size (sliding window).
+// Weights: Wt[ci][ky][co / CB][kx][CB] -- the K*CB values a thread needs for one (ci, ky) row are contiguous: one base pointer, immediate offsets.
+// K > 0: kernel size known at compile time: the weights of row r+1 are loaded (second register set) before the K*CB*XB FMAs of row r run;
+// K == 0: any size (sliding window).
 template <int CB, int K>
-__device__ __forceinline__ void conv_items(const float* __restrict__ in, int Cin, int Sin, int vp, int So, int Co, int kdyn, const float* __restrict__ Wt,
-                                           float* __restrict__ scratch, int lo, int hi, int ksplit) {
+__device__ __forceinline__ void load_wrow(const float* __restrict__ wp, float (&w)[K > 0 ? K : 1][CB]) {
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+        if constexpr (CB == 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(wp) + kx);
+            w[kx][0] = q.x, w[kx][1] = q.y, w[kx][2] = q.z, w[kx][3] = q.w;
+        } else if constexpr (CB == 2) {
+            const float2 q = __ldg(reinterpret_cast<const float2*>(wp) + kx);
+            w[kx][0] = q.x, w[kx][1] = q.y;
+        } else {
+            w[kx][0] = __ldg(wp + kx);
+        }
+    }
+}
+// row = first input value of the block (x index xb of an unpadded row when xlim > 0: values outside [0, xlim) count as 0)
+template <int CB, int K>
+__device__ __forceinline__ void fma_row(const float* __restrict__ row, int xb, int xlim, const float (&w)[K > 0 ? K : 1][CB], float (&acc)[CB][TILE / CB]) {
+    constexpr int XB = TILE / CB, RW = XB + K - 1;
+    float r[RW];  // ragged pixel blocks read (finite or not) junk that only reaches accumulators which are never stored
+    if (xlim > 0) {
+#pragma unroll
+        for (int j = 0; j < RW; ++j) r[j] = (unsigned)(xb + j) < (unsigned)xlim ? row[j] : 0.f;
+    } else {
+#pragma unroll
+        for (int j = 0; j < RW; ++j) r[j] = row[j];
+    }
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+        for (int c = 0; c < CB; ++c)
+#pragma unroll
+            for (int j = 0; j < XB; ++j) acc[c][j] = fmaf(w[kx][c], r[j + kx], acc[c][j]);
+}
+
+template <int CB, int K>
+LMR_CONE_ITEMS_INLINE void conv_items(const float* __restrict__ in, int Cin, int RS, int PS, int rows, int vp, int xlim, int So, int Co, int kdyn,
+                                           const float* __restrict__ Wt, float* __restrict__ scratch, int lo, int hi, int ksplit) {
     constexpr int XB = TILE / CB;
     const int k = K > 0 ? K : kdyn;
     const int nseg = (So + XB - 1) / XB, ncb = Co / CB;
     const int nloc = hi - lo, nitems = nloc * ksplit;
+    const int wstep = ncb * k * CB;  // floats from one (ci, ky) weight row to the next
     for (int item = threadIdx.x; item < nitems; item += NT) {
         const int ks = item / nloc, fl = lo + item - ks * nloc;
         const int sp = fl / ncb, cb = fl - sp * ncb;
@@ -110,105 +164,73 @@ __device__ __forceinline__ void conv_items(const float* __restrict__ in, int Cin
         for (int c = 0; c < CB; ++c)
 #pragma unroll
             for (int j = 0; j < XB; ++j) acc[c][j] = 0.f;
-        const int kx_lo = max(0, vp - x0 - (XB - 1)), kx_hi = min(k, vp - x0 + Sin);
-        const int ky_lo = max(0, vp - y), ky_hi = min(k, vp - y + Sin);
-        const int xb = x0 - vp;
-        for (int ci = c_lo; ci < c_hi; ++ci) {
-            const float* plane = in + ci * Sin * Sin;
-            for (int ky = ky_lo; ky < ky_hi; ++ky) {
-                const float* row = plane + (y + ky - vp) * Sin;
-                const float* wrow = Wt + ((size_t)(ci * k + ky) * k) * Co + cb * CB;
-                if constexpr (K > 0) {
-                    constexpr int RW = XB + K - 1;
-                    float wv[K][CB];
+        const int ky_lo = max(0, vp - y), ky_hi = min(k, vp - y + rows), nky = ky_hi - ky_lo;
+        const int nrows = nky > 0 ? (c_hi - c_lo) * nky : 0;
+        const float* wp = Wt + ((size_t)(c_lo * k + ky_lo) * ncb + cb) * (k * CB);
+        const int xb = xlim > 0 ? x0 - vp : x0;  // unpadded rows (xlim > 0): the block starts vp values to the left, bounds checked per value
+        const float* rp = in + c_lo * PS + (y + ky_lo - vp) * RS + xb;
+        const int wskip = (k - nky) * wstep, rskip = PS - nky * RS;  // extra steps when the row index wraps to the next input channel
+        int kyc = 0;
+        auto advance = [&]() {
+            wp += wstep, rp += RS;
+            if (++kyc == nky) kyc = 0, wp += wskip, rp += rskip;
+        };
+        if constexpr (K > 0) {
+#pragma unroll ROW_UNROLL
+            for (int rr = 0; rr < nrows; ++rr) {
+                float w0[K][CB];
+                load_wrow<CB, K>(wp, w0);
+                fma_row<CB, K>(rp, xb, xlim, w0, acc);
+                advance();
+            }
+        } else {
+#pragma unroll 1
+            for (int rr = 0; rr < nrows; ++rr) {
+                float r[XB];
+                auto ld = [&](int j) { return (xlim <= 0 || (unsigned)(xb + j) < (unsigned)xlim) ? rp[j] : 0.f; };
 #pragma unroll
-                    for (int kx = 0; kx < K; ++kx) {
-                        if constexpr (CB == 4) {
-                            const float4 q = __ldg(reinterpret_cast<const float4*>(wrow + kx * Co));
-                            wv[kx][0] = q.x, wv[kx][1] = q.y, wv[kx][2] = q.z, wv[kx][3] = q.w;
-                        } else if constexpr (CB == 2) {
-                            const float2 q = __ldg(reinterpret_cast<const float2*>(wrow + kx * Co));
-                            wv[kx][0] = q.x, wv[kx][1] = q.y;
-                        } else {
-                            wv[kx][0] = __ldg(wrow + kx * Co);
-                        }
-                    }
-                    float r[RW];
-                    if (vp == 0) {  // forward: every read of a valid output pixel is inside the window; ragged blocks read (finite or not) junk
-#pragma unroll                      // that only reaches accumulators which are never stored
-                        for (int j = 0; j < RW; ++j) r[j] = row[xb + j];
+                for (int j = 0; j < XB - 1; ++j) r[j + 1] = ld(j);
+#pragma unroll 2
+                for (int kx = 0; kx < k; ++kx) {
 #pragma unroll
-                        for (int kx = 0; kx < K; ++kx)
+                    for (int j = 0; j < XB - 1; ++j) r[j] = r[j + 1];
+                    r[XB - 1] = ld(kx + XB - 1);
+                    float wv[CB];
 #pragma unroll
-                            for (int c = 0; c < CB; ++c)
+                    for (int c = 0; c < CB; ++c) wv[c] = __ldg(wp + kx * CB + c);
 #pragma unroll
-                                for (int j = 0; j < XB; ++j) acc[c][j] = fmaf(wv[kx][c], r[j + kx], acc[c][j]);
-                    } else {
+                    for (int c = 0; c < CB; ++c)
 #pragma unroll
-                        for (int j = 0; j < RW; ++j) {
-                            const int ix = xb + j;
-                            r[j] = (ix >= 0 && ix < Sin) ? row[ix] : 0.f;
-                        }
-#pragma unroll
-                        for (int kx = 0; kx < K; ++kx) {
-                            if (kx < kx_lo || kx >= kx_hi) continue;  // taps that only see the virtual zero border
-#pragma unroll
-                            for (int c = 0; c < CB; ++c)
-#pragma unroll
-                                for (int j = 0; j < XB; ++j) acc[c][j] = fmaf(wv[kx][c], r[j + kx], acc[c][j]);
-                        }
-                    }
-                } else {
-                    float r[XB];
-                    const int base = x0 + kx_lo - vp;
-#pragma unroll
-                    for (int j = 0; j < XB - 1; ++j) {
-                        const int ix = base + j;
-                        r[j + 1] = (ix >= 0 && ix < Sin) ? row[ix] : 0.f;
-                    }
-#pragma unroll 4
-                    for (int kx = kx_lo; kx < kx_hi; ++kx) {
-#pragma unroll
-                        for (int j = 0; j < XB - 1; ++j) r[j] = r[j + 1];
-                        const int ix = x0 + kx - vp + XB - 1;
-                        r[XB - 1] = (ix >= 0 && ix < Sin) ? row[ix] : 0.f;
-                        float wv[CB];
-#pragma unroll
-                        for (int c = 0; c < CB; ++c) wv[c] = __ldg(wrow + kx * Co + c);
-#pragma unroll
-                        for (int c = 0; c < CB; ++c)
-#pragma unroll
-                            for (int j = 0; j < XB; ++j) acc[c][j] = fmaf(wv[c], r[j], acc[c][j]);
-                    }
+                        for (int j = 0; j < XB; ++j) acc[c][j] = fmaf(wv[c], r[j], acc[c][j]);
                 }
+                advance();
             }
         }
-        float* o = scratch + (size_t)item * TILE;
+        float4* o = reinterpret_cast<float4*>(scratch + (size_t)item * TILE);
+        const float* af = &acc[0][0];
 #pragma unroll
-        for (int c = 0; c < CB; ++c)
-#pragma unroll
-            for (int j = 0; j < XB; ++j) o[c * XB + j] = acc[c][j];
+        for (int u = 0; u < TILE / 4; ++u) o[u] = make_float4(af[4 * u], af[4 * u + 1], af[4 * u + 2], af[4 * u + 3]);
     }
 }
 
 template <int CB>
-__device__ __forceinline__ void conv_by_k(const float* in, int Cin, int Sin, int vp, int So, int Co, int k, const float* Wt, float* scratch, int lo,
-                                          int hi, int ksplit) {
+__device__ __forceinline__ void conv_by_k(const float* in, int Cin, int RS, int PS, int rows, int vp, int xlim, int So, int Co, int k, const float* Wt,
+                                          float* scratch, int lo, int hi, int ksplit) {
     switch (k) {
-        case 3: conv_items<CB, 3>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit); break;
-        case 5: conv_items<CB, 5>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit); break;
-        case 7: conv_items<CB, 7>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit); break;
-        case 9: conv_items<CB, 9>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit); break;
-        default: conv_items<CB, 0>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit);
+        case 3: conv_items<CB, 3>(in, Cin, RS, PS, rows, vp, xlim, So, Co, k, Wt, scratch, lo, hi, ksplit); break;
+        case 5: conv_items<CB, 5>(in, Cin, RS, PS, rows, vp, xlim, So, Co, k, Wt, scratch, lo, hi, ksplit); break;
+        case 7: conv_items<CB, 7>(in, Cin, RS, PS, rows, vp, xlim, So, Co, k, Wt, scratch, lo, hi, ksplit); break;
+        case 9: conv_items<CB, 9>(in, Cin, RS, PS, rows, vp, xlim, So, Co, k, Wt, scratch, lo, hi, ksplit); break;
+        default: conv_items<CB, 0>(in, Cin, RS, PS, rows, vp, xlim, So, Co, k, Wt, scratch, lo, hi, ksplit);
     }
 }
 
-__device__ __forceinline__ void conv_dispatch(const float* in, int Cin, int Sin, int vp, int So, int Co, int k, const float* Wt, float* scratch, int lo,
-                                              int hi, int ksplit) {
+__device__ __forceinline__ void conv_dispatch(const float* in, int Cin, int RS, int PS, int rows, int vp, int xlim, int So, int Co, int k, const float* Wt,
+                                              float* scratch, int lo, int hi, int ksplit) {
     const int cb = pick_cb(Co);
-    if (cb == 4) conv_by_k<4>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit);
-    else if (cb == 2) conv_by_k<2>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit);
-    else conv_by_k<1>(in, Cin, Sin, vp, So, Co, k, Wt, scratch, lo, hi, ksplit);
+    if (cb == 4) conv_by_k<4>(in, Cin, RS, PS, rows, vp, xlim, So, Co, k, Wt, scratch, lo, hi, ksplit);
+    else if (cb == 2) conv_by_k<2>(in, Cin, RS, PS, rows, vp, xlim, So, Co, k, Wt, scratch, lo, hi, ksplit);
+    else conv_by_k<1>(in, Cin, RS, PS, rows, vp, xlim, So, Co, k, Wt, scratch, lo, hi, ksplit);
 }
 
 __device__ __forceinline__ float elu_shifted(float v, float xs, float ys) {
@@ -228,7 +250,9 @@ enum { EPI_FWD = 0, EPI_BWD = 1, EPI_PLAIN = 2 };
 //   EPI_FWD:   v*scale[c] + shift[c], optional shifted ELU, 0 outside the frame (= the next layer's zero padding)
 //   EPI_BWD:   v * scale[c] * elu'(aout) , 0 outside the frame   (gradient wrt the pre-batch-norm output of the layer below)
 //   EPI_PLAIN: v
-__device__ __forceinline__ void reduce_store(cg::cluster_group& cl, int CS, const float* scratch, int lo, int hi, int ksplit, int So, int Co, float* dst, int mode,
+// `dst` rows have stride DS and start dpad floats in (activations: DS = So, dpad = 0; gradient maps: Plan::GS, k - 1).
+__device__ __forceinline__ void reduce_store(cg::cluster_group& cl, int CS, const float* scratch, int lo, int hi, int ksplit, int So, int Co, float* dst, int DS,
+                                             int dpad, int mode,
                                              const float* __restrict__ scale, const float* __restrict__ shift, int nonlin, float xs, float ys,
                                              const float* aout, int oy, int ox, int H, int W) {
     const int CB = pick_cb(Co), XB = TILE / CB;
@@ -252,9 +276,10 @@ __device__ __forceinline__ void reduce_store(cg::cluster_group& cl, int CS, cons
             const int gy = oy + y, gx = ox + x;
             if (!(gy >= 0 && gy < H && gx >= 0 && gx < W)) v = 0.f;
         }
-        if (CS == 1) dst[idx] = v;
+        const int didx = (c * So + y) * DS + x + dpad;  // (gradient maps: padded rows)
+        if (CS == 1) dst[didx] = v;
         else
-            for (int r = 0; r < CS; ++r) *cl.map_shared_rank(dst + idx, r) = v;
+            for (int r = 0; r < CS; ++r) *cl.map_shared_rank(dst + didx, r) = v;
     }
 }
 
@@ -309,6 +334,8 @@ __global__ void __launch_bounds__(NT, 1) convcone_kernel(const Args a) {
         win[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(img + (size_t)c * P + gy * W + gx) : 0.f;
     }
     for (int i = tid; i < 64; i += NT) sm[pl.total - 64 + i] = 0.f;
+    if (with_grad)  // gradient maps: the row borders must read as zeros (the interiors are overwritten layer by layer)
+        for (int i = pl.off_g[0] + tid; i < pl.off_gin; i += NT) sm[i] = 0.f;
     cl.sync();  // also: every CTA of the cluster is running before the first remote shared-memory write
 
     // ---- forward through the layers
@@ -318,9 +345,9 @@ __global__ void __launch_bounds__(NT, 1) convcone_kernel(const Args a) {
         const float* in = l == 0 ? win : sm + pl.off_a[l - 1];
         const int nflat = flat_items(So, Hc), lo = rank * nflat / CS, hi = (rank + 1) * nflat / CS;
         const int ks = ksplit_for(hi - lo, cin);
-        conv_dispatch(in, cin, Si, 0, So, Hc, k, a.w.w_fwd[l], scratch, lo, hi, ks);
+        conv_dispatch(in, cin, Si, Si * Si, Si, 0, 0, So, Hc, k, a.w.w_fwd[l], scratch, lo, hi, ks);
         __syncthreads();
-        reduce_store(cl, CS, scratch, lo, hi, ks, So, Hc, sm + pl.off_a[l], EPI_FWD, a.w.scale[l], a.w.shift[l], d.nonlin[l], d.elu_xshift, d.elu_yshift, nullptr,
+        reduce_store(cl, CS, scratch, lo, hi, ks, So, Hc, sm + pl.off_a[l], So, 0, EPI_FWD, a.w.scale[l], a.w.shift[l], d.nonlin[l], d.elu_xshift, d.elu_yshift, nullptr,
                      Y0 - pl.halo[l], X0 - pl.halo[l], H, W);
         cl.sync();
     }
@@ -343,7 +370,7 @@ __global__ void __launch_bounds__(NT, 1) convcone_kernel(const Args a) {
             const int gyy = Y0 + (tap >> 1), gxx = X0 + (tap & 1);
             float v = gy_ * __ldg(a.w.features + (size_t)neuron * Hc + c) * s_tap[tap];
             v *= __ldg(a.w.scale[L - 1] + c) * (d.nonlin[L - 1] ? elu_grad_from_out(top[i], d.elu_yshift) : 1.f);
-            gl[i] = (gyy >= 0 && gyy < H && gxx >= 0 && gxx < W) ? v : 0.f;
+            gl[(c * 2 + (tap >> 1)) * pl.GS[L - 1] + (tap & 1) + ((pl.GS[L - 1] - 2) >> 1)] = (gyy >= 0 && gyy < H && gxx >= 0 && gxx < W) ? v : 0.f;
         }
     }
     __syncthreads();
@@ -352,13 +379,13 @@ __global__ void __launch_bounds__(NT, 1) convcone_kernel(const Args a) {
         const int cout = l == 0 ? Cin : Hc, So = l == 0 ? Sin : pl.S[l - 1], Si = pl.S[l], k = d.kernel[l];
         const int nflat = flat_items(So, cout), lo = rank * nflat / CS, hi = (rank + 1) * nflat / CS;
         const int ks = ksplit_for(hi - lo, Hc);
-        conv_dispatch(sm + pl.off_g[l], Hc, Si, k - 1, So, cout, k, a.w.w_bwd[l], scratch, lo, hi, ks);
+        conv_dispatch(sm + pl.off_g[l], Hc, pl.GS[l], Si * pl.GS[l], Si, k - 1, pl.GS[l] == Si ? Si : 0, So, cout, k, a.w.w_bwd[l], scratch, lo, hi, ks);
         __syncthreads();
         if (l > 0)
-            reduce_store(cl, CS, scratch, lo, hi, ks, So, cout, sm + pl.off_g[l - 1], EPI_BWD, a.w.scale[l - 1], nullptr, d.nonlin[l - 1], d.elu_xshift,
+            reduce_store(cl, CS, scratch, lo, hi, ks, So, cout, sm + pl.off_g[l - 1], pl.GS[l - 1], (pl.GS[l - 1] - So) >> 1, EPI_BWD, a.w.scale[l - 1], nullptr, d.nonlin[l - 1], d.elu_xshift,
                          d.elu_yshift, sm + pl.off_a[l - 1], Y0 - pl.halo[l - 1], X0 - pl.halo[l - 1], H, W);
         else
-            reduce_store(cl, CS, scratch, lo, hi, ks, So, cout, sm + pl.off_gin, EPI_PLAIN, nullptr, nullptr, 0, 0.f, 0.f, nullptr, 0, 0, H, W);
+            reduce_store(cl, CS, scratch, lo, hi, ks, So, cout, sm + pl.off_gin, So, 0, EPI_PLAIN, nullptr, nullptr, 0, 0.f, 0.f, nullptr, 0, 0, H, W);
         cl.sync();
     }
     // ---- write the image gradient (this cluster owns the whole image: no atomics; the CTAs interleave)
@@ -371,10 +398,22 @@ __global__ void __launch_bounds__(NT, 1) convcone_kernel(const Args a) {
             if (gyy >= 0 && gyy < H && gxx >= 0 && gxx < W) gimg[(size_t)c * P + gyy * W + gxx] += gin[i];
         }
     } else {
-        for (int i = rank * NT + tid; i < Cin * P; i += NT * CS) {
-            const int c = i / P, r = i - c * P, gyy = r / W, gxx = r - gyy * W;
-            const int y = gyy - iy0, x = gxx - ix0;
-            gimg[i] = (y >= 0 && y < Sin && x >= 0 && x < Sin) ? gin[(c * Sin + y) * Sin + x] : 0.f;
+        // one warp per image row (the cluster's warps interleave): rows that miss the window are zero-filled with 16-byte stores, the others
+        // test the column only -- no division per pixel (the flat-index version of this loop was 10 % of the kernel's instructions)
+        const int wg = rank * (NT / 32) + (tid >> 5), nwg = CS * (NT / 32), lane = tid & 31;
+        const bool vec = (W & 3) == 0 && (reinterpret_cast<size_t>(gimg) & 15) == 0;
+        for (int rw = wg; rw < Cin * H; rw += nwg) {
+            const int c = rw / H, gyy = rw - c * H, y = gyy - iy0;
+            float* dst = gimg + (size_t)c * P + (size_t)gyy * W;
+            if (y < 0 || y >= Sin) {
+                if (vec)
+                    for (int x4 = lane; x4 < (W >> 2); x4 += 32) reinterpret_cast<float4*>(dst)[x4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                else
+                    for (int gxx = lane; gxx < W; gxx += 32) dst[gxx] = 0.f;
+            } else {
+                const float* src = gin + (c * Sin + y) * Sin - ix0;
+                for (int gxx = lane; gxx < W; gxx += 32) dst[gxx] = (gxx >= ix0 && gxx < ix0 + Sin) ? src[gxx] : 0.f;
+            }
         }
     }
 }

@@ -365,6 +365,14 @@ def simresp(x, filters, nfilt, neuron_of_group, eps=1e-6):
 # ------------------------------------------------------------------------------------------------------------------
 # stacked-conv core + Gaussian readout response (receptive-field cone of the selected neuron)
 # ------------------------------------------------------------------------------------------------------------------
+def _pack_cone(w):
+    """[c_in][k][c_out][k] -> [c_in][k][c_out / CB][k][CB], CB = 4 / 2 / 1 by the divisibility of c_out (csrc/convcone.cu pick_cb): the k * CB
+    weights a thread needs for one (input channel, kernel row) are contiguous."""
+    cin, k, cout, _ = w.shape
+    cb = 4 if cout % 4 == 0 else 2 if cout % 2 == 0 else 1
+    return w.reshape(cin, k, cout // cb, cb, k).permute(0, 1, 2, 4, 3).contiguous()
+
+
 class ConvCone:
     """Device-side weight pack + descriptor of a FiringRateEncoder(Stacked2dCore, FullGaussian2d) in eval mode, in the layout
     lmr_convcore_response reads (include/laminr_b200.h).  Built once from the module's parameters (the response model is frozen)."""
@@ -384,8 +392,8 @@ class ConvCone:
             if co != hidden or k != k2 or k % 2 == 0 or (l > 0 and ci != hidden):
                 raise ValueError("ConvCone: every layer must be a square odd-kernel convolution with `hidden` output channels")
             d.kernel[l], d.nonlin[l] = k, int(bool(L["nonlin"]))
-            wf = W.permute(1, 2, 3, 0).contiguous()
-            wb = W.flip(2, 3).permute(0, 2, 3, 1).contiguous()
+            wf = _pack_cone(W.permute(1, 2, 0, 3))                # [ci][ky][co][kx]
+            wb = _pack_cone(W.flip(2, 3).permute(0, 2, 1, 3))     # [co][ky][ci][kx] of the flipped kernel
             # eval-mode batch norm + conv bias folded into v*scale + shift (float64 on the way, like the oracle)
             scale, shift = torch.ones(co, dtype=torch.float64, device=W.device), torch.zeros(co, dtype=torch.float64, device=W.device)
             if L.get("conv_bias") is not None:
