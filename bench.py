@@ -35,7 +35,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_LATENTS = 20
-TRAFFIC_BWD_KEEP = 165600000 + 3900000  # dram read + write of inr_bwd_pp_kernel (kept activations; profiles/r2a_ncu_bwd_pp.md)
+TRAFFIC_BWD_KEEP = 165694720 + 3682048  # dram read + write of inr_bwd_pp_kernel (kept activations; profiles/r2g_ncu_learn_step.md)
 
 
 def algorithmic_flops(res, N=N_LATENTS, h=50, pe=50, C=1):
@@ -829,7 +829,7 @@ def run_ours(args):
                          "frac": achieved / peak_tf,
                          # dram__bytes_read.sum + dram__bytes_write.sum of the tile kernel, one `ncu --set full` capture of this workload:
                          # recompute variant 2.995 MB (profiles/r1b_ncu_inr_bwd_tc.md); kept-activation variant: the 160 MB of operand tiles it loads
-                         # (profiles/r2a_ncu_bwd_pp.md)
+                         # (profiles/r2g_ncu_learn_step.md)
                          "traffic": (TRAFFIC_BWD_KEEP if keep else 2995456) if (res == 100 and args.precision != "fp32") else None,
                          "traffic_unit": "bytes per launch (ncu, DRAM)", "kept_activations": keep,
                          "peak_source": "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback",
