@@ -848,6 +848,12 @@ def run_ours(args):
                          "traffic": (TRAFFIC_BWD_KEEP if keep else 2995456) if (res == 100 and args.precision != "fp32") else None,
                          "traffic_unit": "bytes per launch (ncu, DRAM)", "kept_activations": keep,
                          "peak_source": "measured (MEASURED_PEAKS.json bf16 burst)" if peaks else "fallback",
+                         # what the low fraction is made of: the split-bf16 operands cost three tensor-core MACs per algorithmic MAC (the
+                         # tensor pipe therefore works at 3x `achieved`), and ncu has the pipe active for 29 % of the tile kernel
+                         # (profiles/r2g_ncu_learn_step.md: sm__pipe_tensor_cycles_active, cold-cache replay; 32 % of the warm kernel time)
+                         "operand_split": "bf16x3" if args.precision != "fp32" else None,
+                         "issued_tflops": 3.0 * achieved if args.precision != "fp32" else None,
+                         "tensor_pipe_active_pct_ncu": 29.0 if (res == 100 and args.precision == "bf16x3" and keep) else None,
                          "algorithmic_gflop": bwd_f / 1e9, "ms": bwd_ms, "forward": {"algorithmic_gflop": fwd_f / 1e9, "ms": fwd_ms, "achieved": fwd_f / (fwd_ms * 1e-3) / 1e12}},
             "cpu_baseline": cpu, "clocks": clocks, "api_learn": api, "roofline_all": roofline_all, "match": match, "conv": conv,
             "scale_summary": scale_summary,  # LAST key on purpose: it must survive a truncated tail of this line at every N
