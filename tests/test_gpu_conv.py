@@ -63,6 +63,46 @@ def test_cone_response_and_gradient_vs_reference(name):
     assert relerr(g1.cpu().numpy(), g_want) < TOL_GRAD
 
 
+@pytest.mark.parametrize("cin,hidden,kernels", [(3, 6, (11, 3)), (1, 5, (5, 13)), (4, 8, (1, 7, 3)), (2, 4, (9, 9))])
+def test_cone_odd_shapes_vs_oracle(cin, hidden, kernels):
+    """Shapes the reference goldens do not hold: kernel sizes without a compile-time instantiation (1, 11, 13: the sliding-window loop),
+    channel counts that run 2- and 1-channel blocks (unpadded, bounds-checked gradient maps) and a 4-channel image (padded first gradient
+    map), against the full-frame numpy oracle on random parameters."""
+    from laminr_b200 import ops
+    from oracle import convcore_oracle as CO
+    rs = np.random.RandomState(cin * 100 + hidden)
+    H, W, B, n = 31, 37, 6, 5
+    d = dict(n_layers=len(kernels), xs=0.0, ys=0.0, offset=0.1, align_corners=True)
+    for l, k in enumerate(kernels):
+        ci = cin if l == 0 else hidden
+        d[f"w{l}"] = (rs.randn(hidden, ci, k, k) / np.sqrt(ci * k * k)).astype(np.float32)
+        d[f"bn{l}_mean"], d[f"bn{l}_var"] = (0.1 * rs.randn(hidden)).astype(np.float32), rs.uniform(0.5, 1.5, hidden).astype(np.float32)
+        d[f"bn{l}_gamma"], d[f"bn{l}_beta"], d[f"bn{l}_eps"] = rs.uniform(0.5, 1.5, hidden).astype(np.float32), (0.1 * rs.randn(hidden)).astype(np.float32), 1e-5
+        d[f"nonlin{l}"] = True
+    d["mu"] = rs.uniform(-0.95, 0.95, (n, 2)).astype(np.float32)
+    d["mu"][0] = (-0.999, 0.999)  # a cone clipped by two borders
+    d["features"] = rs.randn(hidden, n).astype(np.float32)
+    d["bias"] = (0.1 * rs.randn(n)).astype(np.float32)
+    x = rs.randn(B, cin, H, W).astype(np.float32)
+    neurons = rs.randint(0, n, B)
+    g_act = rs.randn(B).astype(np.float32)
+    d["x"] = x
+    cone = _cone_from_golden(d)
+    xg = torch.as_tensor(x).cuda()
+    g_img = torch.full_like(xg, 3.0)
+    act = ops.raw_convcore_response(cone, xg, cin * H * W, 1, B, torch.as_tensor(neurons, dtype=torch.int32).cuda(),
+                                    g_act=torch.as_tensor(g_act).cuda().view(B, 1), g_img=g_img, accumulate=False)
+    a_want, g_want, _ = CO.response_and_grad(x, CO.model_from_arrays(d), list(neurons), g_act=g_act)
+    assert relerr(act.cpu().numpy().ravel(), a_want) < TOL_ACT
+    assert relerr(g_img.cpu().numpy(), g_want) < TOL_GRAD
+    # the learn-stage layout (one neuron, every image: a cluster of CTAs per image)
+    g1 = torch.empty_like(xg)
+    a1 = ops.raw_convcore_response(cone, xg, 0, B, 1, torch.tensor([1], dtype=torch.int32, device="cuda"), g_img=g1, accumulate=False)
+    a_want, g_want, _ = CO.response_and_grad(x, CO.model_from_arrays(d), [1] * B)
+    assert relerr(a1.cpu().numpy().ravel(), a_want) < TOL_ACT
+    assert relerr(g1.cpu().numpy(), g_want) < TOL_GRAD
+
+
 def _load_mirror(d):
     """The host mirror (laminr_b200.neuron_models) with the golden fixture's parameters loaded through state_dict names."""
     from laminr_b200.neuron_models import FiringRateEncoder, FullGaussian2d, Stacked2dCore
