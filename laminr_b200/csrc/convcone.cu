@@ -54,7 +54,7 @@ struct Plan {  // built on the host, handed to the kernel inside Args (parameter
     int off_in, off_a[MAXL], off_g[MAXL], off_gin, off_scratch, total;  // float offsets into dynamic shared memory
 };
 
-__host__ __device__ inline void make_plan(const lmr_convcore_desc& d, bool with_grad, Plan& p) {
+__host__ __device__ inline void make_plan(const lmr_convcore_desc& d, bool with_grad, Plan& p, bool allow_pad = true) {
     const int L = d.n_layers;
     p.S[L - 1] = 2, p.halo[L - 1] = 0;
     for (int l = L - 2; l >= 0; --l) p.S[l] = p.S[l + 1] + d.kernel[l + 1] - 1, p.halo[l] = p.halo[l + 1] + d.kernel[l + 1] / 2;
@@ -72,7 +72,7 @@ __host__ __device__ inline void make_plan(const lmr_convcore_desc& d, bool with_
         for (int l = 0; l < L; ++l) {
             // padded rows where the data-gradient convolution that reads the map runs 4-channel blocks (the bulk of the work); the others keep
             // plain rows and check their bounds: shared memory left over is L1 cache, and the weight rows are shared between warps through L1
-            const bool pad = pick_cb(l == 0 ? d.c_in : d.hidden) == 4;
+            const bool pad = allow_pad && pick_cb(l == 0 ? d.c_in : d.hidden) == 4;
             p.GS[l] = p.S[l] + (pad ? 2 * (d.kernel[l] - 1) : 0), p.off_g[l] = take(d.hidden * p.S[l] * p.GS[l]);
         }
         p.off_gin = take(d.c_in * p.Sin * p.Sin);
@@ -439,6 +439,7 @@ extern "C" int lmr_convcore_response(const lmr_convcore_desc* desc, const lmr_co
     LMR_CHECK_ARG(!g_img || img_group_stride != 0 || G == 1, "convcore_response: the gradient needs one image set per group (img_group_stride != 0)");
     cone::Plan pl;
     cone::make_plan(d, g_img != nullptr, pl);
+    if ((size_t)pl.total * sizeof(float) > 220 * 1024) cone::make_plan(d, g_img != nullptr, pl, false);  // large cones: plain gradient rows, bounds-checked
     const size_t smem = (size_t)pl.total * sizeof(float);
     LMR_CHECK_ARG(smem <= 220 * 1024, "convcore_response: the receptive-field cone needs %zu bytes of shared memory (> 220 KB)", smem);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -63,11 +63,12 @@ def test_cone_response_and_gradient_vs_reference(name):
     assert relerr(g1.cpu().numpy(), g_want) < TOL_GRAD
 
 
-@pytest.mark.parametrize("cin,hidden,kernels", [(3, 6, (11, 3)), (1, 5, (5, 13)), (4, 8, (1, 7, 3)), (2, 4, (9, 9))])
+@pytest.mark.parametrize("cin,hidden,kernels", [(3, 6, (11, 3)), (1, 5, (5, 13)), (4, 8, (1, 7, 3)), (2, 4, (9, 9)), (4, 32, (9, 9, 9))])
 def test_cone_odd_shapes_vs_oracle(cin, hidden, kernels):
     """Shapes the reference goldens do not hold: kernel sizes without a compile-time instantiation (1, 11, 13: the sliding-window loop),
     channel counts that run 2- and 1-channel blocks (unpadded, bounds-checked gradient maps) and a 4-channel image (padded first gradient
-    map), against the full-frame numpy oracle on random parameters."""
+    map), and a cone too large for padded gradient maps (4 -> 32 channels, 9 / 9 / 9: 238 KB padded, falls back to plain rows), against the
+    full-frame numpy oracle on random parameters."""
     from laminr_b200 import ops
     from oracle import convcore_oracle as CO
     rs = np.random.RandomState(cin * 100 + hidden)
