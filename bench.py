@@ -8,8 +8,9 @@ One "step" is one pass of the learn hot path (reference laminr/inv_temp_learn_ma
 
   value    : steps/s with inputs resident in HBM.  Each step is timed with its own CUDA-event pair on the launching
              stream; L2 is flushed (256 MiB write) between timed steps, outside the event pairs.
-  e2e      : steps/s through the host-facing call: per step H2D of the jittered latent grid from pinned memory, the
-             step, D2H of the step's loss.
+  e2e      : steps/s through the host-facing call, the host waiting for every step's loss: LearnStepper.step(host row) + sync_loss() --
+             the step's N latents travel host -> device (pinned memory read by the step's first kernel), its loss device -> host
+             (written into pinned memory by the objective kernel); `copy_engine` = the same loop with cudaMemcpyAsync copies.
   roofline : the INR backward launch group (dominant), algorithmic FLOPs / CUDA-event time vs measured bf16 peak.
   cpu_baseline : the reference's CPU path (torch-CPU port of its op sequence, oracle/torch_port.py; or the reference
              itself when /root/reference is mounted) on a bounded sample of the same workload.
@@ -544,17 +545,49 @@ def run_ours(args):
     b2b_ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler is not None else None
 
-    # ---- e2e: host grid (pinned) -> H2D -> step -> D2H loss, every step
-    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    # ---- e2e: host grid -> step -> loss on the host, every step, through LearnStepper.step with a HOST row: the row is written into pinned memory
+    #      that the step's first kernel reads over PCIe (80 bytes host -> device), the objective kernel writes the loss into pinned memory (4 bytes
+    #      device -> host), sync_loss() waits for the step and returns the float.  `copy_engine` = the same loop with cudaMemcpyAsync H2D / D2H
+    #      around the device-fed step (what round 1 and 2 a-f reported as e2e).
     for i in range(3):
         stepper.step(grids_host[i])
+        stepper.sync_loss()
     barrier()
     t0 = time.perf_counter()
+    e2e_loss = 0.0
     for i in range(K):
-        stepper.step(grids_host[Wm + i])  # H2D of the step's jittered latents from pinned memory into the stepper's static input, then the step
+        stepper.step(grids_host[Wm + i])   # CPU tensor: host-fed step
+        e2e_loss = stepper.sync_loss()     # the step's loss as a Python float
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    if not np.isfinite(e2e_loss):
+        raise SystemExit("bench.py: the host-fed step returned a non-finite loss")
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    t0 = time.perf_counter()
+    for i in range(K):
+        stepper.grid.copy_(grids_host[Wm + i], non_blocking=True)  # H2D of the step's jittered latents from pinned memory into the static input
+        stepper.graph.replay()
         loss_host.copy_(stepper.loss().reshape(1), non_blocking=True)  # D2H of the step's loss
         torch.cuda.current_stream().synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_copy_s = time.perf_counter() - t0
+    barrier()
+    # extra, NOT the e2e value: the same copies every step, but the loss of step k is read (two pinned slots, one event each) after step k + 1 has
+    # been queued, so the GPU does not wait for the host's round trip -- how a host loop that only logs the loss would be written
+    loss2 = torch.zeros(2, dtype=torch.float32).pin_memory()
+    done = [torch.cuda.Event(), torch.cuda.Event()]
+    acc_loss = 0.0
+    t0 = time.perf_counter()
+    for i in range(K):
+        stepper.grid.copy_(grids_host[Wm + i], non_blocking=True)
+        stepper.graph.replay()
+        loss2[i & 1:(i & 1) + 1].copy_(stepper.loss().reshape(1), non_blocking=True)
+        done[i & 1].record()
+        if i > 0:
+            done[(i - 1) & 1].synchronize()
+            acc_loss += float(loss2[(i - 1) & 1])
+    done[(K - 1) & 1].synchronize()
+    acc_loss += float(loss2[(K - 1) & 1])
+    e2e_lag_s = time.perf_counter() - t0
     barrier()
 
     # ---- the public call itself (extra): InvarianceManifold.learn(0) for a fixed number of epochs -- stepper construction, graph capture, the
@@ -837,7 +870,13 @@ def run_ours(args):
             "notes": {"precision": args.precision or "fp32", "l2": "flushed (256 MiB write) between timed steps, outside the event pairs",
                       "multi_gpu": "value: replicas only (learn has one template); the sharded match / MEI record is scale_summary", "cuda_graph": True},
             "back_to_back": {"value": world * K / (b2b_ms / 1e3), "unit": "steps/s", "ms_per_step": b2b_ms / K, "note": "K graph replays in one event pair, no L2 flush (the loop as it runs)"},
-            "e2e": {"value": world * K / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": 4 * N_LATENTS, "d2h_bytes_per_step": 4},
+            "e2e": {"value": world * K / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": 4 * N_LATENTS, "d2h_bytes_per_step": 4,
+                    "sync": "the host waits for every step's loss before it queues the next step",
+                    "path": "LearnStepper.step(host row) + sync_loss(): pinned memory read / written by the step's kernels, one graph launch per step",
+                    "copy_engine": {"value": K / e2e_copy_s, "unit": "steps/s per GPU (this rank)",
+                                    "note": "same loop with cudaMemcpyAsync H2D / D2H around the device-fed step"},
+                    "loss_read_one_step_late": {"value": K / e2e_lag_s, "unit": "steps/s per GPU (this rank)", "mean_loss": acc_loss / K,
+                                                "note": "extra: same H2D + D2H every step, the loss of step k read while step k + 1 runs"}},
             "gpu_launches": int(stepper.kernels_per_step * K),
             "roofline": {"bound": "tensor", "kernel": ("lmr_inr_backward_adam launch group: inr_bwd_pp_kernel (dominant) + learn_tail_kernel (layer-0 weight gradient, partial reductions, Adam)"
                                                        if fused_tail else "lmr_inr_backward launch group (tile kernel + layer-0 weight gradient and partial reduction launches)"), "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",

@@ -172,6 +172,7 @@ class LearnStepper:
         self.ws_con = _ws(lib.lmr_constrain_workspace_bytes(N, Cc * P), dev)
         self.ws_clr = _ws(lib.lmr_simclr_workspace_bytes(N, Cc, P), dev)
         self.use_graph, self.graph, self.eval_graph = use_graph, None, None
+        self.host_graph, self.grid_map, self.loss_map, self.host_done = None, None, None, None  # host-fed steps (step() with a CPU row)
         self._table_written = False
         self.side = torch.cuda.Stream(device=dev)
         # fused objective (one persistent launch for constraint + response + contrastive, forward and backward) for simulated neurons when it fits
@@ -202,18 +203,21 @@ class LearnStepper:
         ops.raw_constrain_fwd(c.mode, self.img_pre, c.target, c.mean, c.pmin, c.pmax, c.eps, out=self.z, stats=self.stats, workspace=self.ws_con)
         self.resp.forward(self.z, 0, N, 1, Cc, P, self.nog, self.act)
 
-    def _train(self):
+    def _train(self, grid=None, loss=None):
+        """grid / loss: where the step reads its latents / writes its loss (default: the stepper's device buffers; the host-fed step passes
+        pinned host memory, ops.MappedHost)."""
         t, c, N, Cc, P = self.t, self.con, self.N, self.C, self.P
         r = self.reg_mod
         if self.ws_obj is not None:
-            ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, None, out=self.img_pre.view(1, N, Cc, P),
+            grid = self.grid if grid is None else grid
+            ops.raw_inr_forward(t._desc, self.flat, t.B, t.auxB, grid, self.coords, None, None, out=self.img_pre.view(1, N, Cc, P),
                                 precision=self.precision, workspace=self.ws_fwd, keep_activations=self.keep, reuse_coord_table=self._table_valid())
             ops.raw_learn_objective(c.mode, self.img_pre, c.target, c.mean, c.pmin, c.pmax, c.eps, self.bank, self.model.eps, self.mei_act, self.mask,
                                     r.flat_neighbor_mask_pos, r.flat_neighbor_mask_neg, r.temperature, r.eps, self.g_reg, self.z, self.act.view(-1),
-                                    self.reg, self.loss_buf, self.g_x, self.ws_obj, stats=self.stats, rmax=self.resp.rmax.view(-1),
+                                    self.reg, self.loss_buf if loss is None else loss, self.g_x, self.ws_obj, stats=self.stats, rmax=self.resp.rmax.view(-1),
                                     argmax=self.resp.argmax.view(-1), K=self.K)
             # backward + Adam as one C-ABI call: one cooperative launch behind the tile kernel instead of four small ones
-            ops.raw_inr_backward_adam(t._desc, self.flat, t.B, t.auxB, self.grid, self.coords, None, self.g_x.view(1, N, Cc, P), self.g_flat, self.m, self.v,
+            ops.raw_inr_backward_adam(t._desc, self.flat, t.B, t.auxB, grid, self.coords, None, self.g_x.view(1, N, Cc, P), self.g_flat, self.m, self.v,
                                       self.step_count, lr=self.lr, precision=self.precision, workspace=self.ws_bwd, forward_workspace=self.ws_fwd,
                                       keep_activations=self.keep)
             return
@@ -239,7 +243,10 @@ class LearnStepper:
         return capture_graph(fn)
 
     def step(self, grid_row):
-        """One optimisation step on the jittered latents `grid_row` ([N] device tensor)."""
+        """One optimisation step on the jittered latents `grid_row` ([N] tensor).  A device row is copied into the step's static input.  A HOST row
+        (fused-objective path, graphs on) takes the host-fed step: see `_step_from_host`."""
+        if not grid_row.is_cuda and self.use_graph and self.ws_obj is not None:
+            return self._step_from_host(grid_row)
         self.grid.copy_(grid_row.reshape(-1), non_blocking=True)
         if not self.use_graph:
             self._train()
@@ -249,6 +256,39 @@ class LearnStepper:
             self.graph = self._capture(self._train)  # stream capture records the launches without executing them
         else:
             self.graph.replay()
+
+    def _step_from_host(self, grid_row):
+        """The step fed from the host without a copy engine: the row is written into a pinned buffer that the preparation kernel reads directly
+        (N loads over PCIe, hidden behind the kernel's other blocks) and the objective kernel writes the loss into pinned memory; one graph
+        launch per step, `sync_loss()` waits for it.  (Measured against the alternatives on B200, host waiting for every step's loss: H2D copy +
+        replay + D2H copy 176 us per step; the two copies as memcpy nodes inside the graph 183 us.)"""
+        if self.grid_map is None:
+            self.grid_map = torch.empty(self.N, dtype=torch.float32).pin_memory()
+            self.loss_map = torch.zeros(1, dtype=torch.float32).pin_memory()
+            self.grid_np, self.loss_np = self.grid_map.numpy(), self.loss_map.numpy()  # views: a NumPy write / read costs a tenth of a tensor op
+            self.host_done = torch.cuda.Event()
+            self._host_fn = lambda: self._train(ops.MappedHost(self.grid_map), ops.MappedHost(self.loss_map))
+            self._host_pending = False
+        if self._host_pending:
+            self.host_done.synchronize()  # the previous host-fed step has read the buffer (and written its loss)
+        self.grid_np[:] = grid_row.numpy().reshape(-1)
+        if self.graph is None:
+            self._host_fn()  # first step of the stepper: eager (see step); the device-fed graph is captured as usual
+            self.graph = self._capture(self._train)
+        elif self.host_graph is None:
+            self.host_graph = self._capture(self._host_fn)
+            self.host_graph.replay()
+        else:
+            self.host_graph.replay()
+        self.host_done.record()
+        self._host_pending = True
+
+    def sync_loss(self):
+        """Loss of the last host-fed step as a Python float (waits for that step)."""
+        if self._host_pending:
+            self.host_done.synchronize()
+            self._host_pending = False
+        return float(self.loss_np[0])
 
     def evaluate(self, grid_row):
         """No-grad forward: images and the template neuron's activations on `grid_row` (normalised by the MEI activation)."""

@@ -43,6 +43,25 @@ def _require_cuda(*tensors):
             )
 
 
+class MappedHost:
+    """A pinned (page-locked) host tensor handed to a kernel as a pointer argument: with unified addressing every cudaHostAlloc'ed block is mapped
+    into the device's address space at the same address, so a kernel can read a few input scalars from it / write a result scalar into it without
+    a copy engine in between (a 4..80-byte cudaMemcpyAsync costs more GPU idle time than the PCIe round trip of the load itself).  Only for such
+    scalars: every access crosses PCIe."""
+    is_cuda = True
+
+    def __init__(self, t):
+        if t.is_cuda or not t.is_pinned() or not t.is_contiguous() or t.dtype != torch.float32:
+            raise ValueError("MappedHost: a contiguous pinned float32 host tensor is required")
+        self.t = t
+
+    def numel(self):
+        return self.t.numel()
+
+    def data_ptr(self):
+        return self.t.data_ptr()
+
+
 def _ptr(t):
     """Device pointer of `t` for the C ABI (every pointer argument of include/laminr_b200.h is device memory): a host tensor here would be an
     illegal address inside the kernel, so it is refused."""

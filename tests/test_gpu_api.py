@@ -98,6 +98,37 @@ def test_fused_learn_trajectory_matches_reference(L, use_graph):
     assert torch.equal(im.template.func.layer1.weight.detach().reshape(-1), st.flat[50 * 201 + 50:50 * 201 + 50 + 2500])
 
 
+def test_host_fed_step_equals_device_fed_step(L):
+    """LearnStepper.step with a HOST row (pinned memory read by the preparation kernel, loss written into pinned memory by the objective kernel,
+    one graph launch) walks the same trajectory, bit for bit, as the device-fed step; sync_loss() returns the step's loss."""
+    from laminr_b200.contrastive_loss import SimCLROnGrid
+    from laminr_b200.fused import LearnStepper
+    d = golden("learn_traj_20")
+    grids = torch.from_numpy(d["grids"])
+    flats, losses = [], []
+    for host in (False, True):
+        model, im = _manifold(L, 20, d, prefix="init_")
+        reg = SimCLROnGrid(1, 20, 0.1, 0.3, True).cuda()
+        st = LearnStepper(im.template, im.img_transforms, model, 0, d["mask"], 1.0000009536743164, reg, -1.0, 1.0, 20, lr=1e-3, reg_scale=2.0,
+                          precision="bf16x3", use_graph=True)
+        ls = []
+        for i in range(6):
+            if host:
+                st.step(grids[i])  # CPU tensor
+                ls.append(st.sync_loss())
+            else:
+                st.step(grids[i].cuda())
+                ls.append(st.loss().item())
+        flats.append(st.flat.detach().cpu().clone()), losses.append(ls)
+        assert st.step_count[0].item() == 6
+    assert losses[0] == losses[1]
+    assert torch.equal(flats[0], flats[1])
+    # mixing the two kinds of step on one stepper
+    st.step(grids[6].cuda())
+    st.step(grids[7])
+    assert np.isfinite(st.sync_loss()) and st.step_count[0].item() == 8
+
+
 def test_learn_api_fused_equals_generic(L):
     """InvarianceManifold.learn: the fused path and the generic autograd path (user-style nn.Module model) walk the same trajectory."""
     class PlainModel(torch.nn.Module):  # a user-supplied response model: stock PyTorch ops, same maths as the simulated population
