@@ -2,6 +2,7 @@
 // masked contrastive objective, Adam, batched MEI ascent.  All fp32, coalesced / vectorised, warp-shuffle
 // reductions, deterministic two-stage reductions (no float atomics).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -106,6 +107,89 @@ __global__ void __launch_bounds__(256) constrain_apply_kernel(int mode, const fl
         if (has_min) y = fmaxf(y, pmin);
         if (has_max) y = fminf(y, pmax);
         zb[i] = y;
+    }
+}
+
+// The ascent update x <- clip(renorm(x + step*g)) of ONE image per CTA, the image held in shared memory between the statistics and the apply pass
+// (one launch and one read of x and g instead of two of each; the conv-encoder MEI ascent runs it 1000 times behind the cone kernel).  Four groups
+// of 256 threads walk the same 2048-element chunks as constrain_stats_kernel, with the same per-thread sums and the same reduction tree per chunk,
+// and one thread combines the chunk partials with combine_stats: bit-identical to the two-launch path.
+constexpr int AUF_NT = 1024, AUF_G = AUF_NT / 256;
+__device__ __forceinline__ float group_sum256(float v, float* scratch /* [AUF_G][40] */, int grp, int lt) {
+    const int lane = lt & 31, warp = lt >> 5;
+    float* sc = scratch + grp * 40;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sc[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < 8 ? sc[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) sc[32] = t;
+    }
+    __syncthreads();
+    return sc[32];
+}
+__global__ void __launch_bounds__(AUF_NT, 1) ascent_update_fused_kernel(int mode, float* x, const float* __restrict__ g, float step, int n, float target,
+                                                                        float mean, int has_min, float pmin, int has_max, float pmax, float eps) {
+    extern __shared__ __align__(16) float aus[];
+    __shared__ float scratch[AUF_G * 40];
+    __shared__ float sh[2];
+    const int S = (n + CCH - 1) / CCH;
+    float* v = aus;                        // [n]  x + step*g
+    float* part = aus + ((n + 3) & ~3);    // [S][4]
+    const int b = blockIdx.x, t = threadIdx.x, grp = t >> 8, lt = t & 255;
+    float* xb = x + (size_t)b * n;
+    const float* gb = g + (size_t)b * n;
+    for (int it = 0; it * AUF_G < S; ++it) {
+        const int s = it * AUF_G + grp;
+        const int i0 = s * CCH, i1 = min(n, i0 + CCH);  // (s >= S: empty chunk, the group only keeps the barriers company)
+        float w[CCH / 256];
+#pragma unroll
+        for (int q = 0; q < CCH / 256; ++q) {
+            const int i = i0 + q * 256 + lt;
+            w[q] = i < i1 ? fmaf(step, gb[i], xb[i]) : 0.f;
+            if (i < i1) v[i] = w[q];
+        }
+        if (mode == LMR_CONSTRAIN_NORM) {
+            float acc = 0.f;
+#pragma unroll
+            for (int q = 0; q < CCH / 256; ++q) {
+                const int i = i0 + q * 256 + lt;
+                const float u = w[q] - mean;
+                acc += i < i1 ? u * u : 0.f;
+            }
+            acc = group_sum256(acc, scratch, grp, lt);
+            if (lt == 0 && s < S) part[s * 4] = acc;
+        } else {
+            float sum = 0.f;
+#pragma unroll
+            for (int q = 0; q < CCH / 256; ++q) sum += w[q];
+            sum = group_sum256(sum, scratch, grp, lt);
+            const float m = sum / (float)(i1 - i0);
+            float m2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < CCH / 256; ++q) {
+                const int i = i0 + q * 256 + lt;
+                const float u = w[q] - m;
+                m2 += i < i1 ? u * u : 0.f;
+            }
+            m2 = group_sum256(m2, scratch, grp, lt);
+            if (lt == 0 && s < S) part[s * 4] = (float)(i1 - i0), part[s * 4 + 1] = m, part[s * 4 + 2] = m2;
+        }
+    }
+    __syncthreads();
+    if (t == 0) combine_stats(mode, part, S, n, &sh[0], &sh[1]);
+    __syncthreads();
+    const float sd = sh[0], mu = sh[1];
+    for (int i = t; i < n; i += AUF_NT) {
+        const float xv = v[i];
+        float y;
+        if (mode == LMR_CONSTRAIN_NORM) y = (xv - mean) / (sd + eps) * target + mean;
+        else y = target * (xv - mu) / (sd + eps) + mean;
+        if (has_min) y = fmaxf(y, pmin);
+        if (has_max) y = fminf(y, pmax);
+        xb[i] = y;
     }
 }
 
@@ -707,6 +791,19 @@ extern "C" int lmr_ascent_update(int mode, float* x, const float* g, float step_
     }
     const int S = (n + CCH - 1) / CCH;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // one CTA per image with the image in shared memory when it fits (bit-identical to the two launches below; LMR_ASCENT_FUSED=0 forces those)
+    const size_t fused_smem = ((size_t)((n + 3) & ~3) + (size_t)S * 4) * sizeof(float);
+    const char* env = getenv("LMR_ASCENT_FUSED");
+    if (fused_smem <= 220 * 1024 && !(env && env[0] == '0')) {
+        static size_t cache = 0;
+        if (fused_smem > cache) {
+            LMR_CUDA_OK(cudaFuncSetAttribute(ascent_update_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_smem));
+            cache = fused_smem;
+        }
+        ascent_update_fused_kernel<<<B, AUF_NT, fused_smem, st>>>(mode, x, g, step_size, n, target, mean, has_min, pmin, has_max, pmax, eps);
+        LMR_LAUNCH_OK();
+        return 0;
+    }
     dim3 grid(S, B);
     constrain_stats_kernel<<<grid, 256, 0, st>>>(mode, x, n, mean, static_cast<float*>(ws), g, step_size);
     LMR_LAUNCH_OK();

@@ -405,3 +405,29 @@ def test_narrow_widths_forward_backward_vs_oracle(L, widths, precision):
         ops.raw_inr_backward_adam(t._desc, flat, t.B, t.auxB, grid.reshape(-1), cflat, None, g.reshape(1, N, 1, H * W).contiguous(), gp, m, v, step,
                                   precision=precision, forward_workspace=ws, keep_activations=True)
     assert float(flat[~live].abs().max()) == 0.0 and float(gp[~live].abs().max()) == 0.0 and float(m[~live].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("mode_name,shape", [("norm", (128, 1, 200, 200)), ("std", (5, 3, 50, 37)), ("norm", (3, 1, 17, 9)), ("std", (40, 1, 100, 100))])
+def test_fused_ascent_update_is_bit_identical_to_the_two_launch_path(L, mode_name, shape, monkeypatch):
+    """lmr_ascent_update: one CTA per image with the image in shared memory (default when it fits) against the statistics + apply launches
+    (LMR_ASCENT_FUSED=0): same chunk partials, same reduction trees, same combine -> identical bits; and against a float64 evaluation."""
+    from laminr_b200 import _lib, ops
+    torch.manual_seed(3)
+    x0 = torch.randn(shape, device="cuda") * 0.3
+    g = torch.randn(shape, device="cuda") * 1e-3
+    g[:, :, : shape[2] // 2] = 0.0  # (a cone's gradient is zero outside its window)
+    mode = _lib.MODE_NORM if mode_name == "norm" else _lib.MODE_STD
+    outs = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("LMR_ASCENT_FUSED", fused)
+        x = x0.clone()
+        ops.raw_ascent_update(mode, x, g, 10.0, 7.5, 0.0, -1.0, 1.0, eps=1e-9)
+        outs.append(x)
+    assert torch.equal(outs[0], outs[1])
+    v = (x0.double() + 10.0 * g.double()).reshape(shape[0], -1)
+    if mode_name == "norm":
+        want = v / (v.norm(dim=1, keepdim=True) + 1e-9) * 7.5
+    else:
+        want = 7.5 * (v - v.mean(dim=1, keepdim=True)) / (v.std(dim=1, keepdim=True) + 1e-9)
+    want = want.clamp(-1.0, 1.0).reshape(shape)
+    assert (outs[0].double() - want).abs().max().item() < 2e-6
