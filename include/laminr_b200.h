@@ -189,7 +189,8 @@ int lmr_simresp_bwd(const float* g_act, const float* rmax, const int* argmax, lo
  * img + g*img_group_stride (stride 0: all groups see the same images; forward only).
  *   act   [G,NB]             = elu(readout + elu_offset) + 1
  *   g_img (nullable, layout of img): (+)= d sum(g_act * act) / d img;  g_act [G,NB] nullable (= 1).  accumulate = 0 overwrites the whole
- *   gradient image (zero outside the cone).
+ *   gradient image (zero outside the cone); 1 adds the cone's window into it; 2 overwrites the window only (for a caller that keeps the rest
+ *   of the image at zero and evaluates the same neurons again and again: the MEI ascent).
  * ---------------------------------------------------------------------------------------------------------- */
 #define LMR_CONV_MAX_LAYERS 6
 typedef struct {

@@ -391,11 +391,15 @@ __global__ void __launch_bounds__(NT, 1) convcone_kernel(const Args a) {
     // ---- write the image gradient (this cluster owns the whole image: no atomics; the CTAs interleave)
     float* gimg = a.g_img + img_off;
     const float* gin = sm + pl.off_gin;
-    if (a.accumulate) {
+    if (a.accumulate) {  // 1: add the window into the image; 2: overwrite the window only (the caller keeps the rest of the image at zero)
+        const bool add = a.accumulate == 1;
         for (int i = rank * NT + tid; i < Cin * Sin * Sin; i += NT * CS) {
             const int c = i / (Sin * Sin), r = i - c * Sin * Sin, y = r / Sin, x = r - y * Sin;
             const int gyy = iy0 + y, gxx = ix0 + x;
-            if (gyy >= 0 && gyy < H && gxx >= 0 && gxx < W) gimg[(size_t)c * P + gyy * W + gxx] += gin[i];
+            if (gyy >= 0 && gyy < H && gxx >= 0 && gxx < W) {
+                float* dst = gimg + (size_t)c * P + gyy * W + gxx;
+                *dst = add ? *dst + gin[i] : gin[i];
+            }
         }
     } else {
         // one warp per image row (the cluster's warps interleave): rows that miss the window are zero-filled with 16-byte stores, the others

@@ -71,9 +71,9 @@ def batched_conv_meis(model, neuron_idxs, initial_images, pixel_min, pixel_max, 
     ws = torch.empty(max(int(_lib.load().lmr_constrain_workspace_bytes(G, per_img)), 16), dtype=torch.uint8, device=x.device)
     _ops.raw_constrain_fwd(mode, x, target, mean, pixel_min, pixel_max, 1e-9, out=x, workspace=ws)  # post_update(initial_image), mei.py:42
     fev = torch.empty((num_iterations + 1, G), dtype=torch.float32, device=x.device)
-    g = torch.empty_like(x)
+    g = torch.zeros_like(x)  # every iteration rewrites the same receptive-field windows (accumulate = 2); the rest stays zero
     for it in range(num_iterations):
-        _ops.raw_convcore_response(cone, x, per_img, 1, G, nog, act=fev[it], g_img=g, accumulate=False)
+        _ops.raw_convcore_response(cone, x, per_img, 1, G, nog, act=fev[it], g_img=g, accumulate=2)
         _ops.raw_ascent_update(mode, x, g, step_size, target, mean, pixel_min, pixel_max, eps=1e-9, workspace=ws)
     _ops.raw_convcore_response(cone, x, per_img, 1, G, nog, act=fev[num_iterations])
     return x, fev.t().contiguous()
