@@ -307,6 +307,8 @@ class LearnStepper:
 
 
 class MatchStepper:
+    PIN_RING = 8  # pinned staging rows for steps fed with CPU tensors
+
     def __init__(self, template, img_transf, model, target_idxs, mei_acts, n_grid, lr=1e-3, total_targets=None, precision=None, use_graph=True):
         lib = _lib.load()
         import ctypes as C
@@ -361,6 +363,7 @@ class MatchStepper:
         self.stats_ready = [torch.cuda.Event(), torch.cuda.Event()]
         self.backup = [[x.detach().clone() for x in grp] for grp in (self.params, self.m, self.v, self.steps)]
         self.graphs = {}
+        self._pin = None
 
     def _affine(self):
         return self.t.affine_args()
@@ -441,7 +444,26 @@ class MatchStepper:
     def step(self, grid_row, slot=0, save=False):
         """One Adam step of every target on the jittered latents `grid_row`.  slot: which of the two statistics slots the step writes;
         save: keep a copy of the state from before the step (first step of an epoch: what `restore_state` goes back to)."""
-        self.grid.copy_(grid_row.reshape(-1), non_blocking=True)
+        if grid_row.is_cuda:
+            self.grid.copy_(grid_row.reshape(-1), non_blocking=True)
+        else:
+            # A CPU row goes through a small ring of pinned rows: the H2D copy is then asynchronous.  (`row.to(device)` from pageable memory
+            # returns only when the GPU has drained, so a loop built on it cannot queue an epoch ahead: 57 us of GPU idle time per epoch of
+            # match([1, 2]), tools/match_hostprof.py.)  A ring slot is reused after PIN_RING steps; its event says the copy out of it is done.
+            if self._pin is None:
+                self._pin = torch.empty((self.PIN_RING, self.N), dtype=torch.float32).pin_memory()
+                self._pin_np = self._pin.numpy()
+                self._pin_ev = [None] * self.PIN_RING
+                self._pin_i = 0
+            k = self._pin_i
+            self._pin_i = (k + 1) % self.PIN_RING
+            if self._pin_ev[k] is not None:
+                self._pin_ev[k].synchronize()
+            else:
+                self._pin_ev[k] = torch.cuda.Event()
+            self._pin_np[k, :] = grid_row.numpy().reshape(-1)
+            self.grid.copy_(self._pin[k], non_blocking=True)
+            self._pin_ev[k].record()
         key = (int(slot), bool(save))
         if not self.use_graph:
             self._train(*key)

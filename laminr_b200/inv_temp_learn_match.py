@@ -285,7 +285,8 @@ class InvarianceManifold:
                 if not template.training:  # (the reference calls .train() every epoch, :350: a walk over the module tree; only the first one changes anything)
                     template.train()
                 rng_before = torch.get_rng_state()
-                epoch_grids = [g.to(device) for g in grid_dataloader.train_dataloader()]  # same generator, same order as the reference (:351)
+                epoch_grids = list(grid_dataloader.train_dataloader())  # same generator, same order as the reference (:351); CPU rows: the stepper
+                #                                                        stages them in pinned memory (an asynchronous copy, see MatchStepper.step)
                 slot = epoch & 1
                 for i, input_grid in enumerate(epoch_grids):
                     stepper.step(input_grid, slot=slot, save=(i == 0))

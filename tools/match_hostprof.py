@@ -29,5 +29,5 @@ with contextlib.redirect_stderr(io.StringIO()):
     torch.cuda.synchronize()
     pr.disable()
 out = io.StringIO()
-pstats.Stats(pr, stream=out).sort_stats("cumulative").print_stats(28)
+pstats.Stats(pr, stream=out).sort_stats(os.environ.get("LMR_PROF_SORT", "cumulative")).print_stats(28)
 print(out.getvalue()[:6000])
