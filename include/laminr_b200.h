@@ -99,7 +99,9 @@ size_t lmr_inr_backward_workspace_bytes(const lmr_inr_desc* desc, int N, int P, 
 size_t lmr_inr_forward_workspace_bytes_keep(const lmr_inr_desc* desc, int N, int P, int D);  /* with LMR_PREC_KEEP_ACTIVATIONS */
 
 /* img[D,N,C,P] = INR(grid[N] latents, coords[P,2] (y,x) pixel coordinates).
- * coord_shift: optional [2] added to coords (centralize_template, inr.py:329-335), learn stage only. */
+ * coord_shift: optional [2] added to coords (centralize_template, inr.py:329-335), learn stage only.
+ * Every pointer is device memory; `grid` alone may also point into pinned host memory (cudaHostAlloc: mapped at the same address under unified
+ * addressing) -- its N floats are read once, by N blocks of the preparation kernel, so a host-fed step needs no H2D copy. */
 int lmr_inr_forward(const lmr_inr_desc* desc, const float* params, const float* B, const float* auxB,
                     const float* grid, int N, const float* coords, int P, const float* coord_shift,
                     const lmr_affine* affine, int D, float* img, void* workspace, size_t workspace_bytes,
@@ -243,6 +245,7 @@ int lmr_simclr_bwd(const float* img, const float* mask, const float* K, const fl
  *     loss = -mean_n(act_n / mei_act) + g_reg[0] * reg        (g_reg = -reg_scale, a device scalar)
  *     g_x  = d loss / d x
  * x, z, g_x: [N, C, HW];  bank: [F, HW] filters of the template neuron;  stats [N,2], rmax [N], argmax [N], Kmat [N,N] nullable.
+ * `loss` (one float, written once) may point into pinned host memory: the host then has the step's loss without a D2H copy.
  * The workspace must be zero-initialised once before its first use (it holds the software grid-barrier state) and must not be shared by
  * launches that may run concurrently.  lmr_learn_objective_workspace_bytes returns 0 when the configuration does not fit the fused
  * kernel (use the unfused entry points then).
