@@ -474,3 +474,26 @@ def test_affine_transform_forward_maps_coordinates_like_the_reference_formula():
             np.testing.assert_allclose(got[d], want, rtol=0, atol=2e-6)
     (ct(x).sum()).backward()  # differentiable in the 7 scalars per target
     assert aff.angles.grad is not None and aff.translation.grad is not None
+
+
+def test_cone_weight_pack_follows_the_header_layout():
+    """ops._pack_cone: w_fwd[ci][ky][co / CB][kx][co % CB] = weight[co][ci][ky][kx] and w_bwd[co][ky][ci / CB][kx][ci % CB] =
+    weight[co][ci][k-1-ky][k-1-kx] with CB = 4 / 2 / 1 by the divisibility of the blocked channel count (include/laminr_b200.h)."""
+    import numpy as np
+    import torch
+    from laminr_b200 import ops
+    rs = np.random.RandomState(0)
+    for co, ci, k in ((8, 3, 5), (6, 4, 3), (5, 2, 7), (32, 1, 9)):
+        W = torch.from_numpy(rs.randn(co, ci, k, k).astype(np.float32))
+        wf = ops._pack_cone(W.permute(1, 2, 0, 3)).numpy()
+        wb = ops._pack_cone(W.flip(2, 3).permute(0, 2, 1, 3)).numpy()
+        cbf = 4 if co % 4 == 0 else 2 if co % 2 == 0 else 1
+        cbb = 4 if ci % 4 == 0 else 2 if ci % 2 == 0 else 1
+        assert wf.shape == (ci, k, co // cbf, k, cbf) and wb.shape == (co, k, ci // cbb, k, cbb)
+        Wn = W.numpy()
+        for o in range(co):
+            for i in range(ci):
+                for ky in range(k):
+                    for kx in range(k):
+                        assert wf[i, ky, o // cbf, kx, o % cbf] == Wn[o, i, ky, kx]
+                        assert wb[o, ky, i // cbb, kx, i % cbb] == Wn[o, i, k - 1 - ky, k - 1 - kx]
