@@ -104,6 +104,26 @@ def test_cone_odd_shapes_vs_oracle(cin, hidden, kernels):
     assert relerr(g1.cpu().numpy(), g_want) < TOL_GRAD
 
 
+def test_cone_window_only_gradient_write():
+    """accumulate = 2: the kernel overwrites the receptive-field window and leaves the rest of the gradient image alone (the MEI ascent keeps it
+    at zero); inside the window the values are those of the whole-image write."""
+    from laminr_b200 import ops
+    d = golden("convcore_a")
+    cone = _cone_from_golden(d)
+    x = torch.as_tensor(d["x"]).cuda()
+    B, C, H, W = x.shape
+    nog = torch.as_tensor(d["neuron_of_image"], dtype=torch.int32).cuda()
+    full = torch.empty_like(x)
+    a0 = ops.raw_convcore_response(cone, x, C * H * W, 1, B, nog, g_img=full, accumulate=0)
+    win = torch.full_like(x, 5.0)
+    a2 = ops.raw_convcore_response(cone, x, C * H * W, 1, B, nog, g_img=win, accumulate=2)
+    assert torch.equal(a0, a2)
+    touched = win != 5.0
+    assert touched.any() and not touched.all()
+    assert torch.equal(win[touched], full[touched])
+    assert torch.all(full[~touched] == 0)
+
+
 def _load_mirror(d):
     """The host mirror (laminr_b200.neuron_models) with the golden fixture's parameters loaded through state_dict names."""
     from laminr_b200.neuron_models import FiringRateEncoder, FullGaussian2d, Stacked2dCore
