@@ -173,6 +173,7 @@ class LearnStepper:
         self.ws_clr = _ws(lib.lmr_simclr_workspace_bytes(N, Cc, P), dev)
         self.use_graph, self.graph, self.eval_graph = use_graph, None, None
         self.host_graph, self.grid_map, self.loss_map, self.host_done = None, None, None, None  # host-fed steps (step() with a CPU row)
+        self._host_pending, self.loss_np = False, None
         self._table_written = False
         self.side = torch.cuda.Stream(device=dev)
         # fused objective (one persistent launch for constraint + response + contrastive, forward and backward) for simulated neurons when it fits
@@ -285,6 +286,8 @@ class LearnStepper:
 
     def sync_loss(self):
         """Loss of the last host-fed step as a Python float (waits for that step)."""
+        if self.loss_np is None:
+            raise RuntimeError("sync_loss(): no host-fed step has run yet (call step() with a CPU tensor; device-fed steps report loss())")
         if self._host_pending:
             self.host_done.synchronize()
             self._host_pending = False
